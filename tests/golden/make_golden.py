@@ -1,0 +1,65 @@
+"""Mint golden vectors from the UNMODIFIED reference binary (oracle/_ref/svbuilder_ref).
+
+The reference ships no tests or fixtures, so its own compiled svbuilder is the
+source of truth.  Run in the build container (needs /root/reference to have been compiled by
+`make -C oracle ref`):
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/<case>.npz holding the input triangle soup, the (levels, step, cross)
+arguments, every file svbuilder wrote, and the per-level "Reduced level" counts parsed from
+its log (geom_octree.cpp:509).  Cases are small so the fixtures stay a few hundred KB.
+"""
+import importlib.util
+import re
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle import oracle as orc  # noqa: E402
+
+spec = importlib.util.spec_from_file_location("_meshgen", ROOT / "svdag-compression_b200" / "meshgen.py")
+mg = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(mg)
+
+CASES = [
+    # name, mesh, mesh kwargs, levels, step, cross
+    ("sphere_L6_s0", "sphere", dict(n_lat=16, n_lon=32), 6, 0, False),
+    ("sphere_L7_s1", "sphere", dict(n_lat=16, n_lon=32), 7, 1, False),
+    ("sphere_L7_s2", "sphere", dict(n_lat=16, n_lon=32), 7, 2, False),
+    ("sphere_L6_s0_c", "sphere", dict(n_lat=16, n_lon=32), 6, 0, True),
+    ("city_L7_s0", "city", dict(lots=4), 7, 0, False),
+    ("city_L7_s2", "city", dict(lots=4), 7, 2, False),
+    ("city_L7_s1_c", "city", dict(lots=4), 7, 1, True),
+    ("terrain_L6_s0", "terrain", dict(n=24), 6, 0, False),
+    ("terrain_L7_s3", "terrain", dict(n=24), 7, 3, False),
+    ("spongeball_L7_s0", "sphere_menger", dict(n_lat=12, n_lon=24, sponge_level=1), 7, 0, False),
+    ("spongeball_L7_s2_c", "sphere_menger", dict(n_lat=12, n_lon=24, sponge_level=1), 7, 2, True),
+]
+
+
+def main():
+    out_dir = Path(__file__).resolve().parent
+    for name, mesh, kw, levels, step, cross in CASES:
+        tris = mg.make_mesh(mesh, **kw)
+        with tempfile.TemporaryDirectory() as td:
+            r = orc.run_reference(td, tris, levels, step, cross=cross)
+        reduced = np.zeros((levels, 2), dtype=np.int64)
+        for m in re.finditer(r"Reduced level (\d+) from (\d+) to (\d+) nodes", r["log"]):
+            reduced[int(m.group(1))] = (int(m.group(2)), int(m.group(3)))
+        stats = {k: int(re.search(rf"{k}:\s+.*\((\d+)\)", r["log"]).group(1))
+                 for k in ("Voxels", "SVO Nodes", "DAG Nodes", "SDAG Nodes")}
+        arrs = {"tris": tris, "levels": levels, "step": step, "cross": cross, "reduced": reduced,
+                "stats": np.array([stats["Voxels"], stats["SVO Nodes"], stats["DAG Nodes"], stats["SDAG Nodes"]], dtype=np.int64)}
+        for ext, data in r["files"].items():
+            arrs["file_" + ext.replace(".", "_")] = np.frombuffer(data, dtype=np.uint8)
+        np.savez_compressed(out_dir / f"{name}.npz", **arrs)
+        print(name, tris.shape[0], "tris", {k: len(v) for k, v in r["files"].items()}, stats)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,42 @@
+"""Pin the CPU restatement (oracle/svdag_oracle.cpp) to the golden vectors minted from the
+unmodified reference binary (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_case
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[p.stem for p in GOLDEN])
+def test_oracle_reproduces_reference_files(orc, path):
+    g = golden_case(path)
+    mine = orc.svbuilder_files(g["tris"], g["levels"], g["step"], cross=g["cross"])
+    key = lambda k: k.replace(".", "_")
+    assert set(key(k) for k in mine) == set(g["files"])
+    for k, data in mine.items():
+        assert data == g["files"][key(k)], f"{g['name']}: {k} differs from the reference's bytes"
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN if not p.stem.endswith("_c")], ids=lambda p: p.stem)
+def test_oracle_level_counts_and_stats(orc, path):
+    g = golden_case(path)
+    o = orc.OracleOctree(g["tris"])
+    o.build(g["levels"], g["step"])
+    before, after = o.level_sizes_before_dag(), o.level_sizes()
+    for lev in range(1, g["levels"]):
+        assert (before[lev], after[lev]) == tuple(g["reduced"][lev]) or g["reduced"][lev].sum() == 0
+    vox, svo, dag, sdag = (int(x) for x in g["stats"])
+    assert o.stat("nTotalVoxels") == vox
+    assert o.stat("nNodesSVO") == svo
+    assert o.stat("nNodesDAG") == dag
+    o.to_sdag()
+    assert o.stat("nNodesSDAG") == sdag
+
+
+def test_tri_box_touching_is_overlap(orc):
+    # closed comparisons: a triangle lying in the face plane of the box overlaps (test_triangle_box.cpp:65,166)
+    tri = np.array([0.5, 0, 0, 0.5, 1, 0, 0.5, 0, 1], np.float32)
+    assert orc.test_tri_box((0.25, 0.25, 0.25), 0.25, tri)
+    assert not orc.test_tri_box((0.2, 0.25, 0.25), 0.25, tri)
+    # degenerate (zero-normal) triangle passes the plane test
+    deg = np.array([0.3, 0.3, 0.3, 0.3, 0.3, 0.3, 0.3, 0.3, 0.3], np.float32)
+    assert orc.test_tri_box((0.25, 0.25, 0.25), 0.25, deg)
