@@ -1,0 +1,146 @@
+/* svb.h -- C ABI of the B200-native svbuilder hot path (libsvb.so).
+ *
+ * The reference (RvanderLaan/SVDAG-Compression, SymVox) has no plugin/FFI layer: the seam
+ * is the C++ class GeomOctree (src/symvox/geom_octree.hpp:107-157) called by
+ * src/svbuilder/main.cpp:147-271 and read by the encoders through getNodeData()
+ * (src/symvox/encoded_octree.hpp:37).  Each entry point below names the reference
+ * interface it stands in for.  Plain pointers and sizes only; every call returns
+ * SVB_OK (0) or a negative SVB_E* code, and svb_last_error() gives the text.
+ * One context per GPU; calls on one context must be serialised by the caller (the
+ * reference's GeomOctree is not re-entrant either: member _clock, geom_octree.hpp:104).
+ *
+ * There is NO CPU fallback: every function that computes runs CUDA kernels for sm_100a
+ * and fails with SVB_ECUDA when no device is usable.
+ */
+#ifndef SVB_H
+#define SVB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVB_OK          0
+#define SVB_EINVAL     -1   /* bad argument / wrong state (reference prints "ERROR! This is not a SVO!", geom_octree.cpp:466-469) */
+#define SVB_ECUDA      -2   /* CUDA runtime error (no device, launch failure, ...) */
+#define SVB_ENOMEM     -3   /* device memory exhausted even after splitting the tile batch */
+#define SVB_ERANGE     -4   /* configuration exceeds an id/order-key bit budget (see DESIGN.md "order key") */
+#define SVB_ECOLLISION -5   /* 64-bit node-key hash collision detected by the exact verify pass */
+
+#define SVB_NULL_NODE 0xFFFFFFFEu   /* Octree::nullNode, src/symvox/octree.cpp:22 */
+
+/* GeomOctree::State, geom_octree.hpp:35-40 */
+enum svb_state { SVB_S_EMPTY = 0, SVB_S_SVO = 1, SVB_S_DAG = 2, SVB_S_SDAG = 3 };
+
+/* GeomOctree::Stats (geom_octree.hpp:42-58) -- counts only, plus device-side timings. */
+typedef struct svb_stats {
+	uint64_t nTotalVoxels;
+	uint64_t nNodesSVO, nNodesDAG, nNodesSDAG;
+	uint64_t nNodesLastLevSVO, nNodesLastLevDAG;
+	uint64_t nCrossLevelMerged;
+	uint64_t nNodes;            /* Octree::_nNodes as the encoders would read it now (getNNodes()) */
+	uint64_t nTiles;            /* sub-octrees built ("Building %zu subtress", geom_octree.cpp:326) */
+	uint64_t nBatches;          /* tile batches the build was split into (device-memory bound) */
+	uint64_t nPairsTotal;       /* (triangle,node) pairs classified == 1/8 of the SAT tests run */
+	double   rootSide;          /* Octree::_rootSide (float value in a double, geom_octree.cpp:184) */
+	float    bboxF[6];          /* Octree::_bbox (float-converted, geom_octree.cpp:177-180) */
+	double   msVoxelize, msDedup, msFinalize, msSdag, msCrossMerge, msTotal; /* CUDA-event times of the last call */
+} svb_stats;
+
+typedef struct svb_ctx svb_ctx;
+
+/* Lifetime.  device = CUDA ordinal this context binds to. */
+svb_ctx*    svb_create(int device);
+void        svb_destroy(svb_ctx* ctx);
+const char* svb_last_error(const svb_ctx* ctx);   /* never NULL */
+const char* svb_version(void);
+
+/* Scene::getTrianglePtr()/getNRawTriangles() (src/symvox/scene.hpp:90-91): the flat float32
+ * triangle soup, 9 floats per triangle, in file order.  The host variant copies H2D (the
+ * pointer is only read during the call); the device variant borrows a device pointer that
+ * must stay valid until the next svb_set_triangles* / svb_destroy. */
+int svb_set_triangles(svb_ctx* ctx, const float* xyz9_host, uint64_t ntris);
+int svb_set_triangles_device(svb_ctx* ctx, const float* xyz9_dev, uint64_t ntris);
+
+/* GeomOctree::buildSVO + toDAG when step == 0 (main.cpp:158-170, geom_octree.cpp:171-280,
+ * 462-548), GeomOctree::buildDAG when step > 0 (main.cpp:173-175, geom_octree.cpp:289-435),
+ * followed by initChildLevels() (main.cpp:203).  bbox is the double-widened scene bbox
+ * (main.cpp:150-155).  Leaves the context in state DAG with node order identical to the
+ * reference's for the same (levels, step). */
+int svb_build(svb_ctx* ctx, uint32_t levels, uint32_t step,
+              const double bbox_min[3], const double bbox_max[3], svb_stats* out);
+
+/* GeomOctree::toSDAG(false,false) (geom_octree.cpp:551-697).  DAG -> SDAG. */
+int svb_to_sdag(svb_ctx* ctx, svb_stats* out);
+
+/* GeomOctree::mergeAcrossAllLevels() (geom_octree_extension.cpp:1192-1544).  DAG -> DAG with
+ * cross-level pointers (childLevels meaningful). */
+int svb_cross_merge(svb_ctx* ctx, svb_stats* out);
+
+/* GeomOctree::getState()/getLevels()/getStats() */
+int svb_state(const svb_ctx* ctx);
+uint32_t svb_levels(const svb_ctx* ctx);
+int svb_get_stats(const svb_ctx* ctx, svb_stats* out);
+
+/* GeomOctree::getNodeData() (geom_octree.hpp:117): one level as SoA, copied D2H into
+ * caller-owned buffers (any pointer may be NULL): mask[n], child8[n*8] (SVB_NULL_NODE = no
+ * child), mirror3[n*3] (childrenMirroredBitmask x,y,z), inv[n] (invariantBitmask),
+ * childLevel8[n*8] (Octree::Node::childLevels). */
+int svb_level_count(const svb_ctx* ctx, uint32_t lev, uint64_t* n);
+int svb_download_level(svb_ctx* ctx, uint32_t lev, uint8_t* mask, uint32_t* child8,
+                       uint8_t* mirror3, uint8_t* inv, uint32_t* childLevel8);
+/* "Reduced level %u from %lu to %lu nodes" (geom_octree.cpp:509): node count of a level
+ * before the final dedup pass (the SVO level size for step 0; the concatenated sub-DAG level
+ * size is NOT reproduced for step > 0, where 0 is returned). */
+int svb_level_count_svo(const svb_ctx* ctx, uint32_t lev, uint64_t* n);
+
+/* GeomOctree(const NodeData&, bbox, rootSide, levels, stats) (geom_octree.cpp:49-60), i.e. what
+ * EncodedSVDAG::decode feeds back in (main.cpp:97-101): replace the context's octree by
+ * host-provided DAG levels (state DAG) so toSDAG / cross-merge can run from a pre-built DAG.
+ * counts[levels]; mask/child8 are the per-level arrays concatenated level by level. */
+int svb_upload_levels(svb_ctx* ctx, uint32_t levels, const uint64_t* counts,
+                      const uint8_t* mask, const uint32_t* child8,
+                      const float bboxF[6], double rootSide, uint64_t nVoxels);
+
+/* EncodedSVDAG / EncodedUSSVDAG / EncodedSSVDAG ::encode(const GeomOctree&) + save()
+ * (encoded_svdag.cpp:76-199, encoded_ussvdag.cpp:60-170, encoded_ssvdag.cpp:84-117,194-466):
+ * copies the levels D2H and writes the exact file image the reference would save.
+ * kind: 0 = .svdag (state DAG), 1 = .ussvdag (state SDAG), 2 = .ssvdag / .esvdag (DAG or SDAG).
+ * Returns the image size in bytes (copied into buf when cap is large enough; call with
+ * buf = NULL to size), or a negative SVB_E* code.  The encoders are linear host passes, as in
+ * the reference. */
+int64_t svb_encode(svb_ctx* ctx, int kind, uint8_t* buf, uint64_t cap);
+
+/* Same encoders, fed from host arrays (no GPU, no context): lets a caller that already holds
+ * GeomOctree::NodeData (e.g. decoded from a .svdag, main.cpp:97-101) write the file formats, and
+ * lets the CPU test-suite pin the encoders without a device.  Arrays are concatenated level by
+ * level; mirror3 / childLevel8 may be NULL (zeros / lev+1). nNodes is Octree::_nNodes as the
+ * reference would hold it at that point; state is a svb_state. */
+int64_t svb_encode_levels(uint32_t levels, const uint64_t* counts, const uint8_t* mask, const uint32_t* child8,
+                          const uint8_t* mirror3, const uint32_t* childLevel8, const float bboxF[6], double rootSide,
+                          uint64_t nNodes, int state, int kind, uint8_t* buf, uint64_t cap);
+
+/* Per-kernel profile of the last svb_build/svb_to_sdag (enabled by svb_set_profiling(ctx,1)):
+ * one record per dedup-family launch group, with the algorithmic byte count SURVEY.md §8(d)
+ * assigns to it.  Used by bench.py for the roofline object. */
+typedef struct svb_prof_rec {
+	char     name[32];     /* kernel family, e.g. "dedup_leaf", "dedup_k64", "dedup_inner", "classify" */
+	uint32_t level;        /* global octree level */
+	uint64_t n_in;         /* units in (nodes or pairs) */
+	uint64_t n_out;        /* unique nodes found so far at that level (dedup) / pairs out */
+	double   ms;           /* CUDA-event duration on the context's stream */
+	double   bytes;        /* algorithmic bytes of this launch group */
+} svb_prof_rec;
+int svb_set_profiling(svb_ctx* ctx, int enabled);
+int svb_profile_count(const svb_ctx* ctx);
+int svb_profile_get(const svb_ctx* ctx, int i, svb_prof_rec* out);
+
+/* Cap on device bytes one tile batch may use for its transient (pair/node) buffers;
+ * 0 = automatic (a fraction of free memory).  Smaller values force more batches (tests). */
+int svb_set_batch_budget(svb_ctx* ctx, uint64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVB_H */

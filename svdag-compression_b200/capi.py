@@ -1,0 +1,207 @@
+"""ctypes binding of include/svb.h and a Python mirror of the reference's GeomOctree call
+surface (src/symvox/geom_octree.hpp:107-157): buildSVO+toDAG / buildDAG -> build(),
+toSDAG -> to_sdag(), mergeAcrossAllLevels -> cross_merge(), getNodeData -> level()."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+STATE_NAMES = {0: "EMPTY", 1: "SVO", 2: "DAG", 3: "SDAG"}
+NULL_NODE = 0xFFFFFFFE
+
+
+class SvbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"svb error {code}: {msg}")
+        self.code = code
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("nTotalVoxels", "nNodesSVO", "nNodesDAG", "nNodesSDAG", "nNodesLastLevSVO",
+                                           "nNodesLastLevDAG", "nCrossLevelMerged", "nNodes", "nTiles", "nBatches", "nPairsTotal")]
+    _fields_ += [("rootSide", C.c_double), ("bboxF", C.c_float * 6)]
+    _fields_ += [(n, C.c_double) for n in ("msVoxelize", "msDedup", "msFinalize", "msSdag", "msCrossMerge", "msTotal")]
+
+    def as_dict(self):
+        d = {}
+        for n, _t in self._fields_:
+            v = getattr(self, n)
+            d[n] = list(v) if n == "bboxF" else v
+        return d
+
+
+class ProfRec(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("level", C.c_uint32), ("n_in", C.c_uint64), ("n_out", C.c_uint64),
+                ("ms", C.c_double), ("bytes", C.c_double)]
+
+
+def lib_path() -> Path:
+    return HERE / "libsvb.so"
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libsvb.so.  Fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        p = lib_path()
+        if not p.exists():
+            raise SvbError(-2, f"{p} missing: build the CUDA extension first (python svdag-compression_b200/build.py)")
+        L = C.CDLL(str(p))
+        vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+        L.svb_create.restype = vp
+        L.svb_create.argtypes = [C.c_int]
+        L.svb_destroy.argtypes = [vp]
+        L.svb_last_error.restype = C.c_char_p
+        L.svb_last_error.argtypes = [vp]
+        L.svb_version.restype = C.c_char_p
+        L.svb_set_triangles.argtypes = [vp, vp, u64]
+        L.svb_set_triangles_device.argtypes = [vp, vp, u64]
+        L.svb_build.argtypes = [vp, u32, u32, vp, vp, C.POINTER(Stats)]
+        L.svb_to_sdag.argtypes = [vp, C.POINTER(Stats)]
+        L.svb_cross_merge.argtypes = [vp, C.POINTER(Stats)]
+        L.svb_state.argtypes = [vp]
+        L.svb_levels.argtypes = [vp]
+        L.svb_levels.restype = u32
+        L.svb_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.svb_level_count.argtypes = [vp, u32, C.POINTER(u64)]
+        L.svb_level_count_svo.argtypes = [vp, u32, C.POINTER(u64)]
+        L.svb_download_level.argtypes = [vp, u32, vp, vp, vp, vp, vp]
+        L.svb_upload_levels.argtypes = [vp, u32, vp, vp, vp, vp, C.c_double, u64]
+        L.svb_set_profiling.argtypes = [vp, C.c_int]
+        L.svb_profile_count.argtypes = [vp]
+        L.svb_profile_get.argtypes = [vp, C.c_int, C.POINTER(ProfRec)]
+        L.svb_set_batch_budget.argtypes = [vp, u64]
+        _lib = L
+    return _lib
+
+
+class GeomOctree:
+    """One GPU-resident octree.  Method names follow the reference class; data stays in HBM until
+    `level()` / `levels_host()` copies it out (what the encoders read through getNodeData())."""
+
+    def __init__(self, tris=None, device: int = 0):
+        self._L = lib()
+        self._h = self._L.svb_create(device)
+        if not self._h:
+            raise SvbError(-2, "svb_create failed: no usable CUDA device (there is no CPU fallback)")
+        self._tris = None
+        if tris is not None:
+            self.set_triangles(tris)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.svb_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SvbError(rc, self._L.svb_last_error(self._h).decode())
+
+    # ---- Scene
+    def set_triangles(self, tris):
+        t = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 9)
+        self._tris = t
+        self._check(self._L.svb_set_triangles(self._h, t.ctypes.data, t.shape[0]))
+
+    def set_triangles_device(self, dev_ptr: int, ntris: int):
+        self._check(self._L.svb_set_triangles_device(self._h, dev_ptr, ntris))
+
+    def scene_bbox(self):
+        v = self._tris.reshape(-1, 3)
+        return v.min(axis=0).astype(np.float64), v.max(axis=0).astype(np.float64)
+
+    # ---- GeomOctree
+    def build(self, levels: int, step: int = 0, bbox=None) -> dict:
+        lo, hi = bbox if bbox is not None else self.scene_bbox()
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        st = Stats()
+        self._check(self._L.svb_build(self._h, levels, step, lo.ctypes.data, hi.ctypes.data, C.byref(st)))
+        return st.as_dict()
+
+    def to_sdag(self) -> dict:
+        st = Stats()
+        self._check(self._L.svb_to_sdag(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def cross_merge(self) -> dict:
+        st = Stats()
+        self._check(self._L.svb_cross_merge(self._h, C.byref(st)))
+        return st.as_dict()
+
+    @property
+    def state(self) -> int:
+        return int(self._L.svb_state(self._h))
+
+    @property
+    def levels(self) -> int:
+        return int(self._L.svb_levels(self._h))
+
+    def stats(self) -> dict:
+        st = Stats()
+        self._check(self._L.svb_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def level_sizes(self):
+        out = []
+        for l in range(self.levels):
+            n = C.c_uint64()
+            self._check(self._L.svb_level_count(self._h, l, C.byref(n)))
+            out.append(int(n.value))
+        return out
+
+    def level_sizes_svo(self):
+        out = []
+        for l in range(self.levels):
+            n = C.c_uint64()
+            self._check(self._L.svb_level_count_svo(self._h, l, C.byref(n)))
+            out.append(int(n.value))
+        return out
+
+    def level(self, lev: int) -> dict:
+        n = C.c_uint64()
+        self._check(self._L.svb_level_count(self._h, lev, C.byref(n)))
+        n = int(n.value)
+        mask = np.zeros(n, np.uint8)
+        child = np.zeros((n, 8), np.uint32)
+        mir = np.zeros((n, 3), np.uint8)
+        inv = np.zeros(n, np.uint8)
+        chl = np.zeros((n, 8), np.uint32)
+        self._check(self._L.svb_download_level(self._h, lev, mask.ctypes.data, child.ctypes.data, mir.ctypes.data,
+                                               inv.ctypes.data, chl.ctypes.data))
+        return {"mask": mask, "child": child, "mirror": mir, "inv": inv, "childLevel": chl}
+
+    def levels_host(self):
+        return [self.level(l) for l in range(self.levels)]
+
+    def upload_levels(self, levels, bboxF, root_side: float, n_voxels: int):
+        counts = np.array([len(l["mask"]) for l in levels], dtype=np.uint64)
+        mask = np.ascontiguousarray(np.concatenate([l["mask"] for l in levels]), dtype=np.uint8)
+        child = np.ascontiguousarray(np.concatenate([l["child"].reshape(-1, 8) for l in levels]), dtype=np.uint32)
+        bb = np.ascontiguousarray(bboxF, dtype=np.float32)
+        self._check(self._L.svb_upload_levels(self._h, len(levels), counts.ctypes.data, mask.ctypes.data, child.ctypes.data,
+                                              bb.ctypes.data, float(root_side), int(n_voxels)))
+
+    # ---- instrumentation
+    def set_profiling(self, on: bool = True):
+        self._L.svb_set_profiling(self._h, 1 if on else 0)
+
+    def profile(self):
+        out = []
+        for i in range(self._L.svb_profile_count(self._h)):
+            r = ProfRec()
+            self._L.svb_profile_get(self._h, i, C.byref(r))
+            out.append({"name": r.name.decode(), "level": int(r.level), "n_in": int(r.n_in), "n_out": int(r.n_out),
+                        "ms": float(r.ms), "bytes": float(r.bytes)})
+        return out
+
+    def set_batch_budget(self, nbytes: int):
+        self._L.svb_set_batch_budget(self._h, int(nbytes))

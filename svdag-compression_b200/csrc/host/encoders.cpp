@@ -1,0 +1,187 @@
+// encoders.cpp -- byte-exact writers of the reference's on-disk formats from SoA level arrays.
+// Linear host passes (< 1 % of the build), kept on the host like the
+// reference does; quirks reproduced on purpose are listed in SURVEY.md Appendix B (5-8).
+#include "octree_data.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <utility>
+
+namespace svbhost {
+
+namespace {
+
+const uint32_t kNull = 0xFFFFFFFEu;
+
+struct ByteSink {
+	std::vector<uint8_t>& v;
+	template <class T> void pod(const T& x) { const uint8_t* p = reinterpret_cast<const uint8_t*>(&x); v.insert(v.end(), p, p + sizeof(T)); }
+	template <class T> void array(const std::vector<T>& a) {
+		pod<uint32_t>((uint32_t)a.size());
+		const uint8_t* p = reinterpret_cast<const uint8_t*>(a.data());
+		v.insert(v.end(), p, p + a.size() * sizeof(T));
+	}
+};
+
+void common_header(ByteSink& s, const OctreeData& o) {
+	for (int k = 0; k < 6; ++k) s.pod<float>(o.bboxF[k]);
+	s.pod<float>((float)o.rootSide);                  // Octree::getRootSide()
+	s.pod<uint32_t>((uint32_t)o.levels.size());
+	s.pod<uint32_t>((uint32_t)o.nNodes);              // low 4 bytes of the size_t
+}
+
+inline int popc(unsigned m) { return __builtin_popcount(m & 0xFF); }
+
+// .svdag / .ussvdag: one u32 stream; node = header word, then the child words for k = 7..0
+bool pointer_stream(const OctreeData& o, bool withMirrorHeader, std::vector<uint8_t>& out) {
+	const size_t L = o.levels.size();
+	// absolute word offset of every node, all levels concatenated
+	std::vector<uint32_t> levelStart(L + 1, 0);        // node index where a level starts in the concatenation
+	size_t totalNodes = 0;
+	for (size_t l = 0; l < L; ++l) { levelStart[l] = (uint32_t)totalNodes; totalNodes += o.levels[l].n; }
+	levelStart[L] = (uint32_t)totalNodes;
+	std::vector<uint32_t> wordOf(totalNodes);
+	uint32_t words = 0;
+	for (size_t l = 0, g = 0; l < L; ++l)
+		for (uint64_t i = 0; i < o.levels[l].n; ++i, ++g) {
+			wordOf[g] = words;
+			words += (l + 1 < L) ? 1u + (uint32_t)popc(o.levels[l].mask[i]) : 1u;
+		}
+	const uint32_t firstLeafPtr = words;               // quirk: computed after the leaf level too
+	std::vector<uint32_t> data;
+	data.reserve(words);
+	for (size_t l = 0; l < L; ++l) {
+		const LevelSoA& lv = o.levels[l];
+		const bool hasCL = lv.childLevel.size() == lv.n * 8;
+		for (uint64_t i = 0; i < lv.n; ++i) {
+			uint32_t head = lv.mask[i];
+			if (withMirrorHeader) head |= ((uint32_t)lv.mirror[i * 3 + 2] << 24) | ((uint32_t)lv.mirror[i * 3 + 1] << 16) | ((uint32_t)lv.mirror[i * 3] << 8);
+			data.push_back(head);
+			if (data.size() >= firstLeafPtr) continue;
+			for (int k = 7; k >= 0; --k) {
+				uint32_t c = lv.child[i * 8 + k];
+				if (c == kNull) continue;
+				// USSVDAG always points into the next level; SVDAG honours childLevels (cross-level merge)
+				size_t tl = withMirrorHeader ? l + 1 : (hasCL ? lv.childLevel[i * 8 + k] : l + 1);
+				data.push_back(wordOf[(size_t)c + levelStart[tl]]);
+			}
+		}
+	}
+	ByteSink s{out};
+	common_header(s, o);
+	s.pod<uint32_t>(firstLeafPtr);
+	s.array(data);
+	return true;
+}
+
+uint8_t mirror_mask(uint8_t m, int s) {   // Node::mirror on a leaf mask: slot i <- slot i^s
+	uint8_t r = 0;
+	for (int i = 0; i < 8; ++i) if ((m >> (i ^ s)) & 1) r |= (uint8_t)(1u << i);
+	return r;
+}
+
+bool ssvdag(const OctreeData& o, std::vector<uint8_t>& out, std::string* err) {
+	const int L = (int)o.levels.size();
+	if (L < 3) { if (err) *err = "SSVDAG needs at least 3 levels"; return false; }
+	std::vector<std::vector<uint16_t>> inner(L - 2);
+	std::vector<uint8_t> leaves;
+	std::vector<uint32_t> addr, nextAddr;   // node index -> address inside its encoded level
+	typedef std::pair<uint32_t, uint32_t> IdxRefs;
+	std::vector<IdxRefs> order;
+	for (int lev = L - 2; lev >= 0; --lev) {
+		const LevelSoA& cur = o.levels[lev];
+		if (cur.n > (1ull << 30)) { if (err) *err = "level too big for 30-bit pointers"; return false; }
+		order.resize(cur.n);
+		for (uint32_t i = 0; i < cur.n; ++i) order[i] = IdxRefs(i, 0);
+		if (lev > 0) {
+			const LevelSoA& up = o.levels[lev - 1];
+			for (uint64_t q = 0; q < up.n * 8; ++q) if (up.child[q] != kNull) order[up.child[q]].second++;
+			// most-referenced first; the reference uses the unstable std::sort, so must we (same libstdc++)
+			std::sort(order.begin(), order.end(), [](IdxRefs a, IdxRefs b) { return a.second > b.second; });
+		}
+		nextAddr.assign(cur.n, 0);
+		if (lev == L - 2) {
+			// two deepest levels fused into 4^3 bit bricks, bits re-ordered x-fastest
+			const LevelSoA& leaf = o.levels[lev + 1];
+			leaves.assign(cur.n * 8, 0);
+			for (uint32_t r = 0; r < order.size(); ++r) {
+				uint32_t i = order[r].first;
+				nextAddr[i] = r;
+				uint8_t sub[8];
+				for (int c = 0; c < 8; ++c) {
+					uint32_t ch = cur.child[(uint64_t)i * 8 + c];
+					if (ch == kNull) { sub[c] = 0; continue; }
+					int s = (((cur.mirror[(uint64_t)i * 3] >> c) & 1) << 2) | (((cur.mirror[(uint64_t)i * 3 + 1] >> c) & 1) << 1) | ((cur.mirror[(uint64_t)i * 3 + 2] >> c) & 1);
+					sub[c] = mirror_mask(leaf.mask[ch], s);
+				}
+				uint8_t* dst = &leaves[(uint64_t)r * 8];
+				for (unsigned bit = 0; bit < 64; ++bit) {
+					unsigned x = bit & 3, y = (bit >> 2) & 3, z = bit >> 4;
+					unsigned byteId = (x >> 1) + ((y >> 1) << 1) + ((z >> 1) << 2);   // encoded_ssvdag.cpp:119-135
+					unsigned bitId = (x & 1) + ((y & 1) << 1) + ((z & 1) << 2);
+					if ((sub[byteId] >> bitId) & 1) dst[bit >> 3] |= (uint8_t)(1u << (bit & 7));
+				}
+			}
+		} else {
+			std::vector<uint16_t>& enc = inner[lev];
+			for (uint32_t r = 0; r < order.size(); ++r) {
+				uint32_t i = order[r].first;
+				nextAddr[i] = (uint32_t)enc.size();
+				size_t headAt = enc.size();
+				enc.push_back(0);
+				uint16_t head = 0;
+				for (int c = 7; c >= 0; --c) {
+					if (!((cur.mask[i] >> c) & 1)) continue;
+					uint32_t a = addr[cur.child[(uint64_t)i * 8 + c]];
+					unsigned mx = (cur.mirror[(uint64_t)i * 3] >> c) & 1, my = (cur.mirror[(uint64_t)i * 3 + 1] >> c) & 1, mz = (cur.mirror[(uint64_t)i * 3 + 2] >> c) & 1;
+					if (a < (1u << 13)) {
+						head |= (uint16_t)(1u << (2 * c));
+						enc.push_back((uint16_t)(a | (mx << 13) | (my << 14) | (mz << 15)));
+					} else if (a < (1u << 30)) {
+						uint32_t p = a;
+						if (p & (1u << 29)) { head |= (uint16_t)(3u << (2 * c)); p &= ~(1u << 29); }
+						else head |= (uint16_t)(2u << (2 * c));
+						p |= (mx << 29) | (my << 30) | (mz << 31);
+						enc.push_back((uint16_t)(p >> 16));
+						enc.push_back((uint16_t)(p & 0xFFFF));
+					}
+				}
+				enc[headAt] = head;
+			}
+		}
+		addr.swap(nextAddr);
+	}
+	std::vector<uint32_t> levelOffsets(L - 2, 0);
+	for (int i = 1; i < L - 2; ++i) levelOffsets[i] = levelOffsets[i - 1] + (uint32_t)inner[i - 1].size();
+	std::vector<uint16_t> all;
+	for (auto& e : inner) all.insert(all.end(), e.begin(), e.end());
+	ByteSink s{out};
+	common_header(s, o);
+	s.array(all);
+	s.array(leaves);
+	s.array(levelOffsets);
+	return true;
+}
+
+}  // namespace
+
+bool encode_file(const OctreeData& o, int kind, std::vector<uint8_t>& out, std::string* err) {
+	out.clear();
+	const int S_DAG = 2, S_SDAG = 3;
+	if (kind == 0) {
+		if (o.state != S_DAG) { if (err) *err = "FAILED! Octree is not in DAG state"; return false; }      // encoded_svdag.cpp:109-112
+		return pointer_stream(o, false, out);
+	}
+	if (kind == 1) {
+		if (o.state != S_SDAG) { if (err) *err = "FAILED! Octree is not in SDAG state"; return false; }    // encoded_ussvdag.cpp:90-93
+		return pointer_stream(o, true, out);
+	}
+	if (kind == 2) {
+		if (o.state != S_DAG && o.state != S_SDAG) { if (err) *err = "FAILED! Octree is not in SDAG state"; return false; }   // encoded_ssvdag.cpp:218-221
+		return ssvdag(o, out, err);
+	}
+	if (err) *err = "unknown encoding";
+	return false;
+}
+
+}  // namespace svbhost

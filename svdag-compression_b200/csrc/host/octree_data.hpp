@@ -1,0 +1,34 @@
+// octree_data.hpp -- host-side SoA snapshot of a GeomOctree (what getNodeData() exposes to the
+// encoders in the reference, src/symvox/geom_octree.hpp:117 + src/symvox/octree.hpp:101-106).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace svbhost {
+
+struct LevelSoA {
+	uint64_t n = 0;
+	std::vector<uint8_t> mask;          // childrenBitmask
+	std::vector<uint32_t> child;        // n*8, 0xFFFFFFFE = nullNode
+	std::vector<uint8_t> mirror;        // n*3, childrenMirroredBitmask[x,y,z]
+	std::vector<uint8_t> inv;           // invariantBitmask
+	std::vector<uint32_t> childLevel;   // n*8, Octree::Node::childLevels
+};
+
+struct OctreeData {
+	std::vector<LevelSoA> levels;
+	float bboxF[6] = {0, 0, 0, 0, 0, 0};   // Octree::_bbox
+	double rootSide = 0;                   // Octree::_rootSide
+	uint64_t nNodes = 0;                   // Octree::_nNodes as the encoder reads it (getNNodes())
+	uint64_t nVoxels = 0;
+	int state = 0;                         // GeomOctree::State
+};
+
+// File images exactly as the reference's encode()+save() pairs write them.
+// kind 0: .svdag   (EncodedSVDAG,   encoded_svdag.cpp:76-199)    needs state DAG
+// kind 1: .ussvdag (EncodedUSSVDAG, encoded_ussvdag.cpp:60-170)  needs state SDAG
+// kind 2: .ssvdag / .esvdag (EncodedSSVDAG, encoded_ssvdag.cpp:84-117,194-466) needs DAG or SDAG
+bool encode_file(const OctreeData& o, int kind, std::vector<uint8_t>& out, std::string* err = nullptr);
+
+}  // namespace svbhost

@@ -1,0 +1,696 @@
+// svb_api.cu -- context, build orchestration and the extern "C" boundary of libsvb.so.
+//
+// Host-side control flow mirrors what src/svbuilder/main.cpp:147-203 asks of GeomOctree:
+//   step == 0 : buildSVO(levels) + toDAG()                    (geom_octree.cpp:171-280, 462-548)
+//   step  > 0 : buildDAG(levels, step)                         (geom_octree.cpp:289-435)
+// but every per-voxel / per-node operation runs in the CUDA kernels of svb_voxelize.cu,
+// svb_dedup.cu, svb_sdag.cu and svb_prims.cu.  The host only sizes buffers, enumerates the
+// sub-octree ("tile") list of step mode from the (tiny) base octree, and sequences launches.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "svb_context.cuh"
+#include "host/octree_data.hpp"
+#include "svb_dedup.cuh"
+#include "svb_sdag.cuh"
+#include "svb_voxelize.cuh"
+
+using namespace svb;
+
+namespace {
+
+int bits_for(uint64_t maxval) {   // bits needed to store values in [0, maxval]
+	int b = 1;
+	while (b < 64 && (maxval >> b)) ++b;
+	return b;
+}
+
+__global__ void k_gather_u32(uint64_t n, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ src, uint32_t* __restrict__ dst) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void k_u8_to_u32(uint64_t n, const uint8_t* __restrict__ src, uint32_t* __restrict__ dst) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) dst[i] = src[i];
+}
+
+struct ProfScope {
+	svb_ctx* c;
+	int idx = -1;
+	ProfScope(svb_ctx* ctx, const char* name, uint32_t level, uint64_t n_in) : c(ctx) {
+		if (!c->profiling) return;
+		svb_ctx::PendingProf p;
+		memset(&p.rec, 0, sizeof(p.rec));
+		snprintf(p.rec.name, sizeof(p.rec.name), "%s", name);
+		p.rec.level = level;
+		p.rec.n_in = n_in;
+		cudaEventCreate(&p.e0);
+		cudaEventCreate(&p.e1);
+		cudaEventRecord(p.e0, c->stream);
+		c->pending.push_back(p);
+		idx = (int)c->pending.size() - 1;
+	}
+	void done(uint64_t n_out, double bytes) {
+		if (idx < 0) return;
+		cudaEventRecord(c->pending[idx].e1, c->stream);
+		c->pending[idx].rec.n_out = n_out;
+		c->pending[idx].rec.bytes = bytes;
+	}
+};
+
+void resolve_profile(svb_ctx* c) {
+	for (auto& p : c->pending) {
+		float ms = 0;
+		cudaEventSynchronize(p.e1);
+		cudaEventElapsedTime(&ms, p.e0, p.e1);
+		p.rec.ms = ms;
+		c->prof.push_back(p.rec);
+		cudaEventDestroy(p.e0);
+		cudaEventDestroy(p.e1);
+	}
+	c->pending.clear();
+}
+
+struct StageTimer {
+	cudaEvent_t e0, e1;
+	cudaStream_t s;
+	StageTimer(cudaStream_t st) : s(st) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
+	double stop() {
+		cudaEventRecord(e1, s);
+		cudaEventSynchronize(e1);
+		float ms = 0;
+		cudaEventElapsedTime(&ms, e0, e1);
+		return ms;
+	}
+	~StageTimer() { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+};
+
+// geom_octree.cpp:177-184: the bbox is narrowed to float, the root side is the max float side
+void float_box(const double lo[3], const double hi[3], float bboxF[6], double& rootSide) {
+	float s = 0.f;
+	for (int k = 0; k < 3; ++k) {
+		bboxF[k] = (float)lo[k];
+		bboxF[3 + k] = (float)hi[k];
+		float side = ((bboxF[3 + k] - bboxF[k]) * 0.5f) * 2.0f;
+		if (k == 0 || side > s) s = side;
+	}
+	rootSide = (double)s;
+}
+
+struct BuildState {
+	uint32_t L = 0, step = 0;
+	int tbits = 1, tileBits = 1;
+	std::vector<LevelTable> tables;
+	std::vector<int> obits;
+	DevBuf<uint64_t> dVoxels;
+	DevBuf<uint32_t> rootKey;
+	int rootChildMode = CH_UID_U32;
+	uint64_t nNodesSVO = 0, nLastLevSVO = 0, pairs = 0, nBatches = 0;
+	std::vector<uint64_t> svoCounts;
+	double msVox = 0, msDedup = 0;
+};
+
+int kind_of(uint32_t g, uint32_t L) { return g == L - 1 ? KIND_LEAF : (g == L - 2 ? KIND_K64 : KIND_INNER); }
+
+// bottom-up reduction of one batch's levels [lo_l, Lt-1] into the global tables
+void dedup_batch(svb_ctx* c, BuildState& B, std::vector<BatchLevel>& lv, int Lt, uint32_t gbase, uint32_t seqBase, int lo_l) {
+	for (int l = Lt - 1; l >= lo_l; --l) {
+		uint32_t g = gbase + l;
+		BatchLevel& X = lv[l];
+		DedupArgs a;
+		a.N = X.n; a.code = X.code.p; a.tstar = X.tstar.p; a.mask = X.mask.p; a.childBase = X.childBase.p;
+		a.l = l; a.tbits = B.tbits; a.seqBase = seqBase;
+		int ob = B.tileBits + B.tbits + 3 * l;
+		if (ob > B.obits[g]) B.obits[g] = ob;
+		LevelTable& T = B.tables[g];
+		if (T.kind == KIND_LEAF) {
+			ProfScope ps(c, "dedup_leaf", g, X.n);
+			dedup_leaf(c->stream, c->pool, T, a, B.dVoxels.p);
+			ps.done(0, 37.0 * (double)X.n);
+		} else {
+			bool leafBelow = (kind_of(g + 1, B.L) == KIND_LEAF);
+			a.childMode = leafBelow ? CH_MASK_U8 : CH_UID_U32;
+			a.childRefs = leafBelow ? (const void*)lv[l + 1].mask.p : (const void*)lv[l + 1].ref.p;
+			X.ref.reset(c->pool, X.n);
+			a.ref = X.ref.p;
+			uint64_t before = T.count;
+			ProfScope ps(c, T.kind == KIND_K64 ? "dedup_k64" : "dedup_inner", g, X.n);
+			dedup_level(c->stream, c->pool, T, a);
+			ps.done(T.count, 37.0 * (double)X.n + 33.0 * (double)(T.count - before));
+			// the level below is no longer needed
+			lv[l + 1] = BatchLevel();
+		}
+	}
+}
+
+struct TileHost {
+	TileGeom g;
+	uint32_t baseNode;   // index (Morton order) of the base leaf node
+	int j;               // child slot inside it
+	int ix, iy, iz;
+};
+
+// Builds tiles [a,b) and reduces them.  Throws BatchTooBig when the batch must be split.
+void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tiles, uint32_t a, uint32_t b,
+                    const TileGridHost& grid, const int* d_gridTile, int Lt, uint32_t gbase, uint64_t budget,
+                    uint32_t* d_tileRootRef, std::vector<BatchLevel>* keepLevels) {
+	cudaStream_t s = c->stream;
+	uint32_t nt = b - a;
+	std::vector<TileGeom> hg(nt);
+	for (uint32_t i = 0; i < nt; ++i) hg[i] = tiles[a + i].g;
+	DevBuf<TileGeom> dTiles(c->pool, nt);
+	SVB_CUDA(cudaMemcpyAsync(dTiles.p, hg.data(), nt * sizeof(TileGeom), cudaMemcpyHostToDevice, s));
+	SVB_CUDA(cudaStreamSynchronize(s));   // hg is a stack-owned staging buffer
+
+	std::vector<BatchLevel> lv;
+	uint64_t pairs = 0;
+	{
+		StageTimer tm(s);
+		ProfScope ps(c, "voxelize", gbase, nt);
+		DevBuf<uint32_t> ptri, pnode;
+		uint64_t P = 0;
+		make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, (int)a, (int)b, ptri, pnode, P);
+		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, P, budget, lv, pairs);
+		ps.done(pairs, 36.0 * (double)c->T + 9.0 * (double)lv[Lt - 1].n);
+		B.msVox += tm.stop();
+	}
+	B.pairs += pairs;
+	B.nBatches++;
+	for (int l = 1; l < Lt; ++l) B.nNodesSVO += lv[l].n;
+	B.nLastLevSVO += lv[Lt - 1].n;
+	if (gbase == 0) { B.svoCounts.assign(Lt, 0); for (int l = 0; l < Lt; ++l) B.svoCounts[l] = lv[l].n; }
+
+	if (keepLevels) {   // base octree of step mode: reduced later, after its tiles
+		*keepLevels = std::move(lv);
+		return;
+	}
+	StageTimer tm(s);
+	if (gbase == 0) {
+		dedup_batch(c, B, lv, Lt, 0, a, 1);
+		if (Lt > 1) {
+			DedupArgs r;
+			r.N = 1; r.code = lv[0].code.p; r.tstar = lv[0].tstar.p; r.mask = lv[0].mask.p; r.childBase = lv[0].childBase.p;
+			bool leafBelow = (kind_of(1, B.L) == KIND_LEAF);
+			r.childMode = leafBelow ? CH_MASK_U8 : CH_UID_U32;
+			r.childRefs = leafBelow ? (const void*)lv[1].mask.p : (const void*)lv[1].ref.p;
+			B.rootChildMode = r.childMode;
+			root_key(s, r, B.rootKey.p);
+		}
+	} else {
+		dedup_batch(c, B, lv, Lt, gbase, a, 0);
+		// remember what the tile roots were reduced to (uid, or the voxel mask for 1-level tiles)
+		if (B.tables[gbase].kind == KIND_LEAF) k_u8_to_u32<<<blocks_for(nt, 256), 256, 0, s>>>(nt, lv[0].mask.p, d_tileRootRef + a);
+		else SVB_CUDA(cudaMemcpyAsync(d_tileRootRef + a, lv[0].ref.p, nt * 4ull, cudaMemcpyDeviceToDevice, s));
+		SVB_KERNEL_CHECK();
+	}
+	B.msDedup += tm.stop();
+}
+
+void run_tiles_split(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tiles, uint32_t a, uint32_t b,
+                     const TileGridHost& grid, const int* d_gridTile, int Lt, uint32_t gbase, uint64_t budget, uint32_t* d_tileRootRef) {
+	try {
+		run_tile_batch(c, B, tiles, a, b, grid, d_gridTile, Lt, gbase, budget, d_tileRootRef, nullptr);
+	} catch (const BatchTooBig&) {
+		if (b - a <= 1) throw Error(SVB_ENOMEM, "a single sub-octree does not fit the batch budget; use a larger step");
+		uint32_t mid = a + (b - a) / 2;
+		run_tiles_split(c, B, tiles, a, mid, grid, d_gridTile, Lt, gbase, budget, d_tileRootRef);
+		run_tiles_split(c, B, tiles, mid, b, grid, d_gridTile, Lt, gbase, budget, d_tileRootRef);
+	}
+}
+
+template <class T>
+std::vector<T> download(cudaStream_t s, const T* d, uint64_t n) {
+	std::vector<T> h(n);
+	if (n) SVB_CUDA(cudaMemcpyAsync(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+	SVB_CUDA(cudaStreamSynchronize(s));
+	return h;
+}
+
+void do_build(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], const double bmax[3]) {
+	cudaStream_t s = c->stream;
+	if (L < 2 || L > 21) throw Error(SVB_EINVAL, "levels must be in [2,21]");
+	if (step > 0 && step + 1 >= L) throw Error(SVB_EINVAL, "step + 1 must be < levels");
+	if (!c->d_tris && c->T) throw Error(SVB_EINVAL, "no triangles set");
+	c->out.clear();
+	c->state = SVB_S_EMPTY;
+	c->prof.clear();
+	memset(&c->stats, 0, sizeof(c->stats));
+	StageTimer total(s);
+
+	BuildState B;
+	B.L = L; B.step = step;
+	B.tbits = bits_for(c->T ? c->T - 1 : 0);
+	B.tables.resize(L);
+	B.obits.assign(L, 1);
+	for (uint32_t g = 1; g < L; ++g) table_init(s, c->pool, B.tables[g], kind_of(g, L));
+	B.dVoxels.reset(c->pool, 1);
+	B.dVoxels.zero();
+	B.rootKey.reset(c->pool, 8);
+	B.rootKey.fill_ff();
+
+	float bboxF[6];
+	double rootSide;
+	float_box(bmin, bmax, bboxF, rootSide);
+	TileGeom rootG;
+	rootG.cx = (bmin[0] + bmax[0]) * 0.5; rootG.cy = (bmin[1] + bmax[1]) * 0.5; rootG.cz = (bmin[2] + bmax[2]) * 0.5;   // bbox.center(), :214
+	rootG.rootSide = rootSide;
+
+	size_t freeB = 0, totalB = 0;
+	SVB_CUDA(cudaMemGetInfo(&freeB, &totalB));
+	uint64_t budget = c->batchBudget ? c->pool.live + c->batchBudget : c->pool.live + (uint64_t)(0.55 * (double)freeB);
+
+	TileGridHost grid1;
+	grid1.G = 1; grid1.cell = rootSide > 0 ? rootSide : 1.0;
+	grid1.ox = rootG.cx - rootSide * 0.5; grid1.oy = rootG.cy - rootSide * 0.5; grid1.oz = rootG.cz - rootSide * 0.5;
+	DevBuf<int> dGrid1(c->pool, 1);
+	dGrid1.zero();
+	std::vector<TileHost> rootTile(1);
+	rootTile[0].g = rootG; rootTile[0].baseNode = 0; rootTile[0].j = 0; rootTile[0].ix = rootTile[0].iy = rootTile[0].iz = 0;
+
+	uint64_t nVoxels = 0, nTiles = 0;
+	if (step == 0) {
+		B.tileBits = 1;
+		if (B.tileBits + B.tbits + 3 * ((int)L - 1) > 63) throw Error(SVB_ERANGE, "order key exceeds 64 bits: use step > 0 for this many levels/triangles");
+		try {
+			run_tile_batch(c, B, rootTile, 0, 1, grid1, dGrid1.p, (int)L, 0, budget, nullptr, nullptr);
+		} catch (const BatchTooBig&) {
+			throw Error(SVB_ENOMEM, "octree does not fit device memory in one piece; use step > 0");
+		}
+		nVoxels = download(s, B.dVoxels.p, 1)[0];
+		nTiles = 1;
+	} else {
+		const uint32_t s1 = step + 1;
+		// ---- base octree (levels 0..step) over all triangles, exact hierarchical tests
+		std::vector<BatchLevel> base;
+		try {
+			run_tile_batch(c, B, rootTile, 0, 1, grid1, dGrid1.p, (int)s1, 0, budget, nullptr, &base);
+		} catch (const BatchTooBig&) {
+			throw Error(SVB_ENOMEM, "base octree does not fit device memory");
+		}
+		B.nBatches = 0;
+		B.nLastLevSVO = 0;            // geom_octree.cpp:318
+		B.svoCounts.clear();
+		// ---- enumerate the sub-octrees exactly like :335-344 (leaf node creation order i, child j = 7..0)
+		const BatchLevel& BL = base[s1 - 1];
+		std::vector<uint64_t> hcode = download(s, BL.code.p, BL.n);
+		std::vector<uint32_t> htstar = download(s, BL.tstar.p, BL.n);
+		std::vector<uint8_t> hmask = download(s, BL.mask.p, BL.n);
+		const int lb = (int)s1 - 1;   // path digits of a base leaf node
+		std::vector<uint32_t> order(BL.n);
+		for (uint32_t i = 0; i < BL.n; ++i) order[i] = i;
+		auto pathp = [&](uint32_t i) { uint64_t p = hcode[i]; return lb > 0 ? ((p & ~7ull) | (7ull - (p & 7ull))) : p; };
+		std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+			if (htstar[x] != htstar[y]) return htstar[x] < htstar[y];
+			return pathp(x) < pathp(y);
+		});
+		std::vector<TileHost> tiles;
+		const int G = 1 << s1;
+		std::vector<int> hgrid((size_t)G * G * G, -1);
+		const double lhs = rootSide / (double)(1u << s1);   // getHalfSideD(stepLevels - 1), :306
+		for (uint32_t oi = 0; oi < BL.n; ++oi) {
+			uint32_t i = order[oi];
+			nVoxels += (uint64_t)__builtin_popcount(hmask[i]);
+			if (!hmask[i]) continue;
+			// centre of base leaf node i: the chain of :222-230
+			double cx = rootG.cx, cy = rootG.cy, cz = rootG.cz, k = rootSide * 0.25;
+			int ix = 0, iy = 0, iz = 0;
+			for (int d = lb - 1; d >= 0; --d) {
+				int dig = (int)((hcode[i] >> (3 * d)) & 7);
+				cx = cx + ((dig & 4) ? k : -k); cy = cy + ((dig & 2) ? k : -k); cz = cz + ((dig & 1) ? k : -k);
+				ix = (ix << 1) | ((dig >> 2) & 1); iy = (iy << 1) | ((dig >> 1) & 1); iz = (iz << 1) | (dig & 1);
+				k *= 0.5;
+			}
+			for (int j = 7; j >= 0; --j) {
+				if (!((hmask[i] >> j) & 1)) continue;
+				TileHost t;
+				double p2x = cx + ((j & 4) ? lhs : -lhs), p2y = cy + ((j & 2) ? lhs : -lhs), p2z = cz + ((j & 1) ? lhs : -lhs);
+				double lo[3] = { std::min(cx, p2x), std::min(cy, p2y), std::min(cz, p2z) };
+				double hi[3] = { std::max(cx, p2x), std::max(cy, p2y), std::max(cz, p2z) };
+				float bf[6];
+				float_box(lo, hi, bf, t.g.rootSide);   // :340-344 -> :177-184
+				t.g.cx = (lo[0] + hi[0]) * 0.5; t.g.cy = (lo[1] + hi[1]) * 0.5; t.g.cz = (lo[2] + hi[2]) * 0.5;
+				t.baseNode = i; t.j = j;
+				t.ix = (ix << 1) | ((j >> 2) & 1); t.iy = (iy << 1) | ((j >> 1) & 1); t.iz = (iz << 1) | (j & 1);
+				hgrid[((size_t)t.ix * G + t.iy) * G + t.iz] = (int)tiles.size();
+				tiles.push_back(t);
+			}
+		}
+		nTiles = tiles.size();
+		B.tileBits = bits_for(nTiles ? nTiles - 1 : 0);
+		const int Lt = (int)(L - s1);
+		if (B.tileBits + B.tbits + 3 * (Lt - 1) > 63 || B.tbits + 3 * lb > 63)
+			throw Error(SVB_ERANGE, "order key exceeds 64 bits: increase step (fewer levels per sub-octree)");
+		TileGridHost grid;
+		grid.G = G; grid.cell = rootSide / (double)G;
+		grid.ox = grid1.ox; grid.oy = grid1.oy; grid.oz = grid1.oz;
+		DevBuf<int> dGrid(c->pool, hgrid.size());
+		SVB_CUDA(cudaMemcpyAsync(dGrid.p, hgrid.data(), hgrid.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+		DevBuf<uint32_t> tileRootRef(c->pool, nTiles ? nTiles : 1);
+		if (nTiles) run_tiles_split(c, B, tiles, 0, (uint32_t)nTiles, grid, dGrid.p, Lt, s1, budget, tileRootRef.p);
+		uint64_t leafVox = download(s, B.dVoxels.p, 1)[0];
+		nVoxels = nVoxels + leafVox - nTiles;   // :352-354 "root doesn't count"
+		// ---- reduce the base octree (levels step..1) on top of the tile roots
+		StageTimer tm(s);
+		{
+			// children of base leaf node n, in ascending child order, are tile roots: gather their refs
+			std::vector<uint32_t> seqOf;   // seqOf[childBase(n) + r]
+			std::vector<uint32_t> cb(BL.n);
+			uint32_t acc = 0;
+			for (uint32_t n = 0; n < BL.n; ++n) { cb[n] = acc; acc += (uint32_t)__builtin_popcount(hmask[n]); }
+			seqOf.assign(acc ? acc : 1, 0);
+			for (uint32_t q = 0; q < tiles.size(); ++q) {
+				const TileHost& t = tiles[q];
+				int r = __builtin_popcount(hmask[t.baseNode] & ((1u << t.j) - 1));
+				seqOf[cb[t.baseNode] + r] = q;
+			}
+			DevBuf<uint32_t> dSeq(c->pool, seqOf.size()), dCb(c->pool, BL.n ? BL.n : 1);
+			SVB_CUDA(cudaMemcpyAsync(dSeq.p, seqOf.data(), seqOf.size() * 4, cudaMemcpyHostToDevice, s));
+			SVB_CUDA(cudaMemcpyAsync(dCb.p, cb.data(), cb.size() * 4, cudaMemcpyHostToDevice, s));
+			DevBuf<uint32_t> topRefs(c->pool, seqOf.size());
+			if (acc) k_gather_u32<<<blocks_for(acc, 256), 256, 0, s>>>(acc, dSeq.p, tileRootRef.p, topRefs.p);
+			SVB_KERNEL_CHECK();
+			base[s1 - 1].childBase = std::move(dCb);
+			SVB_CUDA(cudaStreamSynchronize(s));
+			const uint32_t* below = topRefs.p;
+			int belowMode = (kind_of(s1, L) == KIND_LEAF) ? CH_MASK_U32 : CH_UID_U32;
+			for (int l = (int)s1 - 1; l >= 0; --l) {
+				BatchLevel& X = base[l];
+				DedupArgs a;
+				a.N = X.n; a.code = X.code.p; a.tstar = X.tstar.p; a.mask = X.mask.p; a.childBase = X.childBase.p;
+				a.l = l; a.tbits = B.tbits; a.seqBase = 0;
+				a.childMode = belowMode; a.childRefs = below;
+				if (l == 0) { B.rootChildMode = belowMode; root_key(s, a, B.rootKey.p); break; }
+				int ob = 1 + B.tbits + 3 * l;
+				if (ob > B.obits[l]) B.obits[l] = ob;
+				X.ref.reset(c->pool, X.n);
+				a.ref = X.ref.p;
+				ProfScope ps(c, B.tables[l].kind == KIND_K64 ? "dedup_k64" : "dedup_inner", (uint32_t)l, X.n);
+				dedup_level(s, c->pool, B.tables[l], a);
+				ps.done(B.tables[l].count, 37.0 * (double)X.n);
+				below = X.ref.p;
+				belowMode = CH_UID_U32;
+			}
+			SVB_CUDA(cudaStreamSynchronize(s));
+		}
+		B.msDedup += tm.stop();
+	}
+
+	// ---- rank + materialise
+	double msFin;
+	{
+		StageTimer tm(s);
+		finalize_levels(s, c->pool, B.tables, B.obits, B.rootKey.p, B.rootChildMode, c->out);
+		msFin = tm.stop();
+	}
+	svb_stats& st = c->stats;
+	st.nTotalVoxels = nVoxels;
+	st.nNodesSVO = B.nNodesSVO;
+	st.nNodesLastLevSVO = B.nLastLevSVO;
+	uint64_t nn = 1;
+	for (uint32_t g = 1; g < L; ++g) nn += c->out[g].n;
+	st.nNodesDAG = nn;              // geom_octree.cpp:471,516,544
+	st.nNodes = nn;
+	st.nNodesLastLevDAG = c->out[L - 1].n;
+	st.nTiles = nTiles;
+	st.nBatches = B.nBatches;
+	st.nPairsTotal = B.pairs;
+	st.rootSide = rootSide;
+	memcpy(st.bboxF, bboxF, sizeof(bboxF));
+	st.msVoxelize = B.msVox;
+	st.msDedup = B.msDedup;
+	st.msFinalize = msFin;
+	c->svoCounts = B.svoCounts;
+	c->levels = L;
+	c->state = SVB_S_DAG;
+	st.msTotal = total.stop();
+	resolve_profile(c);
+}
+
+template <class F>
+int guarded(svb_ctx* c, F&& f) {
+	if (!c) return SVB_EINVAL;
+	try {
+		if (cudaSetDevice(c->device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return SVB_ECUDA; }
+		f();
+		c->err.clear();
+		return SVB_OK;
+	} catch (const Error& e) {
+		c->err = e.what();
+		for (auto& p : c->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+		c->pending.clear();
+		return e.code;
+	} catch (const BatchTooBig&) {
+		c->err = "batch too big";
+		return SVB_ENOMEM;
+	} catch (const std::exception& e) {
+		c->err = e.what();
+		return SVB_ECUDA;
+	}
+}
+
+}  // namespace
+
+// ===================================================================================== C ABI
+extern "C" {
+
+const char* svb_version(void) { return "svb 0.1 (sm_100a)"; }
+
+svb_ctx* svb_create(int device) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return nullptr;   // no device: no context, no fallback
+	if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+	svb_ctx* c = new svb_ctx();
+	c->device = device;
+	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+	c->pool.stream = c->stream;
+	cudaMemPool_t mp;
+	if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
+		uint64_t thr = ~0ull;
+		cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+	}
+	return c;
+}
+
+void svb_destroy(svb_ctx* c) {
+	if (!c) return;
+	cudaSetDevice(c->device);
+	c->out.clear();
+	c->trisOwned.release();
+	cudaStreamSynchronize(c->stream);
+	cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+const char* svb_last_error(const svb_ctx* c) { return c ? c->err.c_str() : "null context (no CUDA device?)"; }
+
+int svb_set_triangles(svb_ctx* c, const float* xyz9_host, uint64_t ntris) {
+	return guarded(c, [&] {
+		if (ntris && !xyz9_host) throw Error(SVB_EINVAL, "null triangle pointer");
+		if (ntris >= (1ull << 32)) throw Error(SVB_ERANGE, "more than 2^32 triangles");
+		c->trisOwned.reset(c->pool, ntris * 9 + 4);
+		if (ntris) SVB_CUDA(cudaMemcpyAsync(c->trisOwned.p, xyz9_host, ntris * 36, cudaMemcpyHostToDevice, c->stream));
+		SVB_CUDA(cudaStreamSynchronize(c->stream));
+		c->d_tris = c->trisOwned.p;
+		c->T = ntris;
+	});
+}
+
+int svb_set_triangles_device(svb_ctx* c, const float* xyz9_dev, uint64_t ntris) {
+	return guarded(c, [&] {
+		if (ntris && !xyz9_dev) throw Error(SVB_EINVAL, "null triangle pointer");
+		if (ntris >= (1ull << 32)) throw Error(SVB_ERANGE, "more than 2^32 triangles");
+		c->trisOwned.release();
+		c->d_tris = xyz9_dev;
+		c->T = ntris;
+	});
+}
+
+int svb_build(svb_ctx* c, uint32_t levels, uint32_t step, const double bmin[3], const double bmax[3], svb_stats* out) {
+	int rc = guarded(c, [&] {
+		if (!bmin || !bmax) throw Error(SVB_EINVAL, "null bbox");
+		do_build(c, levels, step, bmin, bmax);
+	});
+	if (rc != SVB_OK && c) { c->out.clear(); c->state = SVB_S_EMPTY; }
+	if (rc == SVB_OK && out) *out = c->stats;
+	return rc;
+}
+
+int svb_to_sdag(svb_ctx* c, svb_stats* out) {
+	int rc = guarded(c, [&] {
+		if (c->state != SVB_S_DAG) throw Error(SVB_EINVAL, "ERROR! This is not a DAG or SDAG!");   // geom_octree.cpp:560-563
+		StageTimer tm(c->stream);
+		uint64_t nn = to_sdag_device(c);
+		c->stats.msSdag = tm.stop();
+		c->stats.nNodesSDAG = nn;   // geom_octree.cpp:578,664,683: root not counted
+		c->stats.nNodes = nn;
+		c->state = SVB_S_SDAG;
+		resolve_profile(c);
+	});
+	if (rc == SVB_OK && out) *out = c->stats;
+	return rc;
+}
+
+int svb_cross_merge(svb_ctx* c, svb_stats* out) {
+	(void)out;
+	return guarded(c, [&] { throw Error(SVB_EINVAL, "cross-level merge is not implemented yet"); });
+}
+
+int svb_state(const svb_ctx* c) { return c ? c->state : SVB_S_EMPTY; }
+uint32_t svb_levels(const svb_ctx* c) { return c ? c->levels : 0; }
+int svb_get_stats(const svb_ctx* c, svb_stats* out) {
+	if (!c || !out) return SVB_EINVAL;
+	*out = c->stats;
+	return SVB_OK;
+}
+
+int svb_level_count(const svb_ctx* c, uint32_t lev, uint64_t* n) {
+	if (!c || !n || lev >= c->out.size()) return SVB_EINVAL;
+	*n = c->out[lev].n;
+	return SVB_OK;
+}
+int svb_level_count_svo(const svb_ctx* c, uint32_t lev, uint64_t* n) {
+	if (!c || !n) return SVB_EINVAL;
+	*n = lev < c->svoCounts.size() ? c->svoCounts[lev] : 0;
+	return SVB_OK;
+}
+
+int svb_download_level(svb_ctx* c, uint32_t lev, uint8_t* mask, uint32_t* child8, uint8_t* mirror3, uint8_t* inv, uint32_t* childLevel8) {
+	return guarded(c, [&] {
+		if (lev >= c->out.size()) throw Error(SVB_EINVAL, "level out of range");
+		OutLevel& o = c->out[lev];
+		cudaStream_t s = c->stream;
+		if (o.n) {
+			if (mask) SVB_CUDA(cudaMemcpyAsync(mask, o.mask.p, o.n, cudaMemcpyDeviceToHost, s));
+			if (child8) SVB_CUDA(cudaMemcpyAsync(child8, o.child.p, o.n * 32, cudaMemcpyDeviceToHost, s));
+			if (mirror3) SVB_CUDA(cudaMemcpyAsync(mirror3, o.mirror.p, o.n * 3, cudaMemcpyDeviceToHost, s));
+			if (inv) SVB_CUDA(cudaMemcpyAsync(inv, o.inv.p, o.n, cudaMemcpyDeviceToHost, s));
+			if (childLevel8) {
+				if (o.hasChildLevel) SVB_CUDA(cudaMemcpyAsync(childLevel8, o.childLevel.p, o.n * 32, cudaMemcpyDeviceToHost, s));
+				else { SVB_CUDA(cudaStreamSynchronize(s)); for (uint64_t i = 0; i < o.n * 8; ++i) childLevel8[i] = lev + 1; }   // initChildLevels(), ext.cpp:21-30
+			}
+		}
+		SVB_CUDA(cudaStreamSynchronize(s));
+	});
+}
+
+int64_t svb_encode(svb_ctx* c, int kind, uint8_t* buf, uint64_t cap) {
+	int64_t size = -1;
+	int rc = guarded(c, [&] {
+		if (c->state != SVB_S_DAG && c->state != SVB_S_SDAG) throw Error(SVB_EINVAL, "nothing to encode");
+		svbhost::OctreeData o;
+		o.levels.resize(c->levels);
+		cudaStream_t s = c->stream;
+		for (uint32_t l = 0; l < c->levels; ++l) {
+			OutLevel& d = c->out[l];
+			svbhost::LevelSoA& h = o.levels[l];
+			h.n = d.n;
+			h.mask.resize(d.n); h.child.resize(d.n * 8); h.mirror.resize(d.n * 3);
+			if (d.n) {
+				SVB_CUDA(cudaMemcpyAsync(h.mask.data(), d.mask.p, d.n, cudaMemcpyDeviceToHost, s));
+				SVB_CUDA(cudaMemcpyAsync(h.child.data(), d.child.p, d.n * 32, cudaMemcpyDeviceToHost, s));
+				SVB_CUDA(cudaMemcpyAsync(h.mirror.data(), d.mirror.p, d.n * 3, cudaMemcpyDeviceToHost, s));
+				if (d.hasChildLevel) {
+					h.childLevel.resize(d.n * 8);
+					SVB_CUDA(cudaMemcpyAsync(h.childLevel.data(), d.childLevel.p, d.n * 32, cudaMemcpyDeviceToHost, s));
+				}
+			}
+		}
+		SVB_CUDA(cudaStreamSynchronize(s));
+		memcpy(o.bboxF, c->stats.bboxF, 24);
+		o.rootSide = c->stats.rootSide;
+		o.nNodes = c->stats.nNodes;
+		o.nVoxels = c->stats.nTotalVoxels;
+		o.state = c->state;
+		std::vector<uint8_t> img;
+		std::string err;
+		if (!svbhost::encode_file(o, kind, img, &err)) throw Error(SVB_EINVAL, err);
+		size = (int64_t)img.size();
+		if (buf && cap >= img.size()) memcpy(buf, img.data(), img.size());
+	});
+	return rc == SVB_OK ? size : (int64_t)rc;
+}
+
+int64_t svb_encode_levels(uint32_t levels, const uint64_t* counts, const uint8_t* mask, const uint32_t* child8,
+                          const uint8_t* mirror3, const uint32_t* childLevel8, const float bboxF[6], double rootSide,
+                          uint64_t nNodes, int state, int kind, uint8_t* buf, uint64_t cap) {
+	if (!counts || !mask || !child8 || !bboxF || levels == 0) return SVB_EINVAL;
+	try {
+		svbhost::OctreeData o;
+		o.levels.resize(levels);
+		uint64_t off = 0;
+		for (uint32_t l = 0; l < levels; ++l) {
+			svbhost::LevelSoA& h = o.levels[l];
+			h.n = counts[l];
+			h.mask.assign(mask + off, mask + off + h.n);
+			h.child.assign(child8 + off * 8, child8 + (off + h.n) * 8);
+			if (mirror3) h.mirror.assign(mirror3 + off * 3, mirror3 + (off + h.n) * 3);
+			else h.mirror.assign(h.n * 3, 0);
+			if (childLevel8) h.childLevel.assign(childLevel8 + off * 8, childLevel8 + (off + h.n) * 8);
+			off += h.n;
+		}
+		memcpy(o.bboxF, bboxF, 24);
+		o.rootSide = rootSide;
+		o.nNodes = nNodes;
+		o.state = state;
+		std::vector<uint8_t> img;
+		if (!svbhost::encode_file(o, kind, img, nullptr)) return SVB_EINVAL;
+		if (buf && cap >= img.size()) memcpy(buf, img.data(), img.size());
+		return (int64_t)img.size();
+	} catch (...) {
+		return SVB_EINVAL;
+	}
+}
+
+int svb_upload_levels(svb_ctx* c, uint32_t levels, const uint64_t* counts, const uint8_t* mask, const uint32_t* child8,
+                      const float bboxF[6], double rootSide, uint64_t nVoxels) {
+	return guarded(c, [&] {
+		if (!counts || !mask || !child8 || levels < 2) throw Error(SVB_EINVAL, "bad arguments");
+		cudaStream_t s = c->stream;
+		c->out.clear();
+		c->out.resize(levels);
+		uint64_t off = 0, nn = 0;
+		for (uint32_t l = 0; l < levels; ++l) {
+			OutLevel& o = c->out[l];
+			o.n = counts[l];
+			o.mask.reset(c->pool, o.n); o.child.reset(c->pool, o.n * 8); o.mirror.reset(c->pool, o.n * 3); o.inv.reset(c->pool, o.n);
+			o.mirror.zero(); o.inv.zero();
+			if (o.n) {
+				SVB_CUDA(cudaMemcpyAsync(o.mask.p, mask + off, o.n, cudaMemcpyHostToDevice, s));
+				SVB_CUDA(cudaMemcpyAsync(o.child.p, child8 + off * 8, o.n * 32, cudaMemcpyHostToDevice, s));
+			}
+			off += o.n;
+			nn += o.n;
+		}
+		SVB_CUDA(cudaStreamSynchronize(s));
+		memset(&c->stats, 0, sizeof(c->stats));
+		c->stats.nTotalVoxels = nVoxels;
+		c->stats.nNodesDAG = nn;
+		c->stats.nNodes = nn;
+		c->stats.nNodesLastLevDAG = counts[levels - 1];
+		c->stats.rootSide = rootSide;
+		if (bboxF) memcpy(c->stats.bboxF, bboxF, 24);
+		c->levels = levels;
+		c->svoCounts.clear();
+		c->state = SVB_S_DAG;
+	});
+}
+
+int svb_set_profiling(svb_ctx* c, int enabled) {
+	if (!c) return SVB_EINVAL;
+	c->profiling = enabled != 0;
+	return SVB_OK;
+}
+int svb_profile_count(const svb_ctx* c) { return c ? (int)c->prof.size() : 0; }
+int svb_profile_get(const svb_ctx* c, int i, svb_prof_rec* out) {
+	if (!c || !out || i < 0 || i >= (int)c->prof.size()) return SVB_EINVAL;
+	*out = c->prof[i];
+	return SVB_OK;
+}
+int svb_set_batch_budget(svb_ctx* c, uint64_t bytes) {
+	if (!c) return SVB_EINVAL;
+	c->batchBudget = bytes;
+	return SVB_OK;
+}
+
+}  // extern "C"

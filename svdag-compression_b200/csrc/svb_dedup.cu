@@ -1,0 +1,478 @@
+// svb_dedup.cu -- per-level bottom-up DAG reduction (unique-node dedup + child remap).
+//
+// Replaces the std::map<Node,id> loop of GeomOctree::toDAG (src/symvox/geom_octree.cpp:462-548)
+// and the "sub-DAGs, join, last DAG pass" of buildDAG (:331-425).  Two nodes are equal iff their
+// keys (child mask + child ids, Node::operator< src/symvox/octree_node.cpp:56-86) are equal; the
+// reference keeps unique nodes in FIRST-OCCURRENCE order, which here is the order of the smallest
+// 64-bit order key  (tile_seq | first-touch triangle | path with the last digit reversed)  among
+// the equal nodes (pinned on CPU by oracle/parallel_model.py).
+//
+// One streaming pass per level over the SoA node arrays; uniqueness is resolved in an
+// open-addressing table that is small whenever the level compresses well (the table then lives in
+// the 126 MB L2 and the pass runs at HBM speed):
+//   KIND_LEAF  (level L-1): key = 8-bit voxel mask -> 256-entry direct table, staged in shared memory.
+//   KIND_K64   (level L-2): key = the 8 child masks = one exact 64-bit word (the 4^3 voxel block).
+//   KIND_INNER (above)    : key = 8 child uids, tagged by a 64-bit hash, verified exactly afterwards.
+#include "svb_dedup.cuh"
+
+namespace svb {
+
+namespace {
+
+constexpr int DD_THREADS = 256;
+
+__device__ __forceinline__ uint64_t order_key(uint64_t code, uint32_t tstar, int l, int tbits, uint32_t seqBase) {
+	uint64_t pmask = (l >= 21) ? ~0ull : ((1ull << (3 * l)) - 1);
+	uint64_t path = code & pmask;
+	uint64_t tile = (l >= 21) ? 0 : (code >> (3 * l));
+	if (l > 0) path = (path & ~7ull) | (7ull - (path & 7ull));   // children are created 7 -> 0 (geom_octree.cpp:234)
+	return ((uint64_t)(seqBase + tile) << (tbits + 3 * l)) | ((uint64_t)tstar << (3 * l)) | path;
+}
+
+template <int CHMODE>
+__device__ __forceinline__ uint32_t read_child(const void* refs, uint64_t i) {
+	if (CHMODE == CH_MASK_U8) return ((const uint8_t*)refs)[i];
+	return ((const uint32_t*)refs)[i];
+}
+
+// Builds the key of node n.  MASK modes: key64 = child masks (byte c = mask of child c); UID mode: key8.
+// Returns false when the node has no non-empty child (cleanEmptyNodes cascade, geom_octree.cpp:437-456).
+template <int CHMODE>
+__device__ __forceinline__ bool build_key(const DedupArgs& a, uint64_t n, uint32_t key8[8], uint64_t& key64) {
+	unsigned m = a.mask[n];
+	uint64_t base = a.childBase[n];
+	bool any = false;
+	key64 = 0;
+	int r = 0;
+#pragma unroll
+	for (int c = 0; c < 8; ++c) {
+		uint32_t v = NULLREF;
+		if ((m >> c) & 1) {
+			uint32_t x = read_child<CHMODE>(a.childRefs, base + r);
+			++r;
+			if (CHMODE == CH_UID_U32) { v = x; any |= (x != NULLREF); }
+			else if (x != 0 && x != NULLREF) { v = x; key64 |= (uint64_t)(x & 0xFF) << (8 * c); any = true; }
+		}
+		key8[c] = v;
+	}
+	return any;
+}
+
+__device__ __forceinline__ uint64_t tag_of_key8(const uint32_t k[8]) {
+	uint64_t h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+	for (int c = 0; c < 8; c += 2) h = mix64(h ^ (((uint64_t)k[c + 1] << 32) | k[c])) + 0x9E3779B97F4A7C15ull * (c + 1);
+	return h ? h : 1ull;
+}
+
+// ------------------------------------------------------------------ KIND_LEAF
+__global__ void __launch_bounds__(DD_THREADS) k_leaf_min(DedupArgs a, unsigned long long* __restrict__ gmin, unsigned long long* __restrict__ voxels) {
+	__shared__ unsigned long long smin[256];
+	smin[threadIdx.x] = MAX_ORDER;
+	__syncthreads();
+	unsigned vox = 0;
+	uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; n < a.N; n += stride) {
+		unsigned m = a.mask[n];
+		if (!m) continue;
+		vox += __popc(m);
+		unsigned long long O = order_key(a.code[n], a.tstar[n], a.l, a.tbits, a.seqBase);
+		if (smin[m] > O) atomicMin(&smin[m], O);
+	}
+	__syncthreads();
+	unsigned long long v = smin[threadIdx.x];
+	if (v != MAX_ORDER && gmin[threadIdx.x] > v) atomicMin(&gmin[threadIdx.x], v);
+#pragma unroll
+	for (int d = 16; d; d >>= 1) vox += __shfl_xor_sync(0xFFFFFFFFu, vox, d);
+	if ((threadIdx.x & 31) == 0 && vox) atomicAdd(voxels, (unsigned long long)vox);
+}
+
+// ------------------------------------------------------------------ KIND_K64 / KIND_INNER
+struct TableDev {
+	unsigned long long* tag;
+	unsigned long long* minO;
+	uint32_t* uid;
+	uint64_t capMask;
+	uint64_t countBefore, maxLoad;
+	uint32_t* flags;   // [0] overflow, [1] collision, [2] new entries
+};
+
+__device__ __forceinline__ bool table_find_or_claim(const TableDev& t, uint64_t tag, uint64_t& slot) {
+	uint64_t idx = mix64(tag) & t.capMask;
+	for (int probe = 0; probe < 8192; ++probe) {
+		unsigned long long cur = t.tag[idx];
+		if (cur == tag) { slot = idx; return true; }
+		if (cur == EMPTY_TAG) {
+			unsigned long long old = atomicCAS(&t.tag[idx], (unsigned long long)EMPTY_TAG, (unsigned long long)tag);
+			if (old == EMPTY_TAG) {
+				uint32_t nc = atomicAdd(&t.flags[2], 1u) + 1;
+				if (t.countBefore + nc > t.maxLoad) t.flags[0] = 1;
+				slot = idx;
+				return true;
+			}
+			if (old == tag) { slot = idx; return true; }
+		}
+		idx = (idx + 1) & t.capMask;
+	}
+	t.flags[0] = 1;
+	return false;
+}
+
+template <int CHMODE>
+__global__ void __launch_bounds__(DD_THREADS) k_insert(DedupArgs a, TableDev t) {
+	uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (n >= a.N) return;
+	uint32_t k8[8];
+	uint64_t k64;
+	if (!build_key<CHMODE>(a, n, k8, k64)) { a.ref[n] = NULLREF; return; }
+	uint64_t tag = (CHMODE == CH_UID_U32) ? tag_of_key8(k8) : k64;
+	uint64_t slot;
+	if (!table_find_or_claim(t, tag, slot)) { a.ref[n] = NULLREF; return; }
+	unsigned long long O = order_key(a.code[n], a.tstar[n], a.l, a.tbits, a.seqBase);
+	if (t.minO[slot] > O) atomicMin(&t.minO[slot], O);
+	a.ref[n] = (uint32_t)slot;
+}
+
+// K64: new slots get their dense uid from a pass over the table (the key is the tag itself)
+__global__ void __launch_bounds__(DD_THREADS) k_assign_k64(uint64_t cap, const unsigned long long* __restrict__ tag, const unsigned long long* __restrict__ minO,
+                                                            uint32_t* __restrict__ uid, uint32_t* __restrict__ dCount,
+                                                            uint64_t* __restrict__ dMinO, uint64_t* __restrict__ dKey64) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= cap) return;
+	unsigned long long tg = tag[i];
+	if (tg == EMPTY_TAG || uid[i] != UNSET) return;
+	uint32_t u = atomicAdd(dCount, 1u);
+	uid[i] = u;
+	dMinO[u] = minO[i];
+	dKey64[u] = tg;
+}
+
+// INNER: the node that holds the minimum order key of a new slot publishes the full key
+template <int CHMODE>
+__global__ void __launch_bounds__(DD_THREADS) k_winner(DedupArgs a, TableDev t, uint32_t* __restrict__ dCount,
+                                                        uint64_t* __restrict__ dMinO, uint32_t* __restrict__ dKey8) {
+	uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (n >= a.N) return;
+	uint32_t slot = a.ref[n];
+	if (slot == NULLREF) return;
+	unsigned long long O = order_key(a.code[n], a.tstar[n], a.l, a.tbits, a.seqBase);
+	if (t.minO[slot] != O) return;
+	uint32_t k8[8];
+	uint64_t k64;
+	build_key<CHMODE>(a, n, k8, k64);
+	uint32_t u = atomicAdd(dCount, 1u);
+	t.uid[slot] = u;
+	dMinO[u] = O;
+#pragma unroll
+	for (int c = 0; c < 8; ++c) dKey8[(uint64_t)u * 8 + c] = k8[c];
+}
+
+// slot -> uid for every node (+ exact key check for hashed keys)
+template <int CHMODE, bool VERIFY>
+__global__ void __launch_bounds__(DD_THREADS) k_convert(DedupArgs a, TableDev t, const uint32_t* __restrict__ dKey8) {
+	uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (n >= a.N) return;
+	uint32_t slot = a.ref[n];
+	if (slot == NULLREF) return;
+	uint32_t u = t.uid[slot];
+	if (VERIFY) {
+		uint32_t k8[8];
+		uint64_t k64;
+		build_key<CHMODE>(a, n, k8, k64);
+		bool same = true;
+#pragma unroll
+		for (int c = 0; c < 8; ++c) same &= (dKey8[(uint64_t)u * 8 + c] == k8[c]);
+		if (!same) t.flags[1] = 1;
+	}
+	a.ref[n] = u;
+}
+
+// re-insert all dense entries into a fresh (larger) slot array
+template <bool K64>
+__global__ void __launch_bounds__(DD_THREADS) k_rebuild(uint64_t count, const uint64_t* __restrict__ dMinO, const uint64_t* __restrict__ dKey64,
+                                                         const uint32_t* __restrict__ dKey8, TableDev t) {
+	uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= count) return;
+	uint64_t tag;
+	if (K64) tag = dKey64[u];
+	else {
+		uint32_t k8[8];
+#pragma unroll
+		for (int c = 0; c < 8; ++c) k8[c] = dKey8[u * 8 + c];
+		tag = tag_of_key8(k8);
+	}
+	uint64_t idx = mix64(tag) & t.capMask;
+	for (;;) {
+		unsigned long long old = atomicCAS(&t.tag[idx], (unsigned long long)EMPTY_TAG, (unsigned long long)tag);
+		if (old == EMPTY_TAG) break;
+		idx = (idx + 1) & t.capMask;
+	}
+	t.minO[idx] = dMinO[u];
+	t.uid[idx] = (uint32_t)u;
+}
+
+template <int CHMODE>
+__global__ void k_root(DedupArgs a, uint32_t* rootKey8) {
+	if (threadIdx.x || blockIdx.x) return;
+	uint32_t k8[8];
+	uint64_t k64;
+	build_key<CHMODE>(a, 0, k8, k64);
+	for (int c = 0; c < 8; ++c) rootKey8[c] = k8[c];
+}
+
+// ------------------------------------------------------------------ finalize kernels
+__global__ void k_iota(uint64_t n, uint32_t* v) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) v[i] = (uint32_t)i;
+}
+__global__ void k_rank_scatter(uint64_t n, const uint32_t* __restrict__ sortedUid, uint32_t* __restrict__ rank) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) rank[sortedUid[i]] = (uint32_t)i;
+}
+__global__ void k_emit_leaf(uint64_t U, const uint32_t* __restrict__ sortedMask, uint8_t* __restrict__ omask, uint32_t* __restrict__ ochild) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= U) return;
+	omask[i] = (uint8_t)sortedMask[i];
+	for (int c = 0; c < 8; ++c) ochild[i * 8 + c] = NULLNODE;
+}
+__global__ void k_emit_k64(uint64_t U, const uint32_t* __restrict__ sortedUid, const uint64_t* __restrict__ dKey64,
+                           const uint32_t* __restrict__ rankLeaf, uint8_t* __restrict__ omask, uint32_t* __restrict__ ochild) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= U) return;
+	uint64_t k = dKey64[sortedUid[i]];
+	unsigned m = 0;
+	for (int c = 0; c < 8; ++c) {
+		unsigned b = (unsigned)((k >> (8 * c)) & 0xFF);
+		ochild[i * 8 + c] = b ? rankLeaf[b] : NULLNODE;
+		if (b) m |= 1u << c;
+	}
+	omask[i] = (uint8_t)m;
+}
+__global__ void k_emit_inner(uint64_t U, const uint32_t* __restrict__ sortedUid, const uint32_t* __restrict__ dKey8,
+                             const uint32_t* __restrict__ rankChild, uint8_t* __restrict__ omask, uint32_t* __restrict__ ochild) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= U) return;
+	uint64_t u = sortedUid[i];
+	unsigned m = 0;
+	for (int c = 0; c < 8; ++c) {
+		uint32_t r = dKey8[u * 8 + c];
+		ochild[i * 8 + c] = (r == NULLREF) ? NULLNODE : rankChild[r];
+		if (r != NULLREF) m |= 1u << c;
+	}
+	omask[i] = (uint8_t)m;
+}
+__global__ void k_emit_root(const uint32_t* rootKey8, const uint32_t* rankChild, uint8_t* omask, uint32_t* ochild) {
+	if (threadIdx.x || blockIdx.x) return;
+	unsigned m = 0;
+	for (int c = 0; c < 8; ++c) {
+		uint32_t r = rootKey8[c];
+		ochild[c] = (r == NULLREF) ? NULLNODE : rankChild[r];
+		if (r != NULLREF) m |= 1u << c;
+	}
+	omask[0] = (uint8_t)m;
+}
+
+uint64_t next_pow2(uint64_t x) {
+	uint64_t p = 1;
+	while (p < x) p <<= 1;
+	return p;
+}
+
+void alloc_slots(cudaStream_t s, Pool& pool, LevelTable& T, uint64_t cap) {
+	T.cap = cap;
+	T.tag.reset(pool, cap);
+	T.minO.reset(pool, cap);
+	T.uid.reset(pool, cap);
+	T.tag.zero();
+	T.minO.fill_ff();
+	T.uid.fill_ff();
+}
+
+TableDev dev_view(LevelTable& T, uint32_t* flags) {
+	TableDev t;
+	t.tag = (unsigned long long*)T.tag.p;
+	t.minO = (unsigned long long*)T.minO.p;
+	t.uid = T.uid.p;
+	t.capMask = T.cap - 1;
+	t.countBefore = T.count;
+	t.maxLoad = T.cap - T.cap / 4;   // 75 %
+	t.flags = flags;
+	return t;
+}
+
+void grow_slots(cudaStream_t s, Pool& pool, LevelTable& T, uint64_t newCap) {
+	alloc_slots(s, pool, T, newCap);
+	if (T.count == 0) return;
+	TableDev t = dev_view(T, nullptr);
+	unsigned nb = blocks_for(T.count, DD_THREADS);
+	if (T.kind == KIND_K64) k_rebuild<true><<<nb, DD_THREADS, 0, s>>>(T.count, T.dMinO.p, T.dKey64.p, nullptr, t);
+	else k_rebuild<false><<<nb, DD_THREADS, 0, s>>>(T.count, T.dMinO.p, nullptr, T.dKey8.p, t);
+	SVB_KERNEL_CHECK();
+}
+
+template <class Tp>
+void grow_copy(cudaStream_t s, Pool& pool, DevBuf<Tp>& b, uint64_t oldElems, uint64_t newElems) {
+	DevBuf<Tp> nb(pool, newElems);
+	if (oldElems) SVB_CUDA(cudaMemcpyAsync(nb.p, b.p, oldElems * sizeof(Tp), cudaMemcpyDeviceToDevice, s));
+	b = std::move(nb);
+}
+
+void ensure_dense(cudaStream_t s, Pool& pool, LevelTable& T, uint64_t need) {
+	if (need <= T.denseCap) return;
+	uint64_t nc = next_pow2(need < 1024 ? 1024 : need);
+	grow_copy(s, pool, T.dMinO, T.count, nc);
+	if (T.kind == KIND_K64) grow_copy(s, pool, T.dKey64, T.count, nc);
+	else grow_copy(s, pool, T.dKey8, T.count * 8, nc * 8);
+	T.denseCap = nc;
+}
+
+}  // namespace
+
+void table_init(cudaStream_t s, Pool& pool, LevelTable& T, int kind) {
+	T.kind = kind;
+	T.count = 0;
+	T.denseCap = 0;
+	T.unique = 0;
+	if (kind == KIND_LEAF) {
+		T.cap = 256;
+		T.minO.reset(pool, 256);
+		T.minO.fill_ff();
+		return;
+	}
+	T.dCount.reset(pool, 1);
+	T.dCount.zero();
+	alloc_slots(s, pool, T, 1ull << 16);
+}
+
+void dedup_leaf(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, uint64_t* d_voxels) {
+	(void)pool;
+	if (a.N == 0) return;
+	unsigned nb = blocks_for(a.N, DD_THREADS * 16);
+	if (nb > 148 * 8) nb = 148 * 8;
+	k_leaf_min<<<nb, DD_THREADS, 0, s>>>(a, (unsigned long long*)T.minO.p, (unsigned long long*)d_voxels);
+	SVB_KERNEL_CHECK();
+}
+
+template <int CHMODE>
+static void dedup_level_t(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a) {
+	if (a.N == 0) return;
+	const bool k64 = (CHMODE != CH_UID_U32);
+	if ((T.kind == KIND_K64) != k64) throw Error(SVB_EINVAL, "dedup_level: table kind does not match child mode");
+	DevBuf<uint32_t> flags(pool, 4);
+	unsigned nb = blocks_for(a.N, DD_THREADS);
+	uint32_t h[4];
+	// size the slot array for this level: at least 2x the entries it may end up holding if ~1/8 of the
+	// nodes are new; an overflow simply grows x4 and redoes the pass (failed attempts leave no trace:
+	// their slots have no uid and are dropped by the rebuild).
+	uint64_t want = next_pow2(2 * (T.count + a.N / 8 + 1024));
+	if (want > T.cap) grow_slots(s, pool, T, want);
+	for (;;) {
+		flags.zero();
+		TableDev t = dev_view(T, flags.p);
+		k_insert<CHMODE><<<nb, DD_THREADS, 0, s>>>(a, t);
+		SVB_KERNEL_CHECK();
+		SVB_CUDA(cudaMemcpyAsync(h, flags.p, 16, cudaMemcpyDeviceToHost, s));
+		SVB_CUDA(cudaStreamSynchronize(s));
+		if (!h[0]) break;
+		grow_slots(s, pool, T, T.cap * 4);
+	}
+	uint64_t fresh = h[2];
+	if (T.count + fresh >= 0xFFFFFFF0ull) throw Error(SVB_ERANGE, "more than 2^32 unique nodes in one level");
+	ensure_dense(s, pool, T, T.count + fresh);
+	TableDev t = dev_view(T, flags.p);
+	if (k64) {
+		if (fresh) {
+			k_assign_k64<<<blocks_for(T.cap, DD_THREADS), DD_THREADS, 0, s>>>(T.cap, t.tag, t.minO, t.uid, T.dCount.p, T.dMinO.p, T.dKey64.p);
+			SVB_KERNEL_CHECK();
+		}
+		k_convert<CHMODE, false><<<nb, DD_THREADS, 0, s>>>(a, t, nullptr);
+		SVB_KERNEL_CHECK();
+	} else {
+		if (fresh) {
+			k_winner<CHMODE><<<nb, DD_THREADS, 0, s>>>(a, t, T.dCount.p, T.dMinO.p, T.dKey8.p);
+			SVB_KERNEL_CHECK();
+		}
+		k_convert<CHMODE, true><<<nb, DD_THREADS, 0, s>>>(a, t, T.dKey8.p);
+		SVB_KERNEL_CHECK();
+		SVB_CUDA(cudaMemcpyAsync(h, flags.p, 16, cudaMemcpyDeviceToHost, s));
+		SVB_CUDA(cudaStreamSynchronize(s));
+		if (h[1]) throw Error(SVB_ECOLLISION, "64-bit node-key hash collision (exact verify failed)");
+	}
+	T.count += fresh;
+}
+
+void dedup_level(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a) {
+	switch (a.childMode) {
+		case CH_MASK_U8: dedup_level_t<CH_MASK_U8>(s, pool, T, a); break;
+		case CH_MASK_U32: dedup_level_t<CH_MASK_U32>(s, pool, T, a); break;
+		case CH_UID_U32: dedup_level_t<CH_UID_U32>(s, pool, T, a); break;
+		default: throw Error(SVB_EINVAL, "bad child mode");
+	}
+}
+
+void root_key(cudaStream_t s, const DedupArgs& a, uint32_t* d_rootKey8) {
+	switch (a.childMode) {
+		case CH_MASK_U8: k_root<CH_MASK_U8><<<1, 32, 0, s>>>(a, d_rootKey8); break;
+		case CH_MASK_U32: k_root<CH_MASK_U32><<<1, 32, 0, s>>>(a, d_rootKey8); break;
+		default: k_root<CH_UID_U32><<<1, 32, 0, s>>>(a, d_rootKey8); break;
+	}
+	SVB_KERNEL_CHECK();
+}
+
+static void alloc_out(Pool& pool, OutLevel& o, uint64_t n) {
+	o.n = n;
+	o.mask.reset(pool, n);
+	o.child.reset(pool, n * 8);
+	o.mirror.reset(pool, n * 3);
+	o.inv.reset(pool, n);
+	o.mirror.zero();
+	o.inv.zero();
+	o.hasChildLevel = false;
+}
+
+void finalize_levels(cudaStream_t s, Pool& pool, std::vector<LevelTable>& tables, const std::vector<int>& obits,
+                     const uint32_t* d_rootKey8, int rootChildMode, std::vector<OutLevel>& out) {
+	const int L = (int)tables.size();
+	out.clear();
+	out.resize(L);
+	for (int g = L - 1; g >= 1; --g) {
+		LevelTable& T = tables[g];
+		uint64_t n = (T.kind == KIND_LEAF) ? 256 : T.count;
+		DevBuf<uint64_t> keys(pool, n);
+		DevBuf<uint32_t> vals(pool, n);
+		T.rank.reset(pool, n ? n : 1);
+		if (n) {
+			SVB_CUDA(cudaMemcpyAsync(keys.p, (T.kind == KIND_LEAF) ? T.minO.p : T.dMinO.p, n * 8, cudaMemcpyDeviceToDevice, s));
+			k_iota<<<blocks_for(n, 256), 256, 0, s>>>(n, vals.p);
+			SVB_KERNEL_CHECK();
+			radix_sort_pairs(s, pool, keys.p, vals.p, n, (T.kind == KIND_LEAF) ? 64 : obits[g]);
+			k_rank_scatter<<<blocks_for(n, 256), 256, 0, s>>>(n, vals.p, T.rank.p);
+			SVB_KERNEL_CHECK();
+		}
+		uint64_t U = n;
+		if (T.kind == KIND_LEAF) {
+			std::vector<uint64_t> hk(256);
+			SVB_CUDA(cudaMemcpyAsync(hk.data(), keys.p, 256 * 8, cudaMemcpyDeviceToHost, s));
+			SVB_CUDA(cudaStreamSynchronize(s));
+			U = 0;
+			while (U < 256 && hk[U] != MAX_ORDER) ++U;
+		}
+		T.unique = U;
+		alloc_out(pool, out[g], U);
+		if (U) {
+			unsigned nb = blocks_for(U, 256);
+			if (T.kind == KIND_LEAF) k_emit_leaf<<<nb, 256, 0, s>>>(U, vals.p, out[g].mask.p, out[g].child.p);
+			else if (T.kind == KIND_K64) k_emit_k64<<<nb, 256, 0, s>>>(U, vals.p, T.dKey64.p, tables[g + 1].rank.p, out[g].mask.p, out[g].child.p);
+			else k_emit_inner<<<nb, 256, 0, s>>>(U, vals.p, T.dKey8.p, tables[g + 1].rank.p, out[g].mask.p, out[g].child.p);
+			SVB_KERNEL_CHECK();
+		}
+	}
+	alloc_out(pool, out[0], 1);
+	if (L > 1) {
+		(void)rootChildMode;   // the root key already holds uids / mask values that index rank[] of level 1 directly
+		k_emit_root<<<1, 32, 0, s>>>(d_rootKey8, tables[1].rank.p, out[0].mask.p, out[0].child.p);
+		SVB_KERNEL_CHECK();
+	}
+}
+
+}  // namespace svb

@@ -1,0 +1,41 @@
+// svb_dedup.cuh -- host-side entry points of the per-level DAG reduction (svb_dedup.cu).
+#pragma once
+#include "svb_internal.cuh"
+
+namespace svb {
+
+// One level of nodes to be reduced.  Children of node n are refs[childBase[n] + r], r = rank of the
+// child among the set bits of mask[n] (ascending child index).
+struct DedupArgs {
+	uint64_t N = 0;
+	const uint64_t* code = nullptr;     // (tile_local << 3l) | path
+	const uint32_t* tstar = nullptr;
+	const uint8_t* mask = nullptr;      // structural child mask
+	const uint32_t* childBase = nullptr;
+	int childMode = CH_UID_U32;         // how to read the level below
+	const void* childRefs = nullptr;    // u8 masks | u32 uids | u32 masks
+	int l = 0;                          // octal digits of `path`
+	int tbits = 0;                      // bits of a triangle id
+	uint32_t seqBase = 0;               // global tile_seq of tile_local 0
+	uint32_t* ref = nullptr;            // out: uid of each node's unique representative (NULLREF = empty node)
+};
+
+void table_init(cudaStream_t s, Pool& pool, LevelTable& T, int kind);
+
+// KIND_LEAF: nodes are bare 8-bit voxel masks. Accumulates popcounts into *d_voxels.
+void dedup_leaf(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, uint64_t* d_voxels);
+
+// KIND_K64 / KIND_INNER.  Throws Error(SVB_ECOLLISION) if the exact verify pass finds two different
+// keys behind one 64-bit tag.
+void dedup_level(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a);
+
+// Level 0 is never reduced (geom_octree.cpp:483): just resolve the root's children.
+// rootKey: 8 x u32 (uids, or child masks when childMode is a MASK mode), NULLREF = none.
+void root_key(cudaStream_t s, const DedupArgs& a, uint32_t* d_rootKey8);
+
+// Rank the unique nodes of every level by order key and materialise the DAG levels.
+// tables[g] for g in [1, L-1]; obits[g] = significant bits of the order keys of level g.
+void finalize_levels(cudaStream_t s, Pool& pool, std::vector<LevelTable>& tables, const std::vector<int>& obits,
+                     const uint32_t* d_rootKey8, int rootChildMode, std::vector<OutLevel>& out);
+
+}  // namespace svb

@@ -1,0 +1,167 @@
+// svb_internal.cuh -- shared declarations of the libsvb.so translation units.
+// Hand-written CUDA for sm_100a; no CPU path exists behind any of these.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/svb.h"
+
+namespace svb {
+
+// ------------------------------------------------------------------ errors
+struct Error : public std::runtime_error {
+	int code;
+	Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define SVB_CUDA(expr)                                                                          \
+	do {                                                                                        \
+		cudaError_t _e = (expr);                                                                \
+		if (_e != cudaSuccess) {                                                                \
+			cudaGetLastError();                                                                 \
+			throw ::svb::Error(_e == cudaErrorMemoryAllocation ? SVB_ENOMEM : SVB_ECUDA,        \
+			                   std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +      \
+			                       __FILE__ + ":" + std::to_string(__LINE__) + ")");            \
+		}                                                                                       \
+	} while (0)
+
+#define SVB_KERNEL_CHECK() SVB_CUDA(cudaGetLastError())
+
+// ------------------------------------------------------------------ constants
+static const uint32_t NULLNODE = SVB_NULL_NODE;   // octree.cpp:22
+static const uint32_t NULLREF = 0xFFFFFFFFu;      // "no child / empty child" inside dedup keys
+static const uint32_t UNSET = 0xFFFFFFFFu;
+static const uint64_t EMPTY_TAG = 0ull;
+static const uint64_t MAX_ORDER = 0xFFFFFFFFFFFFFFFFull;
+
+enum LevelKind { KIND_LEAF = 0, KIND_K64 = 1, KIND_INNER = 2 };
+// how a dedup kernel reads the refs of the level below
+enum ChildMode { CH_MASK_U8 = 0, CH_SLOT_U32 = 1, CH_UID_U32 = 2, CH_MASK_U32 = 3 };
+
+// ------------------------------------------------------------------ device memory (stream ordered)
+struct Pool {
+	cudaStream_t stream = nullptr;
+	size_t live = 0, peak = 0;
+	void* alloc(size_t bytes) {
+		if (bytes == 0) bytes = 16;
+		void* p = nullptr;
+		SVB_CUDA(cudaMallocAsync(&p, bytes, stream));
+		live += bytes;
+		if (live > peak) peak = live;
+		return p;
+	}
+	void free(void* p, size_t bytes) {
+		if (!p) return;
+		cudaFreeAsync(p, stream);
+		live -= (bytes == 0 ? 16 : bytes);
+	}
+};
+
+template <class T>
+struct DevBuf {
+	Pool* pool = nullptr;
+	T* p = nullptr;
+	size_t n = 0;   // elements
+	DevBuf() {}
+	DevBuf(Pool& pl, size_t count) { reset(pl, count); }
+	DevBuf(const DevBuf&) = delete;
+	DevBuf& operator=(const DevBuf&) = delete;
+	DevBuf(DevBuf&& o) noexcept : pool(o.pool), p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+	DevBuf& operator=(DevBuf&& o) noexcept {
+		if (this != &o) { release(); pool = o.pool; p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+		return *this;
+	}
+	~DevBuf() { release(); }
+	void reset(Pool& pl, size_t count) {
+		release();
+		pool = &pl;
+		n = count;
+		p = (T*)pl.alloc(count * sizeof(T));
+	}
+	void release() {
+		if (p && pool) pool->free(p, n * sizeof(T));
+		p = nullptr;
+		n = 0;
+	}
+	size_t bytes() const { return n * sizeof(T); }
+	void zero() { if (p) SVB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T) ? n * sizeof(T) : 16, pool->stream)); }
+	void fill_ff() { if (p) SVB_CUDA(cudaMemsetAsync(p, 0xFF, n * sizeof(T) ? n * sizeof(T) : 16, pool->stream)); }
+};
+
+// ------------------------------------------------------------------ geometry of one (sub-)octree
+struct TileGeom {   // host computed, exactly as geom_octree.cpp:177-184,214 / :340-344 would
+	double cx, cy, cz;   // root centre (double)
+	double rootSide;     // float-rounded max side, widened
+};
+
+// ------------------------------------------------------------------ one level of the current tile batch
+struct BatchLevel {
+	uint64_t n = 0;
+	DevBuf<uint64_t> code;        // (tile_local << 3l) | path   (ascending == Morton order, tile major)
+	DevBuf<uint32_t> tstar;       // first-touch triangle
+	DevBuf<uint8_t> mask;         // structural child mask / leaf voxel mask (OR'd with 32-bit atomics; padded)
+	DevBuf<uint32_t> childBase;   // index of first child in the next level
+	DevBuf<uint32_t> ref;         // dedup result (slot / uid / NULLREF)
+};
+
+// ------------------------------------------------------------------ persistent per-level dedup table
+struct LevelTable {
+	int kind = KIND_INNER;
+	// open-addressing slots
+	uint64_t cap = 0;
+	DevBuf<uint64_t> tag;     // K64: the key itself; INNER: 64-bit hash of the 8 child uids; 0 = empty
+	DevBuf<uint64_t> minO;    // min order key seen for this slot
+	DevBuf<uint32_t> uid;     // dense id (UNSET until the winner pass)
+	// dense, indexed by uid
+	uint64_t count = 0;       // host copy of *dCount
+	uint64_t denseCap = 0;
+	DevBuf<uint32_t> dCount;  // device counter (1 element)
+	DevBuf<uint64_t> dMinO;
+	DevBuf<uint64_t> dKey64;  // KIND_K64: 8 child masks
+	DevBuf<uint32_t> dKey8;   // KIND_INNER: 8 child uids (NULLREF = none)
+	// KIND_LEAF: 256-entry direct table lives in minO (cap = 256)
+	// finalize
+	DevBuf<uint32_t> rank;    // uid -> final id (LEAF: mask value -> final id)
+	uint64_t unique = 0;
+};
+
+// ------------------------------------------------------------------ final octree (what getNodeData() exposes)
+struct OutLevel {
+	uint64_t n = 0;
+	DevBuf<uint8_t> mask;
+	DevBuf<uint32_t> child;      // n*8
+	DevBuf<uint8_t> mirror;      // n*3 (zero until toSDAG)
+	DevBuf<uint8_t> inv;         // n
+	DevBuf<uint32_t> childLevel; // n*8 (only materialised by cross-merge; otherwise lev+1)
+	bool hasChildLevel = false;
+};
+
+// ------------------------------------------------------------------ primitives (svb_prims.cu)
+// exclusive scan of popcount(bytes[i]) -> out[i] (uint32), returns total through *d_total (device, u64)
+void scan_popc8(cudaStream_t s, Pool& pool, const uint8_t* bytes, uint64_t n, uint32_t* out, uint64_t* d_total);
+// exclusive scan of uint32 values (in place allowed), total to *d_total
+void scan_u32(cudaStream_t s, Pool& pool, const uint32_t* in, uint64_t n, uint32_t* out, uint64_t* d_total);
+// stable LSD radix sort of (key u64, val u32) pairs on the low `bits` bits of the key.
+// Results end up back in keys/vals.
+void radix_sort_pairs(cudaStream_t s, Pool& pool, uint64_t* keys, uint32_t* vals, uint64_t n, int bits);
+
+// ------------------------------------------------------------------ device helpers
+__host__ __device__ inline uint64_t mix64(uint64_t x) {
+	x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+	return x;
+}
+
+static inline unsigned blocks_for(uint64_t n, unsigned threads) {
+	uint64_t b = (n + threads - 1) / threads;
+	if (b == 0) b = 1;
+	if (b > 0x7FFFFFFFull) throw Error(SVB_ERANGE, "grid too large");
+	return (unsigned)b;
+}
+
+}  // namespace svb

@@ -1,0 +1,224 @@
+// svb_prims.cu -- scan and radix-sort primitives (hand-written; no CUB/Thrust on the hot path).
+//
+//  * exclusive scans: reduce-then-scan over 2048-item tiles (block sums -> single-block
+//    scan of the sums in 64 bit -> re-scan with the tile offset).  Inputs are read twice
+//    (1 B or 4 B per item), outputs written once: HBM-bound, 2 passes.
+//  * radix sort: stable LSD, 8-bit digits, (u64 key, u32 payload); used to rank the unique
+//    nodes of a level by their order key (U_l elements, not N_l).
+#include "svb_internal.cuh"
+
+namespace svb {
+
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+struct Popc8In {
+	const uint8_t* p;
+	__device__ void load(uint64_t base, uint64_t n, uint32_t v[SCAN_ITEMS]) const {
+		if (base + SCAN_ITEMS <= n) {
+			uint2 w = *reinterpret_cast<const uint2*>(p + base);   // base is a multiple of 8, p 16B aligned
+			uint32_t a = w.x, b = w.y;
+#pragma unroll
+			for (int i = 0; i < 4; ++i) { v[i] = __popc((a >> (8 * i)) & 0xFF); v[4 + i] = __popc((b >> (8 * i)) & 0xFF); }
+		} else {
+#pragma unroll
+			for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = (base + i < n) ? __popc((uint32_t)p[base + i]) : 0;
+		}
+	}
+};
+struct U32In {
+	const uint32_t* p;
+	__device__ void load(uint64_t base, uint64_t n, uint32_t v[SCAN_ITEMS]) const {
+#pragma unroll
+		for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = (base + i < n) ? p[base + i] : 0;
+	}
+};
+
+__device__ inline uint32_t warp_incl_scan(uint32_t x, int lane) {
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+		if (lane >= d) x += y;
+	}
+	return x;
+}
+
+// exclusive scan of one value per thread across the block; returns the exclusive prefix, *total = block sum
+__device__ inline uint32_t block_excl_scan(uint32_t x, uint32_t* total) {
+	__shared__ uint32_t wsum[SCAN_THREADS / 32];
+	__shared__ uint32_t wtot;
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint32_t inc = warp_incl_scan(x, lane);
+	if (lane == 31) wsum[w] = inc;
+	__syncthreads();
+	if (w == 0) {
+		uint32_t s = (lane < SCAN_THREADS / 32) ? wsum[lane] : 0;
+		uint32_t si = warp_incl_scan(s, lane);
+		if (lane < SCAN_THREADS / 32) wsum[lane] = si - s;
+		if (lane == SCAN_THREADS / 32 - 1) wtot = si;
+	}
+	__syncthreads();
+	uint32_t r = inc - x + wsum[w];
+	*total = wtot;
+	__syncthreads();
+	return r;
+}
+
+template <class In>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(In in, uint64_t n, uint32_t* blockSums) {
+	uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+	uint32_t v[SCAN_ITEMS];
+	in.load(base, n, v);
+	uint32_t s = 0;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) s += v[i];
+	uint32_t tot;
+	block_excl_scan(s, &tot);
+	if (threadIdx.x == 0) blockSums[blockIdx.x] = tot;
+}
+
+// single block: exclusive scan of nb u32 sums into u64 offsets, grand total to *total
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const uint32_t* sums, uint64_t nb, uint64_t* offs, uint64_t* total) {
+	__shared__ uint64_t carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (uint64_t base = 0; base < nb; base += SCAN_THREADS) {
+		uint64_t i = base + threadIdx.x;
+		uint32_t x = (i < nb) ? sums[i] : 0;
+		uint32_t tot;
+		uint32_t ex = block_excl_scan(x, &tot);
+		if (i < nb) offs[i] = carry + ex;
+		__syncthreads();
+		if (threadIdx.x == 0) carry += tot;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) *total = carry;
+}
+
+template <class In>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(In in, uint64_t n, const uint64_t* offs, uint32_t* out) {
+	uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+	uint32_t v[SCAN_ITEMS];
+	in.load(base, n, v);
+	uint32_t s = 0;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) s += v[i];
+	uint32_t tot;
+	uint32_t ex = block_excl_scan(s, &tot);
+	uint64_t o = offs[blockIdx.x] + ex;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) {
+		if (base + i < n) out[base + i] = (uint32_t)o;
+		o += v[i];
+	}
+}
+
+template <class In>
+void scan_impl(cudaStream_t s, Pool& pool, In in, uint64_t n, uint32_t* out, uint64_t* d_total) {
+	if (n == 0) { SVB_CUDA(cudaMemsetAsync(d_total, 0, 8, s)); return; }
+	uint64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+	DevBuf<uint32_t> sums(pool, nb);
+	DevBuf<uint64_t> offs(pool, nb);
+	k_scan_reduce<In><<<(unsigned)nb, SCAN_THREADS, 0, s>>>(in, n, sums.p);
+	SVB_KERNEL_CHECK();
+	k_scan_sums<<<1, SCAN_THREADS, 0, s>>>(sums.p, nb, offs.p, d_total);
+	SVB_KERNEL_CHECK();
+	k_scan_apply<In><<<(unsigned)nb, SCAN_THREADS, 0, s>>>(in, n, offs.p, out);
+	SVB_KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------- radix sort
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ROUNDS = 16;
+constexpr int RS_CHUNK = RS_THREADS * RS_ROUNDS;
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* keys, uint64_t n, int shift, uint32_t* hist, unsigned nblocks) {
+	__shared__ uint32_t h[256];
+	h[threadIdx.x] = 0;
+	__syncthreads();
+	uint64_t base = (uint64_t)blockIdx.x * RS_CHUNK;
+	for (int r = 0; r < RS_ROUNDS; ++r) {
+		uint64_t i = base + (uint64_t)r * RS_THREADS + threadIdx.x;
+		if (i < n) atomicAdd(&h[(keys[i] >> shift) & 0xFF], 1u);
+	}
+	__syncthreads();
+	hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];   // digit-major
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* keys, const uint32_t* vals, uint64_t n, int shift,
+                                                            const uint32_t* histScan, unsigned nblocks, uint64_t* okeys, uint32_t* ovals) {
+	__shared__ uint32_t off[256];
+	__shared__ uint32_t wcnt[RS_WARPS][256];
+	off[threadIdx.x] = histScan[(uint64_t)threadIdx.x * nblocks + blockIdx.x];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint64_t base = (uint64_t)blockIdx.x * RS_CHUNK;
+	for (int r = 0; r < RS_ROUNDS; ++r) {
+		for (int j = threadIdx.x; j < RS_WARPS * 256; j += RS_THREADS) (&wcnt[0][0])[j] = 0;
+		__syncthreads();
+		uint64_t i = base + (uint64_t)r * RS_THREADS + threadIdx.x;
+		bool valid = i < n;
+		uint64_t k = valid ? keys[i] : 0;
+		uint32_t v = valid ? vals[i] : 0;
+		unsigned d = valid ? (unsigned)((k >> shift) & 0xFF) : 256u + lane;   // invalid lanes never match
+		unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+		unsigned below = __popc(peers & ((1u << lane) - 1));
+		if (valid && below == 0) wcnt[w][d] = __popc(peers);
+		__syncthreads();
+		if (valid) {
+			uint32_t pos = off[d] + below;
+			for (int ww = 0; ww < w; ++ww) pos += wcnt[ww][d];
+			okeys[pos] = k;
+			ovals[pos] = v;
+		}
+		__syncthreads();
+		{
+			uint32_t add = 0;
+#pragma unroll
+			for (int ww = 0; ww < RS_WARPS; ++ww) add += wcnt[ww][threadIdx.x];
+			off[threadIdx.x] += add;
+		}
+		__syncthreads();
+	}
+}
+
+}  // namespace
+
+void scan_popc8(cudaStream_t s, Pool& pool, const uint8_t* bytes, uint64_t n, uint32_t* out, uint64_t* d_total) {
+	scan_impl(s, pool, Popc8In{bytes}, n, out, d_total);
+}
+void scan_u32(cudaStream_t s, Pool& pool, const uint32_t* in, uint64_t n, uint32_t* out, uint64_t* d_total) {
+	scan_impl(s, pool, U32In{in}, n, out, d_total);
+}
+
+void radix_sort_pairs(cudaStream_t s, Pool& pool, uint64_t* keys, uint32_t* vals, uint64_t n, int bits) {
+	if (n <= 1) return;
+	if (bits > 64) bits = 64;
+	int passes = (bits + 7) / 8;
+	if (passes < 1) passes = 1;
+	unsigned nb = (unsigned)((n + RS_CHUNK - 1) / RS_CHUNK);
+	DevBuf<uint64_t> k2(pool, n);
+	DevBuf<uint32_t> v2(pool, n);
+	DevBuf<uint32_t> hist(pool, (uint64_t)256 * nb);
+	DevBuf<uint64_t> tot(pool, 1);
+	uint64_t* ka = keys; uint32_t* va = vals;
+	uint64_t* kb = k2.p; uint32_t* vb = v2.p;
+	for (int p = 0; p < passes; ++p) {
+		k_rs_hist<<<nb, RS_THREADS, 0, s>>>(ka, n, 8 * p, hist.p, nb);
+		SVB_KERNEL_CHECK();
+		scan_u32(s, pool, hist.p, (uint64_t)256 * nb, hist.p, tot.p);
+		k_rs_scatter<<<nb, RS_THREADS, 0, s>>>(ka, va, n, 8 * p, hist.p, nb, kb, vb);
+		SVB_KERNEL_CHECK();
+		uint64_t* tk = ka; ka = kb; kb = tk;
+		uint32_t* tv = va; va = vb; vb = tv;
+	}
+	if (ka != keys) {
+		SVB_CUDA(cudaMemcpyAsync(keys, ka, n * 8, cudaMemcpyDeviceToDevice, s));
+		SVB_CUDA(cudaMemcpyAsync(vals, va, n * 4, cudaMemcpyDeviceToDevice, s));
+	}
+}
+
+}  // namespace svb

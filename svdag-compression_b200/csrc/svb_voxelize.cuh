@@ -1,0 +1,24 @@
+// svb_voxelize.cuh -- host-side entry points of the voxelizer (svb_voxelize.cu).
+#pragma once
+#include "svb_internal.cuh"
+
+namespace svb {
+
+struct BatchTooBig {};   // thrown when a tile batch outgrows its buffers: the caller halves the batch
+
+struct TileGridHost {    // regular grid of tile cubes over the root cube (G = 2^(step+1) per axis; 1 for step 0)
+	double ox = 0, oy = 0, oz = 0;   // min corner of the root cube
+	double cell = 1;                 // tile side
+	int G = 1;
+};
+
+// (triangle, tile) candidate pairs for tiles with seq in [seq_lo, seq_hi); pairs sorted by triangle id.
+void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T, const TileGridHost& grid,
+                     const int* d_gridTile, int seq_lo, int seq_hi, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t& P);
+
+// Level-synchronous SVO build of `ntiles` sub-octrees of Lt levels each.  Consumes the root pairs.
+void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
+                    DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t P, uint64_t budget_bytes,
+                    std::vector<BatchLevel>& lv, uint64_t& pairsTotal);
+
+}  // namespace svb

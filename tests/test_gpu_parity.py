@@ -1,0 +1,126 @@
+"""GPU parity tests: the CUDA path through the C ABI (libsvb.so) against the CPU oracle and the
+golden files minted from the unmodified reference binary.  Bit-exact: node arrays, counts, bytes."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _assert_levels_equal(got, want, what, fields=("mask", "child")):
+    assert len(got) == len(want), f"{what}: level count {len(got)} != {len(want)}"
+    for l, (a, b) in enumerate(zip(got, want)):
+        assert len(a["mask"]) == len(b["mask"]), f"{what}: level {l} has {len(a['mask'])} nodes, oracle {len(b['mask'])}"
+        for f in fields:
+            if not np.array_equal(a[f], b[f]):
+                bad = np.nonzero((a[f].reshape(len(a["mask"]), -1) != b[f].reshape(len(b["mask"]), -1)).any(axis=1))[0]
+                raise AssertionError(f"{what}: level {l} field {f} differs at {len(bad)} nodes, first {bad[:5]}: "
+                                     f"got {a[f][bad[0]]} want {b[f][bad[0]]}")
+
+
+def _oracle_levels(o):
+    return [o.level(l) for l in range(o.levels)]
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN if not p.stem.endswith("_c")], ids=lambda p: p.stem)
+def test_golden_files_bit_exact(pkg, path):
+    """mesh -> SVDAG/ESVDAG/USSVDAG/SSVDAG on the GPU == the files the reference binary wrote."""
+    g = golden_case(path)
+    t = pkg.GeomOctree(g["tris"])
+    st = t.build(g["levels"], g["step"])
+    vox, svo, dag, sdag = (int(x) for x in g["stats"])
+    assert (st["nTotalVoxels"], st["nNodesSVO"], st["nNodesDAG"]) == (vox, svo, dag)
+    sizes = t.level_sizes()
+    for lev in range(1, g["levels"]):
+        if g["reduced"][lev].sum():
+            assert sizes[lev] == int(g["reduced"][lev][1])
+    assert pkg.encoders.encode(t, "svdag") == g["files"]["svdag"]
+    assert pkg.encoders.encode(t, "esvdag") == g["files"]["esvdag"]
+    st = t.to_sdag()
+    assert st["nNodesSDAG"] == sdag
+    assert pkg.encoders.encode(t, "ussvdag") == g["files"]["ussvdag"]
+    assert pkg.encoders.encode(t, "ssvdag") == g["files"]["ssvdag"]
+
+
+CASES = [
+    # mesh, kwargs, levels, step
+    ("sphere", dict(n_lat=64, n_lon=128), 8, 0),
+    ("sphere", dict(n_lat=64, n_lon=128), 9, 2),
+    ("sphere", dict(n_lat=64, n_lon=128), 9, 3),
+    ("city", dict(lots=8), 8, 0),
+    ("city", dict(lots=8), 9, 2),
+    ("terrain", dict(n=64), 8, 1),
+    ("terrain", dict(n=64), 9, 3),
+    ("sphere_menger", dict(n_lat=32, n_lon=64, sponge_level=2), 8, 0),
+    ("sphere_menger", dict(n_lat=32, n_lon=64, sponge_level=2), 9, 2),
+]
+
+
+@pytest.mark.parametrize("mesh,kw,levels,step", CASES, ids=[f"{m}-L{l}-s{s}" for m, _, l, s in CASES])
+def test_dag_and_sdag_match_oracle(pkg, orc, meshgen, mesh, kw, levels, step):
+    tris = meshgen.make_mesh(mesh, **kw)
+    o = orc.OracleOctree(tris)
+    o.build(levels, step)
+    t = pkg.GeomOctree(tris)
+    st = t.build(levels, step)
+    for k in ("nTotalVoxels", "nNodesSVO", "nNodesDAG", "nNodesLastLevSVO", "nNodesLastLevDAG"):
+        assert st[k] == o.stat(k), k
+    _assert_levels_equal(t.levels_host(), _oracle_levels(o), "DAG")
+    if step == 0:
+        assert t.level_sizes_svo()[1:] == o.level_sizes_before_dag()[1:]
+    assert pkg.encoders.encode(t, "svdag") == o.encode("svdag")
+    o.to_sdag()
+    st = t.to_sdag()
+    assert st["nNodesSDAG"] == o.stat("nNodesSDAG")
+    _assert_levels_equal(t.levels_host(), _oracle_levels(o), "SDAG", fields=("mask", "child", "mirror", "inv"))
+    assert pkg.encoders.encode(t, "ussvdag") == o.encode("ussvdag")
+    assert pkg.encoders.encode(t, "ssvdag") == o.encode("ssvdag")
+
+
+def test_batch_splitting_gives_identical_result(pkg, meshgen):
+    """A tiny batch budget forces many tile batches; node order must not depend on the batching."""
+    tris = meshgen.make_mesh("sphere", n_lat=64, n_lon=128)
+    a = pkg.GeomOctree(tris)
+    a.build(9, 2)
+    b = pkg.GeomOctree(tris)
+    b.set_batch_budget(8 << 20)
+    st = b.build(9, 2)
+    assert st["nBatches"] > 1
+    _assert_levels_equal(b.levels_host(), a.levels_host(), "batched DAG")
+
+
+def test_sdag_from_uploaded_dag(pkg, orc, meshgen):
+    """Stage entry: a DAG produced elsewhere (here: the oracle) uploaded, reduced to an SDAG on the GPU."""
+    tris = meshgen.make_mesh("terrain", n=48)
+    o = orc.OracleOctree(tris)
+    o.build(8, 0)
+    lv = _oracle_levels(o)
+    lo, hi = o.scene_bbox()
+    t = pkg.GeomOctree()
+    t.upload_levels(lv, np.concatenate([lo, hi]).astype(np.float32), 1.0, o.stat("nTotalVoxels"))
+    o.to_sdag()
+    t.to_sdag()
+    _assert_levels_equal(t.levels_host(), _oracle_levels(o), "SDAG(uploaded)", fields=("mask", "child", "mirror", "inv"))
+
+
+def test_wrong_state_and_bad_args(pkg, meshgen):
+    tris = meshgen.make_mesh("sphere", n_lat=8, n_lon=16)
+    t = pkg.GeomOctree(tris)
+    with pytest.raises(pkg.SvbError):
+        t.to_sdag()                      # "ERROR! This is not a DAG or SDAG!" (geom_octree.cpp:560-563)
+    with pytest.raises(pkg.SvbError):
+        t.build(6, 5)                    # step + 1 must be < levels
+    t.build(5, 0)
+    t.to_sdag()
+    with pytest.raises(pkg.SvbError):
+        t.to_sdag()                      # already an SDAG
+    with pytest.raises(pkg.SvbError):
+        pkg.encoders.encode(t, "svdag")  # EncodedSVDAG::encode needs DAG state (encoded_svdag.cpp:109)
+
+
+def test_empty_scene(pkg):
+    t = pkg.GeomOctree(np.zeros((0, 3, 3), np.float32))
+    st = t.build(5, 0, bbox=(np.zeros(3), np.ones(3)))
+    assert st["nTotalVoxels"] == 0 and st["nNodesDAG"] == 1
+    assert t.level_sizes() == [1, 0, 0, 0, 0]
