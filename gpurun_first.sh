@@ -1,6 +1,6 @@
 #!/bin/bash
-# scratch helper (not part of the product): first contact with the GPU
+# scratch helper (not part of the product)
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,memory.total --format=csv > gpurun_out/smi.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
 cat gpurun_out/pytest_gpu.log
+python gpurun_probe.py "$@" 2>&1 | tee gpurun_out/probe3.log | tail -70

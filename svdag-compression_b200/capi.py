@@ -24,6 +24,7 @@ class Stats(C.Structure):
                                            "nNodesLastLevDAG", "nCrossLevelMerged", "nNodes", "nTiles", "nBatches", "nPairsTotal")]
     _fields_ += [("rootSide", C.c_double), ("bboxF", C.c_float * 6)]
     _fields_ += [(n, C.c_double) for n in ("msVoxelize", "msDedup", "msFinalize", "msSdag", "msCrossMerge", "msTotal")]
+    _fields_ += [("nKernelLaunches", C.c_uint64)]
 
     def as_dict(self):
         d = {}

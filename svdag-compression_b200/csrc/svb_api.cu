@@ -54,6 +54,7 @@ struct ProfScope {
 	void done(uint64_t n_out, double bytes) {
 		if (idx < 0) return;
 		cudaEventRecord(c->pending[idx].e1, c->stream);
+		c->pending[idx].closed = true;
 		c->pending[idx].rec.n_out = n_out;
 		c->pending[idx].rec.bytes = bytes;
 	}
@@ -61,11 +62,13 @@ struct ProfScope {
 
 void resolve_profile(svb_ctx* c) {
 	for (auto& p : c->pending) {
-		float ms = 0;
-		cudaEventSynchronize(p.e1);
-		cudaEventElapsedTime(&ms, p.e0, p.e1);
-		p.rec.ms = ms;
-		c->prof.push_back(p.rec);
+		if (p.closed) {   // scopes left by an exception (e.g. a batch that had to be split) never recorded e1
+			float ms = 0;
+			cudaEventSynchronize(p.e1);
+			cudaEventElapsedTime(&ms, p.e0, p.e1);
+			p.rec.ms = ms;
+			c->prof.push_back(p.rec);
+		}
 		cudaEventDestroy(p.e0);
 		cudaEventDestroy(p.e1);
 	}
@@ -153,7 +156,7 @@ struct TileHost {
 
 // Builds tiles [a,b) and reduces them.  Throws BatchTooBig when the batch must be split.
 void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tiles, uint32_t a, uint32_t b,
-                    const TileGridHost& grid, const int* d_gridTile, int Lt, uint32_t gbase, uint64_t budget,
+                    const TileGridHost& grid, const int* d_gridTile, int Lt, uint32_t gbase, uint64_t budget, uint64_t nodeCap,
                     uint32_t* d_tileRootRef, std::vector<BatchLevel>* keepLevels) {
 	cudaStream_t s = c->stream;
 	uint32_t nt = b - a;
@@ -171,7 +174,7 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 		DevBuf<uint32_t> ptri, pnode;
 		uint64_t P = 0;
 		make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, (int)a, (int)b, ptri, pnode, P);
-		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, P, budget, lv, pairs);
+		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, P, budget, nodeCap, lv, pairs);
 		ps.done(pairs, 36.0 * (double)c->T + 9.0 * (double)lv[Lt - 1].n);
 		B.msVox += tm.stop();
 	}
@@ -207,15 +210,40 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 	B.msDedup += tm.stop();
 }
 
+// Batching: start with every tile in one batch.  When the voxelizer predicts (or hits) an overflow it
+// throws BatchTooBig before anything was reduced, carrying per-tile node counts of the level it
+// reached; the range is then cut by cumulative weight into pieces that should fit.  Batches are
+// always processed in ascending tile order (the order keys of later batches are larger, which the
+// dedup tables rely on).
 void run_tiles_split(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tiles, uint32_t a, uint32_t b,
-                     const TileGridHost& grid, const int* d_gridTile, int Lt, uint32_t gbase, uint64_t budget, uint32_t* d_tileRootRef) {
-	try {
-		run_tile_batch(c, B, tiles, a, b, grid, d_gridTile, Lt, gbase, budget, d_tileRootRef, nullptr);
-	} catch (const BatchTooBig&) {
-		if (b - a <= 1) throw Error(SVB_ENOMEM, "a single sub-octree does not fit the batch budget; use a larger step");
-		uint32_t mid = a + (b - a) / 2;
-		run_tiles_split(c, B, tiles, a, mid, grid, d_gridTile, Lt, gbase, budget, d_tileRootRef);
-		run_tiles_split(c, B, tiles, mid, b, grid, d_gridTile, Lt, gbase, budget, d_tileRootRef);
+                     const TileGridHost& grid, const int* d_gridTile, int Lt, uint32_t gbase, uint64_t budget, uint64_t nodeCap,
+                     uint32_t* d_tileRootRef) {
+	std::vector<uint32_t> plan(1, b);   // upcoming batch ends, ascending; plan.front() is the current one
+	while (a < b) {
+		uint32_t e = plan.front();
+		try {
+			run_tile_batch(c, B, tiles, a, e, grid, d_gridTile, Lt, gbase, budget, nodeCap, d_tileRootRef, nullptr);
+			a = e;
+			plan.erase(plan.begin());
+		} catch (const BatchTooBig& x) {
+			if (e - a <= 1) throw Error(SVB_ENOMEM, "a single sub-octree does not fit the batch budget; use a larger step");
+			std::vector<uint32_t> cuts;
+			if (x.weight.size() == e - a) {
+				double scale = 1.0;
+				for (int r = 0; r < x.remaining; ++r) scale *= x.growth;
+				double total = 0;
+				for (uint32_t w : x.weight) total += (double)w * scale;
+				double cap = 0.7 * (double)nodeCap;
+				uint32_t pieces = (uint32_t)std::max(2.0, std::ceil(total / cap));
+				double per = total / pieces, acc = 0;
+				for (uint32_t i = 0; i + 1 < e - a; ++i) {
+					acc += (double)x.weight[i] * scale;
+					if (acc >= per) { cuts.push_back(a + i + 1); acc = 0; }
+				}
+			}
+			if (cuts.empty()) cuts.push_back(a + (e - a) / 2);
+			plan.insert(plan.begin(), cuts.begin(), cuts.end());
+		}
 	}
 }
 
@@ -236,6 +264,7 @@ void do_build(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], const
 	c->state = SVB_S_EMPTY;
 	c->prof.clear();
 	memset(&c->stats, 0, sizeof(c->stats));
+	const uint64_t launches0 = g_launches.load();
 	StageTimer total(s);
 
 	BuildState B;
@@ -256,9 +285,8 @@ void do_build(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], const
 	rootG.cx = (bmin[0] + bmax[0]) * 0.5; rootG.cy = (bmin[1] + bmax[1]) * 0.5; rootG.cz = (bmin[2] + bmax[2]) * 0.5;   // bbox.center(), :214
 	rootG.rootSide = rootSide;
 
-	size_t freeB = 0, totalB = 0;
-	SVB_CUDA(cudaMemGetInfo(&freeB, &totalB));
-	uint64_t budget = c->batchBudget ? c->pool.live + c->batchBudget : c->pool.live + (uint64_t)(0.55 * (double)freeB);
+	// transient budget of one tile batch: a fraction of what the slab allocator can still hand out
+	uint64_t budget = c->batchBudget ? c->pool.live + c->batchBudget : c->pool.live + (uint64_t)(0.80 * (double)c->pool.headroom());
 
 	TileGridHost grid1;
 	grid1.G = 1; grid1.cell = rootSide > 0 ? rootSide : 1.0;
@@ -273,7 +301,7 @@ void do_build(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], const
 		B.tileBits = 1;
 		if (B.tileBits + B.tbits + 3 * ((int)L - 1) > 63) throw Error(SVB_ERANGE, "order key exceeds 64 bits: use step > 0 for this many levels/triangles");
 		try {
-			run_tile_batch(c, B, rootTile, 0, 1, grid1, dGrid1.p, (int)L, 0, budget, nullptr, nullptr);
+			run_tile_batch(c, B, rootTile, 0, 1, grid1, dGrid1.p, (int)L, 0, budget, 0, nullptr, nullptr);
 		} catch (const BatchTooBig&) {
 			throw Error(SVB_ENOMEM, "octree does not fit device memory in one piece; use step > 0");
 		}
@@ -284,7 +312,7 @@ void do_build(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], const
 		// ---- base octree (levels 0..step) over all triangles, exact hierarchical tests
 		std::vector<BatchLevel> base;
 		try {
-			run_tile_batch(c, B, rootTile, 0, 1, grid1, dGrid1.p, (int)s1, 0, budget, nullptr, &base);
+			run_tile_batch(c, B, rootTile, 0, 1, grid1, dGrid1.p, (int)s1, 0, budget, 0, nullptr, &base);
 		} catch (const BatchTooBig&) {
 			throw Error(SVB_ENOMEM, "base octree does not fit device memory");
 		}
@@ -347,7 +375,9 @@ void do_build(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], const
 		DevBuf<int> dGrid(c->pool, hgrid.size());
 		SVB_CUDA(cudaMemcpyAsync(dGrid.p, hgrid.data(), hgrid.size() * sizeof(int), cudaMemcpyHostToDevice, s));
 		DevBuf<uint32_t> tileRootRef(c->pool, nTiles ? nTiles : 1);
-		if (nTiles) run_tiles_split(c, B, tiles, 0, (uint32_t)nTiles, grid, dGrid.p, Lt, s1, budget, tileRootRef.p);
+		// leaf-level nodes one batch may hold: 32-bit indices, and ~40 bytes of transient state per leaf node
+		uint64_t nodeCap = std::min<uint64_t>(3600000000ull, (budget - c->pool.live) / 40);
+		if (nTiles) run_tiles_split(c, B, tiles, 0, (uint32_t)nTiles, grid, dGrid.p, Lt, s1, budget, nodeCap, tileRootRef.p);
 		uint64_t leafVox = download(s, B.dVoxels.p, 1)[0];
 		nVoxels = nVoxels + leafVox - nTiles;   // :352-354 "root doesn't count"
 		// ---- reduce the base octree (levels step..1) on top of the tile roots
@@ -424,6 +454,7 @@ void do_build(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], const
 	c->levels = L;
 	c->state = SVB_S_DAG;
 	st.msTotal = total.stop();
+	st.nKernelLaunches = g_launches.load() - launches0;
 	resolve_profile(c);
 }
 
@@ -464,11 +495,6 @@ svb_ctx* svb_create(int device) {
 	c->device = device;
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
 	c->pool.stream = c->stream;
-	cudaMemPool_t mp;
-	if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
-		uint64_t thr = ~0ull;
-		cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
-	}
 	return c;
 }
 
@@ -478,6 +504,7 @@ void svb_destroy(svb_ctx* c) {
 	c->out.clear();
 	c->trisOwned.release();
 	cudaStreamSynchronize(c->stream);
+	c->pool.release_all();
 	cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -519,9 +546,11 @@ int svb_build(svb_ctx* c, uint32_t levels, uint32_t step, const double bmin[3], 
 int svb_to_sdag(svb_ctx* c, svb_stats* out) {
 	int rc = guarded(c, [&] {
 		if (c->state != SVB_S_DAG) throw Error(SVB_EINVAL, "ERROR! This is not a DAG or SDAG!");   // geom_octree.cpp:560-563
+		const uint64_t launches0 = g_launches.load();
 		StageTimer tm(c->stream);
 		uint64_t nn = to_sdag_device(c);
 		c->stats.msSdag = tm.stop();
+		c->stats.nKernelLaunches = g_launches.load() - launches0;
 		c->stats.nNodesSDAG = nn;   // geom_octree.cpp:578,664,683: root not counted
 		c->stats.nNodes = nn;
 		c->state = SVB_S_SDAG;

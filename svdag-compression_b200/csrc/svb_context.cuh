@@ -19,7 +19,7 @@ struct svb_ctx {
 	std::vector<uint64_t> svoCounts;
 	// instrumentation
 	bool profiling = false;
-	struct PendingProf { svb_prof_rec rec; cudaEvent_t e0, e1; };
+	struct PendingProf { svb_prof_rec rec; cudaEvent_t e0, e1; bool closed = false; };
 	std::vector<PendingProf> pending;
 	std::vector<svb_prof_rec> prof;
 	uint64_t batchBudget = 0;

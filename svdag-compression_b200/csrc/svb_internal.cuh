@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdio>
 #include <stdexcept>
 #include <string>
@@ -31,7 +32,13 @@ struct Error : public std::runtime_error {
 		}                                                                                       \
 	} while (0)
 
-#define SVB_KERNEL_CHECK() SVB_CUDA(cudaGetLastError())
+// every kernel launch is followed by this check; it also counts launches (svb_stats::nKernelLaunches)
+extern std::atomic<uint64_t> g_launches;
+#define SVB_KERNEL_CHECK()            \
+	do {                              \
+		::svb::g_launches.fetch_add(1, std::memory_order_relaxed); \
+		SVB_CUDA(cudaGetLastError()); \
+	} while (0)
 
 // ------------------------------------------------------------------ constants
 static const uint32_t NULLNODE = SVB_NULL_NODE;   // octree.cpp:22
@@ -44,22 +51,94 @@ enum LevelKind { KIND_LEAF = 0, KIND_K64 = 1, KIND_INNER = 2 };
 // how a dedup kernel reads the refs of the level below
 enum ChildMode { CH_MASK_U8 = 0, CH_SLOT_U32 = 1, CH_UID_U32 = 2, CH_MASK_U32 = 3 };
 
-// ------------------------------------------------------------------ device memory (stream ordered)
+// ------------------------------------------------------------------ device memory
+// Slab allocator: a few large cudaMalloc'ed slabs (grown geometrically, kept for the lifetime of the
+// context) carved up by an address-ordered first-fit free list with coalescing.  Every buffer of the
+// build lives on ONE stream, so a block can be handed out again the moment it is freed (stream order
+// serialises the old user before the new one); no driver call sits on the build's critical path once
+// the slabs exist.  (cudaMallocAsync's pool was measured to re-map physical memory between builds:
+// 2-3x run-to-run variance on the 16K^3 workload.)
 struct Pool {
 	cudaStream_t stream = nullptr;
 	size_t live = 0, peak = 0;
+	struct Slab { char* base; size_t size; };
+	struct Free { size_t slab; size_t off; size_t size; };
+	std::vector<Slab> slabs;
+	std::vector<Free> freeList;   // sorted by (slab, off)
+	size_t reserved = 0;
+	size_t nextSlab = 1ull << 30;
+	static size_t round_up(size_t b) { return (b + 511) & ~(size_t)511; }
+
 	void* alloc(size_t bytes) {
-		if (bytes == 0) bytes = 16;
-		void* p = nullptr;
-		SVB_CUDA(cudaMallocAsync(&p, bytes, stream));
-		live += bytes;
-		if (live > peak) peak = live;
-		return p;
+		bytes = round_up(bytes ? bytes : 16);
+		for (int attempt = 0; attempt < 2; ++attempt) {
+			for (size_t i = 0; i < freeList.size(); ++i) {
+				Free& f = freeList[i];
+				if (f.size < bytes) continue;
+				char* p = slabs[f.slab].base + f.off;
+				if (f.size == bytes) freeList.erase(freeList.begin() + i);
+				else { f.off += bytes; f.size -= bytes; }
+				live += bytes;
+				if (live > peak) peak = live;
+				return p;
+			}
+			grow(bytes);
+		}
+		throw Error(SVB_ENOMEM, "device slab allocator: out of memory");
 	}
-	void free(void* p, size_t bytes) {
-		if (!p) return;
-		cudaFreeAsync(p, stream);
-		live -= (bytes == 0 ? 16 : bytes);
+	void free(void* ptr, size_t bytes) {
+		if (!ptr) return;
+		bytes = round_up(bytes ? bytes : 16);
+		char* p = (char*)ptr;
+		size_t si = 0;
+		for (; si < slabs.size(); ++si) if (p >= slabs[si].base && p < slabs[si].base + slabs[si].size) break;
+		if (si == slabs.size()) return;
+		Free nf{si, (size_t)(p - slabs[si].base), bytes};
+		size_t pos = 0;
+		while (pos < freeList.size() && (freeList[pos].slab < nf.slab || (freeList[pos].slab == nf.slab && freeList[pos].off < nf.off))) ++pos;
+		freeList.insert(freeList.begin() + pos, nf);
+		if (pos + 1 < freeList.size() && freeList[pos + 1].slab == nf.slab && nf.off + nf.size == freeList[pos + 1].off) {
+			freeList[pos].size += freeList[pos + 1].size;
+			freeList.erase(freeList.begin() + pos + 1);
+		}
+		if (pos > 0 && freeList[pos - 1].slab == nf.slab && freeList[pos - 1].off + freeList[pos - 1].size == freeList[pos].off) {
+			freeList[pos - 1].size += freeList[pos].size;
+			freeList.erase(freeList.begin() + pos);
+		}
+		live -= bytes;
+	}
+	void grow(size_t need) {
+		size_t want = nextSlab;
+		while (want < need) want <<= 1;
+		size_t freeB = 0, totalB = 0;
+		cudaMemGetInfo(&freeB, &totalB);
+		size_t room = freeB > (1ull << 30) ? freeB - (1ull << 30) : 0;   // leave 1 GiB to the rest of the process
+		if (want > room) want = round_up(need) <= room ? (room & ~(size_t)511) : 0;
+		if (want < need) throw Error(SVB_ENOMEM, "device slab allocator: cannot grow (requested " + std::to_string(need >> 20) + " MiB)");
+		void* p = nullptr;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e != cudaSuccess) {
+			cudaGetLastError();
+			throw Error(SVB_ENOMEM, std::string("cudaMalloc(slab): ") + cudaGetErrorString(e));
+		}
+		slabs.push_back(Slab{(char*)p, want});
+		reserved += want;
+		Free nf{slabs.size() - 1, 0, want};
+		freeList.push_back(nf);   // highest slab index: stays sorted
+		if (nextSlab < (32ull << 30)) nextSlab <<= 1;
+	}
+	// bytes that can still be handed out without exhausting the device
+	size_t headroom() const {
+		size_t freeB = 0, totalB = 0;
+		cudaMemGetInfo(&freeB, &totalB);
+		size_t room = freeB > (1ull << 30) ? freeB - (1ull << 30) : 0;
+		return room + (reserved - live);
+	}
+	void release_all() {
+		for (auto& sl : slabs) cudaFree(sl.base);
+		slabs.clear();
+		freeList.clear();
+		reserved = live = 0;
 	}
 };
 

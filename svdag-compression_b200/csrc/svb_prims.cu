@@ -9,6 +9,8 @@
 
 namespace svb {
 
+std::atomic<uint64_t> g_launches{0};
+
 namespace {
 
 constexpr int SCAN_THREADS = 256;

@@ -9,6 +9,8 @@
 // Layout per level (SoA, nodes in Morton order, tile-major):
 //   code[n]  u64  (tile_local << 3l) | path      tstar[n] u32      mask[n] u8      childBase[n] u32
 // Pairs: tri[p] u32, node[p] u32, hit[p] u8 -- pairs stay sorted by triangle id at every level.
+#include <cstdlib>
+
 #include "svb_internal.cuh"
 #include "svb_sat.cuh"
 #include "svb_voxelize.cuh"
@@ -111,6 +113,146 @@ __global__ void __launch_bounds__(VX_THREADS) k_classify(uint64_t P, const uint3
 	}
 }
 
+// ------------------------------------------------------------------ classify, filtered (default)
+// One thread per pair decides all 8 children.  A cheap FP64 filter, evaluated relative to the PARENT
+// centre and shared between the children, decides every child whose 13 separating-axis inequalities
+// hold or fail with a margin far above any rounding error (tolerances 2^-40 relative, i.e. >= 4000x
+// the worst-case accumulated error of either evaluation order); the few children that sit within
+// that margin of a threshold (exact ties such as a wall lying in a voxel face) are re-decided by the
+// reference-order predicate tri_box_overlap().  The result is therefore bit-identical to testing all
+// 8 children with tri_box_overlap() (k_classify above, kept selectable with SVB_CLASSIFY=exact and
+// compared against in tests/test_gpu_parity.py), at ~1/5 of the FP64 work for large triangles:
+// interior nodes pass all nine edge axes at the parent level and never evaluate them per child.
+__device__ __forceinline__ void node_centre(uint64_t cd, int l, const TileGeom& tg, double& cx, double& cy, double& cz, double& k) {
+	cx = tg.cx; cy = tg.cy; cz = tg.cz;
+	k = tg.rootSide * 0.25;
+	for (int d = l - 1; d >= 0; --d) {
+		int dig = (int)((cd >> (3 * d)) & 7);
+		cx = __dadd_rn(cx, (dig & 4) ? k : -k);
+		cy = __dadd_rn(cy, (dig & 2) ? k : -k);
+		cz = __dadd_rn(cz, (dig & 1) ? k : -k);
+		k *= 0.5;
+	}
+}
+
+// children whose index has bit `b` clear / set
+#define SVB_LO(b) ((b) == 4 ? 0x0Fu : (b) == 2 ? 0x33u : 0x55u)
+#define SVB_HI(b) ((b) == 4 ? 0xF0u : (b) == 2 ? 0xCCu : 0xAAu)
+
+// one edge-cross axis: p = ca*v[A] + cb*v[B] on vertices i and j; per child the centre moves by k*s,
+// so p_child = p_parent - k*(ca*sA + cb*sB); rad = (|ca|+|cb|)*k.
+__device__ __forceinline__ void edge_axis(double ca, double cb, double viA, double viB, double vjA, double vjB, double k, double tol2,
+                                          unsigned bitA, unsigned bitB, unsigned& alive, unsigned& unsure) {
+	double pi = fma(ca, viA, cb * viB), pj = fma(ca, vjA, cb * vjB);
+	double mn = fmin(pi, pj), mx = fmax(pi, pj);
+	double rad = (fabs(ca) + fabs(cb)) * k;
+	double r2 = rad + rad;
+	// |shift| <= rad for every child, so if the parent centre projects strictly inside the triangle's
+	// interval (mn < 0 < mx) no child interval can leave [-rad, rad]: every child overlaps on this axis
+	if (mn < -tol2 && mx > tol2) return;
+	if (mn > r2 + tol2 || mx < -r2 - tol2) { alive = 0; return; }      // no child does
+	double qa = k * ca, qb = k * cb;
+	unsigned m = alive;
+	while (m) {
+		int c = __ffs(m) - 1;
+		m &= m - 1;
+		double sh = ((c & bitA) ? qa : -qa) + ((c & bitB) ? qb : -qb);
+		double lo = mn - sh, hi = mx - sh;
+		if (lo > rad + tol2 || hi < -rad - tol2) alive &= ~(1u << c);
+		else if (!(lo < rad - tol2 && hi > -rad + tol2)) unsure |= 1u << c;
+	}
+}
+
+__global__ void __launch_bounds__(VX_THREADS) k_classify_filtered(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
+                                                                   const uint64_t* __restrict__ code, int l, const TileGeom* __restrict__ tiles,
+                                                                   const float* __restrict__ tris, uint8_t* __restrict__ hit, uint8_t* __restrict__ mask,
+                                                                   unsigned long long* __restrict__ nExact) {
+	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= P) return;
+	const uint32_t t = ptri[p], n = pnode[p];
+	const uint64_t cd = code[n];
+	const TileGeom tg = tiles[(uint32_t)(cd >> (3 * l))];
+	double Cx, Cy, Cz, k;
+	node_centre(cd, l, tg, Cx, Cy, Cz, k);
+	const float* tp = tris + 9ull * t;
+	float tf[9];
+#pragma unroll
+	for (int i = 0; i < 9; ++i) tf[i] = tp[i];
+	const double v0x = (double)tf[0] - Cx, v0y = (double)tf[1] - Cy, v0z = (double)tf[2] - Cz;
+	const double v1x = (double)tf[3] - Cx, v1y = (double)tf[4] - Cy, v1z = (double)tf[5] - Cz;
+	const double v2x = (double)tf[6] - Cx, v2y = (double)tf[7] - Cy, v2z = (double)tf[8] - Cz;
+	const double k2 = k + k;
+	double M = fmax(fmax(fmax(fabs(v0x), fabs(v0y)), fmax(fabs(v0z), fabs(v1x))), fmax(fmax(fabs(v1y), fabs(v1z)), fmax(fabs(v2x), fmax(fabs(v2y), fabs(v2z))))) + k2;
+	const double eps = 9.094947017729282e-13;   // 2^-40
+	const double tol1 = M * eps, tol2 = M * tol1, tol3 = M * tol2;
+	unsigned alive = 0xFFu, unsure = 0;
+	// --- box axes: child with bit clear sits at -k, with bit set at +k
+#define SVB_BOX_AXIS(a0, a1, a2, BIT)                                                          \
+	{                                                                                          \
+		double mn = fmin(fmin(a0, a1), a2), mx = fmax(fmax(a0, a1), a2);                       \
+		if (mn > tol1 || mx < -k2 - tol1) alive &= ~SVB_LO(BIT);                               \
+		else if (!(mn < -tol1 && mx > -k2 + tol1)) unsure |= SVB_LO(BIT);                      \
+		if (mn > k2 + tol1 || mx < -tol1) alive &= ~SVB_HI(BIT);                               \
+		else if (!(mn < k2 - tol1 && mx > tol1)) unsure |= SVB_HI(BIT);                        \
+	}
+	SVB_BOX_AXIS(v0x, v1x, v2x, 4)
+	SVB_BOX_AXIS(v0y, v1y, v2y, 2)
+	SVB_BOX_AXIS(v0z, v1z, v2z, 1)
+#undef SVB_BOX_AXIS
+	if (alive) {
+		const double e0x = v1x - v0x, e0y = v1y - v0y, e0z = v1z - v0z;
+		const double e1x = v2x - v1x, e1y = v2y - v1y, e1z = v2z - v1z;
+		// --- plane: overlap <=> |N.v0| <= k*(|Nx|+|Ny|+|Nz|)
+		const double nx = fma(e0y, e1z, -(e0z * e1y)), ny = fma(e0z, e1x, -(e0x * e1z)), nz = fma(e0x, e1y, -(e0y * e1x));
+		const double g = fma(nx, v0x, fma(ny, v0y, nz * v0z));
+		const double r = k * (fabs(nx) + fabs(ny) + fabs(nz));
+		const double dx = k * nx, dy = k * ny, dz = k * nz;
+		unsigned m = alive;
+		while (m) {
+			int c = __ffs(m) - 1;
+			m &= m - 1;
+			double gc = fabs(g - (((c & 4) ? dx : -dx) + ((c & 2) ? dy : -dy) + ((c & 1) ? dz : -dz))) - r;
+			if (gc > tol3) alive &= ~(1u << c);
+			else if (gc > -tol3) unsure |= 1u << c;
+		}
+		if (alive) {
+			const double e2x = v0x - v2x, e2y = v0y - v2y, e2z = v0z - v2z;
+			// edge 0: X01(v0,v2)  Y02(v0,v2)  Z12(v1,v2)      p_X = ez*vy - ey*vz, p_Y = -ez*vx + ex*vz, p_Z = ey*vx - ex*vy
+			edge_axis(e0z, -e0y, v0y, v0z, v2y, v2z, k, tol2, 2, 1, alive, unsure);
+			if (alive) edge_axis(-e0z, e0x, v0x, v0z, v2x, v2z, k, tol2, 4, 1, alive, unsure);
+			if (alive) edge_axis(e0y, -e0x, v1x, v1y, v2x, v2y, k, tol2, 4, 2, alive, unsure);
+			// edge 1: X01(v0,v2)  Y02(v0,v2)  Z0(v0,v1)
+			if (alive) edge_axis(e1z, -e1y, v0y, v0z, v2y, v2z, k, tol2, 2, 1, alive, unsure);
+			if (alive) edge_axis(-e1z, e1x, v0x, v0z, v2x, v2z, k, tol2, 4, 1, alive, unsure);
+			if (alive) edge_axis(e1y, -e1x, v0x, v0y, v1x, v1y, k, tol2, 4, 2, alive, unsure);
+			// edge 2: X2(v0,v1)  Y1(v0,v1)  Z12(v1,v2)
+			if (alive) edge_axis(e2z, -e2y, v0y, v0z, v1y, v1z, k, tol2, 2, 1, alive, unsure);
+			if (alive) edge_axis(-e2z, e2x, v0x, v0z, v1x, v1z, k, tol2, 4, 1, alive, unsure);
+			if (alive) edge_axis(e2y, -e2x, v1x, v1y, v2x, v2y, k, tol2, 4, 2, alive, unsure);
+		}
+	}
+	unsure &= alive;
+	unsigned m = alive & ~unsure;
+	if (unsure) {
+		unsigned u = unsure, ne = 0;
+		while (u) {
+			int c = __ffs(u) - 1;
+			u &= u - 1;
+			++ne;
+			double cx = __dadd_rn(Cx, (c & 4) ? k : -k), cy = __dadd_rn(Cy, (c & 2) ? k : -k), cz = __dadd_rn(Cz, (c & 1) ? k : -k);
+			if (tri_box_overlap(cx, cy, cz, k, tf)) m |= 1u << c;
+		}
+		if (nExact) atomicAdd(nExact, (unsigned long long)ne);
+	}
+	hit[p] = (uint8_t)m;
+	if (m) {
+		unsigned cur = mask[n];
+		if ((cur & m) != m) atomicOr(reinterpret_cast<unsigned*>(mask) + (n >> 2), m << (8 * (n & 3)));
+	}
+}
+#undef SVB_LO
+#undef SVB_HI
+
 // children of node n: contiguous at childBase[n], ascending child index == Morton order
 __global__ void __launch_bounds__(VX_THREADS) k_children(uint64_t N, const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask,
                                                           const uint32_t* __restrict__ childBase, uint64_t* __restrict__ ccode) {
@@ -151,9 +293,23 @@ __global__ void __launch_bounds__(VX_THREADS) k_emit(uint64_t P, const uint32_t*
 	}
 }
 
+// nodes the next level will hold, per tile (weights for cutting an oversized batch)
+__global__ void __launch_bounds__(VX_THREADS) k_tile_weights(uint64_t N, const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask, int l, uint32_t* __restrict__ w) {
+	uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (n >= N) return;
+	unsigned m = mask[n];
+	if (m) atomicAdd(&w[(uint32_t)(code[n] >> (3 * l))], (uint32_t)__popc(m));
+}
+
 __global__ void k_init_roots(uint32_t ntiles, uint64_t* code, uint32_t* tstar) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < ntiles) { code[i] = i; tstar[i] = 0; }
+}
+
+// SVB_CLASSIFY=exact selects the unfiltered 8-lanes-per-pair kernel (verification of the filter)
+bool classify_exact_only() {
+	const char* e = getenv("SVB_CLASSIFY");
+	return e && e[0] == 'e';
 }
 
 uint64_t read_u64(cudaStream_t s, const uint64_t* d) {
@@ -189,7 +345,7 @@ void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T
 }
 
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
-                    DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t P, uint64_t budget_bytes,
+                    DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t P, uint64_t budget_bytes, uint64_t nodeCap,
                     std::vector<BatchLevel>& lv, uint64_t& pairsTotal) {
 	lv.clear();
 	lv.resize(Lt);
@@ -207,7 +363,10 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		DevBuf<uint8_t> hit(pool, P + 16);
 		if (P) {
 			if (P > (1ull << 59)) throw Error(SVB_ERANGE, "too many pairs");
-			k_classify<<<blocks_for(P * 8, VX_THREADS), VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p);
+			if (classify_exact_only())
+				k_classify<<<blocks_for(P * 8, VX_THREADS), VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p);
+			else
+				k_classify_filtered<<<blocks_for(P, VX_THREADS), VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p, nullptr);
 			SVB_KERNEL_CHECK();
 		}
 		pairsTotal += P;
@@ -220,8 +379,29 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		DevBuf<uint32_t> poff(pool, P);
 		scan_popc8(s, pool, hit.p, P, poff.p, tot.p);
 		uint64_t Pn = read_u64(s, tot.p);
-		if (Nn >= 0xFFFFFFF0ull || Pn >= 0xFFFFFFF0ull) throw BatchTooBig();
-		if (budget_bytes && pool.live + Nn * 13 + Pn * 9 > budget_bytes) throw BatchTooBig();
+		{
+			// will this batch fit all the way down?  Surfaces grow ~4x per level; use the observed ratio.
+			const int remaining = (Lt - 1) - (l + 1);
+			double growth = (l >= 2 && L.n) ? (double)Nn / (double)L.n : 4.0;
+			if (growth < 2.0) growth = 2.0;
+			if (growth > 5.0) growth = 5.0;
+			double estLeaf = (double)Nn;
+			for (int r = 0; r < remaining; ++r) estLeaf *= growth;
+			bool hard = Nn >= 0xFFFFFFF0ull || Pn >= 0xFFFFFFF0ull || (budget_bytes && pool.live + Nn * 13 + Pn * 9 > budget_bytes);
+			bool predicted = ntiles > 1 && l >= 2 && nodeCap && estLeaf > (double)nodeCap;
+			if (hard || predicted) {
+				BatchTooBig e;
+				e.level = l + 1; e.remaining = remaining; e.growth = growth;
+				DevBuf<uint32_t> w(pool, ntiles);
+				w.zero();
+				k_tile_weights<<<blocks_for(L.n, VX_THREADS), VX_THREADS, 0, s>>>(L.n, L.code.p, L.mask.p, l, w.p);
+				SVB_KERNEL_CHECK();
+				e.weight.resize(ntiles);
+				SVB_CUDA(cudaMemcpyAsync(e.weight.data(), w.p, ntiles * 4ull, cudaMemcpyDeviceToHost, s));
+				SVB_CUDA(cudaStreamSynchronize(s));
+				throw e;
+			}
+		}
 		BatchLevel& C = lv[l + 1];
 		C.n = Nn;
 		C.code.reset(pool, Nn);

@@ -4,7 +4,14 @@
 
 namespace svb {
 
-struct BatchTooBig {};   // thrown when a tile batch outgrows its buffers: the caller halves the batch
+// Thrown (before anything is reduced) when a tile batch would outgrow its buffers.  Carries the
+// per-tile node counts of the level it stopped at so the caller can cut the batch by weight.
+struct BatchTooBig {
+	int level = -1;                   // tile-local level the weights were taken at (-1: none)
+	int remaining = 0;                // levels still to descend from there to the leaf level
+	double growth = 4.0;              // observed node growth per level
+	std::vector<uint32_t> weight;     // nodes per tile of the batch at `level`
+};
 
 struct TileGridHost {    // regular grid of tile cubes over the root cube (G = 2^(step+1) per axis; 1 for step 0)
 	double ox = 0, oy = 0, oz = 0;   // min corner of the root cube
@@ -18,7 +25,7 @@ void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T
 
 // Level-synchronous SVO build of `ntiles` sub-octrees of Lt levels each.  Consumes the root pairs.
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
-                    DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t P, uint64_t budget_bytes,
+                    DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t P, uint64_t budget_bytes, uint64_t nodeCap,
                     std::vector<BatchLevel>& lv, uint64_t& pairsTotal);
 
 }  // namespace svb

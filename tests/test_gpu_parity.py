@@ -124,3 +124,24 @@ def test_empty_scene(pkg):
     st = t.build(5, 0, bbox=(np.zeros(3), np.ones(3)))
     assert st["nTotalVoxels"] == 0 and st["nNodesDAG"] == 1
     assert t.level_sizes() == [1, 0, 0, 0, 0]
+
+
+@pytest.mark.parametrize("mesh,kw,levels,step", [
+    ("city", dict(lots=16), 10, 3),
+    ("terrain", dict(n=128), 10, 2),
+    ("sphere_menger", dict(n_lat=48, n_lon=96, sponge_level=2), 9, 0),
+], ids=["city", "terrain", "spongeball"])
+def test_filtered_classifier_equals_exact_predicate(pkg, meshgen, mesh, kw, levels, step, monkeypatch):
+    """The FP64 interval filter in front of the SAT predicate must never change a decision: a build
+    with every child decided by the reference-order predicate (SVB_CLASSIFY=exact) gives the same
+    octree, node for node.  (city: walls lying exactly in voxel faces -> many exact ties.)"""
+    tris = meshgen.make_mesh(mesh, **kw)
+    a = pkg.GeomOctree(tris)
+    sa = a.build(levels, step)
+    monkeypatch.setenv("SVB_CLASSIFY", "exact")
+    b = pkg.GeomOctree(tris)
+    sb = b.build(levels, step)
+    monkeypatch.delenv("SVB_CLASSIFY")
+    for k in ("nTotalVoxels", "nNodesSVO", "nNodesDAG", "nPairsTotal"):
+        assert sa[k] == sb[k], k
+    _assert_levels_equal(a.levels_host(), b.levels_host(), "filtered vs exact")
