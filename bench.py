@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- mesh -> SSVDAG build on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one full pass of the hot path over the workload: svb_build (voxelize + per-level DAG
+reduction) followed by svb_to_sdag (mirror-symmetry reduction), i.e. triangle soup -> SSVDAG node
+arrays.  `value` is measured with the triangle soup already resident in HBM; `e2e` goes through the
+public C ABI with HOST buffers every step (H2D of the triangles, build, D2H of the SSVDAG levels and
+the host-side .ssvdag encoding).  `--impl reference` times the UNMODIFIED reference svbuilder
+(oracle/_ref/svbuilder_ref, compiled from /root/reference by oracle/Makefile) on the host cores, on
+a bounded sample of the same workload (see WORKLOADS[*]["cpu_sample"]).
+
+Default workload: BASELINE.json configs[2], the configuration its metric is quoted on -- the
+procedural city (256x256 lots, ~11 M triangles) at 16384^3 (levels 14, step 4); it fits one B200
+(the build streams it through ~20 tile batches).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: mesh generator + args, octree levels, build step, and the bounded CPU sample
+    "city_16k": dict(mesh="city", kw=dict(lots=256), levels=14, step=4, grid="16384^3",
+                     cpu_sample=dict(mesh="city", kw=dict(lots=32), levels=11, step=2,
+                                     note="same generator at lots=32, 2048^3 (levels 11, step 2): every lot spans 64 voxels as in the full workload; 1/64 of its ground area")),
+    "terrain_4k": dict(mesh="terrain", kw=dict(n=1024), levels=12, step=3, grid="4096^3",
+                       cpu_sample=dict(mesh="terrain", kw=dict(n=257), levels=10, step=2,
+                                       note="same generator at n=257, 1024^3 (levels 10, step 2): 4 voxels per grid cell as in the full workload")),
+    "spongeball_1k": dict(mesh="sphere_menger", kw=dict(), levels=10, step=1, grid="1024^3",
+                          cpu_sample=dict(mesh="sphere_menger", kw=dict(), levels=10, step=1, note="the full workload")),
+    "city_small": dict(mesh="city", kw=dict(lots=32), levels=11, step=2, grid="2048^3",
+                       cpu_sample=dict(mesh="city", kw=dict(lots=16), levels=10, step=2, note="lots=16 at 1024^3")),
+}
+METRIC = "mesh->SSVDAG build throughput (Gvoxel/s; BASELINE.json: build time at 16K^3 + dedup HBM GB/s vs peak)"
+
+
+def load_pkg():
+    import __graft_entry__ as g
+    return g._pkg()
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device_index=0):
+        self.dev = device_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.dev)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------- reference arm
+def run_reference_once(orc, tris, levels, step, threads):
+    with tempfile.TemporaryDirectory() as td:
+        r = orc.run_reference(td, tris, levels, step, threads=threads)
+    vox = int(re.search(r"Voxels:\s+.*\((\d+)\)", r["log"]).group(1))
+    return vox, r["seconds"]
+
+
+def run_port_once(orc, tris, levels, step):
+    t0 = time.time()
+    o = orc.OracleOctree(tris)
+    o.build(levels, step)
+    o.to_sdag()
+    o.encode("ssvdag")
+    return o.stat("nTotalVoxels"), time.time() - t0
+
+
+def cpu_arm(pkg, wl, steps, warmup):
+    """Times the reference's own CPU svbuilder (or, if its binary did not travel, the oracle port)."""
+    from oracle import oracle as orc
+    cs = wl["cpu_sample"]
+    tris = pkg.meshgen.make_mesh(cs["mesh"], **cs["kw"])
+    cores = os.cpu_count() or 1
+    use_ref = orc.REF_BIN.exists()
+    kind = "reference" if use_ref else "port"
+    if not use_ref:
+        cores = 1
+    times, vox = [], 0
+    for i in range(warmup + steps):
+        if use_ref:
+            vox, dt = run_reference_once(orc, tris, cs["levels"], cs["step"], cores)
+        else:
+            vox, dt = run_port_once(orc, tris, cs["levels"], cs["step"])
+        if i >= warmup:
+            times.append(dt)
+    avg = sum(times) / len(times)
+    return {"value": vox / avg / 1e9, "unit": "Gvoxel/s", "cores": cores, "kind": kind,
+            "sample": f"{cs['note']}; {tris.shape[0]} triangles, {vox} voxels, svbuilder wall {avg:.2f} s/step "
+                      f"(bincache load + buildDAG + toSDAG + encoders + file writes), OMP_NUM_THREADS={cores}",
+            "seconds_per_step": avg, "voxels": vox}
+
+
+# ------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("SVB_BENCH_WORKLOAD", "city_16k"), choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"{args.workload}: procedural {wl['mesh']} mesh {wl['kw']} at {wl['grid']} (levels {wl['levels']}, step {wl['step']}) -> SVDAG -> SSVDAG",
+              "l2_policy": "inputs larger than L2 (every pass streams GBs of freshly written pair/node arrays)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        pkg = load_pkg()
+        steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+        cb = cpu_arm(pkg, wl, steps, warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "Gvoxel/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": warmup, "ms_per_step": cb["seconds_per_step"] * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "Gvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    pkg = load_pkg()
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this framework has no CPU fallback"}))
+        return 2
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    tris = pkg.meshgen.make_mesh(wl["mesh"], **wl["kw"])
+    T = tris.shape[0]
+    v = tris.reshape(-1, 3)
+    bbox = (v.min(axis=0).astype(np.float64), v.max(axis=0).astype(np.float64))
+    L, S = wl["levels"], wl["step"]
+    pinned = torch.from_numpy(tris.reshape(-1)).pin_memory()
+
+    oct_ = pkg.GeomOctree(device=local_rank)
+    shard = dict(rank=rank, world=world) if world > 1 else {}
+
+    def step_resident():
+        st = oct_.build(L, S, bbox=bbox, **shard)
+        sd = oct_.to_sdag()
+        return st, sd
+
+    def step_e2e():
+        oct_.set_triangles_ptr(pinned.data_ptr(), T)          # H2D from pinned host memory
+        st = oct_.build(L, S, bbox=bbox, **shard)
+        sd = oct_.to_sdag()
+        img = pkg.encoders.encode(oct_, "ssvdag")             # D2H of the SSVDAG levels + host encoding
+        return st, sd, img
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input timing (value)
+    oct_.set_triangles_ptr(pinned.data_ptr(), T)
+    for _ in range(args.warmup):
+        step_resident()
+    oct_.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    prof, launches = [], 0
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        st, sd = step_resident()
+        prof += oct_.profile()
+        launches += st["nKernelLaunches"] + sd["nKernelLaunches"]
+        dev_ms += st["msTotal"] + sd["msSdag"]
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clocks = sampler.stop()
+    oct_.set_profiling(False)
+
+    # ---- end-to-end timing through the public API with host buffers
+    step_e2e()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        st_e, sd_e, img = step_e2e()
+    barrier()
+    elapsed_e2e = time.perf_counter() - t1
+    d2h = sum(n * (1 + 32 + 3) for n in oct_.level_sizes())
+
+    if world > 1:
+        tmax = torch.tensor([elapsed, elapsed_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        elapsed, elapsed_e2e = float(tmax[0]), float(tmax[1])
+
+    vox = st["nTotalVoxels"]
+    sec = elapsed / args.steps
+    sec_e2e = elapsed_e2e / args.steps
+    # ---- roofline of the dominant dedup kernel (k_leaf_min at the leaf level: the largest launch of the family
+    #      BASELINE.json's "dedup HBM GB/s vs peak" names); per-family table alongside
+    peak, peak_src = measured_peak_gbs()
+    fam = {}
+    for r in prof:
+        f = fam.setdefault(r["name"], {"launches": 0, "ms": 0.0, "units": 0, "bytes_survey": 0.0})
+        f["launches"] += 1; f["ms"] += r["ms"]; f["units"] += r["n_in"]; f["bytes_survey"] += r["bytes"]
+    leaf = fam.get("dedup_leaf")
+    roof = None
+    if leaf and leaf["ms"] > 0:
+        per_unit = 13.0   # leaf node = 1 B mask + 4 B first-touch triangle + 8 B Morton code, read once
+        alg = per_unit * leaf["units"]
+        ach = alg / (leaf["ms"] * 1e-3) / 1e9
+        roof = {"kernel": "k_leaf_min (dedup, leaf level)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peak_src, "bytes_per_unit": per_unit,
+                "units_per_launch": leaf["units"] / leaf["launches"], "avg_launch_ms": leaf["ms"] / leaf["launches"],
+                "achieved_with_survey_formula_37B_per_node": leaf["bytes_survey"] / (leaf["ms"] * 1e-3) / 1e9,
+                "note": "SURVEY.md 8(d) charges 37 B/node for a materialised 33-byte key; this layout never materialises it and reads 13 B/node"}
+    kernels = {k: {"launches": f["launches"] // args.steps, "ms_per_step": f["ms"] / args.steps, "units_per_step": f["units"] // args.steps}
+               for k, f in sorted(fam.items())}
+
+    line = {"metric": METRIC, "value": vox / sec / 1e9, "unit": "Gvoxel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config, "build_s": sec, "device_ms_per_step": dev_ms / args.steps,
+            "voxels": vox, "triangles": int(T), "nodes": {"svo": st["nNodesSVO"], "dag": st["nNodesDAG"], "sdag": sd["nNodesSDAG"]},
+            "tiles": st["nTiles"], "batches": st["nBatches"], "pairs": st["nPairsTotal"], "exact_retests": st["nExactTests"],
+            "e2e": {"value": vox / sec_e2e / 1e9, "unit": "Gvoxel/s", "h2d_bytes_per_step": int(T) * 36, "d2h_bytes_per_step": int(d2h),
+                    "seconds_per_step": sec_e2e, "ssvdag_bytes": len(img)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels}
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                cb = cpu_arm(pkg, wl, 1, 0)
+                line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:  # the baseline is reported, never required
+                line["cpu_baseline"] = {"value": None, "unit": "Gvoxel/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -23,8 +23,8 @@ for w in which:
         t1 = time.time()
         sd = t.to_sdag()
         t2 = time.time()
-        print("  it%d build %.3fs sdag %.3fs | vox %.3e svo %.3e dag %d sdag %d tiles %d batches %d pairs %.3e launches %d | ms total %.1f vox %.1f dedup %.1f fin %.1f sdag %.1f" % (
-            it, t1 - t0, t2 - t1, st["nTotalVoxels"], st["nNodesSVO"], st["nNodesDAG"], sd["nNodesSDAG"], st["nTiles"], st["nBatches"], st["nPairsTotal"], st["nKernelLaunches"],
+        print("  it%d build %.3fs sdag %.3fs | vox %.3e svo %.3e dag %d sdag %d tiles %d batches %d pairs %.3e exact %.3e launches %d | ms total %.1f vox %.1f dedup %.1f fin %.1f sdag %.1f" % (
+            it, t1 - t0, t2 - t1, st["nTotalVoxels"], st["nNodesSVO"], st["nNodesDAG"], sd["nNodesSDAG"], st["nTiles"], st["nBatches"], st["nPairsTotal"], st["nExactTests"], st["nKernelLaunches"],
             st["msTotal"], st["msVoxelize"], st["msDedup"], st["msFinalize"], sd["msSdag"]), flush=True)
     prof = t.profile()
     agg = {}

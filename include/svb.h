@@ -47,6 +47,7 @@ typedef struct svb_stats {
 	float    bboxF[6];          /* Octree::_bbox (float-converted, geom_octree.cpp:177-180) */
 	double   msVoxelize, msDedup, msFinalize, msSdag, msCrossMerge, msTotal; /* CUDA-event times of the last call */
 	uint64_t nKernelLaunches;   /* CUDA kernels launched by the last svb_build / svb_to_sdag / svb_cross_merge call */
+	uint64_t nExactTests;       /* (triangle, child) tests the interval filter left to the reference-order predicate */
 } svb_stats;
 
 typedef struct svb_ctx svb_ctx;

@@ -24,7 +24,7 @@ class Stats(C.Structure):
                                            "nNodesLastLevDAG", "nCrossLevelMerged", "nNodes", "nTiles", "nBatches", "nPairsTotal")]
     _fields_ += [("rootSide", C.c_double), ("bboxF", C.c_float * 6)]
     _fields_ += [(n, C.c_double) for n in ("msVoxelize", "msDedup", "msFinalize", "msSdag", "msCrossMerge", "msTotal")]
-    _fields_ += [("nKernelLaunches", C.c_uint64)]
+    _fields_ += [("nKernelLaunches", C.c_uint64), ("nExactTests", C.c_uint64)]
 
     def as_dict(self):
         d = {}
@@ -111,6 +111,11 @@ class GeomOctree:
         t = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 9)
         self._tris = t
         self._check(self._L.svb_set_triangles(self._h, t.ctypes.data, t.shape[0]))
+
+    def set_triangles_ptr(self, host_ptr: int, ntris: int):
+        """Raw host pointer (e.g. pinned memory) to ntris*9 float32; copied H2D during the call."""
+        self._tris = None
+        self._check(self._L.svb_set_triangles(self._h, host_ptr, ntris))
 
     def set_triangles_device(self, dev_ptr: int, ntris: int):
         self._check(self._L.svb_set_triangles_device(self._h, dev_ptr, ntris))

@@ -107,6 +107,7 @@ struct BuildState {
 	std::vector<LevelTable> tables;
 	std::vector<int> obits;
 	DevBuf<uint64_t> dVoxels;
+	DevBuf<uint64_t> dExact;   // children the filter could not decide (re-tested with the reference-order predicate)
 	DevBuf<uint32_t> rootKey;
 	int rootChildMode = CH_UID_U32;
 	uint64_t nNodesSVO = 0, nLastLevSVO = 0, pairs = 0, nBatches = 0;
@@ -174,7 +175,7 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 		DevBuf<uint32_t> ptri, pnode;
 		uint64_t P = 0;
 		make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, (int)a, (int)b, ptri, pnode, P);
-		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, P, budget, nodeCap, lv, pairs);
+		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, P, budget, nodeCap, lv, pairs, B.dExact.p);
 		ps.done(pairs, 36.0 * (double)c->T + 9.0 * (double)lv[Lt - 1].n);
 		B.msVox += tm.stop();
 	}
@@ -275,6 +276,8 @@ void do_build(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], const
 	for (uint32_t g = 1; g < L; ++g) table_init(s, c->pool, B.tables[g], kind_of(g, L));
 	B.dVoxels.reset(c->pool, 1);
 	B.dVoxels.zero();
+	B.dExact.reset(c->pool, 1);
+	B.dExact.zero();
 	B.rootKey.reset(c->pool, 8);
 	B.rootKey.fill_ff();
 
@@ -445,6 +448,7 @@ void do_build(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], const
 	st.nTiles = nTiles;
 	st.nBatches = B.nBatches;
 	st.nPairsTotal = B.pairs;
+	st.nExactTests = download(s, B.dExact.p, 1)[0];
 	st.rootSide = rootSide;
 	memcpy(st.bboxF, bboxF, sizeof(bboxF));
 	st.msVoxelize = B.msVox;

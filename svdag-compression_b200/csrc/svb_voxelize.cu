@@ -141,8 +141,12 @@ __device__ __forceinline__ void node_centre(uint64_t cd, int l, const TileGeom& 
 
 // one edge-cross axis: p = ca*v[A] + cb*v[B] on vertices i and j; per child the centre moves by k*s,
 // so p_child = p_parent - k*(ca*sA + cb*sB); rad = (|ca|+|cb|)*k.
-__device__ __forceinline__ void edge_axis(double ca, double cb, double viA, double viB, double vjA, double vjB, double k, double tol2,
+// `degenerate`: both edge components are differences of bitwise-equal float inputs, hence exactly 0
+// for any box centre in the reference-order predicate too: p0 = p1 = +-0, rad = 0, and neither
+// "min > rad" nor "max < -rad" can hold -- the axis never separates (axis-aligned edges).
+__device__ __forceinline__ void edge_axis(bool degenerate, double ca, double cb, double viA, double viB, double vjA, double vjB, double k, double tol2,
                                           unsigned bitA, unsigned bitB, unsigned& alive, unsigned& unsure) {
+	if (degenerate) return;
 	double pi = fma(ca, viA, cb * viB), pj = fma(ca, vjA, cb * vjB);
 	double mn = fmin(pi, pj), mx = fmax(pi, pj);
 	double rad = (fabs(ca) + fabs(cb)) * k;
@@ -217,18 +221,22 @@ __global__ void __launch_bounds__(VX_THREADS) k_classify_filtered(uint64_t P, co
 		}
 		if (alive) {
 			const double e2x = v0x - v2x, e2y = v0y - v2y, e2z = v0z - v2z;
+			// bitwise-equal input coordinates => that edge component is exactly zero in either evaluation
+			const bool x01 = tf[0] == tf[3], y01 = tf[1] == tf[4], z01 = tf[2] == tf[5];
+			const bool x12 = tf[3] == tf[6], y12 = tf[4] == tf[7], z12 = tf[5] == tf[8];
+			const bool x20 = tf[6] == tf[0], y20 = tf[7] == tf[1], z20 = tf[8] == tf[2];
 			// edge 0: X01(v0,v2)  Y02(v0,v2)  Z12(v1,v2)      p_X = ez*vy - ey*vz, p_Y = -ez*vx + ex*vz, p_Z = ey*vx - ex*vy
-			edge_axis(e0z, -e0y, v0y, v0z, v2y, v2z, k, tol2, 2, 1, alive, unsure);
-			if (alive) edge_axis(-e0z, e0x, v0x, v0z, v2x, v2z, k, tol2, 4, 1, alive, unsure);
-			if (alive) edge_axis(e0y, -e0x, v1x, v1y, v2x, v2y, k, tol2, 4, 2, alive, unsure);
+			edge_axis(z01 && y01, e0z, -e0y, v0y, v0z, v2y, v2z, k, tol2, 2, 1, alive, unsure);
+			if (alive) edge_axis(z01 && x01, -e0z, e0x, v0x, v0z, v2x, v2z, k, tol2, 4, 1, alive, unsure);
+			if (alive) edge_axis(y01 && x01, e0y, -e0x, v1x, v1y, v2x, v2y, k, tol2, 4, 2, alive, unsure);
 			// edge 1: X01(v0,v2)  Y02(v0,v2)  Z0(v0,v1)
-			if (alive) edge_axis(e1z, -e1y, v0y, v0z, v2y, v2z, k, tol2, 2, 1, alive, unsure);
-			if (alive) edge_axis(-e1z, e1x, v0x, v0z, v2x, v2z, k, tol2, 4, 1, alive, unsure);
-			if (alive) edge_axis(e1y, -e1x, v0x, v0y, v1x, v1y, k, tol2, 4, 2, alive, unsure);
+			if (alive) edge_axis(z12 && y12, e1z, -e1y, v0y, v0z, v2y, v2z, k, tol2, 2, 1, alive, unsure);
+			if (alive) edge_axis(z12 && x12, -e1z, e1x, v0x, v0z, v2x, v2z, k, tol2, 4, 1, alive, unsure);
+			if (alive) edge_axis(y12 && x12, e1y, -e1x, v0x, v0y, v1x, v1y, k, tol2, 4, 2, alive, unsure);
 			// edge 2: X2(v0,v1)  Y1(v0,v1)  Z12(v1,v2)
-			if (alive) edge_axis(e2z, -e2y, v0y, v0z, v1y, v1z, k, tol2, 2, 1, alive, unsure);
-			if (alive) edge_axis(-e2z, e2x, v0x, v0z, v1x, v1z, k, tol2, 4, 1, alive, unsure);
-			if (alive) edge_axis(e2y, -e2x, v1x, v1y, v2x, v2y, k, tol2, 4, 2, alive, unsure);
+			if (alive) edge_axis(z20 && y20, e2z, -e2y, v0y, v0z, v1y, v1z, k, tol2, 2, 1, alive, unsure);
+			if (alive) edge_axis(z20 && x20, -e2z, e2x, v0x, v0z, v1x, v1z, k, tol2, 4, 1, alive, unsure);
+			if (alive) edge_axis(y20 && x20, e2y, -e2x, v1x, v1y, v2x, v2y, k, tol2, 4, 2, alive, unsure);
 		}
 	}
 	unsure &= alive;
@@ -346,7 +354,7 @@ void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T
 
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
                     DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t P, uint64_t budget_bytes, uint64_t nodeCap,
-                    std::vector<BatchLevel>& lv, uint64_t& pairsTotal) {
+                    std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact) {
 	lv.clear();
 	lv.resize(Lt);
 	lv[0].n = ntiles;
@@ -366,7 +374,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 			if (classify_exact_only())
 				k_classify<<<blocks_for(P * 8, VX_THREADS), VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p);
 			else
-				k_classify_filtered<<<blocks_for(P, VX_THREADS), VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p, nullptr);
+				k_classify_filtered<<<blocks_for(P, VX_THREADS), VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p, (unsigned long long*)d_nExact);
 			SVB_KERNEL_CHECK();
 		}
 		pairsTotal += P;

@@ -26,6 +26,6 @@ void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T
 // Level-synchronous SVO build of `ntiles` sub-octrees of Lt levels each.  Consumes the root pairs.
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
                     DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t P, uint64_t budget_bytes, uint64_t nodeCap,
-                    std::vector<BatchLevel>& lv, uint64_t& pairsTotal);
+                    std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact);
 
 }  // namespace svb
