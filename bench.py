@@ -197,7 +197,7 @@ def main():
     pinned = torch.from_numpy(tris.reshape(-1)).pin_memory()
 
     oct_ = pkg.GeomOctree(device=local_rank)
-    shard = dict(rank=rank, world=world) if world > 1 else {}
+    shard = dict(sharded=True) if world > 1 else {}
 
     def step_resident():
         st = oct_.build(L, S, bbox=bbox, **shard)

@@ -73,6 +73,32 @@ int svb_set_triangles_device(svb_ctx* ctx, const float* xyz9_dev, uint64_t ntris
 int svb_build(svb_ctx* ctx, uint32_t levels, uint32_t step,
               const double bbox_min[3], const double bbox_max[3], svb_stats* out);
 
+/* ---- multi-GPU (one context per GPU, one process per GPU) -------------------------------------
+ * GeomOctree::buildDAG's decomposition (geom_octree.cpp:331-378: independent sub-octrees; :397-425:
+ * join + global toDAG) spread over `world` devices.  Protocol, identical on every rank:
+ *   svb_shard_build(rank, world)        builds the base octree (redundantly) and this rank's share of the
+ *                                       sub-octrees, reduced into rank-local tables;
+ *   svb_shard_info                      levels to merge [first,last] (= step+1 .. levels-1), tile count, and
+ *                                       this rank's counters {leafVoxels, nodesSVO, lastLevSVO, pairs, exact};
+ *   for level = last .. first:          svb_shard_level_count -> n records of recBytes each;
+ *                                       svb_shard_export_level writes them to a DEVICE buffer; the caller
+ *                                       all-gathers (NCCL) into world rows of strideBytes;
+ *                                       svb_shard_import_level rebuilds the identical global table everywhere;
+ *   svb_shard_export_roots / all-gather / svb_shard_import_roots   (nTiles x u32 per rank);
+ *   svb_shard_finish(totals)            totals = the counters summed over ranks; reduces the base octree,
+ *                                       ranks all levels, leaves every rank in state DAG with the same octree
+ *                                       a single-GPU svb_build would have produced.
+ * Device pointers are plain CUDA pointers (e.g. torch tensors' data_ptr()).  world == 1 callers use svb_build. */
+int svb_shard_build(svb_ctx* ctx, uint32_t levels, uint32_t step, const double bbox_min[3], const double bbox_max[3],
+                    uint32_t rank, uint32_t world);
+int svb_shard_info(const svb_ctx* ctx, uint32_t* firstLevel, uint32_t* lastLevel, uint64_t* nTiles, uint64_t counters[5]);
+int svb_shard_level_count(const svb_ctx* ctx, uint32_t level, uint64_t* n, uint32_t* recBytes);
+int svb_shard_export_level(svb_ctx* ctx, uint32_t level, void* d_out);
+int svb_shard_import_level(svb_ctx* ctx, uint32_t level, const void* d_all, const uint64_t* counts, uint64_t strideBytes);
+int svb_shard_export_roots(svb_ctx* ctx, void* d_out);
+int svb_shard_import_roots(svb_ctx* ctx, const void* d_all);
+int svb_shard_finish(svb_ctx* ctx, const uint64_t totals[5], svb_stats* out);
+
 /* GeomOctree::toSDAG(false,false) (geom_octree.cpp:551-697).  DAG -> SDAG. */
 int svb_to_sdag(svb_ctx* ctx, svb_stats* out);
 

@@ -165,104 +165,160 @@ def _lexrank(keys):
 
 
 class Builder:
-    """mesh -> DAG levels, parallel formulation.  levels[l] = dict(mask (U,), child (U,8))."""
+    """mesh -> DAG levels, parallel formulation.  levels[l] = dict(mask (U,), child (U,8)).
+
+    Also speaks the multi-GPU protocol of include/svb.h (shard_* methods) on CPU memory, so that
+    svdag-compression_b200/sharded.py can be exercised over gloo: keys here are structural (nested
+    tuples), records are pickled dicts."""
 
     def __init__(self, tris):
         self.tris = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 9)
         self.stats = {}
 
-    def build(self, L, step, lo=None, hi=None):
+    # ------------------------------------------------------------------ local phase
+    def _dedup_tile(self, lv, tile_seq, lvl0):
+        """bottom-up insert of one tile's levels into the tables; returns per-level keys."""
+        Lt = len(lv)
+        eff = clean_and_effective_masks(lv)
+        ids = [None] * Lt
+        for l in range(Lt - 1, 0 if lvl0 == 0 else -1, -1):
+            ok = order_key(lv, l, tile_seq)
+            keys = []
+            for i in range(len(eff[l])):
+                if eff[l][i] == 0:
+                    keys.append(None)
+                    continue
+                if l == Lt - 1:
+                    key = (int(eff[l][i]),) + (None,) * 8
+                else:
+                    ch, r = [], 0
+                    for c in range(8):
+                        if (lv[l]["mask"][i] >> c) & 1:
+                            ch.append(ids[l + 1][lv[l]["childBase"][i] + r])
+                            r += 1
+                        else:
+                            ch.append(None)
+                    key = (int(eff[l][i]),) + tuple(ch)
+                keys.append(key)
+                o = tuple(int(x) for x in ok[i])
+                tab = self.tables[lvl0 + l]
+                if key not in tab or o < tab[key]:
+                    tab[key] = o
+            ids[l] = keys
+        return ids, eff
+
+    def shard_build(self, L, step, bbox, rank=0, world=1):
         tris = self.tris
         v = tris.reshape(-1, 3)
-        lo = v.min(0).astype(np.float64) if lo is None else np.asarray(lo, np.float64)
-        hi = v.max(0).astype(np.float64) if hi is None else np.asarray(hi, np.float64)
+        lo, hi = bbox if bbox is not None else (v.min(0), v.max(0))
+        lo = np.asarray(lo, np.float64)
+        hi = np.asarray(hi, np.float64)
         all_t = np.arange(len(tris))
         root_side, lf, hf = _float_root_side(lo, hi)
+        self.L, self.step, self.rank, self.world = L, step, rank, world
         self.root_side, self.bboxF = root_side, (lf, hf)
-        tables = [dict() for _ in range(L)]    # level -> {key tuple: [min order key tuple, mask, children tuple]}
-        n_svo = 0
-
-        def dedup_tile(lv, tile_seq, lvl0):
-            """bottom-up insert of one tile's levels into the global tables; returns per-level slot keys."""
-            Lt = len(lv)
-            eff = clean_and_effective_masks(lv)
-            ids = [None] * Lt
-            for l in range(Lt - 1, 0 if lvl0 == 0 else -1, -1):
-                ok = order_key(lv, l, tile_seq)
-                keys = []
-                for i in range(len(eff[l])):
-                    if eff[l][i] == 0:
-                        keys.append(None)
-                        continue
-                    if l == Lt - 1:
-                        key = (int(eff[l][i]),) + (None,) * 8
-                    else:
-                        ch, r = [], 0
-                        for c in range(8):
-                            if (lv[l]["mask"][i] >> c) & 1:
-                                ch.append(ids[l + 1][lv[l]["childBase"][i] + r])
-                                r += 1
-                            else:
-                                ch.append(None)
-                        key = (int(eff[l][i]),) + tuple(ch)
-                    keys.append(key)
-                    o = tuple(int(x) for x in ok[i])
-                    tab = tables[lvl0 + l]
-                    if key not in tab or o < tab[key]:
-                        tab[key] = o
-                ids[l] = keys
-            return ids, eff
-
+        self.tables = [dict() for _ in range(L)]
+        self.n_svo = 0
+        self.leaf_vox = 0
+        self.top = None
+        centre = (lo + hi) * 0.5
         if step == 0:
-            centre = (lo + hi) * 0.5
+            assert world == 1
             lv = voxelize_tile(tris, all_t, centre, root_side, L)
-            n_svo = sum(len(x["path"]) for x in lv[1:])
-            ids, eff = dedup_tile(lv, 0, 0)
-            self.stats["nTotalVoxels"] = int(sum(bin(int(m)).count("1") for m in eff[L - 1]))
-            root_children = (lv[0], ids, eff)
-            top = None
-        else:
-            s1 = step + 1
-            centre = (lo + hi) * 0.5
-            base = voxelize_tile(tris, all_t, centre, root_side, s1)
-            beff = clean_and_effective_masks(base)
-            n_svo = sum(len(x["path"]) for x in base[1:])
-            # SVO creation order of the base leaf level
-            rank, order = _lexrank(order_key(base, s1 - 1)) if s1 > 1 else (np.zeros(1, np.int64), np.zeros(1, np.int64))
-            lhs = root_side / float(1 << s1)      # getHalfSideD(stepLevels - 1)
-            tile_root_key = {}
-            nvox = int(sum(bin(int(m)).count("1") for m in beff[s1 - 1]))
-            seq = 0
-            # leaf-node centres were accumulated while descending: base[s1-1]["centre"]
-            for i in order:
-                for j in range(7, -1, -1):
-                    if not (beff[s1 - 1][i] >> j) & 1:
-                        continue
+            self.n_svo = sum(len(x["path"]) for x in lv[1:])
+            ids, eff = self._dedup_tile(lv, 0, 0)
+            self.leaf_vox = int(sum(bin(int(m)).count("1") for m in eff[L - 1]))
+            self.root_children = (lv[0], ids, eff)
+            self.ntiles = 1
+            return
+        s1 = step + 1
+        base = voxelize_tile(tris, all_t, centre, root_side, s1)
+        beff = clean_and_effective_masks(base)
+        self.base_svo = sum(len(x["path"]) for x in base[1:])
+        rank_, order = _lexrank(order_key(base, s1 - 1)) if s1 > 1 else (np.zeros(1, np.int64), np.zeros(1, np.int64))
+        lhs = root_side / float(1 << s1)      # getHalfSideD(stepLevels - 1)
+        self.base_vox = int(sum(bin(int(m)).count("1") for m in beff[s1 - 1]))
+        self.tile_of = {}                      # (base leaf index, child) -> tile_seq
+        self.tile_root_key = {}                # tile_seq -> key (only tiles built here, until the roots are exchanged)
+        seq = 0
+        for i in order:
+            for j in range(7, -1, -1):
+                if not (beff[s1 - 1][i] >> j) & 1:
+                    continue
+                self.tile_of[(int(i), j)] = seq
+                if seq % world == rank:
                     p1 = base[s1 - 1]["centre"][i]
                     p2 = p1 + np.array([lhs if j & 4 else -lhs, lhs if j & 2 else -lhs, lhs if j & 1 else -lhs])
                     tlo, thi = np.minimum(p1, p2), np.maximum(p1, p2)
                     t_side, _, _ = _float_root_side(tlo, thi)
                     lv = voxelize_tile(tris, all_t, (tlo + thi) * 0.5, t_side, L - s1)
-                    n_svo += sum(len(x["path"]) for x in lv[1:])
-                    ids, eff = dedup_tile(lv, seq, s1)
-                    # the tile root itself is a level-s1 node: dedup it too (not skipped even when it is alone)
-                    nvox += int(sum(bin(int(m)).count("1") for m in eff[-1])) - 1
-                    tile_root_key[(int(i), j)] = ids[0][0]
-                    seq += 1
-            self.stats["nTotalVoxels"] = nvox
-            top = (base, beff, tile_root_key, s1)
-        self.stats["nNodesSVO"] = n_svo
+                    self.n_svo += sum(len(x["path"]) for x in lv[1:])
+                    ids, eff = self._dedup_tile(lv, seq, s1)
+                    self.leaf_vox += int(sum(bin(int(m)).count("1") for m in eff[-1]))
+                    self.tile_root_key[seq] = ids[0][0]
+                seq += 1
+        self.ntiles = seq
+        self.top = (base, beff, s1)
 
-        # ---- finalize: rank every level's table by min order key -> final ids
+    # ------------------------------------------------------------------ exchange (CPU memory)
+    def shard_info(self):
+        s1 = self.step + 1 if self.step else 0
+        return s1, self.L - 1, self.ntiles, [self.leaf_vox, self.n_svo, 0, 0, 0]
+
+    def shard_level_count(self, g):
+        import pickle
+        self._blob = pickle.dumps(self.tables[g])
+        return len(self._blob), 1
+
+    def shard_export_level(self, g, ptr):
+        import ctypes
+        ctypes.memmove(ptr, self._blob, len(self._blob))
+
+    def shard_import_level(self, g, ptr, counts, stride):
+        import ctypes
+        import pickle
+        merged = {}
+        for r, n in enumerate(counts):
+            blob = ctypes.string_at(ptr + r * int(stride), int(n))
+            for key, o in pickle.loads(blob).items():
+                if key not in merged or o < merged[key]:
+                    merged[key] = o
+        self.tables[g] = merged
+
+    def _root_uids(self):
+        s1 = self.step + 1
+        items = sorted(self.tables[s1].items(), key=lambda kv: kv[1])
+        return {key: u for u, (key, _) in enumerate(items)}, [key for key, _ in items]
+
+    def shard_export_roots(self, ptr):
+        uid, _ = self._root_uids()
+        a = np.full(max(self.ntiles, 1), 0xFFFFFFFF, dtype=np.uint32)
+        for seq, key in self.tile_root_key.items():
+            a[seq] = 0xFFFFFFFE if key is None else uid[key]
+        import ctypes
+        ctypes.memmove(ptr, a.ctypes.data, a.nbytes)
+
+    def shard_import_roots(self, ptr):
+        import ctypes
+        n = max(self.ntiles, 1)
+        a = np.frombuffer(ctypes.string_at(ptr, 4 * n * self.world), dtype=np.uint32).reshape(self.world, n).min(axis=0)
+        _, keys = self._root_uids()
+        self.tile_root_key = {seq: (None if a[seq] == 0xFFFFFFFE else keys[a[seq]]) for seq in range(self.ntiles)}
+
+    # ------------------------------------------------------------------ finish
+    def shard_finish(self, totals=None):
+        L, tables = self.L, self.tables
+        leaf_vox, n_svo = (self.leaf_vox, self.n_svo) if totals is None else (int(totals[0]), int(totals[1]))
         final = [dict() for _ in range(L)]
         for l in range(L - 1, 0, -1):
             items = sorted(tables[l].items(), key=lambda kv: kv[1])
             for r, (key, _) in enumerate(items):
                 final[l][key] = r
-        # top part (levels <= step) in step mode: dedup in base SVO order
         levels_out = [None] * L
-        if top is not None:
-            base, beff, tile_root_key, s1 = top
+        if self.top is not None:
+            base, beff, s1 = self.top
+            self.stats["nTotalVoxels"] = self.base_vox + leaf_vox - self.ntiles
+            self.stats["nNodesSVO"] = self.base_svo + n_svo
             ids_top = [None] * s1
             for l in range(s1 - 1, -1, -1):
                 keys = []
@@ -273,8 +329,11 @@ class Builder:
                     ch = []
                     if l == s1 - 1:
                         for c in range(8):
-                            ch.append(("id", final[s1][tile_root_key[(i, c)]]) if (beff[l][i] >> c) & 1 and tile_root_key[(i, c)] is not None
-                                      else (("id", 0) if (beff[l][i] >> c) & 1 else None))
+                            if (beff[l][i] >> c) & 1:
+                                k = self.tile_root_key[self.tile_of[(i, c)]]
+                                ch.append(("id", final[s1][k]) if k is not None else ("id", 0))
+                            else:
+                                ch.append(None)
                     else:
                         r = 0
                         for c in range(8):
@@ -292,13 +351,14 @@ class Builder:
                 if l > 0:
                     items = sorted(tables[l].items(), key=lambda kv: kv[1])
                     final[l] = {key: r for r, (key, _) in enumerate(items)}
-                    # children of the level above refer to final ids of this level
                     ids_top[l] = [None if k is None else ("id", final[l][k]) for k in keys]
                 else:
                     ids_top[l] = keys
             root_key = ids_top[0][0]
         else:
-            lv0, ids, eff = root_children
+            self.stats["nTotalVoxels"] = leaf_vox
+            self.stats["nNodesSVO"] = n_svo
+            lv0, ids, eff = self.root_children
             ch, r = [], 0
             for c in range(8):
                 if (lv0["mask"][0] >> c) & 1:
@@ -309,7 +369,6 @@ class Builder:
             root_key = (int(eff[0][0]),) + tuple(ch)
 
         def resolve(l, key):
-            """children of a level-l key -> final ids of level l+1"""
             out = np.full(8, NULL, dtype=np.uint32)
             for c in range(8):
                 k = key[1 + c]
@@ -327,10 +386,15 @@ class Builder:
                 if l < L - 1:
                     child[r] = resolve(l, key)
             levels_out[l] = {"mask": mask, "child": child}
-        levels_out[0] = {"mask": np.array([root_key[0]], np.uint8), "child": resolve(0, root_key).reshape(1, 8) if L > 1 else np.full((1, 8), NULL, np.uint32)}
+        levels_out[0] = {"mask": np.array([root_key[0]], np.uint8), "child": resolve(0, root_key).reshape(1, 8)}
         self.levels = levels_out
         self.stats["nNodesDAG"] = 1 + sum(len(x["mask"]) for x in levels_out[1:])
-        return levels_out
+        return dict(self.stats)
+
+    def build(self, L, step, lo=None, hi=None):
+        self.shard_build(L, step, None if lo is None else (lo, hi))
+        self.shard_finish()
+        return self.levels
 
 
 # --------------------------------------------------------------------------- SDAG (orbit-min)

@@ -12,6 +12,7 @@ from . import meshgen  # noqa: F401
 from . import build as _build  # noqa: F401
 from .capi import SvbError, GeomOctree, lib, lib_path, STATE_NAMES  # noqa: F401
 from . import encoders  # noqa: F401
+from . import sharded  # noqa: F401
 
 __all__ = ["meshgen", "GeomOctree", "SvbError", "lib", "lib_path", "encoders", "build_native"]
 

@@ -74,6 +74,14 @@ def lib() -> C.CDLL:
         L.svb_level_count_svo.argtypes = [vp, u32, C.POINTER(u64)]
         L.svb_download_level.argtypes = [vp, u32, vp, vp, vp, vp, vp]
         L.svb_upload_levels.argtypes = [vp, u32, vp, vp, vp, vp, C.c_double, u64]
+        L.svb_shard_build.argtypes = [vp, u32, u32, vp, vp, u32, u32]
+        L.svb_shard_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64), vp]
+        L.svb_shard_level_count.argtypes = [vp, u32, C.POINTER(u64), C.POINTER(u32)]
+        L.svb_shard_export_level.argtypes = [vp, u32, vp]
+        L.svb_shard_import_level.argtypes = [vp, u32, vp, vp, u64]
+        L.svb_shard_export_roots.argtypes = [vp, vp]
+        L.svb_shard_import_roots.argtypes = [vp, vp]
+        L.svb_shard_finish.argtypes = [vp, vp, C.POINTER(Stats)]
         L.svb_set_profiling.argtypes = [vp, C.c_int]
         L.svb_profile_count.argtypes = [vp]
         L.svb_profile_get.argtypes = [vp, C.c_int, C.POINTER(ProfRec)]
@@ -125,12 +133,54 @@ class GeomOctree:
         return v.min(axis=0).astype(np.float64), v.max(axis=0).astype(np.float64)
 
     # ---- GeomOctree
-    def build(self, levels: int, step: int = 0, bbox=None) -> dict:
+    def build(self, levels: int, step: int = 0, bbox=None, group=None, sharded: bool = False) -> dict:
+        """step == 0: buildSVO + toDAG; step > 0: buildDAG.  With sharded=True (inside an initialised
+        torch.distributed job) the sub-octrees are spread over the ranks and merged (sharded.py)."""
+        if sharded:
+            from .sharded import build_sharded
+            return build_sharded(self, levels, step, bbox if bbox is not None else self.scene_bbox(), group=group)
         lo, hi = bbox if bbox is not None else self.scene_bbox()
         lo = np.ascontiguousarray(lo, dtype=np.float64)
         hi = np.ascontiguousarray(hi, dtype=np.float64)
         st = Stats()
         self._check(self._L.svb_build(self._h, levels, step, lo.ctypes.data, hi.ctypes.data, C.byref(st)))
+        return st.as_dict()
+
+    # ---- multi-GPU protocol (include/svb.h); driven by sharded.build_sharded()
+    def shard_build(self, levels, step, bbox, rank, world):
+        lo, hi = bbox if bbox is not None else self.scene_bbox()
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        self._check(self._L.svb_shard_build(self._h, levels, step, lo.ctypes.data, hi.ctypes.data, rank, world))
+
+    def shard_info(self):
+        a, b, n = C.c_uint32(), C.c_uint32(), C.c_uint64()
+        cnt = np.zeros(5, np.uint64)
+        self._check(self._L.svb_shard_info(self._h, C.byref(a), C.byref(b), C.byref(n), cnt.ctypes.data))
+        return int(a.value), int(b.value), int(n.value), [int(x) for x in cnt]
+
+    def shard_level_count(self, g):
+        n, r = C.c_uint64(), C.c_uint32()
+        self._check(self._L.svb_shard_level_count(self._h, g, C.byref(n), C.byref(r)))
+        return int(n.value), int(r.value)
+
+    def shard_export_level(self, g, dev_ptr):
+        self._check(self._L.svb_shard_export_level(self._h, g, dev_ptr))
+
+    def shard_import_level(self, g, dev_ptr, counts, stride):
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        self._check(self._L.svb_shard_import_level(self._h, g, dev_ptr, counts.ctypes.data, int(stride)))
+
+    def shard_export_roots(self, dev_ptr):
+        self._check(self._L.svb_shard_export_roots(self._h, dev_ptr))
+
+    def shard_import_roots(self, dev_ptr):
+        self._check(self._L.svb_shard_import_roots(self._h, dev_ptr))
+
+    def shard_finish(self, totals) -> dict:
+        t = np.ascontiguousarray(totals, dtype=np.uint64)
+        st = Stats()
+        self._check(self._L.svb_shard_finish(self._h, t.ctypes.data, C.byref(st)))
         return st.as_dict()
 
     def to_sdag(self) -> dict:

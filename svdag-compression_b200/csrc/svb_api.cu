@@ -30,9 +30,25 @@ __global__ void k_gather_u32(uint64_t n, const uint32_t* __restrict__ idx, const
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) dst[i] = src[idx[i]];
 }
-__global__ void k_u8_to_u32(uint64_t n, const uint8_t* __restrict__ src, uint32_t* __restrict__ dst) {
+__global__ void k_scatter_u32(uint64_t n, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ src, uint32_t* __restrict__ dst) {
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) dst[i] = src[i];
+	if (i < n) dst[idx[i]] = src[i];
+}
+__global__ void k_scatter_u8(uint64_t n, const uint32_t* __restrict__ idx, const uint8_t* __restrict__ src, uint32_t* __restrict__ dst) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) dst[idx[i]] = src[i];
+}
+// sub-octree roots after the merge: local uid -> global uid (entries of other ranks stay UNSET)
+__global__ void k_remap_refs(uint64_t n, uint32_t* __restrict__ refs, const uint32_t* __restrict__ l2g) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n && refs[i] != UNSET) refs[i] = l2g[refs[i]];
+}
+__global__ void k_min_u32_rows(uint64_t n, uint32_t rows, const uint32_t* __restrict__ all, uint32_t* __restrict__ out) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t m = UNSET;
+	for (uint32_t r = 0; r < rows; ++r) { uint32_t v = all[(uint64_t)r * n + i]; if (v < m) m = v; }
+	out[i] = m;
 }
 
 struct ProfScope {
@@ -101,30 +117,78 @@ void float_box(const double lo[3], const double hi[3], float bboxF[6], double& r
 	rootSide = (double)s;
 }
 
-struct BuildState {
-	uint32_t L = 0, step = 0;
+int kind_of(uint32_t g, uint32_t L) { return g == L - 1 ? KIND_LEAF : (g == L - 2 ? KIND_K64 : KIND_INNER); }
+
+struct TileHost {
+	TileGeom g;
+	uint32_t baseNode;   // index (Morton order) of the base leaf node
+	int j;               // child slot inside it
+	int ix, iy, iz;
+};
+
+template <class T>
+std::vector<T> download(cudaStream_t s, const T* d, uint64_t n) {
+	std::vector<T> h(n);
+	if (n) SVB_CUDA(cudaMemcpyAsync(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+	SVB_CUDA(cudaStreamSynchronize(s));
+	return h;
+}
+template <class T>
+void upload(cudaStream_t s, Pool& pool, DevBuf<T>& d, const std::vector<T>& h) {
+	d.reset(pool, h.size() ? h.size() : 1);
+	if (!h.empty()) SVB_CUDA(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+	SVB_CUDA(cudaStreamSynchronize(s));
+}
+
+}  // namespace
+
+// Everything a build keeps between its phases (local reduction -> [multi-GPU merge] -> finish).
+struct svb_build_state {
+	uint32_t L = 0, step = 0, s1 = 0;   // s1 = step + 1 = global level of the sub-octree roots (0: no sub-octrees)
+	uint32_t rank = 0, world = 1;
 	int tbits = 1, tileBits = 1;
-	std::vector<LevelTable> tables;
+	std::vector<LevelTable> tables;      // per global level
 	std::vector<int> obits;
-	DevBuf<uint64_t> dVoxels;
-	DevBuf<uint64_t> dExact;   // children the filter could not decide (re-tested with the reference-order predicate)
+	DevBuf<uint64_t> dVoxels, dExact;
 	DevBuf<uint32_t> rootKey;
 	int rootChildMode = CH_UID_U32;
 	uint64_t nNodesSVO = 0, nLastLevSVO = 0, pairs = 0, nBatches = 0;
+	uint64_t baseNodesSVO = 0, baseVoxels = 0, basePairs = 0, baseExact = 0;   // base octree: built by every rank, counted once
 	std::vector<uint64_t> svoCounts;
 	double msVox = 0, msDedup = 0;
+	// geometry
+	float bboxF[6];
+	double rootSide = 0;
+	TileGeom rootG;
+	TileGridHost grid1;
+	DevBuf<int> dGrid1, dLocal1;
+	DevBuf<uint32_t> dSeq1;
+	// step mode
+	std::vector<BatchLevel> base;        // base octree levels 0..step (reduced last)
+	std::vector<uint8_t> baseLeafMask;
+	std::vector<TileHost> tiles;         // all sub-octrees, in the reference's order
+	TileGridHost grid;
+	DevBuf<int> dGrid;
+	DevBuf<uint32_t> tileRootRef;        // per tile: uid of its (reduced) root at level s1; UNSET if not built here
+	std::vector<DevBuf<uint32_t>> l2g;   // multi-GPU merge: local uid -> global uid per level
+	std::vector<bool> merged;
+	bool finished = false;
+	uint64_t launches0 = 0;
+	cudaEvent_t evStart = nullptr;
 };
 
-int kind_of(uint32_t g, uint32_t L) { return g == L - 1 ? KIND_LEAF : (g == L - 2 ? KIND_K64 : KIND_INNER); }
+namespace {
 
-// bottom-up reduction of one batch's levels [lo_l, Lt-1] into the global tables
-void dedup_batch(svb_ctx* c, BuildState& B, std::vector<BatchLevel>& lv, int Lt, uint32_t gbase, uint32_t seqBase, int lo_l) {
+typedef svb_build_state BuildState;
+
+// bottom-up reduction of one batch's levels [lo_l, Lt-1] into the tables
+void dedup_batch(svb_ctx* c, BuildState& B, std::vector<BatchLevel>& lv, int Lt, uint32_t gbase, const uint32_t* d_tileSeq, int lo_l) {
 	for (int l = Lt - 1; l >= lo_l; --l) {
 		uint32_t g = gbase + l;
 		BatchLevel& X = lv[l];
 		DedupArgs a;
 		a.N = X.n; a.code = X.code.p; a.tstar = X.tstar.p; a.mask = X.mask.p; a.childBase = X.childBase.p;
-		a.l = l; a.tbits = B.tbits; a.seqBase = seqBase;
+		a.l = l; a.tbits = B.tbits; a.tileSeq = d_tileSeq;
 		int ob = B.tileBits + B.tbits + 3 * l;
 		if (ob > B.obits[g]) B.obits[g] = ob;
 		LevelTable& T = B.tables[g];
@@ -142,30 +206,28 @@ void dedup_batch(svb_ctx* c, BuildState& B, std::vector<BatchLevel>& lv, int Lt,
 			ProfScope ps(c, T.kind == KIND_K64 ? "dedup_k64" : "dedup_inner", g, X.n);
 			dedup_level(c->stream, c->pool, T, a);
 			ps.done(T.count, 37.0 * (double)X.n + 33.0 * (double)(T.count - before));
-			// the level below is no longer needed
-			lv[l + 1] = BatchLevel();
+			lv[l + 1] = BatchLevel();   // the level below is no longer needed
 		}
 	}
 }
 
-struct TileHost {
-	TileGeom g;
-	uint32_t baseNode;   // index (Morton order) of the base leaf node
-	int j;               // child slot inside it
-	int ix, iy, iz;
-};
-
-// Builds tiles [a,b) and reduces them.  Throws BatchTooBig when the batch must be split.
-void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tiles, uint32_t a, uint32_t b,
+// Voxelizes and reduces the sub-octrees sel[a..b) (indices into `tiles`, ascending).  Throws BatchTooBig
+// (before anything was reduced) when the batch must be cut.
+void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tiles, const std::vector<uint32_t>& sel, uint32_t a, uint32_t b,
                     const TileGridHost& grid, const int* d_gridTile, int Lt, uint32_t gbase, uint64_t budget, uint64_t nodeCap,
-                    uint32_t* d_tileRootRef, std::vector<BatchLevel>* keepLevels) {
+                    std::vector<BatchLevel>* keepLevels) {
 	cudaStream_t s = c->stream;
-	uint32_t nt = b - a;
+	const uint32_t nt = b - a;
 	std::vector<TileGeom> hg(nt);
-	for (uint32_t i = 0; i < nt; ++i) hg[i] = tiles[a + i].g;
-	DevBuf<TileGeom> dTiles(c->pool, nt);
-	SVB_CUDA(cudaMemcpyAsync(dTiles.p, hg.data(), nt * sizeof(TileGeom), cudaMemcpyHostToDevice, s));
-	SVB_CUDA(cudaStreamSynchronize(s));   // hg is a stack-owned staging buffer
+	std::vector<uint32_t> hseq(nt);
+	std::vector<int> hlocal(tiles.size(), -1);
+	for (uint32_t i = 0; i < nt; ++i) { hg[i] = tiles[sel[a + i]].g; hseq[i] = sel[a + i]; hlocal[sel[a + i]] = (int)i; }
+	DevBuf<TileGeom> dTiles;
+	DevBuf<uint32_t> dSeq;
+	DevBuf<int> dLocal;
+	upload(s, c->pool, dTiles, hg);
+	upload(s, c->pool, dSeq, hseq);
+	upload(s, c->pool, dLocal, hlocal);
 
 	std::vector<BatchLevel> lv;
 	uint64_t pairs = 0;
@@ -174,7 +236,7 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 		ProfScope ps(c, "voxelize", gbase, nt);
 		DevBuf<uint32_t> ptri, pnode;
 		uint64_t P = 0;
-		make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, (int)a, (int)b, ptri, pnode, P);
+		make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, dLocal.p, ptri, pnode, P);
 		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, P, budget, nodeCap, lv, pairs, B.dExact.p);
 		ps.done(pairs, 36.0 * (double)c->T + 9.0 * (double)lv[Lt - 1].n);
 		B.msVox += tm.stop();
@@ -184,46 +246,43 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 	for (int l = 1; l < Lt; ++l) B.nNodesSVO += lv[l].n;
 	B.nLastLevSVO += lv[Lt - 1].n;
 	if (gbase == 0) { B.svoCounts.assign(Lt, 0); for (int l = 0; l < Lt; ++l) B.svoCounts[l] = lv[l].n; }
-
-	if (keepLevels) {   // base octree of step mode: reduced later, after its tiles
+	if (keepLevels) {   // base octree of step mode: reduced last, on top of the sub-octree roots
 		*keepLevels = std::move(lv);
 		return;
 	}
 	StageTimer tm(s);
 	if (gbase == 0) {
-		dedup_batch(c, B, lv, Lt, 0, a, 1);
-		if (Lt > 1) {
-			DedupArgs r;
-			r.N = 1; r.code = lv[0].code.p; r.tstar = lv[0].tstar.p; r.mask = lv[0].mask.p; r.childBase = lv[0].childBase.p;
-			bool leafBelow = (kind_of(1, B.L) == KIND_LEAF);
-			r.childMode = leafBelow ? CH_MASK_U8 : CH_UID_U32;
-			r.childRefs = leafBelow ? (const void*)lv[1].mask.p : (const void*)lv[1].ref.p;
-			B.rootChildMode = r.childMode;
-			root_key(s, r, B.rootKey.p);
-		}
+		dedup_batch(c, B, lv, Lt, 0, dSeq.p, 1);
+		DedupArgs r;
+		r.N = 1; r.code = lv[0].code.p; r.tstar = lv[0].tstar.p; r.mask = lv[0].mask.p; r.childBase = lv[0].childBase.p;
+		bool leafBelow = (kind_of(1, B.L) == KIND_LEAF);
+		r.childMode = leafBelow ? CH_MASK_U8 : CH_UID_U32;
+		r.childRefs = leafBelow ? (const void*)lv[1].mask.p : (const void*)lv[1].ref.p;
+		B.rootChildMode = r.childMode;
+		root_key(s, r, B.rootKey.p);
 	} else {
-		dedup_batch(c, B, lv, Lt, gbase, a, 0);
-		// remember what the tile roots were reduced to (uid, or the voxel mask for 1-level tiles)
-		if (B.tables[gbase].kind == KIND_LEAF) k_u8_to_u32<<<blocks_for(nt, 256), 256, 0, s>>>(nt, lv[0].mask.p, d_tileRootRef + a);
-		else SVB_CUDA(cudaMemcpyAsync(d_tileRootRef + a, lv[0].ref.p, nt * 4ull, cudaMemcpyDeviceToDevice, s));
+		dedup_batch(c, B, lv, Lt, gbase, dSeq.p, 0);
+		// remember what each sub-octree root was reduced to (uid, or the voxel mask for 1-level sub-octrees)
+		if (B.tables[gbase].kind == KIND_LEAF) k_scatter_u8<<<blocks_for(nt, 256), 256, 0, s>>>(nt, dSeq.p, lv[0].mask.p, B.tileRootRef.p);
+		else k_scatter_u32<<<blocks_for(nt, 256), 256, 0, s>>>(nt, dSeq.p, lv[0].ref.p, B.tileRootRef.p);
 		SVB_KERNEL_CHECK();
 	}
 	B.msDedup += tm.stop();
 }
 
-// Batching: start with every tile in one batch.  When the voxelizer predicts (or hits) an overflow it
-// throws BatchTooBig before anything was reduced, carrying per-tile node counts of the level it
-// reached; the range is then cut by cumulative weight into pieces that should fit.  Batches are
-// always processed in ascending tile order (the order keys of later batches are larger, which the
-// dedup tables rely on).
-void run_tiles_split(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tiles, uint32_t a, uint32_t b,
-                     const TileGridHost& grid, const int* d_gridTile, int Lt, uint32_t gbase, uint64_t budget, uint64_t nodeCap,
-                     uint32_t* d_tileRootRef) {
-	std::vector<uint32_t> plan(1, b);   // upcoming batch ends, ascending; plan.front() is the current one
+// Batching: start with all of this rank's sub-octrees in one batch.  When the voxelizer predicts (or
+// hits) an overflow it throws BatchTooBig before anything was reduced, carrying per-tile node counts
+// of the level it reached; the range is then cut by cumulative weight into pieces that should fit.
+// Batches are processed in ascending sub-octree order (order keys of later batches are larger, which
+// the dedup tables rely on when they freeze an entry's representative).
+void run_tiles_split(svb_ctx* c, BuildState& B, const std::vector<uint32_t>& sel, int Lt, uint32_t gbase, uint64_t budget, uint64_t nodeCap) {
+	uint32_t a = 0;
+	const uint32_t b = (uint32_t)sel.size();
+	std::vector<uint32_t> plan(1, b);   // upcoming batch ends, ascending
 	while (a < b) {
 		uint32_t e = plan.front();
 		try {
-			run_tile_batch(c, B, tiles, a, e, grid, d_gridTile, Lt, gbase, budget, nodeCap, d_tileRootRef, nullptr);
+			run_tile_batch(c, B, B.tiles, sel, a, e, B.grid, B.dGrid.p, Lt, gbase, budget, nodeCap, nullptr);
 			a = e;
 			plan.erase(plan.begin());
 		} catch (const BatchTooBig& x) {
@@ -248,188 +307,213 @@ void run_tiles_split(svb_ctx* c, BuildState& B, const std::vector<TileHost>& til
 	}
 }
 
-template <class T>
-std::vector<T> download(cudaStream_t s, const T* d, uint64_t n) {
-	std::vector<T> h(n);
-	if (n) SVB_CUDA(cudaMemcpyAsync(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost, s));
-	SVB_CUDA(cudaStreamSynchronize(s));
-	return h;
+uint64_t batch_budget(svb_ctx* c) {
+	// transient budget of one tile batch: a fraction of what the slab allocator can still hand out
+	return c->batchBudget ? c->pool.live + c->batchBudget : c->pool.live + (uint64_t)(0.80 * (double)c->pool.headroom());
 }
 
-void do_build(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], const double bmax[3]) {
+// ---- phase 1: voxelize + reduce this rank's share into rank-local tables
+void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], const double bmax[3], uint32_t rank, uint32_t world) {
 	cudaStream_t s = c->stream;
 	if (L < 2 || L > 21) throw Error(SVB_EINVAL, "levels must be in [2,21]");
 	if (step > 0 && step + 1 >= L) throw Error(SVB_EINVAL, "step + 1 must be < levels");
 	if (!c->d_tris && c->T) throw Error(SVB_EINVAL, "no triangles set");
+	if (world == 0 || rank >= world) throw Error(SVB_EINVAL, "bad rank/world");
+	if (world > 1 && step == 0) throw Error(SVB_EINVAL, "a sharded build needs step > 0 (sub-octrees are the unit of distribution)");
 	c->out.clear();
 	c->state = SVB_S_EMPTY;
 	c->prof.clear();
 	memset(&c->stats, 0, sizeof(c->stats));
-	const uint64_t launches0 = g_launches.load();
-	StageTimer total(s);
-
-	BuildState B;
-	B.L = L; B.step = step;
+	c->build.reset(new BuildState());
+	BuildState& B = *c->build;
+	B.launches0 = g_launches.load();
+	cudaEventCreate(&B.evStart);
+	cudaEventRecord(B.evStart, s);
+	B.L = L; B.step = step; B.rank = rank; B.world = world;
 	B.tbits = bits_for(c->T ? c->T - 1 : 0);
 	B.tables.resize(L);
 	B.obits.assign(L, 1);
+	B.l2g.resize(L);
+	B.merged.assign(L, false);
 	for (uint32_t g = 1; g < L; ++g) table_init(s, c->pool, B.tables[g], kind_of(g, L));
-	B.dVoxels.reset(c->pool, 1);
-	B.dVoxels.zero();
-	B.dExact.reset(c->pool, 1);
-	B.dExact.zero();
-	B.rootKey.reset(c->pool, 8);
-	B.rootKey.fill_ff();
+	B.dVoxels.reset(c->pool, 1); B.dVoxels.zero();
+	B.dExact.reset(c->pool, 1); B.dExact.zero();
+	B.rootKey.reset(c->pool, 8); B.rootKey.fill_ff();
 
-	float bboxF[6];
-	double rootSide;
-	float_box(bmin, bmax, bboxF, rootSide);
-	TileGeom rootG;
-	rootG.cx = (bmin[0] + bmax[0]) * 0.5; rootG.cy = (bmin[1] + bmax[1]) * 0.5; rootG.cz = (bmin[2] + bmax[2]) * 0.5;   // bbox.center(), :214
-	rootG.rootSide = rootSide;
-
-	// transient budget of one tile batch: a fraction of what the slab allocator can still hand out
-	uint64_t budget = c->batchBudget ? c->pool.live + c->batchBudget : c->pool.live + (uint64_t)(0.80 * (double)c->pool.headroom());
-
-	TileGridHost grid1;
-	grid1.G = 1; grid1.cell = rootSide > 0 ? rootSide : 1.0;
-	grid1.ox = rootG.cx - rootSide * 0.5; grid1.oy = rootG.cy - rootSide * 0.5; grid1.oz = rootG.cz - rootSide * 0.5;
-	DevBuf<int> dGrid1(c->pool, 1);
-	dGrid1.zero();
+	float_box(bmin, bmax, B.bboxF, B.rootSide);
+	const double rootSide = B.rootSide;
+	B.rootG.cx = (bmin[0] + bmax[0]) * 0.5; B.rootG.cy = (bmin[1] + bmax[1]) * 0.5; B.rootG.cz = (bmin[2] + bmax[2]) * 0.5;   // bbox.center(), :214
+	B.rootG.rootSide = rootSide;
+	B.grid1.G = 1; B.grid1.cell = rootSide > 0 ? rootSide : 1.0;
+	B.grid1.ox = B.rootG.cx - rootSide * 0.5; B.grid1.oy = B.rootG.cy - rootSide * 0.5; B.grid1.oz = B.rootG.cz - rootSide * 0.5;
+	B.dGrid1.reset(c->pool, 1); B.dGrid1.zero();
 	std::vector<TileHost> rootTile(1);
-	rootTile[0].g = rootG; rootTile[0].baseNode = 0; rootTile[0].j = 0; rootTile[0].ix = rootTile[0].iy = rootTile[0].iz = 0;
+	rootTile[0].g = B.rootG; rootTile[0].baseNode = 0; rootTile[0].j = 0; rootTile[0].ix = rootTile[0].iy = rootTile[0].iz = 0;
+	const std::vector<uint32_t> sel0(1, 0);
+	const uint64_t budget = batch_budget(c);
 
-	uint64_t nVoxels = 0, nTiles = 0;
 	if (step == 0) {
+		B.s1 = 0;
 		B.tileBits = 1;
 		if (B.tileBits + B.tbits + 3 * ((int)L - 1) > 63) throw Error(SVB_ERANGE, "order key exceeds 64 bits: use step > 0 for this many levels/triangles");
 		try {
-			run_tile_batch(c, B, rootTile, 0, 1, grid1, dGrid1.p, (int)L, 0, budget, 0, nullptr, nullptr);
+			run_tile_batch(c, B, rootTile, sel0, 0, 1, B.grid1, B.dGrid1.p, (int)L, 0, budget, 0, nullptr);
 		} catch (const BatchTooBig&) {
 			throw Error(SVB_ENOMEM, "octree does not fit device memory in one piece; use step > 0");
 		}
-		nVoxels = download(s, B.dVoxels.p, 1)[0];
-		nTiles = 1;
-	} else {
-		const uint32_t s1 = step + 1;
-		// ---- base octree (levels 0..step) over all triangles, exact hierarchical tests
-		std::vector<BatchLevel> base;
-		try {
-			run_tile_batch(c, B, rootTile, 0, 1, grid1, dGrid1.p, (int)s1, 0, budget, 0, nullptr, &base);
-		} catch (const BatchTooBig&) {
-			throw Error(SVB_ENOMEM, "base octree does not fit device memory");
+		return;
+	}
+	const uint32_t s1 = step + 1;
+	B.s1 = s1;
+	// ---- base octree (levels 0..step) over all triangles, exact hierarchical tests (every rank, identical)
+	try {
+		run_tile_batch(c, B, rootTile, sel0, 0, 1, B.grid1, B.dGrid1.p, (int)s1, 0, budget, 0, &B.base);
+	} catch (const BatchTooBig&) {
+		throw Error(SVB_ENOMEM, "base octree does not fit device memory");
+	}
+	B.baseNodesSVO = B.nNodesSVO;
+	B.basePairs = B.pairs;
+	B.baseExact = download(s, B.dExact.p, 1)[0];
+	B.pairs = 0;
+	B.dExact.zero();
+	B.nNodesSVO = 0;
+	B.nBatches = 0;
+	B.nLastLevSVO = 0;            // geom_octree.cpp:318
+	B.svoCounts.clear();
+	// ---- enumerate the sub-octrees exactly like :335-344 (leaf node creation order i, child j = 7..0)
+	const BatchLevel& BL = B.base[s1 - 1];
+	std::vector<uint64_t> hcode = download(s, BL.code.p, BL.n);
+	std::vector<uint32_t> htstar = download(s, BL.tstar.p, BL.n);
+	B.baseLeafMask = download(s, BL.mask.p, BL.n);
+	const std::vector<uint8_t>& hmask = B.baseLeafMask;
+	const int lb = (int)s1 - 1;   // path digits of a base leaf node
+	std::vector<uint32_t> order(BL.n);
+	for (uint32_t i = 0; i < BL.n; ++i) order[i] = i;
+	auto pathp = [&](uint32_t i) { uint64_t p = hcode[i]; return lb > 0 ? ((p & ~7ull) | (7ull - (p & 7ull))) : p; };
+	std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+		if (htstar[x] != htstar[y]) return htstar[x] < htstar[y];
+		return pathp(x) < pathp(y);
+	});
+	const int G = 1 << s1;
+	std::vector<int> hgrid((size_t)G * G * G, -1);
+	const double lhs = rootSide / (double)(1u << s1);   // getHalfSideD(stepLevels - 1), :306
+	B.baseVoxels = 0;
+	for (uint32_t oi = 0; oi < BL.n; ++oi) {
+		uint32_t i = order[oi];
+		B.baseVoxels += (uint64_t)__builtin_popcount(hmask[i]);
+		if (!hmask[i]) continue;
+		// centre of base leaf node i: the chain of :222-230
+		double cx = B.rootG.cx, cy = B.rootG.cy, cz = B.rootG.cz, k = rootSide * 0.25;
+		int ix = 0, iy = 0, iz = 0;
+		for (int d = lb - 1; d >= 0; --d) {
+			int dig = (int)((hcode[i] >> (3 * d)) & 7);
+			cx = cx + ((dig & 4) ? k : -k); cy = cy + ((dig & 2) ? k : -k); cz = cz + ((dig & 1) ? k : -k);
+			ix = (ix << 1) | ((dig >> 2) & 1); iy = (iy << 1) | ((dig >> 1) & 1); iz = (iz << 1) | (dig & 1);
+			k *= 0.5;
 		}
-		B.nBatches = 0;
-		B.nLastLevSVO = 0;            // geom_octree.cpp:318
-		B.svoCounts.clear();
-		// ---- enumerate the sub-octrees exactly like :335-344 (leaf node creation order i, child j = 7..0)
-		const BatchLevel& BL = base[s1 - 1];
-		std::vector<uint64_t> hcode = download(s, BL.code.p, BL.n);
-		std::vector<uint32_t> htstar = download(s, BL.tstar.p, BL.n);
-		std::vector<uint8_t> hmask = download(s, BL.mask.p, BL.n);
-		const int lb = (int)s1 - 1;   // path digits of a base leaf node
-		std::vector<uint32_t> order(BL.n);
-		for (uint32_t i = 0; i < BL.n; ++i) order[i] = i;
-		auto pathp = [&](uint32_t i) { uint64_t p = hcode[i]; return lb > 0 ? ((p & ~7ull) | (7ull - (p & 7ull))) : p; };
-		std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-			if (htstar[x] != htstar[y]) return htstar[x] < htstar[y];
-			return pathp(x) < pathp(y);
-		});
-		std::vector<TileHost> tiles;
-		const int G = 1 << s1;
-		std::vector<int> hgrid((size_t)G * G * G, -1);
-		const double lhs = rootSide / (double)(1u << s1);   // getHalfSideD(stepLevels - 1), :306
-		for (uint32_t oi = 0; oi < BL.n; ++oi) {
-			uint32_t i = order[oi];
-			nVoxels += (uint64_t)__builtin_popcount(hmask[i]);
-			if (!hmask[i]) continue;
-			// centre of base leaf node i: the chain of :222-230
-			double cx = rootG.cx, cy = rootG.cy, cz = rootG.cz, k = rootSide * 0.25;
-			int ix = 0, iy = 0, iz = 0;
-			for (int d = lb - 1; d >= 0; --d) {
-				int dig = (int)((hcode[i] >> (3 * d)) & 7);
-				cx = cx + ((dig & 4) ? k : -k); cy = cy + ((dig & 2) ? k : -k); cz = cz + ((dig & 1) ? k : -k);
-				ix = (ix << 1) | ((dig >> 2) & 1); iy = (iy << 1) | ((dig >> 1) & 1); iz = (iz << 1) | (dig & 1);
-				k *= 0.5;
-			}
-			for (int j = 7; j >= 0; --j) {
-				if (!((hmask[i] >> j) & 1)) continue;
-				TileHost t;
-				double p2x = cx + ((j & 4) ? lhs : -lhs), p2y = cy + ((j & 2) ? lhs : -lhs), p2z = cz + ((j & 1) ? lhs : -lhs);
-				double lo[3] = { std::min(cx, p2x), std::min(cy, p2y), std::min(cz, p2z) };
-				double hi[3] = { std::max(cx, p2x), std::max(cy, p2y), std::max(cz, p2z) };
-				float bf[6];
-				float_box(lo, hi, bf, t.g.rootSide);   // :340-344 -> :177-184
-				t.g.cx = (lo[0] + hi[0]) * 0.5; t.g.cy = (lo[1] + hi[1]) * 0.5; t.g.cz = (lo[2] + hi[2]) * 0.5;
-				t.baseNode = i; t.j = j;
-				t.ix = (ix << 1) | ((j >> 2) & 1); t.iy = (iy << 1) | ((j >> 1) & 1); t.iz = (iz << 1) | (j & 1);
-				hgrid[((size_t)t.ix * G + t.iy) * G + t.iz] = (int)tiles.size();
-				tiles.push_back(t);
-			}
+		for (int j = 7; j >= 0; --j) {
+			if (!((hmask[i] >> j) & 1)) continue;
+			TileHost t;
+			double p2x = cx + ((j & 4) ? lhs : -lhs), p2y = cy + ((j & 2) ? lhs : -lhs), p2z = cz + ((j & 1) ? lhs : -lhs);
+			double lo[3] = { std::min(cx, p2x), std::min(cy, p2y), std::min(cz, p2z) };
+			double hi[3] = { std::max(cx, p2x), std::max(cy, p2y), std::max(cz, p2z) };
+			float bf[6];
+			float_box(lo, hi, bf, t.g.rootSide);   // :340-344 -> :177-184
+			t.g.cx = (lo[0] + hi[0]) * 0.5; t.g.cy = (lo[1] + hi[1]) * 0.5; t.g.cz = (lo[2] + hi[2]) * 0.5;
+			t.baseNode = i; t.j = j;
+			t.ix = (ix << 1) | ((j >> 2) & 1); t.iy = (iy << 1) | ((j >> 1) & 1); t.iz = (iz << 1) | (j & 1);
+			hgrid[((size_t)t.ix * G + t.iy) * G + t.iz] = (int)B.tiles.size();
+			B.tiles.push_back(t);
 		}
-		nTiles = tiles.size();
-		B.tileBits = bits_for(nTiles ? nTiles - 1 : 0);
-		const int Lt = (int)(L - s1);
-		if (B.tileBits + B.tbits + 3 * (Lt - 1) > 63 || B.tbits + 3 * lb > 63)
-			throw Error(SVB_ERANGE, "order key exceeds 64 bits: increase step (fewer levels per sub-octree)");
-		TileGridHost grid;
-		grid.G = G; grid.cell = rootSide / (double)G;
-		grid.ox = grid1.ox; grid.oy = grid1.oy; grid.oz = grid1.oz;
-		DevBuf<int> dGrid(c->pool, hgrid.size());
-		SVB_CUDA(cudaMemcpyAsync(dGrid.p, hgrid.data(), hgrid.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-		DevBuf<uint32_t> tileRootRef(c->pool, nTiles ? nTiles : 1);
-		// leaf-level nodes one batch may hold: 32-bit indices, and ~40 bytes of transient state per leaf node
-		uint64_t nodeCap = std::min<uint64_t>(3600000000ull, (budget - c->pool.live) / 40);
-		if (nTiles) run_tiles_split(c, B, tiles, 0, (uint32_t)nTiles, grid, dGrid.p, Lt, s1, budget, nodeCap, tileRootRef.p);
-		uint64_t leafVox = download(s, B.dVoxels.p, 1)[0];
-		nVoxels = nVoxels + leafVox - nTiles;   // :352-354 "root doesn't count"
-		// ---- reduce the base octree (levels step..1) on top of the tile roots
+	}
+	const uint64_t nTiles = B.tiles.size();
+	B.tileBits = bits_for(nTiles ? nTiles - 1 : 0);
+	const int Lt = (int)(L - s1);
+	if (B.tileBits + B.tbits + 3 * (Lt - 1) > 63 || B.tbits + 3 * lb > 63)
+		throw Error(SVB_ERANGE, "order key exceeds 64 bits: increase step (fewer levels per sub-octree)");
+	B.grid.G = G; B.grid.cell = rootSide / (double)G;
+	B.grid.ox = B.grid1.ox; B.grid.oy = B.grid1.oy; B.grid.oz = B.grid1.oz;
+	upload(s, c->pool, B.dGrid, hgrid);
+	B.tileRootRef.reset(c->pool, nTiles ? nTiles : 1);
+	B.tileRootRef.fill_ff();
+	// ---- this rank's share: sub-octrees dealt round-robin in the reference's order (SVB_SHARD=octant: by
+	//      top-level octant, the decomposition BASELINE.json names; unbalanced for flat scenes)
+	std::vector<uint32_t> mine;
+	const char* pol = getenv("SVB_SHARD");
+	const bool byOctant = pol && pol[0] == 'o';
+	for (uint32_t q = 0; q < nTiles; ++q) {
+		uint32_t owner;
+		if (byOctant) {
+			const TileHost& t = B.tiles[q];
+			uint32_t oct = (uint32_t)((((t.ix >> (s1 - 1)) & 1) << 2) | (((t.iy >> (s1 - 1)) & 1) << 1) | ((t.iz >> (s1 - 1)) & 1));
+			owner = (uint32_t)(((uint64_t)oct * world) / 8);
+		} else owner = q % world;
+		if (owner == rank) mine.push_back(q);
+	}
+	// leaf-level nodes one batch may hold: 32-bit indices, and ~40 bytes of transient state per leaf node
+	uint64_t nodeCap = std::min<uint64_t>(3600000000ull, (budget - c->pool.live) / 40);
+	if (!mine.empty()) run_tiles_split(c, B, mine, Lt, s1, budget, nodeCap);
+}
+
+// ---- phase 3: reduce the base octree on top of the (global) sub-octree roots, rank, materialise
+void build_finish(svb_ctx* c, const uint64_t* totals) {
+	if (!c->build) throw Error(SVB_EINVAL, "no build in progress");
+	BuildState& B = *c->build;
+	cudaStream_t s = c->stream;
+	const uint32_t L = B.L, s1 = B.s1;
+	uint64_t leafVox = download(s, B.dVoxels.p, 1)[0];
+	uint64_t nodesSVO = B.nNodesSVO, lastLev = B.nLastLevSVO, pairs = B.pairs, exact = download(s, B.dExact.p, 1)[0];
+	if (totals) { leafVox = totals[0]; nodesSVO = totals[1]; lastLev = totals[2]; pairs = totals[3]; exact = totals[4]; }
+	uint64_t nVoxels = leafVox, nTiles = 1;
+	if (s1 > 0) {
+		nTiles = B.tiles.size();
+		nVoxels = B.baseVoxels + leafVox - nTiles;   // :352-354 "root doesn't count"
+		nodesSVO += B.baseNodesSVO;
+		pairs += B.basePairs;
+		exact += B.baseExact;
 		StageTimer tm(s);
-		{
-			// children of base leaf node n, in ascending child order, are tile roots: gather their refs
-			std::vector<uint32_t> seqOf;   // seqOf[childBase(n) + r]
-			std::vector<uint32_t> cb(BL.n);
-			uint32_t acc = 0;
-			for (uint32_t n = 0; n < BL.n; ++n) { cb[n] = acc; acc += (uint32_t)__builtin_popcount(hmask[n]); }
-			seqOf.assign(acc ? acc : 1, 0);
-			for (uint32_t q = 0; q < tiles.size(); ++q) {
-				const TileHost& t = tiles[q];
-				int r = __builtin_popcount(hmask[t.baseNode] & ((1u << t.j) - 1));
-				seqOf[cb[t.baseNode] + r] = q;
-			}
-			DevBuf<uint32_t> dSeq(c->pool, seqOf.size()), dCb(c->pool, BL.n ? BL.n : 1);
-			SVB_CUDA(cudaMemcpyAsync(dSeq.p, seqOf.data(), seqOf.size() * 4, cudaMemcpyHostToDevice, s));
-			SVB_CUDA(cudaMemcpyAsync(dCb.p, cb.data(), cb.size() * 4, cudaMemcpyHostToDevice, s));
-			DevBuf<uint32_t> topRefs(c->pool, seqOf.size());
-			if (acc) k_gather_u32<<<blocks_for(acc, 256), 256, 0, s>>>(acc, dSeq.p, tileRootRef.p, topRefs.p);
-			SVB_KERNEL_CHECK();
-			base[s1 - 1].childBase = std::move(dCb);
-			SVB_CUDA(cudaStreamSynchronize(s));
-			const uint32_t* below = topRefs.p;
-			int belowMode = (kind_of(s1, L) == KIND_LEAF) ? CH_MASK_U32 : CH_UID_U32;
-			for (int l = (int)s1 - 1; l >= 0; --l) {
-				BatchLevel& X = base[l];
-				DedupArgs a;
-				a.N = X.n; a.code = X.code.p; a.tstar = X.tstar.p; a.mask = X.mask.p; a.childBase = X.childBase.p;
-				a.l = l; a.tbits = B.tbits; a.seqBase = 0;
-				a.childMode = belowMode; a.childRefs = below;
-				if (l == 0) { B.rootChildMode = belowMode; root_key(s, a, B.rootKey.p); break; }
-				int ob = 1 + B.tbits + 3 * l;
-				if (ob > B.obits[l]) B.obits[l] = ob;
-				X.ref.reset(c->pool, X.n);
-				a.ref = X.ref.p;
-				ProfScope ps(c, B.tables[l].kind == KIND_K64 ? "dedup_k64" : "dedup_inner", (uint32_t)l, X.n);
-				dedup_level(s, c->pool, B.tables[l], a);
-				ps.done(B.tables[l].count, 37.0 * (double)X.n);
-				below = X.ref.p;
-				belowMode = CH_UID_U32;
-			}
-			SVB_CUDA(cudaStreamSynchronize(s));
+		const BatchLevel& BL = B.base[s1 - 1];
+		const std::vector<uint8_t>& hmask = B.baseLeafMask;
+		// children of base leaf node n, in ascending child order, are sub-octree roots: gather their refs
+		std::vector<uint32_t> cb(BL.n), seqOf;
+		uint32_t acc = 0;
+		for (uint32_t n = 0; n < BL.n; ++n) { cb[n] = acc; acc += (uint32_t)__builtin_popcount(hmask[n]); }
+		seqOf.assign(acc ? acc : 1, 0);
+		for (uint32_t q = 0; q < B.tiles.size(); ++q) {
+			const TileHost& t = B.tiles[q];
+			int r = __builtin_popcount(hmask[t.baseNode] & ((1u << t.j) - 1));
+			seqOf[cb[t.baseNode] + r] = q;
 		}
+		DevBuf<uint32_t> dSeq, dCb, dZero;
+		upload(s, c->pool, dSeq, seqOf);
+		upload(s, c->pool, dCb, cb);
+		upload(s, c->pool, dZero, std::vector<uint32_t>(1, 0));
+		DevBuf<uint32_t> topRefs(c->pool, seqOf.size());
+		if (acc) k_gather_u32<<<blocks_for(acc, 256), 256, 0, s>>>(acc, dSeq.p, B.tileRootRef.p, topRefs.p);
+		SVB_KERNEL_CHECK();
+		B.base[s1 - 1].childBase = std::move(dCb);
+		const uint32_t* below = topRefs.p;
+		int belowMode = (kind_of(s1, L) == KIND_LEAF) ? CH_MASK_U32 : CH_UID_U32;
+		for (int l = (int)s1 - 1; l >= 0; --l) {
+			BatchLevel& X = B.base[l];
+			DedupArgs a;
+			a.N = X.n; a.code = X.code.p; a.tstar = X.tstar.p; a.mask = X.mask.p; a.childBase = X.childBase.p;
+			a.l = l; a.tbits = B.tbits; a.tileSeq = dZero.p;
+			a.childMode = belowMode; a.childRefs = below;
+			if (l == 0) { B.rootChildMode = belowMode; root_key(s, a, B.rootKey.p); break; }
+			int ob = 1 + B.tbits + 3 * l;
+			if (ob > B.obits[l]) B.obits[l] = ob;
+			X.ref.reset(c->pool, X.n);
+			a.ref = X.ref.p;
+			ProfScope ps(c, B.tables[l].kind == KIND_K64 ? "dedup_k64" : "dedup_inner", (uint32_t)l, X.n);
+			dedup_level(s, c->pool, B.tables[l], a);
+			ps.done(B.tables[l].count, 37.0 * (double)X.n);
+			below = X.ref.p;
+			belowMode = CH_UID_U32;
+		}
+		SVB_CUDA(cudaStreamSynchronize(s));
 		B.msDedup += tm.stop();
 	}
-
-	// ---- rank + materialise
 	double msFin;
 	{
 		StageTimer tm(s);
@@ -438,8 +522,8 @@ void do_build(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], const
 	}
 	svb_stats& st = c->stats;
 	st.nTotalVoxels = nVoxels;
-	st.nNodesSVO = B.nNodesSVO;
-	st.nNodesLastLevSVO = B.nLastLevSVO;
+	st.nNodesSVO = nodesSVO;
+	st.nNodesLastLevSVO = lastLev;
 	uint64_t nn = 1;
 	for (uint32_t g = 1; g < L; ++g) nn += c->out[g].n;
 	st.nNodesDAG = nn;              // geom_octree.cpp:471,516,544
@@ -447,18 +531,29 @@ void do_build(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], const
 	st.nNodesLastLevDAG = c->out[L - 1].n;
 	st.nTiles = nTiles;
 	st.nBatches = B.nBatches;
-	st.nPairsTotal = B.pairs;
-	st.nExactTests = download(s, B.dExact.p, 1)[0];
-	st.rootSide = rootSide;
-	memcpy(st.bboxF, bboxF, sizeof(bboxF));
+	st.nPairsTotal = pairs;
+	st.nExactTests = exact;
+	st.rootSide = B.rootSide;
+	memcpy(st.bboxF, B.bboxF, sizeof(B.bboxF));
 	st.msVoxelize = B.msVox;
 	st.msDedup = B.msDedup;
 	st.msFinalize = msFin;
 	c->svoCounts = B.svoCounts;
 	c->levels = L;
 	c->state = SVB_S_DAG;
-	st.msTotal = total.stop();
-	st.nKernelLaunches = g_launches.load() - launches0;
+	{
+		cudaEvent_t e1;
+		cudaEventCreate(&e1);
+		cudaEventRecord(e1, s);
+		cudaEventSynchronize(e1);
+		float ms = 0;
+		cudaEventElapsedTime(&ms, B.evStart, e1);
+		st.msTotal = ms;
+		cudaEventDestroy(e1);
+		cudaEventDestroy(B.evStart);
+	}
+	st.nKernelLaunches = g_launches.load() - B.launches0;
+	c->build.reset();
 	resolve_profile(c);
 }
 
@@ -540,9 +635,108 @@ int svb_set_triangles_device(svb_ctx* c, const float* xyz9_dev, uint64_t ntris) 
 int svb_build(svb_ctx* c, uint32_t levels, uint32_t step, const double bmin[3], const double bmax[3], svb_stats* out) {
 	int rc = guarded(c, [&] {
 		if (!bmin || !bmax) throw Error(SVB_EINVAL, "null bbox");
-		do_build(c, levels, step, bmin, bmax);
+		build_local(c, levels, step, bmin, bmax, 0, 1);
+		build_finish(c, nullptr);
 	});
-	if (rc != SVB_OK && c) { c->out.clear(); c->state = SVB_S_EMPTY; }
+	if (rc != SVB_OK && c) { c->out.clear(); c->state = SVB_S_EMPTY; c->build.reset(); }
+	if (rc == SVB_OK && out) *out = c->stats;
+	return rc;
+}
+
+// ---- multi-GPU: local phase, per-level exchange, finish
+int svb_shard_build(svb_ctx* c, uint32_t levels, uint32_t step, const double bmin[3], const double bmax[3], uint32_t rank, uint32_t world) {
+	int rc = guarded(c, [&] {
+		if (!bmin || !bmax) throw Error(SVB_EINVAL, "null bbox");
+		build_local(c, levels, step, bmin, bmax, rank, world);
+		SVB_CUDA(cudaStreamSynchronize(c->stream));
+	});
+	if (rc != SVB_OK && c) { c->out.clear(); c->state = SVB_S_EMPTY; c->build.reset(); }
+	return rc;
+}
+
+int svb_shard_info(const svb_ctx* c, uint32_t* firstLevel, uint32_t* lastLevel, uint64_t* nTiles, uint64_t counters[5]) {
+	if (!c || !c->build) return SVB_EINVAL;
+	const svb_build_state& B = *c->build;
+	if (firstLevel) *firstLevel = B.s1;
+	if (lastLevel) *lastLevel = B.L - 1;
+	if (nTiles) *nTiles = B.tiles.size();
+	if (counters) {
+		uint64_t v[2] = {0, 0};
+		cudaMemcpy(&v[0], B.dVoxels.p, 8, cudaMemcpyDeviceToHost);
+		cudaMemcpy(&v[1], B.dExact.p, 8, cudaMemcpyDeviceToHost);
+		counters[0] = v[0]; counters[1] = B.nNodesSVO; counters[2] = B.nLastLevSVO; counters[3] = B.pairs; counters[4] = v[1];
+	}
+	return SVB_OK;
+}
+
+int svb_shard_level_count(const svb_ctx* c, uint32_t level, uint64_t* n, uint32_t* recBytes) {
+	if (!c || !c->build || level == 0 || level >= c->build->L) return SVB_EINVAL;
+	const LevelTable& T = c->build->tables[level];
+	if (n) *n = merge_count(T);
+	if (recBytes) *recBytes = merge_rec_bytes(T.kind);
+	return SVB_OK;
+}
+
+int svb_shard_export_level(svb_ctx* c, uint32_t level, void* d_out) {
+	return guarded(c, [&] {
+		if (!c->build || level < c->build->s1 || level >= c->build->L) throw Error(SVB_EINVAL, "bad level");
+		svb_build_state& B = *c->build;
+		LevelTable& T = B.tables[level];
+		const uint32_t* l2gChild = nullptr;
+		if (T.kind == KIND_INNER) {
+			if (!B.merged[level + 1]) throw Error(SVB_EINVAL, "levels must be merged bottom-up");
+			l2gChild = B.l2g[level + 1].p;
+		}
+		merge_export(c->stream, c->pool, T, l2gChild, d_out);
+		SVB_CUDA(cudaStreamSynchronize(c->stream));
+	});
+}
+
+int svb_shard_import_level(svb_ctx* c, uint32_t level, const void* d_all, const uint64_t* counts, uint64_t strideBytes) {
+	return guarded(c, [&] {
+		if (!c->build || level < c->build->s1 || level >= c->build->L || !counts) throw Error(SVB_EINVAL, "bad level");
+		svb_build_state& B = *c->build;
+		merge_import(c->stream, c->pool, B.tables[level], d_all, counts, B.world, strideBytes, B.rank, B.l2g[level]);
+		B.merged[level] = true;
+		if (level == B.s1) {   // sub-octree roots now have global uids
+			if (B.tables[level].kind != KIND_LEAF && !B.tiles.empty()) {
+				k_remap_refs<<<blocks_for(B.tiles.size(), 256), 256, 0, c->stream>>>(B.tiles.size(), B.tileRootRef.p, B.l2g[level].p);
+				SVB_KERNEL_CHECK();
+			}
+		}
+		SVB_CUDA(cudaStreamSynchronize(c->stream));
+	});
+}
+
+int svb_shard_export_roots(svb_ctx* c, void* d_out) {
+	return guarded(c, [&] {
+		if (!c->build) throw Error(SVB_EINVAL, "no build in progress");
+		svb_build_state& B = *c->build;
+		if (!B.merged[B.s1]) throw Error(SVB_EINVAL, "merge the sub-octree root level first");
+		SVB_CUDA(cudaMemcpyAsync(d_out, B.tileRootRef.p, (B.tiles.size() ? B.tiles.size() : 1) * 4ull, cudaMemcpyDeviceToDevice, c->stream));
+		SVB_CUDA(cudaStreamSynchronize(c->stream));
+	});
+}
+
+int svb_shard_import_roots(svb_ctx* c, const void* d_all) {
+	return guarded(c, [&] {
+		if (!c->build) throw Error(SVB_EINVAL, "no build in progress");
+		svb_build_state& B = *c->build;
+		uint64_t n = B.tiles.size();
+		if (n) {
+			k_min_u32_rows<<<blocks_for(n, 256), 256, 0, c->stream>>>(n, B.world, (const uint32_t*)d_all, B.tileRootRef.p);
+			SVB_KERNEL_CHECK();
+		}
+		SVB_CUDA(cudaStreamSynchronize(c->stream));
+	});
+}
+
+int svb_shard_finish(svb_ctx* c, const uint64_t totals[5], svb_stats* out) {
+	int rc = guarded(c, [&] {
+		if (!c->build) throw Error(SVB_EINVAL, "no build in progress");
+		build_finish(c, totals);
+	});
+	if (rc != SVB_OK && c) { c->out.clear(); c->state = SVB_S_EMPTY; c->build.reset(); }
 	if (rc == SVB_OK && out) *out = c->stats;
 	return rc;
 }

@@ -1,6 +1,10 @@
 // svb_context.cuh -- the opaque svb_ctx behind the C ABI.
 #pragma once
+#include <memory>
+
 #include "svb_internal.cuh"
+
+struct svb_build_state;   // svb_api.cu: tables and tile list a build keeps between its phases
 
 struct svb_ctx {
 	int device = 0;
@@ -23,5 +27,6 @@ struct svb_ctx {
 	std::vector<PendingProf> pending;
 	std::vector<svb_prof_rec> prof;
 	uint64_t batchBudget = 0;
+	std::shared_ptr<svb_build_state> build;   // non-null between svb_shard_build and svb_shard_finish
 	svb_ctx() { memset(&stats, 0, sizeof(stats)); }
 };

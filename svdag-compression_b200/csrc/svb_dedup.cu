@@ -21,12 +21,12 @@ namespace {
 
 constexpr int DD_THREADS = 256;
 
-__device__ __forceinline__ uint64_t order_key(uint64_t code, uint32_t tstar, int l, int tbits, uint32_t seqBase) {
+__device__ __forceinline__ uint64_t order_key(uint64_t code, uint32_t tstar, int l, int tbits, const uint32_t* __restrict__ tileSeq) {
 	uint64_t pmask = (l >= 21) ? ~0ull : ((1ull << (3 * l)) - 1);
 	uint64_t path = code & pmask;
 	uint64_t tile = (l >= 21) ? 0 : (code >> (3 * l));
 	if (l > 0) path = (path & ~7ull) | (7ull - (path & 7ull));   // children are created 7 -> 0 (geom_octree.cpp:234)
-	return ((uint64_t)(seqBase + tile) << (tbits + 3 * l)) | ((uint64_t)tstar << (3 * l)) | path;
+	return ((uint64_t)tileSeq[tile] << (tbits + 3 * l)) | ((uint64_t)tstar << (3 * l)) | path;
 }
 
 template <int CHMODE>
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(DD_THREADS) k_leaf_min(DedupArgs a, unsigned l
 		unsigned m = a.mask[n];
 		if (!m) continue;
 		vox += __popc(m);
-		unsigned long long O = order_key(a.code[n], a.tstar[n], a.l, a.tbits, a.seqBase);
+		unsigned long long O = order_key(a.code[n], a.tstar[n], a.l, a.tbits, a.tileSeq);
 		if (smin[m] > O) atomicMin(&smin[m], O);
 	}
 	__syncthreads();
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(DD_THREADS) k_insert(DedupArgs a, TableDev t) 
 	uint64_t tag = (CHMODE == CH_UID_U32) ? tag_of_key8(k8) : k64;
 	uint64_t slot;
 	if (!table_find_or_claim(t, tag, slot)) { a.ref[n] = NULLREF; return; }
-	unsigned long long O = order_key(a.code[n], a.tstar[n], a.l, a.tbits, a.seqBase);
+	unsigned long long O = order_key(a.code[n], a.tstar[n], a.l, a.tbits, a.tileSeq);
 	if (t.minO[slot] > O) atomicMin(&t.minO[slot], O);
 	a.ref[n] = (uint32_t)slot;
 }
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(DD_THREADS) k_winner(DedupArgs a, TableDev t, 
 	if (n >= a.N) return;
 	uint32_t slot = a.ref[n];
 	if (slot == NULLREF) return;
-	unsigned long long O = order_key(a.code[n], a.tstar[n], a.l, a.tbits, a.seqBase);
+	unsigned long long O = order_key(a.code[n], a.tstar[n], a.l, a.tbits, a.tileSeq);
 	if (t.minO[slot] != O) return;
 	uint32_t k8[8];
 	uint64_t k64;
@@ -399,6 +399,200 @@ static void dedup_level_t(cudaStream_t s, Pool& pool, LevelTable& T, const Dedup
 		if (h[1]) throw Error(SVB_ECOLLISION, "64-bit node-key hash collision (exact verify failed)");
 	}
 	T.count += fresh;
+}
+
+// =================================================================== multi-GPU merge of one level
+// Every rank reduced its own sub-octrees into rank-local tables.  Bottom-up, level by level, the ranks
+// exchange their unique nodes as records {key with GLOBAL child uids, min order key} (an all-gather
+// done by the caller over NCCL), and every rank rebuilds the identical global table from the union:
+// equal keys collapse, the smallest order key survives, so the final first-occurrence ranking is the
+// one a single GPU would have produced.  Replaces the serial "Joining subtrees" + "Last DAG pass"
+// of GeomOctree::buildDAG (src/symvox/geom_octree.cpp:397-425) across devices.
+namespace {
+
+struct RecK64 { uint64_t key; uint64_t minO; };
+struct RecInner { uint32_t key[8]; uint64_t minO; };
+
+__global__ void __launch_bounds__(DD_THREADS) k_export_k64(uint64_t n, const uint64_t* __restrict__ dKey64, const uint64_t* __restrict__ dMinO, RecK64* __restrict__ out) {
+	uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= n) return;
+	RecK64 r; r.key = dKey64[u]; r.minO = dMinO[u];
+	out[u] = r;
+}
+__global__ void __launch_bounds__(DD_THREADS) k_export_inner(uint64_t n, const uint32_t* __restrict__ dKey8, const uint64_t* __restrict__ dMinO,
+                                                              const uint32_t* __restrict__ l2gChild, RecInner* __restrict__ out) {
+	uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= n) return;
+	RecInner r;
+#pragma unroll
+	for (int c = 0; c < 8; ++c) {
+		uint32_t k = dKey8[u * 8 + c];
+		r.key[c] = (k == NULLREF) ? NULLREF : l2gChild[k];
+	}
+	r.minO = dMinO[u];
+	out[u] = r;
+}
+
+// entry e of the gathered buffer = (rank e / maxCount, index e % maxCount); valid iff index < counts[rank]
+template <bool K64>
+__global__ void __launch_bounds__(DD_THREADS) k_import_insert(uint64_t total, uint64_t maxCount, const uint64_t* __restrict__ counts, const char* __restrict__ all,
+                                                               uint64_t strideBytes, TableDev t, uint32_t* __restrict__ slotOf) {
+	uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= total) return;
+	uint64_t r = e / maxCount, i = e % maxCount;
+	if (i >= counts[r]) { slotOf[e] = NULLREF; return; }
+	uint64_t tag, O;
+	if (K64) { const RecK64* p = (const RecK64*)(all + r * strideBytes) + i; tag = p->key; O = p->minO; }
+	else { const RecInner* p = (const RecInner*)(all + r * strideBytes) + i; tag = tag_of_key8(p->key); O = p->minO; }
+	uint64_t slot;
+	if (!table_find_or_claim(t, tag, slot)) { slotOf[e] = NULLREF; return; }
+	if (t.minO[slot] > O) atomicMin(&t.minO[slot], (unsigned long long)O);
+	slotOf[e] = (uint32_t)slot;
+}
+// The global uid of a merged node must be the SAME on every rank (the next level's keys are built
+// from it), so it cannot come from an atomic counter: the winner of a slot (the record carrying the
+// slot's minimum order key) is flagged, and uid = exclusive scan of the flags over the gathered
+// buffer, which is byte-identical on all ranks.
+template <bool K64>
+__global__ void __launch_bounds__(DD_THREADS) k_import_flag(uint64_t total, uint64_t maxCount, const char* __restrict__ all, uint64_t strideBytes, TableDev t,
+                                                             const uint32_t* __restrict__ slotOf, uint32_t* __restrict__ flag) {
+	uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= total) return;
+	uint32_t slot = slotOf[e];
+	uint32_t f = 0;
+	if (slot != NULLREF) {
+		uint64_t O;
+		if (K64) O = ((const RecK64*)(all + (e / maxCount) * strideBytes) + (e % maxCount))->minO;
+		else O = ((const RecInner*)(all + (e / maxCount) * strideBytes) + (e % maxCount))->minO;
+		f = (t.minO[slot] == O) ? 1u : 0u;
+	}
+	flag[e] = f;
+}
+template <bool K64>
+__global__ void __launch_bounds__(DD_THREADS) k_import_assign(uint64_t total, uint64_t maxCount, const char* __restrict__ all, uint64_t strideBytes, TableDev t,
+                                                               const uint32_t* __restrict__ slotOf, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos,
+                                                               uint64_t* __restrict__ dMinO, uint64_t* __restrict__ dKey64, uint32_t* __restrict__ dKey8) {
+	uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= total || !flag[e]) return;
+	uint32_t slot = slotOf[e];
+	uint32_t u = pos[e];
+	t.uid[slot] = u;
+	if (K64) {
+		const RecK64* p = (const RecK64*)(all + (e / maxCount) * strideBytes) + (e % maxCount);
+		dMinO[u] = p->minO;
+		dKey64[u] = p->key;
+	} else {
+		const RecInner* p = (const RecInner*)(all + (e / maxCount) * strideBytes) + (e % maxCount);
+		dMinO[u] = p->minO;
+#pragma unroll
+		for (int c = 0; c < 8; ++c) dKey8[(uint64_t)u * 8 + c] = p->key[c];
+	}
+}
+__global__ void __launch_bounds__(DD_THREADS) k_import_verify(uint64_t total, uint64_t maxCount, const char* __restrict__ all, uint64_t strideBytes, TableDev t,
+                                                               const uint32_t* __restrict__ slotOf, const uint32_t* __restrict__ dKey8) {
+	uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= total) return;
+	uint32_t slot = slotOf[e];
+	if (slot == NULLREF) return;
+	const RecInner* p = (const RecInner*)(all + (e / maxCount) * strideBytes) + (e % maxCount);
+	uint32_t u = t.uid[slot];
+	bool same = true;
+#pragma unroll
+	for (int c = 0; c < 8; ++c) same &= (dKey8[(uint64_t)u * 8 + c] == p->key[c]);
+	if (!same) t.flags[1] = 1;
+}
+__global__ void __launch_bounds__(DD_THREADS) k_import_l2g(uint64_t n, const uint32_t* __restrict__ slotOfMine, const uint32_t* __restrict__ uid, uint32_t* __restrict__ l2g) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) l2g[i] = (slotOfMine[i] == NULLREF) ? NULLREF : uid[slotOfMine[i]];
+}
+__global__ void k_min256(uint32_t world, const unsigned long long* __restrict__ all, uint64_t strideWords, unsigned long long* __restrict__ out) {
+	unsigned i = threadIdx.x;
+	unsigned long long m = MAX_ORDER;
+	for (uint32_t r = 0; r < world; ++r) { unsigned long long v = all[r * strideWords + i]; if (v < m) m = v; }
+	out[i] = m;
+}
+
+}  // namespace
+
+uint32_t merge_rec_bytes(int kind) { return kind == KIND_LEAF ? 8u : (kind == KIND_K64 ? (uint32_t)sizeof(RecK64) : (uint32_t)sizeof(RecInner)); }
+uint64_t merge_count(const LevelTable& T) { return T.kind == KIND_LEAF ? 256 : T.count; }
+
+void merge_export(cudaStream_t s, Pool& pool, LevelTable& T, const uint32_t* l2gChild, void* d_out) {
+	(void)pool;
+	if (T.kind == KIND_LEAF) { SVB_CUDA(cudaMemcpyAsync(d_out, T.minO.p, 256 * 8, cudaMemcpyDeviceToDevice, s)); return; }
+	if (T.count == 0) return;
+	unsigned nb = blocks_for(T.count, DD_THREADS);
+	if (T.kind == KIND_K64) k_export_k64<<<nb, DD_THREADS, 0, s>>>(T.count, T.dKey64.p, T.dMinO.p, (RecK64*)d_out);
+	else {
+		if (!l2gChild) throw Error(SVB_EINVAL, "merge_export: the level below has not been merged yet");
+		k_export_inner<<<nb, DD_THREADS, 0, s>>>(T.count, T.dKey8.p, T.dMinO.p, l2gChild, (RecInner*)d_out);
+	}
+	SVB_KERNEL_CHECK();
+}
+
+void merge_import(cudaStream_t s, Pool& pool, LevelTable& T, const void* d_all, const uint64_t* counts, uint32_t world, uint64_t strideBytes,
+                  uint32_t myRank, DevBuf<uint32_t>& l2g) {
+	if (T.kind == KIND_LEAF) {
+		k_min256<<<1, 256, 0, s>>>(world, (const unsigned long long*)d_all, strideBytes / 8, (unsigned long long*)T.minO.p);
+		SVB_KERNEL_CHECK();
+		return;
+	}
+	const bool k64 = T.kind == KIND_K64;
+	uint64_t maxCount = 0, sum = 0;
+	for (uint32_t r = 0; r < world; ++r) { if (counts[r] > maxCount) maxCount = counts[r]; sum += counts[r]; }
+	const uint64_t myCount = counts[myRank];
+	l2g.reset(pool, myCount ? myCount : 1);
+	// fresh global table
+	LevelTable G;
+	G.kind = T.kind;
+	G.dCount.reset(pool, 1);
+	G.dCount.zero();
+	alloc_slots(s, pool, G, next_pow2(2 * sum + 1024));
+	if (sum) {
+		const uint64_t total = (uint64_t)world * maxCount;
+		DevBuf<uint64_t> dCounts(pool, world);
+		SVB_CUDA(cudaMemcpyAsync(dCounts.p, counts, world * 8ull, cudaMemcpyHostToDevice, s));
+		DevBuf<uint32_t> slotOf(pool, total), flags(pool, 4);
+		flags.zero();
+		TableDev t = dev_view(G, flags.p);
+		unsigned nb = blocks_for(total, DD_THREADS);
+		if (k64) k_import_insert<true><<<nb, DD_THREADS, 0, s>>>(total, maxCount, dCounts.p, (const char*)d_all, strideBytes, t, slotOf.p);
+		else k_import_insert<false><<<nb, DD_THREADS, 0, s>>>(total, maxCount, dCounts.p, (const char*)d_all, strideBytes, t, slotOf.p);
+		SVB_KERNEL_CHECK();
+		uint32_t h[4];
+		SVB_CUDA(cudaMemcpyAsync(h, flags.p, 16, cudaMemcpyDeviceToHost, s));
+		SVB_CUDA(cudaStreamSynchronize(s));
+		if (h[0]) throw Error(SVB_ECUDA, "merge_import: table overflow");
+		DevBuf<uint32_t> flag(pool, total), pos(pool, total);
+		DevBuf<uint64_t> dTot(pool, 1);
+		if (k64) k_import_flag<true><<<nb, DD_THREADS, 0, s>>>(total, maxCount, (const char*)d_all, strideBytes, t, slotOf.p, flag.p);
+		else k_import_flag<false><<<nb, DD_THREADS, 0, s>>>(total, maxCount, (const char*)d_all, strideBytes, t, slotOf.p, flag.p);
+		SVB_KERNEL_CHECK();
+		scan_u32(s, pool, flag.p, total, pos.p, dTot.p);
+		uint64_t fresh = 0;
+		SVB_CUDA(cudaMemcpyAsync(&fresh, dTot.p, 8, cudaMemcpyDeviceToHost, s));
+		SVB_CUDA(cudaStreamSynchronize(s));
+		if (fresh != h[2]) throw Error(SVB_ECUDA, "merge_import: winner count does not match the number of claimed slots");
+		ensure_dense(s, pool, G, fresh);
+		if (k64) k_import_assign<true><<<nb, DD_THREADS, 0, s>>>(total, maxCount, (const char*)d_all, strideBytes, t, slotOf.p, flag.p, pos.p, G.dMinO.p, G.dKey64.p, nullptr);
+		else k_import_assign<false><<<nb, DD_THREADS, 0, s>>>(total, maxCount, (const char*)d_all, strideBytes, t, slotOf.p, flag.p, pos.p, G.dMinO.p, nullptr, G.dKey8.p);
+		SVB_KERNEL_CHECK();
+		if (!k64) {
+			k_import_verify<<<nb, DD_THREADS, 0, s>>>(total, maxCount, (const char*)d_all, strideBytes, t, slotOf.p, G.dKey8.p);
+			SVB_KERNEL_CHECK();
+			SVB_CUDA(cudaMemcpyAsync(h, flags.p, 16, cudaMemcpyDeviceToHost, s));
+			SVB_CUDA(cudaStreamSynchronize(s));
+			if (h[1]) throw Error(SVB_ECOLLISION, "merge_import: 64-bit node-key hash collision (exact verify failed)");
+		}
+		SVB_CUDA(cudaMemcpyAsync(G.dCount.p, &fresh, 4, cudaMemcpyHostToDevice, s));   // little endian: low word
+		G.count = fresh;
+		if (myCount) {
+			k_import_l2g<<<blocks_for(myCount, DD_THREADS), DD_THREADS, 0, s>>>(myCount, slotOf.p + (uint64_t)myRank * maxCount, G.uid.p, l2g.p);
+			SVB_KERNEL_CHECK();
+		}
+		SVB_CUDA(cudaStreamSynchronize(s));
+	}
+	T = std::move(G);
 }
 
 void dedup_level(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a) {

@@ -16,7 +16,7 @@ struct DedupArgs {
 	const void* childRefs = nullptr;    // u8 masks | u32 uids | u32 masks
 	int l = 0;                          // octal digits of `path`
 	int tbits = 0;                      // bits of a triangle id
-	uint32_t seqBase = 0;               // global tile_seq of tile_local 0
+	const uint32_t* tileSeq = nullptr;  // device: tile_local -> global tile_seq (sub-octree sequence number)
 	uint32_t* ref = nullptr;            // out: uid of each node's unique representative (NULLREF = empty node)
 };
 
@@ -28,6 +28,14 @@ void dedup_leaf(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, u
 // KIND_K64 / KIND_INNER.  Throws Error(SVB_ECOLLISION) if the exact verify pass finds two different
 // keys behind one 64-bit tag.
 void dedup_level(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a);
+
+// ---- multi-GPU merge of one level (see svb_dedup.cu): record size / count to exchange, export of this
+// rank's unique nodes with global child uids, import of the all-gathered union into a fresh global table.
+uint32_t merge_rec_bytes(int kind);
+uint64_t merge_count(const LevelTable& T);
+void merge_export(cudaStream_t s, Pool& pool, LevelTable& T, const uint32_t* l2gChild, void* d_out);
+void merge_import(cudaStream_t s, Pool& pool, LevelTable& T, const void* d_all, const uint64_t* counts, uint32_t world, uint64_t strideBytes,
+                  uint32_t myRank, DevBuf<uint32_t>& l2g);
 
 // Level 0 is never reduced (geom_octree.cpp:483): just resolve the root's children.
 // rootKey: 8 x u32 (uids, or child masks when childMode is a MASK mode), NULLREF = none.

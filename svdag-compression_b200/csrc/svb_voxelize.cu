@@ -31,7 +31,6 @@ struct GridDesc {
 	double inv_cell;     // 1 / tile side
 	double margin;       // absolute
 	int G;               // tiles per axis
-	int seq_lo, seq_hi;  // tile_seq range of this batch [lo, hi)
 };
 
 __device__ inline void tile_range(double mn, double mx, double o, const GridDesc& g, int& a, int& b) {
@@ -43,7 +42,7 @@ __device__ inline void tile_range(double mn, double mx, double o, const GridDesc
 
 template <bool EMIT>
 __global__ void __launch_bounds__(VX_THREADS) k_candidates(const float* __restrict__ tris, uint64_t T, GridDesc g,
-                                                            const int* __restrict__ gridTile, uint32_t* __restrict__ cnt_or_off,
+                                                            const int* __restrict__ gridTile, const int* __restrict__ localOf, uint32_t* __restrict__ cnt_or_off,
                                                             uint32_t* __restrict__ ptri, uint32_t* __restrict__ pnode) {
 	uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= T) return;
@@ -60,9 +59,10 @@ __global__ void __launch_bounds__(VX_THREADS) k_candidates(const float* __restri
 	for (int x = ax; x <= bx; ++x)
 		for (int y = ay; y <= by; ++y)
 			for (int z = az; z <= bz; ++z) {
-				int s = gridTile[((size_t)x * g.G + y) * g.G + z];
-				if (s >= g.seq_lo && s < g.seq_hi) {
-					if (EMIT) { ptri[o + c] = (uint32_t)t; pnode[o + c] = (uint32_t)(s - g.seq_lo); }
+				int s = gridTile[((size_t)x * g.G + y) * g.G + z];   // global tile_seq of the cell, -1 = no tile
+				int loc = (s >= 0) ? localOf[s] : -1;                // index inside this batch, -1 = other batch / other rank
+				if (loc >= 0) {
+					if (EMIT) { ptri[o + c] = (uint32_t)t; pnode[o + c] = (uint32_t)loc; }
 					++c;
 				}
 			}
@@ -331,24 +331,23 @@ uint64_t read_u64(cudaStream_t s, const uint64_t* d) {
 
 // ------------------------------------------------------------------ host drivers
 void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T, const TileGridHost& grid,
-                     const int* d_gridTile, int seq_lo, int seq_hi, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t& P) {
+                     const int* d_gridTile, const int* d_localOf, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t& P) {
 	GridDesc g;
 	g.ox = grid.ox; g.oy = grid.oy; g.oz = grid.oz;
 	g.inv_cell = 1.0 / grid.cell;
 	g.margin = grid.cell * 1e-6;
 	g.G = grid.G;
-	g.seq_lo = seq_lo; g.seq_hi = seq_hi;
 	DevBuf<uint32_t> cnt(pool, T);
 	DevBuf<uint64_t> tot(pool, 1);
 	unsigned nb = blocks_for(T, VX_THREADS);
-	k_candidates<false><<<nb, VX_THREADS, 0, s>>>(d_tris, T, g, d_gridTile, cnt.p, nullptr, nullptr);
+	k_candidates<false><<<nb, VX_THREADS, 0, s>>>(d_tris, T, g, d_gridTile, d_localOf, cnt.p, nullptr, nullptr);
 	SVB_KERNEL_CHECK();
 	scan_u32(s, pool, cnt.p, T, cnt.p, tot.p);
 	P = read_u64(s, tot.p);
 	if (P >= 0xFFFFFFF0ull) throw BatchTooBig();
 	ptri.reset(pool, P);
 	pnode.reset(pool, P);
-	k_candidates<true><<<nb, VX_THREADS, 0, s>>>(d_tris, T, g, d_gridTile, cnt.p, ptri.p, pnode.p);
+	k_candidates<true><<<nb, VX_THREADS, 0, s>>>(d_tris, T, g, d_gridTile, d_localOf, cnt.p, ptri.p, pnode.p);
 	SVB_KERNEL_CHECK();
 }
 

@@ -19,9 +19,10 @@ struct TileGridHost {    // regular grid of tile cubes over the root cube (G = 2
 	int G = 1;
 };
 
-// (triangle, tile) candidate pairs for tiles with seq in [seq_lo, seq_hi); pairs sorted by triangle id.
+// (triangle, tile) candidate pairs for the tiles of one batch; pairs sorted by triangle id.
+// d_gridTile: grid cell -> global tile_seq (-1 none); d_localOf: global tile_seq -> index in the batch (-1 not in it).
 void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T, const TileGridHost& grid,
-                     const int* d_gridTile, int seq_lo, int seq_hi, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t& P);
+                     const int* d_gridTile, const int* d_localOf, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t& P);
 
 // Level-synchronous SVO build of `ntiles` sub-octrees of Lt levels each.  Consumes the root pairs.
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,

@@ -145,3 +145,66 @@ def test_filtered_classifier_equals_exact_predicate(pkg, meshgen, mesh, kw, leve
     for k in ("nTotalVoxels", "nNodesSVO", "nNodesDAG", "nPairsTotal"):
         assert sa[k] == sb[k], k
     _assert_levels_equal(a.levels_host(), b.levels_host(), "filtered vs exact")
+
+
+def _simulate_ranks(pkg, tris, levels, step, world):
+    """Run the multi-GPU protocol with `world` contexts on ONE device, doing the all-gathers by hand
+    (torch.cat of the per-rank export buffers).  Exercises svb_shard_* end to end without NCCL."""
+    import torch
+    dev = torch.device("cuda", 0)
+    octs = [pkg.GeomOctree(tris) for _ in range(world)]
+    bbox = octs[0].scene_bbox()
+    for r, o in enumerate(octs):
+        o.shard_build(levels, step, bbox, r, world)
+    first, last, ntiles, _ = octs[0].shard_info()
+    counters = [o.shard_info()[3] for o in octs]
+    for g in range(last, first - 1, -1):
+        cr = [o.shard_level_count(g) for o in octs]
+        counts = np.array([c[0] for c in cr], dtype=np.uint64)
+        rec = cr[0][1]
+        stride = int(max(16, (int(counts.max()) * rec + 15) // 16 * 16))
+        bufs = []
+        for o in octs:
+            b = torch.zeros(stride, dtype=torch.uint8, device=dev)
+            o.shard_export_level(g, b.data_ptr())
+            bufs.append(b)
+        allb = torch.cat(bufs)
+        torch.cuda.synchronize()
+        for o in octs:
+            o.shard_import_level(g, allb.data_ptr(), counts, stride)
+    nt = max(ntiles, 1)
+    roots = []
+    for o in octs:
+        b = torch.zeros(nt, dtype=torch.int32, device=dev)
+        o.shard_export_roots(b.data_ptr())
+        roots.append(b)
+    allr = torch.cat(roots)
+    torch.cuda.synchronize()
+    totals = np.sum(np.array(counters, dtype=np.uint64), axis=0)
+    stats = []
+    for o in octs:
+        o.shard_import_roots(allr.data_ptr())
+        stats.append(o.shard_finish(totals))
+    return octs, stats
+
+
+@pytest.mark.parametrize("mesh,kw,levels,step,world", [
+    ("sphere", dict(n_lat=64, n_lon=128), 9, 2, 2),
+    ("city", dict(lots=8), 9, 3, 4),
+    ("terrain", dict(n=64), 9, 2, 8),
+    ("sphere_menger", dict(n_lat=32, n_lon=64, sponge_level=2), 8, 5, 3),   # 2-level sub-octrees: roots are the K64 level
+], ids=["sphere-w2", "city-w4", "terrain-w8", "spongeball-w3"])
+def test_sharded_protocol_equals_single_gpu_build(pkg, meshgen, mesh, kw, levels, step, world):
+    tris = meshgen.make_mesh(mesh, **kw)
+    ref = pkg.GeomOctree(tris)
+    sref = ref.build(levels, step)
+    want = ref.levels_host()
+    octs, stats = _simulate_ranks(pkg, tris, levels, step, world)
+    for r, (o, st) in enumerate(zip(octs, stats)):
+        for k in ("nTotalVoxels", "nNodesSVO", "nNodesDAG", "nNodesLastLevSVO", "nPairsTotal"):
+            assert st[k] == sref[k], (r, k)
+        _assert_levels_equal(o.levels_host(), want, f"rank {r} of {world}")
+    # and the merged octree goes on through toSDAG + the encoders like any other
+    ref.to_sdag()
+    octs[-1].to_sdag()
+    assert pkg.encoders.encode(octs[-1], "ssvdag") == pkg.encoders.encode(ref, "ssvdag")
