@@ -18,7 +18,7 @@ SVBUILDER = HERE / "svbuilder"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = "/usr/bin/g++"   # the environment's CXX points at a compiler without libgomp; pin the system one
 
-CU_SOURCES = ["svb_prims.cu", "svb_voxelize.cu", "svb_dedup.cu", "svb_sdag.cu", "svb_api.cu", "host/encoders.cpp"]
+CU_SOURCES = ["svb_prims.cu", "svb_voxelize.cu", "svb_dedup.cu", "svb_sdag.cu", "svb_cross.cu", "svb_api.cu", "host/encoders.cpp"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unused-function",

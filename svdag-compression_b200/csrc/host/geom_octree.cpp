@@ -1,0 +1,113 @@
+#include "geom_octree.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+
+namespace svbhost {
+
+GeomOctree::GeomOctree(Scene* scene, int device) : _scene(scene) {
+	memset(&_stats, 0, sizeof(_stats));
+	_ctx = svb_create(device);
+	if (!_ctx) {
+		fprintf(stderr, "ERROR: no usable CUDA device %d (this build of svbuilder has no CPU path)\n", device);
+		exit(1);
+	}
+}
+GeomOctree::~GeomOctree() { svb_destroy(_ctx); }
+
+void GeomOctree::check(int rc, const char* what) {
+	if (rc == SVB_OK) return;
+	fprintf(stderr, "ERROR in %s: %s (code %d)\n", what, svb_last_error(_ctx), rc);
+	exit(1);   // the reference's fatal paths exit(1) too (e.g. encoded_ssvdag.cpp:251-254)
+}
+
+void GeomOctree::buildSVO(unsigned levels, const double bmin[3], const double bmax[3]) {
+	printf("* Building SVO... (deferred: voxelization and reduction run together on the GPU in toDAG)\n");
+	_pendingLevels = levels;
+	memcpy(_pendMin, bmin, 24);
+	memcpy(_pendMax, bmax, 24);
+	_state = S_SVO;
+}
+
+void GeomOctree::toDAG(bool internalCall) {
+	if (_state != S_SVO) { printf("ERROR! This is not a SVO!\n"); return; }   // geom_octree.cpp:466-469
+	if (!internalCall) { printf("* Transforming SVO -> DAG ... \n"); fflush(stdout); }
+	if (!_trisUploaded) { check(svb_set_triangles(_ctx, _scene->getTrianglePtr(), _scene->getNRawTriangles()), "svb_set_triangles"); _trisUploaded = true; }
+	check(svb_build(_ctx, _pendingLevels, 0, _pendMin, _pendMax, &_stats), "svb_build");
+	_levels = _pendingLevels;
+	for (unsigned lev = _levels - 1; lev > 0; --lev) {
+		uint64_t a = 0, b = 0;
+		svb_level_count_svo(_ctx, lev, &a);
+		svb_level_count(_ctx, lev, &b);
+		if (!internalCall) printf("Reduced level %u from %lu to %lu nodes\n", lev, (unsigned long)a, (unsigned long)b);   // :509
+	}
+	_state = S_DAG;
+	if (!internalCall) printf("OK! [%.2f ms on the GPU]\n", _stats.msTotal);
+}
+
+void GeomOctree::buildDAG(unsigned levels, unsigned stepLevel, const double bmin[3], const double bmax[3], bool verbose) {
+	printf("* Building DAG [stepLevel: %i]\n", stepLevel); fflush(stdout);
+	if (!_trisUploaded) { check(svb_set_triangles(_ctx, _scene->getTrianglePtr(), _scene->getNRawTriangles()), "svb_set_triangles"); _trisUploaded = true; }
+	check(svb_build(_ctx, levels, stepLevel, bmin, bmax, &_stats), "svb_build");
+	_levels = levels;
+	_state = S_DAG;
+	if (verbose) printf("\t- %lu subtrees in %lu device batches, %lu (triangle,node) pairs\n", (unsigned long)_stats.nTiles, (unsigned long)_stats.nBatches, (unsigned long)_stats.nPairsTotal);
+	printf("\t- Finished! Total time [%.2f ms on the GPU: voxelize %.2f, reduce %.2f, rank %.2f]\n", _stats.msTotal, _stats.msVoxelize, _stats.msDedup, _stats.msFinalize);
+}
+
+void GeomOctree::toSDAG(bool internalCall, bool skipSymmetry) {
+	if (skipSymmetry) { fprintf(stderr, "toSDAG(skipSymmetry=true) is not used by svbuilder and not provided\n"); exit(1); }
+	if (_state != S_DAG) { printf("ERROR! This is not a DAG or SDAG!\n"); return; }   // :560-563
+	if (!internalCall) { printf("* Transforming DAG -> SDAG (normal)... "); fflush(stdout); }
+	check(svb_to_sdag(_ctx, &_stats), "svb_to_sdag");
+	_state = S_SDAG;
+	if (!internalCall) printf("OK! [%.2f ms]\n", _stats.msSdag);
+}
+
+unsigned GeomOctree::mergeAcrossAllLevels() {
+	check(svb_cross_merge(_ctx, &_stats), "svb_cross_merge");
+	return (unsigned)_stats.nCrossLevelMerged;
+}
+
+void GeomOctree::resizeSceneBbox(const float mn[3], const float mx[3]) {
+	_bboxOverride = true;
+	float s = 0;
+	for (int k = 0; k < 3; ++k) { _bboxF[k] = mn[k]; _bboxF[3 + k] = mx[k]; float side = ((mx[k] - mn[k]) * 0.5f) * 2.0f; if (k == 0 || side > s) s = side; }
+	_rootSideOverride = s;
+}
+
+OctreeData GeomOctree::getNodeData() {
+	OctreeData o;
+	o.levels.resize(_levels);
+	for (unsigned l = 0; l < _levels; ++l) {
+		LevelSoA& h = o.levels[l];
+		uint64_t n = 0;
+		check(svb_level_count(_ctx, l, &n), "svb_level_count");
+		h.n = n;
+		h.mask.resize(n); h.child.resize(n * 8); h.mirror.resize(n * 3); h.inv.resize(n); h.childLevel.resize(n * 8);
+		check(svb_download_level(_ctx, l, h.mask.data(), h.child.data(), h.mirror.data(), h.inv.data(), h.childLevel.data()), "svb_download_level");
+	}
+	memcpy(o.bboxF, _bboxOverride ? _bboxF : _stats.bboxF, 24);
+	o.rootSide = _bboxOverride ? _rootSideOverride : _stats.rootSide;
+	o.nNodes = _stats.nNodes;
+	o.nVoxels = _stats.nTotalVoxels;
+	o.state = (int)_state;
+	return o;
+}
+
+bool GeomOctree::encodeToFile(int kind, const std::string& fileName, size_t* bytes) {
+	OctreeData o = getNodeData();
+	std::vector<uint8_t> img;
+	std::string err;
+	if (!encode_file(o, kind, img, &err)) { printf("%s\n", err.c_str()); return false; }
+	std::ofstream out(fileName, std::ios::binary);
+	if (!out.is_open()) { printf("FAILED!!!\n"); return false; }
+	out.write((const char*)img.data(), (std::streamsize)img.size());
+	if (bytes) *bytes = img.size();
+	return true;
+}
+
+}  // namespace svbhost

@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "svb_context.cuh"
+#include "svb_cross.cuh"
 #include "host/octree_data.hpp"
 #include "svb_dedup.cuh"
 #include "svb_sdag.cuh"
@@ -759,8 +760,20 @@ int svb_to_sdag(svb_ctx* c, svb_stats* out) {
 }
 
 int svb_cross_merge(svb_ctx* c, svb_stats* out) {
-	(void)out;
-	return guarded(c, [&] { throw Error(SVB_EINVAL, "cross-level merge is not implemented yet"); });
+	int rc = guarded(c, [&] {
+		if (c->state != SVB_S_DAG) throw Error(SVB_EINVAL, "cross-level merge needs an octree in DAG state");
+		const uint64_t launches0 = g_launches.load();
+		StageTimer tm(c->stream);
+		uint64_t nn = 0;
+		uint64_t removed = cross_merge_device(c, &nn);
+		c->stats.msCrossMerge = tm.stop();
+		c->stats.nCrossLevelMerged = removed;   // ext.cpp:1517
+		c->stats.nNodesDAG = nn;                // ext.cpp:1448
+		c->stats.nNodes = nn;
+		c->stats.nKernelLaunches = g_launches.load() - launches0;
+	});
+	if (rc == SVB_OK && out) *out = c->stats;
+	return rc;
 }
 
 int svb_state(const svb_ctx* c) { return c ? c->state : SVB_S_EMPTY; }

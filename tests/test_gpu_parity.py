@@ -208,3 +208,58 @@ def test_sharded_protocol_equals_single_gpu_build(pkg, meshgen, mesh, kw, levels
     ref.to_sdag()
     octs[-1].to_sdag()
     assert pkg.encoders.encode(octs[-1], "ssvdag") == pkg.encoders.encode(ref, "ssvdag")
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN if p.stem.endswith("_c")], ids=lambda p: p.stem)
+def test_cross_level_merge_golden_files(pkg, path):
+    """mesh -> SVDAG -> CSVDAG (-c): <base>_<L>.svdag and <base>_<L>-multi.svdag equal the reference's files."""
+    g = golden_case(path)
+    t = pkg.GeomOctree(g["tris"])
+    t.build(g["levels"], g["step"])
+    assert pkg.encoders.encode(t, "svdag") == g["files"]["svdag"]
+    t.cross_merge()
+    assert pkg.encoders.encode(t, "svdag") == g["files"]["multi_svdag"]
+
+
+@pytest.mark.parametrize("mesh,kw,levels,step", [
+    ("sphere", dict(n_lat=64, n_lon=128), 9, 0),
+    ("city", dict(lots=8), 9, 2),
+    ("terrain", dict(n=64), 8, 1),
+    ("sphere_menger", dict(n_lat=32, n_lon=64, sponge_level=2), 9, 2),
+], ids=["sphere", "city", "terrain", "spongeball"])
+def test_cross_level_merge_matches_oracle(pkg, orc, meshgen, mesh, kw, levels, step):
+    tris = meshgen.make_mesh(mesh, **kw)
+    o = orc.OracleOctree(tris)
+    o.build(levels, step)
+    removed = o.cross_merge()
+    t = pkg.GeomOctree(tris)
+    t.build(levels, step)
+    st = t.cross_merge()
+    assert st["nCrossLevelMerged"] == removed
+    assert st["nNodesDAG"] == o.stat("nNodesDAG")
+    got, want = t.levels_host(), _oracle_levels(o)
+    _assert_levels_equal(got, want, "CSVDAG", fields=("mask", "child"))
+    for l, (a, b) in enumerate(zip(got, want)):
+        live = b["child"] != 0xFFFFFFFE
+        assert np.array_equal(a["childLevel"][live], b["childLevel"][live]), f"childLevels differ at level {l}"
+    assert pkg.encoders.encode(t, "svdag") == o.encode("svdag")
+
+
+def test_svbuilder_cli_writes_reference_files(pkg, tmp_path):
+    """The C++ drop-in tool: `svbuilder m.obj L s` from an ASCII OBJ -> the four files of the reference, byte for byte."""
+    import subprocess
+    tool = pkg.lib_path().parent / "svbuilder"
+    if not tool.exists():
+        pytest.skip("svbuilder host tool not built")
+    for path in [p for p in GOLDEN if p.stem in ("sphere_L7_s1", "city_L7_s2", "terrain_L6_s0", "city_L7_s1_c")]:
+        g = golden_case(path)
+        d = tmp_path / g["name"]
+        d.mkdir()
+        pkg.meshgen.write_obj(d / "m.obj", g["tris"])
+        cmd = [str(tool), str(d / "m.obj"), str(g["levels"]), str(g["step"])] + (["-c"] if g["cross"] else [])
+        r = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        for ext, data in g["files"].items():
+            f = d / (f"m_{g['levels']}-multi.svdag" if ext == "multi_svdag" else f"m_{g['levels']}.{ext}")
+            assert f.read_bytes() == data, f"{g['name']}: {f.name} differs from the reference's file"
+        assert (d / "m.obj.bincache").exists() and (d / "stats.txt").exists()
