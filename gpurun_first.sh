@@ -1,6 +1,6 @@
 #!/bin/bash
-# scratch helper (not part of the product)
 cd /root/repo
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/pytest_gpu.log
 cat gpurun_out/pytest_gpu.log
+python gpurun_probe.py city256 terrain 2>&1 | grep -E "it[12]"

@@ -1,5 +1,6 @@
 #!/bin/bash
 # scratch: ncu launch list + full capture of the top kernels on a mid-size city build
+cd /root/repo
 mkdir -p gpurun_out
 cat > /tmp/ncu_target.py <<'PY'
 import sys
@@ -10,11 +11,9 @@ tris = pkg.meshgen.city(64)
 t = pkg.GeomOctree(tris)
 for it in range(2):
     st = t.build(12, 3); t.to_sdag()
-print(st["nTotalVoxels"], st["msTotal"], st["msVoxelize"], st["nKernelLaunches"])
+print(st["nTotalVoxels"], st["msTotal"], st["msVoxelize"], st["nKernelLaunches"], st["nExactTests"], st["nPairsTotal"])
 PY
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python gpurun_probe.py city256 2>&1 | tee gpurun_out/probe4.log | grep -E "it[0-9]|mesh"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_r1.csv python /tmp/ncu_target.py > gpurun_out/ncu_list.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_classify_filtered" -s 16 -c 8 -o gpurun_out/prof_classify python /tmp/ncu_target.py > gpurun_out/ncu_full.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_emit|k_leaf_min|k_insert|k_convert|k_children|k_scan_apply" -s 60 -c 30 -o gpurun_out/prof_rest python /tmp/ncu_target.py > gpurun_out/ncu_full2.log 2>&1
-tail -n 3 gpurun_out/ncu_list.log gpurun_out/ncu_full.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_r1b.csv python /tmp/ncu_target.py > gpurun_out/ncu_list.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_classify_filtered" -s 22 -c 2 -o gpurun_out/prof_classify2 python /tmp/ncu_target.py > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_emit|k_leaf_min|k_children" -s 36 -c 6 -o gpurun_out/prof_rest2 python /tmp/ncu_target.py > gpurun_out/ncu_full2.log 2>&1
+tail -n 2 gpurun_out/ncu_list.log

@@ -139,41 +139,75 @@ __device__ __forceinline__ void node_centre(uint64_t cd, int l, const TileGeom& 
 #define SVB_LO(b) ((b) == 4 ? 0x0Fu : (b) == 2 ? 0x33u : 0x55u)
 #define SVB_HI(b) ((b) == 4 ? 0xF0u : (b) == 2 ? 0xCCu : 0xAAu)
 
-// one edge-cross axis: p = ca*v[A] + cb*v[B] on vertices i and j; per child the centre moves by k*s,
-// so p_child = p_parent - k*(ca*sA + cb*sB); rad = (|ca|+|cb|)*k.
-// `degenerate`: both edge components are differences of bitwise-equal float inputs, hence exactly 0
-// for any box centre in the reference-order predicate too: p0 = p1 = +-0, rad = 0, and neither
-// "min > rad" nor "max < -rad" can hold -- the axis never separates (axis-aligned edges).
-__device__ __forceinline__ void edge_axis(bool degenerate, double ca, double cb, double viA, double viB, double vjA, double vjB, double k, double tol2,
-                                          unsigned bitA, unsigned bitB, unsigned& alive, unsigned& unsure) {
-	if (degenerate) return;
-	double pi = fma(ca, viA, cb * viB), pj = fma(ca, vjA, cb * vjB);
-	double mn = fmin(pi, pj), mx = fmax(pi, pj);
-	double rad = (fabs(ca) + fabs(cb)) * k;
-	double r2 = rad + rad;
-	// |shift| <= rad for every child, so if the parent centre projects strictly inside the triangle's
-	// interval (mn < 0 < mx) no child interval can leave [-rad, rad]: every child overlaps on this axis
+// Per-pair "settled axis" flags, inherited by every descendant pair of the same triangle: bit i set
+// means separating axis i can never reject a box that lies inside the pair's node, so it is skipped
+// from there on.  Large triangles settle all nine edge axes and the box axes a few levels above the
+// leaves; their deep pairs then cost one plane evaluation.
+//   bits 0..8  edge axes (edge 0: X,Y,Z; edge 1: X,Y,Z; edge 2: X,Y,Z)     bits 9..11 box axes x,y,z
+constexpr unsigned FL_BOX = 9;
+
+// One edge-cross axis: p = ca*v[A] + cb*v[B] on the two vertices the reference projects; the child with
+// signs (sA,sB) sees p - k*(ca*sA + cb*sB) against rad = (|ca|+|cb|)*k.  Straight-line over the four
+// sign combinations (each shared by two children).
+template <unsigned BITA, unsigned BITB>
+__device__ __forceinline__ void edge_axis(unsigned flbit, bool degenerate, double ca, double cb, double viA, double viB, double vjA, double vjB,
+                                          double k, double tol2, unsigned& alive, unsigned& unsure, unsigned& fl) {
+	// `degenerate`: both coefficients are differences of bitwise-equal float inputs, hence exactly 0 for any
+	// box centre in the reference-order predicate too: p0 = p1 = +-0, rad = 0, neither "min > rad" nor
+	// "max < -rad" can hold -- the axis never separates (axis-aligned edges).
+	if (degenerate) { fl |= flbit; return; }
+	const double pi = fma(ca, viA, cb * viB), pj = fma(ca, vjA, cb * vjB);
+	const bool swap = pj < pi;
+	const double mn = swap ? pj : pi, mx = swap ? pi : pj;
+	const double rad = (fabs(ca) + fabs(cb)) * k;
+	const double r2 = rad + rad;
+	// the whole NODE (half side 2k) projects strictly inside the triangle's interval: no box inside it can be
+	// separated on this axis, now or at any deeper level
+	if (mn + r2 < -tol2 && mx - r2 > tol2) { fl |= flbit; return; }
+	// |shift| <= rad for every child: parent centre strictly inside => every child overlaps on this axis
 	if (mn < -tol2 && mx > tol2) return;
-	if (mn > r2 + tol2 || mx < -r2 - tol2) { alive = 0; return; }      // no child does
-	double qa = k * ca, qb = k * cb;
-	unsigned m = alive;
-	while (m) {
-		int c = __ffs(m) - 1;
-		m &= m - 1;
-		double sh = ((c & bitA) ? qa : -qa) + ((c & bitB) ? qb : -qb);
-		double lo = mn - sh, hi = mx - sh;
-		if (lo > rad + tol2 || hi < -rad - tol2) alive &= ~(1u << c);
-		else if (!(lo < rad - tol2 && hi > -rad + tol2)) unsure |= 1u << c;
+	if (mn > r2 + tol2 || mx < -r2 - tol2) { alive = 0; return; }
+	const double qa = k * ca, qb = k * cb;
+	const double R1 = rad + tol2, R0 = rad - tol2;
+	const double spp = qa + qb, spm = qa - qb;
+#define SVB_COMBO(SH, MASK)                                                       \
+	{                                                                             \
+		const double lo = mn - (SH), hi = mx - (SH);                              \
+		if (lo > R1 || hi < -R1) alive &= ~(MASK);                                \
+		else if (!(lo < R0 && hi > -R0)) unsure |= (MASK);                        \
 	}
+	SVB_COMBO(spp, SVB_HI(BITA) & SVB_HI(BITB))
+	SVB_COMBO(spm, SVB_HI(BITA) & SVB_LO(BITB))
+	SVB_COMBO(-spm, SVB_LO(BITA) & SVB_HI(BITB))
+	SVB_COMBO(-spp, SVB_LO(BITA) & SVB_LO(BITB))
+#undef SVB_COMBO
 }
 
-__global__ void __launch_bounds__(VX_THREADS) k_classify_filtered(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
-                                                                   const uint64_t* __restrict__ code, int l, const TileGeom* __restrict__ tiles,
-                                                                   const float* __restrict__ tris, uint8_t* __restrict__ hit, uint8_t* __restrict__ mask,
-                                                                   unsigned long long* __restrict__ nExact) {
+// children the filter could not decide: the reference-order predicate decides (kept out of line so that
+// its registers do not burden the filter)
+__device__ __noinline__ unsigned exact_children(unsigned unsure, double Cx, double Cy, double Cz, double k, const float* __restrict__ tp) {
+	float tf[9];
+#pragma unroll
+	for (int i = 0; i < 9; ++i) tf[i] = tp[i];
+	unsigned m = 0;
+	while (unsure) {
+		int c = __ffs(unsure) - 1;
+		unsure &= unsure - 1;
+		double cx = __dadd_rn(Cx, (c & 4) ? k : -k), cy = __dadd_rn(Cy, (c & 2) ? k : -k), cz = __dadd_rn(Cz, (c & 1) ? k : -k);
+		if (tri_box_overlap(cx, cy, cz, k, tf)) m |= 1u << c;
+	}
+	return m;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(VX_THREADS, MINB) k_classify_filtered(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
+                                                                   uint16_t* __restrict__ pflags, const uint64_t* __restrict__ code, int l,
+                                                                   const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
+                                                                   uint8_t* __restrict__ hit, uint8_t* __restrict__ mask, unsigned long long* __restrict__ nExact) {
 	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= P) return;
 	const uint32_t t = ptri[p], n = pnode[p];
+	unsigned fl = pflags[p];
 	const uint64_t cd = code[n];
 	const TileGeom tg = tiles[(uint32_t)(cd >> (3 * l))];
 	double Cx, Cy, Cz, k;
@@ -185,74 +219,89 @@ __global__ void __launch_bounds__(VX_THREADS) k_classify_filtered(uint64_t P, co
 	const double v0x = (double)tf[0] - Cx, v0y = (double)tf[1] - Cy, v0z = (double)tf[2] - Cz;
 	const double v1x = (double)tf[3] - Cx, v1y = (double)tf[4] - Cy, v1z = (double)tf[5] - Cz;
 	const double v2x = (double)tf[6] - Cx, v2y = (double)tf[7] - Cy, v2z = (double)tf[8] - Cz;
+	// Axis-aligned ("flat") triangles -- all three vertices share a bitwise-equal coordinate, as every face of
+	// a box mesh does.  Say x is shared: the edge x-components are exactly 0 in the reference-order predicate
+	// for any box centre, the normal is (nx, +-0, +-0), and
+	//   * the six Y-/Z-type edge axes degenerate to  fl(|e|*|vx|) > fl(|e|*h)  (both projected vertices coincide),
+	//   * the plane test degenerates to  vx < -h  or  vx > h,
+	// all of which are implied false by the box-axis test on x (|vx| <= h; rounding is monotone).  So for such a
+	// triangle the predicate IS box-x & box-y & box-z & the three X-type axes: the other seven tests are settled
+	// from the start, rigorously (no tolerance involved).
+	bool planeImplied = false;
+	if (tf[0] == tf[3] && tf[3] == tf[6]) { fl |= 0x1B6u; planeImplied = true; }   // Y,Z-type axes of all edges
+	if (tf[1] == tf[4] && tf[4] == tf[7]) { fl |= 0x16Du; planeImplied = true; }   // X,Z-type
+	if (tf[2] == tf[5] && tf[5] == tf[8]) { fl |= 0x0DBu; planeImplied = true; }   // X,Y-type
 	const double k2 = k + k;
 	double M = fmax(fmax(fmax(fabs(v0x), fabs(v0y)), fmax(fabs(v0z), fabs(v1x))), fmax(fmax(fabs(v1y), fabs(v1z)), fmax(fabs(v2x), fmax(fabs(v2y), fabs(v2z))))) + k2;
 	const double eps = 9.094947017729282e-13;   // 2^-40
 	const double tol1 = M * eps, tol2 = M * tol1, tol3 = M * tol2;
 	unsigned alive = 0xFFu, unsure = 0;
 	// --- box axes: child with bit clear sits at -k, with bit set at +k
-#define SVB_BOX_AXIS(a0, a1, a2, BIT)                                                          \
-	{                                                                                          \
+#define SVB_BOX_AXIS(a0, a1, a2, BIT, FLB)                                                     \
+	if (!(fl & (FLB))) {                                                                       \
 		double mn = fmin(fmin(a0, a1), a2), mx = fmax(fmax(a0, a1), a2);                       \
-		if (mn > tol1 || mx < -k2 - tol1) alive &= ~SVB_LO(BIT);                               \
-		else if (!(mn < -tol1 && mx > -k2 + tol1)) unsure |= SVB_LO(BIT);                      \
-		if (mn > k2 + tol1 || mx < -tol1) alive &= ~SVB_HI(BIT);                               \
-		else if (!(mn < k2 - tol1 && mx > tol1)) unsure |= SVB_HI(BIT);                        \
+		if (mn + k2 < -tol1 && mx - k2 > tol1) fl |= (FLB);   /* node strictly inside the triangle's slab */ \
+		else {                                                                                 \
+			if (mn > tol1 || mx < -k2 - tol1) alive &= ~SVB_LO(BIT);                           \
+			else if (!(mn < -tol1 && mx > -k2 + tol1)) unsure |= SVB_LO(BIT);                  \
+			if (mn > k2 + tol1 || mx < -tol1) alive &= ~SVB_HI(BIT);                           \
+			else if (!(mn < k2 - tol1 && mx > tol1)) unsure |= SVB_HI(BIT);                    \
+		}                                                                                      \
 	}
-	SVB_BOX_AXIS(v0x, v1x, v2x, 4)
-	SVB_BOX_AXIS(v0y, v1y, v2y, 2)
-	SVB_BOX_AXIS(v0z, v1z, v2z, 1)
+	SVB_BOX_AXIS(v0x, v1x, v2x, 4, 1u << (FL_BOX + 0))
+	SVB_BOX_AXIS(v0y, v1y, v2y, 2, 1u << (FL_BOX + 1))
+	SVB_BOX_AXIS(v0z, v1z, v2z, 1, 1u << (FL_BOX + 2))
 #undef SVB_BOX_AXIS
 	if (alive) {
 		const double e0x = v1x - v0x, e0y = v1y - v0y, e0z = v1z - v0z;
 		const double e1x = v2x - v1x, e1y = v2y - v1y, e1z = v2z - v1z;
-		// --- plane: overlap <=> |N.v0| <= k*(|Nx|+|Ny|+|Nz|)
+		// --- plane: overlap <=> |N.v0| <= k*(|Nx|+|Ny|+|Nz|); straight-line over the 8 sign combinations
 		const double nx = fma(e0y, e1z, -(e0z * e1y)), ny = fma(e0z, e1x, -(e0x * e1z)), nz = fma(e0x, e1y, -(e0y * e1x));
 		const double g = fma(nx, v0x, fma(ny, v0y, nz * v0z));
 		const double r = k * (fabs(nx) + fabs(ny) + fabs(nz));
 		const double dx = k * nx, dy = k * ny, dz = k * nz;
-		unsigned m = alive;
-		while (m) {
-			int c = __ffs(m) - 1;
-			m &= m - 1;
-			double gc = fabs(g - (((c & 4) ? dx : -dx) + ((c & 2) ? dy : -dy) + ((c & 1) ? dz : -dz))) - r;
-			if (gc > tol3) alive &= ~(1u << c);
-			else if (gc > -tol3) unsure |= 1u << c;
+		if (!planeImplied) {
+			const double rp = r + tol3, rm = r - tol3;
+			const double g0 = g + dx, g1 = g - dx;                      // x bit clear / set
+			const double g00 = g0 + dy, g01 = g0 - dy, g10 = g1 + dy, g11 = g1 - dy;
+#define SVB_PLANE(GV, C)                                                          \
+			{                                                                     \
+				const double a = fabs(GV);                                        \
+				if (a > rp) alive &= ~(1u << (C));                                \
+				else if (a > rm) unsure |= 1u << (C);                             \
+			}
+			SVB_PLANE(g00 + dz, 0) SVB_PLANE(g00 - dz, 1) SVB_PLANE(g01 + dz, 2) SVB_PLANE(g01 - dz, 3)
+			SVB_PLANE(g10 + dz, 4) SVB_PLANE(g10 - dz, 5) SVB_PLANE(g11 + dz, 6) SVB_PLANE(g11 - dz, 7)
+#undef SVB_PLANE
 		}
-		if (alive) {
+		if (alive && (fl & 0x1FFu) != 0x1FFu) {
 			const double e2x = v0x - v2x, e2y = v0y - v2y, e2z = v0z - v2z;
 			// bitwise-equal input coordinates => that edge component is exactly zero in either evaluation
 			const bool x01 = tf[0] == tf[3], y01 = tf[1] == tf[4], z01 = tf[2] == tf[5];
 			const bool x12 = tf[3] == tf[6], y12 = tf[4] == tf[7], z12 = tf[5] == tf[8];
 			const bool x20 = tf[6] == tf[0], y20 = tf[7] == tf[1], z20 = tf[8] == tf[2];
 			// edge 0: X01(v0,v2)  Y02(v0,v2)  Z12(v1,v2)      p_X = ez*vy - ey*vz, p_Y = -ez*vx + ex*vz, p_Z = ey*vx - ex*vy
-			edge_axis(z01 && y01, e0z, -e0y, v0y, v0z, v2y, v2z, k, tol2, 2, 1, alive, unsure);
-			if (alive) edge_axis(z01 && x01, -e0z, e0x, v0x, v0z, v2x, v2z, k, tol2, 4, 1, alive, unsure);
-			if (alive) edge_axis(y01 && x01, e0y, -e0x, v1x, v1y, v2x, v2y, k, tol2, 4, 2, alive, unsure);
+			if (!(fl & 0x001u)) edge_axis<2, 1>(0x001u, z01 && y01, e0z, -e0y, v0y, v0z, v2y, v2z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x002u)) edge_axis<4, 1>(0x002u, z01 && x01, -e0z, e0x, v0x, v0z, v2x, v2z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x004u)) edge_axis<4, 2>(0x004u, y01 && x01, e0y, -e0x, v1x, v1y, v2x, v2y, k, tol2, alive, unsure, fl);
 			// edge 1: X01(v0,v2)  Y02(v0,v2)  Z0(v0,v1)
-			if (alive) edge_axis(z12 && y12, e1z, -e1y, v0y, v0z, v2y, v2z, k, tol2, 2, 1, alive, unsure);
-			if (alive) edge_axis(z12 && x12, -e1z, e1x, v0x, v0z, v2x, v2z, k, tol2, 4, 1, alive, unsure);
-			if (alive) edge_axis(y12 && x12, e1y, -e1x, v0x, v0y, v1x, v1y, k, tol2, 4, 2, alive, unsure);
+			if (alive && !(fl & 0x008u)) edge_axis<2, 1>(0x008u, z12 && y12, e1z, -e1y, v0y, v0z, v2y, v2z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x010u)) edge_axis<4, 1>(0x010u, z12 && x12, -e1z, e1x, v0x, v0z, v2x, v2z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x020u)) edge_axis<4, 2>(0x020u, y12 && x12, e1y, -e1x, v0x, v0y, v1x, v1y, k, tol2, alive, unsure, fl);
 			// edge 2: X2(v0,v1)  Y1(v0,v1)  Z12(v1,v2)
-			if (alive) edge_axis(z20 && y20, e2z, -e2y, v0y, v0z, v1y, v1z, k, tol2, 2, 1, alive, unsure);
-			if (alive) edge_axis(z20 && x20, -e2z, e2x, v0x, v0z, v1x, v1z, k, tol2, 4, 1, alive, unsure);
-			if (alive) edge_axis(y20 && x20, e2y, -e2x, v1x, v1y, v2x, v2y, k, tol2, 4, 2, alive, unsure);
+			if (alive && !(fl & 0x040u)) edge_axis<2, 1>(0x040u, z20 && y20, e2z, -e2y, v0y, v0z, v1y, v1z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x080u)) edge_axis<4, 1>(0x080u, z20 && x20, -e2z, e2x, v0x, v0z, v1x, v1z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x100u)) edge_axis<4, 2>(0x100u, y20 && x20, e2y, -e2x, v1x, v1y, v2x, v2y, k, tol2, alive, unsure, fl);
 		}
 	}
 	unsure &= alive;
 	unsigned m = alive & ~unsure;
 	if (unsure) {
-		unsigned u = unsure, ne = 0;
-		while (u) {
-			int c = __ffs(u) - 1;
-			u &= u - 1;
-			++ne;
-			double cx = __dadd_rn(Cx, (c & 4) ? k : -k), cy = __dadd_rn(Cy, (c & 2) ? k : -k), cz = __dadd_rn(Cz, (c & 1) ? k : -k);
-			if (tri_box_overlap(cx, cy, cz, k, tf)) m |= 1u << c;
-		}
-		if (nExact) atomicAdd(nExact, (unsigned long long)ne);
+		m |= exact_children(unsure, Cx, Cy, Cz, k, tp);
+		if (nExact) atomicAdd(nExact, (unsigned long long)__popc(unsure));
 	}
 	hit[p] = (uint8_t)m;
+	pflags[p] = (uint16_t)fl;   // inherited by the child pairs (k_emit)
 	if (m) {
 		unsigned cur = mask[n];
 		if ((cur & m) != m) atomicOr(reinterpret_cast<unsigned*>(mask) + (n >> 2), m << (8 * (n & 3)));
@@ -279,14 +328,15 @@ __global__ void __launch_bounds__(VX_THREADS) k_children(uint64_t N, const uint6
 // emit the child pairs of every pair; first-touch triangle by atomicMin (pairs are sorted by
 // triangle, so after the first touch the pre-check load filters almost every later atomic)
 __global__ void __launch_bounds__(VX_THREADS) k_emit(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
-                                                      const uint8_t* __restrict__ hit, const uint32_t* __restrict__ poff,
+                                                      const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit, const uint32_t* __restrict__ poff,
                                                       const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase,
-                                                      uint32_t* __restrict__ otri, uint32_t* __restrict__ onode, uint32_t* __restrict__ ctstar) {
+                                                      uint32_t* __restrict__ otri, uint32_t* __restrict__ onode, uint16_t* __restrict__ oflags, uint32_t* __restrict__ ctstar) {
 	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= P) return;
 	unsigned m = hit[p];
 	if (!m) return;
 	uint32_t t = ptri[p], n = pnode[p];
+	const uint16_t fl = pflags[p];
 	unsigned nm = mask[n];
 	uint32_t base = childBase[n];
 	uint32_t o = poff[p];
@@ -296,6 +346,7 @@ __global__ void __launch_bounds__(VX_THREADS) k_emit(uint64_t P, const uint32_t*
 		uint32_t child = base + __popc(nm & ((1u << c) - 1));
 		otri[o] = t;
 		onode[o] = child;
+		oflags[o] = fl;
 		++o;
 		if (ctstar[child] > t) atomicMin(&ctstar[child], t);
 	}
@@ -363,6 +414,8 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 	SVB_KERNEL_CHECK();
 	DevBuf<uint64_t> tot(pool, 1);
 	pairsTotal = 0;
+	DevBuf<uint16_t> pflags(pool, P + 8);   // settled-axis flags per pair (see k_classify_filtered)
+	pflags.zero();
 	for (int l = 0; l < Lt; ++l) {
 		BatchLevel& L = lv[l];
 		L.mask.reset(pool, (L.n + 3 + 16) & ~3ull);
@@ -372,11 +425,32 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 			if (P > (1ull << 59)) throw Error(SVB_ERANGE, "too many pairs");
 			if (classify_exact_only())
 				k_classify<<<blocks_for(P * 8, VX_THREADS), VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p);
-			else
-				k_classify_filtered<<<blocks_for(P, VX_THREADS), VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p, (unsigned long long*)d_nExact);
+			else {
+				static const int occ = [] { const char* e = getenv("SVB_VX_OCC"); return e ? atoi(e) : 4; }();
+				unsigned nb = blocks_for(P, VX_THREADS);
+				if (occ >= 6) k_classify_filtered<6><<<nb, VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, pflags.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p, (unsigned long long*)d_nExact);
+				else if (occ == 5) k_classify_filtered<5><<<nb, VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, pflags.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p, (unsigned long long*)d_nExact);
+				else if (occ >= 4) k_classify_filtered<4><<<nb, VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, pflags.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p, (unsigned long long*)d_nExact);
+				else if (occ == 3) k_classify_filtered<3><<<nb, VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, pflags.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p, (unsigned long long*)d_nExact);
+				else k_classify_filtered<1><<<nb, VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, pflags.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p, (unsigned long long*)d_nExact);
+			}
 			SVB_KERNEL_CHECK();
 		}
 		pairsTotal += P;
+		if (getenv("SVB_VX_STATS") && P) {   // debug: how many axes are settled per pair at this level
+			uint64_t ns = P < 4000000 ? P : 4000000;
+			std::vector<uint16_t> hf(ns);
+			std::vector<uint8_t> hh(ns);
+			SVB_CUDA(cudaMemcpyAsync(hf.data(), pflags.p + (P - ns) / 2, ns * 2, cudaMemcpyDeviceToHost, s));
+			SVB_CUDA(cudaMemcpyAsync(hh.data(), hit.p + (P - ns) / 2, ns, cudaMemcpyDeviceToHost, s));
+			SVB_CUDA(cudaStreamSynchronize(s));
+			uint64_t hist[13] = {0}, allEdge = 0, allBox = 0, hits = 0;
+			for (uint64_t i = 0; i < ns; ++i) { hist[__builtin_popcount(hf[i])]++; allEdge += (hf[i] & 0x1FF) == 0x1FF; allBox += (hf[i] >> 9) == 7; hits += __builtin_popcount(hh[i]); }
+			fprintf(stderr, "[vx-stats] level %d P=%llu sample=%llu allEdge=%.3f allBox=%.3f hits/pair=%.2f hist:", l, (unsigned long long)P, (unsigned long long)ns,
+			        (double)allEdge / ns, (double)allBox / ns, (double)hits / ns);
+			for (int i = 0; i <= 12; ++i) fprintf(stderr, " %.3f", (double)hist[i] / ns);
+			fprintf(stderr, "\n");
+		}
 		if (l == Lt - 1) break;
 		// children
 		L.childBase.reset(pool, L.n);
@@ -417,12 +491,14 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		k_children<<<blocks_for(L.n, VX_THREADS), VX_THREADS, 0, s>>>(L.n, L.code.p, L.mask.p, L.childBase.p, C.code.p);
 		SVB_KERNEL_CHECK();
 		DevBuf<uint32_t> ntri(pool, Pn), nnode(pool, Pn);
+		DevBuf<uint16_t> nflags(pool, Pn + 8);
 		if (P) {
-			k_emit<<<blocks_for(P, VX_THREADS), VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, hit.p, poff.p, L.mask.p, L.childBase.p, ntri.p, nnode.p, C.tstar.p);
+			k_emit<<<blocks_for(P, VX_THREADS), VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, pflags.p, hit.p, poff.p, L.mask.p, L.childBase.p, ntri.p, nnode.p, nflags.p, C.tstar.p);
 			SVB_KERNEL_CHECK();
 		}
 		ptri = std::move(ntri);
 		pnode = std::move(nnode);
+		pflags = std::move(nflags);
 		P = Pn;
 	}
 	ptri.release();
