@@ -66,13 +66,35 @@ __device__ __forceinline__ uint64_t tag_of_key8(const uint32_t k[8]) {
 }
 
 // ------------------------------------------------------------------ KIND_LEAF
+// 4 nodes per thread per trip, 128-bit loads (1 x uchar4 masks, 1 x uint4 t*, 2 x ulonglong2 codes): the kernel
+// only streams 13 B/node, so bytes in flight per thread decide how close it gets to the HBM roofline.
 __global__ void __launch_bounds__(DD_THREADS) k_leaf_min(DedupArgs a, unsigned long long* __restrict__ gmin, unsigned long long* __restrict__ voxels) {
 	__shared__ unsigned long long smin[256];
 	smin[threadIdx.x] = MAX_ORDER;
 	__syncthreads();
 	unsigned vox = 0;
-	uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; n < a.N; n += stride) {
+	const uint64_t nq = a.N >> 2;   // full quads
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	const uchar4* __restrict__ m4 = reinterpret_cast<const uchar4*>(a.mask);
+	const uint4* __restrict__ t4 = reinterpret_cast<const uint4*>(a.tstar);
+	const ulonglong2* __restrict__ c2 = reinterpret_cast<const ulonglong2*>(a.code);
+	for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+		const uchar4 mm = m4[q];
+		const uint4 tt = t4[q];
+		const ulonglong2 ca = c2[2 * q], cb = c2[2 * q + 1];
+		const unsigned m[4] = {mm.x, mm.y, mm.z, mm.w};
+		const uint32_t ts[4] = {tt.x, tt.y, tt.z, tt.w};
+		const unsigned long long cd[4] = {ca.x, ca.y, cb.x, cb.y};
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			if (!m[j]) continue;
+			vox += __popc(m[j]);
+			unsigned long long O = order_key(cd[j], ts[j], a.l, a.tbits, a.tileSeq);
+			if (smin[m[j]] > O) atomicMin(&smin[m[j]], O);
+		}
+	}
+	// tail (< 4 nodes)
+	for (uint64_t n = (nq << 2) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; n < a.N; n += stride) {
 		unsigned m = a.mask[n];
 		if (!m) continue;
 		vox += __popc(m);
@@ -348,7 +370,7 @@ void dedup_leaf(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, u
 	(void)pool;
 	if (a.N == 0) return;
 	unsigned nb = blocks_for(a.N, DD_THREADS * 16);
-	if (nb > 148 * 8) nb = 148 * 8;
+	if (nb > 148 * 8) nb = 148 * 8;   // persistent-style grid: 8 CTAs of 256 threads per SM, grid-stride
 	k_leaf_min<<<nb, DD_THREADS, 0, s>>>(a, (unsigned long long*)T.minO.p, (unsigned long long*)d_voxels);
 	SVB_KERNEL_CHECK();
 }
