@@ -238,7 +238,9 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 		DevBuf<uint32_t> ptri, pnode;
 		uint64_t P = 0;
 		make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, dLocal.p, ptri, pnode, P);
-		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, P, budget, nodeCap, lv, pairs, B.dExact.p);
+		bool direct = true;
+		for (uint32_t i = 0; i < nt && direct; ++i) direct = centre_chain_exact(hg[i], Lt);
+		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, P, budget, nodeCap, lv, pairs, B.dExact.p, direct);
 		ps.done(pairs, 36.0 * (double)c->T + 9.0 * (double)lv[Lt - 1].n);
 		B.msVox += tm.stop();
 	}
@@ -484,6 +486,24 @@ void build_finish(svb_ctx* c, const uint64_t* totals) {
 			const TileHost& t = B.tiles[q];
 			int r = __builtin_popcount(hmask[t.baseNode] & ((1u << t.j) - 1));
 			seqOf[cb[t.baseNode] + r] = q;
+		}
+		// A sub-octree whose root came out EMPTY although the base octree set its bit (its cube is rebuilt from a
+		// float-narrowed box, geom_octree.cpp:340-344 -> :177-184, so it can be a hair smaller than the base child
+		// cube; a triangle that only touches the base cube's face then misses every child of the sub-octree):
+		// the reference keeps the parent's bit, and its last toDAG pass skips the empty node, leaving
+		// correspondences[] at 0 (:495, :519-526) -- the child pointer ends up at UNIQUE NODE 0 of level s1,
+		// i.e. at the root of the first non-empty sub-octree in join order.  Reproduced here, bit for bit.
+		{
+			const bool maskMode = (kind_of(s1, L) == KIND_LEAF);
+			std::vector<uint32_t> hroot = download(s, B.tileRootRef.p, B.tiles.size());
+			auto empty = [&](uint32_t v) { return v == UNSET || (maskMode && v == 0); };
+			uint32_t first = UNSET;
+			for (uint32_t v : hroot) if (!empty(v)) { first = v; break; }
+			bool patched = false;
+			if (first != UNSET)
+				for (uint32_t& v : hroot) if (empty(v)) { v = first; patched = true; }
+			if (patched) SVB_CUDA(cudaMemcpyAsync(B.tileRootRef.p, hroot.data(), hroot.size() * 4ull, cudaMemcpyHostToDevice, s));
+			SVB_CUDA(cudaStreamSynchronize(s));
 		}
 		DevBuf<uint32_t> dSeq, dCb, dZero;
 		upload(s, c->pool, dSeq, seqOf);

@@ -1,0 +1,291 @@
+// svb_classify.cuh -- the per-pair decision of the voxelizer: which of the 8 children of a node does a triangle
+// overlap, bit-identical with 8 calls of the reference's testTriBox (src/symvox/test_triangle_box.cpp:105-184).
+//
+// Written as host/device code: libsvb.so only ever runs it inside k_classify_filtered (svb_voxelize.cu);
+// tests/classify_harness.cpp compiles the same source with g++ so that the filter can be checked against the
+// reference-order predicate on the CPU, pair by pair (test infrastructure, not a fallback).
+#pragma once
+#include <stdint.h>
+
+#include <cmath>
+
+#include "svb_sat.cuh"
+
+namespace svb {
+
+#ifndef SVB_TILEGEOM_DEFINED
+#define SVB_TILEGEOM_DEFINED
+struct TileGeom {   // host computed, exactly as geom_octree.cpp:177-184,214 / :340-344 would
+	double cx, cy, cz;   // root centre (double)
+	double rootSide;     // float-rounded max side, widened
+};
+#endif
+
+// ------------------------------------------------------------------ classify, filtered (default)
+// One thread per pair decides all 8 children.  A cheap FP64 filter, evaluated relative to the PARENT
+// centre and shared between the children, decides every child whose 13 separating-axis inequalities
+// hold or fail with a margin far above any rounding error (tolerances 2^-40 relative, i.e. >= 4000x
+// the worst-case accumulated error of either evaluation order); the few children that sit within
+// that margin of a threshold (exact ties such as a wall lying in a voxel face) are re-decided by the
+// reference-order predicate tri_box_overlap().  The result is therefore bit-identical to testing all
+// 8 children with tri_box_overlap() (k_classify above, kept selectable with SVB_CLASSIFY=exact and
+// compared against in tests/test_gpu_parity.py), at ~1/5 of the FP64 work for large triangles:
+// interior nodes pass all nine edge axes at the parent level and never evaluate them per child.
+SVB_HD void node_centre(uint64_t cd, int l, const TileGeom& tg, double& cx, double& cy, double& cz, double& k) {
+	cx = tg.cx; cy = tg.cy; cz = tg.cz;
+	k = tg.rootSide * 0.25;
+	for (int d = l - 1; d >= 0; --d) {
+		int dig = (int)((cd >> (3 * d)) & 7);
+		cx = SVB_DADD(cx, (dig & 4) ? k : -k);
+		cy = SVB_DADD(cy, (dig & 2) ? k : -k);
+		cz = SVB_DADD(cz, (dig & 1) ? k : -k);
+		k *= 0.5;
+	}
+}
+
+// Direct form of the same chain.  Every partial sum of the chain is c0 + (integer) * k_finest; when the host
+// has verified that all those values are representable doubles for every tile of the batch (centre_chain_exact()),
+// each rounding of the chain is the identity and the chain equals  c0 + k * (4X - 2^(l+1) + 2),  X = the node's
+// integer coordinate inside the tile (de-interleaved path), evaluated with one exact product and one exact sum.
+SVB_HD uint32_t compact3(uint64_t v, int l) {   // bits 0,3,6,... of v -> contiguous
+	if (l <= 10) {
+		uint32_t x = (uint32_t)v & 0x09249249u;
+		x = (x ^ (x >> 2)) & 0x030c30c3u;
+		x = (x ^ (x >> 4)) & 0x0300f00fu;
+		x = (x ^ (x >> 8)) & 0x030000ffu;
+		x = (x ^ (x >> 16)) & 0x000003ffu;
+		return x;
+	}
+	v &= 0x1249249249249249ull;
+	v = (v ^ (v >> 2)) & 0x10c30c30c30c30c3ull;
+	v = (v ^ (v >> 4)) & 0x100f00f00f00f00full;
+	v = (v ^ (v >> 8)) & 0x001f0000ff0000ffull;
+	v = (v ^ (v >> 16)) & 0x001f00000000ffffull;
+	v = (v ^ (v >> 32)) & 0x00000000001fffffull;
+	return (uint32_t)v;
+}
+// one coordinate of the node centre; sh = 2 (x), 1 (y), 0 (z); k = child half side of level l
+SVB_HD double centre_axis_direct(uint64_t path, int l, int sh, double c0, double k) {
+	const int X = (int)compact3(path >> sh, l);
+	const int m = 4 * X - (2 << l) + 2;
+	return SVB_FMA((double)m, k, c0);
+}
+SVB_HD double centre_axis_chain(uint64_t cd, int l, int sh, double c0, double rootSide) {
+	double c = c0, k = rootSide * 0.25;
+	for (int d = l - 1; d >= 0; --d) {
+		c = SVB_DADD(c, ((cd >> (3 * d + sh)) & 1) ? k : -k);
+		k *= 0.5;
+	}
+	return c;
+}
+
+// children whose index has bit `b` clear / set
+#define SVB_LO(b) ((b) == 4 ? 0x0Fu : (b) == 2 ? 0x33u : 0x55u)
+#define SVB_HI(b) ((b) == 4 ? 0xF0u : (b) == 2 ? 0xCCu : 0xAAu)
+
+// Per-pair "settled axis" flags, inherited by every descendant pair of the same triangle: bit i set
+// means separating axis i can never reject a box that lies inside the pair's node, so it is skipped
+// from there on.  Large triangles settle all nine edge axes and the box axes a few levels above the
+// leaves; their deep pairs then cost one plane evaluation.
+//   bits 0..8  edge axes (edge 0: X,Y,Z; edge 1: X,Y,Z; edge 2: X,Y,Z)     bits 9..11 box axes x,y,z
+//   bits 12..14  the triangle is flat on x / y / z (all three vertices share that coordinate bitwise)
+constexpr unsigned FL_BOX = 9;
+constexpr unsigned FL_FLAT = 12;
+
+// One edge-cross axis: p = ca*v[A] + cb*v[B] on the two vertices the reference projects; the child with
+// signs (sA,sB) sees p - k*(ca*sA + cb*sB) against rad = (|ca|+|cb|)*k.  Straight-line over the four
+// sign combinations (each shared by two children).
+template <unsigned BITA, unsigned BITB>
+SVB_HD void edge_axis(unsigned flbit, bool degenerate, double ca, double cb, double viA, double viB, double vjA, double vjB,
+                                          double k, double tol2, unsigned& alive, unsigned& unsure, unsigned& fl) {
+	// `degenerate`: both coefficients are differences of bitwise-equal float inputs, hence exactly 0 for any
+	// box centre in the reference-order predicate too: p0 = p1 = +-0, rad = 0, neither "min > rad" nor
+	// "max < -rad" can hold -- the axis never separates (axis-aligned edges).
+	if (degenerate) { fl |= flbit; return; }
+	const double pi = fma(ca, viA, cb * viB), pj = fma(ca, vjA, cb * vjB);
+	const bool swap = pj < pi;
+	const double mn = swap ? pj : pi, mx = swap ? pi : pj;
+	const double rad = (fabs(ca) + fabs(cb)) * k;
+	const double r2 = rad + rad;
+	// the whole NODE (half side 2k) projects strictly inside the triangle's interval: no box inside it can be
+	// separated on this axis, now or at any deeper level
+	if (mn + r2 < -tol2 && mx - r2 > tol2) { fl |= flbit; return; }
+	// |shift| <= rad for every child: parent centre strictly inside => every child overlaps on this axis
+	if (mn < -tol2 && mx > tol2) return;
+	if (mn > r2 + tol2 || mx < -r2 - tol2) { alive = 0; return; }
+	const double qa = k * ca, qb = k * cb;
+	const double R1 = rad + tol2, R0 = rad - tol2;
+	const double spp = qa + qb, spm = qa - qb;
+#define SVB_COMBO(SH, MASK)                                                       \
+	{                                                                             \
+		const double lo = mn - (SH), hi = mx - (SH);                              \
+		if (lo > R1 || hi < -R1) alive &= ~(MASK);                                \
+		else if (!(lo < R0 && hi > -R0)) unsure |= (MASK);                        \
+	}
+	SVB_COMBO(spp, SVB_HI(BITA) & SVB_HI(BITB))
+	SVB_COMBO(spm, SVB_HI(BITA) & SVB_LO(BITB))
+	SVB_COMBO(-spm, SVB_LO(BITA) & SVB_HI(BITB))
+	SVB_COMBO(-spp, SVB_LO(BITA) & SVB_LO(BITB))
+#undef SVB_COMBO
+}
+
+// children the filter could not decide: the reference-order predicate decides (kept out of line so that
+// its registers do not burden the filter)
+SVB_HD_NOINLINE unsigned exact_children(unsigned unsure, double Cx, double Cy, double Cz, double k, const float* __restrict__ tp) {
+	float tf[9];
+#pragma unroll
+	for (int i = 0; i < 9; ++i) tf[i] = tp[i];
+	unsigned m = 0;
+	while (unsure) {
+		int c = SVB_FFS(unsure) - 1;
+		unsure &= unsure - 1;
+		double cx = SVB_DADD(Cx, (c & 4) ? k : -k), cy = SVB_DADD(Cy, (c & 2) ? k : -k), cz = SVB_DADD(Cz, (c & 1) ? k : -k);
+		if (tri_box_overlap(cx, cy, cz, k, tf)) m |= 1u << c;
+	}
+	return m;
+}
+
+// ---- "fast" pairs: a flat (axis-aligned) triangle whose nine edge axes and two in-plane box axes are settled.
+// Seven of the thirteen tests are implied by the flat-axis box test (see classify_pair), five are settled for
+// every box inside the pair's node, so the predicate of child c IS the reference's box test on the flat axis a:
+//   v = fl(t_a - fl(C_a +- k));  overlap <=> !(v > k || v < -k)      (test_triangle_box.cpp:165-174)
+// evaluated in the reference's own operation order -- exact, no tolerance, one coordinate.  The flags of a fast
+// pair never change, so all its descendants are fast too: the voxelizer keeps them in a separate pair stream.
+SVB_HD bool pair_is_fast(unsigned fl) {
+	const unsigned ub = (~fl >> FL_BOX) & 7u;   // unsettled box axes (bit 0 = x)
+	return (fl & 0x1FFu) == 0x1FFu && ub != 0 && (ub & (ub - 1)) == 0 && ((fl >> FL_FLAT) & ub) != 0;
+}
+SVB_HD int fast_axis(unsigned fl) {   // 0 = x, 1 = y, 2 = z
+	const unsigned ub = (~fl >> FL_BOX) & 7u;
+	return (ub == 1u) ? 0 : (ub == 2u) ? 1 : 2;
+}
+template <bool DIRECT>
+SVB_HD unsigned classify_pair_fast(const uint64_t cd, const int l, const double c0, const double rootSide, const double kscale, const float ta_f, const int a) {
+	const double k = rootSide * kscale;
+	const uint64_t path = cd & ((1ull << (3 * l)) - 1);
+	const double C = DIRECT ? centre_axis_direct(path, l, 2 - a, c0, k) : centre_axis_chain(cd, l, 2 - a, c0, rootSide);
+	const double ta = (double)ta_f;
+	const double vLo = SVB_DSUB(ta, SVB_DADD(C, -k)), vHi = SVB_DSUB(ta, SVB_DADD(C, k));
+	const unsigned lo = (a == 0) ? 0x0Fu : (a == 1) ? 0x33u : 0x55u;
+	unsigned m = 0;
+	if (!(vLo > k || vLo < -k)) m |= lo;
+	if (!(vHi > k || vHi < -k)) m |= lo ^ 0xFFu;
+	return m;
+}
+
+// Decides the 8 children of the node with Morton code `cd` (tile-local level l, tile geometry tg) against the
+// triangle tp[0..8].  fl: the pair's settled-axis flags (in: inherited from the parent pair, out: for the child
+// pairs).  nUnsure: children that had to be re-decided by the reference-order predicate.  Returns the hit mask.
+template <bool DIRECT>
+SVB_HD unsigned classify_pair(const uint64_t cd, const int l, const TileGeom& tg, const double kscale, const float* __restrict__ tp,
+                              unsigned& fl, unsigned& nUnsure) {
+	nUnsure = 0;
+	const double k = tg.rootSide * kscale;   // child half side rootSide / 2^(l+2) (octree.hpp:115), exact scaling
+	const uint64_t path = cd & ((1ull << (3 * l)) - 1);
+	if (pair_is_fast(fl)) {   // never taken inside k_classify_filtered: such pairs live in the fast stream (k_classify_fast)
+		const int a = fast_axis(fl);
+		const double c0 = (a == 0) ? tg.cx : (a == 1) ? tg.cy : tg.cz;
+		return classify_pair_fast<DIRECT>(cd, l, c0, tg.rootSide, kscale, tp[a], a);   // flags unchanged
+	}
+	double Cx, Cy, Cz;
+	if (DIRECT) {
+		Cx = centre_axis_direct(path, l, 2, tg.cx, k);
+		Cy = centre_axis_direct(path, l, 1, tg.cy, k);
+		Cz = centre_axis_direct(path, l, 0, tg.cz, k);
+	} else {
+		double kk;
+		node_centre(cd, l, tg, Cx, Cy, Cz, kk);
+	}
+	float tf[9];
+#pragma unroll
+	for (int i = 0; i < 9; ++i) tf[i] = tp[i];
+	const double v0x = (double)tf[0] - Cx, v0y = (double)tf[1] - Cy, v0z = (double)tf[2] - Cz;
+	const double v1x = (double)tf[3] - Cx, v1y = (double)tf[4] - Cy, v1z = (double)tf[5] - Cz;
+	const double v2x = (double)tf[6] - Cx, v2y = (double)tf[7] - Cy, v2z = (double)tf[8] - Cz;
+	// Axis-aligned ("flat") triangles -- all three vertices share a bitwise-equal coordinate, as every face of
+	// a box mesh does.  Say x is shared: the edge x-components are exactly 0 in the reference-order predicate
+	// for any box centre, the normal is (nx, +-0, +-0), and
+	//   * the six Y-/Z-type edge axes degenerate to  fl(|e|*|vx|) > fl(|e|*h)  (both projected vertices coincide),
+	//   * the plane test degenerates to  vx < -h  or  vx > h,
+	// all of which are implied false by the box-axis test on x (|vx| <= h; rounding is monotone).  So for such a
+	// triangle the predicate IS box-x & box-y & box-z & the three X-type axes: the other seven tests are settled
+	// from the start, rigorously (no tolerance involved).
+	bool planeImplied = false;
+	if (tf[0] == tf[3] && tf[3] == tf[6]) { fl |= 0x1B6u | (1u << (FL_FLAT + 0)); planeImplied = true; }   // Y,Z-type axes of all edges
+	if (tf[1] == tf[4] && tf[4] == tf[7]) { fl |= 0x16Du | (1u << (FL_FLAT + 1)); planeImplied = true; }   // X,Z-type
+	if (tf[2] == tf[5] && tf[5] == tf[8]) { fl |= 0x0DBu | (1u << (FL_FLAT + 2)); planeImplied = true; }   // X,Y-type
+	const double k2 = k + k;
+	double M = fmax(fmax(fmax(fabs(v0x), fabs(v0y)), fmax(fabs(v0z), fabs(v1x))), fmax(fmax(fabs(v1y), fabs(v1z)), fmax(fabs(v2x), fmax(fabs(v2y), fabs(v2z))))) + k2;
+	const double eps = 9.094947017729282e-13;   // 2^-40
+	const double tol1 = M * eps, tol2 = M * tol1, tol3 = M * tol2;
+	unsigned alive = 0xFFu, unsure = 0;
+	// --- box axes: child with bit clear sits at -k, with bit set at +k
+#define SVB_BOX_AXIS(a0, a1, a2, BIT, FLB)                                                     \
+	if (!(fl & (FLB))) {                                                                       \
+		double mn = fmin(fmin(a0, a1), a2), mx = fmax(fmax(a0, a1), a2);                       \
+		if (mn + k2 < -tol1 && mx - k2 > tol1) fl |= (FLB);   /* node strictly inside the triangle's slab */ \
+		else {                                                                                 \
+			if (mn > tol1 || mx < -k2 - tol1) alive &= ~SVB_LO(BIT);                           \
+			else if (!(mn < -tol1 && mx > -k2 + tol1)) unsure |= SVB_LO(BIT);                  \
+			if (mn > k2 + tol1 || mx < -tol1) alive &= ~SVB_HI(BIT);                           \
+			else if (!(mn < k2 - tol1 && mx > tol1)) unsure |= SVB_HI(BIT);                    \
+		}                                                                                      \
+	}
+	SVB_BOX_AXIS(v0x, v1x, v2x, 4, 1u << (FL_BOX + 0))
+	SVB_BOX_AXIS(v0y, v1y, v2y, 2, 1u << (FL_BOX + 1))
+	SVB_BOX_AXIS(v0z, v1z, v2z, 1, 1u << (FL_BOX + 2))
+#undef SVB_BOX_AXIS
+	if (alive) {
+		const double e0x = v1x - v0x, e0y = v1y - v0y, e0z = v1z - v0z;
+		const double e1x = v2x - v1x, e1y = v2y - v1y, e1z = v2z - v1z;
+		// --- plane: overlap <=> |N.v0| <= k*(|Nx|+|Ny|+|Nz|); straight-line over the 8 sign combinations
+		const double nx = fma(e0y, e1z, -(e0z * e1y)), ny = fma(e0z, e1x, -(e0x * e1z)), nz = fma(e0x, e1y, -(e0y * e1x));
+		const double g = fma(nx, v0x, fma(ny, v0y, nz * v0z));
+		const double r = k * (fabs(nx) + fabs(ny) + fabs(nz));
+		const double dx = k * nx, dy = k * ny, dz = k * nz;
+		if (!planeImplied) {
+			const double rp = r + tol3, rm = r - tol3;
+			const double g0 = g + dx, g1 = g - dx;                      // x bit clear / set
+			const double g00 = g0 + dy, g01 = g0 - dy, g10 = g1 + dy, g11 = g1 - dy;
+#define SVB_PLANE(GV, C)                                                          \
+			{                                                                     \
+				const double a = fabs(GV);                                        \
+				if (a > rp) alive &= ~(1u << (C));                                \
+				else if (a > rm) unsure |= 1u << (C);                             \
+			}
+			SVB_PLANE(g00 + dz, 0) SVB_PLANE(g00 - dz, 1) SVB_PLANE(g01 + dz, 2) SVB_PLANE(g01 - dz, 3)
+			SVB_PLANE(g10 + dz, 4) SVB_PLANE(g10 - dz, 5) SVB_PLANE(g11 + dz, 6) SVB_PLANE(g11 - dz, 7)
+#undef SVB_PLANE
+		}
+		if (alive && (fl & 0x1FFu) != 0x1FFu) {
+			const double e2x = v0x - v2x, e2y = v0y - v2y, e2z = v0z - v2z;
+			// bitwise-equal input coordinates => that edge component is exactly zero in either evaluation
+			const bool x01 = tf[0] == tf[3], y01 = tf[1] == tf[4], z01 = tf[2] == tf[5];
+			const bool x12 = tf[3] == tf[6], y12 = tf[4] == tf[7], z12 = tf[5] == tf[8];
+			const bool x20 = tf[6] == tf[0], y20 = tf[7] == tf[1], z20 = tf[8] == tf[2];
+			// edge 0: X01(v0,v2)  Y02(v0,v2)  Z12(v1,v2)      p_X = ez*vy - ey*vz, p_Y = -ez*vx + ex*vz, p_Z = ey*vx - ex*vy
+			if (!(fl & 0x001u)) edge_axis<2, 1>(0x001u, z01 && y01, e0z, -e0y, v0y, v0z, v2y, v2z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x002u)) edge_axis<4, 1>(0x002u, z01 && x01, -e0z, e0x, v0x, v0z, v2x, v2z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x004u)) edge_axis<4, 2>(0x004u, y01 && x01, e0y, -e0x, v1x, v1y, v2x, v2y, k, tol2, alive, unsure, fl);
+			// edge 1: X01(v0,v2)  Y02(v0,v2)  Z0(v0,v1)
+			if (alive && !(fl & 0x008u)) edge_axis<2, 1>(0x008u, z12 && y12, e1z, -e1y, v0y, v0z, v2y, v2z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x010u)) edge_axis<4, 1>(0x010u, z12 && x12, -e1z, e1x, v0x, v0z, v2x, v2z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x020u)) edge_axis<4, 2>(0x020u, y12 && x12, e1y, -e1x, v0x, v0y, v1x, v1y, k, tol2, alive, unsure, fl);
+			// edge 2: X2(v0,v1)  Y1(v0,v1)  Z12(v1,v2)
+			if (alive && !(fl & 0x040u)) edge_axis<2, 1>(0x040u, z20 && y20, e2z, -e2y, v0y, v0z, v1y, v1z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x080u)) edge_axis<4, 1>(0x080u, z20 && x20, -e2z, e2x, v0x, v0z, v1x, v1z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x100u)) edge_axis<4, 2>(0x100u, y20 && x20, e2y, -e2x, v1x, v1y, v2x, v2y, k, tol2, alive, unsure, fl);
+		}
+	}
+	unsure &= alive;
+	unsigned m = alive & ~unsure;
+	if (unsure) {
+		m |= exact_children(unsure, Cx, Cy, Cz, k, tp);
+		nUnsure = (unsigned)SVB_POPC(unsure);
+	}
+	return m;
+}
+#undef SVB_LO
+#undef SVB_HI
+
+}  // namespace svb

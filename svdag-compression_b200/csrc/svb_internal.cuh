@@ -174,10 +174,13 @@ struct DevBuf {
 };
 
 // ------------------------------------------------------------------ geometry of one (sub-)octree
+#ifndef SVB_TILEGEOM_DEFINED
+#define SVB_TILEGEOM_DEFINED
 struct TileGeom {   // host computed, exactly as geom_octree.cpp:177-184,214 / :340-344 would
 	double cx, cy, cz;   // root centre (double)
 	double rootSide;     // float-rounded max side, widened
 };
+#endif
 
 // ------------------------------------------------------------------ one level of the current tile batch
 struct BatchLevel {
@@ -224,6 +227,8 @@ struct OutLevel {
 // ------------------------------------------------------------------ primitives (svb_prims.cu)
 // exclusive scan of popcount(bytes[i]) -> out[i] (uint32), returns total through *d_total (device, u64)
 void scan_popc8(cudaStream_t s, Pool& pool, const uint8_t* bytes, uint64_t n, uint32_t* out, uint64_t* d_total);
+// same, counting only the pairs whose flags make their children "fast" pairs (pair_is_fast, svb_classify.cuh)
+void scan_popc8_fast(cudaStream_t s, Pool& pool, const uint8_t* bytes, const uint16_t* flags, uint64_t n, uint32_t* out, uint64_t* d_total);
 // exclusive scan of uint32 values (in place allowed), total to *d_total
 void scan_u32(cudaStream_t s, Pool& pool, const uint32_t* in, uint64_t n, uint32_t* out, uint64_t* d_total);
 // stable LSD radix sort of (key u64, val u32) pairs on the low `bits` bits of the key.

@@ -9,9 +9,12 @@
 // Layout per level (SoA, nodes in Morton order, tile-major):
 //   code[n]  u64  (tile_local << 3l) | path      tstar[n] u32      mask[n] u8      childBase[n] u32
 // Pairs: tri[p] u32, node[p] u32, hit[p] u8 -- pairs stay sorted by triangle id at every level.
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include "svb_internal.cuh"
+#include "svb_classify.cuh"
 #include "svb_sat.cuh"
 #include "svb_voxelize.cuh"
 
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(VX_THREADS) k_candidates(const float* __restri
 // (geom_octree.cpp:222-230), so it carries exactly the reference's roundings for any bbox.
 __global__ void __launch_bounds__(VX_THREADS) k_classify(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
                                                           const uint64_t* __restrict__ code, int l, const TileGeom* __restrict__ tiles,
-                                                          const float* __restrict__ tris, uint8_t* __restrict__ hit, uint8_t* __restrict__ mask) {
+                                                          const float* __restrict__ tris, uint8_t* __restrict__ hit, uint8_t* __restrict__ mask, int last) {
 	uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	uint64_t p = gid >> 3;
 	int c = (int)(gid & 7);
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(VX_THREADS) k_classify(uint64_t P, const uint3
 	int lane = threadIdx.x & 31;
 	unsigned m = (b >> (lane & 24)) & 0xFFu;
 	if (c == 0 && p < P) {
-		hit[p] = (uint8_t)m;
+		if (!last) hit[p] = (uint8_t)m;
 		if (m) {
 			unsigned cur = mask[n];   // may be stale (L1); bits only ever get set, so a stale value only costs an extra atomic
 			if ((cur & m) != m) atomicOr(reinterpret_cast<unsigned*>(mask) + (n >> 2), m << (8 * (n & 3)));
@@ -114,201 +117,31 @@ __global__ void __launch_bounds__(VX_THREADS) k_classify(uint64_t P, const uint3
 }
 
 // ------------------------------------------------------------------ classify, filtered (default)
-// One thread per pair decides all 8 children.  A cheap FP64 filter, evaluated relative to the PARENT
-// centre and shared between the children, decides every child whose 13 separating-axis inequalities
-// hold or fail with a margin far above any rounding error (tolerances 2^-40 relative, i.e. >= 4000x
-// the worst-case accumulated error of either evaluation order); the few children that sit within
-// that margin of a threshold (exact ties such as a wall lying in a voxel face) are re-decided by the
-// reference-order predicate tri_box_overlap().  The result is therefore bit-identical to testing all
-// 8 children with tri_box_overlap() (k_classify above, kept selectable with SVB_CLASSIFY=exact and
-// compared against in tests/test_gpu_parity.py), at ~1/5 of the FP64 work for large triangles:
-// interior nodes pass all nine edge axes at the parent level and never evaluate them per child.
-__device__ __forceinline__ void node_centre(uint64_t cd, int l, const TileGeom& tg, double& cx, double& cy, double& cz, double& k) {
-	cx = tg.cx; cy = tg.cy; cz = tg.cz;
-	k = tg.rootSide * 0.25;
-	for (int d = l - 1; d >= 0; --d) {
-		int dig = (int)((cd >> (3 * d)) & 7);
-		cx = __dadd_rn(cx, (dig & 4) ? k : -k);
-		cy = __dadd_rn(cy, (dig & 2) ? k : -k);
-		cz = __dadd_rn(cz, (dig & 1) ? k : -k);
-		k *= 0.5;
-	}
-}
-
-// children whose index has bit `b` clear / set
-#define SVB_LO(b) ((b) == 4 ? 0x0Fu : (b) == 2 ? 0x33u : 0x55u)
-#define SVB_HI(b) ((b) == 4 ? 0xF0u : (b) == 2 ? 0xCCu : 0xAAu)
-
-// Per-pair "settled axis" flags, inherited by every descendant pair of the same triangle: bit i set
-// means separating axis i can never reject a box that lies inside the pair's node, so it is skipped
-// from there on.  Large triangles settle all nine edge axes and the box axes a few levels above the
-// leaves; their deep pairs then cost one plane evaluation.
-//   bits 0..8  edge axes (edge 0: X,Y,Z; edge 1: X,Y,Z; edge 2: X,Y,Z)     bits 9..11 box axes x,y,z
-constexpr unsigned FL_BOX = 9;
-
-// One edge-cross axis: p = ca*v[A] + cb*v[B] on the two vertices the reference projects; the child with
-// signs (sA,sB) sees p - k*(ca*sA + cb*sB) against rad = (|ca|+|cb|)*k.  Straight-line over the four
-// sign combinations (each shared by two children).
-template <unsigned BITA, unsigned BITB>
-__device__ __forceinline__ void edge_axis(unsigned flbit, bool degenerate, double ca, double cb, double viA, double viB, double vjA, double vjB,
-                                          double k, double tol2, unsigned& alive, unsigned& unsure, unsigned& fl) {
-	// `degenerate`: both coefficients are differences of bitwise-equal float inputs, hence exactly 0 for any
-	// box centre in the reference-order predicate too: p0 = p1 = +-0, rad = 0, neither "min > rad" nor
-	// "max < -rad" can hold -- the axis never separates (axis-aligned edges).
-	if (degenerate) { fl |= flbit; return; }
-	const double pi = fma(ca, viA, cb * viB), pj = fma(ca, vjA, cb * vjB);
-	const bool swap = pj < pi;
-	const double mn = swap ? pj : pi, mx = swap ? pi : pj;
-	const double rad = (fabs(ca) + fabs(cb)) * k;
-	const double r2 = rad + rad;
-	// the whole NODE (half side 2k) projects strictly inside the triangle's interval: no box inside it can be
-	// separated on this axis, now or at any deeper level
-	if (mn + r2 < -tol2 && mx - r2 > tol2) { fl |= flbit; return; }
-	// |shift| <= rad for every child: parent centre strictly inside => every child overlaps on this axis
-	if (mn < -tol2 && mx > tol2) return;
-	if (mn > r2 + tol2 || mx < -r2 - tol2) { alive = 0; return; }
-	const double qa = k * ca, qb = k * cb;
-	const double R1 = rad + tol2, R0 = rad - tol2;
-	const double spp = qa + qb, spm = qa - qb;
-#define SVB_COMBO(SH, MASK)                                                       \
-	{                                                                             \
-		const double lo = mn - (SH), hi = mx - (SH);                              \
-		if (lo > R1 || hi < -R1) alive &= ~(MASK);                                \
-		else if (!(lo < R0 && hi > -R0)) unsure |= (MASK);                        \
-	}
-	SVB_COMBO(spp, SVB_HI(BITA) & SVB_HI(BITB))
-	SVB_COMBO(spm, SVB_HI(BITA) & SVB_LO(BITB))
-	SVB_COMBO(-spm, SVB_LO(BITA) & SVB_HI(BITB))
-	SVB_COMBO(-spp, SVB_LO(BITA) & SVB_LO(BITB))
-#undef SVB_COMBO
-}
-
-// children the filter could not decide: the reference-order predicate decides (kept out of line so that
-// its registers do not burden the filter)
-__device__ __noinline__ unsigned exact_children(unsigned unsure, double Cx, double Cy, double Cz, double k, const float* __restrict__ tp) {
-	float tf[9];
-#pragma unroll
-	for (int i = 0; i < 9; ++i) tf[i] = tp[i];
-	unsigned m = 0;
-	while (unsure) {
-		int c = __ffs(unsure) - 1;
-		unsure &= unsure - 1;
-		double cx = __dadd_rn(Cx, (c & 4) ? k : -k), cy = __dadd_rn(Cy, (c & 2) ? k : -k), cz = __dadd_rn(Cz, (c & 1) ? k : -k);
-		if (tri_box_overlap(cx, cy, cz, k, tf)) m |= 1u << c;
-	}
-	return m;
-}
-
-template <int MINB>
+// One thread per pair decides all 8 children with classify_pair() (svb_classify.cuh): exact single-axis fast path
+// for settled flat triangles, FP64 interval filter + reference-order predicate for the rest.
+template <int MINB, bool DIRECT>
 __global__ void __launch_bounds__(VX_THREADS, MINB) k_classify_filtered(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
-                                                                   uint16_t* __restrict__ pflags, const uint64_t* __restrict__ code, int l,
+                                                                   uint16_t* __restrict__ pflags, const uint64_t* __restrict__ code, int l, double kscale, int last,
                                                                    const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
                                                                    uint8_t* __restrict__ hit, uint8_t* __restrict__ mask, unsigned long long* __restrict__ nExact) {
 	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= P) return;
 	const uint32_t t = ptri[p], n = pnode[p];
-	unsigned fl = pflags[p];
+	const unsigned fl0 = pflags[p];
+	unsigned fl = fl0, nUnsure;
 	const uint64_t cd = code[n];
 	const TileGeom tg = tiles[(uint32_t)(cd >> (3 * l))];
-	double Cx, Cy, Cz, k;
-	node_centre(cd, l, tg, Cx, Cy, Cz, k);
-	const float* tp = tris + 9ull * t;
-	float tf[9];
-#pragma unroll
-	for (int i = 0; i < 9; ++i) tf[i] = tp[i];
-	const double v0x = (double)tf[0] - Cx, v0y = (double)tf[1] - Cy, v0z = (double)tf[2] - Cz;
-	const double v1x = (double)tf[3] - Cx, v1y = (double)tf[4] - Cy, v1z = (double)tf[5] - Cz;
-	const double v2x = (double)tf[6] - Cx, v2y = (double)tf[7] - Cy, v2z = (double)tf[8] - Cz;
-	// Axis-aligned ("flat") triangles -- all three vertices share a bitwise-equal coordinate, as every face of
-	// a box mesh does.  Say x is shared: the edge x-components are exactly 0 in the reference-order predicate
-	// for any box centre, the normal is (nx, +-0, +-0), and
-	//   * the six Y-/Z-type edge axes degenerate to  fl(|e|*|vx|) > fl(|e|*h)  (both projected vertices coincide),
-	//   * the plane test degenerates to  vx < -h  or  vx > h,
-	// all of which are implied false by the box-axis test on x (|vx| <= h; rounding is monotone).  So for such a
-	// triangle the predicate IS box-x & box-y & box-z & the three X-type axes: the other seven tests are settled
-	// from the start, rigorously (no tolerance involved).
-	bool planeImplied = false;
-	if (tf[0] == tf[3] && tf[3] == tf[6]) { fl |= 0x1B6u; planeImplied = true; }   // Y,Z-type axes of all edges
-	if (tf[1] == tf[4] && tf[4] == tf[7]) { fl |= 0x16Du; planeImplied = true; }   // X,Z-type
-	if (tf[2] == tf[5] && tf[5] == tf[8]) { fl |= 0x0DBu; planeImplied = true; }   // X,Y-type
-	const double k2 = k + k;
-	double M = fmax(fmax(fmax(fabs(v0x), fabs(v0y)), fmax(fabs(v0z), fabs(v1x))), fmax(fmax(fabs(v1y), fabs(v1z)), fmax(fabs(v2x), fmax(fabs(v2y), fabs(v2z))))) + k2;
-	const double eps = 9.094947017729282e-13;   // 2^-40
-	const double tol1 = M * eps, tol2 = M * tol1, tol3 = M * tol2;
-	unsigned alive = 0xFFu, unsure = 0;
-	// --- box axes: child with bit clear sits at -k, with bit set at +k
-#define SVB_BOX_AXIS(a0, a1, a2, BIT, FLB)                                                     \
-	if (!(fl & (FLB))) {                                                                       \
-		double mn = fmin(fmin(a0, a1), a2), mx = fmax(fmax(a0, a1), a2);                       \
-		if (mn + k2 < -tol1 && mx - k2 > tol1) fl |= (FLB);   /* node strictly inside the triangle's slab */ \
-		else {                                                                                 \
-			if (mn > tol1 || mx < -k2 - tol1) alive &= ~SVB_LO(BIT);                           \
-			else if (!(mn < -tol1 && mx > -k2 + tol1)) unsure |= SVB_LO(BIT);                  \
-			if (mn > k2 + tol1 || mx < -tol1) alive &= ~SVB_HI(BIT);                           \
-			else if (!(mn < k2 - tol1 && mx > tol1)) unsure |= SVB_HI(BIT);                    \
-		}                                                                                      \
+	const unsigned m = classify_pair<DIRECT>(cd, l, tg, kscale, tris + 9ull * t, fl, nUnsure);
+	if (nUnsure && nExact) atomicAdd(nExact, (unsigned long long)nUnsure);
+	if (!last) {
+		hit[p] = (uint8_t)m;
+		if (fl != fl0) pflags[p] = (uint16_t)fl;   // inherited by the child pairs (k_emit)
 	}
-	SVB_BOX_AXIS(v0x, v1x, v2x, 4, 1u << (FL_BOX + 0))
-	SVB_BOX_AXIS(v0y, v1y, v2y, 2, 1u << (FL_BOX + 1))
-	SVB_BOX_AXIS(v0z, v1z, v2z, 1, 1u << (FL_BOX + 2))
-#undef SVB_BOX_AXIS
-	if (alive) {
-		const double e0x = v1x - v0x, e0y = v1y - v0y, e0z = v1z - v0z;
-		const double e1x = v2x - v1x, e1y = v2y - v1y, e1z = v2z - v1z;
-		// --- plane: overlap <=> |N.v0| <= k*(|Nx|+|Ny|+|Nz|); straight-line over the 8 sign combinations
-		const double nx = fma(e0y, e1z, -(e0z * e1y)), ny = fma(e0z, e1x, -(e0x * e1z)), nz = fma(e0x, e1y, -(e0y * e1x));
-		const double g = fma(nx, v0x, fma(ny, v0y, nz * v0z));
-		const double r = k * (fabs(nx) + fabs(ny) + fabs(nz));
-		const double dx = k * nx, dy = k * ny, dz = k * nz;
-		if (!planeImplied) {
-			const double rp = r + tol3, rm = r - tol3;
-			const double g0 = g + dx, g1 = g - dx;                      // x bit clear / set
-			const double g00 = g0 + dy, g01 = g0 - dy, g10 = g1 + dy, g11 = g1 - dy;
-#define SVB_PLANE(GV, C)                                                          \
-			{                                                                     \
-				const double a = fabs(GV);                                        \
-				if (a > rp) alive &= ~(1u << (C));                                \
-				else if (a > rm) unsure |= 1u << (C);                             \
-			}
-			SVB_PLANE(g00 + dz, 0) SVB_PLANE(g00 - dz, 1) SVB_PLANE(g01 + dz, 2) SVB_PLANE(g01 - dz, 3)
-			SVB_PLANE(g10 + dz, 4) SVB_PLANE(g10 - dz, 5) SVB_PLANE(g11 + dz, 6) SVB_PLANE(g11 - dz, 7)
-#undef SVB_PLANE
-		}
-		if (alive && (fl & 0x1FFu) != 0x1FFu) {
-			const double e2x = v0x - v2x, e2y = v0y - v2y, e2z = v0z - v2z;
-			// bitwise-equal input coordinates => that edge component is exactly zero in either evaluation
-			const bool x01 = tf[0] == tf[3], y01 = tf[1] == tf[4], z01 = tf[2] == tf[5];
-			const bool x12 = tf[3] == tf[6], y12 = tf[4] == tf[7], z12 = tf[5] == tf[8];
-			const bool x20 = tf[6] == tf[0], y20 = tf[7] == tf[1], z20 = tf[8] == tf[2];
-			// edge 0: X01(v0,v2)  Y02(v0,v2)  Z12(v1,v2)      p_X = ez*vy - ey*vz, p_Y = -ez*vx + ex*vz, p_Z = ey*vx - ex*vy
-			if (!(fl & 0x001u)) edge_axis<2, 1>(0x001u, z01 && y01, e0z, -e0y, v0y, v0z, v2y, v2z, k, tol2, alive, unsure, fl);
-			if (alive && !(fl & 0x002u)) edge_axis<4, 1>(0x002u, z01 && x01, -e0z, e0x, v0x, v0z, v2x, v2z, k, tol2, alive, unsure, fl);
-			if (alive && !(fl & 0x004u)) edge_axis<4, 2>(0x004u, y01 && x01, e0y, -e0x, v1x, v1y, v2x, v2y, k, tol2, alive, unsure, fl);
-			// edge 1: X01(v0,v2)  Y02(v0,v2)  Z0(v0,v1)
-			if (alive && !(fl & 0x008u)) edge_axis<2, 1>(0x008u, z12 && y12, e1z, -e1y, v0y, v0z, v2y, v2z, k, tol2, alive, unsure, fl);
-			if (alive && !(fl & 0x010u)) edge_axis<4, 1>(0x010u, z12 && x12, -e1z, e1x, v0x, v0z, v2x, v2z, k, tol2, alive, unsure, fl);
-			if (alive && !(fl & 0x020u)) edge_axis<4, 2>(0x020u, y12 && x12, e1y, -e1x, v0x, v0y, v1x, v1y, k, tol2, alive, unsure, fl);
-			// edge 2: X2(v0,v1)  Y1(v0,v1)  Z12(v1,v2)
-			if (alive && !(fl & 0x040u)) edge_axis<2, 1>(0x040u, z20 && y20, e2z, -e2y, v0y, v0z, v1y, v1z, k, tol2, alive, unsure, fl);
-			if (alive && !(fl & 0x080u)) edge_axis<4, 1>(0x080u, z20 && x20, -e2z, e2x, v0x, v0z, v1x, v1z, k, tol2, alive, unsure, fl);
-			if (alive && !(fl & 0x100u)) edge_axis<4, 2>(0x100u, y20 && x20, e2y, -e2x, v1x, v1y, v2x, v2y, k, tol2, alive, unsure, fl);
-		}
-	}
-	unsure &= alive;
-	unsigned m = alive & ~unsure;
-	if (unsure) {
-		m |= exact_children(unsure, Cx, Cy, Cz, k, tp);
-		if (nExact) atomicAdd(nExact, (unsigned long long)__popc(unsure));
-	}
-	hit[p] = (uint8_t)m;
-	pflags[p] = (uint16_t)fl;   // inherited by the child pairs (k_emit)
 	if (m) {
-		unsigned cur = mask[n];
+		unsigned cur = mask[n];   // may be stale (L1); bits only ever get set, so a stale value only costs an extra atomic
 		if ((cur & m) != m) atomicOr(reinterpret_cast<unsigned*>(mask) + (n >> 2), m << (8 * (n & 3)));
 	}
 }
-#undef SVB_LO
-#undef SVB_HI
 
 // children of node n: contiguous at childBase[n], ascending child index == Morton order
 __global__ void __launch_bounds__(VX_THREADS) k_children(uint64_t N, const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask,
@@ -325,30 +158,111 @@ __global__ void __launch_bounds__(VX_THREADS) k_children(uint64_t N, const uint6
 	}
 }
 
-// emit the child pairs of every pair; first-touch triangle by atomicMin (pairs are sorted by
-// triangle, so after the first touch the pre-check load filters almost every later atomic)
-__global__ void __launch_bounds__(VX_THREADS) k_emit(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
-                                                      const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit, const uint32_t* __restrict__ poff,
-                                                      const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase,
-                                                      uint32_t* __restrict__ otri, uint32_t* __restrict__ onode, uint16_t* __restrict__ oflags, uint32_t* __restrict__ ctstar) {
+// ------------------------------------------------------------------ classify, fast stream
+// Pairs of the fast stream (pair_is_fast(), svb_classify.cuh): one exact box test on the flat axis.  Few registers,
+// full occupancy: the kernel is a chain of three dependent loads (pair -> node code -> tile geometry / vertex
+// coordinate), so resident warps are what hides the latency.
+template <bool DIRECT>
+__global__ void __launch_bounds__(VX_THREADS, 8) k_classify_fast(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
+                                                                 const uint16_t* __restrict__ pflags, const uint64_t* __restrict__ code, int l, double kscale, int last,
+                                                                 const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
+                                                                 uint8_t* __restrict__ hit, uint8_t* __restrict__ mask) {
 	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= P) return;
-	unsigned m = hit[p];
-	if (!m) return;
-	uint32_t t = ptri[p], n = pnode[p];
-	const uint16_t fl = pflags[p];
-	unsigned nm = mask[n];
-	uint32_t base = childBase[n];
-	uint32_t o = poff[p];
-	while (m) {
-		int c = __ffs(m) - 1;
-		m &= m - 1;
-		uint32_t child = base + __popc(nm & ((1u << c) - 1));
-		otri[o] = t;
-		onode[o] = child;
-		oflags[o] = fl;
-		++o;
-		if (ctstar[child] > t) atomicMin(&ctstar[child], t);
+	const uint32_t t = ptri[p], n = pnode[p];
+	const int a = fast_axis(pflags[p]);
+	const uint64_t cd = code[n];
+	const double* tg = reinterpret_cast<const double*>(tiles + (uint32_t)(cd >> (3 * l)));   // {cx, cy, cz, rootSide}
+	const unsigned m = classify_pair_fast<DIRECT>(cd, l, tg[a], tg[3], kscale, tris[9ull * t + a], a);
+	if (!last) hit[p] = (uint8_t)m;
+	if (m) {
+		unsigned cur = mask[n];
+		if ((cur & m) != m) atomicOr(reinterpret_cast<unsigned*>(mask) + (n >> 2), m << (8 * (n & 3)));
+	}
+}
+
+// ------------------------------------------------------------------ emit the child pairs
+// One thread per parent pair; the CTA's child pairs are staged in shared memory and written out as contiguous,
+// coalesced runs.  The pair arrays are kept as two streams: [0, nFast) fast pairs, [slowBase, ...) the others
+// (stable partition: both streams stay sorted by triangle id).  SLOW = false: parents of the fast stream (all
+// children fast, offsets offA).  SLOW = true: parents of the slow stream; offA = exclusive scan of all their
+// children, offB = of their fast children; fast children go to fastBase + offB, slow ones to slowBase + offA - offB.
+// First-touch triangle of the child nodes by atomicMin (pairs are sorted by triangle, so after the first touch the
+// pre-check load filters almost every later atomic).
+constexpr int EM_THREADS = 256;
+template <bool SLOW>
+__global__ void __launch_bounds__(EM_THREADS) k_emit(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
+                                                     const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit,
+                                                     const uint32_t* __restrict__ offA, const uint32_t* __restrict__ offB, uint64_t fastBase, uint64_t slowBase,
+                                                     const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase,
+                                                     uint32_t* __restrict__ otri, uint32_t* __restrict__ onode, uint16_t* __restrict__ oflags, uint32_t* __restrict__ ctstar) {
+	__shared__ uint32_t s_tri[EM_THREADS * 8];
+	__shared__ uint32_t s_node[EM_THREADS * 8];
+	__shared__ uint16_t s_fl[EM_THREADS * 8];
+	__shared__ uint32_t s_nFast, s_nSlow;
+	const uint64_t p0 = (uint64_t)blockIdx.x * EM_THREADS;
+	const uint64_t p = p0 + threadIdx.x;
+	const uint64_t pLast = (p0 + EM_THREADS <= P ? p0 + EM_THREADS : P) - 1;
+	// offsets of the CTA's first parent (broadcast loads)
+	const uint32_t a0 = offA[p0];
+	const uint32_t b0 = SLOW ? offB[p0] : 0;
+	unsigned m = 0;
+	uint32_t t = 0, n = 0, fl = 0, oa = 0, ob = 0;
+	bool fastKids = !SLOW;
+	if (p < P) {
+		m = hit[p];
+		oa = offA[p];
+		if (SLOW) ob = offB[p];
+		if (m || p == pLast) {
+			fl = pflags[p];
+			if (SLOW) fastKids = pair_is_fast(fl);
+		}
+		if (m) { t = ptri[p]; n = pnode[p]; }
+	}
+	const uint32_t cnt = __popc(m);
+	if (p == pLast) {   // totals of the CTA
+		if (SLOW) {
+			const uint32_t eb = ob + (fastKids ? cnt : 0), ea = oa + cnt;
+			s_nFast = eb - b0;
+			s_nSlow = (ea - eb) - (a0 - b0);
+		} else {
+			s_nFast = oa + cnt - a0;
+			s_nSlow = 0;
+		}
+	}
+	__syncthreads();
+	const uint32_t nFast = s_nFast, nSlow = s_nSlow;
+	if (m) {
+		// local slot of this parent's first child: fast children fill [0, nFast), slow children [nFast, nFast + nSlow)
+		uint32_t o = SLOW ? (fastKids ? ob - b0 : nFast + (oa - ob) - (a0 - b0)) : oa - a0;
+		const unsigned nm = mask[n];
+		const uint32_t base = childBase[n];
+		unsigned mm = m;
+		while (mm) {
+			const int c = __ffs(mm) - 1;
+			mm &= mm - 1;
+			const uint32_t child = base + __popc(nm & ((1u << c) - 1));
+			s_tri[o] = t;
+			s_node[o] = child;
+			s_fl[o] = (uint16_t)fl;
+			++o;
+			if (ctstar[child] > t) atomicMin(&ctstar[child], t);
+		}
+	}
+	__syncthreads();
+	const uint64_t dstFast = fastBase + (SLOW ? b0 : a0);
+	for (uint32_t i = threadIdx.x; i < nFast; i += EM_THREADS) {
+		otri[dstFast + i] = s_tri[i];
+		onode[dstFast + i] = s_node[i];
+		oflags[dstFast + i] = s_fl[i];
+	}
+	if (SLOW) {
+		const uint64_t dstSlow = slowBase + (a0 - b0);
+		for (uint32_t i = threadIdx.x; i < nSlow; i += EM_THREADS) {
+			otri[dstSlow + i] = s_tri[nFast + i];
+			onode[dstSlow + i] = s_node[nFast + i];
+			oflags[dstSlow + i] = s_fl[nFast + i];
+		}
 	}
 }
 
@@ -381,12 +295,40 @@ uint64_t read_u64(cudaStream_t s, const uint64_t* d) {
 }  // namespace
 
 // ------------------------------------------------------------------ host drivers
+namespace {
+// exponent of the lowest set bit of a finite double (x = odd * 2^e); 0 -> +inf-like sentinel
+int low_bit_exp(double x) {
+	if (x == 0.0) return 1 << 20;
+	int e;
+	double m = frexp(fabs(x), &e);               // x = m * 2^e, m in [0.5,1)
+	uint64_t mi = (uint64_t)ldexp(m, 53);        // 53-bit integer mantissa
+	return e - 53 + __builtin_ctzll(mi);
+}
+}  // namespace
+
+bool centre_chain_exact(const TileGeom& g, int Lt) {
+	if (!(g.rootSide > 0.0) || !std::isfinite(g.rootSide) || Lt < 1 || Lt > 20) return false;
+	const double kFinest = ldexp(g.rootSide, -(Lt + 1));   // half side of the deepest children (level Lt-1 nodes test C +- k)
+	if (kFinest < 1e-290) return false;
+	int ge = low_bit_exp(kFinest);
+	ge = std::min(ge, std::min(low_bit_exp(g.cx), std::min(low_bit_exp(g.cy), low_bit_exp(g.cz))));
+	const double span = std::max(fabs(g.cx), std::max(fabs(g.cy), fabs(g.cz))) + g.rootSide;
+	if (!std::isfinite(span)) return false;
+	// every partial sum is an integer multiple of 2^ge with magnitude <= span: representable iff span / 2^ge <= 2^53
+	return ldexp(span, -ge) <= 9007199254740992.0;
+}
+
 void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T, const TileGridHost& grid,
                      const int* d_gridTile, const int* d_localOf, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t& P) {
 	GridDesc g;
 	g.ox = grid.ox; g.oy = grid.oy; g.oz = grid.oz;
 	g.inv_cell = 1.0 / grid.cell;
-	g.margin = grid.cell * 1e-6;
+	// a sub-octree cube is rebuilt from a float-narrowed box (geom_octree.cpp:177-184): it can stick out of its
+	// nominal grid cell by up to one float ulp of the largest coordinate; the margin must dominate that
+	const double ext = grid.cell * (double)grid.G;
+	const double maxAbs = std::max(std::max(std::max(fabs(grid.ox), fabs(grid.ox + ext)), std::max(fabs(grid.oy), fabs(grid.oy + ext))),
+	                               std::max(fabs(grid.oz), fabs(grid.oz + ext)));
+	g.margin = grid.cell * 1e-6 + maxAbs * 4.8e-7;   // 4.8e-7 = 4 * 2^-23
 	g.G = grid.G;
 	DevBuf<uint32_t> cnt(pool, T);
 	DevBuf<uint64_t> tot(pool, 1);
@@ -404,7 +346,8 @@ void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T
 
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
                     DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t P, uint64_t budget_bytes, uint64_t nodeCap,
-                    std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact) {
+                    std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre) {
+	if (const char* e = getenv("SVB_CENTRE")) directCentre = directCentre && e[0] != 'c';   // SVB_CENTRE=chain: always replay the chain
 	lv.clear();
 	lv.resize(Lt);
 	lv[0].n = ntiles;
@@ -412,54 +355,61 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 	lv[0].tstar.reset(pool, ntiles);
 	k_init_roots<<<blocks_for(ntiles, 256), 256, 0, s>>>(ntiles, lv[0].code.p, lv[0].tstar.p);
 	SVB_KERNEL_CHECK();
-	DevBuf<uint64_t> tot(pool, 1);
+	DevBuf<uint64_t> tot(pool, 4);   // device totals of the four scans of a level, read back together
 	pairsTotal = 0;
-	DevBuf<uint16_t> pflags(pool, P + 8);   // settled-axis flags per pair (see k_classify_filtered)
+	// Pair streams: [0, F) fast pairs, [Fa, Fa + S) the others (Fa = F rounded up to 16 so that both streams start
+	// on an aligned address in every pair array); the root pairs are all "slow" (no axis is settled yet).
+	uint64_t F = 0, Fa = 0, S = P;
+	DevBuf<uint16_t> pflags(pool, P + 16);   // settled-axis flags per pair (svb_classify.cuh)
 	pflags.zero();
+	const bool exactOnly = classify_exact_only();
+	static const int occ = [] { const char* e = getenv("SVB_VX_OCC"); return e ? atoi(e) : 4; }();
 	for (int l = 0; l < Lt; ++l) {
 		BatchLevel& L = lv[l];
 		L.mask.reset(pool, (L.n + 3 + 16) & ~3ull);
 		L.mask.zero();
-		DevBuf<uint8_t> hit(pool, P + 16);
-		if (P) {
-			if (P > (1ull << 59)) throw Error(SVB_ERANGE, "too many pairs");
-			if (classify_exact_only())
-				k_classify<<<blocks_for(P * 8, VX_THREADS), VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p);
+		const int last = (l == Lt - 1) ? 1 : 0;
+		DevBuf<uint8_t> hit(pool, last ? 16 : Fa + S + 16);
+		if (F + S > (1ull << 59)) throw Error(SVB_ERANGE, "too many pairs");
+		const double kscale = ldexp(1.0, -(l + 2));
+		if (F) {
+			unsigned nb = blocks_for(F, VX_THREADS);
+			if (directCentre) k_classify_fast<true><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, hit.p, L.mask.p);
+			else k_classify_fast<false><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, hit.p, L.mask.p);
+			SVB_KERNEL_CHECK();
+		}
+		if (S) {
+			const uint32_t* st = ptri.p + Fa; const uint32_t* sn = pnode.p + Fa; uint16_t* sf = pflags.p + Fa; uint8_t* sh = hit.p + (last ? 0 : Fa);
+			if (exactOnly)
+				k_classify<<<blocks_for(S * 8, VX_THREADS), VX_THREADS, 0, s>>>(S, st, sn, L.code.p, l, d_tiles, d_tris, sh, L.mask.p, last);
 			else {
-				static const int occ = [] { const char* e = getenv("SVB_VX_OCC"); return e ? atoi(e) : 4; }();
-				unsigned nb = blocks_for(P, VX_THREADS);
-				if (occ >= 6) k_classify_filtered<6><<<nb, VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, pflags.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p, (unsigned long long*)d_nExact);
-				else if (occ == 5) k_classify_filtered<5><<<nb, VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, pflags.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p, (unsigned long long*)d_nExact);
-				else if (occ >= 4) k_classify_filtered<4><<<nb, VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, pflags.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p, (unsigned long long*)d_nExact);
-				else if (occ == 3) k_classify_filtered<3><<<nb, VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, pflags.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p, (unsigned long long*)d_nExact);
-				else k_classify_filtered<1><<<nb, VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, pflags.p, L.code.p, l, d_tiles, d_tris, hit.p, L.mask.p, (unsigned long long*)d_nExact);
+				unsigned nb = blocks_for(S, VX_THREADS);
+#define SVB_LAUNCH_CF(OCC, DIR) k_classify_filtered<OCC, DIR><<<nb, VX_THREADS, 0, s>>>(S, st, sn, sf, L.code.p, l, kscale, last, d_tiles, d_tris, sh, L.mask.p, (unsigned long long*)d_nExact)
+				if (directCentre) {
+					if (occ >= 6) SVB_LAUNCH_CF(6, true); else if (occ == 5) SVB_LAUNCH_CF(5, true); else if (occ == 4) SVB_LAUNCH_CF(4, true);
+					else if (occ == 3) SVB_LAUNCH_CF(3, true); else SVB_LAUNCH_CF(1, true);
+				} else {
+					if (occ >= 6) SVB_LAUNCH_CF(6, false); else if (occ == 5) SVB_LAUNCH_CF(5, false); else if (occ == 4) SVB_LAUNCH_CF(4, false);
+					else if (occ == 3) SVB_LAUNCH_CF(3, false); else SVB_LAUNCH_CF(1, false);
+				}
+#undef SVB_LAUNCH_CF
 			}
 			SVB_KERNEL_CHECK();
 		}
-		pairsTotal += P;
-		if (getenv("SVB_VX_STATS") && P) {   // debug: how many axes are settled per pair at this level
-			uint64_t ns = P < 4000000 ? P : 4000000;
-			std::vector<uint16_t> hf(ns);
-			std::vector<uint8_t> hh(ns);
-			SVB_CUDA(cudaMemcpyAsync(hf.data(), pflags.p + (P - ns) / 2, ns * 2, cudaMemcpyDeviceToHost, s));
-			SVB_CUDA(cudaMemcpyAsync(hh.data(), hit.p + (P - ns) / 2, ns, cudaMemcpyDeviceToHost, s));
-			SVB_CUDA(cudaStreamSynchronize(s));
-			uint64_t hist[13] = {0}, allEdge = 0, allBox = 0, hits = 0;
-			for (uint64_t i = 0; i < ns; ++i) { hist[__builtin_popcount(hf[i])]++; allEdge += (hf[i] & 0x1FF) == 0x1FF; allBox += (hf[i] >> 9) == 7; hits += __builtin_popcount(hh[i]); }
-			fprintf(stderr, "[vx-stats] level %d P=%llu sample=%llu allEdge=%.3f allBox=%.3f hits/pair=%.2f hist:", l, (unsigned long long)P, (unsigned long long)ns,
-			        (double)allEdge / ns, (double)allBox / ns, (double)hits / ns);
-			for (int i = 0; i <= 12; ++i) fprintf(stderr, " %.3f", (double)hist[i] / ns);
-			fprintf(stderr, "\n");
-		}
-		if (l == Lt - 1) break;
-		// children
+		pairsTotal += F + S;
+		if (last) break;
+		// children of the nodes, child pairs of the pairs: four scans, one read-back
 		L.childBase.reset(pool, L.n);
-		scan_popc8(s, pool, L.mask.p, L.n, L.childBase.p, tot.p);
-		uint64_t Nn = read_u64(s, tot.p);
-		// next pairs
-		DevBuf<uint32_t> poff(pool, P);
-		scan_popc8(s, pool, hit.p, P, poff.p, tot.p);
-		uint64_t Pn = read_u64(s, tot.p);
+		scan_popc8(s, pool, L.mask.p, L.n, L.childBase.p, tot.p + 0);
+		DevBuf<uint32_t> offF(pool, F + 1), offS(pool, S + 1), offSF(pool, S + 1);
+		scan_popc8(s, pool, hit.p, F, offF.p, tot.p + 1);
+		scan_popc8(s, pool, hit.p + Fa, S, offS.p, tot.p + 2);
+		scan_popc8_fast(s, pool, hit.p + Fa, pflags.p + Fa, S, offSF.p, tot.p + 3);
+		uint64_t h[4];
+		SVB_CUDA(cudaMemcpyAsync(h, tot.p, 32, cudaMemcpyDeviceToHost, s));
+		SVB_CUDA(cudaStreamSynchronize(s));
+		const uint64_t Nn = h[0], cF = h[1], cS = h[2], cSF = h[3];
+		const uint64_t Fn = cF + cSF, Fan = (Fn + 15) & ~15ull, Sn = cS - cSF, Pn = Fan + Sn;
 		{
 			// will this batch fit all the way down?  Surfaces grow ~4x per level; use the observed ratio.
 			const int remaining = (Lt - 1) - (l + 1);
@@ -490,16 +440,22 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		C.tstar.fill_ff();
 		k_children<<<blocks_for(L.n, VX_THREADS), VX_THREADS, 0, s>>>(L.n, L.code.p, L.mask.p, L.childBase.p, C.code.p);
 		SVB_KERNEL_CHECK();
-		DevBuf<uint32_t> ntri(pool, Pn), nnode(pool, Pn);
-		DevBuf<uint16_t> nflags(pool, Pn + 8);
-		if (P) {
-			k_emit<<<blocks_for(P, VX_THREADS), VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, pflags.p, hit.p, poff.p, L.mask.p, L.childBase.p, ntri.p, nnode.p, nflags.p, C.tstar.p);
+		DevBuf<uint32_t> ntri(pool, Pn + 16), nnode(pool, Pn + 16);
+		DevBuf<uint16_t> nflags(pool, Pn + 16);
+		if (F) {
+			k_emit<false><<<blocks_for(F, EM_THREADS), EM_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p,
+			                                                                ntri.p, nnode.p, nflags.p, C.tstar.p);
+			SVB_KERNEL_CHECK();
+		}
+		if (S) {
+			k_emit<true><<<blocks_for(S, EM_THREADS), EM_THREADS, 0, s>>>(S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, cF, Fan, L.mask.p, L.childBase.p,
+			                                                               ntri.p, nnode.p, nflags.p, C.tstar.p);
 			SVB_KERNEL_CHECK();
 		}
 		ptri = std::move(ntri);
 		pnode = std::move(nnode);
 		pflags = std::move(nflags);
-		P = Pn;
+		F = Fn; Fa = Fan; S = Sn;
 	}
 	ptri.release();
 	pnode.release();

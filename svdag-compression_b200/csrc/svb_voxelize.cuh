@@ -27,6 +27,11 @@ void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T
 // Level-synchronous SVO build of `ntiles` sub-octrees of Lt levels each.  Consumes the root pairs.
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
                     DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t P, uint64_t budget_bytes, uint64_t nodeCap,
-                    std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact);
+                    std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre);
+
+// True when every partial sum of the centre chain (geom_octree.cpp:222-230) of a sub-octree with root centre
+// (cx,cy,cz), root side `rootSide` and `Lt` levels is a representable double, i.e. the chain is exact and the
+// kernels may evaluate node centres in closed form (see centre_axis_direct in svb_voxelize.cu).
+bool centre_chain_exact(const TileGeom& g, int Lt);
 
 }  // namespace svb

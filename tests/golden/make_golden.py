@@ -39,13 +39,25 @@ CASES = [
     ("terrain_L7_s3", "terrain", dict(n=24), 7, 3, False),
     ("spongeball_L7_s0", "sphere_menger", dict(n_lat=12, n_lon=24, sponge_level=1), 7, 0, False),
     ("spongeball_L7_s2_c", "sphere_menger", dict(n_lat=12, n_lon=24, sponge_level=1), 7, 2, True),
+    # scaled + shifted scenes (bbox is not the unit cube): float narrowing of sub-octree boxes, empty sub-octree roots
+    ("city_affine_L8_s2", "city", dict(lots=4, affine=((3.7, 2.9, 5.3), (11.3, -5.1, 2.9))), 8, 2, False),
+    ("terrain_affine_L7_s1", "terrain", dict(n=24, affine=((3.7, 2.9, 5.3), (11.3, -5.1, 2.9))), 7, 1, False),
+    ("city_affine_L7_s1_c", "city", dict(lots=4, affine=((3.7, 2.9, 5.3), (11.3, -5.1, 2.9))), 7, 1, True),
 ]
 
 
 def main():
     out_dir = Path(__file__).resolve().parent
+    only = set(sys.argv[1:])
     for name, mesh, kw, levels, step, cross in CASES:
+        if only and name not in only:
+            continue
+        kw = dict(kw)
+        affine = kw.pop("affine", None)
         tris = mg.make_mesh(mesh, **kw)
+        if affine is not None:
+            t = tris.reshape(-1, 3).astype(np.float64) * np.asarray(affine[0]) + np.asarray(affine[1])
+            tris = np.ascontiguousarray(t.astype(np.float32).reshape(-1, 9))
         with tempfile.TemporaryDirectory() as td:
             r = orc.run_reference(td, tris, levels, step, cross=cross)
         reduced = np.zeros((levels, 2), dtype=np.int64)

@@ -1,0 +1,83 @@
+"""CPU check of the voxelizer's per-pair decision (svb_classify.cuh compiled with g++, see
+tests/harness/classify_harness.cpp): the FP64 interval filter, the inherited settled-axis flags, the exact
+single-axis fast path for flat triangles and the closed-form node centres must give, for EVERY (triangle, node)
+pair of a hierarchical build, the 8-child mask of the reference-order predicate.  Test infrastructure only --
+the product never runs this code on the CPU."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+SRC = ROOT / "tests" / "harness" / "classify_harness.cpp"
+OUT = ROOT / "tests" / "harness" / "build" / "libclassify_harness.so"
+
+
+@pytest.fixture(scope="module")
+def harness():
+    OUT.parent.mkdir(exist_ok=True)
+    deps = [SRC] + list((ROOT / "svdag-compression_b200" / "csrc").glob("svb_*.cuh"))
+    if not OUT.exists() or any(d.stat().st_mtime > OUT.stat().st_mtime for d in deps):
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                        str(SRC), "-o", str(OUT)], check=True)
+    L = C.CDLL(str(OUT))
+    L.harness_run.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    return L
+
+
+def _run(L, tris, lo, hi, levels, direct):
+    tris = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 9)
+    bf = np.concatenate([lo, hi]).astype(np.float32)                      # geom_octree.cpp:177-184
+    side = max(np.float32(np.float32(np.float32(bf[3 + k] - bf[k]) * np.float32(0.5)) * np.float32(2.0)) for k in range(3))
+    centre = np.ascontiguousarray((np.asarray(lo, np.float64) + np.asarray(hi, np.float64)) * 0.5)   # bbox.center(), :214
+    out = np.zeros(10, np.uint64)
+    L.harness_run(tris.ctypes.data, tris.shape[0], centre.ctypes.data, float(side), levels, int(direct), 0, out.ctypes.data)
+    return dict(pairs=int(out[0]), bad=int(out[1]), fast=int(out[2]), exact=int(out[3]),
+                first=dict(level=int(out[4]), tri=int(out[5]), code=int(out[6]), got=int(out[7]), want=int(out[8]), fl=int(out[9])))
+
+
+def _affine(tris, scale, offset):
+    t = tris.reshape(-1, 3).astype(np.float64) * np.asarray(scale) + np.asarray(offset)
+    return np.ascontiguousarray(t.astype(np.float32).reshape(-1, 9))
+
+
+CASES = [
+    ("city", dict(lots=8), 8),
+    ("terrain", dict(n=32), 8),
+    ("sphere", dict(n_lat=16, n_lon=32), 8),
+    ("sphere_menger", dict(n_lat=16, n_lon=32, sponge_level=2), 7),
+]
+
+
+@pytest.mark.parametrize("direct", [True, False], ids=["direct", "chain"])
+@pytest.mark.parametrize("mesh,kw,levels", CASES, ids=[c[0] for c in CASES])
+def test_filter_equals_predicate_unit_cube(harness, meshgen, mesh, kw, levels, direct):
+    tris = meshgen.make_mesh(mesh, **kw)
+    v = tris.reshape(-1, 3).astype(np.float64)
+    r = _run(harness, tris, v.min(axis=0), v.max(axis=0), levels, direct)
+    assert r["bad"] == 0, r
+    if mesh == "city":
+        assert r["fast"] > 0.1 * r["pairs"], r   # the flat fast path must actually be exercised
+
+
+@pytest.mark.parametrize("direct", [True, False], ids=["direct", "chain"])
+@pytest.mark.parametrize("mesh,kw,levels", CASES[:3], ids=[c[0] for c in CASES[:3]])
+def test_filter_equals_predicate_arbitrary_float_bbox(harness, meshgen, mesh, kw, levels, direct):
+    """Scaled / shifted scene: centres are (lo+hi)/2 of float bounds -- the chain is still exact, so the
+    closed form must agree with it."""
+    tris = _affine(meshgen.make_mesh(mesh, **kw), (3.7, 2.9, 5.3), (11.3, -5.1, 2.9))
+    v = tris.reshape(-1, 3).astype(np.float64)
+    r = _run(harness, tris, v.min(axis=0), v.max(axis=0), levels, direct)
+    assert r["bad"] == 0, r
+
+
+def test_filter_equals_predicate_full_double_bbox(harness, meshgen):
+    """Caller-supplied bbox with 53-bit doubles: the chain rounds at every level; the kernels then replay it
+    (DIRECT=false, chosen on the host by centre_chain_exact)."""
+    tris = _affine(meshgen.make_mesh("city", lots=8), (3.7, 2.9, 5.3), (11.3, -5.1, 2.9))
+    v = tris.reshape(-1, 3).astype(np.float64)
+    lo, hi = v.min(axis=0) - np.array([0.1, 0.2, 0.3]) / 3.0, v.max(axis=0) + np.array([0.7, 0.1, 0.05]) / 7.0
+    r = _run(harness, tris, lo, hi, 8, False)
+    assert r["bad"] == 0, r

@@ -147,6 +147,45 @@ def test_filtered_classifier_equals_exact_predicate(pkg, meshgen, mesh, kw, leve
     _assert_levels_equal(a.levels_host(), b.levels_host(), "filtered vs exact")
 
 
+def _affine(tris, scale, offset):
+    t = tris.reshape(-1, 3).astype(np.float64) * np.asarray(scale) + np.asarray(offset)
+    return np.ascontiguousarray(t.astype(np.float32).reshape(-1, 9))
+
+
+@pytest.mark.parametrize("centre", ["auto", "chain"])
+@pytest.mark.parametrize("mesh,kw,levels,step,bbox_mode", [
+    ("terrain", dict(n=48), 8, 0, "scene"),
+    ("city", dict(lots=8), 9, 2, "scene"),
+    ("sphere", dict(n_lat=32, n_lon=64), 9, 3, "scene"),
+    ("city", dict(lots=8), 9, 2, "double"),
+    ("terrain", dict(n=48), 9, 1, "double"),
+], ids=["terrain-s0", "city-s2", "sphere-s3", "city-doublebox", "terrain-doublebox"])
+def test_arbitrary_bbox_matches_oracle(pkg, orc, meshgen, mesh, kw, levels, step, bbox_mode, centre, monkeypatch):
+    """Scenes whose bbox is NOT the unit cube: node centres are no longer short dyadic numbers, so the
+    reference's centre chain (geom_octree.cpp:222-230) and the float narrowing of sub-octree boxes (:177-184,
+    :340-344) matter.  "scene": float bbox of a scaled/shifted mesh (the chain is still exact -> closed-form
+    centres); "double": a caller-supplied bbox with full 53-bit doubles (chain rounds -> the kernels must replay
+    it).  SVB_CENTRE=chain forces the replay everywhere; all variants must equal the oracle bit for bit."""
+    tris = _affine(meshgen.make_mesh(mesh, **kw), (3.7, 2.9, 5.3), (11.3, -5.1, 2.9))
+    bbox = None
+    if bbox_mode == "double":
+        v = tris.reshape(-1, 3).astype(np.float64)
+        lo, hi = v.min(axis=0), v.max(axis=0)
+        bbox = (lo - np.array([0.1, 0.2, 0.3]) / 3.0, hi + np.array([0.7, 0.1, 0.05]) / 7.0)
+    if centre == "chain":
+        monkeypatch.setenv("SVB_CENTRE", "chain")
+    o = orc.OracleOctree(tris)
+    o.build(levels, step, bbox=bbox)
+    t = pkg.GeomOctree(tris)
+    st = t.build(levels, step, bbox=bbox)
+    for k in ("nTotalVoxels", "nNodesSVO", "nNodesDAG"):
+        assert st[k] == o.stat(k), k
+    _assert_levels_equal(t.levels_host(), _oracle_levels(o), "DAG (arbitrary bbox)")
+    o.to_sdag()
+    t.to_sdag()
+    assert pkg.encoders.encode(t, "ssvdag") == o.encode("ssvdag")
+
+
 def _simulate_ranks(pkg, tris, levels, step, world):
     """Run the multi-GPU protocol with `world` contexts on ONE device, doing the all-gathers by hand
     (torch.cat of the per-rank export buffers).  Exercises svb_shard_* end to end without NCCL."""
