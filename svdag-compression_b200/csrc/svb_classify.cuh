@@ -89,19 +89,17 @@ SVB_HD double centre_axis_chain(uint64_t cd, int l, int sh, double c0, double ro
 // leaves; their deep pairs then cost one plane evaluation.
 //   bits 0..8  edge axes (edge 0: X,Y,Z; edge 1: X,Y,Z; edge 2: X,Y,Z)     bits 9..11 box axes x,y,z
 //   bits 12..14  the triangle is flat on x / y / z (all three vertices share that coordinate bitwise)
+//   bit 15       the static analysis of the triangle (flat bits, edge axes implied by box axes) has been done
 constexpr unsigned FL_BOX = 9;
 constexpr unsigned FL_FLAT = 12;
+constexpr unsigned FL_INIT = 1u << 15;
 
 // One edge-cross axis: p = ca*v[A] + cb*v[B] on the two vertices the reference projects; the child with
 // signs (sA,sB) sees p - k*(ca*sA + cb*sB) against rad = (|ca|+|cb|)*k.  Straight-line over the four
 // sign combinations (each shared by two children).
 template <unsigned BITA, unsigned BITB>
-SVB_HD void edge_axis(unsigned flbit, bool degenerate, double ca, double cb, double viA, double viB, double vjA, double vjB,
-                                          double k, double tol2, unsigned& alive, unsigned& unsure, unsigned& fl) {
-	// `degenerate`: both coefficients are differences of bitwise-equal float inputs, hence exactly 0 for any
-	// box centre in the reference-order predicate too: p0 = p1 = +-0, rad = 0, neither "min > rad" nor
-	// "max < -rad" can hold -- the axis never separates (axis-aligned edges).
-	if (degenerate) { fl |= flbit; return; }
+SVB_HD void edge_axis(unsigned flbit, double ca, double cb, double viA, double viB, double vjA, double vjB,
+                      double k, double tol2, unsigned& alive, unsigned& unsure, unsigned& fl) {
 	const double pi = fma(ca, viA, cb * viB), pj = fma(ca, vjA, cb * vjB);
 	const bool swap = pj < pi;
 	const double mn = swap ? pj : pi, mx = swap ? pi : pj;
@@ -145,31 +143,47 @@ SVB_HD_NOINLINE unsigned exact_children(unsigned unsure, double Cx, double Cy, d
 	return m;
 }
 
-// ---- "fast" pairs: a flat (axis-aligned) triangle whose nine edge axes and two in-plane box axes are settled.
-// Seven of the thirteen tests are implied by the flat-axis box test (see classify_pair), five are settled for
-// every box inside the pair's node, so the predicate of child c IS the reference's box test on the flat axis a:
-//   v = fl(t_a - fl(C_a +- k));  overlap <=> !(v > k || v < -k)      (test_triangle_box.cpp:165-174)
-// evaluated in the reference's own operation order -- exact, no tolerance, one coordinate.  The flags of a fast
-// pair never change, so all its descendants are fast too: the voxelizer keeps them in a separate pair stream.
-SVB_HD bool pair_is_fast(unsigned fl) {
-	const unsigned ub = (~fl >> FL_BOX) & 7u;   // unsettled box axes (bit 0 = x)
-	return (fl & 0x1FFu) == 0x1FFu && ub != 0 && (ub & (ub - 1)) == 0 && ((fl >> FL_FLAT) & ub) != 0;
-}
-SVB_HD int fast_axis(unsigned fl) {   // 0 = x, 1 = y, 2 = z
-	const unsigned ub = (~fl >> FL_BOX) & 7u;
-	return (ub == 1u) ? 0 : (ub == 2u) ? 1 : 2;
-}
+// ---- the "flat" pair stream: a flat (axis-aligned) triangle, say on axis a, all of whose nine edge axes are settled.
+// The plane test and the six edge axes that involve the a-component are implied by the box test on a (see
+// classify_pair), the other edge axes are settled for every box inside the pair's node, so the predicate of a
+// child IS the conjunction of the reference's three box-axis tests (test_triangle_box.cpp:165-174):
+//   mn = fl(min_i t_i - c), mx = fl(max_i t_i - c);  overlap <=> !(mn > k || mx < -k)      per axis,
+// (fl(t - c) is monotone in t, so the min/max may be taken on the float inputs) evaluated here in the reference's
+// own operation order at the chain-rounded child centres -- exact, no tolerance.  Box axes that are already settled
+// are skipped; an in-plane axis becomes settled once the node lies strictly inside the triangle's slab.  The edge
+// flags of such a pair never change, so all its descendants stay in this stream (k_classify_fast).
+SVB_HD bool pair_is_fast(unsigned fl) { return (fl & 0x1FFu) == 0x1FFu && (fl & (7u << FL_FLAT)) != 0; }
+
 template <bool DIRECT>
-SVB_HD unsigned classify_pair_fast(const uint64_t cd, const int l, const double c0, const double rootSide, const double kscale, const float ta_f, const int a) {
-	const double k = rootSide * kscale;
+SVB_HD unsigned classify_pair_flat(const uint64_t cd, const int l, const double* __restrict__ tg4, const double kscale, const float* __restrict__ tp, unsigned& fl) {
+	const double rootSide = tg4[3];
+	const double k = rootSide * kscale, k2 = k + k;
 	const uint64_t path = cd & ((1ull << (3 * l)) - 1);
-	const double C = DIRECT ? centre_axis_direct(path, l, 2 - a, c0, k) : centre_axis_chain(cd, l, 2 - a, c0, rootSide);
-	const double ta = (double)ta_f;
-	const double vLo = SVB_DSUB(ta, SVB_DADD(C, -k)), vHi = SVB_DSUB(ta, SVB_DADD(C, k));
-	const unsigned lo = (a == 0) ? 0x0Fu : (a == 1) ? 0x33u : 0x55u;
-	unsigned m = 0;
-	if (!(vLo > k || vLo < -k)) m |= lo;
-	if (!(vHi > k || vHi < -k)) m |= lo ^ 0xFFu;
+	const unsigned ub = (~fl >> FL_BOX) & 7u;   // unsettled box axes (bit 0 = x)
+	unsigned m = 0xFFu;
+#pragma unroll
+	for (int a = 0; a < 3; ++a) {
+		if (!((ub >> a) & 1u)) continue;
+		float tmin = tp[a], tmax = tmin;
+		if (!((fl >> (FL_FLAT + a)) & 1u)) {
+			const float f1 = tp[3 + a], f2 = tp[6 + a];
+			tmin = fminf(tmin, fminf(f1, f2));
+			tmax = fmaxf(tmax, fmaxf(f1, f2));
+		}
+		const double C = DIRECT ? centre_axis_direct(path, l, 2 - a, tg4[a], k) : centre_axis_chain(cd, l, 2 - a, tg4[a], rootSide);
+		const double dmin = (double)tmin, dmax = (double)tmax;
+		const double cLo = SVB_DADD(C, -k), cHi = SVB_DADD(C, k);
+		const unsigned lo = (a == 0) ? 0x0Fu : (a == 1) ? 0x33u : 0x55u;
+		unsigned pass = 0;
+		if (!(SVB_DSUB(dmin, cLo) > k || SVB_DSUB(dmax, cLo) < -k)) pass |= lo;
+		if (!(SVB_DSUB(dmin, cHi) > k || SVB_DSUB(dmax, cHi) < -k)) pass |= lo ^ 0xFFu;
+		m &= pass;
+		// node strictly inside the triangle's slab on this axis (margin 2^-40 relative, far above any rounding):
+		// the axis can never reject a box inside this node
+		const double mn = dmin - C, mx = dmax - C;
+		const double tol = (fmax(fabs(mn), fabs(mx)) + k2) * 9.094947017729282e-13;
+		if (mn + k2 < -tol && mx - k2 > tol) fl |= 1u << (FL_BOX + a);
+	}
 	return m;
 }
 
@@ -182,10 +196,9 @@ SVB_HD unsigned classify_pair(const uint64_t cd, const int l, const TileGeom& tg
 	nUnsure = 0;
 	const double k = tg.rootSide * kscale;   // child half side rootSide / 2^(l+2) (octree.hpp:115), exact scaling
 	const uint64_t path = cd & ((1ull << (3 * l)) - 1);
-	if (pair_is_fast(fl)) {   // never taken inside k_classify_filtered: such pairs live in the fast stream (k_classify_fast)
-		const int a = fast_axis(fl);
-		const double c0 = (a == 0) ? tg.cx : (a == 1) ? tg.cy : tg.cz;
-		return classify_pair_fast<DIRECT>(cd, l, c0, tg.rootSide, kscale, tp[a], a);   // flags unchanged
+	if (pair_is_fast(fl)) {   // never taken inside k_classify_filtered: such pairs live in the flat stream (k_classify_fast)
+		const double tg4[4] = {tg.cx, tg.cy, tg.cz, tg.rootSide};
+		return classify_pair_flat<DIRECT>(cd, l, tg4, kscale, tp, fl);
 	}
 	double Cx, Cy, Cz;
 	if (DIRECT) {
@@ -202,18 +215,29 @@ SVB_HD unsigned classify_pair(const uint64_t cd, const int l, const TileGeom& tg
 	const double v0x = (double)tf[0] - Cx, v0y = (double)tf[1] - Cy, v0z = (double)tf[2] - Cz;
 	const double v1x = (double)tf[3] - Cx, v1y = (double)tf[4] - Cy, v1z = (double)tf[5] - Cz;
 	const double v2x = (double)tf[6] - Cx, v2y = (double)tf[7] - Cy, v2z = (double)tf[8] - Cz;
-	// Axis-aligned ("flat") triangles -- all three vertices share a bitwise-equal coordinate, as every face of
-	// a box mesh does.  Say x is shared: the edge x-components are exactly 0 in the reference-order predicate
-	// for any box centre, the normal is (nx, +-0, +-0), and
-	//   * the six Y-/Z-type edge axes degenerate to  fl(|e|*|vx|) > fl(|e|*h)  (both projected vertices coincide),
-	//   * the plane test degenerates to  vx < -h  or  vx > h,
-	// all of which are implied false by the box-axis test on x (|vx| <= h; rounding is monotone).  So for such a
-	// triangle the predicate IS box-x & box-y & box-z & the three X-type axes: the other seven tests are settled
-	// from the start, rigorously (no tolerance involved).
-	bool planeImplied = false;
-	if (tf[0] == tf[3] && tf[3] == tf[6]) { fl |= 0x1B6u | (1u << (FL_FLAT + 0)); planeImplied = true; }   // Y,Z-type axes of all edges
-	if (tf[1] == tf[4] && tf[4] == tf[7]) { fl |= 0x16Du | (1u << (FL_FLAT + 1)); planeImplied = true; }   // X,Z-type
-	if (tf[2] == tf[5] && tf[5] == tf[8]) { fl |= 0x0DBu | (1u << (FL_FLAT + 2)); planeImplied = true; }   // X,Y-type
+	// ---- static analysis of the triangle, once per triangle/pair lineage (FL_INIT), rigorous (no tolerance):
+	// (1) An edge whose endpoints share a coordinate q BITWISE has e_q = +0 in the reference-order predicate for any
+	//     box centre (fl(t - c) - fl(t - c)).  Its two cross axes that involve e_q then read  p = fl(+-e_r * v_q),
+	//     rad = fl(|e_r| * h)  on the vertex pair {one endpoint, opposite vertex}, which spans the triangle's full
+	//     q-extent: since rounding is monotone, "min > rad" / "max < -rad" would imply  min_i v_iq > h / max_i v_iq < -h,
+	//     i.e. the box test on q rejects too.  Those axes can never change the conjunction: settled from the start.
+	//     (test_triangle_box.cpp:60-102 for the vertex pairs, :137-156 for the operand order.)
+	// (2) A triangle flat on q (all three vertices share q): (1) settles six edge axes, the normal is (+-0,..,n_q,..)
+	//     and the plane test degenerates to  v_q < -h  or  v_q > h  -- implied by the box test on q as well.
+	if (!(fl & FL_INIT)) {
+		const bool x01 = tf[0] == tf[3], y01 = tf[1] == tf[4], z01 = tf[2] == tf[5];
+		const bool x12 = tf[3] == tf[6], y12 = tf[4] == tf[7], z12 = tf[5] == tf[8];
+		const bool x20 = tf[6] == tf[0], y20 = tf[7] == tf[1], z20 = tf[8] == tf[2];
+		// edge axes: bit 0,1,2 = X,Y,Z of edge 0; 3,4,5 edge 1; 6,7,8 edge 2.   e_x = 0 -> Y,Z;  e_y = 0 -> X,Z;  e_z = 0 -> X,Y
+		if (x01) fl |= 0x006u; if (y01) fl |= 0x005u; if (z01) fl |= 0x003u;
+		if (x12) fl |= 0x030u; if (y12) fl |= 0x028u; if (z12) fl |= 0x018u;
+		if (x20) fl |= 0x180u; if (y20) fl |= 0x140u; if (z20) fl |= 0x0C0u;
+		if (x01 && x12) fl |= 1u << (FL_FLAT + 0);
+		if (y01 && y12) fl |= 1u << (FL_FLAT + 1);
+		if (z01 && z12) fl |= 1u << (FL_FLAT + 2);
+		fl |= FL_INIT;
+	}
+	const bool planeImplied = (fl & (7u << FL_FLAT)) != 0;
 	const double k2 = k + k;
 	double M = fmax(fmax(fmax(fabs(v0x), fabs(v0y)), fmax(fabs(v0z), fabs(v1x))), fmax(fmax(fabs(v1y), fabs(v1z)), fmax(fabs(v2x), fmax(fabs(v2y), fabs(v2z))))) + k2;
 	const double eps = 9.094947017729282e-13;   // 2^-40
@@ -259,22 +283,18 @@ SVB_HD unsigned classify_pair(const uint64_t cd, const int l, const TileGeom& tg
 		}
 		if (alive && (fl & 0x1FFu) != 0x1FFu) {
 			const double e2x = v0x - v2x, e2y = v0y - v2y, e2z = v0z - v2z;
-			// bitwise-equal input coordinates => that edge component is exactly zero in either evaluation
-			const bool x01 = tf[0] == tf[3], y01 = tf[1] == tf[4], z01 = tf[2] == tf[5];
-			const bool x12 = tf[3] == tf[6], y12 = tf[4] == tf[7], z12 = tf[5] == tf[8];
-			const bool x20 = tf[6] == tf[0], y20 = tf[7] == tf[1], z20 = tf[8] == tf[2];
 			// edge 0: X01(v0,v2)  Y02(v0,v2)  Z12(v1,v2)      p_X = ez*vy - ey*vz, p_Y = -ez*vx + ex*vz, p_Z = ey*vx - ex*vy
-			if (!(fl & 0x001u)) edge_axis<2, 1>(0x001u, z01 && y01, e0z, -e0y, v0y, v0z, v2y, v2z, k, tol2, alive, unsure, fl);
-			if (alive && !(fl & 0x002u)) edge_axis<4, 1>(0x002u, z01 && x01, -e0z, e0x, v0x, v0z, v2x, v2z, k, tol2, alive, unsure, fl);
-			if (alive && !(fl & 0x004u)) edge_axis<4, 2>(0x004u, y01 && x01, e0y, -e0x, v1x, v1y, v2x, v2y, k, tol2, alive, unsure, fl);
+			if (!(fl & 0x001u)) edge_axis<2, 1>(0x001u, e0z, -e0y, v0y, v0z, v2y, v2z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x002u)) edge_axis<4, 1>(0x002u, -e0z, e0x, v0x, v0z, v2x, v2z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x004u)) edge_axis<4, 2>(0x004u, e0y, -e0x, v1x, v1y, v2x, v2y, k, tol2, alive, unsure, fl);
 			// edge 1: X01(v0,v2)  Y02(v0,v2)  Z0(v0,v1)
-			if (alive && !(fl & 0x008u)) edge_axis<2, 1>(0x008u, z12 && y12, e1z, -e1y, v0y, v0z, v2y, v2z, k, tol2, alive, unsure, fl);
-			if (alive && !(fl & 0x010u)) edge_axis<4, 1>(0x010u, z12 && x12, -e1z, e1x, v0x, v0z, v2x, v2z, k, tol2, alive, unsure, fl);
-			if (alive && !(fl & 0x020u)) edge_axis<4, 2>(0x020u, y12 && x12, e1y, -e1x, v0x, v0y, v1x, v1y, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x008u)) edge_axis<2, 1>(0x008u, e1z, -e1y, v0y, v0z, v2y, v2z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x010u)) edge_axis<4, 1>(0x010u, -e1z, e1x, v0x, v0z, v2x, v2z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x020u)) edge_axis<4, 2>(0x020u, e1y, -e1x, v0x, v0y, v1x, v1y, k, tol2, alive, unsure, fl);
 			// edge 2: X2(v0,v1)  Y1(v0,v1)  Z12(v1,v2)
-			if (alive && !(fl & 0x040u)) edge_axis<2, 1>(0x040u, z20 && y20, e2z, -e2y, v0y, v0z, v1y, v1z, k, tol2, alive, unsure, fl);
-			if (alive && !(fl & 0x080u)) edge_axis<4, 1>(0x080u, z20 && x20, -e2z, e2x, v0x, v0z, v1x, v1z, k, tol2, alive, unsure, fl);
-			if (alive && !(fl & 0x100u)) edge_axis<4, 2>(0x100u, y20 && x20, e2y, -e2x, v1x, v1y, v2x, v2y, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x040u)) edge_axis<2, 1>(0x040u, e2z, -e2y, v0y, v0z, v1y, v1z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x080u)) edge_axis<4, 1>(0x080u, -e2z, e2x, v0x, v0z, v1x, v1z, k, tol2, alive, unsure, fl);
+			if (alive && !(fl & 0x100u)) edge_axis<4, 2>(0x100u, e2y, -e2x, v1x, v1y, v2x, v2y, k, tol2, alive, unsure, fl);
 		}
 	}
 	unsure &= alive;

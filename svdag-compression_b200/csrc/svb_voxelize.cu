@@ -159,21 +159,23 @@ __global__ void __launch_bounds__(VX_THREADS) k_children(uint64_t N, const uint6
 }
 
 // ------------------------------------------------------------------ classify, fast stream
-// Pairs of the fast stream (pair_is_fast(), svb_classify.cuh): one exact box test on the flat axis.  Few registers,
-// full occupancy: the kernel is a chain of three dependent loads (pair -> node code -> tile geometry / vertex
-// coordinate), so resident warps are what hides the latency.
+// Pairs of the flat stream (pair_is_fast(), svb_classify.cuh): exact box-axis tests only.  Few registers, full
+// occupancy: the kernel is a chain of three dependent loads (pair -> node code -> tile geometry / vertex
+// coordinates), so resident warps are what hides the latency.
 template <bool DIRECT>
 __global__ void __launch_bounds__(VX_THREADS, 8) k_classify_fast(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
-                                                                 const uint16_t* __restrict__ pflags, const uint64_t* __restrict__ code, int l, double kscale, int last,
+                                                                 uint16_t* __restrict__ pflags, const uint64_t* __restrict__ code, int l, double kscale, int last,
                                                                  const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
                                                                  uint8_t* __restrict__ hit, uint8_t* __restrict__ mask) {
 	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= P) return;
 	const uint32_t t = ptri[p], n = pnode[p];
-	const int a = fast_axis(pflags[p]);
+	const unsigned fl0 = pflags[p];
+	unsigned fl = fl0;
 	const uint64_t cd = code[n];
 	const double* tg = reinterpret_cast<const double*>(tiles + (uint32_t)(cd >> (3 * l)));   // {cx, cy, cz, rootSide}
-	const unsigned m = classify_pair_fast<DIRECT>(cd, l, tg[a], tg[3], kscale, tris[9ull * t + a], a);
+	const unsigned m = classify_pair_flat<DIRECT>(cd, l, tg, kscale, tris + 9ull * t, fl);
+	if (!last && fl != fl0) pflags[p] = (uint16_t)fl;   // a box axis settled: inherited by the child pairs
 	if (!last) hit[p] = (uint8_t)m;
 	if (m) {
 		unsigned cur = mask[n];
