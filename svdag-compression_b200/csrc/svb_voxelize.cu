@@ -183,6 +183,42 @@ __global__ void __launch_bounds__(VX_THREADS, 8) k_classify_fast(uint64_t P, con
 	}
 }
 
+// ------------------------------------------------------------------ flat stream, last two levels fused
+// At the second-to-last level the children of a flat-stream pair are not emitted as pairs: the thread that owns the
+// parent pair decides each hit child's 8 voxels on the spot (same exact box-axis tests, one level down) and ORs the
+// voxel mask / first-touch triangle straight into the leaf level.  Saves writing and re-reading the bulk of the
+// last-level pair list (the interior of every wall), which is the largest array of the whole build.
+template <bool DIRECT>
+__global__ void __launch_bounds__(VX_THREADS, 6) k_flat_leaves(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
+                                                               const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit,
+                                                               const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase,
+                                                               int lc, double kscaleChild, const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
+                                                               uint8_t* __restrict__ cmask, uint32_t* __restrict__ ctstar) {
+	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= P) return;
+	unsigned m = hit[p];
+	if (!m) return;
+	const uint32_t t = ptri[p], n = pnode[p];
+	const unsigned fl = pflags[p];
+	const uint64_t cd = code[n];
+	const unsigned nm = mask[n];
+	const uint32_t base = childBase[n];
+	const double* tg = reinterpret_cast<const double*>(tiles + (uint32_t)(cd >> (3 * (lc - 1))));
+	const float* tp = tris + 9ull * t;
+	while (m) {
+		const int c = __ffs(m) - 1;
+		m &= m - 1;
+		const uint32_t child = base + __popc(nm & ((1u << c) - 1));
+		unsigned flc = fl;
+		const unsigned mc = classify_pair_flat<DIRECT>((cd << 3) | (uint64_t)c, lc, tg, kscaleChild, tp, flc);
+		if (mc) {
+			unsigned cur = cmask[child];
+			if ((cur & mc) != mc) atomicOr(reinterpret_cast<unsigned*>(cmask) + (child >> 2), mc << (8 * (child & 3)));
+		}
+		if (ctstar[child] > t) atomicMin(&ctstar[child], t);
+	}
+}
+
 // ------------------------------------------------------------------ emit the child pairs
 // One thread per parent pair; the CTA's child pairs are staged in shared memory and written out as contiguous,
 // coalesced runs.  The pair arrays are kept as two streams: [0, nFast) fast pairs, [slowBase, ...) the others
@@ -368,8 +404,10 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 	static const int occ = [] { const char* e = getenv("SVB_VX_OCC"); return e ? atoi(e) : 4; }();
 	for (int l = 0; l < Lt; ++l) {
 		BatchLevel& L = lv[l];
-		L.mask.reset(pool, (L.n + 3 + 16) & ~3ull);
-		L.mask.zero();
+		if (!L.mask.p) {   // (the leaf level's mask is created one level early, see k_flat_leaves)
+			L.mask.reset(pool, (L.n + 3 + 16) & ~3ull);
+			L.mask.zero();
+		}
 		const int last = (l == Lt - 1) ? 1 : 0;
 		DevBuf<uint8_t> hit(pool, last ? 16 : Fa + S + 16);
 		if (F + S > (1ull << 59)) throw Error(SVB_ERANGE, "too many pairs");
@@ -411,7 +449,10 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		SVB_CUDA(cudaMemcpyAsync(h, tot.p, 32, cudaMemcpyDeviceToHost, s));
 		SVB_CUDA(cudaStreamSynchronize(s));
 		const uint64_t Nn = h[0], cF = h[1], cS = h[2], cSF = h[3];
-		const uint64_t Fn = cF + cSF, Fan = (Fn + 15) & ~15ull, Sn = cS - cSF, Pn = Fan + Sn;
+		// second-to-last level: the children of the flat stream are decided in place (k_flat_leaves), not emitted
+		const bool fuseFlat = (l == Lt - 2) && F && !getenv("SVB_NO_FUSE");
+		const uint64_t cFe = fuseFlat ? 0 : cF;
+		const uint64_t Fn = cFe + cSF, Fan = (Fn + 15) & ~15ull, Sn = cS - cSF, Pn = Fan + Sn;
 		{
 			// will this batch fit all the way down?  Surfaces grow ~4x per level; use the observed ratio.
 			const int remaining = (Lt - 1) - (l + 1);
@@ -444,13 +485,21 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		SVB_KERNEL_CHECK();
 		DevBuf<uint32_t> ntri(pool, Pn + 16), nnode(pool, Pn + 16);
 		DevBuf<uint16_t> nflags(pool, Pn + 16);
-		if (F) {
+		if (fuseFlat) {
+			C.mask.reset(pool, (Nn + 3 + 16) & ~3ull);
+			C.mask.zero();
+			const double ksc = ldexp(1.0, -(l + 3));
+			if (directCentre) k_flat_leaves<true><<<blocks_for(F, VX_THREADS), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, L.code.p, L.mask.p, L.childBase.p, l + 1, ksc, d_tiles, d_tris, C.mask.p, C.tstar.p);
+			else k_flat_leaves<false><<<blocks_for(F, VX_THREADS), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, L.code.p, L.mask.p, L.childBase.p, l + 1, ksc, d_tiles, d_tris, C.mask.p, C.tstar.p);
+			SVB_KERNEL_CHECK();
+			pairsTotal += cF;   // decided here instead of as pairs of the last level
+		} else if (F) {
 			k_emit<false><<<blocks_for(F, EM_THREADS), EM_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p,
 			                                                                ntri.p, nnode.p, nflags.p, C.tstar.p);
 			SVB_KERNEL_CHECK();
 		}
 		if (S) {
-			k_emit<true><<<blocks_for(S, EM_THREADS), EM_THREADS, 0, s>>>(S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, cF, Fan, L.mask.p, L.childBase.p,
+			k_emit<true><<<blocks_for(S, EM_THREADS), EM_THREADS, 0, s>>>(S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, cFe, Fan, L.mask.p, L.childBase.p,
 			                                                               ntri.p, nnode.p, nflags.p, C.tstar.p);
 			SVB_KERNEL_CHECK();
 		}
