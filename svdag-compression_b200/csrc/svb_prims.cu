@@ -104,22 +104,60 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(In in, uint64_t n,
 	if (threadIdx.x == 0) blockSums[blockIdx.x] = tot;
 }
 
-// single block: exclusive scan of nb u32 sums into u64 offsets, grand total to *total
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const uint32_t* sums, uint64_t nb, uint64_t* offs, uint64_t* total) {
+// single block: exclusive scan of nb u32 sums into u64 offsets, grand total to *total (SCAN_TILE sums per trip)
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const uint32_t* __restrict__ sums, uint64_t nb, uint64_t* __restrict__ offs, uint64_t* __restrict__ total) {
 	__shared__ uint64_t carry;
 	if (threadIdx.x == 0) carry = 0;
 	__syncthreads();
-	for (uint64_t base = 0; base < nb; base += SCAN_THREADS) {
-		uint64_t i = base + threadIdx.x;
-		uint32_t x = (i < nb) ? sums[i] : 0;
+	for (uint64_t base = 0; base < nb; base += SCAN_TILE) {
+		const uint64_t i0 = base + (uint64_t)threadIdx.x * SCAN_ITEMS;
+		uint32_t v[SCAN_ITEMS];
+		uint32_t x = 0;
+#pragma unroll
+		for (int j = 0; j < SCAN_ITEMS; ++j) { v[j] = (i0 + j < nb) ? sums[i0 + j] : 0; x += v[j]; }
 		uint32_t tot;
 		uint32_t ex = block_excl_scan(x, &tot);
-		if (i < nb) offs[i] = carry + ex;
+		uint64_t o = carry + ex;
+#pragma unroll
+		for (int j = 0; j < SCAN_ITEMS; ++j) { if (i0 + j < nb) offs[i0 + j] = o; o += v[j]; }
 		__syncthreads();
 		if (threadIdx.x == 0) carry += tot;
 		__syncthreads();
 	}
 	if (threadIdx.x == 0) *total = carry;
+}
+
+// pair streams: per tile of SCAN_TILE pairs, the number of child pairs (popcount of the hit masks) and the number of
+// those whose flags put them into the flat stream (pair_is_fast, svb_classify.cuh), in one pass
+__global__ void __launch_bounds__(SCAN_THREADS) k_pair_reduce(const uint8_t* __restrict__ hit, const uint16_t* __restrict__ fl, uint64_t n,
+                                                              uint32_t* __restrict__ sumsA, uint32_t* __restrict__ sumsB) {
+	uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+	uint32_t a = 0, b = 0;
+	if (base + SCAN_ITEMS <= n) {
+		uint2 w = *reinterpret_cast<const uint2*>(hit + base);     // base is a multiple of 8, hit and fl 16B aligned
+		if (w.x | w.y) {
+			uint4 f = *reinterpret_cast<const uint4*>(fl + base);
+			const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+			for (int i = 0; i < SCAN_ITEMS; ++i) {
+				uint32_t c = __popc(((i < 4 ? w.x : w.y) >> (8 * (i & 3))) & 0xFF);
+				uint32_t g = (fw[i >> 1] >> (16 * (i & 1))) & 0xFFFF;
+				a += c;
+				if (pair_is_fast(g)) b += c;
+			}
+		}
+	} else {
+		for (int i = 0; i < SCAN_ITEMS; ++i)
+			if (base + i < n) {
+				uint32_t c = __popc((uint32_t)hit[base + i]);
+				a += c;
+				if (c && pair_is_fast(fl[base + i])) b += c;
+			}
+	}
+	uint32_t packed = a | (b << 16);   // a, b <= 8 * SCAN_ITEMS per thread, <= 8 * SCAN_TILE = 16384 per tile: fits 16 bits each
+	uint32_t tot;
+	block_excl_scan(packed, &tot);
+	if (threadIdx.x == 0) { sumsA[blockIdx.x] = tot & 0xFFFF; sumsB[blockIdx.x] = tot >> 16; }
 }
 
 template <class In>
@@ -214,6 +252,34 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* keys,
 void scan_popc8(cudaStream_t s, Pool& pool, const uint8_t* bytes, uint64_t n, uint32_t* out, uint64_t* d_total) {
 	scan_impl(s, pool, Popc8In{bytes}, n, out, d_total);
 }
+uint64_t scan_tile_items() { return SCAN_TILE; }
+
+void scan_tiles_popc8(cudaStream_t s, Pool& pool, const uint8_t* bytes, uint64_t n, DevBuf<uint64_t>& tileOffs, uint64_t* d_total) {
+	uint64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+	tileOffs.reset(pool, nb ? nb : 1);
+	if (n == 0) { SVB_CUDA(cudaMemsetAsync(d_total, 0, 8, s)); return; }
+	DevBuf<uint32_t> sums(pool, nb);
+	k_scan_reduce<Popc8In><<<(unsigned)nb, SCAN_THREADS, 0, s>>>(Popc8In{bytes}, n, sums.p);
+	SVB_KERNEL_CHECK();
+	k_scan_sums<<<1, SCAN_THREADS, 0, s>>>(sums.p, nb, tileOffs.p, d_total);
+	SVB_KERNEL_CHECK();
+}
+
+void scan_tiles_pairs(cudaStream_t s, Pool& pool, const uint8_t* hit, const uint16_t* flags, uint64_t n,
+                      DevBuf<uint64_t>& tileOffsA, DevBuf<uint64_t>& tileOffsB, uint64_t* d_totalA, uint64_t* d_totalB) {
+	uint64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+	tileOffsA.reset(pool, nb ? nb : 1);
+	tileOffsB.reset(pool, nb ? nb : 1);
+	if (n == 0) { SVB_CUDA(cudaMemsetAsync(d_totalA, 0, 8, s)); SVB_CUDA(cudaMemsetAsync(d_totalB, 0, 8, s)); return; }
+	DevBuf<uint32_t> sumsA(pool, nb), sumsB(pool, nb);
+	k_pair_reduce<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(hit, flags, n, sumsA.p, sumsB.p);
+	SVB_KERNEL_CHECK();
+	k_scan_sums<<<1, SCAN_THREADS, 0, s>>>(sumsA.p, nb, tileOffsA.p, d_totalA);
+	SVB_KERNEL_CHECK();
+	k_scan_sums<<<1, SCAN_THREADS, 0, s>>>(sumsB.p, nb, tileOffsB.p, d_totalB);
+	SVB_KERNEL_CHECK();
+}
+
 void scan_popc8_fast(cudaStream_t s, Pool& pool, const uint8_t* bytes, const uint16_t* flags, uint64_t n, uint32_t* out, uint64_t* d_total) {
 	scan_impl(s, pool, PopcFastIn{bytes, flags}, n, out, d_total);
 }

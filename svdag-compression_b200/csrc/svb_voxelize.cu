@@ -143,18 +143,65 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_classify_filtered(uint64_t
 	}
 }
 
-// children of node n: contiguous at childBase[n], ascending child index == Morton order
+// ------------------------------------------------------------------ tile-local scans
+// The scans of svb_prims.cu only deliver the exclusive offset of every tile of VX_TILE consecutive items; the two
+// expansion kernels below walk their tile in VX_TILE / 256 chunks, rebuild the per-item offsets with a block scan
+// and stage their output in shared memory so that it leaves the SM as contiguous, coalesced runs.
+constexpr int VX_TILE = 2048;
+constexpr int VX_CHUNKS = VX_TILE / VX_THREADS;
+
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t x, int lane) {
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+		if (lane >= d) x += y;
+	}
+	return x;
+}
+// exclusive prefix of x over the CTA (256 threads); *total = CTA sum.  Two barriers; wsum is caller-provided smem[9].
+__device__ __forceinline__ uint32_t cta_excl_scan(uint32_t x, uint32_t* wsum, uint32_t* total) {
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const uint32_t inc = warp_incl_scan_u32(x, lane);
+	if (lane == 31) wsum[w] = inc;
+	__syncthreads();
+	if (w == 0) {
+		uint32_t sv = (lane < VX_THREADS / 32) ? wsum[lane] : 0;
+		uint32_t si = warp_incl_scan_u32(sv, lane);
+		if (lane < VX_THREADS / 32) wsum[lane] = si - sv;
+		if (lane == VX_THREADS / 32 - 1) wsum[8] = si;
+	}
+	__syncthreads();
+	*total = wsum[8];
+	return inc - x + wsum[w];
+}
+
+// children of node n: contiguous at childBase[n], ascending child index == Morton order.  Writes childBase and the
+// child codes of one tile of nodes.
 __global__ void __launch_bounds__(VX_THREADS) k_children(uint64_t N, const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask,
-                                                          const uint32_t* __restrict__ childBase, uint64_t* __restrict__ ccode) {
-	uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (n >= N) return;
-	unsigned m = mask[n];
-	uint64_t cd = code[n] << 3;
-	uint32_t o = childBase[n];
-	while (m) {
-		int c = __ffs(m) - 1;
-		m &= m - 1;
-		ccode[o++] = cd | (uint64_t)c;
+                                                          const uint64_t* __restrict__ tileOffs, uint32_t* __restrict__ childBase, uint64_t* __restrict__ ccode) {
+	__shared__ uint64_t s_code[VX_THREADS * 8];
+	__shared__ uint32_t wsum[9];
+	const uint64_t n0 = (uint64_t)blockIdx.x * VX_TILE;
+	uint64_t run = tileOffs[blockIdx.x];
+	for (int ch = 0; ch < VX_CHUNKS; ++ch) {
+		const uint64_t nb = n0 + (uint64_t)ch * VX_THREADS;
+		if (nb >= N) break;
+		const uint64_t n = nb + threadIdx.x;
+		unsigned m = 0;
+		uint64_t cd = 0;
+		if (n < N) { m = mask[n]; cd = code[n] << 3; }
+		uint32_t tot;
+		uint32_t o = cta_excl_scan(__popc(m), wsum, &tot);
+		if (n < N) childBase[n] = (uint32_t)(run + o);
+		while (m) {
+			const int c = __ffs(m) - 1;
+			m &= m - 1;
+			s_code[o++] = cd | (uint64_t)c;
+		}
+		__syncthreads();
+		for (uint32_t i = threadIdx.x; i < tot; i += VX_THREADS) ccode[run + i] = s_code[i];
+		run += tot;
+		__syncthreads();
 	}
 }
 
@@ -220,87 +267,76 @@ __global__ void __launch_bounds__(VX_THREADS, 6) k_flat_leaves(uint64_t P, const
 }
 
 // ------------------------------------------------------------------ emit the child pairs
-// One thread per parent pair; the CTA's child pairs are staged in shared memory and written out as contiguous,
-// coalesced runs.  The pair arrays are kept as two streams: [0, nFast) fast pairs, [slowBase, ...) the others
-// (stable partition: both streams stay sorted by triangle id).  SLOW = false: parents of the fast stream (all
-// children fast, offsets offA).  SLOW = true: parents of the slow stream; offA = exclusive scan of all their
-// children, offB = of their fast children; fast children go to fastBase + offB, slow ones to slowBase + offA - offB.
-// First-touch triangle of the child nodes by atomicMin (pairs are sorted by triangle, so after the first touch the
-// pre-check load filters almost every later atomic).
-constexpr int EM_THREADS = 256;
+// One CTA per tile of parent pairs.  The pair arrays are kept as two streams: [0, nFlat) flat-stream pairs,
+// [slowBase, ...) the others (stable partition: both streams stay sorted by triangle id).  SLOW = false: parents of
+// the flat stream (all children flat, tile offsets offsA).  SLOW = true: parents of the other stream; offsA = tile
+// offsets over all their children, offsB = over their flat children; flat children go to fastBase + B, the others to
+// slowBase + (A - B).  First-touch triangle of the child nodes by atomicMin (pairs are sorted by triangle, so after
+// the first touch the pre-check load filters almost every later atomic).
 template <bool SLOW>
-__global__ void __launch_bounds__(EM_THREADS) k_emit(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
+__global__ void __launch_bounds__(VX_THREADS) k_emit(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
                                                      const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit,
-                                                     const uint32_t* __restrict__ offA, const uint32_t* __restrict__ offB, uint64_t fastBase, uint64_t slowBase,
+                                                     const uint64_t* __restrict__ offsA, const uint64_t* __restrict__ offsB, uint64_t fastBase, uint64_t slowBase,
                                                      const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase,
                                                      uint32_t* __restrict__ otri, uint32_t* __restrict__ onode, uint16_t* __restrict__ oflags, uint32_t* __restrict__ ctstar) {
-	__shared__ uint32_t s_tri[EM_THREADS * 8];
-	__shared__ uint32_t s_node[EM_THREADS * 8];
-	__shared__ uint16_t s_fl[EM_THREADS * 8];
-	__shared__ uint32_t s_nFast, s_nSlow;
-	const uint64_t p0 = (uint64_t)blockIdx.x * EM_THREADS;
-	const uint64_t p = p0 + threadIdx.x;
-	const uint64_t pLast = (p0 + EM_THREADS <= P ? p0 + EM_THREADS : P) - 1;
-	// offsets of the CTA's first parent (broadcast loads)
-	const uint32_t a0 = offA[p0];
-	const uint32_t b0 = SLOW ? offB[p0] : 0;
-	unsigned m = 0;
-	uint32_t t = 0, n = 0, fl = 0, oa = 0, ob = 0;
-	bool fastKids = !SLOW;
-	if (p < P) {
-		m = hit[p];
-		oa = offA[p];
-		if (SLOW) ob = offB[p];
-		if (m || p == pLast) {
-			fl = pflags[p];
-			if (SLOW) fastKids = pair_is_fast(fl);
+	__shared__ uint32_t s_tri[VX_THREADS * 8];
+	__shared__ uint32_t s_node[VX_THREADS * 8];
+	__shared__ uint16_t s_fl[VX_THREADS * 8];
+	__shared__ uint32_t wsum[9];
+	const uint64_t p0 = (uint64_t)blockIdx.x * VX_TILE;
+	uint64_t runF, runS = 0;
+	if (SLOW) { const uint64_t a = offsA[blockIdx.x], b = offsB[blockIdx.x]; runF = fastBase + b; runS = slowBase + (a - b); }
+	else runF = fastBase + offsA[blockIdx.x];
+	for (int ch = 0; ch < VX_CHUNKS; ++ch) {
+		const uint64_t pb = p0 + (uint64_t)ch * VX_THREADS;
+		if (pb >= P) break;
+		const uint64_t p = pb + threadIdx.x;
+		unsigned m = 0;
+		uint32_t t = 0, n = 0, fl = 0;
+		bool flatKids = true;
+		if (p < P) {
+			m = hit[p];
+			if (m) {
+				t = ptri[p]; n = pnode[p]; fl = pflags[p];
+				if (SLOW) flatKids = pair_is_fast(fl);
+			}
 		}
-		if (m) { t = ptri[p]; n = pnode[p]; }
-	}
-	const uint32_t cnt = __popc(m);
-	if (p == pLast) {   // totals of the CTA
+		const uint32_t cnt = __popc(m);
+		uint32_t tot;
+		const uint32_t ex = cta_excl_scan(flatKids ? cnt : (cnt << 16), wsum, &tot);   // low half: flat children, high half: others
+		const uint32_t nFlat = tot & 0xFFFF, nSlow = tot >> 16;
+		if (m) {
+			uint32_t o = flatKids ? (ex & 0xFFFF) : nFlat + (ex >> 16);
+			const unsigned nm = mask[n];
+			const uint32_t base = childBase[n];
+			unsigned mm = m;
+			while (mm) {
+				const int c = __ffs(mm) - 1;
+				mm &= mm - 1;
+				const uint32_t child = base + __popc(nm & ((1u << c) - 1));
+				s_tri[o] = t;
+				s_node[o] = child;
+				s_fl[o] = (uint16_t)fl;
+				++o;
+				if (ctstar[child] > t) atomicMin(&ctstar[child], t);
+			}
+		}
+		__syncthreads();
+		for (uint32_t i = threadIdx.x; i < nFlat; i += VX_THREADS) {
+			otri[runF + i] = s_tri[i];
+			onode[runF + i] = s_node[i];
+			oflags[runF + i] = s_fl[i];
+		}
 		if (SLOW) {
-			const uint32_t eb = ob + (fastKids ? cnt : 0), ea = oa + cnt;
-			s_nFast = eb - b0;
-			s_nSlow = (ea - eb) - (a0 - b0);
-		} else {
-			s_nFast = oa + cnt - a0;
-			s_nSlow = 0;
+			for (uint32_t i = threadIdx.x; i < nSlow; i += VX_THREADS) {
+				otri[runS + i] = s_tri[nFlat + i];
+				onode[runS + i] = s_node[nFlat + i];
+				oflags[runS + i] = s_fl[nFlat + i];
+			}
 		}
-	}
-	__syncthreads();
-	const uint32_t nFast = s_nFast, nSlow = s_nSlow;
-	if (m) {
-		// local slot of this parent's first child: fast children fill [0, nFast), slow children [nFast, nFast + nSlow)
-		uint32_t o = SLOW ? (fastKids ? ob - b0 : nFast + (oa - ob) - (a0 - b0)) : oa - a0;
-		const unsigned nm = mask[n];
-		const uint32_t base = childBase[n];
-		unsigned mm = m;
-		while (mm) {
-			const int c = __ffs(mm) - 1;
-			mm &= mm - 1;
-			const uint32_t child = base + __popc(nm & ((1u << c) - 1));
-			s_tri[o] = t;
-			s_node[o] = child;
-			s_fl[o] = (uint16_t)fl;
-			++o;
-			if (ctstar[child] > t) atomicMin(&ctstar[child], t);
-		}
-	}
-	__syncthreads();
-	const uint64_t dstFast = fastBase + (SLOW ? b0 : a0);
-	for (uint32_t i = threadIdx.x; i < nFast; i += EM_THREADS) {
-		otri[dstFast + i] = s_tri[i];
-		onode[dstFast + i] = s_node[i];
-		oflags[dstFast + i] = s_fl[i];
-	}
-	if (SLOW) {
-		const uint64_t dstSlow = slowBase + (a0 - b0);
-		for (uint32_t i = threadIdx.x; i < nSlow; i += EM_THREADS) {
-			otri[dstSlow + i] = s_tri[nFast + i];
-			onode[dstSlow + i] = s_node[nFast + i];
-			oflags[dstSlow + i] = s_fl[nFast + i];
-		}
+		runF += nFlat;
+		runS += nSlow;
+		__syncthreads();
 	}
 }
 
@@ -438,13 +474,11 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		}
 		pairsTotal += F + S;
 		if (last) break;
-		// children of the nodes, child pairs of the pairs: four scans, one read-back
-		L.childBase.reset(pool, L.n);
-		scan_popc8(s, pool, L.mask.p, L.n, L.childBase.p, tot.p + 0);
-		DevBuf<uint32_t> offF(pool, F + 1), offS(pool, S + 1), offSF(pool, S + 1);
-		scan_popc8(s, pool, hit.p, F, offF.p, tot.p + 1);
-		scan_popc8(s, pool, hit.p + Fa, S, offS.p, tot.p + 2);
-		scan_popc8_fast(s, pool, hit.p + Fa, pflags.p + Fa, S, offSF.p, tot.p + 3);
+		// children of the nodes, child pairs of the pairs: tile-granular scans, one read-back
+		DevBuf<uint64_t> nodeOffs, offF, offFB, offS, offSF;
+		scan_tiles_popc8(s, pool, L.mask.p, L.n, nodeOffs, tot.p + 0);
+		scan_tiles_popc8(s, pool, hit.p, F, offF, tot.p + 1);
+		scan_tiles_pairs(s, pool, hit.p + Fa, pflags.p + Fa, S, offS, offSF, tot.p + 2, tot.p + 3);
 		uint64_t h[4];
 		SVB_CUDA(cudaMemcpyAsync(h, tot.p, 32, cudaMemcpyDeviceToHost, s));
 		SVB_CUDA(cudaStreamSynchronize(s));
@@ -481,7 +515,8 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		C.code.reset(pool, Nn);
 		C.tstar.reset(pool, Nn);
 		C.tstar.fill_ff();
-		k_children<<<blocks_for(L.n, VX_THREADS), VX_THREADS, 0, s>>>(L.n, L.code.p, L.mask.p, L.childBase.p, C.code.p);
+		L.childBase.reset(pool, L.n);
+		k_children<<<blocks_for(L.n, VX_TILE), VX_THREADS, 0, s>>>(L.n, L.code.p, L.mask.p, nodeOffs.p, L.childBase.p, C.code.p);
 		SVB_KERNEL_CHECK();
 		DevBuf<uint32_t> ntri(pool, Pn + 16), nnode(pool, Pn + 16);
 		DevBuf<uint16_t> nflags(pool, Pn + 16);
@@ -494,12 +529,12 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 			SVB_KERNEL_CHECK();
 			pairsTotal += cF;   // decided here instead of as pairs of the last level
 		} else if (F) {
-			k_emit<false><<<blocks_for(F, EM_THREADS), EM_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p,
+			k_emit<false><<<blocks_for(F, VX_TILE), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p,
 			                                                                ntri.p, nnode.p, nflags.p, C.tstar.p);
 			SVB_KERNEL_CHECK();
 		}
 		if (S) {
-			k_emit<true><<<blocks_for(S, EM_THREADS), EM_THREADS, 0, s>>>(S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, cFe, Fan, L.mask.p, L.childBase.p,
+			k_emit<true><<<blocks_for(S, VX_TILE), VX_THREADS, 0, s>>>(S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, cFe, Fan, L.mask.p, L.childBase.p,
 			                                                               ntri.p, nnode.p, nflags.p, C.tstar.p);
 			SVB_KERNEL_CHECK();
 		}
