@@ -154,67 +154,99 @@ SVB_HD_NOINLINE unsigned exact_children(unsigned unsure, double Cx, double Cy, d
 // flags of such a pair never change, so all its descendants stay in this stream (k_classify_fast).
 SVB_HD bool pair_is_fast(unsigned fl) { return (fl & 0x1FFu) == 0x1FFu && (fl & (7u << FL_FLAT)) != 0; }
 
+// children whose index has the bit of axis a (0 = x, 1 = y, 2 = z) clear
+SVB_HD unsigned axis_lo_mask(int a) { return (0x55330Fu >> (8 * a)) & 0xFFu; }
+
+// The reference's box test of axis a (test_triangle_box.cpp:165-174) for the two child positions c = fl(C -+ k) of a
+// node centred at C (child half side k): children with the axis bit clear / set that pass.  dmin/dmax: the triangle's
+// extent on the axis (float inputs widened).  Exact: same operations, same order, same roundings as the reference.
+SVB_HD unsigned box_axis_children(const int a, const double C, const double k, const double dmin, const double dmax) {
+	const double cLo = SVB_DADD(C, -k), cHi = SVB_DADD(C, k);
+	const unsigned lo = axis_lo_mask(a);
+	unsigned pass = 0;
+	if (!(SVB_DSUB(dmin, cLo) > k || SVB_DSUB(dmax, cLo) < -k)) pass |= lo;
+	if (!(SVB_DSUB(dmin, cHi) > k || SVB_DSUB(dmax, cHi) < -k)) pass |= lo ^ 0xFFu;
+	return pass;
+}
+// node (half side 2k) strictly inside the triangle's slab on this axis, with a margin (2^-40 relative) far above
+// any rounding: the axis can never reject a box inside this node
+SVB_HD bool box_axis_settled(const double C, const double k2, const double dmin, const double dmax) {
+	const double mn = dmin - C, mx = dmax - C;
+	const double tol = (fmax(fabs(mn), fabs(mx)) + k2) * 9.094947017729282e-13;
+	return mn + k2 < -tol && mx - k2 > tol;
+}
+SVB_HD void axis_extent(const float* __restrict__ tp, const int a, const bool flat, double& dmin, double& dmax) {
+	float tmin = tp[a], tmax = tmin;
+	if (!flat) {
+		const float f1 = tp[3 + a], f2 = tp[6 + a];
+		tmin = fminf(tmin, fminf(f1, f2));
+		tmax = fmaxf(tmax, fmaxf(f1, f2));
+	}
+	dmin = (double)tmin; dmax = (double)tmax;
+}
+
+// All unsettled box axes of a pair, exactly; settles the axes the node has moved strictly inside of.
 template <bool DIRECT>
-SVB_HD unsigned classify_pair_flat(const uint64_t cd, const int l, const double* __restrict__ tg4, const double kscale, const float* __restrict__ tp, unsigned& fl) {
+SVB_HD unsigned box_axes_exact(const uint64_t cd, const int l, const double* __restrict__ tg4, const double k, const float* __restrict__ tp, unsigned& fl) {
 	const double rootSide = tg4[3];
-	const double k = rootSide * kscale, k2 = k + k;
 	const uint64_t path = cd & ((1ull << (3 * l)) - 1);
-	const unsigned ub = (~fl >> FL_BOX) & 7u;   // unsettled box axes (bit 0 = x)
+	unsigned ub = (~fl >> FL_BOX) & 7u;   // unsettled box axes (bit 0 = x)
 	unsigned m = 0xFFu;
-#pragma unroll
-	for (int a = 0; a < 3; ++a) {
-		if (!((ub >> a) & 1u)) continue;
-		float tmin = tp[a], tmax = tmin;
-		if (!((fl >> (FL_FLAT + a)) & 1u)) {
-			const float f1 = tp[3 + a], f2 = tp[6 + a];
-			tmin = fminf(tmin, fminf(f1, f2));
-			tmax = fmaxf(tmax, fmaxf(f1, f2));
-		}
+	while (ub) {
+		const int a = SVB_FFS(ub) - 1;
+		ub &= ub - 1;
+		double dmin, dmax;
+		axis_extent(tp, a, ((fl >> (FL_FLAT + a)) & 1u) != 0, dmin, dmax);
 		const double C = DIRECT ? centre_axis_direct(path, l, 2 - a, tg4[a], k) : centre_axis_chain(cd, l, 2 - a, tg4[a], rootSide);
-		const double dmin = (double)tmin, dmax = (double)tmax;
-		const double cLo = SVB_DADD(C, -k), cHi = SVB_DADD(C, k);
-		const unsigned lo = (a == 0) ? 0x0Fu : (a == 1) ? 0x33u : 0x55u;
-		unsigned pass = 0;
-		if (!(SVB_DSUB(dmin, cLo) > k || SVB_DSUB(dmax, cLo) < -k)) pass |= lo;
-		if (!(SVB_DSUB(dmin, cHi) > k || SVB_DSUB(dmax, cHi) < -k)) pass |= lo ^ 0xFFu;
-		m &= pass;
-		// node strictly inside the triangle's slab on this axis (margin 2^-40 relative, far above any rounding):
-		// the axis can never reject a box inside this node
-		const double mn = dmin - C, mx = dmax - C;
-		const double tol = (fmax(fabs(mn), fabs(mx)) + k2) * 9.094947017729282e-13;
-		if (mn + k2 < -tol && mx - k2 > tol) fl |= 1u << (FL_BOX + a);
+		m &= box_axis_children(a, C, k, dmin, dmax);
+		if (box_axis_settled(C, k + k, dmin, dmax)) fl |= 1u << (FL_BOX + a);
 	}
 	return m;
 }
 
-// Decides the 8 children of the node with Morton code `cd` (tile-local level l, tile geometry tg) against the
+template <bool DIRECT>
+SVB_HD unsigned classify_pair_flat(const uint64_t cd, const int l, const double* __restrict__ tg4, const double kscale, const float* __restrict__ tp, unsigned& fl) {
+	return box_axes_exact<DIRECT>(cd, l, tg4, tg4[3] * kscale, tp, fl);
+}
+
+// Flat-stream pair at the second-to-last level: the voxel masks of its children (the leaf nodes), without emitting
+// child pairs.  Child c sits at fl(C +- k) on every axis (the next step of the centre chain); its voxels at
+// fl(c +- k/2).  Per unsettled axis the two possible child positions are tested once; childMask[j] (j = the child's
+// bit on that axis) then combine by AND.  out[c] is only meaningful for children the pair hits.
+template <bool DIRECT>
+SVB_HD void flat_leaf_masks(const uint64_t cd, const int l, const double* __restrict__ tg4, const double kscale, const float* __restrict__ tp,
+                            const unsigned fl, unsigned lohi[3][2]) {
+	const double rootSide = tg4[3];
+	const double k = rootSide * kscale, kh = k * 0.5;
+	const uint64_t path = cd & ((1ull << (3 * l)) - 1);
+	const unsigned ub = (~fl >> FL_BOX) & 7u;
+#pragma unroll
+	for (int a = 0; a < 3; ++a) {
+		lohi[a][0] = lohi[a][1] = 0xFFu;
+		if (!((ub >> a) & 1u)) continue;
+		double dmin, dmax;
+		axis_extent(tp, a, ((fl >> (FL_FLAT + a)) & 1u) != 0, dmin, dmax);
+		const double C = DIRECT ? centre_axis_direct(path, l, 2 - a, tg4[a], k) : centre_axis_chain(cd, l, 2 - a, tg4[a], rootSide);
+		lohi[a][0] = box_axis_children(a, SVB_DADD(C, -k), kh, dmin, dmax);
+		lohi[a][1] = box_axis_children(a, SVB_DADD(C, k), kh, dmin, dmax);
+	}
+}
+
+// Decides the 8 children of the node with Morton code `cd` (tile-local level l, tile geometry tg4 = {cx,cy,cz,rootSide}) against the
 // triangle tp[0..8].  fl: the pair's settled-axis flags (in: inherited from the parent pair, out: for the child
 // pairs).  nUnsure: children that had to be re-decided by the reference-order predicate.  Returns the hit mask.
 template <bool DIRECT>
-SVB_HD unsigned classify_pair(const uint64_t cd, const int l, const TileGeom& tg, const double kscale, const float* __restrict__ tp,
+SVB_HD unsigned classify_pair(const uint64_t cd, const int l, const double* __restrict__ tg4, const double kscale, const float* __restrict__ tp,
                               unsigned& fl, unsigned& nUnsure) {
 	nUnsure = 0;
-	const double k = tg.rootSide * kscale;   // child half side rootSide / 2^(l+2) (octree.hpp:115), exact scaling
+	const double k = tg4[3] * kscale;   // child half side rootSide / 2^(l+2) (octree.hpp:115), exact scaling
 	const uint64_t path = cd & ((1ull << (3 * l)) - 1);
 	if (pair_is_fast(fl)) {   // never taken inside k_classify_filtered: such pairs live in the flat stream (k_classify_fast)
-		const double tg4[4] = {tg.cx, tg.cy, tg.cz, tg.rootSide};
 		return classify_pair_flat<DIRECT>(cd, l, tg4, kscale, tp, fl);
-	}
-	double Cx, Cy, Cz;
-	if (DIRECT) {
-		Cx = centre_axis_direct(path, l, 2, tg.cx, k);
-		Cy = centre_axis_direct(path, l, 1, tg.cy, k);
-		Cz = centre_axis_direct(path, l, 0, tg.cz, k);
-	} else {
-		double kk;
-		node_centre(cd, l, tg, Cx, Cy, Cz, kk);
 	}
 	float tf[9];
 #pragma unroll
 	for (int i = 0; i < 9; ++i) tf[i] = tp[i];
-	const double v0x = (double)tf[0] - Cx, v0y = (double)tf[1] - Cy, v0z = (double)tf[2] - Cz;
-	const double v1x = (double)tf[3] - Cx, v1y = (double)tf[4] - Cy, v1z = (double)tf[5] - Cz;
-	const double v2x = (double)tf[6] - Cx, v2y = (double)tf[7] - Cy, v2z = (double)tf[8] - Cz;
 	// ---- static analysis of the triangle, once per triangle/pair lineage (FL_INIT), rigorous (no tolerance):
 	// (1) An edge whose endpoints share a coordinate q BITWISE has e_q = +0 in the reference-order predicate for any
 	//     box centre (fl(t - c) - fl(t - c)).  Its two cross axes that involve e_q then read  p = fl(+-e_r * v_q),
@@ -238,27 +270,29 @@ SVB_HD unsigned classify_pair(const uint64_t cd, const int l, const TileGeom& tg
 		fl |= FL_INIT;
 	}
 	const bool planeImplied = (fl & (7u << FL_FLAT)) != 0;
+	// ---- box axes: the reference's own 1-D tests at the chain-rounded child centres -- exact, so a wall lying in a
+	//      voxel face (a tie on a box axis) never needs the full predicate
+	unsigned alive = box_axes_exact<DIRECT>(cd, l, tg4, k, tp, fl);   // (tp, not tf: dynamic axis index)
+	unsigned unsure = 0;
+	if (!alive) return 0;
+	if (planeImplied && (fl & 0x1FFu) == 0x1FFu) return alive;   // nothing but box axes left (the pair joins the flat stream)
+	double Cx, Cy, Cz;
+	if (DIRECT) {
+		Cx = centre_axis_direct(path, l, 2, tg4[0], k);
+		Cy = centre_axis_direct(path, l, 1, tg4[1], k);
+		Cz = centre_axis_direct(path, l, 0, tg4[2], k);
+	} else {
+		double kk;
+		const TileGeom tg{tg4[0], tg4[1], tg4[2], tg4[3]};
+		node_centre(cd, l, tg, Cx, Cy, Cz, kk);
+	}
+	const double v0x = (double)tf[0] - Cx, v0y = (double)tf[1] - Cy, v0z = (double)tf[2] - Cz;
+	const double v1x = (double)tf[3] - Cx, v1y = (double)tf[4] - Cy, v1z = (double)tf[5] - Cz;
+	const double v2x = (double)tf[6] - Cx, v2y = (double)tf[7] - Cy, v2z = (double)tf[8] - Cz;
 	const double k2 = k + k;
 	double M = fmax(fmax(fmax(fabs(v0x), fabs(v0y)), fmax(fabs(v0z), fabs(v1x))), fmax(fmax(fabs(v1y), fabs(v1z)), fmax(fabs(v2x), fmax(fabs(v2y), fabs(v2z))))) + k2;
 	const double eps = 9.094947017729282e-13;   // 2^-40
-	const double tol1 = M * eps, tol2 = M * tol1, tol3 = M * tol2;
-	unsigned alive = 0xFFu, unsure = 0;
-	// --- box axes: child with bit clear sits at -k, with bit set at +k
-#define SVB_BOX_AXIS(a0, a1, a2, BIT, FLB)                                                     \
-	if (!(fl & (FLB))) {                                                                       \
-		double mn = fmin(fmin(a0, a1), a2), mx = fmax(fmax(a0, a1), a2);                       \
-		if (mn + k2 < -tol1 && mx - k2 > tol1) fl |= (FLB);   /* node strictly inside the triangle's slab */ \
-		else {                                                                                 \
-			if (mn > tol1 || mx < -k2 - tol1) alive &= ~SVB_LO(BIT);                           \
-			else if (!(mn < -tol1 && mx > -k2 + tol1)) unsure |= SVB_LO(BIT);                  \
-			if (mn > k2 + tol1 || mx < -tol1) alive &= ~SVB_HI(BIT);                           \
-			else if (!(mn < k2 - tol1 && mx > tol1)) unsure |= SVB_HI(BIT);                    \
-		}                                                                                      \
-	}
-	SVB_BOX_AXIS(v0x, v1x, v2x, 4, 1u << (FL_BOX + 0))
-	SVB_BOX_AXIS(v0y, v1y, v2y, 2, 1u << (FL_BOX + 1))
-	SVB_BOX_AXIS(v0z, v1z, v2z, 1, 1u << (FL_BOX + 2))
-#undef SVB_BOX_AXIS
+	const double tol2 = M * (M * eps), tol3 = M * tol2;
 	if (alive) {
 		const double e0x = v1x - v0x, e0y = v1y - v0y, e0z = v1z - v0z;
 		const double e1x = v2x - v1x, e1y = v2y - v1y, e1z = v2z - v1z;

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_classify_filtered(uint64_t
 	const unsigned fl0 = pflags[p];
 	unsigned fl = fl0, nUnsure;
 	const uint64_t cd = code[n];
-	const TileGeom tg = tiles[(uint32_t)(cd >> (3 * l))];
+	const double* tg = reinterpret_cast<const double*>(tiles + (uint32_t)(cd >> (3 * l)));   // {cx, cy, cz, rootSide}
 	const unsigned m = classify_pair<DIRECT>(cd, l, tg, kscale, tris + 9ull * t, fl, nUnsure);
 	if (nUnsure && nExact) atomicAdd(nExact, (unsigned long long)nUnsure);
 	if (!last) {
@@ -239,8 +239,8 @@ template <bool DIRECT>
 __global__ void __launch_bounds__(VX_THREADS, 6) k_flat_leaves(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
                                                                const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit,
                                                                const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase,
-                                                               int lc, double kscaleChild, const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
-                                                               uint8_t* __restrict__ cmask, uint32_t* __restrict__ ctstar, int expNoTstar) {
+                                                               int lc, double kscaleParent, const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
+                                                               uint8_t* __restrict__ cmask, uint32_t* __restrict__ ctstar) {
 	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= P) return;
 	unsigned m = hit[p];
@@ -252,6 +252,8 @@ __global__ void __launch_bounds__(VX_THREADS, 6) k_flat_leaves(uint64_t P, const
 	const uint32_t base = childBase[n];
 	const double* tg = reinterpret_cast<const double*>(tiles + (uint32_t)(cd >> (3 * (lc - 1))));
 	const float* tp = tris + 9ull * t;
+	unsigned lohi[3][2];
+	flat_leaf_masks<DIRECT>(cd, lc - 1, tg, kscaleParent, tp, fl, lohi);
 	// the children of one node are consecutive, so their voxel masks are consecutive bytes: OR them word by word
 	unsigned* const words = reinterpret_cast<unsigned*>(cmask);
 	uint32_t curWord = 0xFFFFFFFFu;
@@ -260,15 +262,13 @@ __global__ void __launch_bounds__(VX_THREADS, 6) k_flat_leaves(uint64_t P, const
 		const int c = __ffs(m) - 1;
 		m &= m - 1;
 		const uint32_t child = base + __popc(nm & ((1u << c) - 1));
-		unsigned flc = fl;
-		const unsigned mc = classify_pair_flat<DIRECT>((cd << 3) | (uint64_t)c, lc, tg, kscaleChild, tp, flc);
+		const unsigned mc = lohi[0][(c >> 2) & 1] & lohi[1][(c >> 1) & 1] & lohi[2][c & 1];
 		if ((child >> 2) != curWord) {
 			if (acc && (words[curWord] & acc) != acc) atomicOr(words + curWord, acc);
 			curWord = child >> 2;
 			acc = 0;
 		}
 		acc |= mc << (8 * (child & 3));
-		if (expNoTstar) continue;
 		if (ctstar[child] > t) atomicMin(&ctstar[child], t);
 	}
 	if (acc && (words[curWord] & acc) != acc) atomicOr(words + curWord, acc);
@@ -531,9 +531,8 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		if (fuseFlat) {
 			C.mask.reset(pool, (Nn + 3 + 16) & ~3ull);
 			C.mask.zero();
-			const double ksc = ldexp(1.0, -(l + 3));
-			if (directCentre) k_flat_leaves<true><<<blocks_for(F, VX_THREADS), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, L.code.p, L.mask.p, L.childBase.p, l + 1, ksc, d_tiles, d_tris, C.mask.p, C.tstar.p, getenv("SVB_EXP_NOTSTAR") ? 1 : 0);
-			else k_flat_leaves<false><<<blocks_for(F, VX_THREADS), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, L.code.p, L.mask.p, L.childBase.p, l + 1, ksc, d_tiles, d_tris, C.mask.p, C.tstar.p, getenv("SVB_EXP_NOTSTAR") ? 1 : 0);
+			if (directCentre) k_flat_leaves<true><<<blocks_for(F, VX_THREADS), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, L.code.p, L.mask.p, L.childBase.p, l + 1, kscale, d_tiles, d_tris, C.mask.p, C.tstar.p);
+			else k_flat_leaves<false><<<blocks_for(F, VX_THREADS), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, L.code.p, L.mask.p, L.childBase.p, l + 1, kscale, d_tiles, d_tris, C.mask.p, C.tstar.p);
 			SVB_KERNEL_CHECK();
 			pairsTotal += cF;   // decided here instead of as pairs of the last level
 		} else if (F) {

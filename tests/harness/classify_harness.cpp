@@ -33,7 +33,8 @@ int harness_run(const float* tris, uint64_t T, const double centre[3], double ro
 		for (const Pair& p : cur) {
 			unsigned fl = p.fl, nUnsure = 0;
 			const float* tp = tris + 9ull * p.tri;
-			unsigned m = direct ? classify_pair<true>(p.code, l, tg, kscale, tp, fl, nUnsure) : classify_pair<false>(p.code, l, tg, kscale, tp, fl, nUnsure);
+			const double tgv[4] = {tg.cx, tg.cy, tg.cz, tg.rootSide};
+			unsigned m = direct ? classify_pair<true>(p.code, l, tgv, kscale, tp, fl, nUnsure) : classify_pair<false>(p.code, l, tgv, kscale, tp, fl, nUnsure);
 			if (pair_is_fast(p.fl)) out[2]++;
 			out[3] += nUnsure;
 			// reference: chain centre of the node, then each child centre, then the predicate
@@ -48,6 +49,29 @@ int harness_run(const float* tris, uint64_t T, const double centre[3], double ro
 			if (m != want) {
 				if (out[1] == 0) { out[4] = (uint64_t)l; out[5] = p.tri; out[6] = p.code; out[7] = m; out[8] = want; out[9] = p.fl; }
 				out[1]++;
+			}
+			// second-to-last level, pair that joins the flat stream: the fused leaf kernel (k_flat_leaves) decides the
+			// voxels of its children with flat_leaf_masks(); compare with the predicate on every voxel
+			if (l == Lt - 2 && pair_is_fast(fl)) {
+				const double tg4[4] = {tg.cx, tg.cy, tg.cz, tg.rootSide};
+				unsigned lohi[3][2];
+				if (direct) flat_leaf_masks<true>(p.code, l, tg4, kscale, tp, fl, lohi); else flat_leaf_masks<false>(p.code, l, tg4, kscale, tp, fl, lohi);
+				for (int c = 0; c < 8; ++c) {
+					if (!((want >> c) & 1)) continue;
+					const unsigned got = lohi[0][(c >> 2) & 1] & lohi[1][(c >> 1) & 1] & lohi[2][c & 1];
+					double ccx = cx + ((c & 4) ? k : -k), ccy = cy + ((c & 2) ? k : -k), ccz = cz + ((c & 1) ? k : -k);
+					const double kh = k * 0.5;
+					unsigned wantv = 0;
+					for (int q = 0; q < 8; ++q) {
+						double vx = ccx + ((q & 4) ? kh : -kh), vy = ccy + ((q & 2) ? kh : -kh), vz = ccz + ((q & 1) ? kh : -kh);
+						if (tri_box_overlap(vx, vy, vz, kh, tp)) wantv |= 1u << q;
+					}
+					out[0]++;
+					if (got != wantv) {
+						if (out[1] == 0) { out[4] = (uint64_t)l + 100; out[5] = p.tri; out[6] = (p.code << 3) | (uint64_t)c; out[7] = got; out[8] = wantv; out[9] = fl; }
+						out[1]++;
+					}
+				}
 			}
 			// descend along the REFERENCE decision so one wrong pair does not hide its subtree
 			for (int c = 0; c < 8; ++c)
