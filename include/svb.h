@@ -27,6 +27,12 @@ extern "C" {
 #define SVB_ENOMEM     -3   /* device memory exhausted even after splitting the tile batch */
 #define SVB_ERANGE     -4   /* configuration exceeds an id/order-key bit budget (see DESIGN.md "order key") */
 #define SVB_ECOLLISION -5   /* 64-bit node-key hash collision detected by the exact verify pass */
+#define SVB_ENODEV     -6   /* no usable CUDA device (there is no CPU fallback) */
+
+/* encoded file kinds (svb_encode / svb_raycast_depth): what EncodedSVDAG / EncodedUSSVDAG / EncodedSSVDAG save */
+#define SVB_FILE_SVDAG   0   /* .svdag and -multi.svdag */
+#define SVB_FILE_USSVDAG 1   /* .ussvdag */
+#define SVB_FILE_SSVDAG  2   /* .ssvdag and .esvdag */
 
 #define SVB_NULL_NODE 0xFFFFFFFEu   /* Octree::nullNode, src/symvox/octree.cpp:22 */
 
@@ -167,6 +173,19 @@ int svb_profile_get(const svb_ctx* ctx, int i, svb_prof_rec* out);
 /* Cap on device bytes one tile batch may use for its transient (pair/node) buffers;
  * 0 = automatic (a fraction of free memory).  Smaller values force more batches (tests). */
 int svb_set_batch_budget(svb_ctx* ctx, uint64_t bytes);
+
+/* ---- depth-image sanity check (BASELINE.json north_star) ----------------------------
+ * CUDA DDA ray caster over an encoded file image, following the reference viewer's fragment shader in
+ * DEPTH_MODE (shaders/octree_dda.frag.glsl:484-585, :846-858) with the uniforms
+ * src/svviewer/octree_dda_renderer.cpp:195-211 derives from the file header.  `file`/`size`: the bytes of a
+ * .svdag / -multi.svdag / .ussvdag / .ssvdag / .esvdag file (host memory); kind: SVB_FILE_*;
+ * viewInv / projInv: the shader's viewMatInv / projMatInv (column-major float[16]); drawLevel 0 = all levels;
+ * projectionFactor: the viewer's LOD factor (octree_dda_renderer.cpp:503-507; 1e30 disables LOD).
+ * out_host receives width*height*3 floats, pixel (x, y) at 3*(y*width + x): (t, level, iterations) of the
+ * hit, or zeros where the shader discards the fragment.  Images are deterministic (no FMA contraction, IEEE
+ * division/sqrt), so two files of the same scene can be compared pixel-exactly.  Stateless; runs on `device`. */
+int svb_raycast_depth(int device, const uint8_t* file, uint64_t size, int kind, const float viewInv[16], const float projInv[16],
+                      uint32_t width, uint32_t height, uint32_t maxIters, uint32_t drawLevel, float projectionFactor, float* out_host);
 
 #ifdef __cplusplus
 }

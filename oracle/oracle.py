@@ -16,6 +16,7 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 REF_BIN = HERE / "_ref" / "svbuilder_ref"
 LIB = HERE / "_ref" / "libsvdag_oracle.so"
+DDA_LIB = HERE / "_ref" / "libdda_oracle.so"
 
 STAT = {"nTotalVoxels": 0, "nNodesSVO": 1, "nNodesDAG": 2, "nNodesSDAG": 3,
         "nNodesLastLevSVO": 4, "nNodesLastLevDAG": 5, "nCrossLevelMerged": 6, "nNodes": 7}
@@ -181,3 +182,30 @@ def run_reference(workdir, tris: np.ndarray, levels: int, step: int, cross: bool
         if f.exists():
             files[ext] = f.read_bytes()
     return {"files": files, "log": p.stdout, "seconds": dt}
+
+
+# ------------------------------------------------------------------ DDA ray caster (oracle/dda_oracle.c)
+_dda = None
+FILE_KIND = {"svdag": 0, "ussvdag": 1, "ssvdag": 2, "esvdag": 2}
+
+
+def dda_render(file_bytes: bytes, kind: str, view_inv, proj_inv, width: int, height: int,
+               max_iters: int = 512, draw_level: int = 0, projection_factor: float = 0.0) -> np.ndarray:
+    """Depth image (h, w, 3) = (t, level, iterations) of an encoded file, CPU restatement of the viewer's DEPTH_MODE
+    shader.  view_inv / proj_inv: 4x4 float32, column-major flattened (what glUniformMatrix4fv receives)."""
+    global _dda
+    if _dda is None:
+        if not DDA_LIB.exists():
+            build(ref=False)
+        _dda = C.CDLL(str(DDA_LIB))
+        _dda.dda_oracle_render.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                           C.c_uint32, C.c_uint32, C.c_float, C.c_void_p]
+    buf = np.frombuffer(file_bytes, dtype=np.uint8)
+    vi = np.ascontiguousarray(view_inv, dtype=np.float32).reshape(16)
+    pi = np.ascontiguousarray(proj_inv, dtype=np.float32).reshape(16)
+    out = np.zeros((height, width, 3), np.float32)
+    rc = _dda.dda_oracle_render(buf.ctypes.data, len(buf), FILE_KIND[kind], vi.ctypes.data, pi.ctypes.data, width, height,
+                                max_iters, draw_level, float(projection_factor), out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("dda_oracle_render failed (bad file?)")
+    return out

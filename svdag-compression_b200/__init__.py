@@ -10,9 +10,10 @@ under the module name `svdag_compression_b200`.
 """
 from . import meshgen  # noqa: F401
 from . import build as _build  # noqa: F401
-from .capi import SvbError, GeomOctree, lib, lib_path, STATE_NAMES  # noqa: F401
+from .capi import SvbError, GeomOctree, lib, lib_path, STATE_NAMES, raycast_depth  # noqa: F401
 from . import encoders  # noqa: F401
 from . import sharded  # noqa: F401
+from . import camera  # noqa: F401
 
 __all__ = ["meshgen", "GeomOctree", "SvbError", "lib", "lib_path", "encoders", "build_native"]
 

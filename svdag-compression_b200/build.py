@@ -18,7 +18,9 @@ SVBUILDER = HERE / "svbuilder"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = "/usr/bin/g++"   # the environment's CXX points at a compiler without libgomp; pin the system one
 
-CU_SOURCES = ["svb_prims.cu", "svb_voxelize.cu", "svb_dedup.cu", "svb_sdag.cu", "svb_cross.cu", "svb_api.cu", "host/encoders.cpp"]
+CU_SOURCES = ["svb_prims.cu", "svb_voxelize.cu", "svb_dedup.cu", "svb_sdag.cu", "svb_cross.cu", "svb_api.cu", "svb_raycast.cu", "host/encoders.cpp"]
+# the ray caster must round every float operation separately (pixel-exact against oracle/dda_oracle.c)
+EXTRA_FLAGS = {"svb_raycast.cu": ["--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false"]}
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unused-function",
@@ -44,7 +46,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     for src in CU_SOURCES:
         obj = objdir / (src.replace("/", "_") + ".o")
         objs.append(str(obj))
-        cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [NVCC] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", str(CSRC / src), "-o", str(obj)]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

@@ -86,6 +86,7 @@ def lib() -> C.CDLL:
         L.svb_profile_count.argtypes = [vp]
         L.svb_profile_get.argtypes = [vp, C.c_int, C.POINTER(ProfRec)]
         L.svb_set_batch_budget.argtypes = [vp, u64]
+        L.svb_raycast_depth.argtypes = [C.c_int, vp, u64, C.c_int, vp, vp, u32, u32, u32, u32, C.c_float, vp]
         _lib = L
     return _lib
 
@@ -261,3 +262,20 @@ class GeomOctree:
 
     def set_batch_budget(self, nbytes: int):
         self._L.svb_set_batch_budget(self._h, int(nbytes))
+
+
+FILE_KIND = {"svdag": 0, "multi.svdag": 0, "ussvdag": 1, "ssvdag": 2, "esvdag": 2}
+
+
+def raycast_depth(file_bytes: bytes, kind: str, view_inv, proj_inv, width: int, height: int, max_iters: int = 512,
+                  draw_level: int = 0, projection_factor: float = 1e30, device: int = 0) -> np.ndarray:
+    """Depth image (h, w, 3) = (t, level, iterations) of an encoded file: svb_raycast_depth (CUDA)."""
+    buf = np.frombuffer(file_bytes, dtype=np.uint8)
+    vi = np.ascontiguousarray(view_inv, dtype=np.float32).reshape(16)
+    pi = np.ascontiguousarray(proj_inv, dtype=np.float32).reshape(16)
+    out = np.zeros((height, width, 3), np.float32)
+    rc = lib().svb_raycast_depth(device, buf.ctypes.data, len(buf), FILE_KIND[kind], vi.ctypes.data, pi.ctypes.data, width, height,
+                                 max_iters, draw_level, float(projection_factor), out.ctypes.data)
+    if rc != 0:
+        raise SvbError(rc, "svb_raycast_depth failed" + (" (no CUDA device: there is no CPU fallback)" if rc == -6 else ""))
+    return out
