@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("SVB_BENCH_WORKLOAD", "city_16k"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only; the line then carries e2e = null)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -238,14 +239,16 @@ def main():
     oct_.set_profiling(False)
 
     # ---- end-to-end timing through the public API with host buffers
-    step_e2e()
-    barrier()
-    t1 = time.perf_counter()
-    for _ in range(args.steps):
-        st_e, sd_e, img = step_e2e()
-    barrier()
-    elapsed_e2e = time.perf_counter() - t1
-    d2h = sum(n * (1 + 32 + 3) for n in oct_.level_sizes())
+    elapsed_e2e, d2h, img = float("nan"), 0, b""
+    if not args.no_e2e:
+        step_e2e()
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(args.steps):
+            st_e, sd_e, img = step_e2e()
+        barrier()
+        elapsed_e2e = time.perf_counter() - t1
+        d2h = sum(n * (1 + 32 + 3) for n in oct_.level_sizes())
 
     if world > 1:
         tmax = torch.tensor([elapsed, elapsed_e2e], dtype=torch.float64, device="cuda")
@@ -268,8 +271,18 @@ def main():
         per_unit = 13.0   # leaf node = 1 B mask + 4 B first-touch triangle + 8 B Morton code, read once
         alg = per_unit * leaf["units"]
         ach = alg / (leaf["ms"] * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        tp = ROOT / "profiles" / "ncu_traffic.json"     # dram__bytes_read+write per leaf node, from one `ncu --set full` capture
+        if tp.exists():
+            try:
+                tj = json.loads(tp.read_text())["k_leaf_min"]
+                traffic = float(tj["dram_bytes_per_unit"]) * leaf["units"] / leaf["launches"]
+                traffic_src = tj.get("source")
+            except Exception:
+                pass
         roof = {"kernel": "k_leaf_min (dedup, leaf level)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peak_src, "bytes_per_unit": per_unit,
+                "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg / leaf["launches"],
+                "peak_source": peak_src, "bytes_per_unit": per_unit,
                 "units_per_launch": leaf["units"] / leaf["launches"], "avg_launch_ms": leaf["ms"] / leaf["launches"],
                 "achieved_with_survey_formula_37B_per_node": leaf["bytes_survey"] / (leaf["ms"] * 1e-3) / 1e9,
                 "note": "SURVEY.md 8(d) charges 37 B/node for a materialised 33-byte key; this layout never materialises it and reads 13 B/node"}
@@ -281,8 +294,8 @@ def main():
             "data": "synthetic", "config": config, "build_s": sec, "device_ms_per_step": dev_ms / args.steps,
             "voxels": vox, "triangles": int(T), "nodes": {"svo": st["nNodesSVO"], "dag": st["nNodesDAG"], "sdag": sd["nNodesSDAG"]},
             "tiles": st["nTiles"], "batches": st["nBatches"], "pairs": st["nPairsTotal"], "exact_retests": st["nExactTests"],
-            "e2e": {"value": vox / sec_e2e / 1e9, "unit": "Gvoxel/s", "h2d_bytes_per_step": int(T) * 36, "d2h_bytes_per_step": int(d2h),
-                    "seconds_per_step": sec_e2e, "ssvdag_bytes": len(img)},
+            "e2e": None if args.no_e2e else {"value": vox / sec_e2e / 1e9, "unit": "Gvoxel/s", "h2d_bytes_per_step": int(T) * 36,
+                                             "d2h_bytes_per_step": int(d2h), "seconds_per_step": sec_e2e, "ssvdag_bytes": len(img)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels}
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:

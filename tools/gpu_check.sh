@@ -1,6 +1,6 @@
 #!/bin/bash
-# scratch: gpu tests + short bench
-cd /root/repo
+# GPU box check: gpu tests + a short bench line (gpurun -- tools/gpu_check.sh)
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/pytest_gpu.log
 cat gpurun_out/pytest_gpu.log

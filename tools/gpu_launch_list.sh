@@ -1,10 +1,10 @@
 #!/bin/bash
-# scratch: launch list of one full 16K^3 city build
-cd /root/repo
+# ncu launch list of one full 16K^3 city build, aggregated per kernel (gpurun -- tools/gpu_launch_list.sh)
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 cat > /tmp/ncu_city.py <<'PY'
 import sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, ".")
 import numpy as np
 import __graft_entry__ as g
 pkg = g._pkg()
