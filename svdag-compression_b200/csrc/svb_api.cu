@@ -8,6 +8,7 @@
 // sub-octree ("tile") list of step mode from the (tiny) base octree, and sequences launches.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "svb_context.cuh"
@@ -181,6 +182,21 @@ struct svb_build_state {
 namespace {
 
 typedef svb_build_state BuildState;
+
+// Order keys (tile_seq | t* | path') must fit 63 bits at every level that is reduced through a 64-bit table.  The
+// deepest level (3*(Lt-1) path bits) is the voxel-mask level, whose 256-entry table can hold a two-word key: if only
+// that level overflows, it runs in wide mode (two passes, svb_dedup.cu::dedup_leaf); e.g. 64K^3 with step 7 and 12 M
+// triangles needs 21 + 24 + 3*7 = 66 bits at the leaves but 63 above.
+void set_order_key_width(BuildState& B, int Lt) {
+	const int leafBits = B.tileBits + B.tbits + 3 * (Lt - 1);
+	const int innerBits = B.tileBits + B.tbits + 3 * std::max(Lt - 2, 0);
+	const char* force = getenv("SVB_WIDE_LEAF");
+	bool wide = leafBits > 63 || (force && force[0] == '1');
+	if ((wide ? innerBits : leafBits) > 63 || B.tileBits + B.tbits > 63)
+		throw Error(SVB_ERANGE, "order key exceeds 63 bits (" + std::to_string(B.tileBits) + " tile + " + std::to_string(B.tbits) + " triangle + " +
+		                            std::to_string(3 * std::max(Lt - 2, 0)) + " path bits): increase step (fewer levels per sub-octree)");
+	B.tables[B.L - 1].wide = wide;
+}
 
 // bottom-up reduction of one batch's levels [lo_l, Lt-1] into the tables
 void dedup_batch(svb_ctx* c, BuildState& B, std::vector<BatchLevel>& lv, int Lt, uint32_t gbase, const uint32_t* d_tileSeq, int lo_l) {
@@ -358,7 +374,7 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 	if (step == 0) {
 		B.s1 = 0;
 		B.tileBits = 1;
-		if (B.tileBits + B.tbits + 3 * ((int)L - 1) > 63) throw Error(SVB_ERANGE, "order key exceeds 64 bits: use step > 0 for this many levels/triangles");
+		set_order_key_width(B, (int)L);
 		try {
 			run_tile_batch(c, B, rootTile, sel0, 0, 1, B.grid1, B.dGrid1.p, (int)L, 0, budget, 0, nullptr);
 		} catch (const BatchTooBig&) {
@@ -432,8 +448,8 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 	const uint64_t nTiles = B.tiles.size();
 	B.tileBits = bits_for(nTiles ? nTiles - 1 : 0);
 	const int Lt = (int)(L - s1);
-	if (B.tileBits + B.tbits + 3 * (Lt - 1) > 63 || B.tbits + 3 * lb > 63)
-		throw Error(SVB_ERANGE, "order key exceeds 64 bits: increase step (fewer levels per sub-octree)");
+	if (1 + B.tbits + 3 * lb > 63) throw Error(SVB_ERANGE, "order key of the base octree exceeds 63 bits: decrease step");
+	set_order_key_width(B, Lt);
 	B.grid.G = G; B.grid.cell = rootSide / (double)G;
 	B.grid.ox = B.grid1.ox; B.grid.oy = B.grid1.oy; B.grid.oz = B.grid1.oz;
 	upload(s, c->pool, B.dGrid, hgrid);

@@ -13,6 +13,8 @@
 //   KIND_LEAF  (level L-1): key = 8-bit voxel mask -> 256-entry direct table, staged in shared memory.
 //   KIND_K64   (level L-2): key = the 8 child masks = one exact 64-bit word (the 4^3 voxel block).
 //   KIND_INNER (above)    : key = 8 child uids, tagged by a 64-bit hash, verified exactly afterwards.
+#include <algorithm>
+
 #include "svb_dedup.cuh"
 
 namespace svb {
@@ -68,9 +70,26 @@ __device__ __forceinline__ uint64_t tag_of_key8(const uint32_t k[8]) {
 // ------------------------------------------------------------------ KIND_LEAF
 // 4 nodes per thread per trip, 128-bit loads (1 x uchar4 masks, 1 x uint4 t*, 2 x ulonglong2 codes): the kernel
 // only streams 13 B/node, so bytes in flight per thread decide how close it gets to the HBM roofline.
+// MODE 0: full 64-bit order key.  Wide mode (the order key of the leaf level needs more than 63 bits): MODE 1 takes
+// the minimum of the high part (tile_seq | t*) per voxel mask, MODE 2 -- a second pass over the same nodes -- the
+// minimum of the low part (path') among the nodes that attain it; (hi, lo) compares like the undivided key.
+__device__ __forceinline__ uint64_t order_key_hi(uint64_t code, uint32_t tstar, int l, int tbits, const uint32_t* __restrict__ tileSeq) {
+	uint64_t tile = (l >= 21) ? 0 : (code >> (3 * l));
+	return ((uint64_t)tileSeq[tile] << tbits) | (uint64_t)tstar;
+}
+__device__ __forceinline__ uint64_t order_key_lo(uint64_t code, int l) {
+	uint64_t pmask = (l >= 21) ? ~0ull : ((1ull << (3 * l)) - 1);
+	uint64_t path = code & pmask;
+	if (l > 0) path = (path & ~7ull) | (7ull - (path & 7ull));
+	return path;
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(DD_THREADS) k_leaf_min(DedupArgs a, unsigned long long* __restrict__ gmin, unsigned long long* __restrict__ voxels) {
 	__shared__ unsigned long long smin[256];
+	__shared__ unsigned long long shi[MODE == 2 ? 256 : 1];
 	smin[threadIdx.x] = MAX_ORDER;
+	if (MODE == 2) shi[threadIdx.x] = gmin[threadIdx.x];
 	__syncthreads();
 	unsigned vox = 0;
 	const uint64_t nq = a.N >> 2;   // full quads
@@ -78,35 +97,39 @@ __global__ void __launch_bounds__(DD_THREADS) k_leaf_min(DedupArgs a, unsigned l
 	const uchar4* __restrict__ m4 = reinterpret_cast<const uchar4*>(a.mask);
 	const uint4* __restrict__ t4 = reinterpret_cast<const uint4*>(a.tstar);
 	const ulonglong2* __restrict__ c2 = reinterpret_cast<const ulonglong2*>(a.code);
+	auto visit = [&](unsigned m, uint32_t ts, unsigned long long cd) {
+		if (!m) return;
+		unsigned long long O;
+		if (MODE == 0) O = order_key(cd, ts, a.l, a.tbits, a.tileSeq);
+		else if (MODE == 1) O = order_key_hi(cd, ts, a.l, a.tbits, a.tileSeq);
+		else {
+			if (order_key_hi(cd, ts, a.l, a.tbits, a.tileSeq) != shi[m]) return;
+			O = order_key_lo(cd, a.l);
+		}
+		if (MODE != 2) vox += __popc(m);
+		if (smin[m] > O) atomicMin(&smin[m], O);
+	};
 	for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
 		const uchar4 mm = m4[q];
 		const uint4 tt = t4[q];
 		const ulonglong2 ca = c2[2 * q], cb = c2[2 * q + 1];
-		const unsigned m[4] = {mm.x, mm.y, mm.z, mm.w};
-		const uint32_t ts[4] = {tt.x, tt.y, tt.z, tt.w};
-		const unsigned long long cd[4] = {ca.x, ca.y, cb.x, cb.y};
-#pragma unroll
-		for (int j = 0; j < 4; ++j) {
-			if (!m[j]) continue;
-			vox += __popc(m[j]);
-			unsigned long long O = order_key(cd[j], ts[j], a.l, a.tbits, a.tileSeq);
-			if (smin[m[j]] > O) atomicMin(&smin[m[j]], O);
-		}
+		visit(mm.x, tt.x, ca.x); visit(mm.y, tt.y, ca.y); visit(mm.z, tt.z, cb.x); visit(mm.w, tt.w, cb.y);
 	}
 	// tail (< 4 nodes)
-	for (uint64_t n = (nq << 2) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; n < a.N; n += stride) {
-		unsigned m = a.mask[n];
-		if (!m) continue;
-		vox += __popc(m);
-		unsigned long long O = order_key(a.code[n], a.tstar[n], a.l, a.tbits, a.tileSeq);
-		if (smin[m] > O) atomicMin(&smin[m], O);
-	}
+	for (uint64_t n = (nq << 2) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; n < a.N; n += stride) visit(a.mask[n], a.tstar[n], a.code[n]);
 	__syncthreads();
+	unsigned long long* g = gmin + (MODE == 2 ? 256 : 0);
 	unsigned long long v = smin[threadIdx.x];
-	if (v != MAX_ORDER && gmin[threadIdx.x] > v) atomicMin(&gmin[threadIdx.x], v);
+	if (v != MAX_ORDER && g[threadIdx.x] > v) atomicMin(&g[threadIdx.x], v);
+	if (MODE != 2) {
 #pragma unroll
-	for (int d = 16; d; d >>= 1) vox += __shfl_xor_sync(0xFFFFFFFFu, vox, d);
-	if ((threadIdx.x & 31) == 0 && vox) atomicAdd(voxels, (unsigned long long)vox);
+		for (int d = 16; d; d >>= 1) vox += __shfl_xor_sync(0xFFFFFFFFu, vox, d);
+		if ((threadIdx.x & 31) == 0 && vox) atomicAdd(voxels, (unsigned long long)vox);
+	}
+}
+// wide mode, between the two passes: a mask whose high part improved in this batch forgets its old low part
+__global__ void k_leaf_reset_lo(unsigned long long* __restrict__ gmin, const unsigned long long* __restrict__ hiBefore) {
+	if (gmin[threadIdx.x] != hiBefore[threadIdx.x]) gmin[256 + threadIdx.x] = MAX_ORDER;
 }
 
 // ------------------------------------------------------------------ KIND_K64 / KIND_INNER
@@ -357,7 +380,7 @@ void table_init(cudaStream_t s, Pool& pool, LevelTable& T, int kind) {
 	T.unique = 0;
 	if (kind == KIND_LEAF) {
 		T.cap = 256;
-		T.minO.reset(pool, 256);
+		T.minO.reset(pool, 512);   // [0,256): order key (or its high part), [256,512): low part (wide mode only)
 		T.minO.fill_ff();
 		return;
 	}
@@ -367,11 +390,22 @@ void table_init(cudaStream_t s, Pool& pool, LevelTable& T, int kind) {
 }
 
 void dedup_leaf(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, uint64_t* d_voxels) {
-	(void)pool;
 	if (a.N == 0) return;
 	unsigned nb = blocks_for(a.N, DD_THREADS * 16);
 	if (nb > 148 * 8) nb = 148 * 8;   // persistent-style grid: 8 CTAs of 256 threads per SM, grid-stride
-	k_leaf_min<<<nb, DD_THREADS, 0, s>>>(a, (unsigned long long*)T.minO.p, (unsigned long long*)d_voxels);
+	unsigned long long* g = (unsigned long long*)T.minO.p;
+	if (!T.wide) {
+		k_leaf_min<0><<<nb, DD_THREADS, 0, s>>>(a, g, (unsigned long long*)d_voxels);
+		SVB_KERNEL_CHECK();
+		return;
+	}
+	DevBuf<uint64_t> before(pool, 256);
+	SVB_CUDA(cudaMemcpyAsync(before.p, T.minO.p, 256 * 8, cudaMemcpyDeviceToDevice, s));
+	k_leaf_min<1><<<nb, DD_THREADS, 0, s>>>(a, g, (unsigned long long*)d_voxels);
+	SVB_KERNEL_CHECK();
+	k_leaf_reset_lo<<<1, 256, 0, s>>>(g, (const unsigned long long*)before.p);
+	SVB_KERNEL_CHECK();
+	k_leaf_min<2><<<nb, DD_THREADS, 0, s>>>(a, g, nullptr);
 	SVB_KERNEL_CHECK();
 }
 
@@ -527,21 +561,26 @@ __global__ void __launch_bounds__(DD_THREADS) k_import_l2g(uint64_t n, const uin
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) l2g[i] = (slotOfMine[i] == NULLREF) ? NULLREF : uid[slotOfMine[i]];
 }
-__global__ void k_min256(uint32_t world, const unsigned long long* __restrict__ all, uint64_t strideWords, unsigned long long* __restrict__ out) {
+__global__ void k_min256(uint32_t world, const unsigned long long* __restrict__ all, uint64_t strideWords, unsigned long long* __restrict__ out, int wide) {
 	unsigned i = threadIdx.x;
-	unsigned long long m = MAX_ORDER;
-	for (uint32_t r = 0; r < world; ++r) { unsigned long long v = all[r * strideWords + i]; if (v < m) m = v; }
+	unsigned long long m = MAX_ORDER, lo = MAX_ORDER;
+	for (uint32_t r = 0; r < world; ++r) {
+		unsigned long long v = all[r * strideWords + i];
+		unsigned long long w = wide ? all[r * strideWords + 256 + i] : 0;
+		if (v < m || (wide && v == m && w < lo)) { m = v; lo = w; }   // lexicographic (hi, lo)
+	}
 	out[i] = m;
+	if (wide) out[256 + i] = lo;
 }
 
 }  // namespace
 
 uint32_t merge_rec_bytes(int kind) { return kind == KIND_LEAF ? 8u : (kind == KIND_K64 ? (uint32_t)sizeof(RecK64) : (uint32_t)sizeof(RecInner)); }
-uint64_t merge_count(const LevelTable& T) { return T.kind == KIND_LEAF ? 256 : T.count; }
+uint64_t merge_count(const LevelTable& T) { return T.kind == KIND_LEAF ? (T.wide ? 512 : 256) : T.count; }
 
 void merge_export(cudaStream_t s, Pool& pool, LevelTable& T, const uint32_t* l2gChild, void* d_out) {
 	(void)pool;
-	if (T.kind == KIND_LEAF) { SVB_CUDA(cudaMemcpyAsync(d_out, T.minO.p, 256 * 8, cudaMemcpyDeviceToDevice, s)); return; }
+	if (T.kind == KIND_LEAF) { SVB_CUDA(cudaMemcpyAsync(d_out, T.minO.p, merge_count(T) * 8, cudaMemcpyDeviceToDevice, s)); return; }
 	if (T.count == 0) return;
 	unsigned nb = blocks_for(T.count, DD_THREADS);
 	if (T.kind == KIND_K64) k_export_k64<<<nb, DD_THREADS, 0, s>>>(T.count, T.dKey64.p, T.dMinO.p, (RecK64*)d_out);
@@ -555,7 +594,7 @@ void merge_export(cudaStream_t s, Pool& pool, LevelTable& T, const uint32_t* l2g
 void merge_import(cudaStream_t s, Pool& pool, LevelTable& T, const void* d_all, const uint64_t* counts, uint32_t world, uint64_t strideBytes,
                   uint32_t myRank, DevBuf<uint32_t>& l2g) {
 	if (T.kind == KIND_LEAF) {
-		k_min256<<<1, 256, 0, s>>>(world, (const unsigned long long*)d_all, strideBytes / 8, (unsigned long long*)T.minO.p);
+		k_min256<<<1, 256, 0, s>>>(world, (const unsigned long long*)d_all, strideBytes / 8, (unsigned long long*)T.minO.p, T.wide ? 1 : 0);
 		SVB_KERNEL_CHECK();
 		return;
 	}
@@ -653,32 +692,51 @@ void finalize_levels(cudaStream_t s, Pool& pool, std::vector<LevelTable>& tables
 	out.resize(L);
 	for (int g = L - 1; g >= 1; --g) {
 		LevelTable& T = tables[g];
-		uint64_t n = (T.kind == KIND_LEAF) ? 256 : T.count;
+		if (T.kind == KIND_LEAF) {
+			// <= 255 distinct voxel masks: rank them on the host by (order key) or, in wide mode, (high part, low part)
+			std::vector<uint64_t> hk(512);
+			SVB_CUDA(cudaMemcpyAsync(hk.data(), T.minO.p, 512 * 8, cudaMemcpyDeviceToHost, s));
+			SVB_CUDA(cudaStreamSynchronize(s));
+			std::vector<uint32_t> ord;
+			for (uint32_t m = 0; m < 256; ++m) if (hk[m] != MAX_ORDER) ord.push_back(m);
+			std::sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) {
+				if (hk[x] != hk[y]) return hk[x] < hk[y];
+				return T.wide ? hk[256 + x] < hk[256 + y] : false;
+			});
+			const uint64_t U = ord.size();
+			std::vector<uint32_t> hrank(256, 0);
+			for (uint32_t i = 0; i < U; ++i) hrank[ord[i]] = i;
+			T.rank.reset(pool, 256);
+			SVB_CUDA(cudaMemcpyAsync(T.rank.p, hrank.data(), 256 * 4, cudaMemcpyHostToDevice, s));
+			DevBuf<uint32_t> vals(pool, U ? U : 1);
+			if (U) SVB_CUDA(cudaMemcpyAsync(vals.p, ord.data(), U * 4, cudaMemcpyHostToDevice, s));
+			T.unique = U;
+			alloc_out(pool, out[g], U);
+			if (U) {
+				k_emit_leaf<<<blocks_for(U, 256), 256, 0, s>>>(U, vals.p, out[g].mask.p, out[g].child.p);
+				SVB_KERNEL_CHECK();
+			}
+			SVB_CUDA(cudaStreamSynchronize(s));   // ord / hrank are host temporaries
+			continue;
+		}
+		uint64_t n = T.count;
 		DevBuf<uint64_t> keys(pool, n);
 		DevBuf<uint32_t> vals(pool, n);
 		T.rank.reset(pool, n ? n : 1);
 		if (n) {
-			SVB_CUDA(cudaMemcpyAsync(keys.p, (T.kind == KIND_LEAF) ? T.minO.p : T.dMinO.p, n * 8, cudaMemcpyDeviceToDevice, s));
+			SVB_CUDA(cudaMemcpyAsync(keys.p, T.dMinO.p, n * 8, cudaMemcpyDeviceToDevice, s));
 			k_iota<<<blocks_for(n, 256), 256, 0, s>>>(n, vals.p);
 			SVB_KERNEL_CHECK();
-			radix_sort_pairs(s, pool, keys.p, vals.p, n, (T.kind == KIND_LEAF) ? 64 : obits[g]);
+			radix_sort_pairs(s, pool, keys.p, vals.p, n, obits[g]);
 			k_rank_scatter<<<blocks_for(n, 256), 256, 0, s>>>(n, vals.p, T.rank.p);
 			SVB_KERNEL_CHECK();
 		}
-		uint64_t U = n;
-		if (T.kind == KIND_LEAF) {
-			std::vector<uint64_t> hk(256);
-			SVB_CUDA(cudaMemcpyAsync(hk.data(), keys.p, 256 * 8, cudaMemcpyDeviceToHost, s));
-			SVB_CUDA(cudaStreamSynchronize(s));
-			U = 0;
-			while (U < 256 && hk[U] != MAX_ORDER) ++U;
-		}
+		const uint64_t U = n;
 		T.unique = U;
 		alloc_out(pool, out[g], U);
 		if (U) {
 			unsigned nb = blocks_for(U, 256);
-			if (T.kind == KIND_LEAF) k_emit_leaf<<<nb, 256, 0, s>>>(U, vals.p, out[g].mask.p, out[g].child.p);
-			else if (T.kind == KIND_K64) k_emit_k64<<<nb, 256, 0, s>>>(U, vals.p, T.dKey64.p, tables[g + 1].rank.p, out[g].mask.p, out[g].child.p);
+			if (T.kind == KIND_K64) k_emit_k64<<<nb, 256, 0, s>>>(U, vals.p, T.dKey64.p, tables[g + 1].rank.p, out[g].mask.p, out[g].child.p);
 			else k_emit_inner<<<nb, 256, 0, s>>>(U, vals.p, T.dKey8.p, tables[g + 1].rank.p, out[g].mask.p, out[g].child.p);
 			SVB_KERNEL_CHECK();
 		}

@@ -207,7 +207,9 @@ struct LevelTable {
 	DevBuf<uint64_t> dMinO;
 	DevBuf<uint64_t> dKey64;  // KIND_K64: 8 child masks
 	DevBuf<uint32_t> dKey8;   // KIND_INNER: 8 child uids (NULLREF = none)
-	// KIND_LEAF: 256-entry direct table lives in minO (cap = 256)
+	// KIND_LEAF: 256-entry direct table lives in minO (cap = 256); wide: the order key of this level does not fit 63
+	// bits and is kept as (high part = tile_seq | t*, low part = path') in minO[0,256) / minO[256,512)
+	bool wide = false;
 	// finalize
 	DevBuf<uint32_t> rank;    // uid -> final id (LEAF: mask value -> final id)
 	uint64_t unique = 0;

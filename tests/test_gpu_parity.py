@@ -186,6 +186,30 @@ def test_arbitrary_bbox_matches_oracle(pkg, orc, meshgen, mesh, kw, levels, step
     assert pkg.encoders.encode(t, "ssvdag") == o.encode("ssvdag")
 
 
+@pytest.mark.parametrize("mesh,kw,levels,step", [
+    ("city", dict(lots=8), 9, 2),
+    ("terrain", dict(n=64), 8, 0),
+    ("sphere_menger", dict(n_lat=32, n_lon=64, sponge_level=2), 9, 3),
+], ids=["city-s2", "terrain-s0", "spongeball-s3"])
+def test_wide_leaf_order_keys(pkg, orc, meshgen, mesh, kw, levels, step, monkeypatch):
+    """Leaf-level order keys kept as two words (what a 64K^3 build needs: tile + triangle + path bits > 63):
+    forced on small scenes with SVB_WIDE_LEAF=1, the result must not change."""
+    tris = meshgen.make_mesh(mesh, **kw)
+    o = orc.OracleOctree(tris)
+    o.build(levels, step)
+    monkeypatch.setenv("SVB_WIDE_LEAF", "1")
+    t = pkg.GeomOctree(tris)
+    t.set_batch_budget(24 << 20)          # several batches: the (hi, lo) minima must merge across them
+    st = t.build(levels, step)
+    for k in ("nTotalVoxels", "nNodesSVO", "nNodesDAG"):
+        assert st[k] == o.stat(k), k
+    _assert_levels_equal(t.levels_host(), _oracle_levels(o), "DAG (wide leaf keys)")
+    if step > 0:
+        octs, _ = _simulate_ranks(pkg, tris, levels, step, 3)
+        for r, oc in enumerate(octs):
+            _assert_levels_equal(oc.levels_host(), _oracle_levels(o), f"sharded DAG rank {r} (wide leaf keys)")
+
+
 def _simulate_ranks(pkg, tris, levels, step, world):
     """Run the multi-GPU protocol with `world` contexts on ONE device, doing the all-gathers by hand
     (torch.cat of the per-rank export buffers).  Exercises svb_shard_* end to end without NCCL."""
