@@ -41,6 +41,9 @@ WORKLOADS = {
                                        note="same generator at n=257, 1024^3 (levels 10, step 2): 4 voxels per grid cell as in the full workload")),
     "spongeball_1k": dict(mesh="sphere_menger", kw=dict(), levels=10, step=1, grid="1024^3",
                           cpu_sample=dict(mesh="sphere_menger", kw=dict(), levels=10, step=1, note="the full workload")),
+    "composite_64k": dict(mesh="composite", kw=dict(n_terrain=1024, lots=256), levels=16, step=7, grid="65536^3",
+                          cpu_sample=dict(mesh="composite", kw=dict(n_terrain=129, lots=32), levels=11, step=2,
+                                          note="same generator at n_terrain=129, lots=32, 2048^3 (levels 11, step 2)")),
     "city_small": dict(mesh="city", kw=dict(lots=32), levels=11, step=2, grid="2048^3",
                        cpu_sample=dict(mesh="city", kw=dict(lots=16), levels=10, step=2, note="lots=16 at 1024^3")),
 }

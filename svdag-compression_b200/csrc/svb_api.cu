@@ -148,7 +148,8 @@ void upload(cudaStream_t s, Pool& pool, DevBuf<T>& d, const std::vector<T>& h) {
 struct svb_build_state {
 	uint32_t L = 0, step = 0, s1 = 0;   // s1 = step + 1 = global level of the sub-octree roots (0: no sub-octrees)
 	uint32_t rank = 0, world = 1;
-	int tbits = 1, tileBits = 1;
+	int tbits = 1, tileBits = 1;   // tbits: bits of a triangle rank inside the root tile (all triangles)
+	int tbLocal = 1;               // bits of a triangle rank inside a sub-octree (max candidates per tile)
 	std::vector<LevelTable> tables;      // per global level
 	std::vector<int> obits;
 	DevBuf<uint64_t> dVoxels, dExact;
@@ -187,26 +188,27 @@ typedef svb_build_state BuildState;
 // deepest level (3*(Lt-1) path bits) is the voxel-mask level, whose 256-entry table can hold a two-word key: if only
 // that level overflows, it runs in wide mode (two passes, svb_dedup.cu::dedup_leaf); e.g. 64K^3 with step 7 and 12 M
 // triangles needs 21 + 24 + 3*7 = 66 bits at the leaves but 63 above.
-void set_order_key_width(BuildState& B, int Lt) {
-	const int leafBits = B.tileBits + B.tbits + 3 * (Lt - 1);
-	const int innerBits = B.tileBits + B.tbits + 3 * std::max(Lt - 2, 0);
+void set_order_key_width(BuildState& B, int Lt, int tb) {
+	const int leafBits = B.tileBits + tb + 3 * (Lt - 1);
+	const int innerBits = B.tileBits + tb + 3 * std::max(Lt - 2, 0);
 	const char* force = getenv("SVB_WIDE_LEAF");
 	bool wide = leafBits > 63 || (force && force[0] == '1');
-	if ((wide ? innerBits : leafBits) > 63 || B.tileBits + B.tbits > 63)
-		throw Error(SVB_ERANGE, "order key exceeds 63 bits (" + std::to_string(B.tileBits) + " tile + " + std::to_string(B.tbits) + " triangle + " +
+	if ((wide ? innerBits : leafBits) > 63 || B.tileBits + tb > 63)
+		throw Error(SVB_ERANGE, "order key exceeds 63 bits (" + std::to_string(B.tileBits) + " tile + " + std::to_string(tb) + " triangle-rank + " +
 		                            std::to_string(3 * std::max(Lt - 2, 0)) + " path bits): increase step (fewer levels per sub-octree)");
 	B.tables[B.L - 1].wide = wide;
 }
 
 // bottom-up reduction of one batch's levels [lo_l, Lt-1] into the tables
-void dedup_batch(svb_ctx* c, BuildState& B, std::vector<BatchLevel>& lv, int Lt, uint32_t gbase, const uint32_t* d_tileSeq, int lo_l) {
+void dedup_batch(svb_ctx* c, BuildState& B, std::vector<BatchLevel>& lv, int Lt, uint32_t gbase, const uint32_t* d_tileSeq, const uint32_t* d_tileStart, int lo_l) {
+	const int tb = gbase == 0 ? B.tbits : B.tbLocal;
 	for (int l = Lt - 1; l >= lo_l; --l) {
 		uint32_t g = gbase + l;
 		BatchLevel& X = lv[l];
 		DedupArgs a;
 		a.N = X.n; a.code = X.code.p; a.tstar = X.tstar.p; a.mask = X.mask.p; a.childBase = X.childBase.p;
-		a.l = l; a.tbits = B.tbits; a.tileSeq = d_tileSeq;
-		int ob = B.tileBits + B.tbits + 3 * l;
+		a.l = l; a.tbits = tb; a.tileSeq = d_tileSeq; a.tileStart = d_tileStart;
+		int ob = B.tileBits + tb + 3 * l;
 		if (ob > B.obits[g]) B.obits[g] = ob;
 		LevelTable& T = B.tables[g];
 		if (T.kind == KIND_LEAF) {
@@ -247,16 +249,17 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 	upload(s, c->pool, dLocal, hlocal);
 
 	std::vector<BatchLevel> lv;
+	DevBuf<uint32_t> dTileStart;   // per tile of the batch: first root-pair index (needed again by the order keys)
 	uint64_t pairs = 0;
 	{
 		StageTimer tm(s);
 		ProfScope ps(c, "voxelize", gbase, nt);
-		DevBuf<uint32_t> ptri, pnode;
+		DevBuf<uint32_t> ptri, pnode, rootTri;
 		uint64_t P = 0;
-		make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, dLocal.p, ptri, pnode, P);
+		make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, dLocal.p, nt, ptri, pnode, rootTri, dTileStart, P);
 		bool direct = true;
 		for (uint32_t i = 0; i < nt && direct; ++i) direct = centre_chain_exact(hg[i], Lt);
-		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, P, budget, nodeCap, lv, pairs, B.dExact.p, direct);
+		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, rootTri.p, dTileStart.p, P, budget, nodeCap, lv, pairs, B.dExact.p, direct);
 		ps.done(pairs, 36.0 * (double)c->T + 9.0 * (double)lv[Lt - 1].n);
 		B.msVox += tm.stop();
 	}
@@ -271,7 +274,7 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 	}
 	StageTimer tm(s);
 	if (gbase == 0) {
-		dedup_batch(c, B, lv, Lt, 0, dSeq.p, 1);
+		dedup_batch(c, B, lv, Lt, 0, dSeq.p, dTileStart.p, 1);
 		DedupArgs r;
 		r.N = 1; r.code = lv[0].code.p; r.tstar = lv[0].tstar.p; r.mask = lv[0].mask.p; r.childBase = lv[0].childBase.p;
 		bool leafBelow = (kind_of(1, B.L) == KIND_LEAF);
@@ -280,7 +283,7 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 		B.rootChildMode = r.childMode;
 		root_key(s, r, B.rootKey.p);
 	} else {
-		dedup_batch(c, B, lv, Lt, gbase, dSeq.p, 0);
+		dedup_batch(c, B, lv, Lt, gbase, dSeq.p, dTileStart.p, 0);
 		// remember what each sub-octree root was reduced to (uid, or the voxel mask for 1-level sub-octrees)
 		if (B.tables[gbase].kind == KIND_LEAF) k_scatter_u8<<<blocks_for(nt, 256), 256, 0, s>>>(nt, dSeq.p, lv[0].mask.p, B.tileRootRef.p);
 		else k_scatter_u32<<<blocks_for(nt, 256), 256, 0, s>>>(nt, dSeq.p, lv[0].ref.p, B.tileRootRef.p);
@@ -374,7 +377,7 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 	if (step == 0) {
 		B.s1 = 0;
 		B.tileBits = 1;
-		set_order_key_width(B, (int)L);
+		set_order_key_width(B, (int)L, B.tbits);
 		try {
 			run_tile_batch(c, B, rootTile, sel0, 0, 1, B.grid1, B.dGrid1.p, (int)L, 0, budget, 0, nullptr);
 		} catch (const BatchTooBig&) {
@@ -449,10 +452,13 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 	B.tileBits = bits_for(nTiles ? nTiles - 1 : 0);
 	const int Lt = (int)(L - s1);
 	if (1 + B.tbits + 3 * lb > 63) throw Error(SVB_ERANGE, "order key of the base octree exceeds 63 bits: decrease step");
-	set_order_key_width(B, Lt);
 	B.grid.G = G; B.grid.cell = rootSide / (double)G;
 	B.grid.ox = B.grid1.ox; B.grid.oy = B.grid1.oy; B.grid.oz = B.grid1.oz;
 	upload(s, c->pool, B.dGrid, hgrid);
+	// triangle ranks inside a sub-octree need as many bits as the busiest tile has candidate triangles (identical on
+	// every rank: all ranks hold all triangles and the same tile grid)
+	B.tbLocal = bits_for(std::max<uint32_t>(1, max_candidates_per_tile(s, c->pool, c->d_tris, c->T, B.grid, B.dGrid.p, nTiles)) - 1);
+	set_order_key_width(B, Lt, B.tbLocal);
 	B.tileRootRef.reset(c->pool, nTiles ? nTiles : 1);
 	B.tileRootRef.fill_ff();
 	// ---- this rank's share: sub-octrees dealt round-robin in the reference's order (SVB_SHARD=octant: by
@@ -535,7 +541,7 @@ void build_finish(svb_ctx* c, const uint64_t* totals) {
 			BatchLevel& X = B.base[l];
 			DedupArgs a;
 			a.N = X.n; a.code = X.code.p; a.tstar = X.tstar.p; a.mask = X.mask.p; a.childBase = X.childBase.p;
-			a.l = l; a.tbits = B.tbits; a.tileSeq = dZero.p;
+			a.l = l; a.tbits = B.tbits; a.tileSeq = dZero.p; a.tileStart = dZero.p;
 			a.childMode = belowMode; a.childRefs = below;
 			if (l == 0) { B.rootChildMode = belowMode; root_key(s, a, B.rootKey.p); break; }
 			int ob = 1 + B.tbits + 3 * l;

@@ -23,12 +23,16 @@ namespace {
 
 constexpr int DD_THREADS = 256;
 
-__device__ __forceinline__ uint64_t order_key(uint64_t code, uint32_t tstar, int l, int tbits, const uint32_t* __restrict__ tileSeq) {
+// tstar is the smallest root-pair index q that touches the node (svb_voxelize.cu::make_root_pairs); q - tileStart[tile]
+// = rank of the first-touch triangle among the tile's candidate triangles, monotone in the triangle id -- all the order
+// needs, in far fewer bits than the id itself (a tile sees thousands of triangles, a scene tens of millions).
+__device__ __forceinline__ uint64_t order_key(uint64_t code, uint32_t tstar, const DedupArgs& a) {
+	const int l = a.l;
 	uint64_t pmask = (l >= 21) ? ~0ull : ((1ull << (3 * l)) - 1);
 	uint64_t path = code & pmask;
 	uint64_t tile = (l >= 21) ? 0 : (code >> (3 * l));
 	if (l > 0) path = (path & ~7ull) | (7ull - (path & 7ull));   // children are created 7 -> 0 (geom_octree.cpp:234)
-	return ((uint64_t)tileSeq[tile] << (tbits + 3 * l)) | ((uint64_t)tstar << (3 * l)) | path;
+	return ((uint64_t)a.tileSeq[tile] << (a.tbits + 3 * l)) | ((uint64_t)(tstar - a.tileStart[tile]) << (3 * l)) | path;
 }
 
 template <int CHMODE>
@@ -73,9 +77,9 @@ __device__ __forceinline__ uint64_t tag_of_key8(const uint32_t k[8]) {
 // MODE 0: full 64-bit order key.  Wide mode (the order key of the leaf level needs more than 63 bits): MODE 1 takes
 // the minimum of the high part (tile_seq | t*) per voxel mask, MODE 2 -- a second pass over the same nodes -- the
 // minimum of the low part (path') among the nodes that attain it; (hi, lo) compares like the undivided key.
-__device__ __forceinline__ uint64_t order_key_hi(uint64_t code, uint32_t tstar, int l, int tbits, const uint32_t* __restrict__ tileSeq) {
-	uint64_t tile = (l >= 21) ? 0 : (code >> (3 * l));
-	return ((uint64_t)tileSeq[tile] << tbits) | (uint64_t)tstar;
+__device__ __forceinline__ uint64_t order_key_hi(uint64_t code, uint32_t tstar, const DedupArgs& a) {
+	uint64_t tile = (a.l >= 21) ? 0 : (code >> (3 * a.l));
+	return ((uint64_t)a.tileSeq[tile] << a.tbits) | (uint64_t)(tstar - a.tileStart[tile]);
 }
 __device__ __forceinline__ uint64_t order_key_lo(uint64_t code, int l) {
 	uint64_t pmask = (l >= 21) ? ~0ull : ((1ull << (3 * l)) - 1);
@@ -100,10 +104,10 @@ __global__ void __launch_bounds__(DD_THREADS) k_leaf_min(DedupArgs a, unsigned l
 	auto visit = [&](unsigned m, uint32_t ts, unsigned long long cd) {
 		if (!m) return;
 		unsigned long long O;
-		if (MODE == 0) O = order_key(cd, ts, a.l, a.tbits, a.tileSeq);
-		else if (MODE == 1) O = order_key_hi(cd, ts, a.l, a.tbits, a.tileSeq);
+		if (MODE == 0) O = order_key(cd, ts, a);
+		else if (MODE == 1) O = order_key_hi(cd, ts, a);
 		else {
-			if (order_key_hi(cd, ts, a.l, a.tbits, a.tileSeq) != shi[m]) return;
+			if (order_key_hi(cd, ts, a) != shi[m]) return;
 			O = order_key_lo(cd, a.l);
 		}
 		if (MODE != 2) vox += __popc(m);
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(DD_THREADS) k_insert(DedupArgs a, TableDev t) 
 	uint64_t tag = (CHMODE == CH_UID_U32) ? tag_of_key8(k8) : k64;
 	uint64_t slot;
 	if (!table_find_or_claim(t, tag, slot)) { a.ref[n] = NULLREF; return; }
-	unsigned long long O = order_key(a.code[n], a.tstar[n], a.l, a.tbits, a.tileSeq);
+	unsigned long long O = order_key(a.code[n], a.tstar[n], a);
 	if (t.minO[slot] > O) atomicMin(&t.minO[slot], O);
 	a.ref[n] = (uint32_t)slot;
 }
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(DD_THREADS) k_winner(DedupArgs a, TableDev t, 
 	if (n >= a.N) return;
 	uint32_t slot = a.ref[n];
 	if (slot == NULLREF) return;
-	unsigned long long O = order_key(a.code[n], a.tstar[n], a.l, a.tbits, a.tileSeq);
+	unsigned long long O = order_key(a.code[n], a.tstar[n], a);
 	if (t.minO[slot] != O) return;
 	uint32_t k8[8];
 	uint64_t k64;

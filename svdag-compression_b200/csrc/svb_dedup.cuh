@@ -15,8 +15,9 @@ struct DedupArgs {
 	int childMode = CH_UID_U32;         // how to read the level below
 	const void* childRefs = nullptr;    // u8 masks | u32 uids | u32 masks
 	int l = 0;                          // octal digits of `path`
-	int tbits = 0;                      // bits of a triangle id
+	int tbits = 0;                      // bits of a tile-local triangle rank
 	const uint32_t* tileSeq = nullptr;  // device: tile_local -> global tile_seq (sub-octree sequence number)
+	const uint32_t* tileStart = nullptr;// device: tile_local -> first root-pair index of the tile (tstar - tileStart = triangle rank)
 	uint32_t* ref = nullptr;            // out: uid of each node's unique representative (NULLREF = empty node)
 };
 

@@ -78,14 +78,14 @@ __global__ void __launch_bounds__(VX_THREADS) k_candidates(const float* __restri
 // (geom_octree.cpp:222-230), so it carries exactly the reference's roundings for any bbox.
 __global__ void __launch_bounds__(VX_THREADS) k_classify(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
                                                           const uint64_t* __restrict__ code, int l, const TileGeom* __restrict__ tiles,
-                                                          const float* __restrict__ tris, uint8_t* __restrict__ hit, uint8_t* __restrict__ mask, int last) {
+                                                          const float* __restrict__ tris, const uint32_t* __restrict__ rootTri, uint8_t* __restrict__ hit, uint8_t* __restrict__ mask, int last) {
 	uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	uint64_t p = gid >> 3;
 	int c = (int)(gid & 7);
 	bool ok = false;
 	uint32_t n = 0;
 	if (p < P) {
-		uint32_t t = ptri[p];
+		uint32_t t = rootTri[ptri[p]];
 		n = pnode[p];
 		uint64_t cd = code[n];
 		uint32_t tile = (uint32_t)(cd >> (3 * l));
@@ -122,11 +122,11 @@ __global__ void __launch_bounds__(VX_THREADS) k_classify(uint64_t P, const uint3
 template <int MINB, bool DIRECT>
 __global__ void __launch_bounds__(VX_THREADS, MINB) k_classify_filtered(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
                                                                    uint16_t* __restrict__ pflags, const uint64_t* __restrict__ code, int l, double kscale, int last,
-                                                                   const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
+                                                                   const TileGeom* __restrict__ tiles, const float* __restrict__ tris, const uint32_t* __restrict__ rootTri,
                                                                    uint8_t* __restrict__ hit, uint8_t* __restrict__ mask, unsigned long long* __restrict__ nExact) {
 	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= P) return;
-	const uint32_t t = ptri[p], n = pnode[p];
+	const uint32_t t = rootTri[ptri[p]], n = pnode[p];   // pairs carry the index of their root pair (see make_root_pairs)
 	const unsigned fl0 = pflags[p];
 	unsigned fl = fl0, nUnsure;
 	const uint64_t cd = code[n];
@@ -212,11 +212,11 @@ __global__ void __launch_bounds__(VX_THREADS) k_children(uint64_t N, const uint6
 template <bool DIRECT>
 __global__ void __launch_bounds__(VX_THREADS, 8) k_classify_fast(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
                                                                  uint16_t* __restrict__ pflags, const uint64_t* __restrict__ code, int l, double kscale, int last,
-                                                                 const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
+                                                                 const TileGeom* __restrict__ tiles, const float* __restrict__ tris, const uint32_t* __restrict__ rootTri,
                                                                  uint8_t* __restrict__ hit, uint8_t* __restrict__ mask) {
 	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= P) return;
-	const uint32_t t = ptri[p], n = pnode[p];
+	const uint32_t t = rootTri[ptri[p]], n = pnode[p];
 	const unsigned fl0 = pflags[p];
 	unsigned fl = fl0;
 	const uint64_t cd = code[n];
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(VX_THREADS, 6) k_flat_leaves(uint64_t P, const
                                                                const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit,
                                                                const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase,
                                                                int lc, double kscaleParent, const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
-                                                               uint8_t* __restrict__ cmask, uint32_t* __restrict__ ctstar) {
+                                                               const uint32_t* __restrict__ rootTri, uint8_t* __restrict__ cmask, uint32_t* __restrict__ ctstar) {
 	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= P) return;
 	unsigned m = hit[p];
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(VX_THREADS, 6) k_flat_leaves(uint64_t P, const
 	const unsigned nm = mask[n];
 	const uint32_t base = childBase[n];
 	const double* tg = reinterpret_cast<const double*>(tiles + (uint32_t)(cd >> (3 * (lc - 1))));
-	const float* tp = tris + 9ull * t;
+	const float* tp = tris + 9ull * rootTri[t];   // t itself (the root pair index) is what orders first touches
 	unsigned lohi[3][2];
 	flat_leaf_masks<DIRECT>(cd, lc - 1, tg, kscaleParent, tp, fl, lohi);
 	// the children of one node are consecutive, so their voxel masks are consecutive bytes: OR them word by word
@@ -356,9 +356,52 @@ __global__ void __launch_bounds__(VX_THREADS) k_tile_weights(uint64_t N, const u
 	if (m) atomicAdd(&w[(uint32_t)(code[n] >> (3 * l))], (uint32_t)__popc(m));
 }
 
-__global__ void k_init_roots(uint32_t ntiles, uint64_t* code, uint32_t* tstar) {
+__global__ void k_init_roots(uint32_t ntiles, uint64_t* code, uint32_t* tstar, const uint32_t* __restrict__ tileStart) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < ntiles) { code[i] = i; tstar[i] = 0; }
+	if (i < ntiles) { code[i] = i; tstar[i] = tileStart[i]; }
+}
+
+// root pairs sorted by (tile, triangle): key = tile_local << 32 | triangle
+__global__ void __launch_bounds__(VX_THREADS) k_root_keys(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode, uint64_t* __restrict__ keys) {
+	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p < P) keys[p] = ((uint64_t)pnode[p] << 32) | ptri[p];
+}
+__global__ void __launch_bounds__(VX_THREADS) k_root_split(uint64_t P, const uint64_t* __restrict__ keys, uint32_t* __restrict__ rootTri, uint32_t* __restrict__ ptri,
+                                                            uint32_t* __restrict__ pnode, uint32_t* __restrict__ tileStart) {
+	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= P) return;
+	const uint64_t k = keys[p];
+	const uint32_t tile = (uint32_t)(k >> 32);
+	rootTri[p] = (uint32_t)k;
+	ptri[p] = (uint32_t)p;       // from here on a pair is identified by the index of its root pair
+	pnode[p] = tile;
+	if (p == 0 || (uint32_t)(keys[p - 1] >> 32) != tile) tileStart[tile] = (uint32_t)p;
+}
+// candidate (triangle, tile) pairs per tile over the WHOLE tile grid: bounds the tile-local triangle rank
+__global__ void __launch_bounds__(VX_THREADS) k_tile_hist(const float* __restrict__ tris, uint64_t T, GridDesc g, const int* __restrict__ gridTile, uint32_t* __restrict__ hist) {
+	uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= T) return;
+	const float* p = tris + 9 * t;
+	double mnx = fmin(fmin((double)p[0], (double)p[3]), (double)p[6]), mxx = fmax(fmax((double)p[0], (double)p[3]), (double)p[6]);
+	double mny = fmin(fmin((double)p[1], (double)p[4]), (double)p[7]), mxy = fmax(fmax((double)p[1], (double)p[4]), (double)p[7]);
+	double mnz = fmin(fmin((double)p[2], (double)p[5]), (double)p[8]), mxz = fmax(fmax((double)p[2], (double)p[5]), (double)p[8]);
+	int ax, bx, ay, by, az, bz;
+	tile_range(mnx, mxx, g.ox, g, ax, bx);
+	tile_range(mny, mxy, g.oy, g, ay, by);
+	tile_range(mnz, mxz, g.oz, g, az, bz);
+	for (int x = ax; x <= bx; ++x)
+		for (int y = ay; y <= by; ++y)
+			for (int z = az; z <= bz; ++z) {
+				int s = gridTile[((size_t)x * g.G + y) * g.G + z];
+				if (s >= 0) atomicAdd(&hist[s], 1u);
+			}
+}
+__global__ void __launch_bounds__(VX_THREADS) k_max_u32(uint64_t n, const uint32_t* __restrict__ v, uint32_t* __restrict__ out) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t x = i < n ? v[i] : 0;
+#pragma unroll
+	for (int d = 16; d; d >>= 1) x = max(x, __shfl_xor_sync(0xFFFFFFFFu, x, d));
+	if ((threadIdx.x & 31) == 0 && x) atomicMax(out, x);
 }
 
 // SVB_CLASSIFY=exact selects the unfiltered 8-lanes-per-pair kernel (verification of the filter)
@@ -400,8 +443,7 @@ bool centre_chain_exact(const TileGeom& g, int Lt) {
 	return ldexp(span, -ge) <= 9007199254740992.0;
 }
 
-void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T, const TileGridHost& grid,
-                     const int* d_gridTile, const int* d_localOf, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t& P) {
+static GridDesc grid_desc(const TileGridHost& grid) {
 	GridDesc g;
 	g.ox = grid.ox; g.oy = grid.oy; g.oz = grid.oz;
 	g.inv_cell = 1.0 / grid.cell;
@@ -412,6 +454,28 @@ void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T
 	                               std::max(fabs(grid.oz), fabs(grid.oz + ext)));
 	g.margin = grid.cell * 1e-6 + maxAbs * 4.8e-7;   // 4.8e-7 = 4 * 2^-23
 	g.G = grid.G;
+	return g;
+}
+
+uint32_t max_candidates_per_tile(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T, const TileGridHost& grid, const int* d_gridTile, uint64_t nTiles) {
+	if (!T || !nTiles) return 0;
+	DevBuf<uint32_t> hist(pool, nTiles), mx(pool, 1);
+	hist.zero();
+	mx.zero();
+	k_tile_hist<<<blocks_for(T, VX_THREADS), VX_THREADS, 0, s>>>(d_tris, T, grid_desc(grid), d_gridTile, hist.p);
+	SVB_KERNEL_CHECK();
+	k_max_u32<<<blocks_for(nTiles, VX_THREADS), VX_THREADS, 0, s>>>(nTiles, hist.p, mx.p);
+	SVB_KERNEL_CHECK();
+	uint32_t h = 0;
+	SVB_CUDA(cudaMemcpyAsync(&h, mx.p, 4, cudaMemcpyDeviceToHost, s));
+	SVB_CUDA(cudaStreamSynchronize(s));
+	return h;
+}
+
+void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T, const TileGridHost& grid,
+                     const int* d_gridTile, const int* d_localOf, uint32_t ntiles, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode,
+                     DevBuf<uint32_t>& rootTri, DevBuf<uint32_t>& tileStart, uint64_t& P) {
+	GridDesc g = grid_desc(grid);
 	DevBuf<uint32_t> cnt(pool, T);
 	DevBuf<uint64_t> tot(pool, 1);
 	unsigned nb = blocks_for(T, VX_THREADS);
@@ -424,18 +488,36 @@ void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T
 	pnode.reset(pool, P);
 	k_candidates<true><<<nb, VX_THREADS, 0, s>>>(d_tris, T, g, d_gridTile, d_localOf, cnt.p, ptri.p, pnode.p);
 	SVB_KERNEL_CHECK();
+	// Sort the root pairs by (tile, triangle).  A pair and all its descendants are then identified by the index q of
+	// their root pair: triangle = rootTri[q], and q - tileStart[tile] is the rank of the triangle among the tile's
+	// candidates -- the compact, order-preserving stand-in for the triangle id inside order keys (svb_dedup.cu).
+	rootTri.reset(pool, P ? P : 1);
+	tileStart.reset(pool, ntiles ? ntiles : 1);
+	tileStart.zero();
+	if (P) {
+		DevBuf<uint64_t> keys(pool, P);
+		DevBuf<uint32_t> dummy(pool, P);
+		unsigned pb = blocks_for(P, VX_THREADS);
+		k_root_keys<<<pb, VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, keys.p);
+		SVB_KERNEL_CHECK();
+		int tileBits = 1;
+		while ((ntiles - 1) >> tileBits) ++tileBits;
+		if (ntiles > 1) radix_sort_pairs(s, pool, keys.p, dummy.p, P, 32 + tileBits);   // emitted per triangle: already sorted when there is one tile
+		k_root_split<<<pb, VX_THREADS, 0, s>>>(P, keys.p, rootTri.p, ptri.p, pnode.p, tileStart.p);
+		SVB_KERNEL_CHECK();
+	}
 }
 
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
-                    DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t P, uint64_t budget_bytes, uint64_t nodeCap,
-                    std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre) {
+                    DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, const uint32_t* rootTri, const uint32_t* tileStart, uint64_t P,
+                    uint64_t budget_bytes, uint64_t nodeCap, std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre) {
 	if (const char* e = getenv("SVB_CENTRE")) directCentre = directCentre && e[0] != 'c';   // SVB_CENTRE=chain: always replay the chain
 	lv.clear();
 	lv.resize(Lt);
 	lv[0].n = ntiles;
 	lv[0].code.reset(pool, ntiles);
 	lv[0].tstar.reset(pool, ntiles);
-	k_init_roots<<<blocks_for(ntiles, 256), 256, 0, s>>>(ntiles, lv[0].code.p, lv[0].tstar.p);
+	k_init_roots<<<blocks_for(ntiles, 256), 256, 0, s>>>(ntiles, lv[0].code.p, lv[0].tstar.p, tileStart);
 	SVB_KERNEL_CHECK();
 	DevBuf<uint64_t> tot(pool, 4);   // device totals of the four scans of a level, read back together
 	pairsTotal = 0;
@@ -458,17 +540,17 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		const double kscale = ldexp(1.0, -(l + 2));
 		if (F) {
 			unsigned nb = blocks_for(F, VX_THREADS);
-			if (directCentre) k_classify_fast<true><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, hit.p, L.mask.p);
-			else k_classify_fast<false><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, hit.p, L.mask.p);
+			if (directCentre) k_classify_fast<true><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, hit.p, L.mask.p);
+			else k_classify_fast<false><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, hit.p, L.mask.p);
 			SVB_KERNEL_CHECK();
 		}
 		if (S) {
 			const uint32_t* st = ptri.p + Fa; const uint32_t* sn = pnode.p + Fa; uint16_t* sf = pflags.p + Fa; uint8_t* sh = hit.p + (last ? 0 : Fa);
 			if (exactOnly)
-				k_classify<<<blocks_for(S * 8, VX_THREADS), VX_THREADS, 0, s>>>(S, st, sn, L.code.p, l, d_tiles, d_tris, sh, L.mask.p, last);
+				k_classify<<<blocks_for(S * 8, VX_THREADS), VX_THREADS, 0, s>>>(S, st, sn, L.code.p, l, d_tiles, d_tris, rootTri, sh, L.mask.p, last);
 			else {
 				unsigned nb = blocks_for(S, VX_THREADS);
-#define SVB_LAUNCH_CF(OCC, DIR) k_classify_filtered<OCC, DIR><<<nb, VX_THREADS, 0, s>>>(S, st, sn, sf, L.code.p, l, kscale, last, d_tiles, d_tris, sh, L.mask.p, (unsigned long long*)d_nExact)
+#define SVB_LAUNCH_CF(OCC, DIR) k_classify_filtered<OCC, DIR><<<nb, VX_THREADS, 0, s>>>(S, st, sn, sf, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, sh, L.mask.p, (unsigned long long*)d_nExact)
 				if (directCentre) {
 					if (occ >= 6) SVB_LAUNCH_CF(6, true); else if (occ == 5) SVB_LAUNCH_CF(5, true); else if (occ == 4) SVB_LAUNCH_CF(4, true);
 					else if (occ == 3) SVB_LAUNCH_CF(3, true); else SVB_LAUNCH_CF(1, true);
@@ -531,8 +613,8 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		if (fuseFlat) {
 			C.mask.reset(pool, (Nn + 3 + 16) & ~3ull);
 			C.mask.zero();
-			if (directCentre) k_flat_leaves<true><<<blocks_for(F, VX_THREADS), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, L.code.p, L.mask.p, L.childBase.p, l + 1, kscale, d_tiles, d_tris, C.mask.p, C.tstar.p);
-			else k_flat_leaves<false><<<blocks_for(F, VX_THREADS), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, L.code.p, L.mask.p, L.childBase.p, l + 1, kscale, d_tiles, d_tris, C.mask.p, C.tstar.p);
+			if (directCentre) k_flat_leaves<true><<<blocks_for(F, VX_THREADS), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, L.code.p, L.mask.p, L.childBase.p, l + 1, kscale, d_tiles, d_tris, rootTri, C.mask.p, C.tstar.p);
+			else k_flat_leaves<false><<<blocks_for(F, VX_THREADS), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, L.code.p, L.mask.p, L.childBase.p, l + 1, kscale, d_tiles, d_tris, rootTri, C.mask.p, C.tstar.p);
 			SVB_KERNEL_CHECK();
 			pairsTotal += cF;   // decided here instead of as pairs of the last level
 		} else if (F) {

@@ -19,15 +19,21 @@ struct TileGridHost {    // regular grid of tile cubes over the root cube (G = 2
 	int G = 1;
 };
 
-// (triangle, tile) candidate pairs for the tiles of one batch; pairs sorted by triangle id.
+// (triangle, tile) candidate pairs for the tiles of one batch, sorted by (tile, triangle).  On return pnode[q] = tile
+// (index inside the batch), rootTri[q] = triangle, ptri[q] = q, tileStart[tile] = first q of the tile.
 // d_gridTile: grid cell -> global tile_seq (-1 none); d_localOf: global tile_seq -> index in the batch (-1 not in it).
 void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T, const TileGridHost& grid,
-                     const int* d_gridTile, const int* d_localOf, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t& P);
+                     const int* d_gridTile, const int* d_localOf, uint32_t ntiles, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode,
+                     DevBuf<uint32_t>& rootTri, DevBuf<uint32_t>& tileStart, uint64_t& P);
 
-// Level-synchronous SVO build of `ntiles` sub-octrees of Lt levels each.  Consumes the root pairs.
+// largest number of candidate triangles any tile of the grid has (bounds the tile-local triangle rank)
+uint32_t max_candidates_per_tile(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T, const TileGridHost& grid, const int* d_gridTile, uint64_t nTiles);
+
+// Level-synchronous SVO build of `ntiles` sub-octrees of Lt levels each.  Consumes the root pairs.  First-touch
+// "triangles" (BatchLevel::tstar) are root pair indices q: monotone in the triangle id within a tile.
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
-                    DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, uint64_t P, uint64_t budget_bytes, uint64_t nodeCap,
-                    std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre);
+                    DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, const uint32_t* rootTri, const uint32_t* tileStart, uint64_t P,
+                    uint64_t budget_bytes, uint64_t nodeCap, std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre);
 
 // True when every partial sum of the centre chain (geom_octree.cpp:222-230) of a sub-octree with root centre
 // (cx,cy,cz), root side `rootSide` and `Lt` levels is a representable double, i.e. the chain is exact and the
