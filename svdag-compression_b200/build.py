@@ -23,7 +23,7 @@ CU_SOURCES = ["svb_prims.cu", "svb_voxelize.cu", "svb_dedup.cu", "svb_sdag.cu", 
 EXTRA_FLAGS = {"svb_raycast.cu": ["--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false"]}
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unused-function",
+    "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-ffp-contract=off,-fopenmp,-Wall,-Wno-unused-function,-Wno-unknown-pragmas",
     "--expt-relaxed-constexpr",
 ]
 
@@ -56,7 +56,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [NVCC, "-shared", "-ccbin", HOSTCXX, "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB)] + objs + ["-lcudart"]
+    cmd = [NVCC, "-shared", "-ccbin", HOSTCXX, "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB)] + objs + ["-lcudart", "-Xcompiler", "-fopenmp"]
     subprocess.run(cmd, check=True)
     return LIB
 

@@ -48,22 +48,25 @@ bool pointer_stream(const OctreeData& o, bool withMirrorHeader, std::vector<uint
 			words += (l + 1 < L) ? 1u + (uint32_t)popc(o.levels[l].mask[i]) : 1u;
 		}
 	const uint32_t firstLeafPtr = words;               // quirk: computed after the leaf level too
-	std::vector<uint32_t> data;
-	data.reserve(words);
+	std::vector<uint32_t> data(words);
 	for (size_t l = 0; l < L; ++l) {
 		const LevelSoA& lv = o.levels[l];
 		const bool hasCL = lv.childLevel.size() == lv.n * 8;
-		for (uint64_t i = 0; i < lv.n; ++i) {
+		const uint32_t* wo = wordOf.data() + levelStart[l];
+#pragma omp parallel for schedule(static) if (lv.n > 65536)
+		for (int64_t ii = 0; ii < (int64_t)lv.n; ++ii) {
+			const uint64_t i = (uint64_t)ii;
 			uint32_t head = lv.mask[i];
 			if (withMirrorHeader) head |= ((uint32_t)lv.mirror[i * 3 + 2] << 24) | ((uint32_t)lv.mirror[i * 3 + 1] << 16) | ((uint32_t)lv.mirror[i * 3] << 8);
-			data.push_back(head);
-			if (data.size() >= firstLeafPtr) continue;
+			uint32_t w = wo[i];
+			data[w++] = head;
+			if (l + 1 >= L) continue;                     // leaf level: mask word only
 			for (int k = 7; k >= 0; --k) {
 				uint32_t c = lv.child[i * 8 + k];
 				if (c == kNull) continue;
 				// USSVDAG always points into the next level; SVDAG honours childLevels (cross-level merge)
 				size_t tl = withMirrorHeader ? l + 1 : (hasCL ? lv.childLevel[i * 8 + k] : l + 1);
-				data.push_back(wordOf[(size_t)c + levelStart[tl]]);
+				data[w++] = wordOf[(size_t)c + levelStart[tl]];
 			}
 		}
 	}
@@ -79,6 +82,27 @@ uint8_t mirror_mask(uint8_t m, int s) {   // Node::mirror on a leaf mask: slot i
 	for (int i = 0; i < 8; ++i) if ((m >> (i ^ s)) & 1) r |= (uint8_t)(1u << i);
 	return r;
 }
+
+// lookup tables for the 4^3 leaf bricks: MIRROR[s][m] = mirror_mask(m, s); BRICK[c][m] = the 64-bit brick bits that the
+// 2^3 voxel mask m of sub-block c contributes (bits re-ordered x-fastest, encoded_ssvdag.cpp:119-135, :280-351)
+struct LeafTables {
+	uint8_t mirror[8][256];
+	uint64_t brick[8][256];
+	LeafTables() {
+		for (int s = 0; s < 8; ++s) for (int m = 0; m < 256; ++m) mirror[s][m] = mirror_mask((uint8_t)m, s);
+		for (int c = 0; c < 8; ++c)
+			for (int m = 0; m < 256; ++m) {
+				uint64_t b = 0;
+				for (unsigned bit = 0; bit < 64; ++bit) {
+					unsigned x = bit & 3, y = (bit >> 2) & 3, z = bit >> 4;
+					unsigned byteId = (x >> 1) + ((y >> 1) << 1) + ((z >> 1) << 2);
+					unsigned bitId = (x & 1) + ((y & 1) << 1) + ((z & 1) << 2);
+					if ((int)byteId == c && ((m >> bitId) & 1)) b |= 1ull << bit;
+				}
+				brick[c][m] = b;
+			}
+	}
+};
 
 bool ssvdag(const OctreeData& o, std::vector<uint8_t>& out, std::string* err) {
 	const int L = (int)o.levels.size();
@@ -102,33 +126,46 @@ bool ssvdag(const OctreeData& o, std::vector<uint8_t>& out, std::string* err) {
 		nextAddr.assign(cur.n, 0);
 		if (lev == L - 2) {
 			// two deepest levels fused into 4^3 bit bricks, bits re-ordered x-fastest
+			static const LeafTables lut;
 			const LevelSoA& leaf = o.levels[lev + 1];
 			leaves.assign(cur.n * 8, 0);
-			for (uint32_t r = 0; r < order.size(); ++r) {
+#pragma omp parallel for schedule(static) if (order.size() > 65536)
+			for (int64_t rr = 0; rr < (int64_t)order.size(); ++rr) {
+				const uint32_t r = (uint32_t)rr;
 				uint32_t i = order[r].first;
 				nextAddr[i] = r;
-				uint8_t sub[8];
+				uint64_t b = 0;
 				for (int c = 0; c < 8; ++c) {
 					uint32_t ch = cur.child[(uint64_t)i * 8 + c];
-					if (ch == kNull) { sub[c] = 0; continue; }
-					int s = (((cur.mirror[(uint64_t)i * 3] >> c) & 1) << 2) | (((cur.mirror[(uint64_t)i * 3 + 1] >> c) & 1) << 1) | ((cur.mirror[(uint64_t)i * 3 + 2] >> c) & 1);
-					sub[c] = mirror_mask(leaf.mask[ch], s);
+					if (ch == kNull) continue;
+					int sft = (((cur.mirror[(uint64_t)i * 3] >> c) & 1) << 2) | (((cur.mirror[(uint64_t)i * 3 + 1] >> c) & 1) << 1) | ((cur.mirror[(uint64_t)i * 3 + 2] >> c) & 1);
+					b |= lut.brick[c][lut.mirror[sft][leaf.mask[ch]]];
 				}
-				uint8_t* dst = &leaves[(uint64_t)r * 8];
-				for (unsigned bit = 0; bit < 64; ++bit) {
-					unsigned x = bit & 3, y = (bit >> 2) & 3, z = bit >> 4;
-					unsigned byteId = (x >> 1) + ((y >> 1) << 1) + ((z >> 1) << 2);   // encoded_ssvdag.cpp:119-135
-					unsigned bitId = (x & 1) + ((y & 1) << 1) + ((z & 1) << 2);
-					if ((sub[byteId] >> bitId) & 1) dst[bit >> 3] |= (uint8_t)(1u << (bit & 7));
-				}
+				memcpy(&leaves[(uint64_t)r * 8], &b, 8);   // little endian: byte j holds brick bits 8j..8j+7
 			}
 		} else {
+			// pass 1: encoded size of every node (1 header + 1 or 2 shorts per child), pass 2: fill at the prefix offsets
 			std::vector<uint16_t>& enc = inner[lev];
-			for (uint32_t r = 0; r < order.size(); ++r) {
-				uint32_t i = order[r].first;
-				nextAddr[i] = (uint32_t)enc.size();
-				size_t headAt = enc.size();
-				enc.push_back(0);
+			std::vector<uint32_t> sz(order.size());
+#pragma omp parallel for schedule(static) if (order.size() > 65536)
+			for (int64_t rr = 0; rr < (int64_t)order.size(); ++rr) {
+				uint32_t i = order[rr].first, n = 1;
+				for (int c = 7; c >= 0; --c) {
+					if (!((cur.mask[i] >> c) & 1)) continue;
+					uint32_t a = addr[cur.child[(uint64_t)i * 8 + c]];
+					n += (a < (1u << 13)) ? 1u : ((a < (1u << 30)) ? 2u : 0u);
+				}
+				sz[rr] = n;
+			}
+			uint64_t total = 0;
+			for (size_t r = 0; r < order.size(); ++r) { uint32_t n = sz[r]; sz[r] = (uint32_t)total; total += n; }
+			enc.assign(total, 0);
+#pragma omp parallel for schedule(static) if (order.size() > 65536)
+			for (int64_t rr = 0; rr < (int64_t)order.size(); ++rr) {
+				uint32_t i = order[rr].first;
+				nextAddr[i] = sz[rr];
+				size_t w = sz[rr];
+				const size_t headAt = w++;
 				uint16_t head = 0;
 				for (int c = 7; c >= 0; --c) {
 					if (!((cur.mask[i] >> c) & 1)) continue;
@@ -136,14 +173,14 @@ bool ssvdag(const OctreeData& o, std::vector<uint8_t>& out, std::string* err) {
 					unsigned mx = (cur.mirror[(uint64_t)i * 3] >> c) & 1, my = (cur.mirror[(uint64_t)i * 3 + 1] >> c) & 1, mz = (cur.mirror[(uint64_t)i * 3 + 2] >> c) & 1;
 					if (a < (1u << 13)) {
 						head |= (uint16_t)(1u << (2 * c));
-						enc.push_back((uint16_t)(a | (mx << 13) | (my << 14) | (mz << 15)));
+						enc[w++] = (uint16_t)(a | (mx << 13) | (my << 14) | (mz << 15));
 					} else if (a < (1u << 30)) {
-						uint32_t p = a;
-						if (p & (1u << 29)) { head |= (uint16_t)(3u << (2 * c)); p &= ~(1u << 29); }
+						uint32_t pp = a;
+						if (pp & (1u << 29)) { head |= (uint16_t)(3u << (2 * c)); pp &= ~(1u << 29); }
 						else head |= (uint16_t)(2u << (2 * c));
-						p |= (mx << 29) | (my << 30) | (mz << 31);
-						enc.push_back((uint16_t)(p >> 16));
-						enc.push_back((uint16_t)(p & 0xFFFF));
+						pp |= (mx << 29) | (my << 30) | (mz << 31);
+						enc[w++] = (uint16_t)(pp >> 16);
+						enc[w++] = (uint16_t)(pp & 0xFFFF);
 					}
 				}
 				enc[headAt] = head;

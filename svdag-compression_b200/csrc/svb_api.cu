@@ -345,6 +345,7 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 	c->out.clear();
 	c->state = SVB_S_EMPTY;
 	c->prof.clear();
+	c->lastImage.clear(); c->lastImageKind = -1;
 	memset(&c->stats, 0, sizeof(c->stats));
 	c->build.reset(new BuildState());
 	BuildState& B = *c->build;
@@ -787,6 +788,7 @@ int svb_shard_finish(svb_ctx* c, const uint64_t totals[5], svb_stats* out) {
 int svb_to_sdag(svb_ctx* c, svb_stats* out) {
 	int rc = guarded(c, [&] {
 		if (c->state != SVB_S_DAG) throw Error(SVB_EINVAL, "ERROR! This is not a DAG or SDAG!");   // geom_octree.cpp:560-563
+		c->lastImage.clear(); c->lastImageKind = -1;
 		const uint64_t launches0 = g_launches.load();
 		StageTimer tm(c->stream);
 		uint64_t nn = to_sdag_device(c);
@@ -804,6 +806,7 @@ int svb_to_sdag(svb_ctx* c, svb_stats* out) {
 int svb_cross_merge(svb_ctx* c, svb_stats* out) {
 	int rc = guarded(c, [&] {
 		if (c->state != SVB_S_DAG) throw Error(SVB_EINVAL, "cross-level merge needs an octree in DAG state");
+		c->lastImage.clear(); c->lastImageKind = -1;
 		const uint64_t launches0 = g_launches.load();
 		StageTimer tm(c->stream);
 		uint64_t nn = 0;
@@ -860,6 +863,11 @@ int64_t svb_encode(svb_ctx* c, int kind, uint8_t* buf, uint64_t cap) {
 	int64_t size = -1;
 	int rc = guarded(c, [&] {
 		if (c->state != SVB_S_DAG && c->state != SVB_S_SDAG) throw Error(SVB_EINVAL, "nothing to encode");
+		if (c->lastImageKind == kind && !c->lastImage.empty()) {
+			size = (int64_t)c->lastImage.size();
+			if (buf && cap >= c->lastImage.size()) memcpy(buf, c->lastImage.data(), c->lastImage.size());
+			return;
+		}
 		svbhost::OctreeData o;
 		o.levels.resize(c->levels);
 		cudaStream_t s = c->stream;
@@ -889,6 +897,8 @@ int64_t svb_encode(svb_ctx* c, int kind, uint8_t* buf, uint64_t cap) {
 		if (!svbhost::encode_file(o, kind, img, &err)) throw Error(SVB_EINVAL, err);
 		size = (int64_t)img.size();
 		if (buf && cap >= img.size()) memcpy(buf, img.data(), img.size());
+		c->lastImage.swap(img);
+		c->lastImageKind = kind;
 	});
 	return rc == SVB_OK ? size : (int64_t)rc;
 }
@@ -928,6 +938,7 @@ int svb_upload_levels(svb_ctx* c, uint32_t levels, const uint64_t* counts, const
                       const float bboxF[6], double rootSide, uint64_t nVoxels) {
 	return guarded(c, [&] {
 		if (!counts || !mask || !child8 || levels < 2) throw Error(SVB_EINVAL, "bad arguments");
+		c->lastImage.clear(); c->lastImageKind = -1;
 		cudaStream_t s = c->stream;
 		c->out.clear();
 		c->out.resize(levels);

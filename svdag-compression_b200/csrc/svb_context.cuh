@@ -27,6 +27,10 @@ struct svb_ctx {
 	std::vector<PendingProf> pending;
 	std::vector<svb_prof_rec> prof;
 	uint64_t batchBudget = 0;
+	// last file image produced by svb_encode (a size query followed by the real call must not encode twice);
+	// dropped whenever the octree changes
+	std::vector<uint8_t> lastImage;
+	int lastImageKind = -1;
 	std::shared_ptr<svb_build_state> build;   // non-null between svb_shard_build and svb_shard_finish
 	svb_ctx() { memset(&stats, 0, sizeof(stats)); }
 };
