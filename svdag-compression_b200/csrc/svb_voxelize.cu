@@ -527,7 +527,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 	DevBuf<uint16_t> pflags(pool, P + 16);   // settled-axis flags per pair (svb_classify.cuh)
 	pflags.zero();
 	const bool exactOnly = classify_exact_only();
-	static const int occ = [] { const char* e = getenv("SVB_VX_OCC"); return e ? atoi(e) : 4; }();
+	static const int occ = [] { const char* e = getenv("SVB_VX_OCC"); return e ? atoi(e) : 5; }();   // CTAs/SM of the slow classify kernel: 5 (48 registers, some spills) measured best on B200
 	for (int l = 0; l < Lt; ++l) {
 		BatchLevel& L = lv[l];
 		if (!L.mask.p) {   // (the leaf level's mask is created one level early, see k_flat_leaves)
