@@ -232,6 +232,40 @@ SVB_HD void flat_leaf_masks(const uint64_t cd, const int l, const double* __rest
 	}
 }
 
+// Flat triangle (all vertices share coordinate A bitwise) whose box axes are already decided exactly (`alive`): the
+// only tests left are the A-type cross axes of its three edges -- a 2-D triangle-vs-square problem in the plane (U, W).
+// Same interval filter as the general path (edge_axis), on 6 instead of 9 vertex offsets and without the plane.
+// p = e_W * v_U - e_U * v_W up to a sign the symmetric test does not see (X: ez*vy - ey*vz, Y: -ez*vx + ex*vz,
+// Z: ey*vx - ex*vy, test_triangle_box.cpp:60-102); projected vertex pair = {an endpoint, the opposite vertex}.
+template <bool DIRECT, int A>
+SVB_HD unsigned classify_flat2d(const uint64_t cd, const int l, const double* __restrict__ tg4, const double k, const float* __restrict__ tp,
+                                unsigned& fl, unsigned alive, unsigned& nUnsure) {
+	constexpr int U = (A == 0) ? 1 : 0, W = (A == 2) ? 1 : 2;
+	constexpr unsigned BITU = (U == 0) ? 4u : 2u, BITW = (W == 2) ? 1u : 2u;
+	constexpr unsigned E0 = 1u << A, E1 = 8u << A, E2 = 64u << A;
+	const uint64_t path = cd & ((1ull << (3 * l)) - 1);
+	const double CU = DIRECT ? centre_axis_direct(path, l, 2 - U, tg4[U], k) : centre_axis_chain(cd, l, 2 - U, tg4[U], tg4[3]);
+	const double CW = DIRECT ? centre_axis_direct(path, l, 2 - W, tg4[W], k) : centre_axis_chain(cd, l, 2 - W, tg4[W], tg4[3]);
+	const double u0 = (double)tp[U] - CU, w0 = (double)tp[W] - CW;
+	const double u1 = (double)tp[3 + U] - CU, w1 = (double)tp[3 + W] - CW;
+	const double u2 = (double)tp[6 + U] - CU, w2 = (double)tp[6 + W] - CW;
+	const double M = fmax(fmax(fmax(fabs(u0), fabs(w0)), fmax(fabs(u1), fabs(w1))), fmax(fabs(u2), fabs(w2))) + (k + k);
+	const double tol2 = M * (M * 9.094947017729282e-13);
+	unsigned unsure = 0;
+	if (!(fl & E0)) edge_axis<BITU, BITW>(E0, w1 - w0, -(u1 - u0), u0, w0, u2, w2, k, tol2, alive, unsure, fl);                // edge 0: v0 -> v1, opposite v2
+	if (alive && !(fl & E1)) edge_axis<BITU, BITW>(E1, w2 - w1, -(u2 - u1), u0, w0, u2, w2, k, tol2, alive, unsure, fl);       // edge 1: v1 -> v2, opposite v0
+	if (alive && !(fl & E2)) edge_axis<BITU, BITW>(E2, w0 - w2, -(u0 - u2), u0, w0, u1, w1, k, tol2, alive, unsure, fl);       // edge 2: v2 -> v0, opposite v1
+	unsure &= alive;
+	unsigned m = alive & ~unsure;
+	if (unsure) {
+		const double CA = DIRECT ? centre_axis_direct(path, l, 2 - A, tg4[A], k) : centre_axis_chain(cd, l, 2 - A, tg4[A], tg4[3]);
+		const double Cx = (A == 0) ? CA : CU, Cy = (A == 1) ? CA : ((A == 0) ? CU : CW), Cz = (A == 2) ? CA : CW;
+		m |= exact_children(unsure, Cx, Cy, Cz, k, tp);
+		nUnsure = (unsigned)SVB_POPC(unsure);
+	}
+	return m;
+}
+
 // Decides the 8 children of the node with Morton code `cd` (tile-local level l, tile geometry tg4 = {cx,cy,cz,rootSide}) against the
 // triangle tp[0..8].  fl: the pair's settled-axis flags (in: inherited from the parent pair, out: for the child
 // pairs).  nUnsure: children that had to be re-decided by the reference-order predicate.  Returns the hit mask.
@@ -275,7 +309,13 @@ SVB_HD unsigned classify_pair(const uint64_t cd, const int l, const double* __re
 	unsigned alive = box_axes_exact<DIRECT>(cd, l, tg4, k, tp, fl);   // (tp, not tf: dynamic axis index)
 	unsigned unsure = 0;
 	if (!alive) return 0;
-	if (planeImplied && (fl & 0x1FFu) == 0x1FFu) return alive;   // nothing but box axes left (the pair joins the flat stream)
+	if (planeImplied) {
+		if ((fl & 0x1FFu) == 0x1FFu) return alive;   // nothing but box axes left (the pair joins the flat stream)
+		// (a triangle flat on two axes is a segment: all nine edge axes are settled statically, handled above)
+		if (fl & (1u << (FL_FLAT + 0))) return classify_flat2d<DIRECT, 0>(cd, l, tg4, k, tp, fl, alive, nUnsure);
+		if (fl & (1u << (FL_FLAT + 1))) return classify_flat2d<DIRECT, 1>(cd, l, tg4, k, tp, fl, alive, nUnsure);
+		return classify_flat2d<DIRECT, 2>(cd, l, tg4, k, tp, fl, alive, nUnsure);
+	}
 	double Cx, Cy, Cz;
 	if (DIRECT) {
 		Cx = centre_axis_direct(path, l, 2, tg4[0], k);
