@@ -137,6 +137,16 @@ int svb_upload_levels(svb_ctx* ctx, uint32_t levels, const uint64_t* counts,
                       const uint8_t* mask, const uint32_t* child8,
                       const float bboxF[6], double rootSide, uint64_t nVoxels);
 
+/* EncodedSVDAG::load + decode (encoded_svdag.cpp:43-74, :200-270; used by svbuilder when its input is a .svdag,
+ * main.cpp:96-101): parse a .svdag image (host memory) into DAG levels and make them the context's octree
+ * (state DAG), ready for svb_to_sdag / svb_cross_merge / svb_encode.  nTotalVoxels is 0 afterwards, as in the
+ * reference.  Cross-level (-multi) files cannot be decoded (nor can the reference). */
+int svb_load_svdag(svb_ctx* ctx, const uint8_t* file, uint64_t size, svb_stats* out);
+/* The same decode without a GPU or a context: call with mask = child8 = NULL to get *levels and counts[0..*levels)
+ * (counts must hold 32 entries), then again with buffers of sum(counts) and 8*sum(counts) elements. */
+int svb_decode_svdag(const uint8_t* file, uint64_t size, uint32_t* levels, uint64_t* counts, uint8_t* mask, uint32_t* child8,
+                     float bboxF[6], double* rootSide, uint64_t* nNodes);
+
 /* EncodedSVDAG / EncodedUSSVDAG / EncodedSSVDAG ::encode(const GeomOctree&) + save()
  * (encoded_svdag.cpp:76-199, encoded_ussvdag.cpp:60-170, encoded_ssvdag.cpp:84-117,194-466):
  * copies the levels D2H and writes the exact file image the reference would save.

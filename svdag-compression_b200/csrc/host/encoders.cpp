@@ -202,6 +202,62 @@ bool ssvdag(const OctreeData& o, std::vector<uint8_t>& out, std::string* err) {
 
 }  // namespace
 
+// EncodedSVDAG::load + decode (encoded_svdag.cpp:43-74, :200-270): one u32 stream, levels stored one after the other;
+// a level ends where the smallest child pointer of its nodes points.  Nodes keep file order; child pointers (absolute
+// word offsets in the file) become indices into the next level.  Cross-level (-multi) files are not decodable, as in
+// the reference.
+bool decode_svdag(const uint8_t* file, uint64_t size, OctreeData& o, std::string* err) {
+	if (size < 44) { if (err) *err = "not an SVDAG file"; return false; }
+	uint32_t levels, nNodes, firstLeafPtr, count;
+	float rootSide;
+	memcpy(o.bboxF, file, 24);
+	memcpy(&rootSide, file + 24, 4);
+	memcpy(&levels, file + 28, 4);
+	memcpy(&nNodes, file + 32, 4);
+	memcpy(&firstLeafPtr, file + 36, 4);
+	memcpy(&count, file + 40, 4);
+	if (levels < 2 || levels > 32 || size < 44 + 4ull * count || count == 0) { if (err) *err = "corrupt SVDAG header"; return false; }
+	const uint32_t* data = reinterpret_cast<const uint32_t*>(file + 44);
+	o.rootSide = rootSide;
+	o.nNodes = nNodes;
+	o.nVoxels = 0;                                    // EncodedSVDAG::load does not know it either
+	o.state = 2;                                      // S_DAG
+	o.levels.assign(levels, LevelSoA());
+	std::vector<uint32_t> indexOfWord(count, 0);      // word offset of a node -> its index inside its level
+	std::vector<uint32_t> levStart(levels, 0xFFFFFFFFu);
+	levStart[0] = 0;
+	uint32_t lev = 0;
+	for (uint32_t i = 0; i < count; ++i) {
+		if (lev + 1 < levels && i == levStart[lev + 1]) ++lev;
+		LevelSoA& L = o.levels[lev];
+		const uint8_t m = (uint8_t)data[i];
+		indexOfWord[i] = (uint32_t)L.n;
+		L.mask.push_back(m);
+		L.child.insert(L.child.end(), 8, kNull);
+		if (lev + 1 < levels) {
+			uint32_t c = 0;
+			for (int k = 7; k >= 0; --k) {
+				if (!((m >> k) & 1)) continue;
+				if (i + 1 + c >= count) { if (err) *err = "corrupt SVDAG stream"; return false; }
+				const uint32_t ptr = data[i + 1 + c];
+				++c;
+				L.child[L.n * 8 + k] = ptr;               // absolute for now
+				levStart[lev + 1] = std::min(levStart[lev + 1], ptr);
+			}
+			i += c;
+		}
+		L.n++;
+	}
+	for (uint32_t l = 0; l + 1 < levels; ++l)
+		for (uint32_t& c : o.levels[l].child)
+			if (c != kNull) {
+				if (c >= count) { if (err) *err = "SVDAG pointer out of range"; return false; }
+				c = indexOfWord[c];
+			}
+	for (auto& L : o.levels) { L.mirror.assign(L.n * 3, 0); L.inv.assign(L.n, 0); }
+	return true;
+}
+
 bool encode_file(const OctreeData& o, int kind, std::vector<uint8_t>& out, std::string* err) {
 	out.clear();
 	const int S_DAG = 2, S_SDAG = 3;

@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iterator>
+#include <vector>
 
 namespace svbhost {
 
@@ -70,6 +72,18 @@ void GeomOctree::toSDAG(bool internalCall, bool skipSymmetry) {
 unsigned GeomOctree::mergeAcrossAllLevels() {
 	check(svb_cross_merge(_ctx, &_stats), "svb_cross_merge");
 	return (unsigned)_stats.nCrossLevelMerged;
+}
+
+bool GeomOctree::loadSVDAG(const std::string& fileName) {
+	printf("* Loading SVDAG '%s'... ", fileName.c_str()); fflush(stdout);
+	std::ifstream in(fileName, std::ios::binary);
+	if (!in.is_open()) { printf("FAILED!!!\n"); return false; }
+	std::vector<uint8_t> img((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+	printf("OK!\nDecoding nodes...\n");
+	check(svb_load_svdag(_ctx, img.data(), img.size(), &_stats), "svb_load_svdag");
+	_levels = svb_levels(_ctx);
+	_state = S_DAG;
+	return true;
 }
 
 void GeomOctree::resizeSceneBbox(const float mn[3], const float mx[3]) {

@@ -28,6 +28,8 @@ public:
 	void toDAG(bool internalCall = false);
 	void toSDAG(bool internalCall = false, bool skipSymmetry = false);
 	unsigned mergeAcrossAllLevels();
+	// EncodedSVDAG::load + decode + GeomOctree(data, ...) (main.cpp:96-101): start from a saved .svdag
+	bool loadSVDAG(const std::string& fileName);
 	void initChildLevels() {}   // pointers of a fresh DAG always target the next level; svb_download_level reports lev+1
 
 	State getState() const { return _state; }

@@ -31,4 +31,7 @@ struct OctreeData {
 // kind 2: .ssvdag / .esvdag (EncodedSSVDAG, encoded_ssvdag.cpp:84-117,194-466) needs DAG or SDAG
 bool encode_file(const OctreeData& o, int kind, std::vector<uint8_t>& out, std::string* err = nullptr);
 
+// EncodedSVDAG::load + decode (encoded_svdag.cpp:43-74, :200-270): a .svdag image back into DAG levels (state DAG).
+bool decode_svdag(const uint8_t* file, uint64_t size, OctreeData& o, std::string* err = nullptr);
+
 }  // namespace svbhost

@@ -56,15 +56,19 @@ int main(int argc, char** argv) {
 	printf("Lossy: %d, Cross-level: %d, Hidden geom: %d\n", 0, multiLevel, 0);
 
 	Scene scene;
-	if (!(strstr(inputFile.c_str(), ".obj") || strstr(inputFile.c_str(), ".OBJ"))) {
+	const bool isObj = strstr(inputFile.c_str(), ".obj") || strstr(inputFile.c_str(), ".OBJ");
+	const bool isInputDAG = !isObj && strstr(inputFile.c_str(), ".svdag");   // main.cpp:96-101
+	if (!isObj && !isInputDAG) {
 		printf("Can't read input file '%s'. Only supported ASCII Obj files.\n", inputFile.c_str());
 		exit(1);
 	}
-	if (!scene.loadObj(inputFile, true)) exit(1);
+	if (isObj && !scene.loadObj(inputFile, true)) exit(1);
 	const char* devEnv = getenv("SVB_DEVICE");
 	GeomOctree octree(&scene, devEnv ? atoi(devEnv) : 0);
+	if (isInputDAG && !octree.loadSVDAG(inputFile)) exit(1);
 
-	float mnF[3], mxF[3];
+	float mnF[3] = {0, 0, 0}, mxF[3] = {1, 1, 1};
+	if (!isInputDAG) {
 	scene.getBounds(mnF, mxF);
 	double mnD[3] = {mnF[0], mnF[1], mnF[2]}, mxD[3] = {mxF[0], mxF[1], mxF[2]};   // main.cpp:150-155
 	if (levelStep == 0) {
@@ -83,6 +87,7 @@ int main(int argc, char** argv) {
 		scene.setAABB(zero, nb);
 		octree.resizeSceneBbox(zero, nb);
 	}
+	}   // !isInputDAG (main.cpp:147-201)
 	octree.initChildLevels();
 
 	std::string basePath = dir_of(inputFile) + "/" + base_of(inputFile) + "_" + std::to_string(nLevels);

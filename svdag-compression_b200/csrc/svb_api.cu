@@ -969,6 +969,51 @@ int svb_upload_levels(svb_ctx* c, uint32_t levels, const uint64_t* counts, const
 	});
 }
 
+int svb_decode_svdag(const uint8_t* file, uint64_t size, uint32_t* levels, uint64_t* counts, uint8_t* mask, uint32_t* child8,
+                     float bboxF[6], double* rootSide, uint64_t* nNodes) {
+	if (!file || !levels || !counts) return SVB_EINVAL;
+	try {
+		svbhost::OctreeData o;
+		if (!svbhost::decode_svdag(file, size, o, nullptr)) return SVB_EINVAL;
+		*levels = (uint32_t)o.levels.size();
+		uint64_t off = 0;
+		for (size_t l = 0; l < o.levels.size(); ++l) {
+			counts[l] = o.levels[l].n;
+			if (mask) memcpy(mask + off, o.levels[l].mask.data(), o.levels[l].n);
+			if (child8) memcpy(child8 + off * 8, o.levels[l].child.data(), o.levels[l].n * 32);
+			off += o.levels[l].n;
+		}
+		if (bboxF) memcpy(bboxF, o.bboxF, 24);
+		if (rootSide) *rootSide = o.rootSide;
+		if (nNodes) *nNodes = o.nNodes;
+		return SVB_OK;
+	} catch (...) {
+		return SVB_EINVAL;
+	}
+}
+
+int svb_load_svdag(svb_ctx* c, const uint8_t* file, uint64_t size, svb_stats* out) {
+	if (!c || !file) return SVB_EINVAL;
+	svbhost::OctreeData o;
+	std::string err;
+	if (!svbhost::decode_svdag(file, size, o, &err)) { c->err = err; return SVB_EINVAL; }
+	std::vector<uint64_t> counts;
+	std::vector<uint8_t> mask;
+	std::vector<uint32_t> child;
+	for (auto& L : o.levels) {
+		counts.push_back(L.n);
+		mask.insert(mask.end(), L.mask.begin(), L.mask.end());
+		child.insert(child.end(), L.child.begin(), L.child.end());
+	}
+	int rc = svb_upload_levels(c, (uint32_t)o.levels.size(), counts.data(), mask.data(), child.data(), o.bboxF, o.rootSide, 0);
+	if (rc == SVB_OK) {
+		c->stats.nNodes = o.nNodes;       // Octree::_nNodes as stored in the file (GeomOctree(data, ..., stats), geom_octree.cpp:49-60)
+		c->stats.nNodesDAG = o.nNodes;
+		if (out) *out = c->stats;
+	}
+	return rc;
+}
+
 int svb_set_profiling(svb_ctx* c, int enabled) {
 	if (!c) return SVB_EINVAL;
 	c->profiling = enabled != 0;

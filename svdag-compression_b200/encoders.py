@@ -47,3 +47,33 @@ def encode_levels(levels, bboxF, root_side: float, n_nodes: int, state: int, kin
     buf = np.zeros(n, np.uint8)
     L.svb_encode_levels(*args, buf.ctypes.data, n)
     return buf.tobytes()
+
+
+def decode_svdag(file_bytes: bytes):
+    """EncodedSVDAG::load + decode through the product's host code (svb_decode_svdag; no GPU): returns
+    (levels, bboxF, root_side, n_nodes) with levels = list of dicts {mask (n,), child (n,8)}."""
+    from .capi import lib
+    L = lib()
+    L.svb_decode_svdag.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    buf = np.frombuffer(file_bytes, dtype=np.uint8)
+    nlev = C.c_uint32()
+    counts = np.zeros(32, np.uint64)
+    rc = L.svb_decode_svdag(buf.ctypes.data, len(buf), C.byref(nlev), counts.ctypes.data, None, None, None, None, None)
+    if rc != 0:
+        raise RuntimeError(f"svb_decode_svdag failed: {rc}")
+    n = int(counts[:nlev.value].sum())
+    mask = np.zeros(n, np.uint8)
+    child = np.zeros((n, 8), np.uint32)
+    bb = np.zeros(6, np.float32)
+    rs = C.c_double()
+    nn = C.c_uint64()
+    rc = L.svb_decode_svdag(buf.ctypes.data, len(buf), C.byref(nlev), counts.ctypes.data, mask.ctypes.data, child.ctypes.data,
+                            bb.ctypes.data, C.byref(rs), C.byref(nn))
+    if rc != 0:
+        raise RuntimeError(f"svb_decode_svdag failed: {rc}")
+    levels, off = [], 0
+    for l in range(nlev.value):
+        c = int(counts[l])
+        levels.append({"mask": mask[off:off + c].copy(), "child": child[off:off + c].copy()})
+        off += c
+    return levels, bb, float(rs.value), int(nn.value)

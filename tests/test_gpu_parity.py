@@ -326,3 +326,29 @@ def test_svbuilder_cli_writes_reference_files(pkg, tmp_path):
             f = d / (f"m_{g['levels']}-multi.svdag" if ext == "multi_svdag" else f"m_{g['levels']}.{ext}")
             assert f.read_bytes() == data, f"{g['name']}: {f.name} differs from the reference's file"
         assert (d / "m.obj.bincache").exists() and (d / "stats.txt").exists()
+
+
+def test_svbuilder_cli_from_svdag_input(pkg, tmp_path):
+    """`svbuilder m_7.svdag 7 0 [-c]` (main.cpp:96-101): decode a saved DAG, then SSVDAG / cross-level merge on the GPU.
+    The reference binary writes exactly the files of the direct build (checked when the goldens were minted), so the
+    goldens of the direct build are the expectation."""
+    import subprocess
+    tool = pkg.lib_path().parent / "svbuilder"
+    if not tool.exists():
+        pytest.skip("svbuilder host tool not built")
+    plain = golden_case([p for p in GOLDEN if p.stem == "city_L7_s2"][0])
+    d = tmp_path / "plain"
+    d.mkdir()
+    (d / "m_7.svdag").write_bytes(plain["files"]["svdag"])
+    r = subprocess.run([str(tool), str(d / "m_7.svdag"), "7", "0"], cwd=d, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for ext in ("svdag", "esvdag", "ussvdag", "ssvdag"):
+        assert (d / f"m_7_7.{ext}").read_bytes() == plain["files"][ext], ext
+    cross = golden_case([p for p in GOLDEN if p.stem == "city_L7_s1_c"][0])
+    d = tmp_path / "cross"
+    d.mkdir()
+    (d / "m_7.svdag").write_bytes(cross["files"]["svdag"])
+    r = subprocess.run([str(tool), str(d / "m_7.svdag"), "7", "0", "-c"], cwd=d, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert (d / "m_7_7.svdag").read_bytes() == cross["files"]["svdag"]
+    assert (d / "m_7_7-multi.svdag").read_bytes() == cross["files"]["multi_svdag"]

@@ -44,3 +44,30 @@ def test_encoder_state_checks(pkg):
         pkg.encoders.encode_levels(lv, np.zeros(6, np.float32), 1.0, 3, 2, "ussvdag")   # USSVDAG needs SDAG state
     with pytest.raises(RuntimeError):
         pkg.encoders.encode_levels(lv, np.zeros(6, np.float32), 1.0, 3, 3, "svdag")     # SVDAG needs DAG state
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN if not p.stem.endswith("_c")], ids=lambda p: p.stem)
+def test_svdag_decode_round_trip(pkg, orc, path):
+    """EncodedSVDAG::load + decode (encoded_svdag.cpp:43-74, :200-270) in the product's host code: the reference's
+    .svdag file decodes to the oracle's DAG levels, and re-encodes to the same bytes (what `svbuilder m.svdag L 0`
+    relies on, main.cpp:96-101)."""
+    g = golden_case(path)
+    data = g["files"]["svdag"]
+    levels, bboxF, rs, nn = pkg.encoders.decode_svdag(data)
+    o = orc.OracleOctree(g["tris"])
+    o.build(g["levels"], g["step"])
+    assert len(levels) == o.levels
+    for l in range(o.levels):
+        want = o.level(l)
+        assert np.array_equal(levels[l]["mask"], want["mask"]), l
+        if l + 1 < o.levels:
+            assert np.array_equal(levels[l]["child"], want["child"]), l
+    assert pkg.encoders.encode_levels(levels, bboxF, rs, nn, 2, "svdag") == data
+    assert pkg.encoders.encode_levels(levels, bboxF, rs, nn, 2, "esvdag") == g["files"]["esvdag"]
+
+
+def test_svdag_decode_rejects_garbage(pkg):
+    with pytest.raises(RuntimeError):
+        pkg.encoders.decode_svdag(b"\x00" * 20)
+    with pytest.raises(RuntimeError):
+        pkg.encoders.decode_svdag(b"\xff" * 200)
