@@ -186,12 +186,26 @@ SVB_HD void axis_extent(const float* __restrict__ tp, const int a, const bool fl
 }
 
 // All unsettled box axes of a pair, exactly; settles the axes the node has moved strictly inside of.
-template <bool DIRECT>
+// STATIC: three predicated axis blocks (best when most lanes of a warp have the same single unsettled axis: the flat
+// stream) instead of a loop over the set bits (best inside the register-hungry general path).
+template <bool DIRECT, bool STATIC = false>
 SVB_HD unsigned box_axes_exact(const uint64_t cd, const int l, const double* __restrict__ tg4, const double k, const float* __restrict__ tp, unsigned& fl) {
 	const double rootSide = tg4[3];
 	const uint64_t path = cd & ((1ull << (3 * l)) - 1);
 	unsigned ub = (~fl >> FL_BOX) & 7u;   // unsettled box axes (bit 0 = x)
 	unsigned m = 0xFFu;
+	if (STATIC) {
+#pragma unroll
+		for (int a = 0; a < 3; ++a) {
+			if (!((ub >> a) & 1u)) continue;
+			double dmin, dmax;
+			axis_extent(tp, a, ((fl >> (FL_FLAT + a)) & 1u) != 0, dmin, dmax);
+			const double C = DIRECT ? centre_axis_direct(path, l, 2 - a, tg4[a], k) : centre_axis_chain(cd, l, 2 - a, tg4[a], rootSide);
+			m &= box_axis_children(a, C, k, dmin, dmax);
+			if (box_axis_settled(C, k + k, dmin, dmax)) fl |= 1u << (FL_BOX + a);
+		}
+		return m;
+	}
 	while (ub) {
 		const int a = SVB_FFS(ub) - 1;
 		ub &= ub - 1;
@@ -206,7 +220,7 @@ SVB_HD unsigned box_axes_exact(const uint64_t cd, const int l, const double* __r
 
 template <bool DIRECT>
 SVB_HD unsigned classify_pair_flat(const uint64_t cd, const int l, const double* __restrict__ tg4, const double kscale, const float* __restrict__ tp, unsigned& fl) {
-	return box_axes_exact<DIRECT>(cd, l, tg4, tg4[3] * kscale, tp, fl);
+	return box_axes_exact<DIRECT, true>(cd, l, tg4, tg4[3] * kscale, tp, fl);
 }
 
 // Flat-stream pair at the second-to-last level: the voxel masks of its children (the leaf nodes), without emitting

@@ -240,13 +240,14 @@ __global__ void __launch_bounds__(VX_THREADS, 6) k_flat_leaves(uint64_t P, const
                                                                const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit,
                                                                const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase,
                                                                int lc, double kscaleParent, const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
-                                                               const uint32_t* __restrict__ rootTri, uint8_t* __restrict__ cmask, uint32_t* __restrict__ ctstar) {
+                                                               const uint32_t* __restrict__ rootTri, uint8_t* __restrict__ cmask, uint32_t* __restrict__ ctstar, int onlyFlatKids) {
 	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= P) return;
 	unsigned m = hit[p];
 	if (!m) return;
-	const uint32_t t = ptri[p], n = pnode[p];
 	const unsigned fl = pflags[p];
+	if (onlyFlatKids && !pair_is_fast(fl)) return;   // slow-stream parents: only those whose children join the flat stream
+	const uint32_t t = ptri[p], n = pnode[p];
 	const uint64_t cd = code[n];
 	const unsigned nm = mask[n];
 	const uint32_t base = childBase[n];
@@ -286,7 +287,8 @@ __global__ void __launch_bounds__(VX_THREADS) k_emit(uint64_t P, const uint32_t*
                                                      const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit,
                                                      const uint64_t* __restrict__ offsA, const uint64_t* __restrict__ offsB, uint64_t fastBase, uint64_t slowBase,
                                                      const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase,
-                                                     uint32_t* __restrict__ otri, uint32_t* __restrict__ onode, uint16_t* __restrict__ oflags, uint32_t* __restrict__ ctstar) {
+                                                     uint32_t* __restrict__ otri, uint32_t* __restrict__ onode, uint16_t* __restrict__ oflags, uint32_t* __restrict__ ctstar,
+                                                     int skipFlat) {
 	__shared__ uint32_t s_tri[VX_THREADS * 8];
 	__shared__ uint32_t s_node[VX_THREADS * 8];
 	__shared__ uint16_t s_fl[VX_THREADS * 8];
@@ -305,8 +307,10 @@ __global__ void __launch_bounds__(VX_THREADS) k_emit(uint64_t P, const uint32_t*
 		if (p < P) {
 			m = hit[p];
 			if (m) {
-				t = ptri[p]; n = pnode[p]; fl = pflags[p];
+				fl = pflags[p];
 				if (SLOW) flatKids = pair_is_fast(fl);
+				if (SLOW && skipFlat && flatKids) m = 0;   // decided in place by k_flat_leaves (second-to-last level)
+				else { t = ptri[p]; n = pnode[p]; }
 			}
 		}
 		const uint32_t cnt = __popc(m);
@@ -574,9 +578,11 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		SVB_CUDA(cudaStreamSynchronize(s));
 		const uint64_t Nn = h[0], cF = h[1], cS = h[2], cSF = h[3];
 		// second-to-last level: the children of the flat stream are decided in place (k_flat_leaves), not emitted
-		const bool fuseFlat = (l == Lt - 2) && F && !getenv("SVB_NO_FUSE");
+		static const bool fuseSlowKids = [] { const char* e = getenv("SVB_FUSE_SLOW"); return e ? e[0] != '0' : false; }();   // measured slower on B200 (850 vs 823 ms): off
+		const bool fuseFlat = (l == Lt - 2) && (fuseSlowKids ? (cF + cSF) != 0 : F != 0) && !getenv("SVB_NO_FUSE");
+		const bool fuseS = fuseFlat && fuseSlowKids;   // also decide the flat children of slow-stream parents in place
 		const uint64_t cFe = fuseFlat ? 0 : cF;
-		const uint64_t Fn = cFe + cSF, Fan = (Fn + 15) & ~15ull, Sn = cS - cSF, Pn = Fan + Sn;
+		const uint64_t Fn = cFe + (fuseS ? 0 : cSF), Fan = (Fn + 15) & ~15ull, Sn = cS - cSF, Pn = Fan + Sn;
 		{
 			// will this batch fit all the way down?  Surfaces grow ~4x per level; use the observed ratio.
 			const int remaining = (Lt - 1) - (l + 1);
@@ -613,18 +619,20 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		if (fuseFlat) {
 			C.mask.reset(pool, (Nn + 3 + 16) & ~3ull);
 			C.mask.zero();
-			if (directCentre) k_flat_leaves<true><<<blocks_for(F, VX_THREADS), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, L.code.p, L.mask.p, L.childBase.p, l + 1, kscale, d_tiles, d_tris, rootTri, C.mask.p, C.tstar.p);
-			else k_flat_leaves<false><<<blocks_for(F, VX_THREADS), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, L.code.p, L.mask.p, L.childBase.p, l + 1, kscale, d_tiles, d_tris, rootTri, C.mask.p, C.tstar.p);
-			SVB_KERNEL_CHECK();
-			pairsTotal += cF;   // decided here instead of as pairs of the last level
+#define SVB_LAUNCH_FL(DIR, N, OFF, ONLY) k_flat_leaves<DIR><<<blocks_for(N, VX_THREADS), VX_THREADS, 0, s>>>(N, ptri.p + (OFF), pnode.p + (OFF), pflags.p + (OFF), hit.p + (OFF), \
+			L.code.p, L.mask.p, L.childBase.p, l + 1, kscale, d_tiles, d_tris, rootTri, C.mask.p, C.tstar.p, ONLY)
+			if (F) { if (directCentre) SVB_LAUNCH_FL(true, F, 0, 0); else SVB_LAUNCH_FL(false, F, 0, 0); SVB_KERNEL_CHECK(); }
+			if (fuseS && S && cSF) { if (directCentre) SVB_LAUNCH_FL(true, S, Fa, 1); else SVB_LAUNCH_FL(false, S, Fa, 1); SVB_KERNEL_CHECK(); }
+#undef SVB_LAUNCH_FL
+			pairsTotal += cF + (fuseS ? cSF : 0);   // decided here instead of as pairs of the last level
 		} else if (F) {
 			k_emit<false><<<blocks_for(F, VX_TILE), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p,
-			                                                                ntri.p, nnode.p, nflags.p, C.tstar.p);
+			                                                                ntri.p, nnode.p, nflags.p, C.tstar.p, 0);
 			SVB_KERNEL_CHECK();
 		}
 		if (S) {
 			k_emit<true><<<blocks_for(S, VX_TILE), VX_THREADS, 0, s>>>(S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, cFe, Fan, L.mask.p, L.childBase.p,
-			                                                               ntri.p, nnode.p, nflags.p, C.tstar.p);
+			                                                               ntri.p, nnode.p, nflags.p, C.tstar.p, fuseS ? 1 : 0);
 			SVB_KERNEL_CHECK();
 		}
 		ptri = std::move(ntri);
