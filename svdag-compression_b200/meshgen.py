@@ -19,7 +19,7 @@ from pathlib import Path
 import numpy as np
 
 __all__ = [
-    "sphere", "menger_sponge", "sphere_menger", "terrain", "city", "composite",
+    "sphere", "menger_sponge", "sphere_menger", "terrain", "city", "composite", "soup",
     "corner_pins", "write_obj", "write_bincache", "make_mesh",
 ]
 
@@ -188,10 +188,45 @@ def composite(n_terrain: int = 1024, lots: int = 256) -> np.ndarray:
     return np.ascontiguousarray(np.concatenate([t, c], axis=0), dtype=np.float32)
 
 
+def soup(n: int = 400, seed: int = 7) -> np.ndarray:
+    """Adversarial triangle soup for parity tests: random triangles of all sizes mixed with degenerate ones
+    (points, segments, axis-aligned segments, zero-area slivers), triangles lying exactly in voxel faces, and
+    scene-spanning triangles.  Vertices on a 1/64 lattice make exact ties with voxel boundaries common."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = []
+    for i in range(n):
+        kind = i % 8
+        c = rng.integers(4, 60, size=3) / 64.0
+        if kind == 0:      # point
+            t = np.stack([c, c, c])
+        elif kind == 1:    # segment along an axis
+            d = np.zeros(3); d[rng.integers(0, 3)] = rng.integers(1, 6) / 64.0
+            t = np.stack([c, c + d, c])
+        elif kind == 2:    # oblique segment (two equal vertices)
+            t = np.stack([c, c + rng.integers(-5, 6, size=3) / 64.0, c])
+        elif kind == 3:    # collinear sliver
+            d = rng.integers(-4, 5, size=3) / 64.0
+            t = np.stack([c, c + d, c + 2 * d])
+        elif kind == 4:    # axis-aligned face triangle on the lattice
+            a = rng.integers(0, 3); u, w = [k for k in range(3) if k != a]
+            p1, p2 = c.copy(), c.copy()
+            p1[u] += rng.integers(1, 8) / 64.0; p2[w] += rng.integers(1, 8) / 64.0
+            t = np.stack([c, p1, p2])
+        elif kind == 5:    # large random triangle
+            t = rng.random((3, 3))
+        elif kind == 6:    # tiny random triangle (sub-voxel at 256^3)
+            t = c + rng.random((3, 3)) / 512.0
+        else:              # medium random triangle off the lattice
+            t = c + (rng.random((3, 3)) - 0.5) / 8.0
+        out.append(np.clip(t, 0.0, 1.0))
+    tris = np.concatenate([np.asarray(out), corner_pins().astype(np.float64)], axis=0)
+    return np.ascontiguousarray(tris, dtype=np.float32)
+
+
 def make_mesh(name: str, **kw) -> np.ndarray:
     """Look a generator up by name ('sphere', 'sphere_menger', 'terrain', 'city', 'composite')."""
     return {"sphere": sphere, "sphere_menger": sphere_menger, "terrain": terrain,
-            "city": city, "composite": composite, "menger": menger_sponge}[name](**kw)
+            "city": city, "composite": composite, "menger": menger_sponge, "soup": soup}[name](**kw)
 
 
 # --------------------------------------------------------------------------- writers

@@ -39,6 +39,9 @@ CASES = [
     ("terrain_L7_s3", "terrain", dict(n=24), 7, 3, False),
     ("spongeball_L7_s0", "sphere_menger", dict(n_lat=12, n_lon=24, sponge_level=1), 7, 0, False),
     ("spongeball_L7_s2_c", "sphere_menger", dict(n_lat=12, n_lon=24, sponge_level=1), 7, 2, True),
+    # adversarial soup: degenerate triangles (points, segments, slivers), lattice ties, scene-spanning triangles
+    ("soup_L7_s1", "soup", dict(n=400, seed=7), 7, 1, False),
+    ("soup_L7_s0_c", "soup", dict(n=400, seed=7), 7, 0, True),
     # scaled + shifted scenes (bbox is not the unit cube): float narrowing of sub-octree boxes, empty sub-octree roots
     ("city_affine_L8_s2", "city", dict(lots=4, affine=((3.7, 2.9, 5.3), (11.3, -5.1, 2.9))), 8, 2, False),
     ("terrain_affine_L7_s1", "terrain", dict(n=24, affine=((3.7, 2.9, 5.3), (11.3, -5.1, 2.9))), 7, 1, False),

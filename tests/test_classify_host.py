@@ -48,11 +48,13 @@ CASES = [
     ("terrain", dict(n=32), 8),
     ("sphere", dict(n_lat=16, n_lon=32), 8),
     ("sphere_menger", dict(n_lat=16, n_lon=32, sponge_level=2), 7),
+    ("soup", dict(n=400, seed=7), 8),       # degenerate triangles, lattice ties, scene-spanning triangles
+    ("soup", dict(n=240, seed=11), 9),
 ]
 
 
 @pytest.mark.parametrize("direct", [True, False], ids=["direct", "chain"])
-@pytest.mark.parametrize("mesh,kw,levels", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("mesh,kw,levels", CASES, ids=[f"{c[0]}{i}" for i, c in enumerate(CASES)])
 def test_filter_equals_predicate_unit_cube(harness, meshgen, mesh, kw, levels, direct):
     tris = meshgen.make_mesh(mesh, **kw)
     v = tris.reshape(-1, 3).astype(np.float64)

@@ -54,6 +54,9 @@ CASES = [
     ("terrain", dict(n=64), 9, 3),
     ("sphere_menger", dict(n_lat=32, n_lon=64, sponge_level=2), 8, 0),
     ("sphere_menger", dict(n_lat=32, n_lon=64, sponge_level=2), 9, 2),
+    ("soup", dict(n=400, seed=7), 8, 0),     # degenerate triangles (points, segments, slivers), lattice ties
+    ("soup", dict(n=400, seed=7), 8, 2),
+    ("soup", dict(n=1200, seed=3), 7, 1),
 ]
 
 
