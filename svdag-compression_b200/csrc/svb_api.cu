@@ -150,6 +150,7 @@ struct svb_build_state {
 	uint32_t rank = 0, world = 1;
 	int tbits = 1, tileBits = 1;   // tbits: bits of a triangle rank inside the root tile (all triangles)
 	int tbLocal = 1;               // bits of a triangle rank inside a sub-octree (max candidates per tile)
+	bool allFlat = false;          // every triangle is flat (box mesh): slow-stream kernel variant without the general filter
 	std::vector<LevelTable> tables;      // per global level
 	std::vector<int> obits;
 	DevBuf<uint64_t> dVoxels, dExact;
@@ -259,7 +260,7 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 		make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, dLocal.p, nt, ptri, pnode, rootTri, dTileStart, P);
 		bool direct = true;
 		for (uint32_t i = 0; i < nt && direct; ++i) direct = centre_chain_exact(hg[i], Lt);
-		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, rootTri.p, dTileStart.p, P, budget, nodeCap, lv, pairs, B.dExact.p, direct);
+		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, rootTri.p, dTileStart.p, P, budget, nodeCap, lv, pairs, B.dExact.p, direct, B.allFlat);
 		ps.done(pairs, 36.0 * (double)c->T + 9.0 * (double)lv[Lt - 1].n);
 		B.msVox += tm.stop();
 	}
@@ -363,6 +364,7 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 	B.dExact.reset(c->pool, 1); B.dExact.zero();
 	B.rootKey.reset(c->pool, 8); B.rootKey.fill_ff();
 
+	B.allFlat = !getenv("SVB_NO_FLATONLY") && all_triangles_flat(s, c->pool, c->d_tris, c->T);
 	float_box(bmin, bmax, B.bboxF, B.rootSide);
 	const double rootSide = B.rootSide;
 	B.rootG.cx = (bmin[0] + bmax[0]) * 0.5; B.rootG.cy = (bmin[1] + bmax[1]) * 0.5; B.rootG.cz = (bmin[2] + bmax[2]) * 0.5;   // bbox.center(), :214

@@ -283,7 +283,9 @@ SVB_HD unsigned classify_flat2d(const uint64_t cd, const int l, const double* __
 // Decides the 8 children of the node with Morton code `cd` (tile-local level l, tile geometry tg4 = {cx,cy,cz,rootSide}) against the
 // triangle tp[0..8].  fl: the pair's settled-axis flags (in: inherited from the parent pair, out: for the child
 // pairs).  nUnsure: children that had to be re-decided by the reference-order predicate.  Returns the hit mask.
-template <bool DIRECT>
+// FLATONLY: the caller guarantees that every triangle of the scene is flat (a box mesh); the general edge / plane
+// filter is then compiled out, which is what lets the kernel fit 40 registers.
+template <bool DIRECT, bool FLATONLY = false>
 SVB_HD unsigned classify_pair(const uint64_t cd, const int l, const double* __restrict__ tg4, const double kscale, const float* __restrict__ tp,
                               unsigned& fl, unsigned& nUnsure) {
 	nUnsure = 0;
@@ -330,6 +332,7 @@ SVB_HD unsigned classify_pair(const uint64_t cd, const int l, const double* __re
 		if (fl & (1u << (FL_FLAT + 1))) return classify_flat2d<DIRECT, 1>(cd, l, tg4, k, tp, fl, alive, nUnsure);
 		return classify_flat2d<DIRECT, 2>(cd, l, tg4, k, tp, fl, alive, nUnsure);
 	}
+	if (FLATONLY) return 0;   // unreachable under the caller's guarantee
 	double Cx, Cy, Cz;
 	if (DIRECT) {
 		Cx = centre_axis_direct(path, l, 2, tg4[0], k);

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(VX_THREADS) k_classify(uint64_t P, const uint3
 // ------------------------------------------------------------------ classify, filtered (default)
 // One thread per pair decides all 8 children with classify_pair() (svb_classify.cuh): exact single-axis fast path
 // for settled flat triangles, FP64 interval filter + reference-order predicate for the rest.
-template <int MINB, bool DIRECT>
+template <int MINB, bool DIRECT, bool FLATONLY>
 __global__ void __launch_bounds__(VX_THREADS, MINB) k_classify_filtered(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
                                                                    uint16_t* __restrict__ pflags, const uint64_t* __restrict__ code, int l, double kscale, int last,
                                                                    const TileGeom* __restrict__ tiles, const float* __restrict__ tris, const uint32_t* __restrict__ rootTri,
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_classify_filtered(uint64_t
 	unsigned fl = fl0, nUnsure;
 	const uint64_t cd = code[n];
 	const double* tg = reinterpret_cast<const double*>(tiles + (uint32_t)(cd >> (3 * l)));   // {cx, cy, cz, rootSide}
-	const unsigned m = classify_pair<DIRECT>(cd, l, tg, kscale, tris + 9ull * t, fl, nUnsure);
+	const unsigned m = classify_pair<DIRECT, FLATONLY>(cd, l, tg, kscale, tris + 9ull * t, fl, nUnsure);
 	if (nUnsure && nExact) atomicAdd(nExact, (unsigned long long)nUnsure);
 	if (!last) {
 		hit[p] = (uint8_t)m;
@@ -423,6 +423,15 @@ uint64_t read_u64(cudaStream_t s, const uint64_t* d) {
 
 }  // namespace
 
+// every triangle flat (all three vertices share a coordinate bitwise)?  0 in *notFlat if so
+__global__ void __launch_bounds__(VX_THREADS) k_all_flat(const float* __restrict__ tris, uint64_t T, uint32_t* __restrict__ notFlat) {
+	uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= T) return;
+	const float* p = tris + 9 * t;
+	const bool flat = (p[0] == p[3] && p[3] == p[6]) || (p[1] == p[4] && p[4] == p[7]) || (p[2] == p[5] && p[5] == p[8]);
+	if (!flat) *notFlat = 1;
+}
+
 // ------------------------------------------------------------------ host drivers
 namespace {
 // exponent of the lowest set bit of a finite double (x = odd * 2^e); 0 -> +inf-like sentinel
@@ -459,6 +468,18 @@ static GridDesc grid_desc(const TileGridHost& grid) {
 	g.margin = grid.cell * 1e-6 + maxAbs * 4.8e-7;   // 4.8e-7 = 4 * 2^-23
 	g.G = grid.G;
 	return g;
+}
+
+bool all_triangles_flat(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T) {
+	if (!T) return false;
+	DevBuf<uint32_t> flag(pool, 1);
+	flag.zero();
+	k_all_flat<<<blocks_for(T, VX_THREADS), VX_THREADS, 0, s>>>(d_tris, T, flag.p);
+	SVB_KERNEL_CHECK();
+	uint32_t h = 1;
+	SVB_CUDA(cudaMemcpyAsync(&h, flag.p, 4, cudaMemcpyDeviceToHost, s));
+	SVB_CUDA(cudaStreamSynchronize(s));
+	return h == 0;
 }
 
 uint32_t max_candidates_per_tile(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T, const TileGridHost& grid, const int* d_gridTile, uint64_t nTiles) {
@@ -514,7 +535,7 @@ void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T
 
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
                     DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, const uint32_t* rootTri, const uint32_t* tileStart, uint64_t P,
-                    uint64_t budget_bytes, uint64_t nodeCap, std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre) {
+                    uint64_t budget_bytes, uint64_t nodeCap, std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre, bool allFlat) {
 	if (const char* e = getenv("SVB_CENTRE")) directCentre = directCentre && e[0] != 'c';   // SVB_CENTRE=chain: always replay the chain
 	lv.clear();
 	lv.resize(Lt);
@@ -531,6 +552,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 	DevBuf<uint16_t> pflags(pool, P + 16);   // settled-axis flags per pair (svb_classify.cuh)
 	pflags.zero();
 	const bool exactOnly = classify_exact_only();
+	static const int occFlat = [] { const char* e = getenv("SVB_VX_OCC_FLAT"); return e ? atoi(e) : 8; }();   // measured on B200: 8 (32 registers, spills) beats 6 and 5: the kernel is latency bound
 	static const int occ = [] { const char* e = getenv("SVB_VX_OCC"); return e ? atoi(e) : 5; }();   // CTAs/SM of the slow classify kernel: 5 (48 registers, some spills) measured best on B200
 	for (int l = 0; l < Lt; ++l) {
 		BatchLevel& L = lv[l];
@@ -554,19 +576,25 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 				k_classify<<<blocks_for(S * 8, VX_THREADS), VX_THREADS, 0, s>>>(S, st, sn, L.code.p, l, d_tiles, d_tris, rootTri, sh, L.mask.p, last);
 			else {
 				unsigned nb = blocks_for(S, VX_THREADS);
-#define SVB_LAUNCH_CF(OCC, DIR) k_classify_filtered<OCC, DIR><<<nb, VX_THREADS, 0, s>>>(S, st, sn, sf, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, sh, L.mask.p, (unsigned long long*)d_nExact)
-				if (directCentre) {
-					if (occ >= 6) SVB_LAUNCH_CF(6, true); else if (occ == 5) SVB_LAUNCH_CF(5, true); else if (occ == 4) SVB_LAUNCH_CF(4, true);
-					else if (occ == 3) SVB_LAUNCH_CF(3, true); else SVB_LAUNCH_CF(1, true);
+#define SVB_LAUNCH_CF(OCC, DIR, FLAT) k_classify_filtered<OCC, DIR, FLAT><<<nb, VX_THREADS, 0, s>>>(S, st, sn, sf, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, sh, L.mask.p, (unsigned long long*)d_nExact)
+				if (allFlat) {   // box meshes: the general edge / plane filter is compiled out, 6 CTAs/SM without spills
+					const int o = occFlat;
+					if (directCentre) { if (o >= 8) SVB_LAUNCH_CF(8, true, true); else if (o == 7) SVB_LAUNCH_CF(7, true, true); else if (o == 6) SVB_LAUNCH_CF(6, true, true); else SVB_LAUNCH_CF(5, true, true); }
+					else { if (o >= 8) SVB_LAUNCH_CF(8, false, true); else if (o == 7) SVB_LAUNCH_CF(7, false, true); else if (o == 6) SVB_LAUNCH_CF(6, false, true); else SVB_LAUNCH_CF(5, false, true); }
+				} else if (directCentre) {
+					if (occ >= 6) SVB_LAUNCH_CF(6, true, false); else if (occ == 5) SVB_LAUNCH_CF(5, true, false); else if (occ == 4) SVB_LAUNCH_CF(4, true, false);
+					else if (occ == 3) SVB_LAUNCH_CF(3, true, false); else SVB_LAUNCH_CF(1, true, false);
 				} else {
-					if (occ >= 6) SVB_LAUNCH_CF(6, false); else if (occ == 5) SVB_LAUNCH_CF(5, false); else if (occ == 4) SVB_LAUNCH_CF(4, false);
-					else if (occ == 3) SVB_LAUNCH_CF(3, false); else SVB_LAUNCH_CF(1, false);
+					if (occ >= 6) SVB_LAUNCH_CF(6, false, false); else if (occ == 5) SVB_LAUNCH_CF(5, false, false); else if (occ == 4) SVB_LAUNCH_CF(4, false, false);
+					else if (occ == 3) SVB_LAUNCH_CF(3, false, false); else SVB_LAUNCH_CF(1, false, false);
 				}
 #undef SVB_LAUNCH_CF
 			}
 			SVB_KERNEL_CHECK();
 		}
 		pairsTotal += F + S;
+		if (getenv("SVB_VX_STATS")) fprintf(stderr, "[vx-stats] tiles %u level %d/%d nodes %llu flat pairs %llu slow pairs %llu\n", ntiles, l, Lt - 1,
+		                                    (unsigned long long)L.n, (unsigned long long)F, (unsigned long long)S);
 		if (last) break;
 		// children of the nodes, child pairs of the pairs: tile-granular scans, one read-back
 		DevBuf<uint64_t> nodeOffs, offF, offFB, offS, offSF;

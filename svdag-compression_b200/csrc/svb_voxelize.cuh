@@ -33,7 +33,10 @@ uint32_t max_candidates_per_tile(cudaStream_t s, Pool& pool, const float* d_tris
 // "triangles" (BatchLevel::tstar) are root pair indices q: monotone in the triangle id within a tile.
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
                     DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, const uint32_t* rootTri, const uint32_t* tileStart, uint64_t P,
-                    uint64_t budget_bytes, uint64_t nodeCap, std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre);
+                    uint64_t budget_bytes, uint64_t nodeCap, std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre, bool allFlat);
+
+// true when every triangle is flat (box meshes): selects the slow-stream kernel without the general edge / plane filter
+bool all_triangles_flat(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T);
 
 // True when every partial sum of the centre chain (geom_octree.cpp:222-230) of a sub-octree with root centre
 // (cx,cy,cz), root side `rootSide` and `Lt` levels is a representable double, i.e. the chain is exact and the
