@@ -235,8 +235,8 @@ __global__ void __launch_bounds__(VX_THREADS, 8) k_classify_fast(uint64_t P, con
 // parent pair decides each hit child's 8 voxels on the spot (same exact box-axis tests, one level down) and ORs the
 // voxel mask / first-touch triangle straight into the leaf level.  Saves writing and re-reading the bulk of the
 // last-level pair list (the interior of every wall), which is the largest array of the whole build.
-template <bool DIRECT>
-__global__ void __launch_bounds__(VX_THREADS, 6) k_flat_leaves(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
+template <bool DIRECT, int MINB>
+__global__ void __launch_bounds__(VX_THREADS, MINB) k_flat_leaves(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
                                                                const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit,
                                                                const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase,
                                                                int lc, double kscaleParent, const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
@@ -647,11 +647,14 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		if (fuseFlat) {
 			C.mask.reset(pool, (Nn + 3 + 16) & ~3ull);
 			C.mask.zero();
-#define SVB_LAUNCH_FL(DIR, N, OFF, ONLY) k_flat_leaves<DIR><<<blocks_for(N, VX_THREADS), VX_THREADS, 0, s>>>(N, ptri.p + (OFF), pnode.p + (OFF), pflags.p + (OFF), hit.p + (OFF), \
+			static const int occLeaves = [] { const char* e = getenv("SVB_VX_OCC_LEAVES"); return e ? atoi(e) : 8; }();   // 8 CTAs/SM measured best
+#define SVB_LAUNCH_FL(DIR, N, OFF, ONLY) if (occLeaves >= 8) SVB_LAUNCH_FL2(DIR, 8, N, OFF, ONLY); else SVB_LAUNCH_FL2(DIR, 6, N, OFF, ONLY)
+#define SVB_LAUNCH_FL2(DIR, MB, N, OFF, ONLY) k_flat_leaves<DIR, MB><<<blocks_for(N, VX_THREADS), VX_THREADS, 0, s>>>(N, ptri.p + (OFF), pnode.p + (OFF), pflags.p + (OFF), hit.p + (OFF), \
 			L.code.p, L.mask.p, L.childBase.p, l + 1, kscale, d_tiles, d_tris, rootTri, C.mask.p, C.tstar.p, ONLY)
 			if (F) { if (directCentre) SVB_LAUNCH_FL(true, F, 0, 0); else SVB_LAUNCH_FL(false, F, 0, 0); SVB_KERNEL_CHECK(); }
 			if (fuseS && S && cSF) { if (directCentre) SVB_LAUNCH_FL(true, S, Fa, 1); else SVB_LAUNCH_FL(false, S, Fa, 1); SVB_KERNEL_CHECK(); }
 #undef SVB_LAUNCH_FL
+#undef SVB_LAUNCH_FL2
 			pairsTotal += cF + (fuseS ? cSF : 0);   // decided here instead of as pairs of the last level
 		} else if (F) {
 			k_emit<false><<<blocks_for(F, VX_TILE), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p,
