@@ -257,7 +257,13 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 		ProfScope ps(c, "voxelize", gbase, nt);
 		DevBuf<uint32_t> ptri, pnode, rootTri;
 		uint64_t P = 0;
-		make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, dLocal.p, nt, ptri, pnode, rootTri, dTileStart, P);
+		int cellLo[3] = {1 << 30, 1 << 30, 1 << 30}, cellHi[3] = {-1, -1, -1};
+		for (uint32_t i = 0; i < nt; ++i) {
+			const TileHost& th = tiles[sel[a + i]];
+			cellLo[0] = std::min(cellLo[0], th.ix); cellLo[1] = std::min(cellLo[1], th.iy); cellLo[2] = std::min(cellLo[2], th.iz);
+			cellHi[0] = std::max(cellHi[0], th.ix); cellHi[1] = std::max(cellHi[1], th.iy); cellHi[2] = std::max(cellHi[2], th.iz);
+		}
+		make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, dLocal.p, nt, ptri, pnode, rootTri, dTileStart, P, cellLo, cellHi);
 		bool direct = true;
 		for (uint32_t i = 0; i < nt && direct; ++i) direct = centre_chain_exact(hg[i], Lt);
 		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, rootTri.p, dTileStart.p, P, budget, nodeCap, lv, pairs, B.dExact.p, direct, B.allFlat);

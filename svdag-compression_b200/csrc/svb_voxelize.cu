@@ -34,6 +34,7 @@ struct GridDesc {
 	double inv_cell;     // 1 / tile side
 	double margin;       // absolute
 	int G;               // tiles per axis
+	int lo[3], hi[3];    // grid-cell bounding box of the tiles of interest (the current batch): triangles outside are skipped early
 };
 
 __device__ inline void tile_range(double mn, double mx, double o, const GridDesc& g, int& a, int& b) {
@@ -57,6 +58,9 @@ __global__ void __launch_bounds__(VX_THREADS) k_candidates(const float* __restri
 	tile_range(mnx, mxx, g.ox, g, ax, bx);
 	tile_range(mny, mxy, g.oy, g, ay, by);
 	tile_range(mnz, mxz, g.oz, g, az, bz);
+	ax = max(ax, g.lo[0]); bx = min(bx, g.hi[0]);
+	ay = max(ay, g.lo[1]); by = min(by, g.hi[1]);
+	az = max(az, g.lo[2]); bz = min(bz, g.hi[2]);
 	uint32_t c = 0;
 	uint32_t o = EMIT ? cnt_or_off[t] : 0;
 	for (int x = ax; x <= bx; ++x)
@@ -467,6 +471,7 @@ static GridDesc grid_desc(const TileGridHost& grid) {
 	                               std::max(fabs(grid.oz), fabs(grid.oz + ext)));
 	g.margin = grid.cell * 1e-6 + maxAbs * 4.8e-7;   // 4.8e-7 = 4 * 2^-23
 	g.G = grid.G;
+	for (int k = 0; k < 3; ++k) { g.lo[k] = 0; g.hi[k] = grid.G - 1; }
 	return g;
 }
 
@@ -499,8 +504,9 @@ uint32_t max_candidates_per_tile(cudaStream_t s, Pool& pool, const float* d_tris
 
 void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T, const TileGridHost& grid,
                      const int* d_gridTile, const int* d_localOf, uint32_t ntiles, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode,
-                     DevBuf<uint32_t>& rootTri, DevBuf<uint32_t>& tileStart, uint64_t& P) {
+                     DevBuf<uint32_t>& rootTri, DevBuf<uint32_t>& tileStart, uint64_t& P, const int cellLo[3], const int cellHi[3]) {
 	GridDesc g = grid_desc(grid);
+	if (cellLo && cellHi) for (int k = 0; k < 3; ++k) { g.lo[k] = std::max(cellLo[k], 0); g.hi[k] = std::min(cellHi[k], grid.G - 1); }
 	DevBuf<uint32_t> cnt(pool, T);
 	DevBuf<uint64_t> tot(pool, 1);
 	unsigned nb = blocks_for(T, VX_THREADS);

@@ -24,7 +24,8 @@ struct TileGridHost {    // regular grid of tile cubes over the root cube (G = 2
 // d_gridTile: grid cell -> global tile_seq (-1 none); d_localOf: global tile_seq -> index in the batch (-1 not in it).
 void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T, const TileGridHost& grid,
                      const int* d_gridTile, const int* d_localOf, uint32_t ntiles, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode,
-                     DevBuf<uint32_t>& rootTri, DevBuf<uint32_t>& tileStart, uint64_t& P);
+                     DevBuf<uint32_t>& rootTri, DevBuf<uint32_t>& tileStart, uint64_t& P, const int cellLo[3] = nullptr, const int cellHi[3] = nullptr);
+// (cellLo / cellHi: grid-cell bounding box of the batch's tiles; triangles that cannot reach it are skipped early)
 
 // largest number of candidate triangles any tile of the grid has (bounds the tile-local triangle rank)
 uint32_t max_candidates_per_tile(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T, const TileGridHost& grid, const int* d_gridTile, uint64_t nTiles);
