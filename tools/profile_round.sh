@@ -23,8 +23,12 @@ tris = pkg.meshgen.city(256)
 v = tris.reshape(-1, 3)
 bbox = (v.min(axis=0).astype(np.float64), v.max(axis=0).astype(np.float64))
 t = pkg.GeomOctree(tris)
+t.set_profiling(True)
 st = t.build(14, 4, bbox=bbox)
 print(st["nTotalVoxels"], st["msTotal"], st["msVoxelize"], st["nKernelLaunches"])
+for r in t.profile():
+    if r["name"].startswith("dedup_leaf") or r["name"].startswith("dedup_k64"):
+        print("PROFREC", r["name"], r["level"], r["n_in"], r["n_out"])
 PY
 cap() {  # name regex skip count
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -o gpurun_out/tmp_$1 python /tmp/ncu_city.py > gpurun_out/ncu_$1_${TAG}.log 2>&1
@@ -34,5 +38,5 @@ cap() {  # name regex skip count
 cap dedup "k_leaf_min|k_insert|k_convert|k_assign_k64|k_winner" 0 14
 cap classify "k_classify_filtered" 28 4
 cap flat "k_flat_leaves|k_classify_fast" 10 6
-cap emit "k_emit|k_children" 40 8
+cap emit "k_emit|k_children" 40 6
 du -sh gpurun_out
