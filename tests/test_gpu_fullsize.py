@@ -73,6 +73,33 @@ def test_depth_images_agree_across_formats(pkg, built):
     assert np.array_equal(s4[..., 0] > 0, ref[..., 0] > 0)
 
 
+def test_cross_level_merge_at_full_size(pkg, built):
+    """BASELINE.json configs[3]: CSVDAG of the same city at 16384^3 -- the merged file must render exactly like the
+    plain one (geometry preserved), point only to existing nodes, and be smaller."""
+    v = built["tris"].reshape(-1, 3)
+    bbox = (v.min(axis=0).astype(np.float64), v.max(axis=0).astype(np.float64))
+    t = pkg.GeomOctree(built["tris"])
+    st = t.build(14, 4, bbox=bbox)
+    cm = t.cross_merge()
+    assert cm["nCrossLevelMerged"] > 0 and cm["nNodesDAG"] == st["nNodesDAG"] - cm["nCrossLevelMerged"]
+    lv = t.levels_host()
+    sizes = [len(l["mask"]) for l in lv]
+    for l, L in enumerate(lv[:-1]):
+        ok = L["child"] != NULL
+        tl = L["childLevel"][ok].astype(np.int64)
+        assert ((tl >= 1) & (tl <= l + 1)).all(), f"level {l}: child level out of range"
+        assert (L["child"][ok].astype(np.int64) < np.asarray(sizes)[tl]).all(), f"level {l}: dangling cross-level pointer"
+    multi = pkg.encoders.encode(t, "svdag")
+    assert len(multi) < len(built["files"]["svdag"])
+    lo, hi = v.min(0).astype(np.float64), v.max(0).astype(np.float64)
+    c, d = (lo + hi) / 2, float(np.linalg.norm(hi - lo))
+    vi = pkg.camera.look_at_inv(c + np.array([0.55, 0.45, 0.5]) * d, c)
+    pi = pkg.camera.perspective_inv(45.0, 1.0)
+    a = pkg.raycast_depth(built["files"]["svdag"], "svdag", vi, pi, 512, 512, 20000)
+    b = pkg.raycast_depth(multi, "svdag", vi, pi, 512, 512, 20000)
+    assert np.array_equal(a, b)
+
+
 @pytest.mark.skipif(not GOLD.exists(), reason="tests/golden/fullsize_city16k.json not minted")
 def test_files_equal_reference_at_full_size(built):
     g = json.loads(GOLD.read_text())
