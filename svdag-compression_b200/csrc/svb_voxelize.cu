@@ -127,7 +127,7 @@ template <int MINB, bool DIRECT, bool FLATONLY>
 __global__ void __launch_bounds__(VX_THREADS, MINB) k_classify_filtered(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
                                                                    uint16_t* __restrict__ pflags, const uint64_t* __restrict__ code, int l, double kscale, int last,
                                                                    const TileGeom* __restrict__ tiles, const float* __restrict__ tris, const uint32_t* __restrict__ rootTri,
-                                                                   uint8_t* __restrict__ hit, uint8_t* __restrict__ mask, unsigned long long* __restrict__ nExact) {
+                                                                   uint8_t* __restrict__ hit, uint8_t* __restrict__ mask, unsigned long long* __restrict__ nExact, int precheck) {
 	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= P) return;
 	const uint32_t t = rootTri[ptri[p]], n = pnode[p];   // pairs carry the index of their root pair (see make_root_pairs)
@@ -141,10 +141,8 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_classify_filtered(uint64_t
 		hit[p] = (uint8_t)m;
 		if (fl != fl0) pflags[p] = (uint16_t)fl;   // inherited by the child pairs (k_emit)
 	}
-	if (m) {
-		unsigned cur = mask[n];   // may be stale (L1); bits only ever get set, so a stale value only costs an extra atomic
-		if ((cur & m) != m) atomicOr(reinterpret_cast<unsigned*>(mask) + (n >> 2), m << (8 * (n & 3)));
-	}
+	// precheck (may read a stale value: bits only ever get set, so that only costs an extra atomic)
+	if (m && (!precheck || (mask[n] & m) != m)) atomicOr(reinterpret_cast<unsigned*>(mask) + (n >> 2), m << (8 * (n & 3)));
 }
 
 // ------------------------------------------------------------------ tile-local scans
@@ -217,7 +215,7 @@ template <bool DIRECT>
 __global__ void __launch_bounds__(VX_THREADS, 8) k_classify_fast(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
                                                                  uint16_t* __restrict__ pflags, const uint64_t* __restrict__ code, int l, double kscale, int last,
                                                                  const TileGeom* __restrict__ tiles, const float* __restrict__ tris, const uint32_t* __restrict__ rootTri,
-                                                                 uint8_t* __restrict__ hit, uint8_t* __restrict__ mask) {
+                                                                 uint8_t* __restrict__ hit, uint8_t* __restrict__ mask, int precheck) {
 	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= P) return;
 	const uint32_t t = rootTri[ptri[p]], n = pnode[p];
@@ -228,10 +226,7 @@ __global__ void __launch_bounds__(VX_THREADS, 8) k_classify_fast(uint64_t P, con
 	const unsigned m = classify_pair_flat<DIRECT>(cd, l, tg, kscale, tris + 9ull * t, fl);
 	if (!last && fl != fl0) pflags[p] = (uint16_t)fl;   // a box axis settled: inherited by the child pairs
 	if (!last) hit[p] = (uint8_t)m;
-	if (m) {
-		unsigned cur = mask[n];
-		if ((cur & m) != m) atomicOr(reinterpret_cast<unsigned*>(mask) + (n >> 2), m << (8 * (n & 3)));
-	}
+	if (m && (!precheck || (mask[n] & m) != m)) atomicOr(reinterpret_cast<unsigned*>(mask) + (n >> 2), m << (8 * (n & 3)));
 }
 
 // ------------------------------------------------------------------ flat stream, last two levels fused
@@ -244,7 +239,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_flat_leaves(uint64_t P, co
                                                                const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit,
                                                                const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase,
                                                                int lc, double kscaleParent, const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
-                                                               const uint32_t* __restrict__ rootTri, uint8_t* __restrict__ cmask, uint32_t* __restrict__ ctstar, int onlyFlatKids) {
+                                                               const uint32_t* __restrict__ rootTri, uint8_t* __restrict__ cmask, uint32_t* __restrict__ ctstar, int onlyFlatKids, int precheck) {
 	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= P) return;
 	unsigned m = hit[p];
@@ -269,14 +264,16 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_flat_leaves(uint64_t P, co
 		const uint32_t child = base + __popc(nm & ((1u << c) - 1));
 		const unsigned mc = lohi[0][(c >> 2) & 1] & lohi[1][(c >> 1) & 1] & lohi[2][c & 1];
 		if ((child >> 2) != curWord) {
-			if (acc && (words[curWord] & acc) != acc) atomicOr(words + curWord, acc);
+			if (acc && (!precheck || (words[curWord] & acc) != acc)) atomicOr(words + curWord, acc);
 			curWord = child >> 2;
 			acc = 0;
 		}
 		acc |= mc << (8 * (child & 3));
-		if (ctstar[child] > t) atomicMin(&ctstar[child], t);
+		// precheck: read before the atomic -- pays off only where many pairs share a node (upper levels); at the leaf
+		// levels (~1.4 pairs per node) the read is a wasted round trip and the reduction goes out fire-and-forget
+		if (!precheck || ctstar[child] > t) atomicMin(&ctstar[child], t);
 	}
-	if (acc && (words[curWord] & acc) != acc) atomicOr(words + curWord, acc);
+	if (acc && (!precheck || (words[curWord] & acc) != acc)) atomicOr(words + curWord, acc);
 }
 
 // ------------------------------------------------------------------ emit the child pairs
@@ -292,7 +289,7 @@ __global__ void __launch_bounds__(VX_THREADS) k_emit(uint64_t P, const uint32_t*
                                                      const uint64_t* __restrict__ offsA, const uint64_t* __restrict__ offsB, uint64_t fastBase, uint64_t slowBase,
                                                      const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase,
                                                      uint32_t* __restrict__ otri, uint32_t* __restrict__ onode, uint16_t* __restrict__ oflags, uint32_t* __restrict__ ctstar,
-                                                     int skipFlat) {
+                                                     int skipFlat, int precheck) {
 	__shared__ uint32_t s_tri[VX_THREADS * 8];
 	__shared__ uint32_t s_node[VX_THREADS * 8];
 	__shared__ uint16_t s_fl[VX_THREADS * 8];
@@ -334,7 +331,7 @@ __global__ void __launch_bounds__(VX_THREADS) k_emit(uint64_t P, const uint32_t*
 				s_node[o] = child;
 				s_fl[o] = (uint16_t)fl;
 				++o;
-				if (ctstar[child] > t) atomicMin(&ctstar[child], t);
+				if (!precheck || ctstar[child] > t) atomicMin(&ctstar[child], t);
 			}
 		}
 		__syncthreads();
@@ -570,10 +567,12 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		DevBuf<uint8_t> hit(pool, last ? 16 : Fa + S + 16);
 		if (F + S > (1ull << 59)) throw Error(SVB_ERANGE, "too many pairs");
 		const double kscale = ldexp(1.0, -(l + 2));
+		static const int forcePre = [] { const char* e = getenv("SVB_PRECHECK"); return e ? atoi(e) : -1; }();
+		const int precheck = forcePre >= 0 ? forcePre : ((F + S) > 2 * L.n ? 1 : 0);   // read-before-atomic only where many pairs share a node
 		if (F) {
 			unsigned nb = blocks_for(F, VX_THREADS);
-			if (directCentre) k_classify_fast<true><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, hit.p, L.mask.p);
-			else k_classify_fast<false><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, hit.p, L.mask.p);
+			if (directCentre) k_classify_fast<true><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, hit.p, L.mask.p, precheck);
+			else k_classify_fast<false><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, hit.p, L.mask.p, precheck);
 			SVB_KERNEL_CHECK();
 		}
 		if (S) {
@@ -582,7 +581,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 				k_classify<<<blocks_for(S * 8, VX_THREADS), VX_THREADS, 0, s>>>(S, st, sn, L.code.p, l, d_tiles, d_tris, rootTri, sh, L.mask.p, last);
 			else {
 				unsigned nb = blocks_for(S, VX_THREADS);
-#define SVB_LAUNCH_CF(OCC, DIR, FLAT) k_classify_filtered<OCC, DIR, FLAT><<<nb, VX_THREADS, 0, s>>>(S, st, sn, sf, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, sh, L.mask.p, (unsigned long long*)d_nExact)
+#define SVB_LAUNCH_CF(OCC, DIR, FLAT) k_classify_filtered<OCC, DIR, FLAT><<<nb, VX_THREADS, 0, s>>>(S, st, sn, sf, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, sh, L.mask.p, (unsigned long long*)d_nExact, precheck)
 				if (allFlat) {   // box meshes: the general edge / plane filter is compiled out, 6 CTAs/SM without spills
 					const int o = occFlat;
 					if (directCentre) { if (o >= 8) SVB_LAUNCH_CF(8, true, true); else if (o == 7) SVB_LAUNCH_CF(7, true, true); else if (o == 6) SVB_LAUNCH_CF(6, true, true); else SVB_LAUNCH_CF(5, true, true); }
@@ -617,6 +616,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		const bool fuseS = fuseFlat && fuseSlowKids;   // also decide the flat children of slow-stream parents in place
 		const uint64_t cFe = fuseFlat ? 0 : cF;
 		const uint64_t Fn = cFe + (fuseS ? 0 : cSF), Fan = (Fn + 15) & ~15ull, Sn = cS - cSF, Pn = Fan + Sn;
+		const int precheckKids = forcePre >= 0 ? forcePre : ((cF + cS) > 2 * Nn ? 1 : 0);
 		{
 			// will this batch fit all the way down?  Surfaces grow ~4x per level; use the observed ratio.
 			const int remaining = (Lt - 1) - (l + 1);
@@ -656,7 +656,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 			static const int occLeaves = [] { const char* e = getenv("SVB_VX_OCC_LEAVES"); return e ? atoi(e) : 8; }();   // 8 CTAs/SM measured best
 #define SVB_LAUNCH_FL(DIR, N, OFF, ONLY) if (occLeaves >= 8) SVB_LAUNCH_FL2(DIR, 8, N, OFF, ONLY); else SVB_LAUNCH_FL2(DIR, 6, N, OFF, ONLY)
 #define SVB_LAUNCH_FL2(DIR, MB, N, OFF, ONLY) k_flat_leaves<DIR, MB><<<blocks_for(N, VX_THREADS), VX_THREADS, 0, s>>>(N, ptri.p + (OFF), pnode.p + (OFF), pflags.p + (OFF), hit.p + (OFF), \
-			L.code.p, L.mask.p, L.childBase.p, l + 1, kscale, d_tiles, d_tris, rootTri, C.mask.p, C.tstar.p, ONLY)
+			L.code.p, L.mask.p, L.childBase.p, l + 1, kscale, d_tiles, d_tris, rootTri, C.mask.p, C.tstar.p, ONLY, precheckKids)
 			if (F) { if (directCentre) SVB_LAUNCH_FL(true, F, 0, 0); else SVB_LAUNCH_FL(false, F, 0, 0); SVB_KERNEL_CHECK(); }
 			if (fuseS && S && cSF) { if (directCentre) SVB_LAUNCH_FL(true, S, Fa, 1); else SVB_LAUNCH_FL(false, S, Fa, 1); SVB_KERNEL_CHECK(); }
 #undef SVB_LAUNCH_FL
@@ -664,12 +664,12 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 			pairsTotal += cF + (fuseS ? cSF : 0);   // decided here instead of as pairs of the last level
 		} else if (F) {
 			k_emit<false><<<blocks_for(F, VX_TILE), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p,
-			                                                                ntri.p, nnode.p, nflags.p, C.tstar.p, 0);
+			                                                                ntri.p, nnode.p, nflags.p, C.tstar.p, 0, precheckKids);
 			SVB_KERNEL_CHECK();
 		}
 		if (S) {
 			k_emit<true><<<blocks_for(S, VX_TILE), VX_THREADS, 0, s>>>(S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, cFe, Fan, L.mask.p, L.childBase.p,
-			                                                               ntri.p, nnode.p, nflags.p, C.tstar.p, fuseS ? 1 : 0);
+			                                                               ntri.p, nnode.p, nflags.p, C.tstar.p, fuseS ? 1 : 0, precheckKids);
 			SVB_KERNEL_CHECK();
 		}
 		ptri = std::move(ntri);
