@@ -212,7 +212,8 @@ def main():
         oct_.set_triangles_ptr(pinned.data_ptr(), T)          # H2D from pinned host memory
         st = oct_.build(L, S, bbox=bbox, **shard)
         sd = oct_.to_sdag()
-        img = pkg.encoders.encode(oct_, "ssvdag")             # D2H of the SSVDAG levels + host encoding
+        # D2H of the SSVDAG levels + host encoding of the .ssvdag image: the file is written once, by rank 0
+        img = pkg.encoders.encode(oct_, "ssvdag") if rank == 0 else b""
         return st, sd, img
 
     def barrier():

@@ -4,7 +4,9 @@
 #include "octree_data.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <utility>
 
 namespace svbhost {
@@ -12,6 +14,17 @@ namespace svbhost {
 namespace {
 
 const uint32_t kNull = 0xFFFFFFFEu;
+
+// Threads of the encoder loops.  Not OMP_NUM_THREADS: launchers such as torchrun pin that to 1 for every rank, and the
+// file is written by one rank only.  SVB_ENCODE_THREADS overrides; default min(8, hardware threads).
+int encode_threads() {
+	static const int n = [] {
+		if (const char* e = getenv("SVB_ENCODE_THREADS")) { int v = atoi(e); if (v > 0) return v; }
+		unsigned hw = std::thread::hardware_concurrency();
+		return (int)std::max(1u, std::min(8u, hw ? hw : 1u));
+	}();
+	return n;
+}
 
 struct ByteSink {
 	std::vector<uint8_t>& v;
@@ -53,7 +66,7 @@ bool pointer_stream(const OctreeData& o, bool withMirrorHeader, std::vector<uint
 		const LevelSoA& lv = o.levels[l];
 		const bool hasCL = lv.childLevel.size() == lv.n * 8;
 		const uint32_t* wo = wordOf.data() + levelStart[l];
-#pragma omp parallel for schedule(static) if (lv.n > 65536)
+#pragma omp parallel for schedule(static) num_threads(encode_threads()) if (lv.n > 65536)
 		for (int64_t ii = 0; ii < (int64_t)lv.n; ++ii) {
 			const uint64_t i = (uint64_t)ii;
 			uint32_t head = lv.mask[i];
@@ -129,7 +142,7 @@ bool ssvdag(const OctreeData& o, std::vector<uint8_t>& out, std::string* err) {
 			static const LeafTables lut;
 			const LevelSoA& leaf = o.levels[lev + 1];
 			leaves.assign(cur.n * 8, 0);
-#pragma omp parallel for schedule(static) if (order.size() > 65536)
+#pragma omp parallel for schedule(static) num_threads(encode_threads()) if (order.size() > 65536)
 			for (int64_t rr = 0; rr < (int64_t)order.size(); ++rr) {
 				const uint32_t r = (uint32_t)rr;
 				uint32_t i = order[r].first;
@@ -147,7 +160,7 @@ bool ssvdag(const OctreeData& o, std::vector<uint8_t>& out, std::string* err) {
 			// pass 1: encoded size of every node (1 header + 1 or 2 shorts per child), pass 2: fill at the prefix offsets
 			std::vector<uint16_t>& enc = inner[lev];
 			std::vector<uint32_t> sz(order.size());
-#pragma omp parallel for schedule(static) if (order.size() > 65536)
+#pragma omp parallel for schedule(static) num_threads(encode_threads()) if (order.size() > 65536)
 			for (int64_t rr = 0; rr < (int64_t)order.size(); ++rr) {
 				uint32_t i = order[rr].first, n = 1;
 				for (int c = 7; c >= 0; --c) {
@@ -160,7 +173,7 @@ bool ssvdag(const OctreeData& o, std::vector<uint8_t>& out, std::string* err) {
 			uint64_t total = 0;
 			for (size_t r = 0; r < order.size(); ++r) { uint32_t n = sz[r]; sz[r] = (uint32_t)total; total += n; }
 			enc.assign(total, 0);
-#pragma omp parallel for schedule(static) if (order.size() > 65536)
+#pragma omp parallel for schedule(static) num_threads(encode_threads()) if (order.size() > 65536)
 			for (int64_t rr = 0; rr < (int64_t)order.size(); ++rr) {
 				uint32_t i = order[rr].first;
 				nextAddr[i] = sz[rr];
