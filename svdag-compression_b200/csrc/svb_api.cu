@@ -165,7 +165,8 @@ struct svb_build_state {
 	double rootSide = 0;
 	TileGeom rootG;
 	TileGridHost grid1;
-	DevBuf<int> dGrid1, dLocal1;
+	DevBuf<int> dGrid1, dLocal1;         // single root tile: grid cell -> tile 0, tile 0 -> position 0
+	DevBuf<int> dSelPos;                 // global tile_seq -> position in this rank's selection (-1: not ours); a batch is a range of positions
 	DevBuf<uint32_t> dSeq1;
 	// step mode
 	std::vector<BatchLevel> base;        // base octree levels 0..step (reduced last)
@@ -234,20 +235,17 @@ void dedup_batch(svb_ctx* c, BuildState& B, std::vector<BatchLevel>& lv, int Lt,
 // Voxelizes and reduces the sub-octrees sel[a..b) (indices into `tiles`, ascending).  Throws BatchTooBig
 // (before anything was reduced) when the batch must be cut.
 void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tiles, const std::vector<uint32_t>& sel, uint32_t a, uint32_t b,
-                    const TileGridHost& grid, const int* d_gridTile, int Lt, uint32_t gbase, uint64_t budget, uint64_t nodeCap,
+                    const TileGridHost& grid, const int* d_gridTile, const int* d_selPos, int Lt, uint32_t gbase, uint64_t budget, uint64_t nodeCap,
                     std::vector<BatchLevel>* keepLevels) {
 	cudaStream_t s = c->stream;
 	const uint32_t nt = b - a;
 	std::vector<TileGeom> hg(nt);
 	std::vector<uint32_t> hseq(nt);
-	std::vector<int> hlocal(tiles.size(), -1);
-	for (uint32_t i = 0; i < nt; ++i) { hg[i] = tiles[sel[a + i]].g; hseq[i] = sel[a + i]; hlocal[sel[a + i]] = (int)i; }
+	for (uint32_t i = 0; i < nt; ++i) { hg[i] = tiles[sel[a + i]].g; hseq[i] = sel[a + i]; }
 	DevBuf<TileGeom> dTiles;
 	DevBuf<uint32_t> dSeq;
-	DevBuf<int> dLocal;
 	upload(s, c->pool, dTiles, hg);
 	upload(s, c->pool, dSeq, hseq);
-	upload(s, c->pool, dLocal, hlocal);
 
 	std::vector<BatchLevel> lv;
 	DevBuf<uint32_t> dTileStart;   // per tile of the batch: first root-pair index (needed again by the order keys)
@@ -263,7 +261,7 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 			cellLo[0] = std::min(cellLo[0], th.ix); cellLo[1] = std::min(cellLo[1], th.iy); cellLo[2] = std::min(cellLo[2], th.iz);
 			cellHi[0] = std::max(cellHi[0], th.ix); cellHi[1] = std::max(cellHi[1], th.iy); cellHi[2] = std::max(cellHi[2], th.iz);
 		}
-		make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, dLocal.p, nt, ptri, pnode, rootTri, dTileStart, P, cellLo, cellHi);
+		make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, d_selPos, a, nt, ptri, pnode, rootTri, dTileStart, P, cellLo, cellHi);
 		bool direct = true;
 		for (uint32_t i = 0; i < nt && direct; ++i) direct = centre_chain_exact(hg[i], Lt);
 		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, rootTri.p, dTileStart.p, P, budget, nodeCap, lv, pairs, B.dExact.p, direct, B.allFlat);
@@ -311,7 +309,7 @@ void run_tiles_split(svb_ctx* c, BuildState& B, const std::vector<uint32_t>& sel
 	while (a < b) {
 		uint32_t e = plan.front();
 		try {
-			run_tile_batch(c, B, B.tiles, sel, a, e, B.grid, B.dGrid.p, Lt, gbase, budget, nodeCap, nullptr);
+			run_tile_batch(c, B, B.tiles, sel, a, e, B.grid, B.dGrid.p, B.dSelPos.p, Lt, gbase, budget, nodeCap, nullptr);
 			a = e;
 			plan.erase(plan.begin());
 		} catch (const BatchTooBig& x) {
@@ -378,6 +376,7 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 	B.grid1.G = 1; B.grid1.cell = rootSide > 0 ? rootSide : 1.0;
 	B.grid1.ox = B.rootG.cx - rootSide * 0.5; B.grid1.oy = B.rootG.cy - rootSide * 0.5; B.grid1.oz = B.rootG.cz - rootSide * 0.5;
 	B.dGrid1.reset(c->pool, 1); B.dGrid1.zero();
+	B.dLocal1.reset(c->pool, 1); B.dLocal1.zero();
 	std::vector<TileHost> rootTile(1);
 	rootTile[0].g = B.rootG; rootTile[0].baseNode = 0; rootTile[0].j = 0; rootTile[0].ix = rootTile[0].iy = rootTile[0].iz = 0;
 	const std::vector<uint32_t> sel0(1, 0);
@@ -388,7 +387,7 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 		B.tileBits = 1;
 		set_order_key_width(B, (int)L, B.tbits);
 		try {
-			run_tile_batch(c, B, rootTile, sel0, 0, 1, B.grid1, B.dGrid1.p, (int)L, 0, budget, 0, nullptr);
+			run_tile_batch(c, B, rootTile, sel0, 0, 1, B.grid1, B.dGrid1.p, B.dLocal1.p, (int)L, 0, budget, 0, nullptr);
 		} catch (const BatchTooBig&) {
 			throw Error(SVB_ENOMEM, "octree does not fit device memory in one piece; use step > 0");
 		}
@@ -398,7 +397,7 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 	B.s1 = s1;
 	// ---- base octree (levels 0..step) over all triangles, exact hierarchical tests (every rank, identical)
 	try {
-		run_tile_batch(c, B, rootTile, sel0, 0, 1, B.grid1, B.dGrid1.p, (int)s1, 0, budget, 0, &B.base);
+		run_tile_batch(c, B, rootTile, sel0, 0, 1, B.grid1, B.dGrid1.p, B.dLocal1.p, (int)s1, 0, budget, 0, &B.base);
 	} catch (const BatchTooBig&) {
 		throw Error(SVB_ENOMEM, "base octree does not fit device memory");
 	}
@@ -486,6 +485,11 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 	}
 	// leaf-level nodes one batch may hold: 32-bit indices, and ~40 bytes of transient state per leaf node
 	uint64_t nodeCap = std::min<uint64_t>(3600000000ull, (budget - c->pool.live) / 40);
+	{
+		std::vector<int> hpos(nTiles ? nTiles : 1, -1);
+		for (size_t i = 0; i < mine.size(); ++i) hpos[mine[i]] = (int)i;
+		upload(s, c->pool, B.dSelPos, hpos);
+	}
 	if (!mine.empty()) run_tiles_split(c, B, mine, Lt, s1, budget, nodeCap);
 }
 

@@ -46,7 +46,7 @@ __device__ inline void tile_range(double mn, double mx, double o, const GridDesc
 
 template <bool EMIT>
 __global__ void __launch_bounds__(VX_THREADS) k_candidates(const float* __restrict__ tris, uint64_t T, GridDesc g,
-                                                            const int* __restrict__ gridTile, const int* __restrict__ localOf, uint32_t* __restrict__ cnt_or_off,
+                                                            const int* __restrict__ gridTile, const int* __restrict__ selPos, int posFirst, int posCount, uint32_t* __restrict__ cnt_or_off,
                                                             uint32_t* __restrict__ ptri, uint32_t* __restrict__ pnode) {
 	uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= T) return;
@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(VX_THREADS) k_candidates(const float* __restri
 		for (int y = ay; y <= by; ++y)
 			for (int z = az; z <= bz; ++z) {
 				int s = gridTile[((size_t)x * g.G + y) * g.G + z];   // global tile_seq of the cell, -1 = no tile
-				int loc = (s >= 0) ? localOf[s] : -1;                // index inside this batch, -1 = other batch / other rank
+				int loc = (s >= 0) ? selPos[s] - posFirst : -1;      // index inside this batch; outside [0, posCount): other batch / other rank
+				if (loc >= posCount) loc = -1;
 				if (loc >= 0) {
 					if (EMIT) { ptri[o + c] = (uint32_t)t; pnode[o + c] = (uint32_t)loc; }
 					++c;
@@ -500,21 +501,21 @@ uint32_t max_candidates_per_tile(cudaStream_t s, Pool& pool, const float* d_tris
 }
 
 void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T, const TileGridHost& grid,
-                     const int* d_gridTile, const int* d_localOf, uint32_t ntiles, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode,
+                     const int* d_gridTile, const int* d_selPos, uint32_t posFirst, uint32_t ntiles, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode,
                      DevBuf<uint32_t>& rootTri, DevBuf<uint32_t>& tileStart, uint64_t& P, const int cellLo[3], const int cellHi[3]) {
 	GridDesc g = grid_desc(grid);
 	if (cellLo && cellHi) for (int k = 0; k < 3; ++k) { g.lo[k] = std::max(cellLo[k], 0); g.hi[k] = std::min(cellHi[k], grid.G - 1); }
 	DevBuf<uint32_t> cnt(pool, T);
 	DevBuf<uint64_t> tot(pool, 1);
 	unsigned nb = blocks_for(T, VX_THREADS);
-	k_candidates<false><<<nb, VX_THREADS, 0, s>>>(d_tris, T, g, d_gridTile, d_localOf, cnt.p, nullptr, nullptr);
+	k_candidates<false><<<nb, VX_THREADS, 0, s>>>(d_tris, T, g, d_gridTile, d_selPos, (int)posFirst, (int)ntiles, cnt.p, nullptr, nullptr);
 	SVB_KERNEL_CHECK();
 	scan_u32(s, pool, cnt.p, T, cnt.p, tot.p);
 	P = read_u64(s, tot.p);
 	if (P >= 0xFFFFFFF0ull) throw BatchTooBig();
 	ptri.reset(pool, P);
 	pnode.reset(pool, P);
-	k_candidates<true><<<nb, VX_THREADS, 0, s>>>(d_tris, T, g, d_gridTile, d_localOf, cnt.p, ptri.p, pnode.p);
+	k_candidates<true><<<nb, VX_THREADS, 0, s>>>(d_tris, T, g, d_gridTile, d_selPos, (int)posFirst, (int)ntiles, cnt.p, ptri.p, pnode.p);
 	SVB_KERNEL_CHECK();
 	// Sort the root pairs by (tile, triangle).  A pair and all its descendants are then identified by the index q of
 	// their root pair: triangle = rootTri[q], and q - tileStart[tile] is the rank of the triangle among the tile's

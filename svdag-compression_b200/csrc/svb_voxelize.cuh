@@ -21,9 +21,10 @@ struct TileGridHost {    // regular grid of tile cubes over the root cube (G = 2
 
 // (triangle, tile) candidate pairs for the tiles of one batch, sorted by (tile, triangle).  On return pnode[q] = tile
 // (index inside the batch), rootTri[q] = triangle, ptri[q] = q, tileStart[tile] = first q of the tile.
-// d_gridTile: grid cell -> global tile_seq (-1 none); d_localOf: global tile_seq -> index in the batch (-1 not in it).
+// d_gridTile: grid cell -> global tile_seq (-1 none); d_selPos: global tile_seq -> position in the caller's tile
+// selection (-1 none); the batch is the positions [posFirst, posFirst + ntiles).
 void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T, const TileGridHost& grid,
-                     const int* d_gridTile, const int* d_localOf, uint32_t ntiles, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode,
+                     const int* d_gridTile, const int* d_selPos, uint32_t posFirst, uint32_t ntiles, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode,
                      DevBuf<uint32_t>& rootTri, DevBuf<uint32_t>& tileStart, uint64_t& P, const int cellLo[3] = nullptr, const int cellHi[3] = nullptr);
 // (cellLo / cellHi: grid-cell bounding box of the batch's tiles; triangles that cannot reach it are skipped early)
 
