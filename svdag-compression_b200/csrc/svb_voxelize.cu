@@ -569,7 +569,8 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		if (F + S > (1ull << 59)) throw Error(SVB_ERANGE, "too many pairs");
 		const double kscale = ldexp(1.0, -(l + 2));
 		static const int forcePre = [] { const char* e = getenv("SVB_PRECHECK"); return e ? atoi(e) : -1; }();
-		const int precheck = forcePre >= 0 ? forcePre : ((F + S) > 2 * L.n ? 1 : 0);   // read-before-atomic only where many pairs share a node
+		static const uint64_t preRatio10 = [] { const char* e = getenv("SVB_PRECHECK_RATIO10"); return (uint64_t)(e ? atoi(e) : 20); }();
+		const int precheck = forcePre >= 0 ? forcePre : (10 * (F + S) > preRatio10 * L.n ? 1 : 0);   // read-before-atomic only where many pairs share a node
 		if (F) {
 			unsigned nb = blocks_for(F, VX_THREADS);
 			if (directCentre) k_classify_fast<true><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, hit.p, L.mask.p, precheck);
@@ -617,7 +618,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		const bool fuseS = fuseFlat && fuseSlowKids;   // also decide the flat children of slow-stream parents in place
 		const uint64_t cFe = fuseFlat ? 0 : cF;
 		const uint64_t Fn = cFe + (fuseS ? 0 : cSF), Fan = (Fn + 15) & ~15ull, Sn = cS - cSF, Pn = Fan + Sn;
-		const int precheckKids = forcePre >= 0 ? forcePre : ((cF + cS) > 2 * Nn ? 1 : 0);
+		const int precheckKids = forcePre >= 0 ? forcePre : (10 * (cF + cS) > preRatio10 * Nn ? 1 : 0);
 		{
 			// will this batch fit all the way down?  Surfaces grow ~4x per level; use the observed ratio.
 			const int remaining = (Lt - 1) - (l + 1);
