@@ -137,10 +137,6 @@ __global__ void k_self_target(uint64_t n, int l, unsigned long long* t) {
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) t[i] = ((unsigned long long)l << 32) | i;
 }
-__global__ void k_mask_to_u32(uint64_t n, const uint8_t* m, uint32_t* o) {
-	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) o[i] = m[i];
-}
 
 }  // namespace
 

@@ -229,8 +229,6 @@ struct OutLevel {
 // ------------------------------------------------------------------ primitives (svb_prims.cu)
 // exclusive scan of popcount(bytes[i]) -> out[i] (uint32), returns total through *d_total (device, u64)
 void scan_popc8(cudaStream_t s, Pool& pool, const uint8_t* bytes, uint64_t n, uint32_t* out, uint64_t* d_total);
-// same, counting only the pairs whose flags make their children "fast" pairs (pair_is_fast, svb_classify.cuh)
-void scan_popc8_fast(cudaStream_t s, Pool& pool, const uint8_t* bytes, const uint16_t* flags, uint64_t n, uint32_t* out, uint64_t* d_total);
 // Tile-granular scans (tiles of scan_tile_items() consecutive items): only the exclusive offset of every tile is
 // produced; the consumer kernels (k_children / k_emit in svb_voxelize.cu) rebuild the per-item offsets inside the CTA.
 uint64_t scan_tile_items();

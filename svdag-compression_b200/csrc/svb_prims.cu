@@ -32,27 +32,6 @@ struct Popc8In {
 		}
 	}
 };
-// popcount(hit[i]) where the pair's (updated) flags make its children "fast" pairs, else 0 (svb_classify.cuh)
-struct PopcFastIn {
-	const uint8_t* p;
-	const uint16_t* fl;
-	__device__ void load(uint64_t base, uint64_t n, uint32_t v[SCAN_ITEMS]) const {
-		if (base + SCAN_ITEMS <= n) {
-			uint2 w = *reinterpret_cast<const uint2*>(p + base);     // base is a multiple of 8, p and fl 16B aligned
-			uint4 f = *reinterpret_cast<const uint4*>(fl + base);
-			const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-			for (int i = 0; i < SCAN_ITEMS; ++i) {
-				uint32_t h = ((i < 4 ? w.x : w.y) >> (8 * (i & 3))) & 0xFF;
-				uint32_t g = (fw[i >> 1] >> (16 * (i & 1))) & 0xFFFF;
-				v[i] = pair_is_fast(g) ? __popc(h) : 0;
-			}
-		} else {
-#pragma unroll
-			for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = (base + i < n && pair_is_fast(fl[base + i])) ? __popc((uint32_t)p[base + i]) : 0;
-		}
-	}
-};
 struct U32In {
 	const uint32_t* p;
 	__device__ void load(uint64_t base, uint64_t n, uint32_t v[SCAN_ITEMS]) const {
@@ -280,9 +259,6 @@ void scan_tiles_pairs(cudaStream_t s, Pool& pool, const uint8_t* hit, const uint
 	SVB_KERNEL_CHECK();
 }
 
-void scan_popc8_fast(cudaStream_t s, Pool& pool, const uint8_t* bytes, const uint16_t* flags, uint64_t n, uint32_t* out, uint64_t* d_total) {
-	scan_impl(s, pool, PopcFastIn{bytes, flags}, n, out, d_total);
-}
 void scan_u32(cudaStream_t s, Pool& pool, const uint32_t* in, uint64_t n, uint32_t* out, uint64_t* d_total) {
 	scan_impl(s, pool, U32In{in}, n, out, d_total);
 }
