@@ -7,6 +7,7 @@
 #pragma once
 #include <stdint.h>
 
+#include <algorithm>
 #include <cmath>
 
 #include "svb_sat.cuh"
@@ -398,5 +399,29 @@ SVB_HD unsigned classify_pair(const uint64_t cd, const int l, const double* __re
 }
 #undef SVB_LO
 #undef SVB_HI
+
+// ------------------------------------------------------------------ host: is the centre chain exact?
+// True when every partial sum of the centre chain (geom_octree.cpp:222-230) of a sub-octree with root centre
+// (cx,cy,cz), root side `rootSide` and `Lt` levels is a representable double: all partial sums are integer multiples of
+// 2^ge (ge = the lowest set bit among the centre coordinates and the finest half side) bounded by |centre| + rootSide,
+// hence representable iff that bound is <= 2^53 * 2^ge.  Then every rounding of the chain is the identity and the
+// kernels may evaluate node centres in closed form (centre_axis_direct).
+inline int low_bit_exp(double x) {   // exponent of the lowest set bit of a finite double (x = odd * 2^e); 0 -> huge
+	if (x == 0.0) return 1 << 20;
+	int e;
+	double m = std::frexp(std::fabs(x), &e);          // x = m * 2^e, m in [0.5,1)
+	uint64_t mi = (uint64_t)std::ldexp(m, 53);        // 53-bit integer mantissa
+	return e - 53 + __builtin_ctzll(mi);
+}
+inline bool centre_chain_exact(const TileGeom& g, int Lt) {
+	if (!(g.rootSide > 0.0) || !std::isfinite(g.rootSide) || Lt < 1 || Lt > 20) return false;
+	const double kFinest = std::ldexp(g.rootSide, -(Lt + 1));   // half side of the deepest children (level Lt-1 nodes test C +- k)
+	if (kFinest < 1e-290) return false;
+	int ge = low_bit_exp(kFinest);
+	ge = std::min(ge, std::min(low_bit_exp(g.cx), std::min(low_bit_exp(g.cy), low_bit_exp(g.cz))));
+	const double span = std::max(std::fabs(g.cx), std::max(std::fabs(g.cy), std::fabs(g.cz))) + g.rootSide;
+	if (!std::isfinite(span)) return false;
+	return std::ldexp(span, -ge) <= 9007199254740992.0;
+}
 
 }  // namespace svb

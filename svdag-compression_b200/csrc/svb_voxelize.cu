@@ -435,29 +435,6 @@ __global__ void __launch_bounds__(VX_THREADS) k_all_flat(const float* __restrict
 }
 
 // ------------------------------------------------------------------ host drivers
-namespace {
-// exponent of the lowest set bit of a finite double (x = odd * 2^e); 0 -> +inf-like sentinel
-int low_bit_exp(double x) {
-	if (x == 0.0) return 1 << 20;
-	int e;
-	double m = frexp(fabs(x), &e);               // x = m * 2^e, m in [0.5,1)
-	uint64_t mi = (uint64_t)ldexp(m, 53);        // 53-bit integer mantissa
-	return e - 53 + __builtin_ctzll(mi);
-}
-}  // namespace
-
-bool centre_chain_exact(const TileGeom& g, int Lt) {
-	if (!(g.rootSide > 0.0) || !std::isfinite(g.rootSide) || Lt < 1 || Lt > 20) return false;
-	const double kFinest = ldexp(g.rootSide, -(Lt + 1));   // half side of the deepest children (level Lt-1 nodes test C +- k)
-	if (kFinest < 1e-290) return false;
-	int ge = low_bit_exp(kFinest);
-	ge = std::min(ge, std::min(low_bit_exp(g.cx), std::min(low_bit_exp(g.cy), low_bit_exp(g.cz))));
-	const double span = std::max(fabs(g.cx), std::max(fabs(g.cy), fabs(g.cz))) + g.rootSide;
-	if (!std::isfinite(span)) return false;
-	// every partial sum is an integer multiple of 2^ge with magnitude <= span: representable iff span / 2^ge <= 2^53
-	return ldexp(span, -ge) <= 9007199254740992.0;
-}
-
 static GridDesc grid_desc(const TileGridHost& grid) {
 	GridDesc g;
 	g.ox = grid.ox; g.oy = grid.oy; g.oz = grid.oz;

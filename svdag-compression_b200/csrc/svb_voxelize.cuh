@@ -1,5 +1,6 @@
 // svb_voxelize.cuh -- host-side entry points of the voxelizer (svb_voxelize.cu).
 #pragma once
+#include "svb_classify.cuh"
 #include "svb_internal.cuh"
 
 namespace svb {
@@ -40,9 +41,6 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 // true when every triangle is flat (box meshes): selects the slow-stream kernel without the general edge / plane filter
 bool all_triangles_flat(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T);
 
-// True when every partial sum of the centre chain (geom_octree.cpp:222-230) of a sub-octree with root centre
-// (cx,cy,cz), root side `rootSide` and `Lt` levels is a representable double, i.e. the chain is exact and the
-// kernels may evaluate node centres in closed form (see centre_axis_direct in svb_voxelize.cu).
-bool centre_chain_exact(const TileGeom& g, int Lt);
+// (centre_chain_exact(): svb_classify.cuh)
 
 }  // namespace svb

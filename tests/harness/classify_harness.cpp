@@ -82,4 +82,10 @@ int harness_run(const float* tris, uint64_t T, const double centre[3], double ro
 	return 0;
 }
 
+// host-side decision whether the kernels may use closed-form node centres (svb_classify.cuh::centre_chain_exact)
+int harness_chain_exact(const double centre[3], double rootSide, int Lt) {
+	svb::TileGeom tg{centre[0], centre[1], centre[2], rootSide};
+	return svb::centre_chain_exact(tg, Lt) ? 1 : 0;
+}
+
 }  // extern "C"

@@ -24,6 +24,7 @@ def harness():
                         str(SRC), "-o", str(OUT)], check=True)
     L = C.CDLL(str(OUT))
     L.harness_run.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.harness_chain_exact.argtypes = [C.c_void_p, C.c_double, C.c_int]
     return L
 
 
@@ -83,3 +84,38 @@ def test_filter_equals_predicate_full_double_bbox(harness, meshgen):
     lo, hi = v.min(axis=0) - np.array([0.1, 0.2, 0.3]) / 3.0, v.max(axis=0) + np.array([0.7, 0.1, 0.05]) / 7.0
     r = _run(harness, tris, lo, hi, 8, False)
     assert r["bad"] == 0, r
+
+
+def _chain_partial_sums_exact(centre, root_side, levels):
+    """Brute force with exact rational arithmetic: is every partial sum c0 + sum(+-k_j) a representable double?"""
+    from fractions import Fraction
+    for c0 in centre:
+        for signs in ((1,) * (levels + 1), (-1,) * (levels + 1), tuple((-1) ** j for j in range(levels + 1))):
+            acc, k = Fraction(c0), Fraction(root_side) / 4
+            for j in range(levels + 1):        # levels steps of the chain + the child step
+                acc += signs[j] * k
+                if Fraction(float(acc)) != acc:
+                    return False
+                k /= 2
+    return True
+
+
+@pytest.mark.parametrize("centre,side,levels", [
+    ((0.5, 0.5, 0.5), 1.0, 16),                                   # unit cube, 64K^3
+    ((13.149999618530273, -3.6499998569488525, 5.550000190734863), 5.300000190734863, 14),   # float scene bbox
+    ((0.1, 0.2, 0.3), 1.0, 9),                                    # full 53-bit doubles: the chain rounds
+    ((1e6 + 1 / 3.0, 2.0, 3.0), 0.37, 12),                        # large offset + full mantissa
+    ((12345.678, -0.001, 7.0), 1e-3, 10),                         # tiny cube far from the origin
+    ((0.0, 0.0, 0.0), 3.0, 20),
+])
+def test_chain_exactness_predicate_is_sound(harness, centre, side, levels):
+    """centre_chain_exact() may say "no" too often, never "yes" wrongly: whenever it allows closed-form centres, every
+    partial sum of the chain must be a representable double (checked with exact rationals)."""
+    c = np.ascontiguousarray(centre, dtype=np.float64)
+    says = bool(harness.harness_chain_exact(c.ctypes.data, float(np.float32(side)), levels))
+    truth = _chain_partial_sums_exact([float(x) for x in c], float(np.float32(side)), levels)
+    assert not (says and not truth), (centre, side, levels)
+    if centre == (0.5, 0.5, 0.5):
+        assert says
+    if centre == (0.1, 0.2, 0.3):
+        assert not says
