@@ -259,8 +259,13 @@ def _simulate_ranks(pkg, tris, levels, step, world):
     ("city", dict(lots=8), 9, 3, 4),
     ("terrain", dict(n=64), 9, 2, 8),
     ("sphere_menger", dict(n_lat=32, n_lon=64, sponge_level=2), 8, 5, 3),   # 2-level sub-octrees: roots are the K64 level
-], ids=["sphere-w2", "city-w4", "terrain-w8", "spongeball-w3"])
-def test_sharded_protocol_equals_single_gpu_build(pkg, meshgen, mesh, kw, levels, step, world):
+    ("sphere", dict(n_lat=32, n_lon=64), 7, 5, 2),                           # 1-level sub-octrees: roots are voxel masks
+    ("city", dict(lots=8), 9, 2, 8),                                         # SVB_SHARD=octant (see below)
+    ("soup", dict(n=400, seed=7), 8, 2, 5),
+], ids=["sphere-w2", "city-w4", "terrain-w8", "spongeball-w3", "sphere-leafroots-w2", "city-octant-w8", "soup-w5"])
+def test_sharded_protocol_equals_single_gpu_build(pkg, meshgen, mesh, kw, levels, step, world, monkeypatch, request):
+    if "octant" in request.node.callspec.id:
+        monkeypatch.setenv("SVB_SHARD", "octant")    # the pure top-level-octant split BASELINE.json names (unbalanced for flat scenes)
     tris = meshgen.make_mesh(mesh, **kw)
     ref = pkg.GeomOctree(tris)
     sref = ref.build(levels, step)
