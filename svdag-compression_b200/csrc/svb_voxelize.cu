@@ -502,7 +502,8 @@ void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T
 	tileStart.zero();
 	if (P) {
 		DevBuf<uint64_t> keys(pool, P);
-		DevBuf<uint32_t> dummy(pool, P);
+		DevBuf<uint32_t> dummy(pool, P);   // payload of the pair sort: unused, zeroed so that the sort never reads uninitialised memory
+		dummy.zero();
 		unsigned pb = blocks_for(P, VX_THREADS);
 		k_root_keys<<<pb, VX_THREADS, 0, s>>>(P, ptri.p, pnode.p, keys.p);
 		SVB_KERNEL_CHECK();
