@@ -20,3 +20,5 @@ PY
 timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 3 --print-limit 20 python /tmp/san.py 2>&1 | tail -12
 timeout 1200 compute-sanitizer --tool initcheck --error-exitcode 3 --print-limit 3 python /tmp/san.py 2>&1 | grep -v 'Host Frame: .*python\|Host Frame: _Py\|Host Frame: Py\|ffi\|ctypes' | head -60
 echo "exit: ${PIPESTATUS[0]}"
+timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 3 --print-limit 5 python /tmp/san.py 2>&1 | tail -4
+timeout 1200 compute-sanitizer --tool synccheck --error-exitcode 3 --print-limit 5 python /tmp/san.py 2>&1 | tail -3
