@@ -247,24 +247,53 @@ SVB_HD void flat_leaf_masks(const uint64_t cd, const int l, const double* __rest
 	}
 }
 
-// Flat triangle (all vertices share coordinate A bitwise) whose box axes are already decided exactly (`alive`): the
-// only tests left are the A-type cross axes of its three edges -- a 2-D triangle-vs-square problem in the plane (U, W).
-// Same interval filter as the general path (edge_axis), on 6 instead of 9 vertex offsets and without the plane.
+// Flat triangle (all vertices share coordinate A bitwise) in the slow stream: everything that is left of the predicate
+// is (1) the exact 1-D box tests of the unsettled axes and (2) the A-type cross axes of the three edges -- a 2-D
+// triangle-vs-square problem in the plane (U, W).  One routine with the axes known at compile time: the six in-plane
+// vertex coordinates and the node centre are fetched / computed once and serve both parts.  The edge part is the same
+// interval filter as the general path (edge_axis), on 6 instead of 9 vertex offsets and without the plane:
 // p = e_W * v_U - e_U * v_W up to a sign the symmetric test does not see (X: ez*vy - ey*vz, Y: -ez*vx + ex*vz,
 // Z: ey*vx - ex*vy, test_triangle_box.cpp:60-102); projected vertex pair = {an endpoint, the opposite vertex}.
-template <bool DIRECT, int A>
-SVB_HD unsigned classify_flat2d(const uint64_t cd, const int l, const double* __restrict__ tg4, const double k, const float* __restrict__ tp,
-                                unsigned& fl, unsigned alive, unsigned& nUnsure) {
+// LAST: the pair has no children, so nothing needs to be settled for them.
+template <bool DIRECT, int A, bool LAST>
+SVB_HD unsigned classify_flat_slow(const uint64_t cd, const int l, const double* __restrict__ tg4, const double k, const float* __restrict__ tp,
+                                   unsigned& fl, unsigned& nUnsure) {
 	constexpr int U = (A == 0) ? 1 : 0, W = (A == 2) ? 1 : 2;
 	constexpr unsigned BITU = (U == 0) ? 4u : 2u, BITW = (W == 2) ? 1u : 2u;
-	constexpr unsigned E0 = 1u << A, E1 = 8u << A, E2 = 64u << A;
+	constexpr unsigned E0 = 1u << A, E1 = 8u << A, E2 = 64u << A, EALL = E0 | E1 | E2;
+	constexpr unsigned BA = 1u << (FL_BOX + A), BU = 1u << (FL_BOX + U), BW = 1u << (FL_BOX + W);
 	const uint64_t path = cd & ((1ull << (3 * l)) - 1);
+	const double k2 = k + k;
+	unsigned alive = 0xFFu;
+	// ---- flat axis: one coordinate, never settles
+	{
+		const double CA = DIRECT ? centre_axis_direct(path, l, 2 - A, tg4[A], k) : centre_axis_chain(cd, l, 2 - A, tg4[A], tg4[3]);
+		const double ta = (double)tp[A];
+		alive &= box_axis_children(A, CA, k, ta, ta);
+		if (!alive) return 0;
+	}
+	const bool needEdges = (fl & EALL) != EALL;
+	if (!needEdges && (fl & (BU | BW)) == (BU | BW)) return alive;   // (such a pair belongs to the flat stream; kept for completeness)
+	const float fu0 = tp[U], fu1 = tp[3 + U], fu2 = tp[6 + U], fw0 = tp[W], fw1 = tp[3 + W], fw2 = tp[6 + W];
 	const double CU = DIRECT ? centre_axis_direct(path, l, 2 - U, tg4[U], k) : centre_axis_chain(cd, l, 2 - U, tg4[U], tg4[3]);
 	const double CW = DIRECT ? centre_axis_direct(path, l, 2 - W, tg4[W], k) : centre_axis_chain(cd, l, 2 - W, tg4[W], tg4[3]);
-	const double u0 = (double)tp[U] - CU, w0 = (double)tp[W] - CW;
-	const double u1 = (double)tp[3 + U] - CU, w1 = (double)tp[3 + W] - CW;
-	const double u2 = (double)tp[6 + U] - CU, w2 = (double)tp[6 + W] - CW;
-	const double M = fmax(fmax(fmax(fabs(u0), fabs(w0)), fmax(fabs(u1), fabs(w1))), fmax(fabs(u2), fabs(w2))) + (k + k);
+	// ---- in-plane box axes (exact; min / max on the float inputs: fl(t - c) is monotone in t)
+	if (!(fl & BU)) {
+		const double dmin = (double)fminf(fu0, fminf(fu1, fu2)), dmax = (double)fmaxf(fu0, fmaxf(fu1, fu2));
+		alive &= box_axis_children(U, CU, k, dmin, dmax);
+		if (!LAST && box_axis_settled(CU, k2, dmin, dmax)) fl |= BU;
+	}
+	if (!(fl & BW)) {
+		const double dmin = (double)fminf(fw0, fminf(fw1, fw2)), dmax = (double)fmaxf(fw0, fmaxf(fw1, fw2));
+		alive &= box_axis_children(W, CW, k, dmin, dmax);
+		if (!LAST && box_axis_settled(CW, k2, dmin, dmax)) fl |= BW;
+	}
+	if (!alive || !needEdges) return alive;
+	// ---- in-plane edge axes (filter, then the reference-order predicate for children within the tolerance band)
+	const double u0 = (double)fu0 - CU, w0 = (double)fw0 - CW;
+	const double u1 = (double)fu1 - CU, w1 = (double)fw1 - CW;
+	const double u2 = (double)fu2 - CU, w2 = (double)fw2 - CW;
+	const double M = fmax(fmax(fmax(fabs(u0), fabs(w0)), fmax(fabs(u1), fabs(w1))), fmax(fabs(u2), fabs(w2))) + k2;
 	const double tol2 = M * (M * 9.094947017729282e-13);
 	unsigned unsure = 0;
 	if (!(fl & E0)) edge_axis<BITU, BITW>(E0, w1 - w0, -(u1 - u0), u0, w0, u2, w2, k, tol2, alive, unsure, fl);                // edge 0: v0 -> v1, opposite v2
@@ -286,7 +315,7 @@ SVB_HD unsigned classify_flat2d(const uint64_t cd, const int l, const double* __
 // pairs).  nUnsure: children that had to be re-decided by the reference-order predicate.  Returns the hit mask.
 // FLATONLY: the caller guarantees that every triangle of the scene is flat (a box mesh); the general edge / plane
 // filter is then compiled out, which is what lets the kernel fit 40 registers.
-template <bool DIRECT, bool FLATONLY = false>
+template <bool DIRECT, bool FLATONLY = false, bool LAST = false>
 SVB_HD unsigned classify_pair(const uint64_t cd, const int l, const double* __restrict__ tg4, const double kscale, const float* __restrict__ tp,
                               unsigned& fl, unsigned& nUnsure) {
 	nUnsure = 0;
@@ -321,19 +350,19 @@ SVB_HD unsigned classify_pair(const uint64_t cd, const int l, const double* __re
 		fl |= FL_INIT;
 	}
 	const bool planeImplied = (fl & (7u << FL_FLAT)) != 0;
+	if (planeImplied) {
+		// flat triangle: box axes + in-plane edge axes in one routine with compile-time axes.  (A triangle flat on two
+		// axes is a segment: all nine edge axes are settled statically, so it is a flat-stream pair -- handled above.)
+		if (fl & (1u << (FL_FLAT + 0))) return classify_flat_slow<DIRECT, 0, LAST>(cd, l, tg4, k, tp, fl, nUnsure);
+		if (fl & (1u << (FL_FLAT + 1))) return classify_flat_slow<DIRECT, 1, LAST>(cd, l, tg4, k, tp, fl, nUnsure);
+		return classify_flat_slow<DIRECT, 2, LAST>(cd, l, tg4, k, tp, fl, nUnsure);
+	}
+	if (FLATONLY) return 0;   // unreachable under the caller's guarantee
 	// ---- box axes: the reference's own 1-D tests at the chain-rounded child centres -- exact, so a wall lying in a
 	//      voxel face (a tie on a box axis) never needs the full predicate
 	unsigned alive = box_axes_exact<DIRECT>(cd, l, tg4, k, tp, fl);   // (tp, not tf: dynamic axis index)
 	unsigned unsure = 0;
 	if (!alive) return 0;
-	if (planeImplied) {
-		if ((fl & 0x1FFu) == 0x1FFu) return alive;   // nothing but box axes left (the pair joins the flat stream)
-		// (a triangle flat on two axes is a segment: all nine edge axes are settled statically, handled above)
-		if (fl & (1u << (FL_FLAT + 0))) return classify_flat2d<DIRECT, 0>(cd, l, tg4, k, tp, fl, alive, nUnsure);
-		if (fl & (1u << (FL_FLAT + 1))) return classify_flat2d<DIRECT, 1>(cd, l, tg4, k, tp, fl, alive, nUnsure);
-		return classify_flat2d<DIRECT, 2>(cd, l, tg4, k, tp, fl, alive, nUnsure);
-	}
-	if (FLATONLY) return 0;   // unreachable under the caller's guarantee
 	double Cx, Cy, Cz;
 	if (DIRECT) {
 		Cx = centre_axis_direct(path, l, 2, tg4[0], k);

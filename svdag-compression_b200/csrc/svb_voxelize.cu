@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(VX_THREADS) k_classify(uint64_t P, const uint3
 // ------------------------------------------------------------------ classify, filtered (default)
 // One thread per pair decides all 8 children with classify_pair() (svb_classify.cuh): exact single-axis fast path
 // for settled flat triangles, FP64 interval filter + reference-order predicate for the rest.
-template <int MINB, bool DIRECT, bool FLATONLY>
+template <int MINB, bool DIRECT, bool FLATONLY, bool LAST>
 __global__ void __launch_bounds__(VX_THREADS, MINB) k_classify_filtered(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
                                                                    uint16_t* __restrict__ pflags, const uint64_t* __restrict__ code, int l, double kscale, int last,
                                                                    const TileGeom* __restrict__ tiles, const float* __restrict__ tris, const uint32_t* __restrict__ rootTri,
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_classify_filtered(uint64_t
 	unsigned fl = fl0, nUnsure;
 	const uint64_t cd = code[n];
 	const double* tg = reinterpret_cast<const double*>(tiles + (uint32_t)(cd >> (3 * l)));   // {cx, cy, cz, rootSide}
-	const unsigned m = classify_pair<DIRECT, FLATONLY>(cd, l, tg, kscale, tris + 9ull * t, fl, nUnsure);
+	const unsigned m = classify_pair<DIRECT, FLATONLY, LAST>(cd, l, tg, kscale, tris + 9ull * t, fl, nUnsure);
 	if (nUnsure && nExact) atomicAdd(nExact, (unsigned long long)nUnsure);
 	if (!last) {
 		hit[p] = (uint8_t)m;
@@ -534,7 +534,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 	DevBuf<uint16_t> pflags(pool, P + 16);   // settled-axis flags per pair (svb_classify.cuh)
 	pflags.zero();
 	const bool exactOnly = classify_exact_only();
-	static const int occFlat = [] { const char* e = getenv("SVB_VX_OCC_FLAT"); return e ? atoi(e) : 8; }();   // measured on B200: 8 (32 registers, spills) beats 6 and 5: the kernel is latency bound
+	static const int occFlat = [] { const char* e = getenv("SVB_VX_OCC_FLAT"); return e ? atoi(e) : 6; }();   // 6 or 8 CTAs/SM (40 / 32 registers, spills) beat 5 on B200: the kernel is latency bound
 	static const int occ = [] { const char* e = getenv("SVB_VX_OCC"); return e ? atoi(e) : 5; }();   // CTAs/SM of the slow classify kernel: 5 (48 registers, some spills) measured best on B200
 	for (int l = 0; l < Lt; ++l) {
 		BatchLevel& L = lv[l];
@@ -561,19 +561,17 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 				k_classify<<<blocks_for(S * 8, VX_THREADS), VX_THREADS, 0, s>>>(S, st, sn, L.code.p, l, d_tiles, d_tris, rootTri, sh, L.mask.p, last);
 			else {
 				unsigned nb = blocks_for(S, VX_THREADS);
-#define SVB_LAUNCH_CF(OCC, DIR, FLAT) k_classify_filtered<OCC, DIR, FLAT><<<nb, VX_THREADS, 0, s>>>(S, st, sn, sf, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, sh, L.mask.p, (unsigned long long*)d_nExact, precheck)
-				if (allFlat) {   // box meshes: the general edge / plane filter is compiled out, 6 CTAs/SM without spills
-					const int o = occFlat;
-					if (directCentre) { if (o >= 8) SVB_LAUNCH_CF(8, true, true); else if (o == 7) SVB_LAUNCH_CF(7, true, true); else if (o == 6) SVB_LAUNCH_CF(6, true, true); else SVB_LAUNCH_CF(5, true, true); }
-					else { if (o >= 8) SVB_LAUNCH_CF(8, false, true); else if (o == 7) SVB_LAUNCH_CF(7, false, true); else if (o == 6) SVB_LAUNCH_CF(6, false, true); else SVB_LAUNCH_CF(5, false, true); }
-				} else if (directCentre) {
-					if (occ >= 6) SVB_LAUNCH_CF(6, true, false); else if (occ == 5) SVB_LAUNCH_CF(5, true, false); else if (occ == 4) SVB_LAUNCH_CF(4, true, false);
-					else if (occ == 3) SVB_LAUNCH_CF(3, true, false); else SVB_LAUNCH_CF(1, true, false);
+#define SVB_LAUNCH_CF3(OCC, DIR, FLAT, LST) k_classify_filtered<OCC, DIR, FLAT, LST><<<nb, VX_THREADS, 0, s>>>(S, st, sn, sf, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, sh, L.mask.p, (unsigned long long*)d_nExact, precheck)
+#define SVB_LAUNCH_CF2(OCC, DIR, FLAT) do { if (last) SVB_LAUNCH_CF3(OCC, DIR, FLAT, true); else SVB_LAUNCH_CF3(OCC, DIR, FLAT, false); } while (0)
+#define SVB_LAUNCH_CF(OCC, FLAT) do { if (directCentre) SVB_LAUNCH_CF2(OCC, true, FLAT); else SVB_LAUNCH_CF2(OCC, false, FLAT); } while (0)
+				if (allFlat) {   // box meshes: the general edge / plane filter is compiled out
+					if (occFlat >= 8) SVB_LAUNCH_CF(8, true); else SVB_LAUNCH_CF(6, true);
 				} else {
-					if (occ >= 6) SVB_LAUNCH_CF(6, false, false); else if (occ == 5) SVB_LAUNCH_CF(5, false, false); else if (occ == 4) SVB_LAUNCH_CF(4, false, false);
-					else if (occ == 3) SVB_LAUNCH_CF(3, false, false); else SVB_LAUNCH_CF(1, false, false);
+					if (occ >= 6) SVB_LAUNCH_CF(6, false); else if (occ == 5) SVB_LAUNCH_CF(5, false); else SVB_LAUNCH_CF(4, false);
 				}
 #undef SVB_LAUNCH_CF
+#undef SVB_LAUNCH_CF2
+#undef SVB_LAUNCH_CF3
 			}
 			SVB_KERNEL_CHECK();
 		}

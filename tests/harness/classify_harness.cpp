@@ -19,11 +19,10 @@ extern "C" {
 
 // out[0] pairs tested, out[1] mismatching pairs, out[2] fast-path pairs, out[3] children re-decided exactly,
 // out[4..9] first mismatch: level, tri, code, got, want, flags-in
-int harness_run(const float* tris, uint64_t T, const double centre[3], double rootSide, int Lt, int direct, int chainExactClaim, uint64_t* out) {
+int harness_run(const float* tris, uint64_t T, const double centre[3], double rootSide, int Lt, int direct, int flatOnly, uint64_t* out) {
 	using namespace svb;
 	TileGeom tg{centre[0], centre[1], centre[2], rootSide};
 	memset(out, 0, 10 * sizeof(uint64_t));
-	(void)chainExactClaim;
 	std::vector<Pair> cur, nxt;
 	cur.reserve(T);
 	for (uint64_t t = 0; t < T; ++t) cur.push_back(Pair{(uint32_t)t, 0ull, 0});
@@ -34,7 +33,16 @@ int harness_run(const float* tris, uint64_t T, const double centre[3], double ro
 			unsigned fl = p.fl, nUnsure = 0;
 			const float* tp = tris + 9ull * p.tri;
 			const double tgv[4] = {tg.cx, tg.cy, tg.cz, tg.rootSide};
-			unsigned m = direct ? classify_pair<true>(p.code, l, tgv, kscale, tp, fl, nUnsure) : classify_pair<false>(p.code, l, tgv, kscale, tp, fl, nUnsure);
+			const bool lastLevel = (l == Lt - 1);
+			unsigned m;
+			// every template variant the kernels instantiate: closed-form / chain centres x box-mesh variant x last level
+			if (flatOnly) {
+				if (direct) m = lastLevel ? classify_pair<true, true, true>(p.code, l, tgv, kscale, tp, fl, nUnsure) : classify_pair<true, true, false>(p.code, l, tgv, kscale, tp, fl, nUnsure);
+				else m = lastLevel ? classify_pair<false, true, true>(p.code, l, tgv, kscale, tp, fl, nUnsure) : classify_pair<false, true, false>(p.code, l, tgv, kscale, tp, fl, nUnsure);
+			} else {
+				if (direct) m = lastLevel ? classify_pair<true, false, true>(p.code, l, tgv, kscale, tp, fl, nUnsure) : classify_pair<true, false, false>(p.code, l, tgv, kscale, tp, fl, nUnsure);
+				else m = lastLevel ? classify_pair<false, false, true>(p.code, l, tgv, kscale, tp, fl, nUnsure) : classify_pair<false, false, false>(p.code, l, tgv, kscale, tp, fl, nUnsure);
+			}
 			if (pair_is_fast(p.fl)) out[2]++;
 			out[3] += nUnsure;
 			// reference: chain centre of the node, then each child centre, then the predicate

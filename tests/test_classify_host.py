@@ -28,13 +28,13 @@ def harness():
     return L
 
 
-def _run(L, tris, lo, hi, levels, direct):
+def _run(L, tris, lo, hi, levels, direct, flat_only=False):
     tris = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 9)
     bf = np.concatenate([lo, hi]).astype(np.float32)                      # geom_octree.cpp:177-184
     side = max(np.float32(np.float32(np.float32(bf[3 + k] - bf[k]) * np.float32(0.5)) * np.float32(2.0)) for k in range(3))
     centre = np.ascontiguousarray((np.asarray(lo, np.float64) + np.asarray(hi, np.float64)) * 0.5)   # bbox.center(), :214
     out = np.zeros(10, np.uint64)
-    L.harness_run(tris.ctypes.data, tris.shape[0], centre.ctypes.data, float(side), levels, int(direct), 0, out.ctypes.data)
+    L.harness_run(tris.ctypes.data, tris.shape[0], centre.ctypes.data, float(side), levels, int(direct), int(flat_only), out.ctypes.data)
     return dict(pairs=int(out[0]), bad=int(out[1]), fast=int(out[2]), exact=int(out[3]),
                 first=dict(level=int(out[4]), tri=int(out[5]), code=int(out[6]), got=int(out[7]), want=int(out[8]), fl=int(out[9])))
 
@@ -63,6 +63,8 @@ def test_filter_equals_predicate_unit_cube(harness, meshgen, mesh, kw, levels, d
     assert r["bad"] == 0, r
     if mesh == "city":
         assert r["fast"] > 0.1 * r["pairs"], r   # the flat fast path must actually be exercised
+        r2 = _run(harness, tris, v.min(axis=0), v.max(axis=0), levels, direct, flat_only=True)   # box-mesh kernel variant
+        assert r2["bad"] == 0 and r2["pairs"] == r["pairs"], r2
 
 
 @pytest.mark.parametrize("direct", [True, False], ids=["direct", "chain"])
