@@ -14,6 +14,7 @@
 //   KIND_K64   (level L-2): key = the 8 child masks = one exact 64-bit word (the 4^3 voxel block).
 //   KIND_INNER (above)    : key = 8 child uids, tagged by a 64-bit hash, verified exactly afterwards.
 #include <algorithm>
+#include <cstdlib>
 
 #include "svb_dedup.cuh"
 
@@ -62,6 +63,48 @@ __device__ __forceinline__ bool build_key(const DedupArgs& a, uint64_t n, uint32
 		key8[c] = v;
 	}
 	return any;
+}
+
+// Nibble c of RANK_SEL[m & 127] = rank of child c among the set bits of child mask m (bit 7 never precedes anyone):
+// the __byte_perm selector that moves the packed run of child bytes (refs[childBase ..]) to their child positions.
+__device__ const uint32_t RANK_SEL[128] = {
+	0x00000000u, 0x11111110u, 0x11111100u, 0x22222210u, 0x11111000u, 0x22222110u, 0x22222100u, 0x33333210u,
+	0x11110000u, 0x22221110u, 0x22221100u, 0x33332210u, 0x22221000u, 0x33332110u, 0x33332100u, 0x44443210u,
+	0x11100000u, 0x22211110u, 0x22211100u, 0x33322210u, 0x22211000u, 0x33322110u, 0x33322100u, 0x44433210u,
+	0x22210000u, 0x33321110u, 0x33321100u, 0x44432210u, 0x33321000u, 0x44432110u, 0x44432100u, 0x55543210u,
+	0x11000000u, 0x22111110u, 0x22111100u, 0x33222210u, 0x22111000u, 0x33222110u, 0x33222100u, 0x44333210u,
+	0x22110000u, 0x33221110u, 0x33221100u, 0x44332210u, 0x33221000u, 0x44332110u, 0x44332100u, 0x55443210u,
+	0x22100000u, 0x33211110u, 0x33211100u, 0x44322210u, 0x33211000u, 0x44322110u, 0x44322100u, 0x55433210u,
+	0x33210000u, 0x44321110u, 0x44321100u, 0x55432210u, 0x44321000u, 0x55432110u, 0x55432100u, 0x66543210u,
+	0x10000000u, 0x21111110u, 0x21111100u, 0x32222210u, 0x21111000u, 0x32222110u, 0x32222100u, 0x43333210u,
+	0x21110000u, 0x32221110u, 0x32221100u, 0x43332210u, 0x32221000u, 0x43332110u, 0x43332100u, 0x54443210u,
+	0x21100000u, 0x32211110u, 0x32211100u, 0x43322210u, 0x32211000u, 0x43322110u, 0x43322100u, 0x54433210u,
+	0x32210000u, 0x43321110u, 0x43321100u, 0x54432210u, 0x43321000u, 0x54432110u, 0x54432100u, 0x65543210u,
+	0x21000000u, 0x32111110u, 0x32111100u, 0x43222210u, 0x32111000u, 0x43222110u, 0x43222100u, 0x54333210u,
+	0x32110000u, 0x43221110u, 0x43221100u, 0x54332210u, 0x43221000u, 0x54332110u, 0x54332100u, 0x65443210u,
+	0x32100000u, 0x43211110u, 0x43211100u, 0x54322210u, 0x43211000u, 0x54322110u, 0x54322100u, 0x65433210u,
+	0x43210000u, 0x54321110u, 0x54321100u, 0x65432210u, 0x54321000u, 0x65432110u, 0x65432100u, 0x76543210u,
+};
+
+// CH_MASK_U8 key without the 8-way predicated byte loop: the children of a node are popc(mask) consecutive bytes, so
+// three aligned 32-bit loads cover them for any alignment of childBase (the mask array of a level is padded by 16 zeroed
+// bytes, svb_voxelize.cu), two funnel shifts pack them, two byte permutes spread them to their child positions and a
+// byte mask clears the positions of absent children (the permute fetched a neighbour's byte there).  A child whose
+// voxel mask is 0 contributes a zero byte = "no child", as in build_key().  ~25 instructions instead of ~90.
+__device__ __forceinline__ bool build_key64_u8(const DedupArgs& a, uint64_t n, uint64_t& key64) {
+	const unsigned m = a.mask[n];
+	const uint32_t base = a.childBase[n];
+	const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>(a.childRefs) + (base >> 2);
+	const uint32_t a0 = w[0], a1 = w[1], a2 = w[2];
+	const unsigned sh = (base & 3u) * 8u;
+	const uint32_t lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);   // child bytes 0..3 / 4..7 of the run
+	const uint32_t sel = __ldg(&RANK_SEL[m & 127u]);
+	const uint32_t bmLo = (((m & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu;   // 4 mask bits -> 4 byte masks
+	const uint32_t bmHi = (((m >> 4) * 0x00204081u) & 0x01010101u) * 0xFFu;
+	const uint32_t kLo = __byte_perm(lo, hi, sel & 0xFFFFu) & bmLo;
+	const uint32_t kHi = __byte_perm(lo, hi, sel >> 16) & bmHi;
+	key64 = ((uint64_t)kHi << 32) | kLo;
+	return key64 != 0;
 }
 
 __device__ __forceinline__ uint64_t tag_of_key8(const uint32_t k[8]) {
@@ -167,13 +210,14 @@ __device__ __forceinline__ bool table_find_or_claim(const TableDev& t, uint64_t 
 	return false;
 }
 
-template <int CHMODE>
+template <int CHMODE, bool PERM = false>
 __global__ void __launch_bounds__(DD_THREADS) k_insert(DedupArgs a, TableDev t) {
 	uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (n >= a.N) return;
 	uint32_t k8[8];
 	uint64_t k64;
-	if (!build_key<CHMODE>(a, n, k8, k64)) { a.ref[n] = NULLREF; return; }
+	const bool any = (PERM && CHMODE == CH_MASK_U8) ? build_key64_u8(a, n, k64) : build_key<CHMODE>(a, n, k8, k64);
+	if (!any) { a.ref[n] = NULLREF; return; }
 	uint64_t tag = (CHMODE == CH_UID_U32) ? tag_of_key8(k8) : k64;
 	uint64_t slot;
 	if (!table_find_or_claim(t, tag, slot)) { a.ref[n] = NULLREF; return; }
@@ -426,10 +470,13 @@ static void dedup_level_t(cudaStream_t s, Pool& pool, LevelTable& T, const Dedup
 	// their slots have no uid and are dropped by the rebuild).
 	uint64_t want = next_pow2(2 * (T.count + a.N / 8 + 1024));
 	if (want > T.cap) grow_slots(s, pool, T, want);
+	const char* pk = getenv("SVB_K64_PERM");   // 0: the byte-by-byte key builder (A/B, verification)
+	const bool permKey = !(pk && pk[0] == '0');
 	for (;;) {
 		flags.zero();
 		TableDev t = dev_view(T, flags.p);
-		k_insert<CHMODE><<<nb, DD_THREADS, 0, s>>>(a, t);
+		if (permKey) k_insert<CHMODE, CHMODE == CH_MASK_U8><<<nb, DD_THREADS, 0, s>>>(a, t);
+		else k_insert<CHMODE><<<nb, DD_THREADS, 0, s>>>(a, t);
 		SVB_KERNEL_CHECK();
 		SVB_CUDA(cudaMemcpyAsync(h, flags.p, 16, cudaMemcpyDeviceToHost, s));
 		SVB_CUDA(cudaStreamSynchronize(s));

@@ -180,19 +180,29 @@ __device__ __forceinline__ uint32_t cta_excl_scan(uint32_t x, uint32_t* wsum, ui
 
 // children of node n: contiguous at childBase[n], ascending child index == Morton order.  Writes childBase and the
 // child codes of one tile of nodes.
+template <bool PIPE>
 __global__ void __launch_bounds__(VX_THREADS) k_children(uint64_t N, const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask,
                                                           const uint64_t* __restrict__ tileOffs, uint32_t* __restrict__ childBase, uint64_t* __restrict__ ccode) {
 	__shared__ uint64_t s_code[VX_THREADS * 8];
 	__shared__ uint32_t wsum[9];
 	const uint64_t n0 = (uint64_t)blockIdx.x * VX_TILE;
 	uint64_t run = tileOffs[blockIdx.x];
+	// the next chunk's node fields are fetched before this chunk's barriers (PIPE): one exposed round trip per tile, not per chunk
+	unsigned mNext = 0;
+	uint64_t cdNext = 0;
+	if (PIPE && n0 + threadIdx.x < N) { mNext = mask[n0 + threadIdx.x]; cdNext = code[n0 + threadIdx.x]; }
 	for (int ch = 0; ch < VX_CHUNKS; ++ch) {
 		const uint64_t nb = n0 + (uint64_t)ch * VX_THREADS;
 		if (nb >= N) break;
 		const uint64_t n = nb + threadIdx.x;
 		unsigned m = 0;
 		uint64_t cd = 0;
-		if (n < N) { m = mask[n]; cd = code[n] << 3; }
+		if (PIPE) {
+			m = mNext; cd = cdNext << 3;
+			const uint64_t nn = n + VX_THREADS;
+			mNext = 0; cdNext = 0;
+			if (ch + 1 < VX_CHUNKS && nn < N) { mNext = mask[nn]; cdNext = code[nn]; }
+		} else if (n < N) { m = mask[n]; cd = code[n] << 3; }
 		uint32_t tot;
 		uint32_t o = cta_excl_scan(__popc(m), wsum, &tot);
 		if (n < N) childBase[n] = (uint32_t)(run + o);
@@ -351,6 +361,88 @@ __global__ void __launch_bounds__(VX_THREADS) k_emit(uint64_t P, const uint32_t*
 		runF += nFlat;
 		runS += nSlow;
 		__syncthreads();
+	}
+}
+
+// Software-pipelined k_emit (default; SVB_EMIT_PIPE=0 selects the kernel above).  k_emit walks its tile in 8 chunks, and
+// every chunk used to pay two dependent global round trips in series behind CTA-wide barriers (pair fields, then the
+// node's mask / childBase gathered after the scan), which no other warp of the CTA can hide because all of them wait on
+// the same barriers.  Here the pair fields are fetched two chunks ahead and the node fields one chunk ahead, so that by
+// the time a chunk is scanned and staged everything it needs is already in registers; results are identical.
+template <bool SLOW, int MINB>
+__global__ void __launch_bounds__(VX_THREADS, MINB) k_emit_pipe(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
+                                                                 const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit,
+                                                                 const uint64_t* __restrict__ offsA, const uint64_t* __restrict__ offsB, uint64_t fastBase, uint64_t slowBase,
+                                                                 const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase,
+                                                                 uint32_t* __restrict__ otri, uint32_t* __restrict__ onode, uint16_t* __restrict__ oflags, uint32_t* __restrict__ ctstar,
+                                                                 int skipFlat, int precheck) {
+	__shared__ uint32_t s_tri[VX_THREADS * 8];
+	__shared__ uint32_t s_node[VX_THREADS * 8];
+	__shared__ uint16_t s_fl[VX_THREADS * 8];
+	__shared__ uint32_t wsum[9];
+	const uint64_t p0 = (uint64_t)blockIdx.x * VX_TILE;
+	uint64_t runF, runS = 0;
+	if (SLOW) { const uint64_t a = offsA[blockIdx.x], b = offsB[blockIdx.x]; runF = fastBase + b; runS = slowBase + (a - b); }
+	else runF = fastBase + offsA[blockIdx.x];
+	struct PairIn { unsigned m; uint32_t t, n, fl; };
+	struct NodeIn { unsigned nm; uint32_t base; };
+	auto load_pair = [&](int ch) {
+		PairIn r = {0u, 0u, 0u, 0u};
+		const uint64_t p = p0 + (uint64_t)ch * VX_THREADS + threadIdx.x;
+		if (ch < VX_CHUNKS && p < P) { r.m = hit[p]; r.fl = pflags[p]; r.t = ptri[p]; r.n = pnode[p]; }
+		return r;
+	};
+	// drops the parents whose children are decided in place by k_flat_leaves, then gathers the node fields of the rest
+	auto load_node = [&](PairIn& f) {
+		NodeIn g = {0u, 0u};
+		if (SLOW && skipFlat && pair_is_fast(f.fl)) f.m = 0;
+		if (f.m) { g.nm = mask[f.n]; g.base = childBase[f.n]; }
+		return g;
+	};
+	PairIn f0 = load_pair(0), f1 = load_pair(1);
+	NodeIn g0 = load_node(f0);
+	for (int ch = 0; ch < VX_CHUNKS; ++ch) {
+		if (p0 + (uint64_t)ch * VX_THREADS >= P) break;
+		const PairIn f2 = load_pair(ch + 2);
+		const NodeIn g1 = load_node(f1);
+		const unsigned m = f0.m;
+		const bool flatKids = SLOW ? pair_is_fast(f0.fl) : true;
+		const uint32_t cnt = __popc(m);
+		uint32_t tot;
+		const uint32_t ex = cta_excl_scan(flatKids ? cnt : (cnt << 16), wsum, &tot);   // low half: flat children, high half: others
+		const uint32_t nFlat = tot & 0xFFFF, nSlow = tot >> 16;
+		if (m) {
+			uint32_t o = flatKids ? (ex & 0xFFFF) : nFlat + (ex >> 16);
+			const uint32_t t = f0.t;
+			unsigned mm = m;
+			while (mm) {
+				const int c = __ffs(mm) - 1;
+				mm &= mm - 1;
+				const uint32_t child = g0.base + __popc(g0.nm & ((1u << c) - 1));
+				s_tri[o] = t;
+				s_node[o] = child;
+				s_fl[o] = (uint16_t)f0.fl;
+				++o;
+				if (!precheck || ctstar[child] > t) atomicMin(&ctstar[child], t);
+			}
+		}
+		__syncthreads();
+		for (uint32_t i = threadIdx.x; i < nFlat; i += VX_THREADS) {
+			otri[runF + i] = s_tri[i];
+			onode[runF + i] = s_node[i];
+			oflags[runF + i] = s_fl[i];
+		}
+		if (SLOW) {
+			for (uint32_t i = threadIdx.x; i < nSlow; i += VX_THREADS) {
+				otri[runS + i] = s_tri[nFlat + i];
+				onode[runS + i] = s_node[nFlat + i];
+				oflags[runS + i] = s_fl[nFlat + i];
+			}
+		}
+		runF += nFlat;
+		runS += nSlow;
+		__syncthreads();
+		f0 = f1; g0 = g1; f1 = f2;
 	}
 }
 
@@ -534,6 +626,9 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 	DevBuf<uint16_t> pflags(pool, P + 16);   // settled-axis flags per pair (svb_classify.cuh)
 	pflags.zero();
 	const bool exactOnly = classify_exact_only();
+	// k_emit variant: 0 = one chunk at a time, 6 / 8 = software-pipelined at 6 / 8 CTAs per SM (read per batch, not cached: A/B inside one process)
+	const bool childrenPipe = [] { const char* e = getenv("SVB_CHILDREN_PIPE"); return !(e && e[0] == '0'); }();
+	const int emitPipe = [] { const char* e = getenv("SVB_EMIT_PIPE"); return e ? atoi(e) : 8; }();
 	static const int occFlat = [] { const char* e = getenv("SVB_VX_OCC_FLAT"); return e ? atoi(e) : 6; }();   // 6 or 8 CTAs/SM (40 / 32 registers, spills) beat 5 on B200: the kernel is latency bound
 	static const int occ = [] { const char* e = getenv("SVB_VX_OCC"); return e ? atoi(e) : 5; }();   // CTAs/SM of the slow classify kernel: 5 (48 registers, some spills) measured best on B200
 	for (int l = 0; l < Lt; ++l) {
@@ -624,7 +719,8 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		C.tstar.reset(pool, Nn);
 		C.tstar.fill_ff();
 		L.childBase.reset(pool, L.n);
-		k_children<<<blocks_for(L.n, VX_TILE), VX_THREADS, 0, s>>>(L.n, L.code.p, L.mask.p, nodeOffs.p, L.childBase.p, C.code.p);
+		if (childrenPipe) k_children<true><<<blocks_for(L.n, VX_TILE), VX_THREADS, 0, s>>>(L.n, L.code.p, L.mask.p, nodeOffs.p, L.childBase.p, C.code.p);
+		else k_children<false><<<blocks_for(L.n, VX_TILE), VX_THREADS, 0, s>>>(L.n, L.code.p, L.mask.p, nodeOffs.p, L.childBase.p, C.code.p);
 		SVB_KERNEL_CHECK();
 		DevBuf<uint32_t> ntri(pool, Pn + 16), nnode(pool, Pn + 16);
 		DevBuf<uint16_t> nflags(pool, Pn + 16);
@@ -641,13 +737,21 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 #undef SVB_LAUNCH_FL2
 			pairsTotal += cF + (fuseS ? cSF : 0);   // decided here instead of as pairs of the last level
 		} else if (F) {
-			k_emit<false><<<blocks_for(F, VX_TILE), VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p,
-			                                                                ntri.p, nnode.p, nflags.p, C.tstar.p, 0, precheckKids);
+#define SVB_EMIT_ARGS_F F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p, ntri.p, nnode.p, nflags.p, C.tstar.p, 0, precheckKids
+			const unsigned nb = blocks_for(F, VX_TILE);
+			if (emitPipe == 0) k_emit<false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F);
+			else if (emitPipe >= 8) k_emit_pipe<false, 8><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F);
+			else k_emit_pipe<false, 6><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F);
+#undef SVB_EMIT_ARGS_F
 			SVB_KERNEL_CHECK();
 		}
 		if (S) {
-			k_emit<true><<<blocks_for(S, VX_TILE), VX_THREADS, 0, s>>>(S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, cFe, Fan, L.mask.p, L.childBase.p,
-			                                                               ntri.p, nnode.p, nflags.p, C.tstar.p, fuseS ? 1 : 0, precheckKids);
+#define SVB_EMIT_ARGS_S S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, cFe, Fan, L.mask.p, L.childBase.p, ntri.p, nnode.p, nflags.p, C.tstar.p, fuseS ? 1 : 0, precheckKids
+			const unsigned nb = blocks_for(S, VX_TILE);
+			if (emitPipe == 0) k_emit<true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S);
+			else if (emitPipe >= 8) k_emit_pipe<true, 8><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S);
+			else k_emit_pipe<true, 6><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S);
+#undef SVB_EMIT_ARGS_S
 			SVB_KERNEL_CHECK();
 		}
 		ptri = std::move(ntri);
