@@ -226,6 +226,120 @@ __global__ void __launch_bounds__(DD_THREADS) k_insert(DedupArgs a, TableDev t) 
 	a.ref[n] = (uint32_t)slot;
 }
 
+// ------------------------------------------------------------------ KIND_K64, single pass (default for CH_MASK_U8)
+// The 4^3 level compresses to a few 10^5 distinct keys while a tile batch streams 10^8 nodes through it, so almost every
+// node finds its key already in the table.  The thread that claims an empty slot draws the dense uid on the spot and
+// appends the slot to a list (the dense arrays are filled from that list afterwards: k_assign_list); every other node
+// reads the uid together with the slot and writes its final ref at once -- no second pass over the node arrays.  A node
+// that finds the slot in the instant between the claim and the claimer's uid store leaves  0x80000000 | slot  as its
+// ref and its index in a second list (k_fix_list); if either list overflows, a full pass (k_fix_all / k_assign_k64)
+// does the same job.  NPT nodes per thread: their loads and first probes are in flight together.
+struct OnePass {
+	uint32_t* dCount;      // next dense uid
+	uint32_t* newSlots;    // slots claimed by this launch
+	uint32_t* unres;       // nodes whose ref is still a marked slot
+	uint32_t listCap;
+	uint32_t* counters;    // [0] unresolved nodes
+};
+constexpr uint32_t REF_MARK = 0x80000000u;
+
+template <int NPT>
+__global__ void __launch_bounds__(DD_THREADS) k_insert_k64(DedupArgs a, TableDev t, OnePass op) {
+	const uint64_t n0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * NPT;
+	if (n0 >= a.N) return;
+	uint64_t key[NPT], idx[NPT];
+	unsigned long long cur[NPT], O[NPT];
+	bool live[NPT];
+	uint32_t out[NPT];
+#pragma unroll
+	for (int j = 0; j < NPT; ++j) {
+		const uint64_t n = n0 + j;
+		live[j] = n < a.N && build_key64_u8(a, n, key[j]);
+		out[j] = NULLREF;
+	}
+#pragma unroll
+	for (int j = 0; j < NPT; ++j) {
+		idx[j] = 0; cur[j] = 0; O[j] = 0;
+		if (live[j]) {
+			idx[j] = mix64(key[j]) & t.capMask;
+			cur[j] = t.tag[idx[j]];
+			O[j] = order_key(a.code[n0 + j], a.tstar[n0 + j], a);
+		}
+	}
+#pragma unroll
+	for (int j = 0; j < NPT; ++j) {
+		if (!live[j]) continue;
+		const uint64_t n = n0 + j, tag = key[j];
+		uint64_t i = idx[j];
+		unsigned long long c = cur[j];
+		bool found = false, claimed = false;
+		for (int probe = 0; probe < 8192; ++probe) {
+			if (c == tag) { found = true; break; }
+			if (c == EMPTY_TAG) {
+				const unsigned long long old = atomicCAS(&t.tag[i], (unsigned long long)EMPTY_TAG, (unsigned long long)tag);
+				if (old == EMPTY_TAG) { found = claimed = true; break; }
+				if (old == tag) { found = true; break; }
+			}
+			i = (i + 1) & t.capMask;
+			c = t.tag[i];
+		}
+		if (!found) { t.flags[0] = 1; continue; }
+		uint32_t u;
+		if (claimed) {
+			const uint32_t nc = atomicAdd(&t.flags[2], 1u);
+			if (t.countBefore + nc + 1 > t.maxLoad) t.flags[0] = 1;
+			u = atomicAdd(op.dCount, 1u);
+			t.uid[i] = u;
+			if (nc < op.listCap) op.newSlots[nc] = (uint32_t)i;
+		} else {
+			u = __ldcg(&t.uid[i]);
+		}
+		if (t.minO[i] > O[j]) atomicMin(&t.minO[i], O[j]);
+		if (u == UNSET) {   // claimed a moment ago by another thread: resolved after the launch
+			const uint32_t k = atomicAdd(&op.counters[0], 1u);
+			if (k < op.listCap) op.unres[k] = (uint32_t)n;
+			u = REF_MARK | (uint32_t)i;
+		}
+		out[j] = u;
+	}
+	if (NPT == 2 && n0 + 1 < a.N) *reinterpret_cast<uint2*>(a.ref + n0) = make_uint2(out[0], out[NPT - 1]);   // n0 is even
+	else {
+#pragma unroll
+		for (int j = 0; j < NPT; ++j) if (n0 + j < a.N) a.ref[n0 + j] = out[j];
+	}
+}
+__global__ void __launch_bounds__(DD_THREADS) k_assign_list(uint32_t fresh, const uint32_t* __restrict__ newSlots, const unsigned long long* __restrict__ tag,
+                                                             const unsigned long long* __restrict__ minO, const uint32_t* __restrict__ uid,
+                                                             uint64_t* __restrict__ dMinO, uint64_t* __restrict__ dKey64) {
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= fresh) return;
+	const uint32_t i = newSlots[k], u = uid[i];
+	dMinO[u] = minO[i];
+	dKey64[u] = tag[i];
+}
+// (list overflow) the same from a pass over the table: the new entries are those with uid >= countBefore
+__global__ void __launch_bounds__(DD_THREADS) k_assign_scan(uint64_t cap, uint32_t countBefore, const unsigned long long* __restrict__ tag, const unsigned long long* __restrict__ minO,
+                                                             const uint32_t* __restrict__ uid, uint64_t* __restrict__ dMinO, uint64_t* __restrict__ dKey64) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= cap) return;
+	const uint32_t u = uid[i];
+	if (u == UNSET || u < countBefore) return;
+	dMinO[u] = minO[i];
+	dKey64[u] = tag[i];
+}
+__global__ void __launch_bounds__(DD_THREADS) k_fix_list(uint32_t cnt, const uint32_t* __restrict__ unres, const uint32_t* __restrict__ uid, uint32_t* __restrict__ ref) {
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= cnt) return;
+	const uint32_t n = unres[k];
+	ref[n] = uid[ref[n] & ~REF_MARK];
+}
+__global__ void __launch_bounds__(DD_THREADS) k_fix_all(uint64_t N, const uint32_t* __restrict__ uid, uint32_t* __restrict__ ref) {
+	const uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (n >= N) return;
+	const uint32_t r = ref[n];
+	if (r != NULLREF && (r & REF_MARK)) ref[n] = uid[r & ~REF_MARK];
+}
+
 // K64: new slots get their dense uid from a pass over the table (the key is the tag itself)
 __global__ void __launch_bounds__(DD_THREADS) k_assign_k64(uint64_t cap, const unsigned long long* __restrict__ tag, const unsigned long long* __restrict__ minO,
                                                             uint32_t* __restrict__ uid, uint32_t* __restrict__ dCount,
@@ -457,6 +571,47 @@ void dedup_leaf(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, u
 	SVB_KERNEL_CHECK();
 }
 
+// KIND_K64 over u8 child masks in one pass over the nodes (k_insert_k64)
+static void dedup_k64_onepass(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, int npt) {
+	constexpr uint32_t LIST_CAP = 1u << 20;
+	DevBuf<uint32_t> flags(pool, 4), counters(pool, 4), newSlots(pool, LIST_CAP), unres(pool, LIST_CAP);
+	uint32_t h[4], hc[4];
+	for (;;) {
+		if (T.cap > (1ull << 30)) throw Error(SVB_ERANGE, "4^3-level table beyond 2^30 slots");
+		flags.zero();
+		counters.zero();
+		TableDev t = dev_view(T, flags.p);
+		OnePass op;
+		op.dCount = T.dCount.p; op.newSlots = newSlots.p; op.unres = unres.p; op.listCap = LIST_CAP; op.counters = counters.p;
+		if (npt == 2) k_insert_k64<2><<<blocks_for((a.N + 1) / 2, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
+		else k_insert_k64<1><<<blocks_for(a.N, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
+		SVB_KERNEL_CHECK();
+		SVB_CUDA(cudaMemcpyAsync(h, flags.p, 16, cudaMemcpyDeviceToHost, s));
+		SVB_CUDA(cudaMemcpyAsync(hc, counters.p, 16, cudaMemcpyDeviceToHost, s));
+		SVB_CUDA(cudaStreamSynchronize(s));
+		if (!h[0]) break;
+		// overflow: the claims of this attempt are dropped by the rebuild; take their uids back too
+		const uint32_t cnt = (uint32_t)T.count;
+		SVB_CUDA(cudaMemcpyAsync(T.dCount.p, &cnt, 4, cudaMemcpyHostToDevice, s));
+		SVB_CUDA(cudaStreamSynchronize(s));   // cnt is a stack temporary
+		grow_slots(s, pool, T, T.cap * 4);
+	}
+	const uint64_t fresh = h[2];
+	if (T.count + fresh >= 0x7FFFFFF0ull) throw Error(SVB_ERANGE, "more than 2^31 unique nodes in the 4^3 level");
+	ensure_dense(s, pool, T, T.count + fresh);
+	if (fresh) {
+		if (fresh <= LIST_CAP) k_assign_list<<<blocks_for(fresh, DD_THREADS), DD_THREADS, 0, s>>>((uint32_t)fresh, newSlots.p, (const unsigned long long*)T.tag.p, (const unsigned long long*)T.minO.p, T.uid.p, T.dMinO.p, T.dKey64.p);
+		else k_assign_scan<<<blocks_for(T.cap, DD_THREADS), DD_THREADS, 0, s>>>(T.cap, (uint32_t)T.count, (const unsigned long long*)T.tag.p, (const unsigned long long*)T.minO.p, T.uid.p, T.dMinO.p, T.dKey64.p);
+		SVB_KERNEL_CHECK();
+	}
+	if (hc[0]) {
+		if (hc[0] <= LIST_CAP) k_fix_list<<<blocks_for(hc[0], DD_THREADS), DD_THREADS, 0, s>>>(hc[0], unres.p, T.uid.p, a.ref);
+		else k_fix_all<<<blocks_for(a.N, DD_THREADS), DD_THREADS, 0, s>>>(a.N, T.uid.p, a.ref);
+		SVB_KERNEL_CHECK();
+	}
+	T.count += fresh;
+}
+
 template <int CHMODE>
 static void dedup_level_t(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a) {
 	if (a.N == 0) return;
@@ -472,6 +627,12 @@ static void dedup_level_t(cudaStream_t s, Pool& pool, LevelTable& T, const Dedup
 	if (want > T.cap) grow_slots(s, pool, T, want);
 	const char* pk = getenv("SVB_K64_PERM");   // 0: the byte-by-byte key builder (A/B, verification)
 	const bool permKey = !(pk && pk[0] == '0');
+	if (CHMODE == CH_MASK_U8) {
+		const char* e = getenv("SVB_K64_ONEPASS");   // 0: insert + table scan + convert passes; 1 / 2: single pass, that many nodes per thread
+		const int npt = e ? atoi(e) : 2;
+		// marked slots must stay distinguishable from NULLREF and from uids
+		if (npt > 0 && T.cap <= (1ull << 28) && T.count + a.N / 8 < (1ull << 30)) { dedup_k64_onepass(s, pool, T, a, npt); return; }
+	}
 	for (;;) {
 		flags.zero();
 		TableDev t = dev_view(T, flags.p);

@@ -245,10 +245,11 @@ __global__ void __launch_bounds__(VX_THREADS, 8) k_classify_fast(uint64_t P, con
 // parent pair decides each hit child's 8 voxels on the spot (same exact box-axis tests, one level down) and ORs the
 // voxel mask / first-touch triangle straight into the leaf level.  Saves writing and re-reading the bulk of the
 // last-level pair list (the interior of every wall), which is the largest array of the whole build.
-template <bool DIRECT, int MINB>
+// STAR: the pair that carries its node's own first-touch index stores the first touch of its children plainly (see k_emit_pipe).
+template <bool DIRECT, int MINB, bool STAR>
 __global__ void __launch_bounds__(VX_THREADS, MINB) k_flat_leaves(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
                                                                const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit,
-                                                               const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase,
+                                                               const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase, const uint32_t* __restrict__ tstar,
                                                                int lc, double kscaleParent, const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
                                                                const uint32_t* __restrict__ rootTri, uint8_t* __restrict__ cmask, uint32_t* __restrict__ ctstar, int onlyFlatKids, int precheck) {
 	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_flat_leaves(uint64_t P, co
 	const uint64_t cd = code[n];
 	const unsigned nm = mask[n];
 	const uint32_t base = childBase[n];
+	const bool star = STAR && tstar[n] == t;
 	const double* tg = reinterpret_cast<const double*>(tiles + (uint32_t)(cd >> (3 * (lc - 1))));
 	const float* tp = tris + 9ull * rootTri[t];   // t itself (the root pair index) is what orders first touches
 	unsigned lohi[3][2];
@@ -283,7 +285,8 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_flat_leaves(uint64_t P, co
 		acc |= mc << (8 * (child & 3));
 		// precheck: read before the atomic -- pays off only where many pairs share a node (upper levels); at the leaf
 		// levels (~1.4 pairs per node) the read is a wasted round trip and the reduction goes out fire-and-forget
-		if (!precheck || ctstar[child] > t) atomicMin(&ctstar[child], t);
+		if (star) ctstar[child] = t;
+		else if (!precheck || ctstar[child] > t) atomicMin(&ctstar[child], t);
 	}
 	if (acc && (!precheck || (words[curWord] & acc) != acc)) atomicOr(words + curWord, acc);
 }
@@ -369,23 +372,34 @@ __global__ void __launch_bounds__(VX_THREADS) k_emit(uint64_t P, const uint32_t*
 // node's mask / childBase gathered after the scan), which no other warp of the CTA can hide because all of them wait on
 // the same barriers.  Here the pair fields are fetched two chunks ahead and the node fields one chunk ahead, so that by
 // the time a chunk is scanned and staged everything it needs is already in registers; results are identical.
-template <bool SLOW, int MINB>
+// REDOUT: the first-touch reductions leave with the coalesced copy-out (entry i = thread i: the children of one parent
+// are consecutive nodes, so a warp's 32 atomics fall into a handful of 32-byte sectors) instead of from the staging loop
+// (where the 32 lanes of a warp own 32 different parents, i.e. 32 different sectors per instruction).
+//
+// STAR: exactly one pair of a node carries the node's own first-touch index (t == tstar[n]; the pairs of
+// a node belong to distinct triangles).  Every triangle that reaches a child also reaches its parent, so no pair of the
+// child can carry a smaller index: the children of that one pair get their first touch with a PLAIN store.  Racing
+// atomicMin's of the node's other pairs carry larger values and cannot change the outcome in either order (the word
+// ends up t).  At the deep levels ~70 % of the pairs are such pairs (pairs/nodes ~ 1.4), and REDG issues at ~1.3
+// cycles per LANE per SM -- the bound of this kernel -- whereas the coalesced stores cost a few wavefronts per warp.
+template <bool SLOW, int MINB, bool REDOUT, bool STAR>
 __global__ void __launch_bounds__(VX_THREADS, MINB) k_emit_pipe(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
                                                                  const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit,
                                                                  const uint64_t* __restrict__ offsA, const uint64_t* __restrict__ offsB, uint64_t fastBase, uint64_t slowBase,
-                                                                 const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase,
+                                                                 const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase, const uint32_t* __restrict__ tstar,
                                                                  uint32_t* __restrict__ otri, uint32_t* __restrict__ onode, uint16_t* __restrict__ oflags, uint32_t* __restrict__ ctstar,
                                                                  int skipFlat, int precheck) {
 	__shared__ uint32_t s_tri[VX_THREADS * 8];
 	__shared__ uint32_t s_node[VX_THREADS * 8];
 	__shared__ uint16_t s_fl[VX_THREADS * 8];
+	__shared__ uint8_t s_star[STAR ? VX_THREADS * 8 : 1];
 	__shared__ uint32_t wsum[9];
 	const uint64_t p0 = (uint64_t)blockIdx.x * VX_TILE;
 	uint64_t runF, runS = 0;
 	if (SLOW) { const uint64_t a = offsA[blockIdx.x], b = offsB[blockIdx.x]; runF = fastBase + b; runS = slowBase + (a - b); }
 	else runF = fastBase + offsA[blockIdx.x];
 	struct PairIn { unsigned m; uint32_t t, n, fl; };
-	struct NodeIn { unsigned nm; uint32_t base; };
+	struct NodeIn { unsigned nm; uint32_t base, ts; };
 	auto load_pair = [&](int ch) {
 		PairIn r = {0u, 0u, 0u, 0u};
 		const uint64_t p = p0 + (uint64_t)ch * VX_THREADS + threadIdx.x;
@@ -394,9 +408,9 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_emit_pipe(uint64_t P, cons
 	};
 	// drops the parents whose children are decided in place by k_flat_leaves, then gathers the node fields of the rest
 	auto load_node = [&](PairIn& f) {
-		NodeIn g = {0u, 0u};
+		NodeIn g = {0u, 0u, 0u};
 		if (SLOW && skipFlat && pair_is_fast(f.fl)) f.m = 0;
-		if (f.m) { g.nm = mask[f.n]; g.base = childBase[f.n]; }
+		if (f.m) { g.nm = mask[f.n]; g.base = childBase[f.n]; if (STAR) g.ts = tstar[f.n]; }
 		return g;
 	};
 	PairIn f0 = load_pair(0), f1 = load_pair(1);
@@ -422,21 +436,28 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_emit_pipe(uint64_t P, cons
 				s_tri[o] = t;
 				s_node[o] = child;
 				s_fl[o] = (uint16_t)f0.fl;
+				if (STAR) s_star[o] = (uint8_t)(g0.ts == t);
 				++o;
-				if (!precheck || ctstar[child] > t) atomicMin(&ctstar[child], t);
+				if (!REDOUT && !(STAR && g0.ts == t) && (!precheck || ctstar[child] > t)) atomicMin(&ctstar[child], t);
 			}
 		}
 		__syncthreads();
 		for (uint32_t i = threadIdx.x; i < nFlat; i += VX_THREADS) {
-			otri[runF + i] = s_tri[i];
-			onode[runF + i] = s_node[i];
+			const uint32_t t = s_tri[i], child = s_node[i];
+			otri[runF + i] = t;
+			onode[runF + i] = child;
 			oflags[runF + i] = s_fl[i];
+			if (STAR && s_star[i]) ctstar[child] = t;
+			else if (REDOUT && (!precheck || ctstar[child] > t)) atomicMin(&ctstar[child], t);
 		}
 		if (SLOW) {
 			for (uint32_t i = threadIdx.x; i < nSlow; i += VX_THREADS) {
-				otri[runS + i] = s_tri[nFlat + i];
-				onode[runS + i] = s_node[nFlat + i];
+				const uint32_t t = s_tri[nFlat + i], child = s_node[nFlat + i];
+				otri[runS + i] = t;
+				onode[runS + i] = child;
 				oflags[runS + i] = s_fl[nFlat + i];
+				if (STAR && s_star[nFlat + i]) ctstar[child] = t;
+				else if (REDOUT && (!precheck || ctstar[child] > t)) atomicMin(&ctstar[child], t);
 			}
 		}
 		runF += nFlat;
@@ -626,9 +647,11 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 	DevBuf<uint16_t> pflags(pool, P + 16);   // settled-axis flags per pair (svb_classify.cuh)
 	pflags.zero();
 	const bool exactOnly = classify_exact_only();
-	// k_emit variant: 0 = one chunk at a time, 6 / 8 = software-pipelined at 6 / 8 CTAs per SM (read per batch, not cached: A/B inside one process)
+	// k_emit variant: 0 = one chunk at a time, else software-pipelined (read per batch, not cached: A/B inside one process)
 	const bool childrenPipe = [] { const char* e = getenv("SVB_CHILDREN_PIPE"); return !(e && e[0] == '0'); }();
 	const int emitPipe = [] { const char* e = getenv("SVB_EMIT_PIPE"); return e ? atoi(e) : 8; }();
+	const bool starStore = [] { const char* e = getenv("SVB_STAR_STORE"); return !(e && e[0] == '0'); }();   // first touch of the children of a node's own first-touch pair by plain store
+	const bool emitRedOut = [] { const char* e = getenv("SVB_EMIT_REDOUT"); return !(e && e[0] == '0'); }();   // the remaining atomics leave with the copy-out too (measured: 667 vs 672 ms voxelize with the star stores; without them the staging loop is the better place)
 	static const int occFlat = [] { const char* e = getenv("SVB_VX_OCC_FLAT"); return e ? atoi(e) : 6; }();   // 6 or 8 CTAs/SM (40 / 32 registers, spills) beat 5 on B200: the kernel is latency bound
 	static const int occ = [] { const char* e = getenv("SVB_VX_OCC"); return e ? atoi(e) : 5; }();   // CTAs/SM of the slow classify kernel: 5 (48 registers, some spills) measured best on B200
 	for (int l = 0; l < Lt; ++l) {
@@ -729,28 +752,34 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 			C.mask.zero();
 			static const int occLeaves = [] { const char* e = getenv("SVB_VX_OCC_LEAVES"); return e ? atoi(e) : 8; }();   // 8 CTAs/SM measured best
 #define SVB_LAUNCH_FL(DIR, N, OFF, ONLY) if (occLeaves >= 8) SVB_LAUNCH_FL2(DIR, 8, N, OFF, ONLY); else SVB_LAUNCH_FL2(DIR, 6, N, OFF, ONLY)
-#define SVB_LAUNCH_FL2(DIR, MB, N, OFF, ONLY) k_flat_leaves<DIR, MB><<<blocks_for(N, VX_THREADS), VX_THREADS, 0, s>>>(N, ptri.p + (OFF), pnode.p + (OFF), pflags.p + (OFF), hit.p + (OFF), \
-			L.code.p, L.mask.p, L.childBase.p, l + 1, kscale, d_tiles, d_tris, rootTri, C.mask.p, C.tstar.p, ONLY, precheckKids)
+#define SVB_LAUNCH_FL2(DIR, MB, N, OFF, ONLY) if (starStore) SVB_LAUNCH_FL3(DIR, MB, true, N, OFF, ONLY); else SVB_LAUNCH_FL3(DIR, MB, false, N, OFF, ONLY)
+#define SVB_LAUNCH_FL3(DIR, MB, ST, N, OFF, ONLY) k_flat_leaves<DIR, MB, ST><<<blocks_for(N, VX_THREADS), VX_THREADS, 0, s>>>(N, ptri.p + (OFF), pnode.p + (OFF), pflags.p + (OFF), hit.p + (OFF), \
+			L.code.p, L.mask.p, L.childBase.p, L.tstar.p, l + 1, kscale, d_tiles, d_tris, rootTri, C.mask.p, C.tstar.p, ONLY, precheckKids)
 			if (F) { if (directCentre) SVB_LAUNCH_FL(true, F, 0, 0); else SVB_LAUNCH_FL(false, F, 0, 0); SVB_KERNEL_CHECK(); }
 			if (fuseS && S && cSF) { if (directCentre) SVB_LAUNCH_FL(true, S, Fa, 1); else SVB_LAUNCH_FL(false, S, Fa, 1); SVB_KERNEL_CHECK(); }
 #undef SVB_LAUNCH_FL
 #undef SVB_LAUNCH_FL2
+#undef SVB_LAUNCH_FL3
 			pairsTotal += cF + (fuseS ? cSF : 0);   // decided here instead of as pairs of the last level
 		} else if (F) {
-#define SVB_EMIT_ARGS_F F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p, ntri.p, nnode.p, nflags.p, C.tstar.p, 0, precheckKids
+#define SVB_EMIT_ARGS_F(...) F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p, __VA_ARGS__ ntri.p, nnode.p, nflags.p, C.tstar.p, 0, precheckKids
 			const unsigned nb = blocks_for(F, VX_TILE);
-			if (emitPipe == 0) k_emit<false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F);
-			else if (emitPipe >= 8) k_emit_pipe<false, 8><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F);
-			else k_emit_pipe<false, 6><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F);
+			if (emitPipe == 0) k_emit<false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F());
+			else if (!emitRedOut && !starStore) k_emit_pipe<false, 8, false, false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F(L.tstar.p,));
+			else if (!emitRedOut) k_emit_pipe<false, 8, false, true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F(L.tstar.p,));
+			else if (!starStore) k_emit_pipe<false, 8, true, false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F(L.tstar.p,));
+			else k_emit_pipe<false, 8, true, true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F(L.tstar.p,));
 #undef SVB_EMIT_ARGS_F
 			SVB_KERNEL_CHECK();
 		}
 		if (S) {
-#define SVB_EMIT_ARGS_S S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, cFe, Fan, L.mask.p, L.childBase.p, ntri.p, nnode.p, nflags.p, C.tstar.p, fuseS ? 1 : 0, precheckKids
+#define SVB_EMIT_ARGS_S(...) S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, cFe, Fan, L.mask.p, L.childBase.p, __VA_ARGS__ ntri.p, nnode.p, nflags.p, C.tstar.p, fuseS ? 1 : 0, precheckKids
 			const unsigned nb = blocks_for(S, VX_TILE);
-			if (emitPipe == 0) k_emit<true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S);
-			else if (emitPipe >= 8) k_emit_pipe<true, 8><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S);
-			else k_emit_pipe<true, 6><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S);
+			if (emitPipe == 0) k_emit<true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S());
+			else if (!emitRedOut && !starStore) k_emit_pipe<true, 8, false, false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S(L.tstar.p,));
+			else if (!emitRedOut) k_emit_pipe<true, 8, false, true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S(L.tstar.p,));
+			else if (!starStore) k_emit_pipe<true, 8, true, false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S(L.tstar.p,));
+			else k_emit_pipe<true, 8, true, true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S(L.tstar.p,));
 #undef SVB_EMIT_ARGS_S
 			SVB_KERNEL_CHECK();
 		}
