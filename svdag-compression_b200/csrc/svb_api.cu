@@ -202,7 +202,10 @@ void set_order_key_width(BuildState& B, int Lt, int tb) {
 }
 
 // bottom-up reduction of one batch's levels [lo_l, Lt-1] into the tables
-void dedup_batch(svb_ctx* c, BuildState& B, std::vector<BatchLevel>& lv, int Lt, uint32_t gbase, const uint32_t* d_tileSeq, const uint32_t* d_tileStart, int lo_l) {
+void dedup_batch(svb_ctx* c, BuildState& B, std::vector<BatchLevel>& lv, int Lt, uint32_t gbase, const uint32_t* d_tileSeq, const uint32_t* d_tileStart, int lo_l,
+                 const std::vector<uint32_t>& hseq) {
+	const uint32_t seqLo = hseq.empty() ? 0 : *std::min_element(hseq.begin(), hseq.end()), seqHi = hseq.empty() ? 0 : *std::max_element(hseq.begin(), hseq.end());
+	const bool seqMono = std::is_sorted(hseq.begin(), hseq.end());
 	const int tb = gbase == 0 ? B.tbits : B.tbLocal;
 	for (int l = Lt - 1; l >= lo_l; --l) {
 		uint32_t g = gbase + l;
@@ -210,6 +213,7 @@ void dedup_batch(svb_ctx* c, BuildState& B, std::vector<BatchLevel>& lv, int Lt,
 		DedupArgs a;
 		a.N = X.n; a.code = X.code.p; a.tstar = X.tstar.p; a.mask = X.mask.p; a.childBase = X.childBase.p;
 		a.l = l; a.tbits = tb; a.tileSeq = d_tileSeq; a.tileStart = d_tileStart;
+		a.seqLo = seqLo; a.seqHi = seqHi; a.seqMonotone = seqMono;
 		int ob = B.tileBits + tb + 3 * l;
 		if (ob > B.obits[g]) B.obits[g] = ob;
 		LevelTable& T = B.tables[g];
@@ -279,7 +283,7 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 	}
 	StageTimer tm(s);
 	if (gbase == 0) {
-		dedup_batch(c, B, lv, Lt, 0, dSeq.p, dTileStart.p, 1);
+		dedup_batch(c, B, lv, Lt, 0, dSeq.p, dTileStart.p, 1, hseq);
 		DedupArgs r;
 		r.N = 1; r.code = lv[0].code.p; r.tstar = lv[0].tstar.p; r.mask = lv[0].mask.p; r.childBase = lv[0].childBase.p;
 		bool leafBelow = (kind_of(1, B.L) == KIND_LEAF);
@@ -288,7 +292,7 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 		B.rootChildMode = r.childMode;
 		root_key(s, r, B.rootKey.p);
 	} else {
-		dedup_batch(c, B, lv, Lt, gbase, dSeq.p, dTileStart.p, 0);
+		dedup_batch(c, B, lv, Lt, gbase, dSeq.p, dTileStart.p, 0, hseq);
 		// remember what each sub-octree root was reduced to (uid, or the voxel mask for 1-level sub-octrees)
 		if (B.tables[gbase].kind == KIND_LEAF) k_scatter_u8<<<blocks_for(nt, 256), 256, 0, s>>>(nt, dSeq.p, lv[0].mask.p, B.tileRootRef.p);
 		else k_scatter_u32<<<blocks_for(nt, 256), 256, 0, s>>>(nt, dSeq.p, lv[0].ref.p, B.tileRootRef.p);

@@ -174,6 +174,59 @@ __global__ void __launch_bounds__(DD_THREADS) k_leaf_min(DedupArgs a, unsigned l
 		if ((threadIdx.x & 31) == 0 && vox) atomicAdd(voxels, (unsigned long long)vox);
 	}
 }
+// Lazy variant of MODE 0 (default when the order key fits one word and tileSeq ascends with the tile-local index).
+// Within one batch order keys compare like (t*, path'): t* is a root-pair index, and root pairs are sorted by (tile,
+// triangle).  So a node whose t* is larger than the smallest t* this CTA has seen for the same voxel mask cannot hold
+// the minimum and its code is never fetched; and when the batch comes after everything the table has seen (`later`), a
+// mask that already has an entry is frozen and not even t* is fetched.  What always streams is the mask byte (voxel
+// count): 1 B/node instead of 13 for all but the first nodes of each mask.  Loads are skipped per 4-node quad, i.e. per
+// 16 B of t* / 32 B of codes, so whole DRAM sectors stay untouched.  Skipping is only ever a filter on nodes that
+// provably lose; the 64-bit minimum itself is taken exactly as in MODE 0.
+__global__ void __launch_bounds__(DD_THREADS) k_leaf_lazy(DedupArgs a, unsigned long long* __restrict__ gmin, unsigned long long* __restrict__ voxels, int later) {
+	__shared__ unsigned long long smin[256];
+	__shared__ uint32_t sq[256];        // smallest t* seen for the mask by this CTA
+	__shared__ uint8_t sfrozen[256];
+	smin[threadIdx.x] = MAX_ORDER;
+	sq[threadIdx.x] = 0xFFFFFFFFu;
+	sfrozen[threadIdx.x] = (later && gmin[threadIdx.x] != MAX_ORDER) ? 1 : 0;
+	if (threadIdx.x == 0) sfrozen[0] = 1;   // empty nodes take no part
+	__syncthreads();
+	unsigned vox = 0;
+	const uint64_t nq = a.N >> 2;   // full quads
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	const uint32_t* __restrict__ m4 = reinterpret_cast<const uint32_t*>(a.mask);
+	const uint4* __restrict__ t4 = reinterpret_cast<const uint4*>(a.tstar);
+	const ulonglong2* __restrict__ c2 = reinterpret_cast<const ulonglong2*>(a.code);
+	auto visit = [&](unsigned m, uint32_t ts, unsigned long long cd) {
+		const unsigned long long O = order_key(cd, ts, a);
+		if (smin[m] > O) atomicMin(&smin[m], O);
+		if (sq[m] > ts) atomicMin(&sq[m], ts);
+	};
+	for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+		const uint32_t mm = m4[q];
+		vox += __popc(mm);
+		const unsigned m0 = mm & 0xFFu, m1 = (mm >> 8) & 0xFFu, m2 = (mm >> 16) & 0xFFu, m3 = mm >> 24;
+		const bool l0 = !sfrozen[m0], l1 = !sfrozen[m1], l2 = !sfrozen[m2], l3 = !sfrozen[m3];
+		if (!(l0 | l1 | l2 | l3)) continue;
+		const uint4 tt = t4[q];
+		const bool n0 = l0 && tt.x <= sq[m0], n1 = l1 && tt.y <= sq[m1], n2 = l2 && tt.z <= sq[m2], n3 = l3 && tt.w <= sq[m3];
+		if (n0 | n1) { const ulonglong2 ca = c2[2 * q]; if (n0) visit(m0, tt.x, ca.x); if (n1) visit(m1, tt.y, ca.y); }
+		if (n2 | n3) { const ulonglong2 cb = c2[2 * q + 1]; if (n2) visit(m2, tt.z, cb.x); if (n3) visit(m3, tt.w, cb.y); }
+	}
+	// tail (< 4 nodes)
+	for (uint64_t n = (nq << 2) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; n < a.N; n += stride) {
+		const unsigned m = a.mask[n];
+		vox += __popc(m);
+		if (!sfrozen[m]) { const uint32_t ts = a.tstar[n]; if (ts <= sq[m]) visit(m, ts, a.code[n]); }
+	}
+	__syncthreads();
+	unsigned long long v = smin[threadIdx.x];
+	if (v != MAX_ORDER && gmin[threadIdx.x] > v) atomicMin(&gmin[threadIdx.x], v);
+#pragma unroll
+	for (int d = 16; d; d >>= 1) vox += __shfl_xor_sync(0xFFFFFFFFu, vox, d);
+	if ((threadIdx.x & 31) == 0 && vox) atomicAdd(voxels, (unsigned long long)vox);
+}
+
 // wide mode, between the two passes: a mask whose high part improved in this batch forgets its old low part
 __global__ void k_leaf_reset_lo(unsigned long long* __restrict__ gmin, const unsigned long long* __restrict__ hiBefore) {
 	if (gmin[threadIdx.x] != hiBefore[threadIdx.x]) gmin[256 + threadIdx.x] = MAX_ORDER;
@@ -187,6 +240,7 @@ struct TableDev {
 	uint64_t capMask;
 	uint64_t countBefore, maxLoad;
 	uint32_t* flags;   // [0] overflow, [1] collision, [2] new entries
+	int later;         // every node of this launch has a larger order key than whatever the existing entries hold (DedupArgs::seqLo)
 };
 
 __device__ __forceinline__ bool table_find_or_claim(const TableDev& t, uint64_t tag, uint64_t& slot) {
@@ -221,9 +275,10 @@ __global__ void __launch_bounds__(DD_THREADS) k_insert(DedupArgs a, TableDev t) 
 	uint64_t tag = (CHMODE == CH_UID_U32) ? tag_of_key8(k8) : k64;
 	uint64_t slot;
 	if (!table_find_or_claim(t, tag, slot)) { a.ref[n] = NULLREF; return; }
+	a.ref[n] = (uint32_t)slot;
+	if (t.later && t.uid[slot] < t.countBefore) return;   // frozen entry (a slot claimed in this launch still has uid UNSET)
 	unsigned long long O = order_key(a.code[n], a.tstar[n], a);
 	if (t.minO[slot] > O) atomicMin(&t.minO[slot], O);
-	a.ref[n] = (uint32_t)slot;
 }
 
 // ------------------------------------------------------------------ KIND_K64, single pass (default for CH_MASK_U8)
@@ -263,7 +318,7 @@ __global__ void __launch_bounds__(DD_THREADS) k_insert_k64(DedupArgs a, TableDev
 		if (live[j]) {
 			idx[j] = mix64(key[j]) & t.capMask;
 			cur[j] = t.tag[idx[j]];
-			O[j] = order_key(a.code[n0 + j], a.tstar[n0 + j], a);
+			if (!t.later) O[j] = order_key(a.code[n0 + j], a.tstar[n0 + j], a);   // (later: only the rare new entries need it)
 		}
 	}
 #pragma unroll
@@ -294,7 +349,10 @@ __global__ void __launch_bounds__(DD_THREADS) k_insert_k64(DedupArgs a, TableDev
 		} else {
 			u = __ldcg(&t.uid[i]);
 		}
-		if (t.minO[i] > O[j]) atomicMin(&t.minO[i], O[j]);
+		if (!(t.later && u < t.countBefore)) {   // frozen entries keep their order key
+			if (t.later) O[j] = order_key(a.code[n], a.tstar[n], a);
+			if (t.minO[i] > O[j]) atomicMin(&t.minO[i], O[j]);
+		}
 		if (u == UNSET) {   // claimed a moment ago by another thread: resolved after the launch
 			const uint32_t k = atomicAdd(&op.counters[0], 1u);
 			if (k < op.listCap) op.unres[k] = (uint32_t)n;
@@ -362,6 +420,7 @@ __global__ void __launch_bounds__(DD_THREADS) k_winner(DedupArgs a, TableDev t, 
 	if (n >= a.N) return;
 	uint32_t slot = a.ref[n];
 	if (slot == NULLREF) return;
+	if (t.uid[slot] != UNSET) return;   // the entry has its key already (only this slot's winner sets the uid, and it is unique)
 	unsigned long long O = order_key(a.code[n], a.tstar[n], a);
 	if (t.minO[slot] != O) return;
 	uint32_t k8[8];
@@ -485,6 +544,15 @@ uint64_t next_pow2(uint64_t x) {
 	return p;
 }
 
+// Does this batch come after everything the table has seen (see DedupArgs::seqLo)?  Records the batch.
+bool later_batch(LevelTable& T, const DedupArgs& a) {
+	const char* e = getenv("SVB_DEDUP_LAZY");   // 0: always update every entry / read every field (A/B, verification)
+	const bool later = T.seenAny && a.seqLo > T.maxSeq && !(e && e[0] == '0');
+	T.maxSeq = T.seenAny ? std::max(T.maxSeq, a.seqHi) : a.seqHi;
+	T.seenAny = true;
+	return later;
+}
+
 void alloc_slots(cudaStream_t s, Pool& pool, LevelTable& T, uint64_t cap) {
 	T.cap = cap;
 	T.tag.reset(pool, cap);
@@ -504,6 +572,7 @@ TableDev dev_view(LevelTable& T, uint32_t* flags) {
 	t.countBefore = T.count;
 	t.maxLoad = T.cap - T.cap / 4;   // 75 %
 	t.flags = flags;
+	t.later = 0;
 	return t;
 }
 
@@ -556,8 +625,11 @@ void dedup_leaf(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, u
 	unsigned nb = blocks_for(a.N, DD_THREADS * 16);
 	if (nb > 148 * 8) nb = 148 * 8;   // persistent-style grid: 8 CTAs of 256 threads per SM, grid-stride
 	unsigned long long* g = (unsigned long long*)T.minO.p;
+	const bool later = later_batch(T, a);
 	if (!T.wide) {
-		k_leaf_min<0><<<nb, DD_THREADS, 0, s>>>(a, g, (unsigned long long*)d_voxels);
+		const char* e = getenv("SVB_LEAF_LAZY");   // 0: stream all 13 B of every node (k_leaf_min<0>)
+		if (a.seqMonotone && !(e && e[0] == '0')) k_leaf_lazy<<<nb, DD_THREADS, 0, s>>>(a, g, (unsigned long long*)d_voxels, later ? 1 : 0);
+		else k_leaf_min<0><<<nb, DD_THREADS, 0, s>>>(a, g, (unsigned long long*)d_voxels);
 		SVB_KERNEL_CHECK();
 		return;
 	}
@@ -572,7 +644,7 @@ void dedup_leaf(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, u
 }
 
 // KIND_K64 over u8 child masks in one pass over the nodes (k_insert_k64)
-static void dedup_k64_onepass(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, int npt) {
+static void dedup_k64_onepass(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, int npt, bool later) {
 	constexpr uint32_t LIST_CAP = 1u << 20;
 	DevBuf<uint32_t> flags(pool, 4), counters(pool, 4), newSlots(pool, LIST_CAP), unres(pool, LIST_CAP);
 	uint32_t h[4], hc[4];
@@ -581,6 +653,7 @@ static void dedup_k64_onepass(cudaStream_t s, Pool& pool, LevelTable& T, const D
 		flags.zero();
 		counters.zero();
 		TableDev t = dev_view(T, flags.p);
+		t.later = later ? 1 : 0;
 		OnePass op;
 		op.dCount = T.dCount.p; op.newSlots = newSlots.p; op.unres = unres.p; op.listCap = LIST_CAP; op.counters = counters.p;
 		if (npt == 2) k_insert_k64<2><<<blocks_for((a.N + 1) / 2, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
@@ -625,17 +698,19 @@ static void dedup_level_t(cudaStream_t s, Pool& pool, LevelTable& T, const Dedup
 	// their slots have no uid and are dropped by the rebuild).
 	uint64_t want = next_pow2(2 * (T.count + a.N / 8 + 1024));
 	if (want > T.cap) grow_slots(s, pool, T, want);
+	const bool later = later_batch(T, a);
 	const char* pk = getenv("SVB_K64_PERM");   // 0: the byte-by-byte key builder (A/B, verification)
 	const bool permKey = !(pk && pk[0] == '0');
 	if (CHMODE == CH_MASK_U8) {
 		const char* e = getenv("SVB_K64_ONEPASS");   // 0: insert + table scan + convert passes; 1 / 2: single pass, that many nodes per thread
 		const int npt = e ? atoi(e) : 2;
 		// marked slots must stay distinguishable from NULLREF and from uids
-		if (npt > 0 && T.cap <= (1ull << 28) && T.count + a.N / 8 < (1ull << 30)) { dedup_k64_onepass(s, pool, T, a, npt); return; }
+		if (npt > 0 && T.cap <= (1ull << 28) && T.count + a.N / 8 < (1ull << 30)) { dedup_k64_onepass(s, pool, T, a, npt, later); return; }
 	}
 	for (;;) {
 		flags.zero();
 		TableDev t = dev_view(T, flags.p);
+		t.later = later ? 1 : 0;
 		if (permKey) k_insert<CHMODE, CHMODE == CH_MASK_U8><<<nb, DD_THREADS, 0, s>>>(a, t);
 		else k_insert<CHMODE><<<nb, DD_THREADS, 0, s>>>(a, t);
 		SVB_KERNEL_CHECK();

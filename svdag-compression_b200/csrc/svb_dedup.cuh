@@ -19,6 +19,11 @@ struct DedupArgs {
 	const uint32_t* tileSeq = nullptr;  // device: tile_local -> global tile_seq (sub-octree sequence number)
 	const uint32_t* tileStart = nullptr;// device: tile_local -> first root-pair index of the tile (tstar - tileStart = triangle rank)
 	uint32_t* ref = nullptr;            // out: uid of each node's unique representative (NULLREF = empty node)
+	// tile_seq range of the batch.  Batches reach a table in ascending sub-octree order (svb_api.cu::run_tiles_split), so
+	// when seqLo exceeds everything the table has seen, no node of this batch can lower the order key of an entry that
+	// already exists: such entries are frozen and their nodes need neither code nor tstar (svb_dedup.cu).
+	uint32_t seqLo = 0, seqHi = 0;
+	bool seqMonotone = false;           // tileSeq ascends with the tile-local index: order keys of the batch compare like (tstar, path')
 };
 
 void table_init(cudaStream_t s, Pool& pool, LevelTable& T, int kind);

@@ -210,6 +210,9 @@ struct LevelTable {
 	// KIND_LEAF: 256-entry direct table lives in minO (cap = 256); wide: the order key of this level does not fit 63
 	// bits and is kept as (high part = tile_seq | t*, low part = path') in minO[0,256) / minO[256,512)
 	bool wide = false;
+	// largest tile_seq reduced into this table so far (see DedupArgs::seqLo)
+	bool seenAny = false;
+	uint32_t maxSeq = 0;
 	// finalize
 	DevBuf<uint32_t> rank;    // uid -> final id (LEAF: mask value -> final id)
 	uint64_t unique = 0;
