@@ -23,6 +23,9 @@ namespace svb {
 namespace {
 
 constexpr int DD_THREADS = 256;
+// A ref that still names a table slot (its entry was created by the running launch and has no uid yet) carries this
+// bit; final refs are uids < 2^31.  Slot arrays are kept <= 2^30 entries wherever marked refs are used.
+constexpr uint32_t REF_MARK = 0x80000000u;
 
 // tstar is the smallest root-pair index q that touches the node (svb_voxelize.cu::make_root_pairs); q - tileStart[tile]
 // = rank of the first-touch triangle among the tile's candidate triangles, monotone in the triangle id -- all the order
@@ -192,9 +195,9 @@ __global__ void __launch_bounds__(DD_THREADS) k_leaf_lazy(DedupArgs a, unsigned 
 	if (threadIdx.x == 0) sfrozen[0] = 1;   // empty nodes take no part
 	__syncthreads();
 	unsigned vox = 0;
-	const uint64_t nq = a.N >> 2;   // full quads
+	const uint64_t ng = a.N >> 4;   // full groups of 16 nodes = one 128-bit load of masks (bytes in flight per thread decide the rate of a 1 B/node stream)
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	const uint32_t* __restrict__ m4 = reinterpret_cast<const uint32_t*>(a.mask);
+	const uint4* __restrict__ m16 = reinterpret_cast<const uint4*>(a.mask);
 	const uint4* __restrict__ t4 = reinterpret_cast<const uint4*>(a.tstar);
 	const ulonglong2* __restrict__ c2 = reinterpret_cast<const ulonglong2*>(a.code);
 	auto visit = [&](unsigned m, uint32_t ts, unsigned long long cd) {
@@ -202,19 +205,23 @@ __global__ void __launch_bounds__(DD_THREADS) k_leaf_lazy(DedupArgs a, unsigned 
 		if (smin[m] > O) atomicMin(&smin[m], O);
 		if (sq[m] > ts) atomicMin(&sq[m], ts);
 	};
-	for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
-		const uint32_t mm = m4[q];
-		vox += __popc(mm);
+	auto quad = [&](uint32_t mm, uint64_t q) {   // nodes 4q .. 4q+3
+		if (!mm) return;
 		const unsigned m0 = mm & 0xFFu, m1 = (mm >> 8) & 0xFFu, m2 = (mm >> 16) & 0xFFu, m3 = mm >> 24;
 		const bool l0 = !sfrozen[m0], l1 = !sfrozen[m1], l2 = !sfrozen[m2], l3 = !sfrozen[m3];
-		if (!(l0 | l1 | l2 | l3)) continue;
+		if (!(l0 | l1 | l2 | l3)) return;
 		const uint4 tt = t4[q];
 		const bool n0 = l0 && tt.x <= sq[m0], n1 = l1 && tt.y <= sq[m1], n2 = l2 && tt.z <= sq[m2], n3 = l3 && tt.w <= sq[m3];
 		if (n0 | n1) { const ulonglong2 ca = c2[2 * q]; if (n0) visit(m0, tt.x, ca.x); if (n1) visit(m1, tt.y, ca.y); }
 		if (n2 | n3) { const ulonglong2 cb = c2[2 * q + 1]; if (n2) visit(m2, tt.z, cb.x); if (n3) visit(m3, tt.w, cb.y); }
+	};
+	for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += stride) {
+		const uint4 mm = m16[g];
+		vox += __popc(mm.x) + __popc(mm.y) + __popc(mm.z) + __popc(mm.w);
+		quad(mm.x, 4 * g); quad(mm.y, 4 * g + 1); quad(mm.z, 4 * g + 2); quad(mm.w, 4 * g + 3);
 	}
-	// tail (< 4 nodes)
-	for (uint64_t n = (nq << 2) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; n < a.N; n += stride) {
+	// tail (< 16 nodes)
+	for (uint64_t n = (ng << 4) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; n < a.N; n += stride) {
 		const unsigned m = a.mask[n];
 		vox += __popc(m);
 		if (!sfrozen[m]) { const uint32_t ts = a.tstar[n]; if (ts <= sq[m]) visit(m, ts, a.code[n]); }
@@ -264,8 +271,11 @@ __device__ __forceinline__ bool table_find_or_claim(const TableDev& t, uint64_t 
 	return false;
 }
 
-template <int CHMODE, bool PERM = false>
-__global__ void __launch_bounds__(DD_THREADS) k_insert(DedupArgs a, TableDev t) {
+// MARKED (inner levels): a node that finds an entry from an earlier launch is finished on the spot -- exact key check
+// against the entry's stored key, final uid as its ref -- and only the nodes of entries created by this launch leave a
+// marked slot for k_winner / k_convert, which are skipped altogether when the launch created nothing.
+template <int CHMODE, bool PERM = false, bool MARKED = false>
+__global__ void __launch_bounds__(DD_THREADS) k_insert(DedupArgs a, TableDev t, const uint32_t* __restrict__ dKey8) {
 	uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (n >= a.N) return;
 	uint32_t k8[8];
@@ -275,8 +285,20 @@ __global__ void __launch_bounds__(DD_THREADS) k_insert(DedupArgs a, TableDev t) 
 	uint64_t tag = (CHMODE == CH_UID_U32) ? tag_of_key8(k8) : k64;
 	uint64_t slot;
 	if (!table_find_or_claim(t, tag, slot)) { a.ref[n] = NULLREF; return; }
-	a.ref[n] = (uint32_t)slot;
-	if (t.later && t.uid[slot] < t.countBefore) return;   // frozen entry (a slot claimed in this launch still has uid UNSET)
+	if (MARKED) {
+		const uint32_t u = t.uid[slot];   // (a slot claimed in this launch still has uid UNSET)
+		if (u < t.countBefore) {
+			bool same = true;
+#pragma unroll
+			for (int c = 0; c < 8; ++c) same &= (dKey8[(uint64_t)u * 8 + c] == k8[c]);
+			if (!same) t.flags[1] = 1;
+			a.ref[n] = u;
+			if (t.later) return;   // frozen entry
+		} else a.ref[n] = REF_MARK | (uint32_t)slot;
+	} else {
+		a.ref[n] = (uint32_t)slot;
+		if (t.later && t.uid[slot] < t.countBefore) return;   // frozen entry
+	}
 	unsigned long long O = order_key(a.code[n], a.tstar[n], a);
 	if (t.minO[slot] > O) atomicMin(&t.minO[slot], O);
 }
@@ -296,7 +318,6 @@ struct OnePass {
 	uint32_t listCap;
 	uint32_t* counters;    // [0] unresolved nodes
 };
-constexpr uint32_t REF_MARK = 0x80000000u;
 
 template <int NPT>
 __global__ void __launch_bounds__(DD_THREADS) k_insert_k64(DedupArgs a, TableDev t, OnePass op) {
@@ -360,7 +381,8 @@ __global__ void __launch_bounds__(DD_THREADS) k_insert_k64(DedupArgs a, TableDev
 		}
 		out[j] = u;
 	}
-	if (NPT == 2 && n0 + 1 < a.N) *reinterpret_cast<uint2*>(a.ref + n0) = make_uint2(out[0], out[NPT - 1]);   // n0 is even
+	if (NPT == 2 && n0 + 1 < a.N) *reinterpret_cast<uint2*>(a.ref + n0) = make_uint2(out[0], out[NPT - 1]);   // n0 is a multiple of NPT
+	else if (NPT == 4 && n0 + 3 < a.N) *reinterpret_cast<uint4*>(a.ref + n0) = make_uint4(out[0], out[1 % NPT], out[2 % NPT], out[3 % NPT]);
 	else {
 #pragma unroll
 		for (int j = 0; j < NPT; ++j) if (n0 + j < a.N) a.ref[n0 + j] = out[j];
@@ -413,13 +435,14 @@ __global__ void __launch_bounds__(DD_THREADS) k_assign_k64(uint64_t cap, const u
 }
 
 // INNER: the node that holds the minimum order key of a new slot publishes the full key
-template <int CHMODE>
+template <int CHMODE, bool MARKED = false>
 __global__ void __launch_bounds__(DD_THREADS) k_winner(DedupArgs a, TableDev t, uint32_t* __restrict__ dCount,
                                                         uint64_t* __restrict__ dMinO, uint32_t* __restrict__ dKey8) {
 	uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (n >= a.N) return;
 	uint32_t slot = a.ref[n];
 	if (slot == NULLREF) return;
+	if (MARKED) { if (!(slot & REF_MARK)) return; slot &= ~REF_MARK; }
 	if (t.uid[slot] != UNSET) return;   // the entry has its key already (only this slot's winner sets the uid, and it is unique)
 	unsigned long long O = order_key(a.code[n], a.tstar[n], a);
 	if (t.minO[slot] != O) return;
@@ -434,12 +457,13 @@ __global__ void __launch_bounds__(DD_THREADS) k_winner(DedupArgs a, TableDev t, 
 }
 
 // slot -> uid for every node (+ exact key check for hashed keys)
-template <int CHMODE, bool VERIFY>
+template <int CHMODE, bool VERIFY, bool MARKED = false>
 __global__ void __launch_bounds__(DD_THREADS) k_convert(DedupArgs a, TableDev t, const uint32_t* __restrict__ dKey8) {
 	uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (n >= a.N) return;
 	uint32_t slot = a.ref[n];
 	if (slot == NULLREF) return;
+	if (MARKED) { if (!(slot & REF_MARK)) return; slot &= ~REF_MARK; }
 	uint32_t u = t.uid[slot];
 	if (VERIFY) {
 		uint32_t k8[8];
@@ -656,7 +680,8 @@ static void dedup_k64_onepass(cudaStream_t s, Pool& pool, LevelTable& T, const D
 		t.later = later ? 1 : 0;
 		OnePass op;
 		op.dCount = T.dCount.p; op.newSlots = newSlots.p; op.unres = unres.p; op.listCap = LIST_CAP; op.counters = counters.p;
-		if (npt == 2) k_insert_k64<2><<<blocks_for((a.N + 1) / 2, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
+		if (npt >= 4) k_insert_k64<4><<<blocks_for((a.N + 3) / 4, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
+		else if (npt == 2) k_insert_k64<2><<<blocks_for((a.N + 1) / 2, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
 		else k_insert_k64<1><<<blocks_for(a.N, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
 		SVB_KERNEL_CHECK();
 		SVB_CUDA(cudaMemcpyAsync(h, flags.p, 16, cudaMemcpyDeviceToHost, s));
@@ -707,12 +732,17 @@ static void dedup_level_t(cudaStream_t s, Pool& pool, LevelTable& T, const Dedup
 		// marked slots must stay distinguishable from NULLREF and from uids
 		if (npt > 0 && T.cap <= (1ull << 28) && T.count + a.N / 8 < (1ull << 30)) { dedup_k64_onepass(s, pool, T, a, npt, later); return; }
 	}
+	const char* mk = getenv("SVB_INNER_MARKED");   // 0: every node goes through the winner and convert passes
+	const bool markedWanted = !k64 && !(mk && mk[0] == '0');
+	bool marked = false;
 	for (;;) {
 		flags.zero();
 		TableDev t = dev_view(T, flags.p);
 		t.later = later ? 1 : 0;
-		if (permKey) k_insert<CHMODE, CHMODE == CH_MASK_U8><<<nb, DD_THREADS, 0, s>>>(a, t);
-		else k_insert<CHMODE><<<nb, DD_THREADS, 0, s>>>(a, t);
+		marked = markedWanted && T.cap <= (1ull << 30) && T.count + a.N < (1ull << 31);
+		if (marked) k_insert<CHMODE, false, CHMODE == CH_UID_U32><<<nb, DD_THREADS, 0, s>>>(a, t, T.dKey8.p);
+		else if (permKey) k_insert<CHMODE, CHMODE == CH_MASK_U8><<<nb, DD_THREADS, 0, s>>>(a, t, nullptr);
+		else k_insert<CHMODE><<<nb, DD_THREADS, 0, s>>>(a, t, nullptr);
 		SVB_KERNEL_CHECK();
 		SVB_CUDA(cudaMemcpyAsync(h, flags.p, 16, cudaMemcpyDeviceToHost, s));
 		SVB_CUDA(cudaStreamSynchronize(s));
@@ -730,6 +760,16 @@ static void dedup_level_t(cudaStream_t s, Pool& pool, LevelTable& T, const Dedup
 		}
 		k_convert<CHMODE, false><<<nb, DD_THREADS, 0, s>>>(a, t, nullptr);
 		SVB_KERNEL_CHECK();
+	} else if (marked) {
+		if (fresh) {   // only the nodes of the entries this launch created are still open
+			k_winner<CHMODE, true><<<nb, DD_THREADS, 0, s>>>(a, t, T.dCount.p, T.dMinO.p, T.dKey8.p);
+			SVB_KERNEL_CHECK();
+			k_convert<CHMODE, true, true><<<nb, DD_THREADS, 0, s>>>(a, t, T.dKey8.p);
+			SVB_KERNEL_CHECK();
+			SVB_CUDA(cudaMemcpyAsync(h, flags.p, 16, cudaMemcpyDeviceToHost, s));
+			SVB_CUDA(cudaStreamSynchronize(s));
+		}
+		if (h[1]) throw Error(SVB_ECOLLISION, "64-bit node-key hash collision (exact verify failed)");
 	} else {
 		if (fresh) {
 			k_winner<CHMODE><<<nb, DD_THREADS, 0, s>>>(a, t, T.dCount.p, T.dMinO.p, T.dKey8.p);
