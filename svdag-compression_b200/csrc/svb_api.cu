@@ -203,11 +203,12 @@ void set_order_key_width(BuildState& B, int Lt, int tb) {
 
 // bottom-up reduction of one batch's levels [lo_l, Lt-1] into the tables
 void dedup_batch(svb_ctx* c, BuildState& B, std::vector<BatchLevel>& lv, int Lt, uint32_t gbase, const uint32_t* d_tileSeq, const uint32_t* d_tileStart, int lo_l,
-                 const std::vector<uint32_t>& hseq) {
+                 const std::vector<uint32_t>& hseq, int hi_l = -1) {
+	if (hi_l < 0) hi_l = Lt - 1;   // (Lt - 2: the leaf level has been reduced already, see run_tile_batch)
 	const uint32_t seqLo = hseq.empty() ? 0 : *std::min_element(hseq.begin(), hseq.end()), seqHi = hseq.empty() ? 0 : *std::max_element(hseq.begin(), hseq.end());
 	const bool seqMono = std::is_sorted(hseq.begin(), hseq.end());
 	const int tb = gbase == 0 ? B.tbits : B.tbLocal;
-	for (int l = Lt - 1; l >= lo_l; --l) {
+	for (int l = hi_l; l >= lo_l; --l) {
 		uint32_t g = gbase + l;
 		BatchLevel& X = lv[l];
 		DedupArgs a;
@@ -254,11 +255,22 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 	std::vector<BatchLevel> lv;
 	DevBuf<uint32_t> dTileStart;   // per tile of the batch: first root-pair index (needed again by the order keys)
 	uint64_t pairs = 0;
+	// First touches of the leaf level are only needed for voxel masks the leaf table has no entry for.  A batch that comes
+	// after everything that table has seen is voxelized without them (no atomics / stores / 4 B per leaf node); if it does
+	// meet an unknown mask (dedup_leaf_known fails, nothing reduced yet) it is voxelized again, this time with them.
+	const uint32_t seqLo = *std::min_element(hseq.begin(), hseq.end());
+	const bool leafLevelBatch = gbase != 0 && !keepLevels && Lt >= 2 && B.tables[gbase + Lt - 1].kind == KIND_LEAF;
+	bool leafT = leafLevelBatch ? leaf_tstar_needed(B.tables[gbase + Lt - 1], seqLo) : true;
+	bool leafDone = false;
+	DevBuf<uint32_t> rootTri;   // root pair -> triangle (outlives the voxelizer: the leaf query below reads it)
+	uint64_t P = 0;
+	DevBuf<uint64_t> exactBefore(c->pool, 1);
+	SVB_CUDA(cudaMemcpyAsync(exactBefore.p, B.dExact.p, 8, cudaMemcpyDeviceToDevice, s));
+	for (;;) {
 	{
 		StageTimer tm(s);
 		ProfScope ps(c, "voxelize", gbase, nt);
-		DevBuf<uint32_t> ptri, pnode, rootTri;
-		uint64_t P = 0;
+		DevBuf<uint32_t> ptri, pnode;
 		int cellLo[3] = {1 << 30, 1 << 30, 1 << 30}, cellHi[3] = {-1, -1, -1};
 		for (uint32_t i = 0; i < nt; ++i) {
 			const TileHost& th = tiles[sel[a + i]];
@@ -268,9 +280,36 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 		make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, d_selPos, a, nt, ptri, pnode, rootTri, dTileStart, P, cellLo, cellHi);
 		bool direct = true;
 		for (uint32_t i = 0; i < nt && direct; ++i) direct = centre_chain_exact(hg[i], Lt);
-		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, rootTri.p, dTileStart.p, P, budget, nodeCap, lv, pairs, B.dExact.p, direct, B.allFlat);
+		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, rootTri.p, dTileStart.p, P, budget, nodeCap, lv, pairs, B.dExact.p, direct, B.allFlat, leafT);
 		ps.done(pairs, 36.0 * (double)c->T + 9.0 * (double)lv[Lt - 1].n);
 		B.msVox += tm.stop();
+	}
+	if (leafT) break;
+	{
+		StageTimer tm(s);
+		const uint32_t g = gbase + Lt - 1;
+		BatchLevel& X = lv[Lt - 1];
+		DedupArgs da;
+		da.N = X.n; da.mask = X.mask.p; da.code = X.code.p; da.l = Lt - 1;
+		da.tbits = B.tbLocal; da.tileSeq = dSeq.p; da.tileStart = dTileStart.p;
+		LeafQuery lq;
+		lq.tris = c->d_tris; lq.rootTri = rootTri.p; lq.P = P; lq.tiles = dTiles.p;
+		da.seqLo = seqLo; da.seqHi = *std::max_element(hseq.begin(), hseq.end()); da.seqMonotone = std::is_sorted(hseq.begin(), hseq.end());
+		ProfScope ps(c, "dedup_leaf", g, X.n);
+		leafDone = dedup_leaf_known(s, c->pool, B.tables[g], da, lq, B.dVoxels.p);
+		ps.done(0, 37.0 * (double)X.n);
+		B.msDedup += tm.stop();
+		if (leafDone) {
+			const int ob = B.tileBits + B.tbLocal + 3 * (Lt - 1);
+			if (ob > B.obits[g]) B.obits[g] = ob;
+			break;
+		}
+	}
+	// an unknown voxel mask: once more, with first touches
+	if (getenv("SVB_VX_STATS")) fprintf(stderr, "[vx-stats] batch [%u,%u): a voxel mask without an entry -- voxelizing again with leaf first touches\n", a, b);
+	leafT = true;
+	SVB_CUDA(cudaMemcpyAsync(B.dExact.p, exactBefore.p, 8, cudaMemcpyDeviceToDevice, s));
+	lv.clear();
 	}
 	B.pairs += pairs;
 	B.nBatches++;
@@ -292,7 +331,7 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 		B.rootChildMode = r.childMode;
 		root_key(s, r, B.rootKey.p);
 	} else {
-		dedup_batch(c, B, lv, Lt, gbase, dSeq.p, dTileStart.p, 0, hseq);
+		dedup_batch(c, B, lv, Lt, gbase, dSeq.p, dTileStart.p, 0, hseq, leafDone ? Lt - 2 : Lt - 1);
 		// remember what each sub-octree root was reduced to (uid, or the voxel mask for 1-level sub-octrees)
 		if (B.tables[gbase].kind == KIND_LEAF) k_scatter_u8<<<blocks_for(nt, 256), 256, 0, s>>>(nt, dSeq.p, lv[0].mask.p, B.tileRootRef.p);
 		else k_scatter_u32<<<blocks_for(nt, 256), 256, 0, s>>>(nt, dSeq.p, lv[0].ref.p, B.tileRootRef.p);

@@ -14,9 +14,12 @@
 //   KIND_K64   (level L-2): key = the 8 child masks = one exact 64-bit word (the 4^3 voxel block).
 //   KIND_INNER (above)    : key = 8 child uids, tagged by a 64-bit hash, verified exactly afterwards.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "svb_dedup.cuh"
+#include "svb_classify.cuh"
+#include "svb_sat.cuh"
 
 namespace svb {
 
@@ -232,6 +235,82 @@ __global__ void __launch_bounds__(DD_THREADS) k_leaf_lazy(DedupArgs a, unsigned 
 #pragma unroll
 	for (int d = 16; d; d >>= 1) vox += __shfl_xor_sync(0xFFFFFFFFu, vox, d);
 	if ((threadIdx.x & 31) == 0 && vox) atomicAdd(voxels, (unsigned long long)vox);
+}
+
+// Leaf level of a later batch whose first touches were not tracked: counts the voxels and checks that every voxel mask
+// of the batch already has a (frozen) entry -- then the level is reduced with nothing else to do.  *fail is raised
+// otherwise (the caller re-voxelizes the batch with first touches and takes the regular path).
+__global__ void __launch_bounds__(DD_THREADS) k_leaf_known(uint64_t N, const uint8_t* __restrict__ mask, const unsigned long long* __restrict__ gmin,
+                                                            unsigned long long* __restrict__ voxels, uint32_t* __restrict__ nUnknown, uint32_t* __restrict__ list, uint32_t listCap) {
+	__shared__ uint8_t sunknown[256];
+	sunknown[threadIdx.x] = (threadIdx.x != 0 && gmin[threadIdx.x] == MAX_ORDER) ? 1 : 0;
+	__syncthreads();
+	unsigned vox = 0;
+	const uint64_t ng = N >> 4;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	const uint4* __restrict__ m16 = reinterpret_cast<const uint4*>(mask);
+	auto unknown = [&](uint64_t n) {   // rare: a node whose voxel mask has no entry yet
+		const uint32_t k = atomicAdd(nUnknown, 1u);
+		if (k < listCap) list[k] = (uint32_t)n;
+	};
+	auto word = [&](uint32_t w, uint64_t n) {
+		vox += __popc(w);
+		if (sunknown[w & 0xFFu] | sunknown[(w >> 8) & 0xFFu] | sunknown[(w >> 16) & 0xFFu] | sunknown[w >> 24]) {
+#pragma unroll
+			for (int j = 0; j < 4; ++j) if (sunknown[(w >> (8 * j)) & 0xFFu]) unknown(n + j);
+		}
+	};
+	for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += stride) {
+		const uint4 mm = m16[g];
+		word(mm.x, 16 * g); word(mm.y, 16 * g + 4); word(mm.z, 16 * g + 8); word(mm.w, 16 * g + 12);
+	}
+	for (uint64_t n = (ng << 4) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += stride) {
+		const unsigned m = mask[n];
+		vox += __popc(m);
+		if (sunknown[m]) unknown(n);
+	}
+#pragma unroll
+	for (int d = 16; d; d >>= 1) vox += __shfl_xor_sync(0xFFFFFFFFu, vox, d);
+	if ((threadIdx.x & 31) == 0 && vox) atomicAdd(voxels, (unsigned long long)vox);
+}
+// One warp per listed leaf node: its first touch t* = the smallest root pair q of its tile whose triangle passes
+// testTriBox (reference operation order, tri_box_overlap) at every box on the node's path -- which is exactly when the
+// level-synchronous build holds a (triangle, node) pair for it (k_classify, svb_voxelize.cu).  Lanes test 32
+// consecutive q at a time; the node exists, so the search ends inside its tile's range.
+__global__ void __launch_bounds__(DD_THREADS) k_leaf_query(uint32_t cnt, const uint32_t* __restrict__ list, DedupArgs a, LeafQuery lq, unsigned long long* __restrict__ gmin) {
+	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (w >= cnt) return;
+	const uint64_t n = list[w];
+	const uint64_t cd = a.code[n];
+	const int l = a.l;
+	const uint32_t tile = (uint32_t)(cd >> (3 * l));
+	const TileGeom tg = reinterpret_cast<const TileGeom*>(lq.tiles)[tile];
+	uint32_t found = UNSET;
+	for (uint64_t q0 = a.tileStart[tile]; q0 < lq.P && found == UNSET; q0 += 32) {
+		const uint64_t q = q0 + lane;
+		bool ok = q < lq.P;
+		if (ok) {
+			const float* tp = lq.tris + 9ull * lq.rootTri[q];
+			double cx = tg.cx, cy = tg.cy, cz = tg.cz, k = tg.rootSide * 0.25;
+			for (int d = l - 1; d >= 0 && ok; --d) {
+				const int dig = (int)((cd >> (3 * d)) & 7);
+				cx = __dadd_rn(cx, (dig & 4) ? k : -k);
+				cy = __dadd_rn(cy, (dig & 2) ? k : -k);
+				cz = __dadd_rn(cz, (dig & 1) ? k : -k);
+				ok = tri_box_overlap(cx, cy, cz, k, tp);
+				k *= 0.5;
+			}
+		}
+		const unsigned b = __ballot_sync(0xFFFFFFFFu, ok);
+		if (b) found = (uint32_t)(q0 + (__ffs(b) - 1));
+	}
+	if (lane == 0 && found != UNSET) atomicMin(&gmin[a.mask[n]], (unsigned long long)order_key(cd, found, a));
+}
+__global__ void k_add_u64(unsigned long long* dst, const unsigned long long* src) { *dst += *src; }
+__global__ void k_count_known(const unsigned long long* __restrict__ gmin, uint32_t* __restrict__ out) {
+	const unsigned n = __syncthreads_count(threadIdx.x != 0 && gmin[threadIdx.x] != MAX_ORDER);
+	if (threadIdx.x == 0) *out = n;
 }
 
 // wide mode, between the two passes: a mask whose high part improved in this batch forgets its old low part
@@ -655,6 +734,15 @@ void dedup_leaf(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, u
 		if (a.seqMonotone && !(e && e[0] == '0')) k_leaf_lazy<<<nb, DD_THREADS, 0, s>>>(a, g, (unsigned long long*)d_voxels, later ? 1 : 0);
 		else k_leaf_min<0><<<nb, DD_THREADS, 0, s>>>(a, g, (unsigned long long*)d_voxels);
 		SVB_KERNEL_CHECK();
+		// did this batch bring new voxel masks?  (leaf_tstar_needed: the next batch goes without first touches only if not)
+		DevBuf<uint32_t> cnt(pool, 1);
+		k_count_known<<<1, 256, 0, s>>>((const unsigned long long*)g, cnt.p);
+		SVB_KERNEL_CHECK();
+		uint32_t h = 0;
+		SVB_CUDA(cudaMemcpyAsync(&h, cnt.p, 4, cudaMemcpyDeviceToHost, s));
+		SVB_CUDA(cudaStreamSynchronize(s));
+		T.lastAdded = h - T.known;
+		T.known = h;
 		return;
 	}
 	DevBuf<uint64_t> before(pool, 256);
@@ -708,6 +796,51 @@ static void dedup_k64_onepass(cudaStream_t s, Pool& pool, LevelTable& T, const D
 		SVB_KERNEL_CHECK();
 	}
 	T.count += fresh;
+}
+
+bool leaf_tstar_needed(const LevelTable& T, uint32_t seqLo) {
+	const char* e = getenv("SVB_DEDUP_LAZY");
+	const char* f = getenv("SVB_LEAF_NOTSTAR");   // 0: always track the first touches of the leaf level
+	if ((e && e[0] == '0') || (f && f[0] == '0')) return true;
+	// ... and only once a batch has come and gone without bringing a new voxel mask (a batch that does meet one
+	// has to be voxelized twice)
+	return !(T.kind == KIND_LEAF && !T.wide && T.seenAny && seqLo > T.maxSeq && T.lastAdded == 0);
+}
+
+bool dedup_leaf_known(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, const LeafQuery& lq, uint64_t* d_voxels) {
+	if (leaf_tstar_needed(T, a.seqLo)) return false;
+	T.lastAdded = 0;
+	if (a.N) {
+		constexpr uint32_t LIST_CAP = 1u << 18;
+		DevBuf<uint64_t> tmp(pool, 1);
+		DevBuf<uint32_t> cnt(pool, 1), list(pool, LIST_CAP);
+		tmp.zero();
+		cnt.zero();
+		unsigned nb = blocks_for(a.N, DD_THREADS * 64);
+		if (nb > 148 * 8) nb = 148 * 8;
+		k_leaf_known<<<nb, DD_THREADS, 0, s>>>(a.N, a.mask, (const unsigned long long*)T.minO.p, (unsigned long long*)tmp.p, cnt.p, list.p, LIST_CAP);
+		SVB_KERNEL_CHECK();
+		uint32_t h = 0;
+		SVB_CUDA(cudaMemcpyAsync(&h, cnt.p, 4, cudaMemcpyDeviceToHost, s));
+		SVB_CUDA(cudaStreamSynchronize(s));
+		if (h > LIST_CAP) return false;   // too many for the direct query: the caller voxelizes again with first touches
+		if (h) {
+			if (getenv("SVB_VX_STATS")) fprintf(stderr, "[vx-stats] leaf level without first touches: %u nodes with a new voxel mask, queried directly\n", h);
+			k_leaf_query<<<blocks_for((uint64_t)h * 32, DD_THREADS), DD_THREADS, 0, s>>>(h, list.p, a, lq, (unsigned long long*)T.minO.p);
+			SVB_KERNEL_CHECK();
+			k_count_known<<<1, 256, 0, s>>>((const unsigned long long*)T.minO.p, cnt.p);
+			SVB_KERNEL_CHECK();
+			SVB_CUDA(cudaMemcpyAsync(&h, cnt.p, 4, cudaMemcpyDeviceToHost, s));
+			SVB_CUDA(cudaStreamSynchronize(s));
+			T.lastAdded = h - T.known;
+			T.known = h;
+		}
+		k_add_u64<<<1, 1, 0, s>>>((unsigned long long*)d_voxels, (const unsigned long long*)tmp.p);
+		SVB_KERNEL_CHECK();
+		SVB_CUDA(cudaStreamSynchronize(s));   // the temporaries go back to the pool
+	}
+	later_batch(T, a);   // records the batch
+	return true;
 }
 
 template <int CHMODE>

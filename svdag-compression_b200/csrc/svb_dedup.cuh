@@ -31,6 +31,22 @@ void table_init(cudaStream_t s, Pool& pool, LevelTable& T, int kind);
 // KIND_LEAF: nodes are bare 8-bit voxel masks. Accumulates popcounts into *d_voxels.
 void dedup_leaf(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, uint64_t* d_voxels);
 
+// Must the voxelizer track the first touches (t*) of the leaf level for a batch whose smallest tile_seq is seqLo?  Not
+// when the batch comes after everything the table has seen: then only voxel masks without an entry would need them.
+bool leaf_tstar_needed(const LevelTable& T, uint32_t seqLo);
+// Leaf level without t* (a.tstar may be null): true when every voxel mask of the batch already had an entry -- the level
+// is then reduced (voxels counted, batch recorded).  false: nothing was changed; re-voxelize with t* and use dedup_leaf.
+// The few leaf nodes whose voxel mask has no entry yet get their first touch from a direct query (LeafQuery: the first
+// root pair of the node's tile whose triangle passes the reference-order predicate at every box on the node's path);
+// a batch with more than a few 10^5 such nodes is refused instead.
+struct LeafQuery {
+	const float* tris = nullptr;        // 9 floats per triangle
+	const uint32_t* rootTri = nullptr;  // root pair q -> triangle
+	uint64_t P = 0;                     // root pairs of the batch
+	const void* tiles = nullptr;        // TileGeom per tile of the batch
+};
+bool dedup_leaf_known(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, const LeafQuery& lq, uint64_t* d_voxels);
+
 // KIND_K64 / KIND_INNER.  Throws Error(SVB_ECOLLISION) if the exact verify pass finds two different
 // keys behind one 64-bit tag.
 void dedup_level(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a);

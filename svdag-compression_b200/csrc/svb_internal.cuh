@@ -213,6 +213,7 @@ struct LevelTable {
 	// largest tile_seq reduced into this table so far (see DedupArgs::seqLo)
 	bool seenAny = false;
 	uint32_t maxSeq = 0;
+	uint32_t known = 0, lastAdded = 0;   // KIND_LEAF: voxel masks with an entry, and how many of them the last batch brought
 	// finalize
 	DevBuf<uint32_t> rank;    // uid -> final id (LEAF: mask value -> final id)
 	uint64_t unique = 0;

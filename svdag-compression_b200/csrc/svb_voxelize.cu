@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_flat_leaves(uint64_t P, co
 	const uint64_t cd = code[n];
 	const unsigned nm = mask[n];
 	const uint32_t base = childBase[n];
-	const bool star = STAR && tstar[n] == t;
+	const bool star = STAR && ctstar && tstar[n] == t;
 	const double* tg = reinterpret_cast<const double*>(tiles + (uint32_t)(cd >> (3 * (lc - 1))));
 	const float* tp = tris + 9ull * rootTri[t];   // t itself (the root pair index) is what orders first touches
 	unsigned lohi[3][2];
@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_flat_leaves(uint64_t P, co
 		acc |= mc << (8 * (child & 3));
 		// precheck: read before the atomic -- pays off only where many pairs share a node (upper levels); at the leaf
 		// levels (~1.4 pairs per node) the read is a wasted round trip and the reduction goes out fire-and-forget
+		if (!ctstar) continue;   // first touches of the leaf nodes are not tracked
 		if (star) ctstar[child] = t;
 		else if (!precheck || ctstar[child] > t) atomicMin(&ctstar[child], t);
 	}
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(VX_THREADS) k_emit(uint64_t P, const uint32_t*
 				s_node[o] = child;
 				s_fl[o] = (uint16_t)fl;
 				++o;
-				if (!precheck || ctstar[child] > t) atomicMin(&ctstar[child], t);
+				if (ctstar && (!precheck || ctstar[child] > t)) atomicMin(&ctstar[child], t);   // (ctstar == nullptr: first touches of the children are not tracked)
 			}
 		}
 		__syncthreads();
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_emit_pipe(uint64_t P, cons
 				s_fl[o] = (uint16_t)f0.fl;
 				if (STAR) s_star[o] = (uint8_t)(g0.ts == t);
 				++o;
-				if (!REDOUT && !(STAR && g0.ts == t) && (!precheck || ctstar[child] > t)) atomicMin(&ctstar[child], t);
+				if (!REDOUT && ctstar && !(STAR && g0.ts == t) && (!precheck || ctstar[child] > t)) atomicMin(&ctstar[child], t);
 			}
 		}
 		__syncthreads();
@@ -447,6 +448,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_emit_pipe(uint64_t P, cons
 			otri[runF + i] = t;
 			onode[runF + i] = child;
 			oflags[runF + i] = s_fl[i];
+			if (!ctstar) continue;   // first touches of the children are not tracked (leaf level of a later batch, see voxelize_batch)
 			if (STAR && s_star[i]) ctstar[child] = t;
 			else if (REDOUT && (!precheck || ctstar[child] > t)) atomicMin(&ctstar[child], t);
 		}
@@ -456,6 +458,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_emit_pipe(uint64_t P, cons
 				otri[runS + i] = t;
 				onode[runS + i] = child;
 				oflags[runS + i] = s_fl[nFlat + i];
+				if (!ctstar) continue;
 				if (STAR && s_star[nFlat + i]) ctstar[child] = t;
 				else if (REDOUT && (!precheck || ctstar[child] > t)) atomicMin(&ctstar[child], t);
 			}
@@ -630,7 +633,7 @@ void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T
 
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
                     DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, const uint32_t* rootTri, const uint32_t* tileStart, uint64_t P,
-                    uint64_t budget_bytes, uint64_t nodeCap, std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre, bool allFlat) {
+                    uint64_t budget_bytes, uint64_t nodeCap, std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre, bool allFlat, bool leafTstar) {
 	if (const char* e = getenv("SVB_CENTRE")) directCentre = directCentre && e[0] != 'c';   // SVB_CENTRE=chain: always replay the chain
 	lv.clear();
 	lv.resize(Lt);
@@ -739,8 +742,13 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		BatchLevel& C = lv[l + 1];
 		C.n = Nn;
 		C.code.reset(pool, Nn);
-		C.tstar.reset(pool, Nn);
-		C.tstar.fill_ff();
+		// first touches of the leaf nodes only matter for voxel masks the dedup table does not know yet: a later batch
+		// goes without them (leafTstar == false; the caller re-runs the batch in the rare case that it does meet one)
+		const bool trackKids = leafTstar || (l + 1 < Lt - 1);
+		if (trackKids) {
+			C.tstar.reset(pool, Nn);
+			C.tstar.fill_ff();
+		}
 		L.childBase.reset(pool, L.n);
 		if (childrenPipe) k_children<true><<<blocks_for(L.n, VX_TILE), VX_THREADS, 0, s>>>(L.n, L.code.p, L.mask.p, nodeOffs.p, L.childBase.p, C.code.p);
 		else k_children<false><<<blocks_for(L.n, VX_TILE), VX_THREADS, 0, s>>>(L.n, L.code.p, L.mask.p, nodeOffs.p, L.childBase.p, C.code.p);
@@ -754,7 +762,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 #define SVB_LAUNCH_FL(DIR, N, OFF, ONLY) if (occLeaves >= 8) SVB_LAUNCH_FL2(DIR, 8, N, OFF, ONLY); else SVB_LAUNCH_FL2(DIR, 6, N, OFF, ONLY)
 #define SVB_LAUNCH_FL2(DIR, MB, N, OFF, ONLY) if (starStore) SVB_LAUNCH_FL3(DIR, MB, true, N, OFF, ONLY); else SVB_LAUNCH_FL3(DIR, MB, false, N, OFF, ONLY)
 #define SVB_LAUNCH_FL3(DIR, MB, ST, N, OFF, ONLY) k_flat_leaves<DIR, MB, ST><<<blocks_for(N, VX_THREADS), VX_THREADS, 0, s>>>(N, ptri.p + (OFF), pnode.p + (OFF), pflags.p + (OFF), hit.p + (OFF), \
-			L.code.p, L.mask.p, L.childBase.p, L.tstar.p, l + 1, kscale, d_tiles, d_tris, rootTri, C.mask.p, C.tstar.p, ONLY, precheckKids)
+			L.code.p, L.mask.p, L.childBase.p, L.tstar.p, l + 1, kscale, d_tiles, d_tris, rootTri, C.mask.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), ONLY, precheckKids)
 			if (F) { if (directCentre) SVB_LAUNCH_FL(true, F, 0, 0); else SVB_LAUNCH_FL(false, F, 0, 0); SVB_KERNEL_CHECK(); }
 			if (fuseS && S && cSF) { if (directCentre) SVB_LAUNCH_FL(true, S, Fa, 1); else SVB_LAUNCH_FL(false, S, Fa, 1); SVB_KERNEL_CHECK(); }
 #undef SVB_LAUNCH_FL
@@ -762,7 +770,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 #undef SVB_LAUNCH_FL3
 			pairsTotal += cF + (fuseS ? cSF : 0);   // decided here instead of as pairs of the last level
 		} else if (F) {
-#define SVB_EMIT_ARGS_F(...) F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p, __VA_ARGS__ ntri.p, nnode.p, nflags.p, C.tstar.p, 0, precheckKids
+#define SVB_EMIT_ARGS_F(...) F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p, __VA_ARGS__ ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), 0, precheckKids
 			const unsigned nb = blocks_for(F, VX_TILE);
 			if (emitPipe == 0) k_emit<false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F());
 			else if (!emitRedOut && !starStore) k_emit_pipe<false, 8, false, false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F(L.tstar.p,));
@@ -773,7 +781,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 			SVB_KERNEL_CHECK();
 		}
 		if (S) {
-#define SVB_EMIT_ARGS_S(...) S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, cFe, Fan, L.mask.p, L.childBase.p, __VA_ARGS__ ntri.p, nnode.p, nflags.p, C.tstar.p, fuseS ? 1 : 0, precheckKids
+#define SVB_EMIT_ARGS_S(...) S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, cFe, Fan, L.mask.p, L.childBase.p, __VA_ARGS__ ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), fuseS ? 1 : 0, precheckKids
 			const unsigned nb = blocks_for(S, VX_TILE);
 			if (emitPipe == 0) k_emit<true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S());
 			else if (!emitRedOut && !starStore) k_emit_pipe<true, 8, false, false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S(L.tstar.p,));
