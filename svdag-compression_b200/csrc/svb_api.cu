@@ -78,6 +78,29 @@ struct ProfScope {
 	}
 };
 
+struct CtxProfHook : ProfHook {
+	svb_ctx* c;
+	explicit CtxProfHook(svb_ctx* ctx) : c(ctx) {}
+	int begin(const char* name, uint32_t level, uint64_t n_in) override {
+		svb_ctx::PendingProf p;
+		memset(&p.rec, 0, sizeof(p.rec));
+		snprintf(p.rec.name, sizeof(p.rec.name), "%s", name);
+		p.rec.level = level;
+		p.rec.n_in = n_in;
+		cudaEventCreate(&p.e0);
+		cudaEventCreate(&p.e1);
+		cudaEventRecord(p.e0, c->stream);
+		c->pending.push_back(p);
+		return (int)c->pending.size() - 1;
+	}
+	void end(int id, uint64_t n_out, double bytes) override {
+		cudaEventRecord(c->pending[id].e1, c->stream);
+		c->pending[id].closed = true;
+		c->pending[id].rec.n_out = n_out;
+		c->pending[id].rec.bytes = bytes;
+	}
+};
+
 void resolve_profile(svb_ctx* c) {
 	for (auto& p : c->pending) {
 		if (p.closed) {   // scopes left by an exception (e.g. a batch that had to be split) never recorded e1
@@ -278,9 +301,10 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 			cellHi[0] = std::max(cellHi[0], th.ix); cellHi[1] = std::max(cellHi[1], th.iy); cellHi[2] = std::max(cellHi[2], th.iz);
 		}
 		make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, d_selPos, a, nt, ptri, pnode, rootTri, dTileStart, P, cellLo, cellHi);
+		CtxProfHook hook(c);
 		bool direct = true;
 		for (uint32_t i = 0; i < nt && direct; ++i) direct = centre_chain_exact(hg[i], Lt);
-		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, rootTri.p, dTileStart.p, P, budget, nodeCap, lv, pairs, B.dExact.p, direct, B.allFlat, leafT);
+		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, rootTri.p, dTileStart.p, P, budget, nodeCap, lv, pairs, B.dExact.p, direct, B.allFlat, leafT, c->profiling ? &hook : nullptr);
 		ps.done(pairs, 36.0 * (double)c->T + 9.0 * (double)lv[Lt - 1].n);
 		B.msVox += tm.stop();
 	}

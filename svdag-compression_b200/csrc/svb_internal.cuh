@@ -219,6 +219,15 @@ struct LevelTable {
 	uint64_t unique = 0;
 };
 
+// Per-launch timing records from inside the stage drivers (svb_api.cu implements it on top of the context's profile list;
+// null = not profiling).  begin() records an event on the stage's stream, end() the closing one plus the launch's units
+// and algorithmic bytes.
+struct ProfHook {
+	virtual int begin(const char* name, uint32_t level, uint64_t n_in) = 0;
+	virtual void end(int id, uint64_t n_out, double bytes) = 0;
+	virtual ~ProfHook() {}
+};
+
 // ------------------------------------------------------------------ final octree (what getNodeData() exposes)
 struct OutLevel {
 	uint64_t n = 0;

@@ -633,7 +633,7 @@ void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T
 
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
                     DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, const uint32_t* rootTri, const uint32_t* tileStart, uint64_t P,
-                    uint64_t budget_bytes, uint64_t nodeCap, std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre, bool allFlat, bool leafTstar) {
+                    uint64_t budget_bytes, uint64_t nodeCap, std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre, bool allFlat, bool leafTstar, ProfHook* prof) {
 	if (const char* e = getenv("SVB_CENTRE")) directCentre = directCentre && e[0] != 'c';   // SVB_CENTRE=chain: always replay the chain
 	lv.clear();
 	lv.resize(Lt);
@@ -750,9 +750,12 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 			C.tstar.fill_ff();
 		}
 		L.childBase.reset(pool, L.n);
+		// algorithmic bytes: 9 B read (code, mask) + 4 B childBase written per node, 8 B code written per child node
+		const int pidC = prof ? prof->begin("children", (uint32_t)l, L.n) : -1;
 		if (childrenPipe) k_children<true><<<blocks_for(L.n, VX_TILE), VX_THREADS, 0, s>>>(L.n, L.code.p, L.mask.p, nodeOffs.p, L.childBase.p, C.code.p);
 		else k_children<false><<<blocks_for(L.n, VX_TILE), VX_THREADS, 0, s>>>(L.n, L.code.p, L.mask.p, nodeOffs.p, L.childBase.p, C.code.p);
 		SVB_KERNEL_CHECK();
+		if (prof) prof->end(pidC, Nn, 13.0 * (double)L.n + 8.0 * (double)Nn);
 		DevBuf<uint32_t> ntri(pool, Pn + 16), nnode(pool, Pn + 16);
 		DevBuf<uint16_t> nflags(pool, Pn + 16);
 		if (fuseFlat) {
@@ -772,6 +775,9 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		} else if (F) {
 #define SVB_EMIT_ARGS_F(...) F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p, __VA_ARGS__ ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), 0, precheckKids
 			const unsigned nb = blocks_for(F, VX_TILE);
+			// algorithmic bytes: 11 B pair + 9 B node fields (mask, childBase, t*) read per parent pair, 10 B pair written
+			// (+ 4 B first touch when tracked) per child pair
+			const int pidE = prof ? prof->begin("emit", (uint32_t)l, F) : -1;
 			if (emitPipe == 0) k_emit<false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F());
 			else if (!emitRedOut && !starStore) k_emit_pipe<false, 8, false, false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F(L.tstar.p,));
 			else if (!emitRedOut) k_emit_pipe<false, 8, false, true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F(L.tstar.p,));
@@ -779,10 +785,13 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 			else k_emit_pipe<false, 8, true, true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F(L.tstar.p,));
 #undef SVB_EMIT_ARGS_F
 			SVB_KERNEL_CHECK();
+			if (prof) prof->end(pidE, cF, 20.0 * (double)F + (trackKids ? 14.0 : 10.0) * (double)cF);
 		}
 		if (S) {
 #define SVB_EMIT_ARGS_S(...) S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, cFe, Fan, L.mask.p, L.childBase.p, __VA_ARGS__ ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), fuseS ? 1 : 0, precheckKids
 			const unsigned nb = blocks_for(S, VX_TILE);
+			const uint64_t kids = fuseS ? cS - cSF : cS;
+			const int pidE = prof ? prof->begin("emit", (uint32_t)l, S) : -1;
 			if (emitPipe == 0) k_emit<true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S());
 			else if (!emitRedOut && !starStore) k_emit_pipe<true, 8, false, false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S(L.tstar.p,));
 			else if (!emitRedOut) k_emit_pipe<true, 8, false, true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S(L.tstar.p,));
@@ -790,6 +799,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 			else k_emit_pipe<true, 8, true, true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S(L.tstar.p,));
 #undef SVB_EMIT_ARGS_S
 			SVB_KERNEL_CHECK();
+			if (prof) prof->end(pidE, kids, 20.0 * (double)S + (trackKids ? 14.0 : 10.0) * (double)kids);
 		}
 		ptri = std::move(ntri);
 		pnode = std::move(nnode);

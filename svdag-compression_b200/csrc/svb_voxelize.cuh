@@ -37,7 +37,9 @@ uint32_t max_candidates_per_tile(cudaStream_t s, Pool& pool, const float* d_tris
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
                     DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, const uint32_t* rootTri, const uint32_t* tileStart, uint64_t P,
                     uint64_t budget_bytes, uint64_t nodeCap, std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre, bool allFlat,
-                    bool leafTstar = true);
+                    bool leafTstar = true, ProfHook* prof = nullptr);
+// prof: per-launch records "emit" (n_in = parent pairs, n_out = child pairs) and "children" (n_in = nodes, n_out = child nodes)
+// with their algorithmic bytes.
 // leafTstar == false: the first touches of the deepest level are not tracked (lv[Lt-1].tstar stays empty); valid only when
 // the caller can reduce that level without them (dedup_leaf_known, svb_dedup.cuh).
 
