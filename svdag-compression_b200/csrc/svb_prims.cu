@@ -6,6 +6,8 @@
 //  * radix sort: stable LSD, 8-bit digits, (u64 key, u32 payload); used to rank the unique
 //    nodes of a level by their order key (U_l elements, not N_l).
 #include "svb_classify.cuh"
+#include <cstdlib>
+
 #include "svb_internal.cuh"
 
 namespace svb {
@@ -106,6 +108,76 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const uint32_t* __re
 	if (threadIdx.x == 0) *total = carry;
 }
 
+// The same with 1024 threads x 16 sums per trip and 64-bit arithmetic throughout: the single-CTA pass over the tile sums
+// is a serial chain of trips (two barriers each), 4 of them per level -- 8x fewer trips (default; SVB_SCAN_WIDE=0: the
+// kernel above).
+constexpr int SW_THREADS = 1024, SW_ITEMS = 16;
+__global__ void __launch_bounds__(SW_THREADS) k_scan_sums_wide(const uint32_t* __restrict__ sums, uint64_t nb, uint64_t* __restrict__ offs, uint64_t* __restrict__ total) {
+	__shared__ unsigned long long wsum[SW_THREADS / 32];
+	__shared__ unsigned long long carry;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (uint64_t base = 0; base < nb; base += (uint64_t)SW_THREADS * SW_ITEMS) {
+		const uint64_t i0 = base + (uint64_t)threadIdx.x * SW_ITEMS;
+		uint32_t v[SW_ITEMS];
+		if (i0 + SW_ITEMS <= nb) {   // i0 is a multiple of 16: 64-byte aligned
+#pragma unroll
+			for (int j = 0; j < SW_ITEMS / 4; ++j) {
+				const uint4 q = reinterpret_cast<const uint4*>(sums + i0)[j];
+				v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+			}
+		} else {
+#pragma unroll
+			for (int j = 0; j < SW_ITEMS; ++j) v[j] = (i0 + j < nb) ? sums[i0 + j] : 0;
+		}
+		unsigned long long x = 0;
+#pragma unroll
+		for (int j = 0; j < SW_ITEMS; ++j) x += v[j];
+		unsigned long long inc = x;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+			if (lane >= d) inc += y;
+		}
+		const unsigned long long c0 = carry;   // (written after the second barrier of the previous trip)
+		if (lane == 31) wsum[w] = inc;
+		__syncthreads();
+		if (w == 0) {
+			const unsigned long long sv = wsum[lane];
+			unsigned long long si = sv;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, si, d);
+				if (lane >= d) si += y;
+			}
+			wsum[lane] = si - sv;
+			if (lane == 31) carry = c0 + si;
+		}
+		__syncthreads();
+		unsigned long long o = c0 + wsum[w] + (inc - x);
+		if (i0 + SW_ITEMS <= nb) {
+#pragma unroll
+			for (int j = 0; j < SW_ITEMS; j += 2) {
+				ulonglong2 pr;
+				pr.x = o; o += v[j];
+				pr.y = o; o += v[j + 1];
+				reinterpret_cast<ulonglong2*>(offs + i0)[j >> 1] = pr;
+			}
+		} else {
+#pragma unroll
+			for (int j = 0; j < SW_ITEMS; ++j) { if (i0 + j < nb) offs[i0 + j] = o; o += v[j]; }
+		}
+		__syncthreads();   // wsum / carry are rewritten by the next trip
+	}
+	if (threadIdx.x == 0) *total = carry;
+}
+static void launch_scan_sums(cudaStream_t s, const uint32_t* sums, uint64_t nb, uint64_t* offs, uint64_t* total) {
+	const char* e = getenv("SVB_SCAN_WIDE");
+	if (e && e[0] == '0') k_scan_sums<<<1, SCAN_THREADS, 0, s>>>(sums, nb, offs, total);
+	else k_scan_sums_wide<<<1, SW_THREADS, 0, s>>>(sums, nb, offs, total);
+}
+
 // pair streams: per tile of SCAN_TILE pairs, the number of child pairs (popcount of the hit masks) and the number of
 // those whose flags put them into the flat stream (pair_is_fast, svb_classify.cuh), in one pass
 __global__ void __launch_bounds__(SCAN_THREADS) k_pair_reduce(const uint8_t* __restrict__ hit, const uint16_t* __restrict__ fl, uint64_t n,
@@ -165,7 +237,7 @@ void scan_impl(cudaStream_t s, Pool& pool, In in, uint64_t n, uint32_t* out, uin
 	DevBuf<uint64_t> offs(pool, nb);
 	k_scan_reduce<In><<<(unsigned)nb, SCAN_THREADS, 0, s>>>(in, n, sums.p);
 	SVB_KERNEL_CHECK();
-	k_scan_sums<<<1, SCAN_THREADS, 0, s>>>(sums.p, nb, offs.p, d_total);
+	launch_scan_sums(s, sums.p, nb, offs.p, d_total);
 	SVB_KERNEL_CHECK();
 	k_scan_apply<In><<<(unsigned)nb, SCAN_THREADS, 0, s>>>(in, n, offs.p, out);
 	SVB_KERNEL_CHECK();
@@ -240,7 +312,7 @@ void scan_tiles_popc8(cudaStream_t s, Pool& pool, const uint8_t* bytes, uint64_t
 	DevBuf<uint32_t> sums(pool, nb);
 	k_scan_reduce<Popc8In><<<(unsigned)nb, SCAN_THREADS, 0, s>>>(Popc8In{bytes}, n, sums.p);
 	SVB_KERNEL_CHECK();
-	k_scan_sums<<<1, SCAN_THREADS, 0, s>>>(sums.p, nb, tileOffs.p, d_total);
+	launch_scan_sums(s, sums.p, nb, tileOffs.p, d_total);
 	SVB_KERNEL_CHECK();
 }
 
@@ -253,9 +325,9 @@ void scan_tiles_pairs(cudaStream_t s, Pool& pool, const uint8_t* hit, const uint
 	DevBuf<uint32_t> sumsA(pool, nb), sumsB(pool, nb);
 	k_pair_reduce<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(hit, flags, n, sumsA.p, sumsB.p);
 	SVB_KERNEL_CHECK();
-	k_scan_sums<<<1, SCAN_THREADS, 0, s>>>(sumsA.p, nb, tileOffsA.p, d_totalA);
+	launch_scan_sums(s, sumsA.p, nb, tileOffsA.p, d_totalA);
 	SVB_KERNEL_CHECK();
-	k_scan_sums<<<1, SCAN_THREADS, 0, s>>>(sumsB.p, nb, tileOffsB.p, d_totalB);
+	launch_scan_sums(s, sumsB.p, nb, tileOffsB.p, d_totalB);
 	SVB_KERNEL_CHECK();
 }
 
