@@ -360,3 +360,72 @@ def test_svbuilder_cli_from_svdag_input(pkg, tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert (d / "m_7_7.svdag").read_bytes() == cross["files"]["svdag"]
     assert (d / "m_7_7-multi.svdag").read_bytes() == cross["files"]["multi_svdag"]
+
+
+# ------------------------------------------------------------------ round 1e: reduced-work paths against the plain ones
+LEGACY = {  # every environment toggle that selects the straightforward variant of a kernel / pass
+    "SVB_EMIT_PIPE": "0", "SVB_CHILDREN_PIPE": "0", "SVB_STAR_STORE": "0", "SVB_K64_PERM": "0", "SVB_K64_ONEPASS": "0",
+    "SVB_DEDUP_LAZY": "0", "SVB_LEAF_LAZY": "0", "SVB_INNER_MARKED": "0", "SVB_LEAF_NOTSTAR": "0", "SVB_SCAN_WIDE": "0",
+}
+
+
+@pytest.mark.parametrize("mesh,kw,levels,step,budget", [
+    ("city", dict(lots=16), 10, 2, 24 << 20),
+    ("sphere", dict(n_lat=64, n_lon=128), 9, 2, 8 << 20),
+    ("terrain", dict(n=96), 9, 3, 8 << 20),
+    ("soup", dict(n=1200, seed=3), 8, 2, 4 << 20),
+], ids=["city", "sphere", "terrain", "soup"])
+def test_reduced_work_paths_equal_plain_paths(pkg, orc, meshgen, mesh, kw, levels, step, budget, monkeypatch):
+    """Single-pass / frozen-entry dedup, lazy leaf pass, leaf level without first touches (direct query for new voxel
+    masks), star stores, pipelined emit: many small batches, default paths vs. every toggle off vs. the oracle."""
+    tris = meshgen.make_mesh(mesh, **kw)
+    o = orc.OracleOctree(tris)
+    o.build(levels, step)
+    fast = pkg.GeomOctree(tris)
+    fast.set_batch_budget(budget)
+    st = fast.build(levels, step)
+    for k in ("nTotalVoxels", "nNodesSVO", "nNodesDAG"):
+        assert st[k] == o.stat(k), k
+    _assert_levels_equal(fast.levels_host(), _oracle_levels(o), "DAG (default paths, many batches)")
+    for k, v in LEGACY.items():
+        monkeypatch.setenv(k, v)
+    plain = pkg.GeomOctree(tris)
+    plain.set_batch_budget(budget)
+    sp = plain.build(levels, step)
+    assert (sp["nTotalVoxels"], sp["nNodesSVO"], sp["nNodesDAG"], sp["nBatches"]) == (st["nTotalVoxels"], st["nNodesSVO"], st["nNodesDAG"], st["nBatches"])
+    _assert_levels_equal(plain.levels_host(), _oracle_levels(o), "DAG (plain paths, many batches)")
+
+
+@pytest.mark.parametrize("toggle", sorted(LEGACY), ids=lambda s: s[4:].lower())
+def test_each_toggle_alone(pkg, meshgen, toggle, monkeypatch):
+    """Each reduced-work path switched off on its own (the others stay on): same DAG, same SSVDAG bytes."""
+    tris = meshgen.make_mesh("city", lots=16)
+    a = pkg.GeomOctree(tris)
+    a.set_batch_budget(24 << 20)
+    a.build(10, 2)
+    want_levels = a.levels_host()
+    a.to_sdag()
+    want = pkg.encoders.encode(a, "ssvdag")
+    monkeypatch.setenv(toggle, LEGACY[toggle])
+    b = pkg.GeomOctree(tris)
+    b.set_batch_budget(24 << 20)
+    b.build(10, 2)
+    _assert_levels_equal(b.levels_host(), want_levels, f"DAG with {toggle}={LEGACY[toggle]}")
+    b.to_sdag()
+    assert pkg.encoders.encode(b, "ssvdag") == want
+
+
+def test_leaf_level_without_first_touches_is_exercised(pkg, meshgen, monkeypatch, capfd):
+    """The batches of a scene whose voxel masks keep trickling in go through all three leaf-level routes (tracked first
+    touches, none needed, direct query for the nodes with a new mask); SVB_VX_STATS reports the query on stderr."""
+    monkeypatch.setenv("SVB_VX_STATS", "1")
+    tris = meshgen.make_mesh("sphere", n_lat=64, n_lon=128)
+    ref = pkg.GeomOctree(tris)
+    ref.build(9, 2)
+    t = pkg.GeomOctree(tris)
+    t.set_batch_budget(8 << 20)
+    st = t.build(9, 2)
+    err = capfd.readouterr().err
+    _assert_levels_equal(t.levels_host(), ref.levels_host(), "batched DAG")
+    if "queried directly" not in err and "voxelizing again" not in err:
+        pytest.skip(f"no batch of this scene met a new voxel mask after a quiet batch ({st['nBatches']} batches)")
