@@ -415,17 +415,21 @@ def test_each_toggle_alone(pkg, meshgen, toggle, monkeypatch):
     assert pkg.encoders.encode(b, "ssvdag") == want
 
 
-def test_leaf_level_without_first_touches_is_exercised(pkg, meshgen, monkeypatch, capfd):
-    """The batches of a scene whose voxel masks keep trickling in go through all three leaf-level routes (tracked first
-    touches, none needed, direct query for the nodes with a new mask); SVB_VX_STATS reports the query on stderr."""
+def test_leaf_level_without_first_touches_is_exercised(pkg, orc, meshgen, monkeypatch, capfd):
+    """A scene whose last batches still bring new voxel masks goes through all three leaf-level routes (tracked first
+    touches, none needed, direct query for the nodes with a new mask); SVB_VX_STATS reports the query on stderr
+    (this scene: 8 batches, 3 leaf nodes queried directly -- tools/gpu_sanitize_quick.sh)."""
     monkeypatch.setenv("SVB_VX_STATS", "1")
-    tris = meshgen.make_mesh("sphere", n_lat=64, n_lon=128)
-    ref = pkg.GeomOctree(tris)
-    ref.build(9, 2)
+    tris = meshgen.make_mesh("city", lots=8)
+    o = orc.OracleOctree(tris)
+    o.build(9, 2)
     t = pkg.GeomOctree(tris)
-    t.set_batch_budget(8 << 20)
+    t.set_batch_budget(6 << 20)
     st = t.build(9, 2)
     err = capfd.readouterr().err
-    _assert_levels_equal(t.levels_host(), ref.levels_host(), "batched DAG")
+    for k in ("nTotalVoxels", "nNodesSVO", "nNodesDAG"):
+        assert st[k] == o.stat(k), k
+    _assert_levels_equal(t.levels_host(), _oracle_levels(o), "batched DAG")
+    assert pkg.encoders.encode(t, "svdag") == o.encode("svdag")
     if "queried directly" not in err and "voxelizing again" not in err:
         pytest.skip(f"no batch of this scene met a new voxel mask after a quiet batch ({st['nBatches']} batches)")
