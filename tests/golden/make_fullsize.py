@@ -2,7 +2,10 @@
 BASELINE.json's headline configuration -- procedural city (lots=256, 11.0 M triangles), 14 levels, step 4 -- and
 record the sizes and SHA-256 of the files it writes plus its result block.  About one hour on 8 cores, ~6 GB RAM.
 
-    python tests/golden/make_fullsize.py [workdir]
+    python tests/golden/make_fullsize.py [fullsize|midsize] [workdir]
+
+`midsize` (city lots=64 at 4096^3, levels 12 step 3) is the same generator at 1/16 of the ground area and finishes in
+minutes: tests/golden/midsize_city4k.json.
 """
 import hashlib
 import importlib.util
@@ -20,15 +23,26 @@ mg = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(mg)
 
 
+CONFIGS = {
+    # name: (lots, levels, step, output file)
+    "fullsize": (256, 14, 4, "fullsize_city16k.json"),    # BASELINE.json's headline configuration (hours of CPU)
+    "midsize": (64, 12, 3, "midsize_city4k.json"),        # same generator, 1/16 of the ground area at the same voxels per lot (minutes)
+}
+
+
 def main():
-    work = sys.argv[1] if len(sys.argv) > 1 else "/tmp/fullref/work"
-    tris = mg.city(256)
-    r = orc.run_reference(work, tris, 14, 4)
-    out = {"workload": "meshgen.city(lots=256), levels 14, step 4", "reference_seconds": r["seconds"],
+    which = sys.argv[1] if len(sys.argv) > 1 and sys.argv[1] in CONFIGS else "fullsize"
+    rest = [a for a in sys.argv[1:] if a not in CONFIGS]
+    lots, levels, step, out_name = CONFIGS[which]
+    work = rest[0] if rest else f"/tmp/fullref/work_{which}"
+    tris = mg.city(lots)
+    r = orc.run_reference(work, tris, levels, step)
+    out = {"workload": f"meshgen.city(lots={lots}), levels {levels}, step {step}", "lots": lots, "levels": levels, "step": step,
+           "triangles": int(len(tris)), "reference_seconds": r["seconds"],
            "files": {k: {"sha256": hashlib.sha256(v).hexdigest(), "bytes": len(v)} for k, v in r["files"].items()}}
     for k in ("Voxels", "SVO Nodes", "DAG Nodes", "SDAG Nodes"):
         out[k] = int(re.search(rf"{k}:\s+.*\((\d+)\)", r["log"]).group(1))
-    (Path(__file__).resolve().parent / "fullsize_city16k.json").write_text(json.dumps(out, indent=1) + "\n")
+    (Path(__file__).resolve().parent / out_name).write_text(json.dumps(out, indent=1) + "\n")
     print(json.dumps(out, indent=1))
 
 

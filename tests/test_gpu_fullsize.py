@@ -111,3 +111,32 @@ def test_files_equal_reference_at_full_size(built):
         got = built["files"][k]
         assert len(got) == want["bytes"], k
         assert hashlib.sha256(got).hexdigest() == want["sha256"], f"{k}: bytes differ from the reference's file"
+
+
+MID = Path(__file__).resolve().parent / "golden" / "midsize_city4k.json"
+
+
+@pytest.mark.skipif(not MID.exists(), reason="tests/golden/midsize_city4k.json not minted")
+def test_files_equal_reference_at_4096(pkg, meshgen):
+    """The same city generator at 64x64 lots / 4096^3 (levels 12, step 3; 0.69 M triangles, every lot spans 64 voxels as
+    in the 16K^3 workload) against the hashes of what the unmodified reference svbuilder wrote
+    (tests/golden/make_fullsize.py midsize); built in several tile batches so that the reduced-work paths take part."""
+    g = json.loads(MID.read_text())
+    tris = meshgen.make_mesh("city", lots=g["lots"])
+    assert len(tris) == g["triangles"]
+    v = tris.reshape(-1, 3)
+    bbox = (v.min(axis=0).astype(np.float64), v.max(axis=0).astype(np.float64))
+    t = pkg.GeomOctree(tris)
+    t.set_batch_budget(1 << 30)
+    st = t.build(g["levels"], g["step"], bbox=bbox)
+    assert (st["nTotalVoxels"], st["nNodesSVO"], st["nNodesDAG"]) == (g["Voxels"], g["SVO Nodes"], g["DAG Nodes"])
+    files = {"svdag": pkg.encoders.encode(t, "svdag"), "esvdag": pkg.encoders.encode(t, "esvdag")}
+    sd = t.to_sdag()
+    assert sd["nNodesSDAG"] == g["SDAG Nodes"]
+    files["ussvdag"] = pkg.encoders.encode(t, "ussvdag")
+    files["ssvdag"] = pkg.encoders.encode(t, "ssvdag")
+    for k, want in g["files"].items():
+        if k not in files:
+            continue
+        assert len(files[k]) == want["bytes"], k
+        assert hashlib.sha256(files[k]).hexdigest() == want["sha256"], f"{k}: bytes differ from the reference's file"

@@ -24,9 +24,10 @@ t = pkg.GeomOctree(tris)
 for _ in range(2):
     t.build(levels, step, bbox=bbox)
 gold = None
-gp = ROOT / "tests" / "golden" / "fullsize_city16k.json"
-if gp.exists() and (levels, step) == (14, 4) and len(tris) > 10_000_000:
-    gold = json.loads(gp.read_text())
+for gp in sorted((ROOT / "tests" / "golden").glob("*size_city*.json")):   # reference hashes (tests/golden/make_fullsize.py)
+    gj = json.loads(gp.read_text())
+    if (gj.get("levels", 14), gj.get("step", 4)) == (levels, step) and gj.get("triangles", 11006740) == len(tris):
+        gold = gj
 first = None
 out = {}
 for spec in sys.argv[1:] or ["default:"]:
@@ -45,7 +46,7 @@ for spec in sys.argv[1:] or ["default:"]:
     ok = "same" if first in (None, (sig, sv, ss)) else "DIFFERENT"
     first = first or (sig, sv, ss)
     if gold:
-        ok += " ref-ok" if (sv == gold["files"]["svdag"]["sha256"] and ss == gold["files"]["ssvdag"]["sha256"] and sig[0] == gold["Voxels"]) else " REF-MISMATCH"
+        ok += " ref-ok" if (sv == gold["files"]["svdag"]["sha256"] and ss == gold["files"]["ssvdag"]["sha256"] and sig == (gold["Voxels"], gold["SVO Nodes"], gold["DAG Nodes"])) else " REF-MISMATCH"
     best = min(ms)
     out[name] = {"ms_total": best[0], "ms_voxelize": best[1], "ms_dedup": best[2], "result": ok}
     print(f"{name:28s} total {best[0]:8.1f}  vox {best[1]:8.1f}  dedup {best[2]:7.1f}   {ok}", flush=True)
