@@ -27,6 +27,7 @@ CONFIGS = {
     # name: (lots, levels, step, output file)
     "fullsize": (256, 14, 4, "fullsize_city16k.json"),    # BASELINE.json's headline configuration (hours of CPU)
     "midsize": (64, 12, 3, "midsize_city4k.json"),        # same generator, 1/16 of the ground area at the same voxels per lot (minutes)
+    "bigsize": (128, 13, 3, "bigsize_city8k.json"),       # 1/4 of the ground area: 2.75 M triangles at 8192^3 (tens of minutes)
 }
 
 

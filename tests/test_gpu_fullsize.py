@@ -113,15 +113,15 @@ def test_files_equal_reference_at_full_size(built):
         assert hashlib.sha256(got).hexdigest() == want["sha256"], f"{k}: bytes differ from the reference's file"
 
 
-MID = Path(__file__).resolve().parent / "golden" / "midsize_city4k.json"
+SIZED = [p for p in sorted((Path(__file__).resolve().parent / "golden").glob("*size_city*.json")) if p.name != GOLD.name]
 
 
-@pytest.mark.skipif(not MID.exists(), reason="tests/golden/midsize_city4k.json not minted")
-def test_files_equal_reference_at_4096(pkg, meshgen):
-    """The same city generator at 64x64 lots / 4096^3 (levels 12, step 3; 0.69 M triangles, every lot spans 64 voxels as
-    in the 16K^3 workload) against the hashes of what the unmodified reference svbuilder wrote
-    (tests/golden/make_fullsize.py midsize); built in several tile batches so that the reduced-work paths take part."""
-    g = json.loads(MID.read_text())
+@pytest.mark.parametrize("gold", SIZED, ids=lambda p: p.stem)
+def test_files_equal_reference_at_4096(pkg, meshgen, gold):
+    """The same city generator at 64x64 lots / 4096^3 (levels 12, step 3; 0.69 M triangles) and 128x128 lots / 8192^3
+    (levels 13, step 3; 2.75 M triangles) -- every lot spans 64 voxels as in the 16K^3 workload -- against the hashes of
+    what the unmodified reference svbuilder wrote (tests/golden/make_fullsize.py midsize | bigsize)."""
+    g = json.loads(gold.read_text())
     tris = meshgen.make_mesh("city", lots=g["lots"])
     assert len(tris) == g["triangles"]
     v = tris.reshape(-1, 3)
