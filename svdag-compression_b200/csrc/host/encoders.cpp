@@ -66,7 +66,7 @@ bool pointer_stream(const OctreeData& o, bool withMirrorHeader, std::vector<uint
 		const LevelSoA& lv = o.levels[l];
 		const bool hasCL = lv.childLevel.size() == lv.n * 8;
 		const uint32_t* wo = wordOf.data() + levelStart[l];
-#pragma omp parallel for schedule(static) num_threads(encode_threads()) if (lv.n > 65536)
+#pragma omp parallel for schedule(static) num_threads(encode_threads()) if (lv.n > 4096)
 		for (int64_t ii = 0; ii < (int64_t)lv.n; ++ii) {
 			const uint64_t i = (uint64_t)ii;
 			uint32_t head = lv.mask[i];
@@ -124,25 +124,35 @@ bool ssvdag(const OctreeData& o, std::vector<uint8_t>& out, std::string* err) {
 	std::vector<uint8_t> leaves;
 	std::vector<uint32_t> addr, nextAddr;   // node index -> address inside its encoded level
 	typedef std::pair<uint32_t, uint32_t> IdxRefs;
-	std::vector<IdxRefs> order;
+	for (int lev = 0; lev <= L - 2; ++lev)
+		if (o.levels[lev].n > (1ull << 30)) { if (err) *err = "level too big for 30-bit pointers"; return false; }
+	// Phase 1: the node order of every level (most-referenced first) only depends on the pointers of the level above,
+	// so the levels are counted and sorted concurrently, one thread per level.  The reference uses the unstable
+	// std::sort, so must we (same libstdc++, same initial sequence, same comparator => same permutation).
+	std::vector<std::vector<IdxRefs>> orders(L - 1);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(encode_threads())
 	for (int lev = L - 2; lev >= 0; --lev) {
 		const LevelSoA& cur = o.levels[lev];
-		if (cur.n > (1ull << 30)) { if (err) *err = "level too big for 30-bit pointers"; return false; }
+		std::vector<IdxRefs>& order = orders[lev];
 		order.resize(cur.n);
 		for (uint32_t i = 0; i < cur.n; ++i) order[i] = IdxRefs(i, 0);
 		if (lev > 0) {
 			const LevelSoA& up = o.levels[lev - 1];
 			for (uint64_t q = 0; q < up.n * 8; ++q) if (up.child[q] != kNull) order[up.child[q]].second++;
-			// most-referenced first; the reference uses the unstable std::sort, so must we (same libstdc++)
 			std::sort(order.begin(), order.end(), [](IdxRefs a, IdxRefs b) { return a.second > b.second; });
 		}
+	}
+	// Phase 2: bottom-up, a level's pointers need the addresses of the level below
+	for (int lev = L - 2; lev >= 0; --lev) {
+		const LevelSoA& cur = o.levels[lev];
+		const std::vector<IdxRefs>& order = orders[lev];
 		nextAddr.assign(cur.n, 0);
 		if (lev == L - 2) {
 			// two deepest levels fused into 4^3 bit bricks, bits re-ordered x-fastest
 			static const LeafTables lut;
 			const LevelSoA& leaf = o.levels[lev + 1];
 			leaves.assign(cur.n * 8, 0);
-#pragma omp parallel for schedule(static) num_threads(encode_threads()) if (order.size() > 65536)
+#pragma omp parallel for schedule(static) num_threads(encode_threads()) if (order.size() > 2048)
 			for (int64_t rr = 0; rr < (int64_t)order.size(); ++rr) {
 				const uint32_t r = (uint32_t)rr;
 				uint32_t i = order[r].first;
@@ -160,7 +170,7 @@ bool ssvdag(const OctreeData& o, std::vector<uint8_t>& out, std::string* err) {
 			// pass 1: encoded size of every node (1 header + 1 or 2 shorts per child), pass 2: fill at the prefix offsets
 			std::vector<uint16_t>& enc = inner[lev];
 			std::vector<uint32_t> sz(order.size());
-#pragma omp parallel for schedule(static) num_threads(encode_threads()) if (order.size() > 65536)
+#pragma omp parallel for schedule(static) num_threads(encode_threads()) if (order.size() > 2048)
 			for (int64_t rr = 0; rr < (int64_t)order.size(); ++rr) {
 				uint32_t i = order[rr].first, n = 1;
 				for (int c = 7; c >= 0; --c) {
@@ -173,7 +183,7 @@ bool ssvdag(const OctreeData& o, std::vector<uint8_t>& out, std::string* err) {
 			uint64_t total = 0;
 			for (size_t r = 0; r < order.size(); ++r) { uint32_t n = sz[r]; sz[r] = (uint32_t)total; total += n; }
 			enc.assign(total, 0);
-#pragma omp parallel for schedule(static) num_threads(encode_threads()) if (order.size() > 65536)
+#pragma omp parallel for schedule(static) num_threads(encode_threads()) if (order.size() > 2048)
 			for (int64_t rr = 0; rr < (int64_t)order.size(); ++rr) {
 				uint32_t i = order[rr].first;
 				nextAddr[i] = sz[rr];
