@@ -71,3 +71,26 @@ def test_svdag_decode_rejects_garbage(pkg):
         pkg.encoders.decode_svdag(b"\x00" * 20)
     with pytest.raises(RuntimeError):
         pkg.encoders.decode_svdag(b"\xff" * 200)
+
+
+def test_threaded_encoder_loops_on_a_larger_dag(pkg, orc, meshgen):
+    """Levels of several thousand nodes (the golden scenes stay below the threshold of the OpenMP loops and of the
+    concurrent per-level sorts of the SSVDAG encoder): the product encoders (default thread count) against the oracle's
+    restatement of the reference encoders, DAG and SDAG state."""
+    tris = meshgen.make_mesh("city", lots=24)
+    o = orc.OracleOctree(tris)
+    o.build(10, 2)
+    lo, hi = o.scene_bbox()
+    bboxF = np.concatenate([lo, hi]).astype(np.float32)
+    rs = orc.lib().orc_root_side(o.h)
+    lv = [o.level(l) for l in range(o.levels)]
+    assert max(len(l["mask"]) for l in lv) > 8192
+    want = {k: o.encode(k) for k in ("svdag", "esvdag")}
+    got = {k: pkg.encoders.encode_levels(lv, bboxF, rs, o.stat("nNodes"), 2, k) for k in ("svdag", "esvdag")}
+    o.to_sdag()
+    lv = [o.level(l) for l in range(o.levels)]
+    for k in ("ussvdag", "ssvdag"):
+        want[k] = o.encode(k)
+        got[k] = pkg.encoders.encode_levels(lv, bboxF, rs, o.stat("nNodes"), 3, k)
+    for k in want:
+        assert got[k] == want[k], k
