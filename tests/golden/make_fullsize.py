@@ -2,7 +2,7 @@
 BASELINE.json's headline configuration -- procedural city (lots=256, 11.0 M triangles), 14 levels, step 4 -- and
 record the sizes and SHA-256 of the files it writes plus its result block.  About one hour on 8 cores, ~6 GB RAM.
 
-    python tests/golden/make_fullsize.py [fullsize|midsize] [workdir]
+    python tests/golden/make_fullsize.py [fullsize|midsize|bigsize|terrain] [workdir]
 
 `midsize` (city lots=64 at 4096^3, levels 12 step 3) is the same generator at 1/16 of the ground area and finishes in
 minutes: tests/golden/midsize_city4k.json.
@@ -24,23 +24,26 @@ spec.loader.exec_module(mg)
 
 
 CONFIGS = {
-    # name: (lots, levels, step, output file)
-    "fullsize": (256, 14, 4, "fullsize_city16k.json"),    # BASELINE.json's headline configuration (hours of CPU)
-    "midsize": (64, 12, 3, "midsize_city4k.json"),        # same generator, 1/16 of the ground area at the same voxels per lot (minutes)
-    "bigsize": (128, 13, 3, "bigsize_city8k.json"),       # 1/4 of the ground area: 2.75 M triangles at 8192^3 (tens of minutes)
+    # name: (mesh generator, kwargs, levels, step, output file)
+    "fullsize": ("city", dict(lots=256), 14, 4, "fullsize_city16k.json"),    # BASELINE.json's headline configuration (hours of CPU)
+    "midsize": ("city", dict(lots=64), 12, 3, "midsize_city4k.json"),        # same generator, 1/16 of the ground area at the same voxels per lot (minutes)
+    "bigsize": ("city", dict(lots=128), 13, 3, "bigsize_city8k.json"),       # 1/4 of the ground area: 2.75 M triangles at 8192^3 (tens of minutes)
+    "terrain": ("terrain", dict(n=1024), 12, 3, "size_terrain4k.json"),      # BASELINE.json configs[1]: 2.09 M general triangles at 4096^3
 }
 
 
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 and sys.argv[1] in CONFIGS else "fullsize"
     rest = [a for a in sys.argv[1:] if a not in CONFIGS]
-    lots, levels, step, out_name = CONFIGS[which]
+    mesh, kw, levels, step, out_name = CONFIGS[which]
     work = rest[0] if rest else f"/tmp/fullref/work_{which}"
-    tris = mg.city(lots)
+    tris = mg.make_mesh(mesh, **kw)
     r = orc.run_reference(work, tris, levels, step)
-    out = {"workload": f"meshgen.city(lots={lots}), levels {levels}, step {step}", "lots": lots, "levels": levels, "step": step,
+    out = {"workload": f"meshgen.make_mesh({mesh!r}, **{kw}), levels {levels}, step {step}", "mesh": mesh, "kw": kw, "levels": levels, "step": step,
            "triangles": int(len(tris)), "reference_seconds": r["seconds"],
            "files": {k: {"sha256": hashlib.sha256(v).hexdigest(), "bytes": len(v)} for k, v in r["files"].items()}}
+    if mesh == "city":
+        out["lots"] = kw["lots"]
     for k in ("Voxels", "SVO Nodes", "DAG Nodes", "SDAG Nodes"):
         out[k] = int(re.search(rf"{k}:\s+.*\((\d+)\)", r["log"]).group(1))
     (Path(__file__).resolve().parent / out_name).write_text(json.dumps(out, indent=1) + "\n")

@@ -16,15 +16,20 @@ import __graft_entry__ as g
 
 REPS = int(os.environ.get("AB_REPS", "2"))
 pkg = g._pkg()
-tris = pkg.meshgen.city(int(os.environ.get("AB_LOTS", "256")))
-levels, step = int(os.environ.get("AB_LEVELS", "14")), int(os.environ.get("AB_STEP", "4"))
+if os.environ.get("AB_GOLD"):   # a tests/golden/*size*.json file: its mesh, levels, step (and its hashes below)
+    _g = json.loads((ROOT / "tests" / "golden" / os.environ["AB_GOLD"]).read_text())
+    tris = pkg.meshgen.make_mesh(_g.get("mesh", "city"), **_g.get("kw", {"lots": _g.get("lots", 256)}))
+    levels, step = _g["levels"], _g["step"]
+else:
+    tris = pkg.meshgen.city(int(os.environ.get("AB_LOTS", "256")))
+    levels, step = int(os.environ.get("AB_LEVELS", "14")), int(os.environ.get("AB_STEP", "4"))
 v = tris.reshape(-1, 3)
 bbox = (v.min(axis=0).astype(np.float64), v.max(axis=0).astype(np.float64))
 t = pkg.GeomOctree(tris)
-for _ in range(2):
+for _ in range(int(os.environ.get("AB_WARMUP", "2"))):
     t.build(levels, step, bbox=bbox)
 gold = None
-for gp in sorted((ROOT / "tests" / "golden").glob("*size_city*.json")):   # reference hashes (tests/golden/make_fullsize.py)
+for gp in sorted((ROOT / "tests" / "golden").glob("*size_*.json")):   # reference hashes (tests/golden/make_fullsize.py)
     gj = json.loads(gp.read_text())
     if (gj.get("levels", 14), gj.get("step", 4)) == (levels, step) and gj.get("triangles", 11006740) == len(tris):
         gold = gj
