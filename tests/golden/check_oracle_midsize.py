@@ -23,7 +23,7 @@ spec.loader.exec_module(mg)
 
 def main():
     gold = json.loads((Path(__file__).resolve().parent / (sys.argv[1] if len(sys.argv) > 1 else "midsize_city4k.json")).read_text())
-    tris = mg.city(gold["lots"])
+    tris = mg.make_mesh(gold.get("mesh", "city"), **gold.get("kw", {"lots": gold.get("lots", 64)}))
     t0 = time.time()
     o = orc.OracleOctree(tris)
     o.build(gold["levels"], gold["step"])

@@ -1,7 +1,8 @@
-"""BASELINE.json configs[1] at full size -- procedural heightfield terrain, 2.09 M general (non-flat) triangles at 4096^3,
-levels 12 step 3 -- against the SHA-256 of the files the UNMODIFIED reference svbuilder wrote for the same input
-(tests/golden/size_terrain4k.json, minted by tests/golden/make_fullsize.py terrain).  Kept in a file that sorts last: it
-is the one reference comparison of the general-triangle classify path at a size no CPU oracle run accompanies."""
+"""BASELINE.json configs[1] and configs[0] at full size -- the procedural heightfield terrain, 2.09 M general (non-flat)
+triangles at 4096^3, levels 12 step 3, and the sphere + Menger sponge at 1024^3, levels 10 step 1 -- against the SHA-256
+of the files the UNMODIFIED reference svbuilder wrote for the same inputs (tests/golden/size_*.json, minted by
+tests/golden/make_fullsize.py terrain | spongeball; the CPU restatement reproduces both as well,
+tests/golden/check_oracle_midsize.py)."""
 import hashlib
 import json
 from pathlib import Path
@@ -10,12 +11,12 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
-GOLD = Path(__file__).resolve().parent / "golden" / "size_terrain4k.json"
+GOLDS = sorted((Path(__file__).resolve().parent / "golden").glob("size_*.json"))   # size_terrain4k.json, size_spongeball1k.json
 
 
-@pytest.mark.skipif(not GOLD.exists(), reason="tests/golden/size_terrain4k.json not minted")
-def test_terrain_4096_files_equal_reference(pkg, meshgen):
-    g = json.loads(GOLD.read_text())
+@pytest.mark.parametrize("gold", GOLDS, ids=lambda p: p.stem)
+def test_baseline_configs_files_equal_reference(pkg, meshgen, gold):
+    g = json.loads(gold.read_text())
     tris = meshgen.make_mesh(g["mesh"], **g["kw"])
     assert len(tris) == g["triangles"]
     v = tris.reshape(-1, 3)
