@@ -1,9 +1,10 @@
 """One-off pin of the CPU restatement (oracle/svdag_oracle.cpp) at a size far above the golden scenes: builds the city of
 tests/golden/midsize_city4k.json (64x64 lots, 4096^3, levels 12 step 3; 1.42 G voxels) with the sequential oracle --
 about 12 minutes on one core -- and compares counts and the SHA-256 of all four encoded files with what the UNMODIFIED
-reference svbuilder wrote (make_fullsize.py midsize).  Last run (round 1, session 3): all equal, 711 s.
+reference svbuilder wrote (make_fullsize.py midsize).  Last runs (round 1, session 3): midsize_city4k.json all equal, 711 s; size_terrain4k.json (BASELINE configs[1] at full
+size) all equal, 526 s; size_spongeball1k.json (configs[0]) all equal, 6.6 s.
 
-    python tests/golden/check_oracle_midsize.py [midsize_city4k.json]
+    python tests/golden/check_oracle_midsize.py [midsize_city4k.json | size_terrain4k.json | size_spongeball1k.json]
 """
 import hashlib
 import importlib.util
