@@ -40,3 +40,29 @@ def test_tri_box_touching_is_overlap(orc):
     # degenerate (zero-normal) triangle passes the plane test
     deg = np.array([0.3, 0.3, 0.3, 0.3, 0.3, 0.3, 0.3, 0.3, 0.3], np.float32)
     assert orc.test_tri_box((0.25, 0.25, 0.25), 0.25, deg)
+
+
+def test_oracle_reproduces_baseline_config0_at_full_size(orc):
+    """BASELINE.json configs[0] -- sphere + Menger sponge at 1024^3, levels 10 step 1 -- at full size: the restatement
+    against the SHA-256 of the four files the unmodified reference wrote (tests/golden/size_spongeball1k.json).  The
+    larger pins (configs[1] at 4096^3, the city at 4096^3) take minutes: tests/golden/check_oracle_midsize.py."""
+    import hashlib
+    import importlib.util
+    import json
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    g = json.loads((root / "tests" / "golden" / "size_spongeball1k.json").read_text())
+    spec = importlib.util.spec_from_file_location("_mg_cfg0", root / "svdag-compression_b200" / "meshgen.py")
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    tris = mg.make_mesh(g["mesh"], **g["kw"])
+    assert len(tris) == g["triangles"]
+    o = orc.OracleOctree(tris)
+    o.build(g["levels"], g["step"])
+    assert (o.stat("nTotalVoxels"), o.stat("nNodesSVO"), o.stat("nNodesDAG")) == (g["Voxels"], g["SVO Nodes"], g["DAG Nodes"])
+    got = {k: o.encode(k) for k in ("svdag", "esvdag")}
+    o.to_sdag()
+    assert o.stat("nNodesSDAG") == g["SDAG Nodes"]
+    got.update({k: o.encode(k) for k in ("ussvdag", "ssvdag")})
+    for k, data in got.items():
+        assert hashlib.sha256(data).hexdigest() == g["files"][k]["sha256"], k
