@@ -33,3 +33,25 @@ def test_baseline_configs_files_equal_reference(pkg, meshgen, gold):
         if k in files:
             assert len(files[k]) == want["bytes"], k
             assert hashlib.sha256(files[k]).hexdigest() == want["sha256"], f"{k}: bytes differ from the reference's file"
+
+
+MID = Path(__file__).resolve().parent / "golden" / "midsize_city4k.json"
+
+
+@pytest.mark.skipif(not MID.exists() or "cross" not in json.loads(MID.read_text()), reason="no CSVDAG reference hashes")
+def test_cross_level_merge_equals_reference_at_4096(pkg, meshgen):
+    """BASELINE.json configs[3] (city -> CSVDAG, `svbuilder ... -c`) at 64x64 lots / 4096^3: the -multi.svdag file and the
+    number of nodes the cross-level merge eliminates against the unmodified reference (96 s on 8 cores; the CPU
+    restatement reproduces the same file, 885 s)."""
+    g = json.loads(MID.read_text())
+    tris = meshgen.make_mesh("city", lots=g["lots"])
+    v = tris.reshape(-1, 3)
+    bbox = (v.min(axis=0).astype(np.float64), v.max(axis=0).astype(np.float64))
+    t = pkg.GeomOctree(tris)
+    t.build(g["levels"], g["step"], bbox=bbox)
+    assert hashlib.sha256(pkg.encoders.encode(t, "svdag")).hexdigest() == g["files"]["svdag"]["sha256"]
+    st = t.cross_merge()
+    assert st["nCrossLevelMerged"] == g["cross"]["nodes_eliminated"]
+    multi = pkg.encoders.encode(t, "svdag")
+    assert len(multi) == g["cross"]["multi.svdag"]["bytes"]
+    assert hashlib.sha256(multi).hexdigest() == g["cross"]["multi.svdag"]["sha256"], "-multi.svdag differs from the reference's file"
