@@ -63,6 +63,13 @@ svb_ctx*    svb_create(int device);
 void        svb_destroy(svb_ctx* ctx);
 const char* svb_last_error(const svb_ctx* ctx);   /* never NULL */
 const char* svb_version(void);
+/* The CUDA stream (cudaStream_t) every call on this context enqueues its work on.  The svb_shard_export_* /
+ * svb_shard_import_* calls are STREAM-ORDERED (they return without waiting for the device): a caller orders its
+ * collective after an export and before the matching import either by issuing it on this stream (NCCL:
+ * ncclAllGather(..., (cudaStream_t)svb_stream(ctx)); torch: torch.cuda.ExternalStream) or with events.  All other calls
+ * return with their results complete. */
+void* svb_stream(const svb_ctx* ctx);
+int   svb_synchronize(svb_ctx* ctx);
 
 /* Scene::getTrianglePtr()/getNRawTriangles() (src/symvox/scene.hpp:90-91): the flat float32
  * triangle soup, 9 floats per triangle, in file order.  The host variant copies H2D (the
@@ -86,10 +93,13 @@ int svb_build(svb_ctx* ctx, uint32_t levels, uint32_t step,
  *                                       sub-octrees, reduced into rank-local tables;
  *   svb_shard_info                      levels to merge [first,last] (= step+1 .. levels-1), tile count, and
  *                                       this rank's counters {leafVoxels, nodesSVO, lastLevSVO, pairs, exact};
- *   for level = last .. first:          svb_shard_level_count -> n records of recBytes each;
+ *   for level = last .. first:          svb_shard_level_count -> n records of recBytes each (known for ALL levels as
+ *                                       soon as svb_shard_build returns: one count exchange serves the whole merge);
  *                                       svb_shard_export_level writes them to a DEVICE buffer; the caller
  *                                       all-gathers (NCCL) into world rows of strideBytes;
  *                                       svb_shard_import_level rebuilds the identical global table everywhere;
+ *                                       (export / import are stream-ordered on svb_stream(ctx), no host sync: errors
+ *                                       of an import -- SVB_ECOLLISION etc. -- surface in svb_shard_finish)
  *   svb_shard_export_roots / all-gather / svb_shard_import_roots   (nTiles x u32 per rank);
  *   svb_shard_finish(totals)            totals = the counters summed over ranks; reduces the base octree,
  *                                       ranks all levels, leaves every rank in state DAG with the same octree

@@ -267,12 +267,14 @@ class Builder:
 
     def shard_level_count(self, g):
         import pickle
-        self._blob = pickle.dumps(self.tables[g])
-        return len(self._blob), 1
+        if not hasattr(self, "_blobs"):
+            self._blobs = {}
+        self._blobs[g] = pickle.dumps(self.tables[g])   # structural keys: final as soon as the local phase ends
+        return len(self._blobs[g]), 1
 
     def shard_export_level(self, g, ptr):
         import ctypes
-        ctypes.memmove(ptr, self._blob, len(self._blob))
+        ctypes.memmove(ptr, self._blobs[g], len(self._blobs[g]))
 
     def shard_import_level(self, g, ptr, counts, stride):
         import ctypes

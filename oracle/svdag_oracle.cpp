@@ -12,7 +12,7 @@
 //  un-vendored SpaceLand library follows oracle/sl_shim (dot left-to-right, textbook
 //  cross, center=(lo+hi)*0.5, half=(hi-lo)*0.5) -- parity w.r.t. the real SL is UNPINNED.
 //  Pinned against: oracle/_ref/svbuilder_ref (the unmodified reference compiled against
-//  the shim) through tests/golden/* and tests/test_oracle_vs_ref.py.
+//  the shim) through tests/golden/* (tests/test_oracle_golden.py, tests/golden/check_oracle_midsize.py).
 //
 //  Built with -ffp-contract=off: the reference is compiled for baseline x86-64, i.e.
 //  without FMA contraction (CMakeLists.txt has no -march).

@@ -61,6 +61,9 @@ def lib() -> C.CDLL:
         L.svb_last_error.restype = C.c_char_p
         L.svb_last_error.argtypes = [vp]
         L.svb_version.restype = C.c_char_p
+        L.svb_stream.restype = vp
+        L.svb_stream.argtypes = [vp]
+        L.svb_synchronize.argtypes = [vp]
         L.svb_set_triangles.argtypes = [vp, vp, u64]
         L.svb_set_triangles_device.argtypes = [vp, vp, u64]
         L.svb_build.argtypes = [vp, u32, u32, vp, vp, C.POINTER(Stats)]
@@ -146,6 +149,13 @@ class GeomOctree:
         st = Stats()
         self._check(self._L.svb_build(self._h, levels, step, lo.ctypes.data, hi.ctypes.data, C.byref(st)))
         return st.as_dict()
+
+    def stream_ptr(self) -> int:
+        """cudaStream_t of this context (the shard_export_* / shard_import_* calls are stream-ordered on it)."""
+        return int(self._L.svb_stream(self._h) or 0)
+
+    def synchronize(self):
+        self._check(self._L.svb_synchronize(self._h))
 
     # ---- multi-GPU protocol (include/svb.h); driven by sharded.build_sharded()
     def shard_build(self, levels, step, bbox, rank, world):

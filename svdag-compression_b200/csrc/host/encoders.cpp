@@ -26,6 +26,44 @@ int encode_threads() {
 	return n;
 }
 
+// ---- the SSVDAG node order: std::sort by reference count, descending (encoded_ssvdag.cpp:261-276) ------------------------
+// The reference's std::sort is UNSTABLE, and the file depends on how it happens to leave the ties.  libstdc++'s std::sort is
+//     __introsort_loop(first, last, 2*lg(n));  __final_insertion_sort(first, last);
+// and the loop is  { cut = __unguarded_partition_pivot(first, last); recurse on [cut, last); last = cut; }  -- after a
+// partition the two sides never interact again.  So the same library routines can run the right-hand sides as tasks on
+// other threads and produce, comparison for comparison and swap for swap, the permutation the sequential call yields.
+// What is called below are libstdc++'s own __unguarded_partition_pivot / __introsort_loop / __partial_sort /
+// __final_insertion_sort (the reference binary is built against the same headers); only the recursion is ours.
+typedef std::pair<uint32_t, uint32_t> IdxRefs;   // (node index, references from the level above)
+struct MoreRefs { bool operator()(const IdxRefs& a, const IdxRefs& b) const { return a.second > b.second; } };
+
+long sort_par_min() {
+	static const long v = [] { const char* e = getenv("SVB_SORT_PAR_MIN"); long x = e ? atol(e) : 0; return x > 32 ? x : 16384L; }();
+	return v;
+}
+
+template <class It, class Comp>
+void introsort_tasks(It first, It last, long depth, Comp comp, long parMin) {
+	while (last - first > 16) {                                   // _S_threshold
+		if (last - first <= parMin) { std::__introsort_loop(first, last, depth, comp); return; }
+		if (depth == 0) { std::__partial_sort(first, last, last, comp); return; }
+		--depth;
+		It cut = std::__unguarded_partition_pivot(first, last, comp);
+#pragma omp task default(none) firstprivate(cut, last, depth, comp, parMin)
+		introsort_tasks(cut, last, depth, comp, parMin);
+		last = cut;
+	}
+}
+
+// == std::sort(v.begin(), v.end(), MoreRefs()); call from inside an OpenMP parallel region to have the tasks shared out
+void sort_by_refs(std::vector<IdxRefs>& v) {
+	if (v.size() < 2) return;
+	auto comp = __gnu_cxx::__ops::__iter_comp_iter(MoreRefs());
+#pragma omp taskgroup
+	introsort_tasks(v.begin(), v.end(), (long)std::__lg((long)v.size()) * 2, comp, sort_par_min());
+	std::__final_insertion_sort(v.begin(), v.end(), comp);
+}
+
 struct ByteSink {
 	std::vector<uint8_t>& v;
 	template <class T> void pod(const T& x) { const uint8_t* p = reinterpret_cast<const uint8_t*>(&x); v.insert(v.end(), p, p + sizeof(T)); }
@@ -123,7 +161,6 @@ bool ssvdag(const OctreeData& o, std::vector<uint8_t>& out, std::string* err) {
 	std::vector<std::vector<uint16_t>> inner(L - 2);
 	std::vector<uint8_t> leaves;
 	std::vector<uint32_t> addr, nextAddr;   // node index -> address inside its encoded level
-	typedef std::pair<uint32_t, uint32_t> IdxRefs;
 	for (int lev = 0; lev <= L - 2; ++lev)
 		if (o.levels[lev].n > (1ull << 30)) { if (err) *err = "level too big for 30-bit pointers"; return false; }
 	// Phase 1: the node order of every level (most-referenced first) only depends on the pointers of the level above,
@@ -139,7 +176,7 @@ bool ssvdag(const OctreeData& o, std::vector<uint8_t>& out, std::string* err) {
 		if (lev > 0) {
 			const LevelSoA& up = o.levels[lev - 1];
 			for (uint64_t q = 0; q < up.n * 8; ++q) if (up.child[q] != kNull) order[up.child[q]].second++;
-			std::sort(order.begin(), order.end(), [](IdxRefs a, IdxRefs b) { return a.second > b.second; });
+			sort_by_refs(order);
 		}
 	}
 	// Phase 2: bottom-up, a level's pointers need the addresses of the level below
@@ -225,6 +262,20 @@ bool ssvdag(const OctreeData& o, std::vector<uint8_t>& out, std::string* err) {
 
 }  // namespace
 
+// The SSVDAG node order of every level from its reference counts (the device encoder computes the counts, svb_encode.cu):
+// refs = counts of levels 0 .. L-2 concatenated, start[l] = first entry of level l; order (same layout) receives the node
+// indices, most referenced first, ties exactly as the reference's std::sort leaves them.
+void ssvdag_order_from_refs(const uint32_t* refs, const uint32_t* start, int nLevels, uint32_t* order) {
+#pragma omp parallel for schedule(dynamic, 1) num_threads(encode_threads())
+	for (int lev = nLevels - 1; lev >= 0; --lev) {
+		const uint32_t n = start[lev + 1] - start[lev];
+		std::vector<IdxRefs> v(n);
+		for (uint32_t i = 0; i < n; ++i) v[i] = IdxRefs(i, refs[start[lev] + i]);
+		if (lev > 0) sort_by_refs(v);
+		for (uint32_t i = 0; i < n; ++i) order[start[lev] + i] = v[i].first;
+	}
+}
+
 // EncodedSVDAG::load + decode (encoded_svdag.cpp:43-74, :200-270): one u32 stream, levels stored one after the other;
 // a level ends where the smallest child pointer of its nodes points.  Nodes keep file order; child pointers (absolute
 // word offsets in the file) become indices into the next level.  Cross-level (-multi) files are not decodable, as in
@@ -247,6 +298,7 @@ bool decode_svdag(const uint8_t* file, uint64_t size, OctreeData& o, std::string
 	o.state = 2;                                      // S_DAG
 	o.levels.assign(levels, LevelSoA());
 	std::vector<uint32_t> indexOfWord(count, 0);      // word offset of a node -> its index inside its level
+	std::vector<uint8_t> levelOfWord(count, 0xFF);    // level of the node whose header sits at that word (0xFF: not a header)
 	std::vector<uint32_t> levStart(levels, 0xFFFFFFFFu);
 	levStart[0] = 0;
 	uint32_t lev = 0;
@@ -255,6 +307,7 @@ bool decode_svdag(const uint8_t* file, uint64_t size, OctreeData& o, std::string
 		LevelSoA& L = o.levels[lev];
 		const uint8_t m = (uint8_t)data[i];
 		indexOfWord[i] = (uint32_t)L.n;
+		levelOfWord[i] = (uint8_t)lev;
 		L.mask.push_back(m);
 		L.child.insert(L.child.end(), 8, kNull);
 		if (lev + 1 < levels) {
@@ -275,6 +328,8 @@ bool decode_svdag(const uint8_t* file, uint64_t size, OctreeData& o, std::string
 		for (uint32_t& c : o.levels[l].child)
 			if (c != kNull) {
 				if (c >= count) { if (err) *err = "SVDAG pointer out of range"; return false; }
+				// a pointer must land on the header word of a node of the next level (a -multi file, or a corrupt one, does not)
+				if (levelOfWord[c] != l + 1) { if (err) *err = "SVDAG pointer does not address a node of the next level (cross-level or corrupt file)"; return false; }
 				c = indexOfWord[c];
 			}
 	for (auto& L : o.levels) { L.mirror.assign(L.n * 3, 0); L.inv.assign(L.n, 0); }

@@ -31,6 +31,10 @@ struct OctreeData {
 // kind 2: .ssvdag / .esvdag (EncodedSSVDAG, encoded_ssvdag.cpp:84-117,194-466) needs DAG or SDAG
 bool encode_file(const OctreeData& o, int kind, std::vector<uint8_t>& out, std::string* err = nullptr);
 
+// EncodedSSVDAG::encode's node order (encoded_ssvdag.cpp:247-276) from per-level reference counts: refs / order hold levels
+// 0 .. nLevels-1 concatenated, level l at [start[l], start[l+1]).  order[start[l] + r] = index of the node at rank r.
+void ssvdag_order_from_refs(const uint32_t* refs, const uint32_t* start, int nLevels, uint32_t* order);
+
 // EncodedSVDAG::load + decode (encoded_svdag.cpp:43-74, :200-270): a .svdag image back into DAG levels (state DAG).
 bool decode_svdag(const uint8_t* file, uint64_t size, OctreeData& o, std::string* err = nullptr);
 

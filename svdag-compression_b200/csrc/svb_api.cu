@@ -200,6 +200,7 @@ struct svb_build_state {
 	DevBuf<uint32_t> tileRootRef;        // per tile: uid of its (reduced) root at level s1; UNSET if not built here
 	std::vector<DevBuf<uint32_t>> l2g;   // multi-GPU merge: local uid -> global uid per level
 	std::vector<bool> merged;
+	DevBuf<uint32_t> mergeStatus;        // multi-GPU merge: 8 x u32 per level, written by merge_import, read back once by build_finish
 	bool finished = false;
 	uint64_t launches0 = 0;
 	cudaEvent_t evStart = nullptr;
@@ -304,7 +305,13 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 		CtxProfHook hook(c);
 		bool direct = true;
 		for (uint32_t i = 0; i < nt && direct; ++i) direct = centre_chain_exact(hg[i], Lt);
-		voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, rootTri.p, dTileStart.p, P, budget, nodeCap, lv, pairs, B.dExact.p, direct, B.allFlat, leafT, c->profiling ? &hook : nullptr);
+		try {
+			voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, rootTri.p, dTileStart.p, P, budget, nodeCap, lv, pairs, B.dExact.p, direct, B.allFlat, leafT, c->profiling ? &hook : nullptr);
+		} catch (const BatchTooBig&) {   // the range is cut and voxelized again: the aborted attempt's exact-test count must not stay in the counter
+			SVB_CUDA(cudaMemcpyAsync(B.dExact.p, exactBefore.p, 8, cudaMemcpyDeviceToDevice, s));
+			SVB_CUDA(cudaStreamSynchronize(s));
+			throw;
+		}
 		ps.done(pairs, 36.0 * (double)c->T + 9.0 * (double)lv[Lt - 1].n);
 		B.msVox += tm.stop();
 	}
@@ -430,6 +437,7 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 	B.obits.assign(L, 1);
 	B.l2g.resize(L);
 	B.merged.assign(L, false);
+	if (world > 1) { B.mergeStatus.reset(c->pool, 8ull * L); B.mergeStatus.zero(); }
 	for (uint32_t g = 1; g < L; ++g) table_init(s, c->pool, B.tables[g], kind_of(g, L));
 	B.dVoxels.reset(c->pool, 1); B.dVoxels.zero();
 	B.dExact.reset(c->pool, 1); B.dExact.zero();
@@ -534,6 +542,10 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 	// every rank: all ranks hold all triangles and the same tile grid)
 	B.tbLocal = bits_for(std::max<uint32_t>(1, max_candidates_per_tile(s, c->pool, c->d_tris, c->T, B.grid, B.dGrid.p, nTiles)) - 1);
 	set_order_key_width(B, Lt, B.tbLocal);
+	// Order-key widths of the sub-octree levels are a function of the scene alone, never of what this rank happened to
+	// reduce: a rank with an empty share (world > nTiles, an empty octant under SVB_SHARD=octant) must rank the merged
+	// tables on the same bits as everyone else.
+	for (uint32_t g = s1; g < L; ++g) B.obits[g] = std::max(B.obits[g], B.tileBits + B.tbLocal + 3 * (int)(g - s1));
 	B.tileRootRef.reset(c->pool, nTiles ? nTiles : 1);
 	B.tileRootRef.fill_ff();
 	// ---- this rank's share: sub-octrees dealt round-robin in the reference's order (SVB_SHARD=octant: by
@@ -566,6 +578,13 @@ void build_finish(svb_ctx* c, const uint64_t* totals) {
 	BuildState& B = *c->build;
 	cudaStream_t s = c->stream;
 	const uint32_t L = B.L, s1 = B.s1;
+	if (B.world > 1) {   // the per-level imports ran stream-ordered; their unique counts and error flags are read back here, once
+		std::vector<uint32_t> hs = download(s, B.mergeStatus.p, 8ull * L);
+		for (uint32_t g = std::max(s1, 1u); g < L; ++g) {
+			if (!B.merged[g]) throw Error(SVB_EINVAL, "svb_shard_finish: level " + std::to_string(g) + " has not been merged");
+			merge_resolve(B.tables[g], &hs[8ull * g]);
+		}
+	}
 	uint64_t leafVox = download(s, B.dVoxels.p, 1)[0];
 	uint64_t nodesSVO = B.nNodesSVO, lastLev = B.nLastLevSVO, pairs = B.pairs, exact = download(s, B.dExact.p, 1)[0];
 	if (totals) { leafVox = totals[0]; nodesSVO = totals[1]; lastLev = totals[2]; pairs = totals[3]; exact = totals[4]; }
@@ -732,6 +751,10 @@ void svb_destroy(svb_ctx* c) {
 }
 
 const char* svb_last_error(const svb_ctx* c) { return c ? c->err.c_str() : "null context (no CUDA device?)"; }
+void* svb_stream(const svb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int svb_synchronize(svb_ctx* c) {
+	return guarded(c, [&] { SVB_CUDA(cudaStreamSynchronize(c->stream)); });
+}
 
 int svb_set_triangles(svb_ctx* c, const float* xyz9_host, uint64_t ntris) {
 	return guarded(c, [&] {
@@ -810,8 +833,7 @@ int svb_shard_export_level(svb_ctx* c, uint32_t level, void* d_out) {
 			if (!B.merged[level + 1]) throw Error(SVB_EINVAL, "levels must be merged bottom-up");
 			l2gChild = B.l2g[level + 1].p;
 		}
-		merge_export(c->stream, c->pool, T, l2gChild, d_out);
-		SVB_CUDA(cudaStreamSynchronize(c->stream));
+		merge_export(c->stream, c->pool, T, l2gChild, d_out);   // stream-ordered on svb_stream(ctx)
 	});
 }
 
@@ -819,7 +841,8 @@ int svb_shard_import_level(svb_ctx* c, uint32_t level, const void* d_all, const 
 	return guarded(c, [&] {
 		if (!c->build || level < c->build->s1 || level >= c->build->L || !counts) throw Error(SVB_EINVAL, "bad level");
 		svb_build_state& B = *c->build;
-		merge_import(c->stream, c->pool, B.tables[level], d_all, counts, B.world, strideBytes, B.rank, B.l2g[level]);
+		if (B.world < 2) throw Error(SVB_EINVAL, "not a sharded build");
+		merge_import(c->stream, c->pool, B.tables[level], d_all, counts, B.world, strideBytes, B.rank, B.l2g[level], B.mergeStatus.p + 8ull * level);
 		B.merged[level] = true;
 		if (level == B.s1) {   // sub-octree roots now have global uids
 			if (B.tables[level].kind != KIND_LEAF && !B.tiles.empty()) {
@@ -827,7 +850,6 @@ int svb_shard_import_level(svb_ctx* c, uint32_t level, const void* d_all, const 
 				SVB_KERNEL_CHECK();
 			}
 		}
-		SVB_CUDA(cudaStreamSynchronize(c->stream));
 	});
 }
 
@@ -837,7 +859,6 @@ int svb_shard_export_roots(svb_ctx* c, void* d_out) {
 		svb_build_state& B = *c->build;
 		if (!B.merged[B.s1]) throw Error(SVB_EINVAL, "merge the sub-octree root level first");
 		SVB_CUDA(cudaMemcpyAsync(d_out, B.tileRootRef.p, (B.tiles.size() ? B.tiles.size() : 1) * 4ull, cudaMemcpyDeviceToDevice, c->stream));
-		SVB_CUDA(cudaStreamSynchronize(c->stream));
 	});
 }
 
@@ -850,7 +871,6 @@ int svb_shard_import_roots(svb_ctx* c, const void* d_all) {
 			k_min_u32_rows<<<blocks_for(n, 256), 256, 0, c->stream>>>(n, B.world, (const uint32_t*)d_all, B.tileRootRef.p);
 			SVB_KERNEL_CHECK();
 		}
-		SVB_CUDA(cudaStreamSynchronize(c->stream));
 	});
 }
 
@@ -1016,7 +1036,24 @@ int64_t svb_encode_levels(uint32_t levels, const uint64_t* counts, const uint8_t
 int svb_upload_levels(svb_ctx* c, uint32_t levels, const uint64_t* counts, const uint8_t* mask, const uint32_t* child8,
                       const float bboxF[6], double rootSide, uint64_t nVoxels) {
 	return guarded(c, [&] {
-		if (!counts || !mask || !child8 || levels < 2) throw Error(SVB_EINVAL, "bad arguments");
+		if (!counts || !mask || !child8 || levels < 2 || levels > 32) throw Error(SVB_EINVAL, "bad arguments");
+		// every later stage (toSDAG, cross merge, encoders) indexes the next level with these values unchecked
+		{
+			uint64_t off = 0;
+			for (uint32_t l = 0; l < levels; ++l) {
+				if (counts[l] >= 0xFFFFFFF0ull) throw Error(SVB_ERANGE, "level too large");
+				const uint64_t nNext = l + 1 < levels ? counts[l + 1] : 0;
+				for (uint64_t i = off; i < off + counts[l]; ++i)
+					for (int k = 0; k < 8; ++k) {
+						const uint32_t ch = child8[i * 8 + k];
+						const bool bit = (mask[i] >> k) & 1;
+						if (l + 1 == levels) continue;                      // voxel masks: child slots are not read
+						if (bit != (ch != NULLNODE) || (bit && ch >= nNext))
+							throw Error(SVB_EINVAL, "svb_upload_levels: child pointer / mask mismatch or child index out of range at level " + std::to_string(l));
+					}
+				off += counts[l];
+			}
+		}
 		c->lastImage.clear(); c->lastImageKind = -1;
 		cudaStream_t s = c->stream;
 		c->out.clear();
@@ -1074,15 +1111,20 @@ int svb_decode_svdag(const uint8_t* file, uint64_t size, uint32_t* levels, uint6
 int svb_load_svdag(svb_ctx* c, const uint8_t* file, uint64_t size, svb_stats* out) {
 	if (!c || !file) return SVB_EINVAL;
 	svbhost::OctreeData o;
-	std::string err;
-	if (!svbhost::decode_svdag(file, size, o, &err)) { c->err = err; return SVB_EINVAL; }
 	std::vector<uint64_t> counts;
 	std::vector<uint8_t> mask;
 	std::vector<uint32_t> child;
-	for (auto& L : o.levels) {
-		counts.push_back(L.n);
-		mask.insert(mask.end(), L.mask.begin(), L.mask.end());
-		child.insert(child.end(), L.child.begin(), L.child.end());
+	try {   // nothing may escape across the C boundary (a hostile header can ask for absurd allocations)
+		std::string err;
+		if (!svbhost::decode_svdag(file, size, o, &err)) { c->err = err; return SVB_EINVAL; }
+		for (auto& L : o.levels) {
+			counts.push_back(L.n);
+			mask.insert(mask.end(), L.mask.begin(), L.mask.end());
+			child.insert(child.end(), L.child.begin(), L.child.end());
+		}
+	} catch (const std::exception& e) {
+		c->err = std::string("svb_load_svdag: ") + e.what();
+		return SVB_EINVAL;
 	}
 	int rc = svb_upload_levels(c, (uint32_t)o.levels.size(), counts.data(), mask.data(), child.data(), o.bboxF, o.rootSide, 0);
 	if (rc == SVB_OK) {

@@ -651,6 +651,11 @@ uint64_t next_pow2(uint64_t x) {
 bool later_batch(LevelTable& T, const DedupArgs& a) {
 	const char* e = getenv("SVB_DEDUP_LAZY");   // 0: always update every entry / read every field (A/B, verification)
 	const bool later = T.seenAny && a.seqLo > T.maxSeq && !(e && e[0] == '0');
+	// An existing entry's improved order key only reaches the slot array (atomicMin), not the dense copy finalize_levels /
+	// k_rebuild / merge_export read: correct as long as batches reach a table in ascending sub-octree order (then an existing
+	// entry can never improve).  run_tiles_split guarantees that; anything else must fail loudly, not rank silently wrong.
+	if (T.kind != KIND_LEAF && T.seenAny && T.count > 0 && a.seqLo <= T.maxSeq)
+		throw Error(SVB_EINVAL, "dedup: tile batches must reach a level table in ascending sub-octree order");
 	T.maxSeq = T.seenAny ? std::max(T.maxSeq, a.seqHi) : a.seqHi;
 	T.seenAny = true;
 	return later;
@@ -1051,8 +1056,23 @@ void merge_export(cudaStream_t s, Pool& pool, LevelTable& T, const uint32_t* l2g
 	SVB_KERNEL_CHECK();
 }
 
+// after the import passes: *status = {overflow, collision, claimed slots, winners != claimed, unique nodes}; the unique count also
+// becomes the table's device counter
+__global__ void k_import_status(const uint32_t* __restrict__ flags, const uint64_t* __restrict__ dTot, uint32_t* __restrict__ dCount, uint32_t* __restrict__ status) {
+	const uint32_t fresh = (uint32_t)*dTot;
+	status[0] = flags[0];
+	status[1] = flags[1];
+	status[2] = flags[2];
+	status[3] = (fresh != flags[2]) ? 1u : 0u;
+	status[4] = fresh;
+	*dCount = fresh;
+}
+
+// Stream-ordered: no host synchronisation.  Everything is sized from the gathered counts (an upper bound of the number of
+// unique nodes); the unique count, overflow / collision flags and the winner check land in d_status (5 x u32, device) and
+// are read back ONCE for all levels by merge_resolve() when the build finishes.
 void merge_import(cudaStream_t s, Pool& pool, LevelTable& T, const void* d_all, const uint64_t* counts, uint32_t world, uint64_t strideBytes,
-                  uint32_t myRank, DevBuf<uint32_t>& l2g) {
+                  uint32_t myRank, DevBuf<uint32_t>& l2g, uint32_t* d_status) {
 	if (T.kind == KIND_LEAF) {
 		k_min256<<<1, 256, 0, s>>>(world, (const unsigned long long*)d_all, strideBytes / 8, (unsigned long long*)T.minO.p, T.wide ? 1 : 0);
 		SVB_KERNEL_CHECK();
@@ -1061,6 +1081,7 @@ void merge_import(cudaStream_t s, Pool& pool, LevelTable& T, const void* d_all, 
 	const bool k64 = T.kind == KIND_K64;
 	uint64_t maxCount = 0, sum = 0;
 	for (uint32_t r = 0; r < world; ++r) { if (counts[r] > maxCount) maxCount = counts[r]; sum += counts[r]; }
+	if (sum >= 0xFFFFFFF0ull) throw Error(SVB_ERANGE, "merge_import: more than 2^32 records in one level");
 	const uint64_t myCount = counts[myRank];
 	l2g.reset(pool, myCount ? myCount : 1);
 	// fresh global table
@@ -1072,7 +1093,7 @@ void merge_import(cudaStream_t s, Pool& pool, LevelTable& T, const void* d_all, 
 	if (sum) {
 		const uint64_t total = (uint64_t)world * maxCount;
 		DevBuf<uint64_t> dCounts(pool, world);
-		SVB_CUDA(cudaMemcpyAsync(dCounts.p, counts, world * 8ull, cudaMemcpyHostToDevice, s));
+		SVB_CUDA(cudaMemcpyAsync(dCounts.p, counts, world * 8ull, cudaMemcpyHostToDevice, s));   // pageable source: consumed before the call returns
 		DevBuf<uint32_t> slotOf(pool, total), flags(pool, 4);
 		flags.zero();
 		TableDev t = dev_view(G, flags.p);
@@ -1080,40 +1101,38 @@ void merge_import(cudaStream_t s, Pool& pool, LevelTable& T, const void* d_all, 
 		if (k64) k_import_insert<true><<<nb, DD_THREADS, 0, s>>>(total, maxCount, dCounts.p, (const char*)d_all, strideBytes, t, slotOf.p);
 		else k_import_insert<false><<<nb, DD_THREADS, 0, s>>>(total, maxCount, dCounts.p, (const char*)d_all, strideBytes, t, slotOf.p);
 		SVB_KERNEL_CHECK();
-		uint32_t h[4];
-		SVB_CUDA(cudaMemcpyAsync(h, flags.p, 16, cudaMemcpyDeviceToHost, s));
-		SVB_CUDA(cudaStreamSynchronize(s));
-		if (h[0]) throw Error(SVB_ECUDA, "merge_import: table overflow");
 		DevBuf<uint32_t> flag(pool, total), pos(pool, total);
 		DevBuf<uint64_t> dTot(pool, 1);
 		if (k64) k_import_flag<true><<<nb, DD_THREADS, 0, s>>>(total, maxCount, (const char*)d_all, strideBytes, t, slotOf.p, flag.p);
 		else k_import_flag<false><<<nb, DD_THREADS, 0, s>>>(total, maxCount, (const char*)d_all, strideBytes, t, slotOf.p, flag.p);
 		SVB_KERNEL_CHECK();
 		scan_u32(s, pool, flag.p, total, pos.p, dTot.p);
-		uint64_t fresh = 0;
-		SVB_CUDA(cudaMemcpyAsync(&fresh, dTot.p, 8, cudaMemcpyDeviceToHost, s));
-		SVB_CUDA(cudaStreamSynchronize(s));
-		if (fresh != h[2]) throw Error(SVB_ECUDA, "merge_import: winner count does not match the number of claimed slots");
-		ensure_dense(s, pool, G, fresh);
+		ensure_dense(s, pool, G, sum);   // the unique count is only known on the device
 		if (k64) k_import_assign<true><<<nb, DD_THREADS, 0, s>>>(total, maxCount, (const char*)d_all, strideBytes, t, slotOf.p, flag.p, pos.p, G.dMinO.p, G.dKey64.p, nullptr);
 		else k_import_assign<false><<<nb, DD_THREADS, 0, s>>>(total, maxCount, (const char*)d_all, strideBytes, t, slotOf.p, flag.p, pos.p, G.dMinO.p, nullptr, G.dKey8.p);
 		SVB_KERNEL_CHECK();
 		if (!k64) {
 			k_import_verify<<<nb, DD_THREADS, 0, s>>>(total, maxCount, (const char*)d_all, strideBytes, t, slotOf.p, G.dKey8.p);
 			SVB_KERNEL_CHECK();
-			SVB_CUDA(cudaMemcpyAsync(h, flags.p, 16, cudaMemcpyDeviceToHost, s));
-			SVB_CUDA(cudaStreamSynchronize(s));
-			if (h[1]) throw Error(SVB_ECOLLISION, "merge_import: 64-bit node-key hash collision (exact verify failed)");
 		}
-		SVB_CUDA(cudaMemcpyAsync(G.dCount.p, &fresh, 4, cudaMemcpyHostToDevice, s));   // little endian: low word
-		G.count = fresh;
+		k_import_status<<<1, 1, 0, s>>>(flags.p, dTot.p, G.dCount.p, d_status);
+		SVB_KERNEL_CHECK();
 		if (myCount) {
 			k_import_l2g<<<blocks_for(myCount, DD_THREADS), DD_THREADS, 0, s>>>(myCount, slotOf.p + (uint64_t)myRank * maxCount, G.uid.p, l2g.p);
 			SVB_KERNEL_CHECK();
 		}
-		SVB_CUDA(cudaStreamSynchronize(s));
-	}
+		G.count = sum;   // upper bound until merge_resolve()
+	} else SVB_CUDA(cudaMemsetAsync(d_status, 0, 5 * sizeof(uint32_t), s));
 	T = std::move(G);
+}
+
+// host copy of one level's import status (read back by the caller for all levels at once)
+void merge_resolve(LevelTable& T, const uint32_t status[5]) {
+	if (T.kind == KIND_LEAF) return;
+	if (status[0]) throw Error(SVB_ECUDA, "merge_import: table overflow");
+	if (status[3]) throw Error(SVB_ECUDA, "merge_import: winner count does not match the number of claimed slots");
+	if (status[1]) throw Error(SVB_ECOLLISION, "merge_import: 64-bit node-key hash collision (exact verify failed)");
+	T.count = status[4];
 }
 
 void dedup_level(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a) {

@@ -57,7 +57,8 @@ uint32_t merge_rec_bytes(int kind);
 uint64_t merge_count(const LevelTable& T);
 void merge_export(cudaStream_t s, Pool& pool, LevelTable& T, const uint32_t* l2gChild, void* d_out);
 void merge_import(cudaStream_t s, Pool& pool, LevelTable& T, const void* d_all, const uint64_t* counts, uint32_t world, uint64_t strideBytes,
-                  uint32_t myRank, DevBuf<uint32_t>& l2g);
+                  uint32_t myRank, DevBuf<uint32_t>& l2g, uint32_t* d_status);
+void merge_resolve(LevelTable& T, const uint32_t status[5]);
 
 // Level 0 is never reduced (geom_octree.cpp:483): just resolve the root's children.
 // rootKey: 8 x u32 (uids, or child masks when childMode is a MASK mode), NULLREF = none.

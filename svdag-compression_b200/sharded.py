@@ -6,26 +6,28 @@ unique nodes of a level (key with global child ids + min order key) and rebuild 
 global table; finally every rank holds the same DAG a single GPU would have built
 (GeomOctree::buildDAG's "join + last DAG pass", geom_octree.cpp:397-425, across devices).
 
+Host round trips: ONE.  The record counts of every level and the per-rank counters are known as
+soon as the local phase ends, so a single small all-gather (read back once) sizes every later
+buffer and yields the summed counters; from there on export -> all-gather -> import of all levels
+and of the sub-octree roots is enqueued on the octree's own CUDA stream (svb_stream(), wrapped as
+a torch ExternalStream so NCCL orders itself against it) without waiting for the device.
+
 The exchange is backend-agnostic: `octree` only has to provide the shard_* methods
 (capi.GeomOctree does, over the C ABI; the CPU test-suite plugs a numpy model in and runs the
 same code over gloo)."""
 from __future__ import annotations
 
+import contextlib
+
 import numpy as np
 
 
-def _all_gather_ints(dist, vals, device, group):
+def octree_stream(octree, device):
+    """torch stream context in which the octree's shard_* calls and the collectives are mutually ordered."""
     import torch
-    t = torch.tensor(vals, dtype=torch.int64, device=device)
-    out = torch.empty(dist.get_world_size(group) * len(vals), dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(out, t, group=group)
-    return out.cpu().numpy().reshape(dist.get_world_size(group), len(vals))
-
-
-def _sync(device):
-    import torch
-    if device.type == "cuda":
-        torch.cuda.current_stream(device).synchronize()
+    if device.type != "cuda" or not hasattr(octree, "stream_ptr"):
+        return contextlib.nullcontext()
+    return torch.cuda.stream(torch.cuda.ExternalStream(octree.stream_ptr(), device=device))
 
 
 def build_sharded(octree, levels: int, step: int, bbox, group=None, device=None):
@@ -37,28 +39,35 @@ def build_sharded(octree, levels: int, step: int, bbox, group=None, device=None)
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
     octree.shard_build(levels, step, bbox, rank, world)
     first, last, ntiles, counters = octree.shard_info()
-    exchanged = 0
-    for g in range(last, first - 1, -1):
-        n, rec = octree.shard_level_count(g)
-        counts = _all_gather_ints(dist, [n], device, group)[:, 0]
-        stride = int(max(16, (int(counts.max()) * rec + 15) // 16 * 16))
-        mine = torch.zeros(stride, dtype=torch.uint8, device=device)
-        octree.shard_export_level(g, mine.data_ptr())
-        allb = torch.empty(world * stride, dtype=torch.uint8, device=device)
-        dist.all_gather_into_tensor(allb, mine, group=group)
-        _sync(device)
-        octree.shard_import_level(g, allb.data_ptr(), np.ascontiguousarray(counts, dtype=np.uint64), stride)
-        exchanged += world * stride
-    nt = max(int(ntiles), 1)
-    roots = torch.zeros(nt, dtype=torch.int32, device=device)
-    octree.shard_export_roots(roots.data_ptr())
-    allr = torch.empty(world * nt, dtype=torch.int32, device=device)
-    dist.all_gather_into_tensor(allr, roots, group=group)
-    _sync(device)
-    octree.shard_import_roots(allr.data_ptr())
-    tot = torch.tensor([int(x) for x in counters], dtype=torch.int64, device=device)
-    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
-    _sync(device)
-    st = octree.shard_finish([int(x) for x in tot.cpu().numpy()])
+    order = list(range(last, first - 1, -1))
+    local = [octree.shard_level_count(g) for g in order]          # (records, bytes per record) per level, final after the local phase
+    with octree_stream(octree, device):
+        # the one host round trip: every rank's record counts for all levels + its counters
+        mine = torch.tensor([n for n, _ in local] + [int(x) for x in counters], dtype=torch.int64, device=device)
+        allv = torch.empty(world * mine.numel(), dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(allv, mine, group=group)
+        table = allv.cpu().numpy().reshape(world, mine.numel())
+        exchanged = 0
+        keep = []                                                 # gathered buffers stay alive until the device is done with them
+        for k, g in enumerate(order):
+            counts = np.ascontiguousarray(table[:, k], dtype=np.uint64)
+            rec = local[k][1]
+            stride = int(max(16, (int(counts.max()) * rec + 15) // 16 * 16))
+            buf = torch.empty(stride, dtype=torch.uint8, device=device)      # padding beyond the records is never read
+            octree.shard_export_level(g, buf.data_ptr())
+            allb = torch.empty(world * stride, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(allb, buf, group=group)
+            octree.shard_import_level(g, allb.data_ptr(), counts, stride)
+            keep.append((buf, allb))
+            exchanged += world * stride
+        nt = max(int(ntiles), 1)
+        roots = torch.empty(nt, dtype=torch.int32, device=device)
+        octree.shard_export_roots(roots.data_ptr())
+        allr = torch.empty(world * nt, dtype=torch.int32, device=device)
+        dist.all_gather_into_tensor(allr, roots, group=group)
+        octree.shard_import_roots(allr.data_ptr())
+        totals = [int(x) for x in table[:, len(order):].sum(axis=0)]
+        st = octree.shard_finish(totals)                          # synchronises: the buffers above may go
+    del keep
     st["bytesExchanged"] = exchanged + world * nt * 4
     return st

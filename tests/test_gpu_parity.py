@@ -231,18 +231,23 @@ def _simulate_ranks(pkg, tris, levels, step, world):
         stride = int(max(16, (int(counts.max()) * rec + 15) // 16 * 16))
         bufs = []
         for o in octs:
-            b = torch.zeros(stride, dtype=torch.uint8, device=dev)
+            b = torch.empty(stride, dtype=torch.uint8, device=dev)    # padding beyond the records is never read
             o.shard_export_level(g, b.data_ptr())
             bufs.append(b)
+        for o in octs:
+            o.synchronize()                                           # exports are stream-ordered on each context's own stream
         allb = torch.cat(bufs)
         torch.cuda.synchronize()
         for o in octs:
             o.shard_import_level(g, allb.data_ptr(), counts, stride)
+        for o in octs:
+            o.synchronize()                                           # allb is dropped at the next iteration
     nt = max(ntiles, 1)
     roots = []
     for o in octs:
-        b = torch.zeros(nt, dtype=torch.int32, device=dev)
+        b = torch.empty(nt, dtype=torch.int32, device=dev)
         o.shard_export_roots(b.data_ptr())
+        o.synchronize()
         roots.append(b)
     allr = torch.cat(roots)
     torch.cuda.synchronize()
@@ -262,7 +267,12 @@ def _simulate_ranks(pkg, tris, levels, step, world):
     ("sphere", dict(n_lat=32, n_lon=64), 7, 5, 2),                           # 1-level sub-octrees: roots are voxel masks
     ("city", dict(lots=8), 9, 2, 8),                                         # SVB_SHARD=octant (see below)
     ("soup", dict(n=400, seed=7), 8, 2, 5),
-], ids=["sphere-w2", "city-w4", "terrain-w8", "spongeball-w3", "sphere-leafroots-w2", "city-octant-w8", "soup-w5"])
+    # ranks with an EMPTY share (six of the eight top-level octants hold nothing; more ranks than sub-octrees): their
+    # order-key widths must still match everyone else's, or they rank the merged tables differently
+    ("sphere", dict(n_lat=32, n_lon=64, center=(0.2, 0.2, 0.2), radius=0.15), 8, 2, 8),
+    ("sphere", dict(n_lat=32, n_lon=64, center=(0.2, 0.2, 0.2), radius=0.15), 7, 1, 12),
+], ids=["sphere-w2", "city-w4", "terrain-w8", "spongeball-w3", "sphere-leafroots-w2", "city-octant-w8", "soup-w5",
+        "cornersphere-octant-w8", "cornersphere-w12"])
 def test_sharded_protocol_equals_single_gpu_build(pkg, meshgen, mesh, kw, levels, step, world, monkeypatch, request):
     if "octant" in request.node.callspec.id:
         monkeypatch.setenv("SVB_SHARD", "octant")    # the pure top-level-octant split BASELINE.json names (unbalanced for flat scenes)
