@@ -6,8 +6,8 @@
 One "step" = one full pass of the hot path over the workload: svb_build (voxelize + per-level DAG
 reduction) followed by svb_to_sdag (mirror-symmetry reduction), i.e. triangle soup -> SSVDAG node
 arrays.  `value` is measured with the triangle soup already resident in HBM; `e2e` goes through the
-public C ABI with HOST buffers every step (H2D of the triangles, build, D2H of the SSVDAG levels and
-the host-side .ssvdag encoding).  `--impl reference` times the UNMODIFIED reference svbuilder
+public C ABI with HOST buffers every step (H2D of the triangles from pinned memory, build, toSDAG, the
+.ssvdag image written on the GPU and copied D2H into pinned host memory by rank 0).  `--impl reference` times the UNMODIFIED reference svbuilder
 (oracle/_ref/svbuilder_ref, compiled from /root/reference by oracle/Makefile) on the host cores, on
 a bounded sample of the same workload (see WORKLOADS[*]["cpu_sample"]).
 
@@ -245,12 +245,20 @@ def main():
         sd = oct_.to_sdag()
         return st, sd
 
+    h2d_bytes = [int(T) * 36]
+
     def step_e2e():
-        oct_.set_triangles_ptr(pinned.data_ptr(), T)          # H2D from pinned host memory
+        # H2D from pinned host memory: the whole soup on one GPU; with N ranks every rank copies its 1/N slice over its own
+        # PCIe link and NCCL all-gathers the rest over NVLink (sharded.set_triangles_sharded)
+        if world > 1:
+            h2d_bytes[0] = pkg.sharded.set_triangles_sharded(oct_, pinned, T)
+        else:
+            oct_.set_triangles_ptr(pinned.data_ptr(), T)
         st = oct_.build(L, S, bbox=bbox, **shard)
         sd = oct_.to_sdag()
-        # D2H of the SSVDAG levels + host encoding of the .ssvdag image: the file is written once, by rank 0
-        img = pkg.encoders.encode(oct_, "ssvdag") if rank == 0 else b""
+        # the .ssvdag image is written on the GPU (svb_encode.cu) and lands in pinned host memory: D2H of the finished file,
+        # once, by rank 0 (the file has one writer)
+        img = pkg.encoders.encode_view(oct_, "ssvdag") if rank == 0 else b""
         return st, sd, img
 
     def barrier():
@@ -289,7 +297,7 @@ def main():
             st_e, sd_e, img = step_e2e()
         barrier()
         elapsed_e2e = time.perf_counter() - t1
-        d2h = sum(n * (1 + 32 + 3) for n in oct_.level_sizes())
+        d2h = len(img) + 4 * sum(oct_.level_sizes()[:-1])       # the image + the per-level reference counts of the SSVDAG node order
 
     if world > 1:
         tmax = torch.tensor([elapsed, elapsed_e2e], dtype=torch.float64, device="cuda")
@@ -299,8 +307,9 @@ def main():
     # ---- parity pin: the .ssvdag image this very run produced (N ranks, NCCL merge and all) against the unmodified
     #      reference's file for the same input (tests/golden/*.json) -- asserted at every N, never assumed
     import hashlib
-    if rank == 0 and not img:
-        img = pkg.encoders.encode(oct_, "ssvdag")
+    if rank == 0 and not len(img):
+        img = pkg.encoders.encode_view(oct_, "ssvdag")
+    img = bytes(img)
     sha = hashlib.sha256(img).hexdigest() if rank == 0 else None
     pin = golden_pin(args.workload)
     parity = {"ssvdag_sha256": sha, "ssvdag_bytes": len(img), "reference_pin": None, "ok": None}
@@ -376,7 +385,7 @@ def main():
             "data": "synthetic", "config": config, "build_s": sec, "device_ms_per_step": dev_ms / args.steps,
             "voxels": vox, "triangles": int(T), "nodes": {"svo": st["nNodesSVO"], "dag": st["nNodesDAG"], "sdag": sd["nNodesSDAG"]},
             "tiles": st["nTiles"], "batches": st["nBatches"], "pairs": st["nPairsTotal"], "exact_retests": st["nExactTests"],
-            "e2e": None if args.no_e2e else {"value": vox / sec_e2e / 1e9, "unit": "Gvoxel/s", "h2d_bytes_per_step": int(T) * 36,
+            "e2e": None if args.no_e2e else {"value": vox / sec_e2e / 1e9, "unit": "Gvoxel/s", "h2d_bytes_per_step": h2d_bytes[0] + (4 * sum(oct_.level_sizes()[:-1]) if rank == 0 else 0),
                                              "d2h_bytes_per_step": int(d2h), "seconds_per_step": sec_e2e, "ssvdag_bytes": len(img)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "dedup_effective": dedup_eff, "kernels": kernels, "parity": parity}
     if rank == 0:

@@ -162,9 +162,14 @@ int svb_decode_svdag(const uint8_t* file, uint64_t size, uint32_t* levels, uint6
  * copies the levels D2H and writes the exact file image the reference would save.
  * kind: 0 = .svdag (state DAG), 1 = .ussvdag (state SDAG), 2 = .ssvdag / .esvdag (DAG or SDAG).
  * Returns the image size in bytes (copied into buf when cap is large enough; call with
- * buf = NULL to size), or a negative SVB_E* code.  The encoders are linear host passes, as in
- * the reference. */
+ * buf = NULL to size), or a negative SVB_E* code.  The formats are written ON THE GPU (csrc/svb_encode.cu): only the
+ * finished image crosses PCIe, into a pinned buffer owned by the context.  (.ssvdag: the per-level reference counts
+ * make one round trip to the host, where libstdc++'s own sort routines reproduce the tie order of the reference's
+ * unstable std::sort, encoded_ssvdag.cpp:273-275.) */
 int64_t svb_encode(svb_ctx* ctx, int kind, uint8_t* buf, uint64_t cap);
+/* The same without the final copy: *image points at the context's pinned image (valid until the next call that
+ * changes the octree or encodes another kind); what svbuilder hands to fwrite (main.cpp:220-271). */
+int svb_encode_view(svb_ctx* ctx, int kind, const uint8_t** image, uint64_t* size);
 
 /* Same encoders, fed from host arrays (no GPU, no context): lets a caller that already holds
  * GeomOctree::NodeData (e.g. decoded from a .svdag, main.cpp:97-101) write the file formats, and
@@ -174,6 +179,13 @@ int64_t svb_encode(svb_ctx* ctx, int kind, uint8_t* buf, uint64_t cap);
 int64_t svb_encode_levels(uint32_t levels, const uint64_t* counts, const uint8_t* mask, const uint32_t* child8,
                           const uint8_t* mirror3, const uint32_t* childLevel8, const float bboxF[6], double rootSide,
                           uint64_t nNodes, int state, int kind, uint8_t* buf, uint64_t cap);
+
+/* The host step of the .ssvdag encoder on its own (no GPU, no context): node order of every level from the per-level
+ * reference counts, i.e. std::sort by count, descending, UNSTABLE, with exactly the tie order libstdc++'s std::sort
+ * gives the reference (encoded_ssvdag.cpp:261-276) -- computed by the same library routines with the independent
+ * halves of every partition running as parallel tasks.  refs / order: levels 0 .. nLevels-1 concatenated, level l at
+ * [start[l], start[l+1]); level 0 (the root) is not sorted.  order[start[l] + r] = index of the node at rank r. */
+int svb_ssvdag_order_from_refs(const uint32_t* refs, const uint32_t* start, uint32_t nLevels, uint32_t* order);
 
 /* Per-kernel profile of the last svb_build/svb_to_sdag (enabled by svb_set_profiling(ctx,1)):
  * one record per dedup-family launch group, with the algorithmic byte count SURVEY.md §8(d)

@@ -665,6 +665,14 @@ uint64_t orc_stat(void* h, int which) {
 	return 0;
 }
 double orc_root_side(void* h) { return ((Oct*)h)->rootSide; }
+// The node order of one SSVDAG level exactly as the reference produces it (encoded_ssvdag.cpp:261-276): pairs (index, refs)
+// in index order, plain std::sort with the reference's comparator.  order[r] = index of the node at rank r.
+void orc_sort_by_refs(uint32_t n, const uint32_t* refs, uint32_t* order) {
+	std::vector<std::pair<id_t32, id_t32>> hist(n);
+	for (uint32_t i = 0; i < n; ++i) { hist[i].first = i; hist[i].second = refs[i]; }
+	std::sort(hist.begin(), hist.end(), [](std::pair<id_t32, id_t32> a, std::pair<id_t32, id_t32> b) { return a.second > b.second; });
+	for (uint32_t i = 0; i < n; ++i) order[i] = hist[i].first;
+}
 // SoA copy-out of one level (any pointer may be NULL)
 int orc_get_level(void* h, unsigned lev, uint8_t* mask, uint32_t* child8, uint8_t* mirror3, uint8_t* inv, uint32_t* childLev8) {
 	Oct* o = (Oct*)h;

@@ -18,7 +18,7 @@ SVBUILDER = HERE / "svbuilder"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = "/usr/bin/g++"   # the environment's CXX points at a compiler without libgomp; pin the system one
 
-CU_SOURCES = ["svb_prims.cu", "svb_voxelize.cu", "svb_dedup.cu", "svb_sdag.cu", "svb_cross.cu", "svb_api.cu", "svb_raycast.cu", "host/encoders.cpp"]
+CU_SOURCES = ["svb_prims.cu", "svb_voxelize.cu", "svb_dedup.cu", "svb_sdag.cu", "svb_cross.cu", "svb_encode.cu", "svb_api.cu", "svb_raycast.cu", "host/encoders.cpp"]
 # the ray caster must round every float operation separately (pixel-exact against oracle/dda_oracle.c)
 EXTRA_FLAGS = {"svb_raycast.cu": ["--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false"]}
 NVCC_FLAGS = [
@@ -71,7 +71,8 @@ def build_svbuilder(force: bool = False) -> Path:
         return SVBUILDER
     cmd = [HOSTCXX, "-O2", "-std=c++14", "-ffp-contract=off", "-Wall", "-I", str(HERE.parent / "include"), "-I", str(host)]
     cmd += [str(s) for s in srcs] + ["-o", str(SVBUILDER), f"-L{HERE}", "-lsvb", f"-Wl,-rpath,{HERE}", "-Wl,-rpath,$ORIGIN",
-                                     "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
+                                     "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-I/usr/local/cuda/include",
+                                     "-lcudart", "-lnccl", "-pthread"]   # NCCL only in the tool (multi-GPU from one process); libsvb.so itself is NCCL-free
     subprocess.run(cmd, check=True)
     return SVBUILDER
 

@@ -1,4 +1,5 @@
 #include "geom_octree.hpp"
+#include "sharded_build.hpp"
 
 #include <algorithm>
 #include <cstdio>
@@ -10,15 +11,22 @@
 
 namespace svbhost {
 
-GeomOctree::GeomOctree(Scene* scene, int device) : _scene(scene) {
+GeomOctree::GeomOctree(Scene* scene, int device) : GeomOctree(scene, std::vector<int>(1, device)) {}
+
+GeomOctree::GeomOctree(Scene* scene, const std::vector<int>& devices) : _scene(scene), _devices(devices) {
 	memset(&_stats, 0, sizeof(_stats));
-	_ctx = svb_create(device);
-	if (!_ctx) {
-		fprintf(stderr, "ERROR: no usable CUDA device %d (this build of svbuilder has no CPU path)\n", device);
-		exit(1);
+	if (_devices.empty()) _devices.push_back(0);
+	for (int d : _devices) {
+		svb_ctx* c = svb_create(d);
+		if (!c) {
+			fprintf(stderr, "ERROR: no usable CUDA device %d (this build of svbuilder has no CPU path)\n", d);
+			exit(1);
+		}
+		_ctxs.push_back(c);
 	}
+	_ctx = _ctxs[0];
 }
-GeomOctree::~GeomOctree() { svb_destroy(_ctx); }
+GeomOctree::~GeomOctree() { for (svb_ctx* c : _ctxs) svb_destroy(c); }
 
 void GeomOctree::check(int rc, const char* what) {
 	if (rc == SVB_OK) return;
@@ -52,8 +60,18 @@ void GeomOctree::toDAG(bool internalCall) {
 
 void GeomOctree::buildDAG(unsigned levels, unsigned stepLevel, const double bmin[3], const double bmax[3], bool verbose) {
 	printf("* Building DAG [stepLevel: %i]\n", stepLevel); fflush(stdout);
-	if (!_trisUploaded) { check(svb_set_triangles(_ctx, _scene->getTrianglePtr(), _scene->getNRawTriangles()), "svb_set_triangles"); _trisUploaded = true; }
-	check(svb_build(_ctx, levels, stepLevel, bmin, bmax, &_stats), "svb_build");
+	if (_ctxs.size() > 1 && stepLevel > 0) {
+		printf("\t- %zu GPUs: sub-octrees dealt over the devices, levels merged over NCCL\n", _ctxs.size()); fflush(stdout);
+		std::string err;
+		if (!build_dag_sharded(_devices, _ctxs, _scene->getTrianglePtr(), _scene->getNRawTriangles(), levels, stepLevel, bmin, bmax, &_stats, &err, &_msUpload, &_msExchange)) {
+			fprintf(stderr, "ERROR in the multi-GPU build: %s\n", err.c_str());
+			exit(1);
+		}
+		_trisUploaded = false;
+	} else {
+		if (!_trisUploaded) { check(svb_set_triangles(_ctx, _scene->getTrianglePtr(), _scene->getNRawTriangles()), "svb_set_triangles"); _trisUploaded = true; }
+		check(svb_build(_ctx, levels, stepLevel, bmin, bmax, &_stats), "svb_build");
+	}
 	_levels = levels;
 	_state = S_DAG;
 	if (verbose) printf("\t- %lu subtrees in %lu device batches, %lu (triangle,node) pairs\n", (unsigned long)_stats.nTiles, (unsigned long)_stats.nBatches, (unsigned long)_stats.nPairsTotal);
@@ -112,15 +130,25 @@ OctreeData GeomOctree::getNodeData() {
 	return o;
 }
 
-bool GeomOctree::encodeToFile(int kind, const std::string& fileName, size_t* bytes) {
-	OctreeData o = getNodeData();
-	std::vector<uint8_t> img;
-	std::string err;
-	if (!encode_file(o, kind, img, &err)) { printf("%s\n", err.c_str()); return false; }
-	std::ofstream out(fileName, std::ios::binary);
-	if (!out.is_open()) { printf("FAILED!!!\n"); return false; }
-	out.write((const char*)img.data(), (std::streamsize)img.size());
-	if (bytes) *bytes = img.size();
+bool GeomOctree::encodeToFile(int kind, const std::string& fileName, size_t* fileBytes, size_t* dataBytes) {
+	const uint8_t* img = nullptr;
+	uint64_t size = 0;
+	int rc = svb_encode_view(_ctx, kind, &img, &size);
+	if (rc != SVB_OK) { printf("%s\n", svb_last_error(_ctx)); return false; }   // e.g. "FAILED! Octree is not in DAG state" (encoded_svdag.cpp:109-112)
+	FILE* f = fopen(fileName.c_str(), "wb");
+	if (!f) { printf("FAILED!!!\n"); return false; }
+	bool ok = true;
+	if (_bboxOverride) {   // main.cpp:179-193: the header carries the rescaled scene box and root side
+		uint8_t head[28];
+		memcpy(head, _bboxF, 24);
+		const float rs = (float)_rootSideOverride;
+		memcpy(head + 24, &rs, 4);
+		ok = fwrite(head, 1, 28, f) == 28 && fwrite(img + 28, 1, size - 28, f) == size - 28;
+	} else ok = fwrite(img, 1, size, f) == size;
+	fclose(f);
+	if (!ok) { printf("FAILED!!!\n"); return false; }
+	if (fileBytes) *fileBytes = size;
+	if (dataBytes) *dataBytes = size - (kind == SVB_FILE_SSVDAG ? 36 + 12 : 44);
 	return true;
 }
 

@@ -5,6 +5,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include "octree_data.hpp"
 #include "scene.hpp"
@@ -18,6 +19,9 @@ public:
 	typedef svb_stats Stats;
 
 	explicit GeomOctree(Scene* scene, int device = 0);
+	// several GPUs of one node: buildDAG (step > 0) spreads the sub-octrees over them (sharded_build.hpp); everything
+	// after the build (toSDAG, cross-level merge, encoders) runs on devices[0]
+	GeomOctree(Scene* scene, const std::vector<int>& devices);
 	~GeomOctree();
 	GeomOctree(const GeomOctree&) = delete;
 	GeomOctree& operator=(const GeomOctree&) = delete;
@@ -42,13 +46,21 @@ public:
 
 	// getNodeData(): copies the levels D2H
 	OctreeData getNodeData();
-	// encode(const GeomOctree&) + save() of the three encoders, through the same host code as svb_encode()
-	bool encodeToFile(int kind, const std::string& fileName, size_t* bytes = nullptr);
+	// encode(const GeomOctree&) + save() of the three encoders: the image is written on the GPU (svb_encode_view) and
+	// handed to fwrite from pinned memory.  *dataBytes receives what the reference's getDataSize() reports for that
+	// encoder (the payload without headers and length prefixes: encoded_svdag.hpp:47, encoded_ssvdag.hpp:43-45).
+	bool encodeToFile(int kind, const std::string& fileName, size_t* fileBytes = nullptr, size_t* dataBytes = nullptr);
+	double lastUploadMs() const { return _msUpload; }
+	double lastExchangeMs() const { return _msExchange; }
+	size_t nDevices() const { return _devices.size(); }
 
 private:
 	void check(int rc, const char* what);
 	Scene* _scene;
-	svb_ctx* _ctx;
+	svb_ctx* _ctx;                       // == _ctxs[0]
+	std::vector<int> _devices;
+	std::vector<svb_ctx*> _ctxs;
+	double _msUpload = 0, _msExchange = 0;
 	State _state = S_EMPTY;
 	Stats _stats;
 	unsigned _levels = 0;

@@ -15,6 +15,7 @@
 #include "svb_cross.cuh"
 #include "host/octree_data.hpp"
 #include "svb_dedup.cuh"
+#include "svb_encode.cuh"
 #include "svb_sdag.cuh"
 #include "svb_voxelize.cuh"
 
@@ -200,6 +201,7 @@ struct svb_build_state {
 	DevBuf<uint32_t> tileRootRef;        // per tile: uid of its (reduced) root at level s1; UNSET if not built here
 	std::vector<DevBuf<uint32_t>> l2g;   // multi-GPU merge: local uid -> global uid per level
 	std::vector<bool> merged;
+	RootPairsAll rootsAll;               // root pairs of all of this rank's sub-octrees, binned once (valid only during the local phase)
 	DevBuf<uint32_t> mergeStatus;        // multi-GPU merge: 8 x u32 per level, written by merge_import, read back once by build_finish
 	bool finished = false;
 	uint64_t launches0 = 0;
@@ -227,7 +229,7 @@ void set_order_key_width(BuildState& B, int Lt, int tb) {
 
 // bottom-up reduction of one batch's levels [lo_l, Lt-1] into the tables
 void dedup_batch(svb_ctx* c, BuildState& B, std::vector<BatchLevel>& lv, int Lt, uint32_t gbase, const uint32_t* d_tileSeq, const uint32_t* d_tileStart, int lo_l,
-                 const std::vector<uint32_t>& hseq, int hi_l = -1) {
+                 const std::vector<uint32_t>& hseq, int hi_l = -1, const LeafQuery* query = nullptr) {
 	if (hi_l < 0) hi_l = Lt - 1;   // (Lt - 2: the leaf level has been reduced already, see run_tile_batch)
 	const uint32_t seqLo = hseq.empty() ? 0 : *std::min_element(hseq.begin(), hseq.end()), seqHi = hseq.empty() ? 0 : *std::max_element(hseq.begin(), hseq.end());
 	const bool seqMono = std::is_sorted(hseq.begin(), hseq.end());
@@ -239,6 +241,7 @@ void dedup_batch(svb_ctx* c, BuildState& B, std::vector<BatchLevel>& lv, int Lt,
 		a.N = X.n; a.code = X.code.p; a.tstar = X.tstar.p; a.mask = X.mask.p; a.childBase = X.childBase.p;
 		a.l = l; a.tbits = tb; a.tileSeq = d_tileSeq; a.tileStart = d_tileStart;
 		a.seqLo = seqLo; a.seqHi = seqHi; a.seqMonotone = seqMono;
+		a.query = query;
 		int ob = B.tileBits + tb + 3 * l;
 		if (ob > B.obits[g]) B.obits[g] = ob;
 		LevelTable& T = B.tables[g];
@@ -285,8 +288,20 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 	const uint32_t seqLo = *std::min_element(hseq.begin(), hseq.end());
 	const bool leafLevelBatch = gbase != 0 && !keepLevels && Lt >= 2 && B.tables[gbase + Lt - 1].kind == KIND_LEAF;
 	bool leafT = leafLevelBatch ? leaf_tstar_needed(B.tables[gbase + Lt - 1], seqLo) : true;
+	// ... and the same one level up: on the 4^3 level only the nodes of entries that are NEW to its table need a first touch
+	// (a few thousand per batch); they are queried directly (svb_dedup.cu::k_k64_query).  SVB_K64_NOTSTAR=0 keeps tracking it.
+	auto k64_untracked_ok = [&] {
+		if (leafT || Lt < 3) return false;
+		const char* e = getenv("SVB_K64_NOTSTAR");
+		if (e && e[0] == '0') return false;
+		return k64_tstar_optional(B.tables[gbase + Lt - 2], seqLo);
+	};
+	bool k64U = k64_untracked_ok();
 	bool leafDone = false;
-	DevBuf<uint32_t> rootTri;   // root pair -> triangle (outlives the voxelizer: the leaf query below reads it)
+	LeafQuery lqBatch;
+	DevBuf<uint32_t> rootTriOwn;   // root pair -> triangle (outlives the voxelizer: the leaf query below reads it)
+	const uint32_t* rootTri = nullptr;
+	const bool rootsOnce = gbase != 0 && B.rootsAll.valid;
 	uint64_t P = 0;
 	DevBuf<uint64_t> exactBefore(c->pool, 1);
 	SVB_CUDA(cudaMemcpyAsync(exactBefore.p, B.dExact.p, 8, cudaMemcpyDeviceToDevice, s));
@@ -301,12 +316,16 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 			cellLo[0] = std::min(cellLo[0], th.ix); cellLo[1] = std::min(cellLo[1], th.iy); cellLo[2] = std::min(cellLo[2], th.iz);
 			cellHi[0] = std::max(cellHi[0], th.ix); cellHi[1] = std::max(cellHi[1], th.iy); cellHi[2] = std::max(cellHi[2], th.iz);
 		}
-		make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, d_selPos, a, nt, ptri, pnode, rootTri, dTileStart, P, cellLo, cellHi);
+		if (rootsOnce) batch_root_pairs(s, c->pool, B.rootsAll, a, nt, ptri, pnode, rootTri, dTileStart, P);
+		else {
+			make_root_pairs(s, c->pool, c->d_tris, c->T, grid, d_gridTile, d_selPos, a, nt, ptri, pnode, rootTriOwn, dTileStart, P, cellLo, cellHi);
+			rootTri = rootTriOwn.p;
+		}
 		CtxProfHook hook(c);
 		bool direct = true;
 		for (uint32_t i = 0; i < nt && direct; ++i) direct = centre_chain_exact(hg[i], Lt);
 		try {
-			voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, rootTri.p, dTileStart.p, P, budget, nodeCap, lv, pairs, B.dExact.p, direct, B.allFlat, leafT, c->profiling ? &hook : nullptr);
+			voxelize_batch(s, c->pool, c->d_tris, dTiles.p, nt, Lt, ptri, pnode, rootTri, dTileStart.p, P, budget, nodeCap, lv, pairs, B.dExact.p, direct, B.allFlat, leafT ? 0 : (k64U ? 2 : 1), c->profiling ? &hook : nullptr);
 		} catch (const BatchTooBig&) {   // the range is cut and voxelized again: the aborted attempt's exact-test count must not stay in the counter
 			SVB_CUDA(cudaMemcpyAsync(B.dExact.p, exactBefore.p, 8, cudaMemcpyDeviceToDevice, s));
 			SVB_CUDA(cudaStreamSynchronize(s));
@@ -324,7 +343,8 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 		da.N = X.n; da.mask = X.mask.p; da.code = X.code.p; da.l = Lt - 1;
 		da.tbits = B.tbLocal; da.tileSeq = dSeq.p; da.tileStart = dTileStart.p;
 		LeafQuery lq;
-		lq.tris = c->d_tris; lq.rootTri = rootTri.p; lq.P = P; lq.tiles = dTiles.p;
+		lq.tris = c->d_tris; lq.rootTri = rootTri; lq.P = P; lq.tiles = dTiles.p;
+		lqBatch = lq;
 		da.seqLo = seqLo; da.seqHi = *std::max_element(hseq.begin(), hseq.end()); da.seqMonotone = std::is_sorted(hseq.begin(), hseq.end());
 		ProfScope ps(c, "dedup_leaf", g, X.n);
 		leafDone = dedup_leaf_known(s, c->pool, B.tables[g], da, lq, B.dVoxels.p);
@@ -339,6 +359,7 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 	// an unknown voxel mask: once more, with first touches
 	if (getenv("SVB_VX_STATS")) fprintf(stderr, "[vx-stats] batch [%u,%u): a voxel mask without an entry -- voxelizing again with leaf first touches\n", a, b);
 	leafT = true;
+	k64U = false;
 	SVB_CUDA(cudaMemcpyAsync(B.dExact.p, exactBefore.p, 8, cudaMemcpyDeviceToDevice, s));
 	lv.clear();
 	}
@@ -362,7 +383,7 @@ void run_tile_batch(svb_ctx* c, BuildState& B, const std::vector<TileHost>& tile
 		B.rootChildMode = r.childMode;
 		root_key(s, r, B.rootKey.p);
 	} else {
-		dedup_batch(c, B, lv, Lt, gbase, dSeq.p, dTileStart.p, 0, hseq, leafDone ? Lt - 2 : Lt - 1);
+		dedup_batch(c, B, lv, Lt, gbase, dSeq.p, dTileStart.p, 0, hseq, leafDone ? Lt - 2 : Lt - 1, (leafDone && k64U) ? &lqBatch : nullptr);
 		// remember what each sub-octree root was reduced to (uid, or the voxel mask for 1-level sub-octrees)
 		if (B.tables[gbase].kind == KIND_LEAF) k_scatter_u8<<<blocks_for(nt, 256), 256, 0, s>>>(nt, dSeq.p, lv[0].mask.p, B.tileRootRef.p);
 		else k_scatter_u32<<<blocks_for(nt, 256), 256, 0, s>>>(nt, dSeq.p, lv[0].ref.p, B.tileRootRef.p);
@@ -424,7 +445,7 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 	c->out.clear();
 	c->state = SVB_S_EMPTY;
 	c->prof.clear();
-	c->lastImage.clear(); c->lastImageKind = -1;
+	c->lastImageKind = -1;
 	memset(&c->stats, 0, sizeof(c->stats));
 	c->build.reset(new BuildState());
 	BuildState& B = *c->build;
@@ -562,14 +583,32 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 		} else owner = q % world;
 		if (owner == rank) mine.push_back(q);
 	}
-	// leaf-level nodes one batch may hold: 32-bit indices, and ~40 bytes of transient state per leaf node
-	uint64_t nodeCap = std::min<uint64_t>(3600000000ull, (budget - c->pool.live) / 40);
 	{
 		std::vector<int> hpos(nTiles ? nTiles : 1, -1);
 		for (size_t i = 0; i < mine.size(); ++i) hpos[mine[i]] = (int)i;
 		upload(s, c->pool, B.dSelPos, hpos);
 	}
-	if (!mine.empty()) run_tiles_split(c, B, mine, Lt, s1, budget, nodeCap);
+	// root pairs of all of this rank's sub-octrees, binned once (SVB_ROOTS_ONCE=0: once per tile batch, as before)
+	if (!mine.empty() && !(getenv("SVB_ROOTS_ONCE") && getenv("SVB_ROOTS_ONCE")[0] == '0')) {
+		int cellLo[3] = {1 << 30, 1 << 30, 1 << 30}, cellHi[3] = {-1, -1, -1};
+		for (uint32_t q : mine) {
+			const TileHost& th = B.tiles[q];
+			cellLo[0] = std::min(cellLo[0], th.ix); cellLo[1] = std::min(cellLo[1], th.iy); cellLo[2] = std::min(cellLo[2], th.iz);
+			cellHi[0] = std::max(cellHi[0], th.ix); cellHi[1] = std::max(cellHi[1], th.iy); cellHi[2] = std::max(cellHi[2], th.iz);
+		}
+		try {
+			StageTimer tm(s);
+			make_root_pairs_all(s, c->pool, c->d_tris, c->T, B.grid, B.dGrid.p, B.dSelPos.p, (uint32_t)mine.size(), B.rootsAll, cellLo, cellHi);
+			B.msVox += tm.stop();
+		} catch (const BatchTooBig&) {
+			B.rootsAll = RootPairsAll();   // more than 2^32 root pairs in one piece: bin per batch
+		}
+	}
+	// leaf-level nodes one batch may hold: 32-bit indices, and ~40 bytes of transient state per leaf node
+	const uint64_t budgetTiles = batch_budget(c);
+	uint64_t nodeCap = std::min<uint64_t>(3600000000ull, (budgetTiles - c->pool.live) / 40);
+	if (!mine.empty()) run_tiles_split(c, B, mine, Lt, s1, budgetTiles, nodeCap);
+	B.rootsAll = RootPairsAll();
 }
 
 // ---- phase 3: reduce the base octree on top of the (global) sub-octree roots, rank, materialise
@@ -745,6 +784,8 @@ void svb_destroy(svb_ctx* c) {
 	c->out.clear();
 	c->trisOwned.release();
 	cudaStreamSynchronize(c->stream);
+	c->image.release();
+	c->staging.release();
 	c->pool.release_all();
 	cudaStreamDestroy(c->stream);
 	delete c;
@@ -887,7 +928,7 @@ int svb_shard_finish(svb_ctx* c, const uint64_t totals[5], svb_stats* out) {
 int svb_to_sdag(svb_ctx* c, svb_stats* out) {
 	int rc = guarded(c, [&] {
 		if (c->state != SVB_S_DAG) throw Error(SVB_EINVAL, "ERROR! This is not a DAG or SDAG!");   // geom_octree.cpp:560-563
-		c->lastImage.clear(); c->lastImageKind = -1;
+		c->lastImageKind = -1;
 		const uint64_t launches0 = g_launches.load();
 		StageTimer tm(c->stream);
 		uint64_t nn = to_sdag_device(c);
@@ -905,7 +946,7 @@ int svb_to_sdag(svb_ctx* c, svb_stats* out) {
 int svb_cross_merge(svb_ctx* c, svb_stats* out) {
 	int rc = guarded(c, [&] {
 		if (c->state != SVB_S_DAG) throw Error(SVB_EINVAL, "cross-level merge needs an octree in DAG state");
-		c->lastImage.clear(); c->lastImageKind = -1;
+		c->lastImageKind = -1;
 		const uint64_t launches0 = g_launches.load();
 		StageTimer tm(c->stream);
 		uint64_t nn = 0;
@@ -958,48 +999,67 @@ int svb_download_level(svb_ctx* c, uint32_t lev, uint8_t* mask, uint32_t* child8
 	});
 }
 
+// the previous round's path: copy the levels D2H and run the host encoders (csrc/host/encoders.cpp); SVB_ENCODE=host selects it
+static uint64_t encode_host_path(svb_ctx* c, int kind) {
+	svbhost::OctreeData o;
+	o.levels.resize(c->levels);
+	cudaStream_t s = c->stream;
+	for (uint32_t l = 0; l < c->levels; ++l) {
+		OutLevel& d = c->out[l];
+		svbhost::LevelSoA& h = o.levels[l];
+		h.n = d.n;
+		h.mask.resize(d.n); h.child.resize(d.n * 8); h.mirror.resize(d.n * 3);
+		if (d.n) {
+			SVB_CUDA(cudaMemcpyAsync(h.mask.data(), d.mask.p, d.n, cudaMemcpyDeviceToHost, s));
+			SVB_CUDA(cudaMemcpyAsync(h.child.data(), d.child.p, d.n * 32, cudaMemcpyDeviceToHost, s));
+			SVB_CUDA(cudaMemcpyAsync(h.mirror.data(), d.mirror.p, d.n * 3, cudaMemcpyDeviceToHost, s));
+			if (d.hasChildLevel) {
+				h.childLevel.resize(d.n * 8);
+				SVB_CUDA(cudaMemcpyAsync(h.childLevel.data(), d.childLevel.p, d.n * 32, cudaMemcpyDeviceToHost, s));
+			}
+		}
+	}
+	SVB_CUDA(cudaStreamSynchronize(s));
+	memcpy(o.bboxF, c->stats.bboxF, 24);
+	o.rootSide = c->stats.rootSide;
+	o.nNodes = c->stats.nNodes;
+	o.nVoxels = c->stats.nTotalVoxels;
+	o.state = c->state;
+	std::vector<uint8_t> img;
+	std::string err;
+	if (!svbhost::encode_file(o, kind, img, &err)) throw Error(SVB_EINVAL, err);
+	memcpy(c->image.reserve(img.size()), img.data(), img.size());
+	return img.size();
+}
+
+static void encode_cached(svb_ctx* c, int kind) {
+	if (c->state != SVB_S_DAG && c->state != SVB_S_SDAG) throw Error(SVB_EINVAL, "nothing to encode");
+	const char* e = getenv("SVB_ENCODE");
+	const bool host = e && e[0] == 'h';
+	const int key = kind + (host ? 16 : 0);
+	if (c->lastImageKind == key && c->imageSize) return;
+	c->lastImageKind = -1;
+	c->imageSize = host ? encode_host_path(c, kind) : encode_device(c, kind);
+	c->lastImageKind = key;
+}
+
 int64_t svb_encode(svb_ctx* c, int kind, uint8_t* buf, uint64_t cap) {
 	int64_t size = -1;
 	int rc = guarded(c, [&] {
-		if (c->state != SVB_S_DAG && c->state != SVB_S_SDAG) throw Error(SVB_EINVAL, "nothing to encode");
-		if (c->lastImageKind == kind && !c->lastImage.empty()) {
-			size = (int64_t)c->lastImage.size();
-			if (buf && cap >= c->lastImage.size()) memcpy(buf, c->lastImage.data(), c->lastImage.size());
-			return;
-		}
-		svbhost::OctreeData o;
-		o.levels.resize(c->levels);
-		cudaStream_t s = c->stream;
-		for (uint32_t l = 0; l < c->levels; ++l) {
-			OutLevel& d = c->out[l];
-			svbhost::LevelSoA& h = o.levels[l];
-			h.n = d.n;
-			h.mask.resize(d.n); h.child.resize(d.n * 8); h.mirror.resize(d.n * 3);
-			if (d.n) {
-				SVB_CUDA(cudaMemcpyAsync(h.mask.data(), d.mask.p, d.n, cudaMemcpyDeviceToHost, s));
-				SVB_CUDA(cudaMemcpyAsync(h.child.data(), d.child.p, d.n * 32, cudaMemcpyDeviceToHost, s));
-				SVB_CUDA(cudaMemcpyAsync(h.mirror.data(), d.mirror.p, d.n * 3, cudaMemcpyDeviceToHost, s));
-				if (d.hasChildLevel) {
-					h.childLevel.resize(d.n * 8);
-					SVB_CUDA(cudaMemcpyAsync(h.childLevel.data(), d.childLevel.p, d.n * 32, cudaMemcpyDeviceToHost, s));
-				}
-			}
-		}
-		SVB_CUDA(cudaStreamSynchronize(s));
-		memcpy(o.bboxF, c->stats.bboxF, 24);
-		o.rootSide = c->stats.rootSide;
-		o.nNodes = c->stats.nNodes;
-		o.nVoxels = c->stats.nTotalVoxels;
-		o.state = c->state;
-		std::vector<uint8_t> img;
-		std::string err;
-		if (!svbhost::encode_file(o, kind, img, &err)) throw Error(SVB_EINVAL, err);
-		size = (int64_t)img.size();
-		if (buf && cap >= img.size()) memcpy(buf, img.data(), img.size());
-		c->lastImage.swap(img);
-		c->lastImageKind = kind;
+		encode_cached(c, kind);
+		size = (int64_t)c->imageSize;
+		if (buf && cap >= c->imageSize) memcpy(buf, c->image.p, c->imageSize);
 	});
 	return rc == SVB_OK ? size : (int64_t)rc;
+}
+
+int svb_encode_view(svb_ctx* c, int kind, const uint8_t** image, uint64_t* size) {
+	return guarded(c, [&] {
+		if (!image || !size) throw Error(SVB_EINVAL, "null output pointer");
+		encode_cached(c, kind);
+		*image = c->image.p;
+		*size = c->imageSize;
+	});
 }
 
 int64_t svb_encode_levels(uint32_t levels, const uint64_t* counts, const uint8_t* mask, const uint32_t* child8,
@@ -1033,6 +1093,16 @@ int64_t svb_encode_levels(uint32_t levels, const uint64_t* counts, const uint8_t
 	}
 }
 
+int svb_ssvdag_order_from_refs(const uint32_t* refs, const uint32_t* start, uint32_t nLevels, uint32_t* order) {
+	if (!refs || !start || !order || nLevels == 0 || nLevels > 64) return SVB_EINVAL;
+	try {
+		svbhost::ssvdag_order_from_refs(refs, start, (int)nLevels, order);
+		return SVB_OK;
+	} catch (...) {
+		return SVB_ENOMEM;
+	}
+}
+
 int svb_upload_levels(svb_ctx* c, uint32_t levels, const uint64_t* counts, const uint8_t* mask, const uint32_t* child8,
                       const float bboxF[6], double rootSide, uint64_t nVoxels) {
 	return guarded(c, [&] {
@@ -1054,7 +1124,7 @@ int svb_upload_levels(svb_ctx* c, uint32_t levels, const uint64_t* counts, const
 				off += counts[l];
 			}
 		}
-		c->lastImage.clear(); c->lastImageKind = -1;
+		c->lastImageKind = -1;
 		cudaStream_t s = c->stream;
 		c->out.clear();
 		c->out.resize(levels);

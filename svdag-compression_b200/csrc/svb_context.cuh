@@ -6,6 +6,24 @@
 
 struct svb_build_state;   // svb_api.cu: tables and tile list a build keeps between its phases
 
+// page-locked host buffer owned by a context: D2H / H2D copies run at full PCIe rate and without a bounce buffer
+struct PinnedBuf {
+	uint8_t* p = nullptr;
+	size_t cap = 0;
+	uint8_t* reserve(size_t bytes) {
+		if (bytes > cap) {
+			if (p) cudaFreeHost(p);
+			p = nullptr;
+			cap = 0;
+			size_t want = bytes + bytes / 4 + 4096;
+			if (cudaMallocHost((void**)&p, want) != cudaSuccess) { cudaGetLastError(); throw svb::Error(SVB_ENOMEM, "cudaMallocHost failed"); }
+			cap = want;
+		}
+		return p;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct svb_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
@@ -29,7 +47,8 @@ struct svb_ctx {
 	uint64_t batchBudget = 0;
 	// last file image produced by svb_encode (a size query followed by the real call must not encode twice);
 	// dropped whenever the octree changes
-	std::vector<uint8_t> lastImage;
+	PinnedBuf image, staging;
+	uint64_t imageSize = 0;
 	int lastImageKind = -1;
 	std::shared_ptr<svb_build_state> build;   // non-null between svb_shard_build and svb_shard_finish
 	svb_ctx() { memset(&stats, 0, sizeof(stats)); }

@@ -395,10 +395,14 @@ struct OnePass {
 	uint32_t* newSlots;    // slots claimed by this launch
 	uint32_t* unres;       // nodes whose ref is still a marked slot
 	uint32_t listCap;
-	uint32_t* counters;    // [0] unresolved nodes
+	uint32_t* counters;    // [0] unresolved nodes, [1] nodes of new entries whose first touch has to be queried (UNTRACKED)
+	uint2* qlist;          // UNTRACKED: (node, slot) of those nodes
 };
 
-template <int NPT>
+// UNTRACKED (only ever with t.later): the level's first touches were not recorded by the voxelizer (a.tstar == nullptr).
+// Existing entries are frozen and need none; a node whose entry is NEW is listed and gets its first touch from a direct
+// query afterwards (k_k64_query) -- a few thousand nodes out of ~3 * 10^8 per tile batch of the 16K^3 city.
+template <int NPT, bool UNTRACKED = false>
 __global__ void __launch_bounds__(DD_THREADS) k_insert_k64(DedupArgs a, TableDev t, OnePass op) {
 	const uint64_t n0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * NPT;
 	if (n0 >= a.N) return;
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(DD_THREADS) k_insert_k64(DedupArgs a, TableDev
 		if (live[j]) {
 			idx[j] = mix64(key[j]) & t.capMask;
 			cur[j] = t.tag[idx[j]];
-			if (!t.later) O[j] = order_key(a.code[n0 + j], a.tstar[n0 + j], a);   // (later: only the rare new entries need it)
+			if (!UNTRACKED && !t.later) O[j] = order_key(a.code[n0 + j], a.tstar[n0 + j], a);   // (later: only the rare new entries need it)
 		}
 	}
 #pragma unroll
@@ -450,8 +454,13 @@ __global__ void __launch_bounds__(DD_THREADS) k_insert_k64(DedupArgs a, TableDev
 			u = __ldcg(&t.uid[i]);
 		}
 		if (!(t.later && u < t.countBefore)) {   // frozen entries keep their order key
-			if (t.later) O[j] = order_key(a.code[n], a.tstar[n], a);
-			if (t.minO[i] > O[j]) atomicMin(&t.minO[i], O[j]);
+			if (UNTRACKED) {
+				const uint32_t k = atomicAdd(&op.counters[1], 1u);
+				if (k < op.listCap) op.qlist[k] = make_uint2((uint32_t)n, (uint32_t)i);
+			} else {
+				if (t.later) O[j] = order_key(a.code[n], a.tstar[n], a);
+				if (t.minO[i] > O[j]) atomicMin(&t.minO[i], O[j]);
+			}
 		}
 		if (u == UNSET) {   // claimed a moment ago by another thread: resolved after the launch
 			const uint32_t k = atomicAdd(&op.counters[0], 1u);
@@ -467,6 +476,80 @@ __global__ void __launch_bounds__(DD_THREADS) k_insert_k64(DedupArgs a, TableDev
 		for (int j = 0; j < NPT; ++j) if (n0 + j < a.N) a.ref[n0 + j] = out[j];
 	}
 }
+// First touch of a node whose level was voxelized without first-touch tracking: the smallest root pair q of its tile whose
+// triangle passes testTriBox (reference operation order, tri_box_overlap) at every box on the node's path -- which is
+// exactly when the level-synchronous build holds a (triangle, node) pair for it.  One warp per node, 32 consecutive q per
+// trip.  A triangle that fails the three box-axis tests of the node's OWN box (the last box of the path; the same
+// subtractions and comparisons tri_box_overlap starts with) cannot pass, so it is dropped before the chain is walked.
+__device__ __forceinline__ uint32_t first_touch_query(const DedupArgs& a, const LeafQuery& lq, uint64_t cd, int lane) {
+	const int l = a.l;
+	const uint32_t tile = (uint32_t)(cd >> (3 * l));
+	const TileGeom tg = reinterpret_cast<const TileGeom*>(lq.tiles)[tile];
+	// the node's own box
+	double nx = tg.cx, ny = tg.cy, nz = tg.cz, nk = tg.rootSide * 0.25, kl = nk;
+	for (int d = l - 1; d >= 0; --d) {
+		const int dig = (int)((cd >> (3 * d)) & 7);
+		nx = __dadd_rn(nx, (dig & 4) ? nk : -nk);
+		ny = __dadd_rn(ny, (dig & 2) ? nk : -nk);
+		nz = __dadd_rn(nz, (dig & 1) ? nk : -nk);
+		kl = nk;
+		nk *= 0.5;
+	}
+	uint32_t found = UNSET;
+	for (uint64_t q0 = a.tileStart[tile]; q0 < lq.P && found == UNSET; q0 += 32) {
+		const uint64_t q = q0 + lane;
+		bool ok = q < lq.P;
+		if (ok) {
+			const float* tp = lq.tris + 9ull * lq.rootTri[q];
+			if (l > 0) {
+				const float x0 = tp[0], x1 = tp[3], x2 = tp[6], y0 = tp[1], y1 = tp[4], y2 = tp[7], z0 = tp[2], z1 = tp[5], z2 = tp[8];
+				// fl(t - c) is monotone in t: min / max may be taken on the float inputs
+				ok = !(__dsub_rn((double)fminf(x0, fminf(x1, x2)), nx) > kl || __dsub_rn((double)fmaxf(x0, fmaxf(x1, x2)), nx) < -kl) &&
+				     !(__dsub_rn((double)fminf(y0, fminf(y1, y2)), ny) > kl || __dsub_rn((double)fmaxf(y0, fmaxf(y1, y2)), ny) < -kl) &&
+				     !(__dsub_rn((double)fminf(z0, fminf(z1, z2)), nz) > kl || __dsub_rn((double)fmaxf(z0, fmaxf(z1, z2)), nz) < -kl);
+			}
+			if (ok) {
+				double cx = tg.cx, cy = tg.cy, cz = tg.cz, k = tg.rootSide * 0.25;
+				for (int d = l - 1; d >= 0 && ok; --d) {
+					const int dig = (int)((cd >> (3 * d)) & 7);
+					cx = __dadd_rn(cx, (dig & 4) ? k : -k);
+					cy = __dadd_rn(cy, (dig & 2) ? k : -k);
+					cz = __dadd_rn(cz, (dig & 1) ? k : -k);
+					ok = tri_box_overlap(cx, cy, cz, k, tp);
+					k *= 0.5;
+				}
+			}
+		}
+		const unsigned b = __ballot_sync(0xFFFFFFFFu, ok);
+		if (b) found = (uint32_t)(q0 + (__ffs(b) - 1));
+	}
+	return found;
+}
+__global__ void __launch_bounds__(DD_THREADS) k_k64_query(uint32_t cnt, const uint2* __restrict__ qlist, DedupArgs a, LeafQuery lq, unsigned long long* __restrict__ minO, uint32_t* __restrict__ flags) {
+	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (w >= cnt) return;
+	const uint2 e = qlist[w];
+	const uint64_t cd = a.code[e.x];
+	const uint32_t found = first_touch_query(a, lq, cd, lane);
+	if (lane) return;
+	if (found == UNSET) { flags[3] = 1; return; }   // cannot happen: the node exists, so some triangle of its tile reaches it
+	atomicMin(&minO[e.y], (unsigned long long)order_key(cd, found, a));
+}
+// (list overflow) the nodes of new entries collected by a pass over the refs: ref = uid >= countBefore, slot found by probing
+__global__ void __launch_bounds__(DD_THREADS) k_k64_collect(DedupArgs a, TableDev t, uint32_t cap, uint32_t* __restrict__ counter, uint2* __restrict__ qlist) {
+	const uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (n >= a.N) return;
+	const uint32_t r = a.ref[n];
+	if (r == NULLREF || r < t.countBefore) return;
+	uint64_t key;
+	build_key64_u8(a, n, key);
+	uint64_t i = mix64(key) & t.capMask;
+	while (t.tag[i] != key) i = (i + 1) & t.capMask;
+	const uint32_t k = atomicAdd(counter, 1u);
+	if (k < cap) qlist[k] = make_uint2((uint32_t)n, (uint32_t)i);
+}
+
 __global__ void __launch_bounds__(DD_THREADS) k_assign_list(uint32_t fresh, const uint32_t* __restrict__ newSlots, const unsigned long long* __restrict__ tag,
                                                              const unsigned long long* __restrict__ minO, const uint32_t* __restrict__ uid,
                                                              uint64_t* __restrict__ dMinO, uint64_t* __restrict__ dKey64) {
@@ -763,7 +846,10 @@ void dedup_leaf(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, u
 // KIND_K64 over u8 child masks in one pass over the nodes (k_insert_k64)
 static void dedup_k64_onepass(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, int npt, bool later) {
 	constexpr uint32_t LIST_CAP = 1u << 20;
+	const bool untracked = a.tstar == nullptr;
+	if (untracked && (!later || !a.query)) throw Error(SVB_EINVAL, "dedup: a level without first touches needs a later batch and the query data");
 	DevBuf<uint32_t> flags(pool, 4), counters(pool, 4), newSlots(pool, LIST_CAP), unres(pool, LIST_CAP);
+	DevBuf<uint2> qlist(pool, untracked ? LIST_CAP : 1);
 	uint32_t h[4], hc[4];
 	for (;;) {
 		if (T.cap > (1ull << 30)) throw Error(SVB_ERANGE, "4^3-level table beyond 2^30 slots");
@@ -772,8 +858,9 @@ static void dedup_k64_onepass(cudaStream_t s, Pool& pool, LevelTable& T, const D
 		TableDev t = dev_view(T, flags.p);
 		t.later = later ? 1 : 0;
 		OnePass op;
-		op.dCount = T.dCount.p; op.newSlots = newSlots.p; op.unres = unres.p; op.listCap = LIST_CAP; op.counters = counters.p;
-		if (npt >= 4) k_insert_k64<4><<<blocks_for((a.N + 3) / 4, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
+		op.dCount = T.dCount.p; op.newSlots = newSlots.p; op.unres = unres.p; op.listCap = LIST_CAP; op.counters = counters.p; op.qlist = qlist.p;
+		if (untracked) k_insert_k64<2, true><<<blocks_for((a.N + 1) / 2, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
+		else if (npt >= 4) k_insert_k64<4><<<blocks_for((a.N + 3) / 4, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
 		else if (npt == 2) k_insert_k64<2><<<blocks_for((a.N + 1) / 2, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
 		else k_insert_k64<1><<<blocks_for(a.N, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
 		SVB_KERNEL_CHECK();
@@ -790,14 +877,33 @@ static void dedup_k64_onepass(cudaStream_t s, Pool& pool, LevelTable& T, const D
 	const uint64_t fresh = h[2];
 	if (T.count + fresh >= 0x7FFFFFF0ull) throw Error(SVB_ERANGE, "more than 2^31 unique nodes in the 4^3 level");
 	ensure_dense(s, pool, T, T.count + fresh);
+	if (hc[0]) {   // (before the query pass below: k_k64_collect reads final refs)
+		if (hc[0] <= LIST_CAP) k_fix_list<<<blocks_for(hc[0], DD_THREADS), DD_THREADS, 0, s>>>(hc[0], unres.p, T.uid.p, a.ref);
+		else k_fix_all<<<blocks_for(a.N, DD_THREADS), DD_THREADS, 0, s>>>(a.N, T.uid.p, a.ref);
+		SVB_KERNEL_CHECK();
+	}
+	if (untracked && hc[1]) {   // first touches of the nodes of the new entries, straight from the triangles
+		uint32_t cnt = hc[1];
+		const uint2* list = qlist.p;
+		DevBuf<uint2> big;
+		if (cnt > LIST_CAP) {
+			big.reset(pool, cnt);
+			SVB_CUDA(cudaMemsetAsync(counters.p + 1, 0, 4, s));
+			TableDev t = dev_view(T, flags.p);
+			k_k64_collect<<<blocks_for(a.N, DD_THREADS), DD_THREADS, 0, s>>>(a, t, cnt, counters.p + 1, big.p);
+			SVB_KERNEL_CHECK();
+			list = big.p;
+		}
+		if (getenv("SVB_VX_STATS")) fprintf(stderr, "[vx-stats] 4^3 level without first touches: %u nodes of %u new entries queried directly\n", cnt, h[2]);
+		k_k64_query<<<blocks_for((uint64_t)cnt * 32, DD_THREADS), DD_THREADS, 0, s>>>(cnt, list, a, *a.query, (unsigned long long*)T.minO.p, flags.p);
+		SVB_KERNEL_CHECK();
+		SVB_CUDA(cudaMemcpyAsync(h, flags.p, 16, cudaMemcpyDeviceToHost, s));
+		SVB_CUDA(cudaStreamSynchronize(s));   // (also keeps `big` alive until the query has run)
+		if (h[3]) throw Error(SVB_ECUDA, "dedup: a node of the 4^3 level has no first touch (internal error)");
+	}
 	if (fresh) {
 		if (fresh <= LIST_CAP) k_assign_list<<<blocks_for(fresh, DD_THREADS), DD_THREADS, 0, s>>>((uint32_t)fresh, newSlots.p, (const unsigned long long*)T.tag.p, (const unsigned long long*)T.minO.p, T.uid.p, T.dMinO.p, T.dKey64.p);
 		else k_assign_scan<<<blocks_for(T.cap, DD_THREADS), DD_THREADS, 0, s>>>(T.cap, (uint32_t)T.count, (const unsigned long long*)T.tag.p, (const unsigned long long*)T.minO.p, T.uid.p, T.dMinO.p, T.dKey64.p);
-		SVB_KERNEL_CHECK();
-	}
-	if (hc[0]) {
-		if (hc[0] <= LIST_CAP) k_fix_list<<<blocks_for(hc[0], DD_THREADS), DD_THREADS, 0, s>>>(hc[0], unres.p, T.uid.p, a.ref);
-		else k_fix_all<<<blocks_for(a.N, DD_THREADS), DD_THREADS, 0, s>>>(a.N, T.uid.p, a.ref);
 		SVB_KERNEL_CHECK();
 	}
 	T.count += fresh;
@@ -810,6 +916,14 @@ bool leaf_tstar_needed(const LevelTable& T, uint32_t seqLo) {
 	// ... and only once a batch has come and gone without bringing a new voxel mask (a batch that does meet one
 	// has to be voxelized twice)
 	return !(T.kind == KIND_LEAF && !T.wide && T.seenAny && seqLo > T.maxSeq && T.lastAdded == 0);
+}
+
+bool k64_tstar_optional(const LevelTable& T, uint32_t seqLo) {
+	const char* e = getenv("SVB_DEDUP_LAZY");
+	const char* f = getenv("SVB_K64_ONEPASS");
+	if ((e && e[0] == '0') || (f && atoi(f) <= 0)) return false;
+	// the single-pass insert must be usable for whatever the batch brings (see dedup_level_t): keep well inside its limits
+	return T.kind == KIND_K64 && T.seenAny && seqLo > T.maxSeq && T.count > 0 && T.cap <= (1ull << 27) && T.count < (1ull << 29);
 }
 
 bool dedup_leaf_known(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, const LeafQuery& lq, uint64_t* d_voxels) {
@@ -870,6 +984,7 @@ static void dedup_level_t(cudaStream_t s, Pool& pool, LevelTable& T, const Dedup
 		// marked slots must stay distinguishable from NULLREF and from uids
 		if (npt > 0 && T.cap <= (1ull << 28) && T.count + a.N / 8 < (1ull << 30)) { dedup_k64_onepass(s, pool, T, a, npt, later); return; }
 	}
+	if (!a.tstar) throw Error(SVB_EINVAL, "dedup: a level without first touches can only go through the single-pass 4^3 insert");
 	const char* mk = getenv("SVB_INNER_MARKED");   // 0: every node goes through the winner and convert passes
 	const bool markedWanted = !k64 && !(mk && mk[0] == '0');
 	bool marked = false;

@@ -6,6 +6,7 @@ namespace svb {
 
 // One level of nodes to be reduced.  Children of node n are refs[childBase[n] + r], r = rank of the
 // child among the set bits of mask[n] (ascending child index).
+struct LeafQuery;
 struct DedupArgs {
 	uint64_t N = 0;
 	const uint64_t* code = nullptr;     // (tile_local << 3l) | path
@@ -24,6 +25,9 @@ struct DedupArgs {
 	// already exists: such entries are frozen and their nodes need neither code nor tstar (svb_dedup.cu).
 	uint32_t seqLo = 0, seqHi = 0;
 	bool seqMonotone = false;           // tileSeq ascends with the tile-local index: order keys of the batch compare like (tstar, path')
+	// tstar == nullptr on the 4^3 level of a later batch: its first touches were not tracked; the nodes of NEW entries get
+	// theirs from a direct query of the triangles (svb_dedup.cu::k_k64_query), which needs:
+	const LeafQuery* query = nullptr;
 };
 
 void table_init(cudaStream_t s, Pool& pool, LevelTable& T, int kind);
@@ -46,6 +50,10 @@ struct LeafQuery {
 	const void* tiles = nullptr;        // TileGeom per tile of the batch
 };
 bool dedup_leaf_known(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, const LeafQuery& lq, uint64_t* d_voxels);
+// May the voxelizer skip the first touches of the 4^3 level for a batch whose smallest tile_seq is seqLo?  Yes when the
+// batch comes after everything the level's table has seen (its existing entries are frozen) and the single-pass insert
+// is in use: only nodes of NEW entries need a first touch then, and dedup_level queries those directly (DedupArgs::query).
+bool k64_tstar_optional(const LevelTable& T, uint32_t seqLo);
 
 // KIND_K64 / KIND_INNER.  Throws Error(SVB_ECOLLISION) if the exact verify pass finds two different
 // keys behind one 64-bit tag.

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_emit_pipe(uint64_t P, cons
 	auto load_node = [&](PairIn& f) {
 		NodeIn g = {0u, 0u, 0u};
 		if (SLOW && skipFlat && pair_is_fast(f.fl)) f.m = 0;
-		if (f.m) { g.nm = mask[f.n]; g.base = childBase[f.n]; if (STAR) g.ts = tstar[f.n]; }
+		if (f.m) { g.nm = mask[f.n]; g.base = childBase[f.n]; if (STAR && ctstar) g.ts = tstar[f.n]; }   // (the parents' first touches only serve the children's)
 		return g;
 	};
 	PairIn f0 = load_pair(0), f1 = load_pair(1);
@@ -631,9 +631,67 @@ void make_root_pairs(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T
 	}
 }
 
+// ---- root pairs of ALL sub-octrees of a build, binned once
+namespace {
+// tileOf is ascending: begin[x] = first q of tile x (an empty tile gets the begin of its successor); begin[nSel] = P
+__global__ void __launch_bounds__(VX_THREADS) k_tile_begin(uint64_t P, uint32_t nSel, const uint32_t* __restrict__ tileOf, uint32_t* __restrict__ begin) {
+	const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= P) return;
+	const int64_t t = tileOf[p], prev = p ? (int64_t)tileOf[p - 1] : -1;
+	for (int64_t x = prev + 1; x <= t; ++x) begin[x] = (uint32_t)p;
+	if (p == P - 1) for (int64_t x = t + 1; x <= (int64_t)nSel; ++x) begin[x] = (uint32_t)P;
+}
+__global__ void __launch_bounds__(VX_THREADS) k_batch_roots(uint64_t Pb, uint32_t a, const uint32_t* __restrict__ tileOf, uint32_t* __restrict__ ptri, uint32_t* __restrict__ pnode) {
+	const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= Pb) return;
+	ptri[p] = (uint32_t)p;          // a pair is identified by the index of its root pair inside the batch
+	pnode[p] = tileOf[p] - a;
+}
+__global__ void __launch_bounds__(VX_THREADS) k_batch_tile_start(uint32_t nt, uint32_t base, const uint32_t* __restrict__ begin, uint32_t* __restrict__ tileStart) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < nt) tileStart[i] = begin[i] - base;
+}
+}  // namespace
+
+void make_root_pairs_all(cudaStream_t s, Pool& pool, const float* d_tris, uint64_t T, const TileGridHost& grid, const int* d_gridTile, const int* d_selPos,
+                         uint32_t nSel, RootPairsAll& R, const int cellLo[3], const int cellHi[3]) {
+	R = RootPairsAll();
+	DevBuf<uint32_t> ptri, tileStart;
+	make_root_pairs(s, pool, d_tris, T, grid, d_gridTile, d_selPos, 0, nSel, ptri, R.tileOf, R.rootTri, tileStart, R.P, cellLo, cellHi);   // throws BatchTooBig beyond 2^32 pairs
+	ptri.release();
+	tileStart.release();
+	R.nSel = nSel;
+	R.tileBegin.reset(pool, (uint64_t)nSel + 1);
+	R.tileBegin.zero();
+	if (R.P) {
+		k_tile_begin<<<blocks_for(R.P, VX_THREADS), VX_THREADS, 0, s>>>(R.P, nSel, R.tileOf.p, R.tileBegin.p);
+		SVB_KERNEL_CHECK();
+	}
+	R.hTileBegin.resize((size_t)nSel + 1);
+	SVB_CUDA(cudaMemcpyAsync(R.hTileBegin.data(), R.tileBegin.p, ((uint64_t)nSel + 1) * 4, cudaMemcpyDeviceToHost, s));
+	SVB_CUDA(cudaStreamSynchronize(s));
+	R.valid = true;
+}
+
+void batch_root_pairs(cudaStream_t s, Pool& pool, const RootPairsAll& R, uint32_t a, uint32_t nt, DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode,
+                      const uint32_t*& rootTri, DevBuf<uint32_t>& tileStart, uint64_t& P) {
+	const uint32_t base = R.hTileBegin[a];
+	P = R.hTileBegin[a + nt] - base;
+	ptri.reset(pool, P ? P : 1);
+	pnode.reset(pool, P ? P : 1);
+	tileStart.reset(pool, nt ? nt : 1);
+	rootTri = R.rootTri.p + base;
+	if (P) {
+		k_batch_roots<<<blocks_for(P, VX_THREADS), VX_THREADS, 0, s>>>(P, a, R.tileOf.p + base, ptri.p, pnode.p);
+		SVB_KERNEL_CHECK();
+	}
+	k_batch_tile_start<<<blocks_for(nt, VX_THREADS), VX_THREADS, 0, s>>>(nt, base, R.tileBegin.p + a, tileStart.p);
+	SVB_KERNEL_CHECK();
+}
+
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
                     DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, const uint32_t* rootTri, const uint32_t* tileStart, uint64_t P,
-                    uint64_t budget_bytes, uint64_t nodeCap, std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre, bool allFlat, bool leafTstar, ProfHook* prof) {
+                    uint64_t budget_bytes, uint64_t nodeCap, std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre, bool allFlat, int untracked, ProfHook* prof) {
 	if (const char* e = getenv("SVB_CENTRE")) directCentre = directCentre && e[0] != 'c';   // SVB_CENTRE=chain: always replay the chain
 	lv.clear();
 	lv.resize(Lt);
@@ -744,7 +802,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		C.code.reset(pool, Nn);
 		// first touches of the leaf nodes only matter for voxel masks the dedup table does not know yet: a later batch
 		// goes without them (leafTstar == false; the caller re-runs the batch in the rare case that it does meet one)
-		const bool trackKids = leafTstar || (l + 1 < Lt - 1);
+		const bool trackKids = (l + 1 < Lt - untracked);   // untracked = 1: the leaf level, 2: the 4^3 level above it as well
 		if (trackKids) {
 			C.tstar.reset(pool, Nn);
 			C.tstar.fill_ff();

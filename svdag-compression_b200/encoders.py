@@ -9,8 +9,25 @@ import numpy as np
 KINDS = {"svdag": 0, "ussvdag": 1, "ssvdag": 2, "esvdag": 2}
 
 
+def encode_view(octree, kind: str) -> np.ndarray:
+    """The file image as a uint8 view of the context's pinned buffer (svb_encode_view: written on the GPU, one D2H copy of
+    the finished image, no further host copy).  Valid until the octree changes or another kind is encoded."""
+    L = octree._L
+    L.svb_encode_view.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    ptr, size = C.c_void_p(), C.c_uint64()
+    octree._check(L.svb_encode_view(octree._h, KINDS[kind], C.byref(ptr), C.byref(size)))
+    if size.value == 0:
+        return np.zeros(0, np.uint8)
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(int(size.value),))
+
+
 def encode(octree, kind: str) -> bytes:
     """octree: capi.GeomOctree in the state the format needs (DAG for svdag/esvdag, SDAG for ussvdag/ssvdag)."""
+    return encode_view(octree, kind).tobytes()
+
+
+def encode_copy(octree, kind: str) -> bytes:
+    """The two-call form of svb_encode (size query, then copy into a caller-owned buffer)."""
     L = octree._L
     L.svb_encode.restype = C.c_int64
     L.svb_encode.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
@@ -23,6 +40,21 @@ def encode(octree, kind: str) -> bytes:
     if n2 != n:
         octree._check(int(n2) if n2 < 0 else -1)
     return buf.tobytes()
+
+
+def ssvdag_order_from_refs(refs_per_level):
+    """svb_ssvdag_order_from_refs (host only): list of uint32 arrays (one per level, level 0 first) -> list of orders."""
+    from .capi import lib
+    L = lib()
+    L.svb_ssvdag_order_from_refs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    start = np.zeros(len(refs_per_level) + 1, np.uint32)
+    start[1:] = np.cumsum([len(r) for r in refs_per_level])
+    refs = np.ascontiguousarray(np.concatenate(refs_per_level), dtype=np.uint32)
+    order = np.zeros(len(refs), np.uint32)
+    rc = L.svb_ssvdag_order_from_refs(refs.ctypes.data, start.ctypes.data, len(refs_per_level), order.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"svb_ssvdag_order_from_refs failed: {rc}")
+    return [order[start[l]:start[l + 1]].copy() for l in range(len(refs_per_level))]
 
 
 def encode_levels(levels, bboxF, root_side: float, n_nodes: int, state: int, kind: str) -> bytes:

@@ -71,3 +71,28 @@ def build_sharded(octree, levels: int, step: int, bbox, group=None, device=None)
     del keep
     st["bytesExchanged"] = exchanged + world * nt * 4
     return st
+
+
+def set_triangles_sharded(octree, host_tris, ntris: int, group=None, device=None):
+    """Collective upload of the triangle soup: every rank copies only its 1/world slice of the (pinned) host array over
+    its own PCIe link, an all-gather over NVLink completes the soup in every rank's HBM, and the octree borrows the
+    device buffer (svb_set_triangles_device).  host_tris: 1-D float32 torch tensor of ntris*9 values, identical on all ranks."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    nfloat = int(ntris) * 9
+    chunk = (-(-nfloat // world) + 3) // 4 * 4                  # floats per rank, 16-byte granular
+    with octree_stream(octree, device):
+        buf = torch.empty(world * chunk + 16, dtype=torch.float32, device=device)   # a few floats of slack, as svb_set_triangles keeps
+        full = buf[:world * chunk]
+        lo, hi = rank * chunk, min((rank + 1) * chunk, nfloat)
+        mine = full[rank * chunk:(rank + 1) * chunk]
+        if hi > lo:
+            mine[:hi - lo].copy_(host_tris[lo:hi], non_blocking=True)
+        dist.all_gather_into_tensor(full, mine, group=group)     # in place: rank r's slice is already where it belongs
+        torch.cuda.current_stream(device).synchronize()
+    octree._dev_tris = buf                                       # keep the buffer alive while the octree borrows it
+    octree.set_triangles_device(full.data_ptr(), int(ntris))
+    return int((hi - lo) * 4 if hi > lo else 0)

@@ -94,3 +94,35 @@ def test_threaded_encoder_loops_on_a_larger_dag(pkg, orc, meshgen):
         got[k] = pkg.encoders.encode_levels(lv, bboxF, rs, o.stat("nNodes"), 3, k)
     for k in want:
         assert got[k] == want[k], k
+
+
+def _std_sort_order(orc, refs):
+    """Plain std::sort with the reference's comparator (oracle/svdag_oracle.cpp::orc_sort_by_refs)."""
+    import ctypes as C
+    L = orc.lib()
+    L.orc_sort_by_refs.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
+    refs = np.ascontiguousarray(refs, dtype=np.uint32)
+    out = np.zeros(len(refs), np.uint32)
+    L.orc_sort_by_refs(len(refs), refs.ctypes.data, out.ctypes.data)
+    return out
+
+
+def test_parallel_ref_sort_reproduces_std_sort_tie_order(pkg, orc):
+    """The SSVDAG node order is the outcome of the reference's UNSTABLE std::sort (encoded_ssvdag.cpp:273-275): the product
+    runs libstdc++'s partition / introsort routines with the independent halves as parallel tasks
+    (csrc/host/encoders.cpp::sort_by_refs) and must land on the same permutation, ties included, for every input --
+    sizes around the task threshold (16384) and far above it, heavy ties, sorted / reversed / constant / organ-pipe inputs."""
+    rng = np.random.default_rng(5)
+    cases = []
+    for n in (0, 1, 2, 15, 16, 17, 100, 4097, 16384, 16385, 50_000, 300_000, 1_000_000):
+        cases.append(rng.integers(1, 4, n))                       # almost everything ties (the usual reference-count picture)
+        cases.append(rng.zipf(1.6, n).clip(1, 10**6))             # a few hot nodes, a long tail of 1s
+    n = 200_000
+    cases += [np.arange(n), np.arange(n)[::-1], np.full(n, 7), np.minimum(np.arange(n), np.arange(n)[::-1]),
+              rng.integers(0, 2**31, n), np.repeat(np.arange(n // 100)[::-1], 100)]
+    levels = [np.zeros(1, np.uint32)] + [np.asarray(c, dtype=np.uint32) for c in cases]
+    got = pkg.encoders.ssvdag_order_from_refs(levels)
+    assert list(got[0]) == [0]
+    for k, (refs, g) in enumerate(zip(levels[1:], got[1:])):
+        want = _std_sort_order(orc, refs)
+        assert np.array_equal(g, want), f"case {k} (n={len(refs)}): permutation differs from std::sort's"
