@@ -396,6 +396,13 @@ def main():
             except Exception as e:  # the baseline is reported, never required
                 line["cpu_baseline"] = {"value": None, "unit": "Gvoxel/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
         print(json.dumps(line))
+    # orderly teardown: the context (and its CUDA stream, which torch's allocator knows as the allocation stream of the exchange
+    # buffers) goes before the process group and the interpreter
+    torch.cuda.synchronize()
+    if hasattr(oct_, "_dev_tris"):
+        del oct_._dev_tris
+    torch.cuda.empty_cache()
+    oct_.close()
     if world > 1:
         dist.destroy_process_group()
     if rank == 0 and parity["ok"] is False:

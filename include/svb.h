@@ -26,7 +26,9 @@ extern "C" {
 #define SVB_ECUDA      -2   /* CUDA runtime error (no device, launch failure, ...) */
 #define SVB_ENOMEM     -3   /* device memory exhausted even after splitting the tile batch */
 #define SVB_ERANGE     -4   /* configuration exceeds an id/order-key bit budget (see DESIGN.md "order key") */
-#define SVB_ECOLLISION -5   /* 64-bit node-key hash collision detected by the exact verify pass */
+#define SVB_ECOLLISION -5   /* 64-bit node-key hash collisions detected by the exact verify pass under five seeds in a row (svb_build, svb_to_sdag
+                               and svb_cross_merge re-run the stage with another seed by themselves), or one detected in the multi-GPU level
+                               merge (svb_shard_finish): there every rank sees it, and the caller repeats the build after svb_set_merge_seed */
 #define SVB_ENODEV     -6   /* no usable CUDA device (there is no CPU fallback) */
 
 /* encoded file kinds (svb_encode / svb_raycast_depth): what EncodedSVDAG / EncodedUSSVDAG / EncodedSSVDAG save */
@@ -54,6 +56,7 @@ typedef struct svb_stats {
 	double   msVoxelize, msDedup, msFinalize, msSdag, msCrossMerge, msTotal; /* CUDA-event times of the last call */
 	uint64_t nKernelLaunches;   /* CUDA kernels launched by the last svb_build / svb_to_sdag / svb_cross_merge call */
 	uint64_t nExactTests;       /* (triangle, child) tests the interval filter left to the reference-order predicate */
+	uint64_t nHashRetries;      /* stages of this context re-run under another hash seed after a detected 64-bit tag collision (normally 0) */
 } svb_stats;
 
 typedef struct svb_ctx svb_ctx;
@@ -114,6 +117,10 @@ int svb_shard_import_level(svb_ctx* ctx, uint32_t level, const void* d_all, cons
 int svb_shard_export_roots(svb_ctx* ctx, void* d_out);
 int svb_shard_import_roots(svb_ctx* ctx, const void* d_all);
 int svb_shard_finish(svb_ctx* ctx, const uint64_t totals[5], svb_stats* out);
+/* Seed of the hashed keys of the level merge (default 0).  Must be the same on every rank.  After svb_shard_finish has
+ * returned SVB_ECOLLISION -- on every rank alike, since all of them import identical records -- set seed + 1 everywhere
+ * and run the protocol again (svdag-compression_b200/sharded.py and csrc/host/sharded_build.cpp do). */
+int svb_set_merge_seed(svb_ctx* ctx, uint64_t seed);
 
 /* GeomOctree::toSDAG(false,false) (geom_octree.cpp:551-697).  DAG -> SDAG. */
 int svb_to_sdag(svb_ctx* ctx, svb_stats* out);

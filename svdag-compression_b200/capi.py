@@ -24,7 +24,7 @@ class Stats(C.Structure):
                                            "nNodesLastLevDAG", "nCrossLevelMerged", "nNodes", "nTiles", "nBatches", "nPairsTotal")]
     _fields_ += [("rootSide", C.c_double), ("bboxF", C.c_float * 6)]
     _fields_ += [(n, C.c_double) for n in ("msVoxelize", "msDedup", "msFinalize", "msSdag", "msCrossMerge", "msTotal")]
-    _fields_ += [("nKernelLaunches", C.c_uint64), ("nExactTests", C.c_uint64)]
+    _fields_ += [("nKernelLaunches", C.c_uint64), ("nExactTests", C.c_uint64), ("nHashRetries", C.c_uint64)]
 
     def as_dict(self):
         d = {}
@@ -64,6 +64,7 @@ def lib() -> C.CDLL:
         L.svb_stream.restype = vp
         L.svb_stream.argtypes = [vp]
         L.svb_synchronize.argtypes = [vp]
+        L.svb_set_merge_seed.argtypes = [vp, u64]
         L.svb_set_triangles.argtypes = [vp, vp, u64]
         L.svb_set_triangles_device.argtypes = [vp, vp, u64]
         L.svb_build.argtypes = [vp, u32, u32, vp, vp, C.POINTER(Stats)]
@@ -153,6 +154,9 @@ class GeomOctree:
     def stream_ptr(self) -> int:
         """cudaStream_t of this context (the shard_export_* / shard_import_* calls are stream-ordered on it)."""
         return int(self._L.svb_stream(self._h) or 0)
+
+    def set_merge_seed(self, seed: int):
+        self._check(self._L.svb_set_merge_seed(self._h, int(seed)))
 
     def synchronize(self):
         self._check(self._L.svb_synchronize(self._h))

@@ -459,7 +459,7 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 	B.l2g.resize(L);
 	B.merged.assign(L, false);
 	if (world > 1) { B.mergeStatus.reset(c->pool, 8ull * L); B.mergeStatus.zero(); }
-	for (uint32_t g = 1; g < L; ++g) table_init(s, c->pool, B.tables[g], kind_of(g, L));
+	for (uint32_t g = 1; g < L; ++g) table_init(s, c->pool, B.tables[g], kind_of(g, L), c->hashSeed);
 	B.dVoxels.reset(c->pool, 1); B.dVoxels.zero();
 	B.dExact.reset(c->pool, 1); B.dExact.zero();
 	B.rootKey.reset(c->pool, 8); B.rootKey.fill_ff();
@@ -760,6 +760,25 @@ int guarded(svb_ctx* c, F&& f) {
 	}
 }
 
+// A 64-bit tag collision found by an exact verify pass is not an error of the input: the stage runs again under the next
+// seed (every tag changes), at most a few times.  f must leave no trace of a failed attempt behind (build_local starts from
+// scratch; cross_merge_device replaces the octree only at its very end).
+template <class F>
+void with_hash_retries(svb_ctx* c, F&& f) {
+	for (int attempt = 0;; ++attempt) {
+		try {
+			f();
+			return;
+		} catch (const Error& e) {
+			if (e.code != SVB_ECOLLISION || attempt >= 4) throw;
+			for (auto& p : c->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+			c->pending.clear();
+			c->hashSeed++;
+			c->nHashRetries++;
+		}
+	}
+}
+
 }  // namespace
 
 // ===================================================================================== C ABI
@@ -822,8 +841,11 @@ int svb_set_triangles_device(svb_ctx* c, const float* xyz9_dev, uint64_t ntris) 
 int svb_build(svb_ctx* c, uint32_t levels, uint32_t step, const double bmin[3], const double bmax[3], svb_stats* out) {
 	int rc = guarded(c, [&] {
 		if (!bmin || !bmax) throw Error(SVB_EINVAL, "null bbox");
-		build_local(c, levels, step, bmin, bmax, 0, 1);
-		build_finish(c, nullptr);
+		with_hash_retries(c, [&] {
+			build_local(c, levels, step, bmin, bmax, 0, 1);
+			build_finish(c, nullptr);
+		});
+		c->stats.nHashRetries = c->nHashRetries;
 	});
 	if (rc != SVB_OK && c) { c->out.clear(); c->state = SVB_S_EMPTY; c->build.reset(); }
 	if (rc == SVB_OK && out) *out = c->stats;
@@ -834,7 +856,7 @@ int svb_build(svb_ctx* c, uint32_t levels, uint32_t step, const double bmin[3], 
 int svb_shard_build(svb_ctx* c, uint32_t levels, uint32_t step, const double bmin[3], const double bmax[3], uint32_t rank, uint32_t world) {
 	int rc = guarded(c, [&] {
 		if (!bmin || !bmax) throw Error(SVB_EINVAL, "null bbox");
-		build_local(c, levels, step, bmin, bmax, rank, world);
+		with_hash_retries(c, [&] { build_local(c, levels, step, bmin, bmax, rank, world); });   // (rank-local tables: the seed is a private matter)
 		SVB_CUDA(cudaStreamSynchronize(c->stream));
 	});
 	if (rc != SVB_OK && c) { c->out.clear(); c->state = SVB_S_EMPTY; c->build.reset(); }
@@ -883,7 +905,7 @@ int svb_shard_import_level(svb_ctx* c, uint32_t level, const void* d_all, const 
 		if (!c->build || level < c->build->s1 || level >= c->build->L || !counts) throw Error(SVB_EINVAL, "bad level");
 		svb_build_state& B = *c->build;
 		if (B.world < 2) throw Error(SVB_EINVAL, "not a sharded build");
-		merge_import(c->stream, c->pool, B.tables[level], d_all, counts, B.world, strideBytes, B.rank, B.l2g[level], B.mergeStatus.p + 8ull * level);
+		merge_import(c->stream, c->pool, B.tables[level], d_all, counts, B.world, strideBytes, B.rank, B.l2g[level], B.mergeStatus.p + 8ull * level, c->mergeSeed);
 		B.merged[level] = true;
 		if (level == B.s1) {   // sub-octree roots now have global uids
 			if (B.tables[level].kind != KIND_LEAF && !B.tiles.empty()) {
@@ -919,6 +941,7 @@ int svb_shard_finish(svb_ctx* c, const uint64_t totals[5], svb_stats* out) {
 	int rc = guarded(c, [&] {
 		if (!c->build) throw Error(SVB_EINVAL, "no build in progress");
 		build_finish(c, totals);
+		c->stats.nHashRetries = c->nHashRetries;
 	});
 	if (rc != SVB_OK && c) { c->out.clear(); c->state = SVB_S_EMPTY; c->build.reset(); }
 	if (rc == SVB_OK && out) *out = c->stats;
@@ -934,6 +957,7 @@ int svb_to_sdag(svb_ctx* c, svb_stats* out) {
 		uint64_t nn = to_sdag_device(c);
 		c->stats.msSdag = tm.stop();
 		c->stats.nKernelLaunches = g_launches.load() - launches0;
+		c->stats.nHashRetries = c->nHashRetries;
 		c->stats.nNodesSDAG = nn;   // geom_octree.cpp:578,664,683: root not counted
 		c->stats.nNodes = nn;
 		c->state = SVB_S_SDAG;
@@ -949,16 +973,23 @@ int svb_cross_merge(svb_ctx* c, svb_stats* out) {
 		c->lastImageKind = -1;
 		const uint64_t launches0 = g_launches.load();
 		StageTimer tm(c->stream);
-		uint64_t nn = 0;
-		uint64_t removed = cross_merge_device(c, &nn);
+		uint64_t nn = 0, removed = 0;
+		with_hash_retries(c, [&] { removed = cross_merge_device(c, &nn); });
 		c->stats.msCrossMerge = tm.stop();
 		c->stats.nCrossLevelMerged = removed;   // ext.cpp:1517
 		c->stats.nNodesDAG = nn;                // ext.cpp:1448
 		c->stats.nNodes = nn;
 		c->stats.nKernelLaunches = g_launches.load() - launches0;
+		c->stats.nHashRetries = c->nHashRetries;
 	});
 	if (rc == SVB_OK && out) *out = c->stats;
 	return rc;
+}
+
+int svb_set_merge_seed(svb_ctx* c, uint64_t seed) {
+	if (!c) return SVB_EINVAL;
+	c->mergeSeed = seed;
+	return SVB_OK;
 }
 
 int svb_state(const svb_ctx* c) { return c ? c->state : SVB_S_EMPTY; }

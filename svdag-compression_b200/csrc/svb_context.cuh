@@ -45,6 +45,10 @@ struct svb_ctx {
 	std::vector<PendingProf> pending;
 	std::vector<svb_prof_rec> prof;
 	uint64_t batchBudget = 0;
+	// seeds of the hashed node keys: a detected 64-bit tag collision re-runs the stage with the next seed (svb_api.cu).
+	// mergeSeed seeds the tables of the multi-GPU level merge and must be the same on every rank.
+	uint64_t hashSeed = 0, mergeSeed = 0;
+	uint64_t nHashRetries = 0;
 	// last file image produced by svb_encode (a size query followed by the real call must not encode twice);
 	// dropped whenever the octree changes
 	PinnedBuf image, staging;

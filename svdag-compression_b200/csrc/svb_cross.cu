@@ -42,20 +42,20 @@ __device__ __forceinline__ void make_key(const Views& V, int l, uint64_t i, int 
 		k.w[1 + c] = (d == 0 || ch == NULLNODE) ? NULLREF : V.lv[l + 1].tidPrev[ch];
 	}
 }
-__device__ __forceinline__ uint64_t key_tag(const CKey& k) {
-	uint64_t h = 0x9E3779B97F4A7C15ull ^ k.w[0];
+__device__ __forceinline__ uint64_t key_tag(const CKey& k, const HashSeed& hs) {
+	uint64_t h = hs.init ^ k.w[0];
 #pragma unroll
 	for (int c = 1; c < 9; c += 2) h = mix64(h ^ (((uint64_t)k.w[c + 1] << 32) | k.w[c])) + 0x9E3779B97F4A7C15ull * c;
-	return h ? h : 1ull;
+	return finish_tag(h, hs);
 }
 
 __global__ void __launch_bounds__(CM_THREADS) k_cm_insert(Views V, int l, int d, unsigned long long* __restrict__ tag, unsigned long long* __restrict__ minLoc,
-                                                           uint64_t capMask, uint32_t* __restrict__ flags) {
+                                                           uint64_t capMask, uint32_t* __restrict__ flags, HashSeed hs) {
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= V.lv[l].n) return;
 	CKey k;
 	make_key(V, l, i, d, k);
-	uint64_t h = key_tag(k);
+	uint64_t h = key_tag(k, hs);
 	uint64_t idx = mix64(h) & capMask;
 	bool found = false;
 	for (int probe = 0; probe < 8192; ++probe) {
@@ -182,7 +182,7 @@ uint64_t cross_merge_device(svb_ctx* c, uint64_t* nNodesOut) {
 		}
 		for (int l = 1; l <= lstar; ++l) {
 			if (!c->out[l].n) continue;
-			k_cm_insert<<<blocks_for(c->out[l].n, CM_THREADS), CM_THREADS, 0, s>>>(V, l, d, (unsigned long long*)tag.p, (unsigned long long*)minLoc.p, cap - 1, flags.p);
+			k_cm_insert<<<blocks_for(c->out[l].n, CM_THREADS), CM_THREADS, 0, s>>>(V, l, d, (unsigned long long*)tag.p, (unsigned long long*)minLoc.p, cap - 1, flags.p, make_hash_seed(c->hashSeed));
 			SVB_KERNEL_CHECK();
 		}
 		for (int l = 1; l <= lstar; ++l) {

@@ -113,11 +113,11 @@ __device__ __forceinline__ bool build_key64_u8(const DedupArgs& a, uint64_t n, u
 	return key64 != 0;
 }
 
-__device__ __forceinline__ uint64_t tag_of_key8(const uint32_t k[8]) {
-	uint64_t h = 0x9E3779B97F4A7C15ull;
+__device__ __forceinline__ uint64_t tag_of_key8(const uint32_t k[8], const HashSeed& hs) {
+	uint64_t h = hs.init;
 #pragma unroll
 	for (int c = 0; c < 8; c += 2) h = mix64(h ^ (((uint64_t)k[c + 1] << 32) | k[c])) + 0x9E3779B97F4A7C15ull * (c + 1);
-	return h ? h : 1ull;
+	return finish_tag(h, hs);
 }
 
 // ------------------------------------------------------------------ KIND_LEAF
@@ -326,6 +326,7 @@ struct TableDev {
 	uint64_t capMask;
 	uint64_t countBefore, maxLoad;
 	uint32_t* flags;   // [0] overflow, [1] collision, [2] new entries
+	HashSeed hs;
 	int later;         // every node of this launch has a larger order key than whatever the existing entries hold (DedupArgs::seqLo)
 };
 
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(DD_THREADS) k_insert(DedupArgs a, TableDev t, 
 	uint64_t k64;
 	const bool any = (PERM && CHMODE == CH_MASK_U8) ? build_key64_u8(a, n, k64) : build_key<CHMODE>(a, n, k8, k64);
 	if (!any) { a.ref[n] = NULLREF; return; }
-	uint64_t tag = (CHMODE == CH_UID_U32) ? tag_of_key8(k8) : k64;
+	uint64_t tag = (CHMODE == CH_UID_U32) ? tag_of_key8(k8, t.hs) : k64;
 	uint64_t slot;
 	if (!table_find_or_claim(t, tag, slot)) { a.ref[n] = NULLREF; return; }
 	if (MARKED) {
@@ -651,7 +652,7 @@ __global__ void __launch_bounds__(DD_THREADS) k_rebuild(uint64_t count, const ui
 		uint32_t k8[8];
 #pragma unroll
 		for (int c = 0; c < 8; ++c) k8[c] = dKey8[u * 8 + c];
-		tag = tag_of_key8(k8);
+		tag = tag_of_key8(k8, t.hs);
 	}
 	uint64_t idx = mix64(tag) & t.capMask;
 	for (;;) {
@@ -763,6 +764,7 @@ TableDev dev_view(LevelTable& T, uint32_t* flags) {
 	t.countBefore = T.count;
 	t.maxLoad = T.cap - T.cap / 4;   // 75 %
 	t.flags = flags;
+	t.hs = T.hs;
 	t.later = 0;
 	return t;
 }
@@ -795,8 +797,17 @@ void ensure_dense(cudaStream_t s, Pool& pool, LevelTable& T, uint64_t need) {
 
 }  // namespace
 
-void table_init(cudaStream_t s, Pool& pool, LevelTable& T, int kind) {
+HashSeed make_hash_seed(uint64_t seed) {
+	HashSeed hs;
+	hs.init = 0x9E3779B97F4A7C15ull ^ (seed * 0xD1B54A32D192ED03ull);
+	if (seed == 0)
+		if (const char* e = getenv("SVB_TEST_WEAK_HASH")) { const int b = atoi(e); if (b > 0 && b < 64) hs.mask = (1ull << b) - 1; }
+	return hs;
+}
+
+void table_init(cudaStream_t s, Pool& pool, LevelTable& T, int kind, uint64_t seed) {
 	T.kind = kind;
+	T.hs = make_hash_seed(seed);
 	T.count = 0;
 	T.denseCap = 0;
 	T.unique = 0;
@@ -1079,7 +1090,7 @@ __global__ void __launch_bounds__(DD_THREADS) k_import_insert(uint64_t total, ui
 	if (i >= counts[r]) { slotOf[e] = NULLREF; return; }
 	uint64_t tag, O;
 	if (K64) { const RecK64* p = (const RecK64*)(all + r * strideBytes) + i; tag = p->key; O = p->minO; }
-	else { const RecInner* p = (const RecInner*)(all + r * strideBytes) + i; tag = tag_of_key8(p->key); O = p->minO; }
+	else { const RecInner* p = (const RecInner*)(all + r * strideBytes) + i; tag = tag_of_key8(p->key, t.hs); O = p->minO; }
 	uint64_t slot;
 	if (!table_find_or_claim(t, tag, slot)) { slotOf[e] = NULLREF; return; }
 	if (t.minO[slot] > O) atomicMin(&t.minO[slot], (unsigned long long)O);
@@ -1187,7 +1198,7 @@ __global__ void k_import_status(const uint32_t* __restrict__ flags, const uint64
 // unique nodes); the unique count, overflow / collision flags and the winner check land in d_status (5 x u32, device) and
 // are read back ONCE for all levels by merge_resolve() when the build finishes.
 void merge_import(cudaStream_t s, Pool& pool, LevelTable& T, const void* d_all, const uint64_t* counts, uint32_t world, uint64_t strideBytes,
-                  uint32_t myRank, DevBuf<uint32_t>& l2g, uint32_t* d_status) {
+                  uint32_t myRank, DevBuf<uint32_t>& l2g, uint32_t* d_status, uint64_t mergeSeed) {
 	if (T.kind == KIND_LEAF) {
 		k_min256<<<1, 256, 0, s>>>(world, (const unsigned long long*)d_all, strideBytes / 8, (unsigned long long*)T.minO.p, T.wide ? 1 : 0);
 		SVB_KERNEL_CHECK();
@@ -1202,6 +1213,7 @@ void merge_import(cudaStream_t s, Pool& pool, LevelTable& T, const void* d_all, 
 	// fresh global table
 	LevelTable G;
 	G.kind = T.kind;
+	G.hs = make_hash_seed(mergeSeed);   // the same on every rank: all of them must reach the same verdict
 	G.dCount.reset(pool, 1);
 	G.dCount.zero();
 	alloc_slots(s, pool, G, next_pow2(2 * sum + 1024));

@@ -30,7 +30,7 @@ struct DedupArgs {
 	const LeafQuery* query = nullptr;
 };
 
-void table_init(cudaStream_t s, Pool& pool, LevelTable& T, int kind);
+void table_init(cudaStream_t s, Pool& pool, LevelTable& T, int kind, uint64_t seed = 0);
 
 // KIND_LEAF: nodes are bare 8-bit voxel masks. Accumulates popcounts into *d_voxels.
 void dedup_leaf(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, uint64_t* d_voxels);
@@ -65,7 +65,7 @@ uint32_t merge_rec_bytes(int kind);
 uint64_t merge_count(const LevelTable& T);
 void merge_export(cudaStream_t s, Pool& pool, LevelTable& T, const uint32_t* l2gChild, void* d_out);
 void merge_import(cudaStream_t s, Pool& pool, LevelTable& T, const void* d_all, const uint64_t* counts, uint32_t world, uint64_t strideBytes,
-                  uint32_t myRank, DevBuf<uint32_t>& l2g, uint32_t* d_status);
+                  uint32_t myRank, DevBuf<uint32_t>& l2g, uint32_t* d_status, uint64_t mergeSeed = 0);
 void merge_resolve(LevelTable& T, const uint32_t status[5]);
 
 // Level 0 is never reduced (geom_octree.cpp:483): just resolve the root's children.

@@ -48,6 +48,20 @@ static const uint64_t EMPTY_TAG = 0ull;
 static const uint64_t MAX_ORDER = 0xFFFFFFFFFFFFFFFFull;
 
 enum LevelKind { KIND_LEAF = 0, KIND_K64 = 1, KIND_INNER = 2 };
+
+// Hashed node keys (inner dedup levels, SDAG class keys, cross-level subtree ids) are 64-bit tags that an exact pass verifies;
+// a detected collision makes the stage run again with another seed (svb_api.cu), so it is never a user-visible failure.
+// init: start value of the hash chain (a function of the seed); mask: all ones -- except under the test hook
+// SVB_TEST_WEAK_HASH=<bits>, which truncates the tags of the FIRST attempt (seed 0) to force the retry path.
+struct HashSeed {
+	uint64_t init = 0x9E3779B97F4A7C15ull;
+	uint64_t mask = ~0ull;
+};
+HashSeed make_hash_seed(uint64_t seed);   // svb_dedup.cu
+__host__ __device__ inline uint64_t finish_tag(uint64_t h, const HashSeed& hs) {
+	h &= hs.mask;
+	return h ? h : 1ull;
+}
 // how a dedup kernel reads the refs of the level below
 enum ChildMode { CH_MASK_U8 = 0, CH_SLOT_U32 = 1, CH_UID_U32 = 2, CH_MASK_U32 = 3 };
 
@@ -217,6 +231,7 @@ struct LevelTable {
 	// finalize
 	DevBuf<uint32_t> rank;    // uid -> final id (LEAF: mask value -> final id)
 	uint64_t unique = 0;
+	HashSeed hs;              // KIND_INNER: seed of the 64-bit tags
 };
 
 // Per-launch timing records from inside the stage drivers (svb_api.cu implements it on top of the context's profile list;

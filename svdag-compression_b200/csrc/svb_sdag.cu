@@ -85,11 +85,11 @@ __device__ __forceinline__ bool key_lt(const SKey& a, const SKey& b) {
 	}
 	return false;
 }
-__device__ __forceinline__ uint64_t key_hash(const SKey& k) {
-	uint64_t h = 0x9E3779B97F4A7C15ull;
+__device__ __forceinline__ uint64_t key_hash(const SKey& k, const HashSeed& hs) {
+	uint64_t h = hs.init;
 #pragma unroll
 	for (int i = 0; i < 12; i += 2) h = mix64(h ^ (((uint64_t)k.w[i + 1] << 32) | k.w[i])) + 0x9E3779B97F4A7C15ull * (i + 1);
-	return h ? h : 1ull;
+	return finish_tag(h, hs);
 }
 
 struct LevelIn {
@@ -102,7 +102,7 @@ struct LevelIn {
 
 // pass 1: invariant bits, class key (as argmin variant), hash-table insert with atomicMin(index)
 __global__ void __launch_bounds__(SD_THREADS) k_sdag_class(LevelIn L, uint8_t* __restrict__ inv, uint8_t* __restrict__ clsVar, uint32_t* __restrict__ slotOf,
-                                                            unsigned long long* __restrict__ tag, uint32_t* __restrict__ minIdx, uint64_t capMask, uint32_t* __restrict__ flags) {
+                                                            unsigned long long* __restrict__ tag, uint32_t* __restrict__ minIdx, uint64_t capMask, uint32_t* __restrict__ flags, HashSeed hs) {
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= L.n) return;
 	NodeIn n;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(SD_THREADS) k_sdag_class(LevelIn L, uint8_t* _
 		if (key_lt(k, best)) { best = k; bs = s; }
 	}
 	clsVar[i] = (uint8_t)bs;
-	uint64_t h = key_hash(best);
+	uint64_t h = key_hash(best, hs);
 	uint64_t idx = mix64(h) & capMask;
 	bool found = false;
 	for (int probe = 0; probe < 8192; ++probe) {
@@ -222,25 +222,31 @@ uint64_t to_sdag_device(svb_ctx* c) {
 		while (cap < 2 * n) cap <<= 1;
 		DevBuf<uint64_t> tag(pool, cap);
 		DevBuf<uint32_t> minIdx(pool, cap);
-		tag.zero();
-		minIdx.fill_ff();
-		flags.zero();
 		DevBuf<uint8_t> inv(pool, n), clsVar(pool, n), flag(pool, n);
 		DevBuf<uint32_t> slotOf(pool, n), rep(pool, n), isRep(pool, n), newId(pool, n);
 		unsigned nb = blocks_for(n, SD_THREADS);
-		k_sdag_class<<<nb, SD_THREADS, 0, s>>>(in, inv.p, clsVar.p, slotOf.p, (unsigned long long*)tag.p, minIdx.p, cap - 1, flags.p);
-		SVB_KERNEL_CHECK();
-		k_sdag_resolve<<<nb, SD_THREADS, 0, s>>>(in, clsVar.p, slotOf.p, minIdx.p, rep.p, flag.p, isRep.p, flags.p);
-		SVB_KERNEL_CHECK();
-		scan_u32(s, pool, isRep.p, n, newId.p, tot.p);
 		uint64_t hU = 0;
-		uint32_t hf[4];
-		SVB_CUDA(cudaMemcpyAsync(&hU, tot.p, 8, cudaMemcpyDeviceToHost, s));
-		SVB_CUDA(cudaMemcpyAsync(hf, flags.p, 16, cudaMemcpyDeviceToHost, s));
-		SVB_CUDA(cudaStreamSynchronize(s));
-		if (hf[0]) throw Error(SVB_ECUDA, "toSDAG: hash table overflow");
-		if (hf[1]) throw Error(SVB_ECOLLISION, "toSDAG: 64-bit class-key hash collision");
-		if (hf[2]) throw Error(SVB_ECOLLISION, "toSDAG: a node matches no mirror image of its class representative");
+		// A level is only replaced once its pass came out clean, so a detected tag collision (two class keys behind one 64-bit
+		// tag: the exact resolve pass sees a node that matches no mirror image of "its" representative) simply repeats the
+		// level's pass with another seed.
+		for (int attempt = 0;; ++attempt) {
+			tag.zero();
+			minIdx.fill_ff();
+			flags.zero();
+			k_sdag_class<<<nb, SD_THREADS, 0, s>>>(in, inv.p, clsVar.p, slotOf.p, (unsigned long long*)tag.p, minIdx.p, cap - 1, flags.p, make_hash_seed(c->hashSeed + (uint64_t)attempt));
+			SVB_KERNEL_CHECK();
+			k_sdag_resolve<<<nb, SD_THREADS, 0, s>>>(in, clsVar.p, slotOf.p, minIdx.p, rep.p, flag.p, isRep.p, flags.p);
+			SVB_KERNEL_CHECK();
+			scan_u32(s, pool, isRep.p, n, newId.p, tot.p);
+			uint32_t hf[4];
+			SVB_CUDA(cudaMemcpyAsync(&hU, tot.p, 8, cudaMemcpyDeviceToHost, s));
+			SVB_CUDA(cudaMemcpyAsync(hf, flags.p, 16, cudaMemcpyDeviceToHost, s));
+			SVB_CUDA(cudaStreamSynchronize(s));
+			if (hf[0]) throw Error(SVB_ECUDA, "toSDAG: hash table overflow");
+			if (!hf[1] && !hf[2]) break;
+			c->nHashRetries++;
+			if (attempt >= 4) throw Error(SVB_ECOLLISION, "toSDAG: 64-bit class-key hash collisions under five different seeds");
+		}
 		OutLevel Y;
 		Y.n = hU;
 		Y.mask.reset(pool, hU); Y.child.reset(pool, hU * 8); Y.mirror.reset(pool, hU * 3); Y.inv.reset(pool, hU);
