@@ -354,8 +354,11 @@ __device__ __forceinline__ bool table_find_or_claim(const TableDev& t, uint64_t 
 // MARKED (inner levels): a node that finds an entry from an earlier launch is finished on the spot -- exact key check
 // against the entry's stored key, final uid as its ref -- and only the nodes of entries created by this launch leave a
 // marked slot for k_winner / k_convert, which are skipped altogether when the launch created nothing.
+// (MARKED) mlist / mcount: the nodes left with a marked ref are also listed (up to mcap), so that k_winner / k_convert visit a
+// few thousand nodes instead of streaming the whole level again for the handful of entries a later batch creates.
 template <int CHMODE, bool PERM = false, bool MARKED = false>
-__global__ void __launch_bounds__(DD_THREADS) k_insert(DedupArgs a, TableDev t, const uint32_t* __restrict__ dKey8) {
+__global__ void __launch_bounds__(DD_THREADS) k_insert(DedupArgs a, TableDev t, const uint32_t* __restrict__ dKey8,
+                                                        uint32_t* __restrict__ mlist = nullptr, uint32_t* __restrict__ mcount = nullptr, uint32_t mcap = 0) {
 	uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (n >= a.N) return;
 	uint32_t k8[8];
@@ -368,13 +371,15 @@ __global__ void __launch_bounds__(DD_THREADS) k_insert(DedupArgs a, TableDev t, 
 	if (MARKED) {
 		const uint32_t u = t.uid[slot];   // (a slot claimed in this launch still has uid UNSET)
 		if (u < t.countBefore) {
-			bool same = true;
-#pragma unroll
-			for (int c = 0; c < 8; ++c) same &= (dKey8[(uint64_t)u * 8 + c] == k8[c]);
+			const uint4 s0 = reinterpret_cast<const uint4*>(dKey8)[(uint64_t)u * 2], s1 = reinterpret_cast<const uint4*>(dKey8)[(uint64_t)u * 2 + 1];   // the stored key: two 128-bit loads
+			const bool same = s0.x == k8[0] && s0.y == k8[1] && s0.z == k8[2] && s0.w == k8[3] && s1.x == k8[4] && s1.y == k8[5] && s1.z == k8[6] && s1.w == k8[7];
 			if (!same) t.flags[1] = 1;
 			a.ref[n] = u;
 			if (t.later) return;   // frozen entry
-		} else a.ref[n] = REF_MARK | (uint32_t)slot;
+		} else {
+			a.ref[n] = REF_MARK | (uint32_t)slot;
+			if (mcount) { const uint32_t k = atomicAdd(mcount, 1u); if (k < mcap) mlist[k] = (uint32_t)n; }
+		}
 	} else {
 		a.ref[n] = (uint32_t)slot;
 		if (t.later && t.uid[slot] < t.countBefore) return;   // frozen entry
@@ -429,6 +434,10 @@ __global__ void __launch_bounds__(DD_THREADS) k_insert_k64(DedupArgs a, TableDev
 #pragma unroll
 	for (int j = 0; j < NPT; ++j) {
 		if (!live[j]) continue;
+		// Neighbours in Morton order are neighbours in space: the interior of a wall is a run of identical 4^3 blocks.  A
+		// node with the key of its predecessor takes the predecessor's result -- valid whenever that result is the final uid
+		// of a frozen entry (nothing else is owed for such a node: no order key, no list entry).
+		if (j > 0 && t.later && live[j - 1] && key[j] == key[j - 1] && out[j - 1] < t.countBefore) { out[j] = out[j - 1]; continue; }
 		const uint64_t n = n0 + j, tag = key[j];
 		uint64_t i = idx[j];
 		unsigned long long c = cur[j];
@@ -600,8 +609,10 @@ __global__ void __launch_bounds__(DD_THREADS) k_assign_k64(uint64_t cap, const u
 // INNER: the node that holds the minimum order key of a new slot publishes the full key
 template <int CHMODE, bool MARKED = false>
 __global__ void __launch_bounds__(DD_THREADS) k_winner(DedupArgs a, TableDev t, uint32_t* __restrict__ dCount,
-                                                        uint64_t* __restrict__ dMinO, uint32_t* __restrict__ dKey8) {
+                                                        uint64_t* __restrict__ dMinO, uint32_t* __restrict__ dKey8,
+                                                        const uint32_t* __restrict__ list = nullptr, uint64_t count = 0) {
 	uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (list) { if (n >= count) return; n = list[n]; }
 	if (n >= a.N) return;
 	uint32_t slot = a.ref[n];
 	if (slot == NULLREF) return;
@@ -621,8 +632,10 @@ __global__ void __launch_bounds__(DD_THREADS) k_winner(DedupArgs a, TableDev t, 
 
 // slot -> uid for every node (+ exact key check for hashed keys)
 template <int CHMODE, bool VERIFY, bool MARKED = false>
-__global__ void __launch_bounds__(DD_THREADS) k_convert(DedupArgs a, TableDev t, const uint32_t* __restrict__ dKey8) {
+__global__ void __launch_bounds__(DD_THREADS) k_convert(DedupArgs a, TableDev t, const uint32_t* __restrict__ dKey8,
+                                                         const uint32_t* __restrict__ list = nullptr, uint64_t count = 0) {
 	uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (list) { if (n >= count) return; n = list[n]; }
 	if (n >= a.N) return;
 	uint32_t slot = a.ref[n];
 	if (slot == NULLREF) return;
@@ -870,7 +883,8 @@ static void dedup_k64_onepass(cudaStream_t s, Pool& pool, LevelTable& T, const D
 		t.later = later ? 1 : 0;
 		OnePass op;
 		op.dCount = T.dCount.p; op.newSlots = newSlots.p; op.unres = unres.p; op.listCap = LIST_CAP; op.counters = counters.p; op.qlist = qlist.p;
-		if (untracked) k_insert_k64<2, true><<<blocks_for((a.N + 1) / 2, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
+		if (untracked && npt >= 4) k_insert_k64<4, true><<<blocks_for((a.N + 3) / 4, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
+		else if (untracked) k_insert_k64<2, true><<<blocks_for((a.N + 1) / 2, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
 		else if (npt >= 4) k_insert_k64<4><<<blocks_for((a.N + 3) / 4, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
 		else if (npt == 2) k_insert_k64<2><<<blocks_for((a.N + 1) / 2, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
 		else k_insert_k64<1><<<blocks_for(a.N, DD_THREADS), DD_THREADS, 0, s>>>(a, t, op);
@@ -978,7 +992,9 @@ static void dedup_level_t(cudaStream_t s, Pool& pool, LevelTable& T, const Dedup
 	if (a.N == 0) return;
 	const bool k64 = (CHMODE != CH_UID_U32);
 	if ((T.kind == KIND_K64) != k64) throw Error(SVB_EINVAL, "dedup_level: table kind does not match child mode");
-	DevBuf<uint32_t> flags(pool, 4);
+	constexpr uint32_t MLIST_CAP = 1u << 20;
+	DevBuf<uint32_t> flags(pool, 4);   // [3]: nodes left with a marked ref (MARKED)
+	DevBuf<uint32_t> mlist;
 	unsigned nb = blocks_for(a.N, DD_THREADS);
 	uint32_t h[4];
 	// size the slot array for this level: at least 2x the entries it may end up holding if ~1/8 of the
@@ -1004,7 +1020,8 @@ static void dedup_level_t(cudaStream_t s, Pool& pool, LevelTable& T, const Dedup
 		TableDev t = dev_view(T, flags.p);
 		t.later = later ? 1 : 0;
 		marked = markedWanted && T.cap <= (1ull << 30) && T.count + a.N < (1ull << 31);
-		if (marked) k_insert<CHMODE, false, CHMODE == CH_UID_U32><<<nb, DD_THREADS, 0, s>>>(a, t, T.dKey8.p);
+		if (marked && !mlist.p) mlist.reset(pool, MLIST_CAP);
+		if (marked) k_insert<CHMODE, false, CHMODE == CH_UID_U32><<<nb, DD_THREADS, 0, s>>>(a, t, T.dKey8.p, mlist.p, flags.p + 3, MLIST_CAP);
 		else if (permKey) k_insert<CHMODE, CHMODE == CH_MASK_U8><<<nb, DD_THREADS, 0, s>>>(a, t, nullptr);
 		else k_insert<CHMODE><<<nb, DD_THREADS, 0, s>>>(a, t, nullptr);
 		SVB_KERNEL_CHECK();
@@ -1025,10 +1042,13 @@ static void dedup_level_t(cudaStream_t s, Pool& pool, LevelTable& T, const Dedup
 		k_convert<CHMODE, false><<<nb, DD_THREADS, 0, s>>>(a, t, nullptr);
 		SVB_KERNEL_CHECK();
 	} else if (marked) {
-		if (fresh) {   // only the nodes of the entries this launch created are still open
-			k_winner<CHMODE, true><<<nb, DD_THREADS, 0, s>>>(a, t, T.dCount.p, T.dMinO.p, T.dKey8.p);
+		if (fresh) {   // only the nodes of the entries this launch created are still open: through their list when it holds them all
+			const uint32_t nm = h[3];
+			const uint32_t* list = nm <= MLIST_CAP ? mlist.p : nullptr;
+			const unsigned nbl = list ? blocks_for(nm, DD_THREADS) : nb;
+			k_winner<CHMODE, true><<<nbl, DD_THREADS, 0, s>>>(a, t, T.dCount.p, T.dMinO.p, T.dKey8.p, list, nm);
 			SVB_KERNEL_CHECK();
-			k_convert<CHMODE, true, true><<<nb, DD_THREADS, 0, s>>>(a, t, T.dKey8.p);
+			k_convert<CHMODE, true, true><<<nbl, DD_THREADS, 0, s>>>(a, t, T.dKey8.p, list, nm);
 			SVB_KERNEL_CHECK();
 			SVB_CUDA(cudaMemcpyAsync(h, flags.p, 16, cudaMemcpyDeviceToHost, s));
 			SVB_CUDA(cudaStreamSynchronize(s));

@@ -260,10 +260,12 @@ void scan_popc8(cudaStream_t s, Pool& pool, const uint8_t* bytes, uint64_t n, ui
 // Tile-granular scans (tiles of scan_tile_items() consecutive items): only the exclusive offset of every tile is
 // produced; the consumer kernels (k_children / k_emit in svb_voxelize.cu) rebuild the per-item offsets inside the CTA.
 uint64_t scan_tile_items();
-void scan_tiles_popc8(cudaStream_t s, Pool& pool, const uint8_t* bytes, uint64_t n, DevBuf<uint64_t>& tileOffs, uint64_t* d_total);
+// rel (optional): tile-relative exclusive offsets at a granularity of 8 items (one u32 per 8 items; the pair variant packs
+// A in the low and B in the high half), so that a consumer can place its output warp by warp.
+void scan_tiles_popc8(cudaStream_t s, Pool& pool, const uint8_t* bytes, uint64_t n, DevBuf<uint64_t>& tileOffs, uint64_t* d_total, DevBuf<uint32_t>* rel = nullptr);
 // A = popcount(hit) of every pair, B = the same restricted to pairs whose flags put their children into the flat stream
 void scan_tiles_pairs(cudaStream_t s, Pool& pool, const uint8_t* hit, const uint16_t* flags, uint64_t n,
-                      DevBuf<uint64_t>& tileOffsA, DevBuf<uint64_t>& tileOffsB, uint64_t* d_totalA, uint64_t* d_totalB);
+                      DevBuf<uint64_t>& tileOffsA, DevBuf<uint64_t>& tileOffsB, uint64_t* d_totalA, uint64_t* d_totalB, DevBuf<uint32_t>* rel = nullptr);
 // exclusive scan of uint32 values (in place allowed), total to *d_total
 void scan_u32(cudaStream_t s, Pool& pool, const uint32_t* in, uint64_t n, uint32_t* out, uint64_t* d_total);
 // stable LSD radix sort of (key u64, val u32) pairs on the low `bits` bits of the key.

@@ -72,8 +72,10 @@ __device__ inline uint32_t block_excl_scan(uint32_t x, uint32_t* total) {
 	return r;
 }
 
+// rel (optional): the exclusive prefix of every thread's 8 items inside its tile, i.e. tile-relative offsets at a granularity of
+// 8 items -- what lets the consumer of the offsets (k_emit_warp, svb_voxelize.cu) work warp by warp without a CTA-wide scan
 template <class In>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(In in, uint64_t n, uint32_t* blockSums) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(In in, uint64_t n, uint32_t* blockSums, uint32_t* __restrict__ rel = nullptr) {
 	uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
 	uint32_t v[SCAN_ITEMS];
 	in.load(base, n, v);
@@ -81,7 +83,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(In in, uint64_t n,
 #pragma unroll
 	for (int i = 0; i < SCAN_ITEMS; ++i) s += v[i];
 	uint32_t tot;
-	block_excl_scan(s, &tot);
+	const uint32_t ex = block_excl_scan(s, &tot);
+	if (rel) rel[(uint64_t)blockIdx.x * SCAN_THREADS + threadIdx.x] = ex;
 	if (threadIdx.x == 0) blockSums[blockIdx.x] = tot;
 }
 
@@ -181,7 +184,7 @@ static void launch_scan_sums(cudaStream_t s, const uint32_t* sums, uint64_t nb, 
 // pair streams: per tile of SCAN_TILE pairs, the number of child pairs (popcount of the hit masks) and the number of
 // those whose flags put them into the flat stream (pair_is_fast, svb_classify.cuh), in one pass
 __global__ void __launch_bounds__(SCAN_THREADS) k_pair_reduce(const uint8_t* __restrict__ hit, const uint16_t* __restrict__ fl, uint64_t n,
-                                                              uint32_t* __restrict__ sumsA, uint32_t* __restrict__ sumsB) {
+                                                              uint32_t* __restrict__ sumsA, uint32_t* __restrict__ sumsB, uint32_t* __restrict__ rel) {
 	uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
 	uint32_t a = 0, b = 0;
 	if (base + SCAN_ITEMS <= n) {
@@ -207,7 +210,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_pair_reduce(const uint8_t* __r
 	}
 	uint32_t packed = a | (b << 16);   // a, b <= 8 * SCAN_ITEMS per thread, <= 8 * SCAN_TILE = 16384 per tile: fits 16 bits each
 	uint32_t tot;
-	block_excl_scan(packed, &tot);
+	const uint32_t ex = block_excl_scan(packed, &tot);   // (an exclusive prefix stays below 16384 in either half: no carry between them)
+	if (rel) rel[(uint64_t)blockIdx.x * SCAN_THREADS + threadIdx.x] = ex;
 	if (threadIdx.x == 0) { sumsA[blockIdx.x] = tot & 0xFFFF; sumsB[blockIdx.x] = tot >> 16; }
 }
 
@@ -305,25 +309,27 @@ void scan_popc8(cudaStream_t s, Pool& pool, const uint8_t* bytes, uint64_t n, ui
 }
 uint64_t scan_tile_items() { return SCAN_TILE; }
 
-void scan_tiles_popc8(cudaStream_t s, Pool& pool, const uint8_t* bytes, uint64_t n, DevBuf<uint64_t>& tileOffs, uint64_t* d_total) {
+void scan_tiles_popc8(cudaStream_t s, Pool& pool, const uint8_t* bytes, uint64_t n, DevBuf<uint64_t>& tileOffs, uint64_t* d_total, DevBuf<uint32_t>* rel) {
 	uint64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
 	tileOffs.reset(pool, nb ? nb : 1);
+	if (rel) rel->reset(pool, nb ? nb * SCAN_THREADS : 1);
 	if (n == 0) { SVB_CUDA(cudaMemsetAsync(d_total, 0, 8, s)); return; }
 	DevBuf<uint32_t> sums(pool, nb);
-	k_scan_reduce<Popc8In><<<(unsigned)nb, SCAN_THREADS, 0, s>>>(Popc8In{bytes}, n, sums.p);
+	k_scan_reduce<Popc8In><<<(unsigned)nb, SCAN_THREADS, 0, s>>>(Popc8In{bytes}, n, sums.p, rel ? rel->p : nullptr);
 	SVB_KERNEL_CHECK();
 	launch_scan_sums(s, sums.p, nb, tileOffs.p, d_total);
 	SVB_KERNEL_CHECK();
 }
 
 void scan_tiles_pairs(cudaStream_t s, Pool& pool, const uint8_t* hit, const uint16_t* flags, uint64_t n,
-                      DevBuf<uint64_t>& tileOffsA, DevBuf<uint64_t>& tileOffsB, uint64_t* d_totalA, uint64_t* d_totalB) {
+                      DevBuf<uint64_t>& tileOffsA, DevBuf<uint64_t>& tileOffsB, uint64_t* d_totalA, uint64_t* d_totalB, DevBuf<uint32_t>* rel) {
 	uint64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
 	tileOffsA.reset(pool, nb ? nb : 1);
 	tileOffsB.reset(pool, nb ? nb : 1);
+	if (rel) rel->reset(pool, nb ? nb * SCAN_THREADS : 1);
 	if (n == 0) { SVB_CUDA(cudaMemsetAsync(d_totalA, 0, 8, s)); SVB_CUDA(cudaMemsetAsync(d_totalB, 0, 8, s)); return; }
 	DevBuf<uint32_t> sumsA(pool, nb), sumsB(pool, nb);
-	k_pair_reduce<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(hit, flags, n, sumsA.p, sumsB.p);
+	k_pair_reduce<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(hit, flags, n, sumsA.p, sumsB.p, rel ? rel->p : nullptr);
 	SVB_KERNEL_CHECK();
 	launch_scan_sums(s, sumsA.p, nb, tileOffsA.p, d_totalA);
 	SVB_KERNEL_CHECK();

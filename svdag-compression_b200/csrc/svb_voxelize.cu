@@ -470,6 +470,111 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_emit_pipe(uint64_t P, cons
 	}
 }
 
+// Warp-granular emit (default since round 2; SVB_EMIT_WARP=0 selects k_emit_pipe).  The scans now deliver tile-relative
+// offsets for every 8 pairs (rel, svb_prims.cu), so a warp knows where the children of its 32 pairs go without any CTA-wide
+// scan: k_emit_pipe spent 4 CTA barriers per 256 pairs (two in the scan, two around the staging buffer), and with every
+// warp of the CTA waiting on the same barriers nothing hid the gathers behind them (ncu: 4.8 - 5.6 warps per issue cycle
+// stalled on the barrier, 7.4 - 9.0 on the scoreboard).  Here each warp walks its 8 groups of 32 pairs on its own: warp
+// scan of the child counts (shuffles), children staged in the warp's private slice of shared memory, written out as
+// contiguous runs, __syncwarp only.  Pair fields are fetched two groups ahead, node fields one ahead, as before.
+// Output, first-touch handling (star stores / atomics with the copy-out) and the two-stream routing are unchanged.
+template <bool SLOW, int MINB, bool STAR>
+__global__ void __launch_bounds__(VX_THREADS, MINB) k_emit_warp(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
+                                                                 const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit,
+                                                                 const uint64_t* __restrict__ offsA, const uint64_t* __restrict__ offsB, const uint32_t* __restrict__ rel,
+                                                                 uint64_t fastBase, uint64_t slowBase,
+                                                                 const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase, const uint32_t* __restrict__ tstar,
+                                                                 uint32_t* __restrict__ otri, uint32_t* __restrict__ onode, uint16_t* __restrict__ oflags, uint32_t* __restrict__ ctstar,
+                                                                 int skipFlat, int precheck) {
+	constexpr int WARPS = VX_THREADS / 32, GROUPS = VX_TILE / VX_THREADS;   // 8 warps x 8 groups of 32 pairs = one 2048-pair tile per CTA
+	__shared__ uint32_t s_tri[WARPS][256];
+	__shared__ uint32_t s_node[WARPS][256];
+	__shared__ uint16_t s_fl[WARPS][256];
+	__shared__ uint8_t s_star[STAR ? WARPS : 1][STAR ? 256 : 1];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const uint64_t tile = blockIdx.x;
+	const uint64_t pw = tile * VX_TILE + (uint64_t)w * (32 * GROUPS);   // first pair of this warp
+	if (pw >= P) return;
+	const uint64_t tA = offsA[tile], tB = SLOW ? offsB[tile] : 0;
+	struct PairIn { unsigned m; uint32_t t, n, fl; };
+	struct NodeIn { unsigned nm; uint32_t base, ts; };
+	auto load_pair = [&](int g) {
+		PairIn r = {0u, 0u, 0u, 0u};
+		const uint64_t p = pw + (uint64_t)g * 32 + lane;
+		if (g < GROUPS && p < P) { r.m = hit[p]; r.fl = pflags[p]; r.t = ptri[p]; r.n = pnode[p]; }
+		return r;
+	};
+	auto load_node = [&](PairIn& f) {
+		NodeIn q = {0u, 0u, 0u};
+		if (SLOW && skipFlat && pair_is_fast(f.fl)) f.m = 0;   // decided in place by k_flat_leaves
+		if (f.m) { q.nm = mask[f.n]; q.base = childBase[f.n]; if (STAR && ctstar) q.ts = tstar[f.n]; }
+		return q;
+	};
+	PairIn f0 = load_pair(0), f1 = load_pair(1);
+	NodeIn g0 = load_node(f0);
+	// the 8 relative offsets of this warp's groups, fetched once (lane g holds group g's)
+	uint32_t relMine = 0;
+	if (lane < GROUPS && pw + (uint64_t)lane * 32 < P) relMine = rel[(pw >> 3) + 4 * lane];
+	uint32_t* const wt = s_tri[w];
+	uint32_t* const wn = s_node[w];
+	uint16_t* const wf = s_fl[w];
+	uint8_t* const ws = s_star[STAR ? w : 0];
+	for (int g = 0; g < GROUPS; ++g) {
+		const uint64_t pg = pw + (uint64_t)g * 32;
+		if (pg >= P) break;
+		const PairIn f2 = load_pair(g + 2);
+		const NodeIn g1 = load_node(f1);
+		const uint32_t r = __shfl_sync(0xFFFFFFFFu, relMine, g);   // exclusive offsets (tile-relative) of the group's first pair: low half all children, high half the flat ones
+		const unsigned m = f0.m;
+		const bool flatKids = SLOW ? pair_is_fast(f0.fl) : true;
+		const uint32_t cnt = __popc(m);
+		const uint32_t inc = warp_incl_scan_u32(flatKids ? cnt : (cnt << 16), lane);   // low half: flat children, high half: the others (<= 256 each)
+		const uint32_t tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+		const uint32_t ex = inc - (flatKids ? cnt : (cnt << 16));
+		const uint32_t nFlat = tot & 0xFFFF, nSlow = tot >> 16;
+		uint64_t runF, runS = 0;
+		if (SLOW) { const uint64_t a = tA + (r & 0xFFFF), b = tB + (r >> 16); runF = fastBase + b; runS = slowBase + (a - b); }
+		else runF = fastBase + tA + r;
+		if (m) {
+			uint32_t o = flatKids ? (ex & 0xFFFF) : nFlat + (ex >> 16);
+			const uint32_t t = f0.t;
+			unsigned mm = m;
+			while (mm) {
+				const int c = __ffs(mm) - 1;
+				mm &= mm - 1;
+				wt[o] = t;
+				wn[o] = g0.base + __popc(g0.nm & ((1u << c) - 1));
+				wf[o] = (uint16_t)f0.fl;
+				if (STAR) ws[o] = (uint8_t)(g0.ts == t);
+				++o;
+			}
+		}
+		__syncwarp();
+		for (uint32_t i = lane; i < nFlat; i += 32) {
+			const uint32_t t = wt[i], child = wn[i];
+			otri[runF + i] = t;
+			onode[runF + i] = child;
+			oflags[runF + i] = wf[i];
+			if (!ctstar) continue;   // first touches of the children are not tracked
+			if (STAR && ws[i]) ctstar[child] = t;
+			else if (!precheck || ctstar[child] > t) atomicMin(&ctstar[child], t);
+		}
+		if (SLOW) {
+			for (uint32_t i = lane; i < nSlow; i += 32) {
+				const uint32_t t = wt[nFlat + i], child = wn[nFlat + i];
+				otri[runS + i] = t;
+				onode[runS + i] = child;
+				oflags[runS + i] = wf[nFlat + i];
+				if (!ctstar) continue;
+				if (STAR && ws[nFlat + i]) ctstar[child] = t;
+				else if (!precheck || ctstar[child] > t) atomicMin(&ctstar[child], t);
+			}
+		}
+		__syncwarp();
+		f0 = f1; g0 = g1; f1 = f2;
+	}
+}
+
 // nodes the next level will hold, per tile (weights for cutting an oversized batch)
 __global__ void __launch_bounds__(VX_THREADS) k_tile_weights(uint64_t N, const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask, int l, uint32_t* __restrict__ w) {
 	uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -711,6 +816,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 	// k_emit variant: 0 = one chunk at a time, else software-pipelined (read per batch, not cached: A/B inside one process)
 	const bool childrenPipe = [] { const char* e = getenv("SVB_CHILDREN_PIPE"); return !(e && e[0] == '0'); }();
 	const int emitPipe = [] { const char* e = getenv("SVB_EMIT_PIPE"); return e ? atoi(e) : 8; }();
+	const bool emitWarp = emitPipe != 0 && [] { const char* e = getenv("SVB_EMIT_WARP"); return !(e && e[0] == '0'); }();   // warp-granular emit (k_emit_warp)
 	const bool starStore = [] { const char* e = getenv("SVB_STAR_STORE"); return !(e && e[0] == '0'); }();   // first touch of the children of a node's own first-touch pair by plain store
 	const bool emitRedOut = [] { const char* e = getenv("SVB_EMIT_REDOUT"); return !(e && e[0] == '0'); }();   // the remaining atomics leave with the copy-out too (measured: 667 vs 672 ms voxelize with the star stores; without them the staging loop is the better place)
 	static const int occFlat = [] { const char* e = getenv("SVB_VX_OCC_FLAT"); return e ? atoi(e) : 6; }();   // 6 or 8 CTAs/SM (40 / 32 registers, spills) beat 5 on B200: the kernel is latency bound
@@ -760,9 +866,10 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		if (last) break;
 		// children of the nodes, child pairs of the pairs: tile-granular scans, one read-back
 		DevBuf<uint64_t> nodeOffs, offF, offFB, offS, offSF;
+		DevBuf<uint32_t> relF, relS;   // tile-relative offsets per 8 pairs (k_emit_warp)
 		scan_tiles_popc8(s, pool, L.mask.p, L.n, nodeOffs, tot.p + 0);
-		scan_tiles_popc8(s, pool, hit.p, F, offF, tot.p + 1);
-		scan_tiles_pairs(s, pool, hit.p + Fa, pflags.p + Fa, S, offS, offSF, tot.p + 2, tot.p + 3);
+		scan_tiles_popc8(s, pool, hit.p, F, offF, tot.p + 1, emitWarp ? &relF : nullptr);
+		scan_tiles_pairs(s, pool, hit.p + Fa, pflags.p + Fa, S, offS, offSF, tot.p + 2, tot.p + 3, emitWarp ? &relS : nullptr);
 		uint64_t h[4];
 		SVB_CUDA(cudaMemcpyAsync(h, tot.p, 32, cudaMemcpyDeviceToHost, s));
 		SVB_CUDA(cudaStreamSynchronize(s));
@@ -837,6 +944,8 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 			// (+ 4 B first touch when tracked) per child pair
 			const int pidE = prof ? prof->begin("emit", (uint32_t)l, F) : -1;
 			if (emitPipe == 0) k_emit<false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F());
+			else if (emitWarp && starStore) k_emit_warp<false, 8, true><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, relF.p, 0, 0, L.mask.p, L.childBase.p, L.tstar.p, ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), 0, precheckKids);
+			else if (emitWarp) k_emit_warp<false, 8, false><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, relF.p, 0, 0, L.mask.p, L.childBase.p, L.tstar.p, ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), 0, precheckKids);
 			else if (!emitRedOut && !starStore) k_emit_pipe<false, 8, false, false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F(L.tstar.p,));
 			else if (!emitRedOut) k_emit_pipe<false, 8, false, true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F(L.tstar.p,));
 			else if (!starStore) k_emit_pipe<false, 8, true, false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_F(L.tstar.p,));
@@ -851,6 +960,8 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 			const uint64_t kids = fuseS ? cS - cSF : cS;
 			const int pidE = prof ? prof->begin("emit", (uint32_t)l, S) : -1;
 			if (emitPipe == 0) k_emit<true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S());
+			else if (emitWarp && starStore) k_emit_warp<true, 8, true><<<nb, VX_THREADS, 0, s>>>(S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, relS.p, cFe, Fan, L.mask.p, L.childBase.p, L.tstar.p, ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), fuseS ? 1 : 0, precheckKids);
+			else if (emitWarp) k_emit_warp<true, 8, false><<<nb, VX_THREADS, 0, s>>>(S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, relS.p, cFe, Fan, L.mask.p, L.childBase.p, L.tstar.p, ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), fuseS ? 1 : 0, precheckKids);
 			else if (!emitRedOut && !starStore) k_emit_pipe<true, 8, false, false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S(L.tstar.p,));
 			else if (!emitRedOut) k_emit_pipe<true, 8, false, true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S(L.tstar.p,));
 			else if (!starStore) k_emit_pipe<true, 8, true, false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S(L.tstar.p,));
