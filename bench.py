@@ -36,6 +36,10 @@ WORKLOADS = {
     "city_16k": dict(mesh="city", kw=dict(lots=256), levels=14, step=4, grid="16384^3",
                      cpu_sample=dict(mesh="city", kw=dict(lots=32), levels=11, step=2,
                                      note="same generator at lots=32, 2048^3 (levels 11, step 2): every lot spans 64 voxels as in the full workload; 1/64 of its ground area")),
+    # BASELINE.json configs[3]: the same city, CSVDAG (svbuilder -c): build + mergeAcrossAllLevels -> <base>-multi.svdag
+    "city_16k_c": dict(mesh="city", kw=dict(lots=256), levels=14, step=4, grid="16384^3", cross=True,
+                       cpu_sample=dict(mesh="city", kw=dict(lots=32), levels=11, step=2, cross=True,
+                                       note="same generator at lots=32, 2048^3 (levels 11, step 2), svbuilder -c: every lot spans 64 voxels as in the full workload; 1/64 of its ground area")),
     "terrain_4k": dict(mesh="terrain", kw=dict(n=1024), levels=12, step=3, grid="4096^3",
                        cpu_sample=dict(mesh="terrain", kw=dict(n=257), levels=10, step=2,
                                        note="same generator at n=257, 1024^3 (levels 10, step 2): 4 voxels per grid cell as in the full workload")),
@@ -49,7 +53,7 @@ WORKLOADS = {
 }
 # reference pins (tests/golden/*.json, minted by tests/golden/make_fullsize.py from the UNMODIFIED reference svbuilder):
 # the bench asserts the SHA-256 of its .ssvdag image and the node counts against them at every N
-GOLDEN = {"city_16k": "fullsize_city16k.json", "terrain_4k": "size_terrain4k.json", "spongeball_1k": "size_spongeball1k.json"}
+GOLDEN = {"city_16k": "fullsize_city16k.json", "city_16k_c": "fullsize_city16k.json", "terrain_4k": "size_terrain4k.json", "spongeball_1k": "size_spongeball1k.json"}
 # committed wall times of the unmodified reference on the same generator at growing sizes (8 cores of the build container)
 REF_SCALING = ["midsize_city4k.json", "bigsize_city8k.json", "fullsize_city16k.json"]
 METRIC = "mesh->SSVDAG build throughput (Gvoxel/s; BASELINE.json: build time at 16K^3 + dedup HBM GB/s vs peak)"
@@ -137,9 +141,9 @@ def reference_scaling():
 
 
 # ------------------------------------------------------------------------------------- reference arm
-def run_reference_once(orc, tris, levels, step, threads):
+def run_reference_once(orc, tris, levels, step, threads, cross=False):
     with tempfile.TemporaryDirectory() as td:
-        r = orc.run_reference(td, tris, levels, step, threads=threads)
+        r = orc.run_reference(td, tris, levels, step, threads=threads, cross=cross)
     vox = int(re.search(r"Voxels:\s+.*\((\d+)\)", r["log"]).group(1))
     return vox, r["seconds"]
 
@@ -166,7 +170,7 @@ def cpu_arm(pkg, wl, steps, warmup):
     times, vox = [], 0
     for i in range(warmup + steps):
         if use_ref:
-            vox, dt = run_reference_once(orc, tris, cs["levels"], cs["step"], cores)
+            vox, dt = run_reference_once(orc, tris, cs["levels"], cs["step"], cores, cross=bool(cs.get("cross")))
         else:
             vox, dt = run_port_once(orc, tris, cs["levels"], cs["step"])
         if i >= warmup:
@@ -193,7 +197,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": f"{args.workload}: procedural {wl['mesh']} mesh {wl['kw']} at {wl['grid']} (levels {wl['levels']}, step {wl['step']}) -> SVDAG -> SSVDAG",
+    cross = bool(wl.get("cross"))
+    config = {"workload": f"{args.workload}: procedural {wl['mesh']} mesh {wl['kw']} at {wl['grid']} (levels {wl['levels']}, step {wl['step']}) -> SVDAG -> " + ("CSVDAG (cross-level merge)" if cross else "SSVDAG"),
               "l2_policy": "inputs larger than L2 (every pass streams GBs of freshly written pair/node arrays)"}
 
     if args.impl == "reference":
@@ -237,12 +242,24 @@ def main():
     L, S = wl["levels"], wl["step"]
     pinned = torch.from_numpy(tris.reshape(-1)).pin_memory()
 
-    oct_ = pkg.GeomOctree(device=local_rank)
+    # N > 1: the context works on a torch-owned stream, so the exchange buffers (torch tensors), the NCCL collectives and the
+    # library's kernels are ordered by one stream that outlives all of them
+    oct_ = pkg.GeomOctree(device=local_rank, stream=torch.cuda.Stream(device=local_rank) if world > 1 else None)
     shard = dict(sharded=True) if world > 1 else {}
+
+    out_kind = "svdag" if cross else "ssvdag"     # the file the step ends in: <base>-multi.svdag or <base>.ssvdag
+
+    def post(o):
+        if not cross:
+            return o.to_sdag()
+        cm = o.cross_merge()                      # mergeAcrossAllLevels (geom_octree_extension.cpp:1192-1544)
+        cm["msSdag"] = cm["msCrossMerge"]
+        cm["nNodesSDAG"] = 0
+        return cm
 
     def step_resident():
         st = oct_.build(L, S, bbox=bbox, **shard)
-        sd = oct_.to_sdag()
+        sd = post(oct_)
         return st, sd
 
     h2d_bytes = [int(T) * 36]
@@ -255,10 +272,10 @@ def main():
         else:
             oct_.set_triangles_ptr(pinned.data_ptr(), T)
         st = oct_.build(L, S, bbox=bbox, **shard)
-        sd = oct_.to_sdag()
-        # the .ssvdag image is written on the GPU (svb_encode.cu) and lands in pinned host memory: D2H of the finished file,
+        sd = post(oct_)
+        # the file image is written on the GPU (svb_encode.cu) and lands in pinned host memory: D2H of the finished file,
         # once, by rank 0 (the file has one writer)
-        img = pkg.encoders.encode_view(oct_, "ssvdag") if rank == 0 else b""
+        img = pkg.encoders.encode_view(oct_, out_kind) if rank == 0 else b""
         return st, sd, img
 
     def barrier():
@@ -270,7 +287,7 @@ def main():
     oct_.set_triangles_ptr(pinned.data_ptr(), T)
     for _ in range(args.warmup):
         step_resident()
-    oct_.set_profiling(True)
+    oct_.set_profiling(2)      # per-launch CUDA-event records accumulate inside the library; they are fetched after the timed region
     sampler = ClockSampler(local_rank)
     prof, launches = [], 0
     barrier()
@@ -279,12 +296,12 @@ def main():
     dev_ms = 0.0
     for _ in range(args.steps):
         st, sd = step_resident()
-        prof += oct_.profile()
         launches += st["nKernelLaunches"] + sd["nKernelLaunches"]
         dev_ms += st["msTotal"] + sd["msSdag"]
     barrier()
     elapsed = time.perf_counter() - t0
     clocks = sampler.stop()
+    prof = oct_.profile()
     oct_.set_profiling(False)
 
     # ---- end-to-end timing through the public API with host buffers
@@ -299,20 +316,32 @@ def main():
         elapsed_e2e = time.perf_counter() - t1
         d2h = len(img) + 4 * sum(oct_.level_sizes()[:-1])       # the image + the per-level reference counts of the SSVDAG node order
 
+    per_rank = None
     if world > 1:
         tmax = torch.tensor([elapsed, elapsed_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         elapsed, elapsed_e2e = float(tmax[0]), float(tmax[1])
+        # where every rank spent its last timed step: device times of its share, host wall clock of the two phases
+        mine = torch.tensor([st["msVoxelize"], st["msDedup"], st["msFinalize"], st["msTotal"], st.get("wallLocalMs", 0.0), st.get("wallMergeMs", 0.0),
+                             float(st["nBatches"]), sd["msSdag"]], dtype=torch.float64, device="cuda")
+        allr = torch.empty(world * mine.numel(), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = {k: [round(float(x), 2) for x in allr.view(world, -1)[:, i]] for i, k in enumerate(
+            ["ms_voxelize", "ms_dedup", "ms_finalize", "ms_total_device", "wall_local_ms", "wall_merge_ms", "batches", "ms_sdag"])}
 
     # ---- parity pin: the .ssvdag image this very run produced (N ranks, NCCL merge and all) against the unmodified
     #      reference's file for the same input (tests/golden/*.json) -- asserted at every N, never assumed
     import hashlib
     if rank == 0 and not len(img):
-        img = pkg.encoders.encode_view(oct_, "ssvdag")
+        img = pkg.encoders.encode_view(oct_, out_kind)
     img = bytes(img)
     sha = hashlib.sha256(img).hexdigest() if rank == 0 else None
     pin = golden_pin(args.workload)
     parity = {"ssvdag_sha256": sha, "ssvdag_bytes": len(img), "reference_pin": None, "ok": None}
+    if cross:
+        parity["file"] = "-multi.svdag"
+        parity["cross_merge"] = {"ms_per_step": sd["msCrossMerge"], "nodes_eliminated": sd["nCrossLevelMerged"], "dag_nodes_after": sd["nNodesDAG"]}
+        pin = None                                # (reference pins of -c exist at 4096^3: tests/golden/midsize_city4k.json["cross"], checked by the GPU suite)
     if pin and rank == 0:
         want = pin["files"]["ssvdag"]
         checks = {"ssvdag_sha256": sha == want["sha256"], "ssvdag_bytes": len(img) == want["bytes"], "voxels": st["nTotalVoxels"] == pin["Voxels"],
@@ -387,7 +416,7 @@ def main():
             "tiles": st["nTiles"], "batches": st["nBatches"], "pairs": st["nPairsTotal"], "exact_retests": st["nExactTests"],
             "e2e": None if args.no_e2e else {"value": vox / sec_e2e / 1e9, "unit": "Gvoxel/s", "h2d_bytes_per_step": h2d_bytes[0] + (4 * sum(oct_.level_sizes()[:-1]) if rank == 0 else 0),
                                              "d2h_bytes_per_step": int(d2h), "seconds_per_step": sec_e2e, "ssvdag_bytes": len(img)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "dedup_effective": dedup_eff, "kernels": kernels, "parity": parity}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "dedup_effective": dedup_eff, "kernels": kernels, "parity": parity, "per_rank": per_rank}
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             try:

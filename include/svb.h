@@ -63,6 +63,10 @@ typedef struct svb_ctx svb_ctx;
 
 /* Lifetime.  device = CUDA ordinal this context binds to. */
 svb_ctx*    svb_create(int device);
+/* The same on a CUDA stream (cudaStream_t) the CALLER owns and keeps alive until svb_destroy: everything the context does is
+ * enqueued there.  What a host that already has a stream discipline uses (a torch stream: tensors handed to the
+ * svb_shard_* calls, NCCL collectives and the context's kernels are then ordered by the stream itself). */
+svb_ctx*    svb_create_on_stream(int device, void* cuda_stream);
 void        svb_destroy(svb_ctx* ctx);
 const char* svb_last_error(const svb_ctx* ctx);   /* never NULL */
 const char* svb_version(void);
@@ -205,7 +209,8 @@ typedef struct svb_prof_rec {
 	double   ms;           /* CUDA-event duration on the context's stream */
 	double   bytes;        /* algorithmic bytes of this launch group */
 } svb_prof_rec;
-int svb_set_profiling(svb_ctx* ctx, int enabled);
+int svb_set_profiling(svb_ctx* ctx, int enabled);   /* 0 off, 1 records of the last build, 2 records accumulate over builds until svb_profile_clear */
+int svb_profile_clear(svb_ctx* ctx);
 int svb_profile_count(const svb_ctx* ctx);
 int svb_profile_get(const svb_ctx* ctx, int i, svb_prof_rec* out);
 

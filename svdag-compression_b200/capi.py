@@ -57,6 +57,8 @@ def lib() -> C.CDLL:
         vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
         L.svb_create.restype = vp
         L.svb_create.argtypes = [C.c_int]
+        L.svb_create_on_stream.restype = vp
+        L.svb_create_on_stream.argtypes = [C.c_int, vp]
         L.svb_destroy.argtypes = [vp]
         L.svb_last_error.restype = C.c_char_p
         L.svb_last_error.argtypes = [vp]
@@ -99,9 +101,11 @@ class GeomOctree:
     """One GPU-resident octree.  Method names follow the reference class; data stays in HBM until
     `level()` / `levels_host()` copies it out (what the encoders read through getNodeData())."""
 
-    def __init__(self, tris=None, device: int = 0):
+    def __init__(self, tris=None, device: int = 0, stream=None):
+        """stream: a torch.cuda.Stream the context should work on (kept alive by this object); default: its own stream."""
         self._L = lib()
-        self._h = self._L.svb_create(device)
+        self._torch_stream = stream
+        self._h = self._L.svb_create_on_stream(device, stream.cuda_stream) if stream is not None else self._L.svb_create(device)
         if not self._h:
             raise SvbError(-2, "svb_create failed: no usable CUDA device (there is no CPU fallback)")
         self._tris = None
@@ -262,8 +266,9 @@ class GeomOctree:
                                               bb.ctypes.data, float(root_side), int(n_voxels)))
 
     # ---- instrumentation
-    def set_profiling(self, on: bool = True):
-        self._L.svb_set_profiling(self._h, 1 if on else 0)
+    def set_profiling(self, on=True):
+        """True / 1: records of the last build; 2: records accumulate over builds (read them once with profile()); False: off."""
+        self._L.svb_set_profiling(self._h, int(on))
 
     def profile(self):
         out = []

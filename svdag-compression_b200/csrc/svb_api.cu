@@ -401,6 +401,14 @@ void run_tiles_split(svb_ctx* c, BuildState& B, const std::vector<uint32_t>& sel
 	uint32_t a = 0;
 	const uint32_t b = (uint32_t)sel.size();
 	std::vector<uint32_t> plan(1, b);   // upcoming batch ends, ascending
+	// The first batches of a share run the expensive variants (first touches tracked on every level, nothing frozen in the
+	// tables yet); two small warm-up batches let the bulk of the share run as "later" batches.  Matters most when the share is
+	// small, i.e. with many GPUs: a rank of an 8-GPU build has 3 - 4 batches in all.
+	{
+		const char* e = getenv("SVB_WARMUP_DIV");
+		const uint32_t div = e ? (uint32_t)atoi(e) : 48u;
+		if (div >= 2 && b >= 4 * div) { plan.insert(plan.begin(), b / div + b / (2 * div)); plan.insert(plan.begin(), b / (2 * div)); }
+	}
 	while (a < b) {
 		uint32_t e = plan.front();
 		try {
@@ -444,7 +452,7 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 	if (world > 1 && step == 0) throw Error(SVB_EINVAL, "a sharded build needs step > 0 (sub-octrees are the unit of distribution)");
 	c->out.clear();
 	c->state = SVB_S_EMPTY;
-	c->prof.clear();
+	if (!c->profAccumulate) c->prof.clear();
 	c->lastImageKind = -1;
 	memset(&c->stats, 0, sizeof(c->stats));
 	c->build.reset(new BuildState());
@@ -797,6 +805,18 @@ svb_ctx* svb_create(int device) {
 	return c;
 }
 
+svb_ctx* svb_create_on_stream(int device, void* cuda_stream) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return nullptr;
+	if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+	svb_ctx* c = new svb_ctx();
+	c->device = device;
+	c->stream = (cudaStream_t)cuda_stream;
+	c->ownsStream = false;
+	c->pool.stream = c->stream;
+	return c;
+}
+
 void svb_destroy(svb_ctx* c) {
 	if (!c) return;
 	cudaSetDevice(c->device);
@@ -806,7 +826,7 @@ void svb_destroy(svb_ctx* c) {
 	c->image.release();
 	c->staging.release();
 	c->pool.release_all();
-	cudaStreamDestroy(c->stream);
+	if (c->ownsStream) cudaStreamDestroy(c->stream);
 	delete c;
 }
 
@@ -1239,6 +1259,13 @@ int svb_load_svdag(svb_ctx* c, const uint8_t* file, uint64_t size, svb_stats* ou
 int svb_set_profiling(svb_ctx* c, int enabled) {
 	if (!c) return SVB_EINVAL;
 	c->profiling = enabled != 0;
+	c->profAccumulate = enabled == 2;   // 2: keep the records of successive builds (read and cleared by the caller: svb_profile_clear)
+	if (!enabled) c->prof.clear();
+	return SVB_OK;
+}
+int svb_profile_clear(svb_ctx* c) {
+	if (!c) return SVB_EINVAL;
+	c->prof.clear();
 	return SVB_OK;
 }
 int svb_profile_count(const svb_ctx* c) { return c ? (int)c->prof.size() : 0; }

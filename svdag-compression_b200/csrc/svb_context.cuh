@@ -27,6 +27,7 @@ struct PinnedBuf {
 struct svb_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
+	bool ownsStream = true;   // false: a caller's stream (svb_create_on_stream)
 	svb::Pool pool;
 	std::string err;
 	// Scene triangle soup (scene.hpp:90-91)
@@ -40,7 +41,7 @@ struct svb_ctx {
 	svb_stats stats;
 	std::vector<uint64_t> svoCounts;
 	// instrumentation
-	bool profiling = false;
+	bool profiling = false, profAccumulate = false;
 	struct PendingProf { svb_prof_rec rec; cudaEvent_t e0, e1; bool closed = false; };
 	std::vector<PendingProf> pending;
 	std::vector<svb_prof_rec> prof;

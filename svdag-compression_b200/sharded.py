@@ -27,6 +27,9 @@ def octree_stream(octree, device):
     import torch
     if device.type != "cuda" or not hasattr(octree, "stream_ptr"):
         return contextlib.nullcontext()
+    ts = getattr(octree, "_torch_stream", None)      # the context was created on a torch stream (capi.GeomOctree(stream=...))
+    if ts is not None:
+        return torch.cuda.stream(ts)
     return torch.cuda.stream(torch.cuda.ExternalStream(octree.stream_ptr(), device=device))
 
 
@@ -50,7 +53,10 @@ def _build_sharded_once(octree, levels: int, step: int, bbox, group=None, device
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
-    octree.shard_build(levels, step, bbox, rank, world)
+    import time
+    t0 = time.perf_counter()
+    octree.shard_build(levels, step, bbox, rank, world)          # returns with this rank's local phase complete
+    t1 = time.perf_counter()
     first, last, ntiles, counters = octree.shard_info()
     order = list(range(last, first - 1, -1))
     local = [octree.shard_level_count(g) for g in order]          # (records, bytes per record) per level, final after the local phase
@@ -83,6 +89,8 @@ def _build_sharded_once(octree, levels: int, step: int, bbox, group=None, device
         st = octree.shard_finish(totals)                          # synchronises: the buffers above may go
     del keep
     st["bytesExchanged"] = exchanged + world * nt * 4
+    st["wallLocalMs"] = (t1 - t0) * 1e3                           # host wall clock: local phase / exchange + finish
+    st["wallMergeMs"] = (time.perf_counter() - t1) * 1e3
     return st
 
 
