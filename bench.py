@@ -352,12 +352,12 @@ def main():
     vox = st["nTotalVoxels"]
     sec = elapsed / args.steps
     sec_e2e = elapsed_e2e / args.steps
-    # ---- roofline.  The dominant HBM-bound kernel is k_emit_pipe (child-pair emission of the voxelizer, ~15 % of the GPU
-    #      time; the larger classify kernels are issue bound): achieved = algorithmic bytes of all its launches
-    #      (recorded per launch by the library: 20 B per parent pair read, 10 B (+ 4 B first touch) per child pair written)
-    #      / their CUDA-event time.  The dedup family BASELINE.json's metric names is reported next to it: since round 1e
-    #      its kernels skip what later batches cannot change, so the same node throughput is quoted as EFFECTIVE bandwidth
-    #      (13 B/node of this layout, 37 B/node by SURVEY.md 8(d)) -- it is not DRAM traffic and may exceed the peak.
+    # ---- roofline.  The largest kernel that is a plain HBM stream is k_emit_warp (child-pair emission of the voxelizer, ~15 % of the
+    #      GPU time; the larger classify kernels are issue bound): achieved = algorithmic bytes of all its launches
+    #      (recorded per launch by the library: 20 B per parent pair read, 10 B (+ 4 B first touch where tracked) per child pair
+    #      written) / their CUDA-event time on the build stream.  `traffic` = DRAM bytes per launch from the ncu capture
+    #      (profiles/ncu_traffic.json).  The dedup family BASELINE.json's metric names gets its own block, `roofline_dedup`, with
+    #      REAL DRAM bytes per node from ncu (not the "effective" figures of round 1).
     peak, peak_src = measured_peak_gbs()
     fam = {}
     for r in prof:
@@ -376,36 +376,37 @@ def main():
         alg = emit["bytes_survey"]
         ach = alg / (emit["ms"] * 1e-3) / 1e9
         traffic, traffic_src = None, None
-        tj = tj_all.get("k_emit_pipe")
+        tj = tj_all.get("k_emit_warp")
         if tj:
             traffic = float(tj["dram_bytes_per_algorithmic_byte"]) * alg / emit["launches"]
             traffic_src = tj.get("source")
-        roof = {"kernel": "k_emit_pipe (voxelizer: child-pair emission; the dominant HBM-bound kernel)", "bound": "hbm", "achieved": ach, "peak": peak,
+        roof = {"kernel": "k_emit_warp (voxelizer: child-pair emission; the largest plain HBM stream of the build)", "bound": "hbm", "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": alg / emit["launches"], "peak_source": peak_src,
-                "bytes_per_unit": "20 B per parent pair (11 B pair + 9 B node fields) + 10 B per child pair (+ 4 B first touch when tracked)",
+                "bytes_per_unit": "20 B per parent pair (11 B pair + 9 B node fields) + 10 B per child pair (+ 4 B first touch where tracked)",
                 "units_per_launch": {"parent_pairs": emit["units"] / emit["launches"], "child_pairs": emit["out"] / emit["launches"]},
                 "avg_launch_ms": emit["ms"] / emit["launches"], "share_of_step": emit["ms"] / (dev_ms if dev_ms else 1.0),
-                "note": "earlier records of this round put the roofline on k_leaf_min (leaf-level dedup, 5.89 TB/s = 90 % of peak); that full-read pass "
-                        "is no longer on the default path (later tile batches skip what they cannot change: see dedup_effective), so the roofline "
-                        "is now quoted on the largest kernel that still is a plain HBM stream; k_children (next largest) alongside"}
+                "note": "all launches of the step, the many small upper-level ones included (the deepest launches alone run at 0.65 of the peak, issue bound: profiles/r2h_ncu_emit_dedup_city16k.md)"}
         ch = fam.get("children")
         if ch and ch["ms"] > 0:
             a2 = ch["bytes_survey"] / (ch["ms"] * 1e-3) / 1e9
             roof["k_children"] = {"achieved": a2, "frac": a2 / peak, "bytes_per_unit": "13 B per node + 8 B per child node", "avg_launch_ms": ch["ms"] / ch["launches"]}
-    leaf = fam.get("dedup_leaf")
-    dedup_eff = None
-    if leaf and leaf["ms"] > 0:
-        dedup_eff = {"kernel": "k_leaf_lazy / k_leaf_known (dedup, leaf level)", "nodes_per_step": leaf["units"] // args.steps, "ms_per_step": leaf["ms"] / args.steps,
-                     "effective_GBps_at_13B_per_node": 13.0 * leaf["units"] / (leaf["ms"] * 1e-3) / 1e9,
-                     "effective_GBps_survey_37B_per_node": leaf["bytes_survey"] / (leaf["ms"] * 1e-3) / 1e9, "peak": peak,
-                     "note": "effective = bytes a full-read pass over this layout would move / time; the pass itself reads 1 B/node once a voxel mask is known "
-                             "(profiles/: k_leaf_min<0>, the full-read kernel it replaces, ran at 5.89 TB/s = 90 % of the measured peak)"}
-        for nm in ("dedup_k64", "dedup_inner"):
-            f = fam.get(nm)
-            if f and f["ms"] > 0:
-                dedup_eff[nm] = {"nodes_per_step": f["units"] // args.steps, "ms_per_step": f["ms"] / args.steps,
-                                 "effective_GBps_survey_37B_per_node": f["bytes_survey"] / (f["ms"] * 1e-3) / 1e9}
+    # per-level dedup kernels (BASELINE.json: "dedup HBM GB/s vs peak"): nodes x DRAM bytes per node (ncu) / CUDA-event time of the
+    # family's launch groups (which also hold the flag read-backs between the passes: a lower bound of the kernels' own rate)
+    dd = tj_all.get("dedup", {})
+    roofline_dedup = {}
+    for famname, key, label in (("dedup_leaf", "k_leaf_known", "leaf level (k_leaf_known / k_leaf_lazy)"),
+                                ("dedup_k64", "k_insert_k64", "4^3 level (k_insert_k64)"),
+                                ("dedup_inner", "k_insert_inner", "inner levels (k_insert + k_winner / k_convert on new entries)")):
+        f = fam.get(famname)
+        if not f or f["ms"] <= 0:
+            continue
+        bpn = float(dd.get(key, {}).get("dram_bytes_per_node", 0.0))
+        achd = bpn * f["units"] / (f["ms"] * 1e-3) / 1e9
+        roofline_dedup[famname] = {"kernels": label, "nodes_per_step": f["units"] // args.steps, "ms_per_step": f["ms"] / args.steps,
+                                   "dram_bytes_per_node": bpn, "achieved": achd, "peak": peak, "unit": "GB/s", "frac": achd / peak,
+                                   "source": dd.get(key, {}).get("source")}
+    dedup_eff = roofline_dedup or None
     kernels = {k: {"launches": f["launches"] // args.steps, "ms_per_step": f["ms"] / args.steps, "units_per_step": f["units"] // args.steps}
                for k, f in sorted(fam.items())}
 
@@ -416,7 +417,7 @@ def main():
             "tiles": st["nTiles"], "batches": st["nBatches"], "pairs": st["nPairsTotal"], "exact_retests": st["nExactTests"],
             "e2e": None if args.no_e2e else {"value": vox / sec_e2e / 1e9, "unit": "Gvoxel/s", "h2d_bytes_per_step": h2d_bytes[0] + (4 * sum(oct_.level_sizes()[:-1]) if rank == 0 else 0),
                                              "d2h_bytes_per_step": int(d2h), "seconds_per_step": sec_e2e, "ssvdag_bytes": len(img)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "dedup_effective": dedup_eff, "kernels": kernels, "parity": parity, "per_rank": per_rank}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_dedup": dedup_eff, "kernels": kernels, "parity": parity, "per_rank": per_rank}
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             try:
