@@ -240,6 +240,35 @@ __global__ void __launch_bounds__(VX_THREADS, 8) k_classify_fast(uint64_t P, con
 	if (m && (!precheck || (mask[n] & m) != m)) atomicOr(reinterpret_cast<unsigned*>(mask) + (n >> 2), m << (8 * (n & 3)));
 }
 
+// Two pairs per thread (default, SVB_FAST_ILP=1 selects the kernel above): the kernel is a chain of dependent loads, so what a
+// warp has in flight decides its rate; the fields of both pairs are fetched before the first is decided.
+template <bool DIRECT>
+__global__ void __launch_bounds__(VX_THREADS, 6) k_classify_fast2(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
+                                                                  uint16_t* __restrict__ pflags, const uint64_t* __restrict__ code, int l, double kscale, int last,
+                                                                  const TileGeom* __restrict__ tiles, const float* __restrict__ tris, const uint32_t* __restrict__ rootTri,
+                                                                  uint8_t* __restrict__ hit, uint8_t* __restrict__ mask, int precheck) {
+	const uint64_t pa = (uint64_t)blockIdx.x * (2 * VX_THREADS) + threadIdx.x, pb = pa + VX_THREADS;
+	if (pa >= P) return;
+	const bool hasB = pb < P;
+	const uint32_t qa = ptri[pa], na = pnode[pa];
+	const uint32_t qb = hasB ? ptri[pb] : qa, nb = hasB ? pnode[pb] : na;
+	const unsigned fla0 = pflags[pa], flb0 = hasB ? pflags[pb] : fla0;
+	const uint32_t ta = rootTri[qa], tb = rootTri[qb];
+	const uint64_t cda = code[na], cdb = code[nb];
+	unsigned fla = fla0, flb = flb0;
+	const double* tga = reinterpret_cast<const double*>(tiles + (uint32_t)(cda >> (3 * l)));
+	const double* tgb = reinterpret_cast<const double*>(tiles + (uint32_t)(cdb >> (3 * l)));
+	const unsigned ma = classify_pair_flat<DIRECT>(cda, l, tga, kscale, tris + 9ull * ta, fla);
+	const unsigned mb = hasB ? classify_pair_flat<DIRECT>(cdb, l, tgb, kscale, tris + 9ull * tb, flb) : 0u;
+	if (!last) {
+		if (fla != fla0) pflags[pa] = (uint16_t)fla;
+		hit[pa] = (uint8_t)ma;
+		if (hasB) { if (flb != flb0) pflags[pb] = (uint16_t)flb; hit[pb] = (uint8_t)mb; }
+	}
+	if (ma && (!precheck || (mask[na] & ma) != ma)) atomicOr(reinterpret_cast<unsigned*>(mask) + (na >> 2), ma << (8 * (na & 3)));
+	if (mb && (!precheck || (mask[nb] & mb) != mb)) atomicOr(reinterpret_cast<unsigned*>(mask) + (nb >> 2), mb << (8 * (nb & 3)));
+}
+
 // ------------------------------------------------------------------ flat stream, last two levels fused
 // At the second-to-last level the children of a flat-stream pair are not emitted as pairs: the thread that owns the
 // parent pair decides each hit child's 8 voxels on the spot (same exact box-axis tests, one level down) and ORs the
@@ -835,9 +864,16 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		static const uint64_t preRatio10 = [] { const char* e = getenv("SVB_PRECHECK_RATIO10"); return (uint64_t)(e ? atoi(e) : 20); }();
 		const int precheck = forcePre >= 0 ? forcePre : (10 * (F + S) > preRatio10 * L.n ? 1 : 0);   // read-before-atomic only where many pairs share a node
 		if (F) {
-			unsigned nb = blocks_for(F, VX_THREADS);
-			if (directCentre) k_classify_fast<true><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, hit.p, L.mask.p, precheck);
-			else k_classify_fast<false><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, hit.p, L.mask.p, precheck);
+			const int ilp = [] { const char* e = getenv("SVB_FAST_ILP"); return e ? atoi(e) : 2; }();
+			if (ilp >= 2) {
+				unsigned nb = blocks_for(F, 2 * VX_THREADS);
+				if (directCentre) k_classify_fast2<true><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, hit.p, L.mask.p, precheck);
+				else k_classify_fast2<false><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, hit.p, L.mask.p, precheck);
+			} else {
+				unsigned nb = blocks_for(F, VX_THREADS);
+				if (directCentre) k_classify_fast<true><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, hit.p, L.mask.p, precheck);
+				else k_classify_fast<false><<<nb, VX_THREADS, 0, s>>>(F, ptri.p, pnode.p, pflags.p, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, hit.p, L.mask.p, precheck);
+			}
 			SVB_KERNEL_CHECK();
 		}
 		if (S) {

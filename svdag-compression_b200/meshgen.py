@@ -19,7 +19,7 @@ from pathlib import Path
 import numpy as np
 
 __all__ = [
-    "sphere", "menger_sponge", "sphere_menger", "terrain", "city", "composite", "soup",
+    "sphere", "menger_sponge", "sphere_menger", "terrain", "city", "composite", "composite_crop", "soup",
     "corner_pins", "write_obj", "write_bincache", "make_mesh",
 ]
 
@@ -188,6 +188,20 @@ def composite(n_terrain: int = 1024, lots: int = 256) -> np.ndarray:
     return np.ascontiguousarray(np.concatenate([t, c], axis=0), dtype=np.float32)
 
 
+def composite_crop(n_terrain: int = 513, lots: int = 128, octant: int = 0) -> np.ndarray:
+    """BASELINE.md row 5 ("CPU parity on a cropped octant"): the triangles of composite(n_terrain, lots) that lie entirely
+    inside top-level octant `octant` (bit 2 = x, bit 1 = y, bit 0 = z high half), mapped onto [0,1]^3 by v -> 2v - o -- exact
+    in float32 for every vertex (a doubling and, for the high half, the subtraction of 1 from a value in [0.5, 1] x 2) -- plus
+    the corner pins.  The sub-scene has the mix of the full composite (general terrain triangles under axis-aligned city
+    boxes) at a size the reference's CPU build finishes in minutes."""
+    t = composite(n_terrain, lots)[:-2].astype(np.float32)
+    o = np.array([(octant >> 2) & 1, (octant >> 1) & 1, octant & 1], dtype=np.float32)
+    lo, hi = 0.5 * o, 0.5 * o + 0.5
+    inside = np.all((t >= lo) & (t <= hi), axis=(1, 2))
+    u = t[inside] * np.float32(2.0) - o
+    return np.ascontiguousarray(np.concatenate([u, corner_pins()], axis=0), dtype=np.float32)
+
+
 def soup(n: int = 400, seed: int = 7) -> np.ndarray:
     """Adversarial triangle soup for parity tests: random triangles of all sizes mixed with degenerate ones
     (points, segments, axis-aligned segments, zero-area slivers), triangles lying exactly in voxel faces, and
@@ -226,7 +240,7 @@ def soup(n: int = 400, seed: int = 7) -> np.ndarray:
 def make_mesh(name: str, **kw) -> np.ndarray:
     """Look a generator up by name ('sphere', 'sphere_menger', 'terrain', 'city', 'composite')."""
     return {"sphere": sphere, "sphere_menger": sphere_menger, "terrain": terrain,
-            "city": city, "composite": composite, "menger": menger_sponge, "soup": soup}[name](**kw)
+            "city": city, "composite": composite, "composite_crop": composite_crop, "menger": menger_sponge, "soup": soup}[name](**kw)
 
 
 # --------------------------------------------------------------------------- writers

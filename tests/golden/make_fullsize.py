@@ -2,7 +2,7 @@
 BASELINE.json's headline configuration -- procedural city (lots=256, 11.0 M triangles), 14 levels, step 4 -- and
 record the sizes and SHA-256 of the files it writes plus its result block.  About one hour on 8 cores, ~6 GB RAM.
 
-    python tests/golden/make_fullsize.py [fullsize|midsize|bigsize|terrain|spongeball] [workdir]
+    python tests/golden/make_fullsize.py [fullsize|midsize|bigsize|terrain|spongeball|composite_crop] [workdir]
 
 `midsize` (city lots=64 at 4096^3, levels 12 step 3) is the same generator at 1/16 of the ground area and finishes in
 minutes: tests/golden/midsize_city4k.json.
@@ -30,6 +30,8 @@ CONFIGS = {
     "bigsize": ("city", dict(lots=128), 13, 3, "bigsize_city8k.json"),       # 1/4 of the ground area: 2.75 M triangles at 8192^3 (tens of minutes)
     "terrain": ("terrain", dict(n=1024), 12, 3, "size_terrain4k.json"),      # BASELINE.json configs[1]: 2.09 M general triangles at 4096^3
     "spongeball": ("sphere_menger", dict(), 10, 1, "size_spongeball1k.json"),  # BASELINE.json configs[0]: sphere + Menger sponge at 1024^3
+    # one top-level octant of the terrain + city composite (configs[4]'s geometry mix), cropped and blown up to the unit cube
+    "composite_crop": ("composite_crop", dict(n_terrain=513, lots=128, octant=0), 12, 3, "size_composite_crop4k.json"),
 }
 
 
