@@ -333,6 +333,9 @@ struct TableDev {
 __device__ __forceinline__ bool table_find_or_claim(const TableDev& t, uint64_t tag, uint64_t& slot) {
 	uint64_t idx = mix64(tag) & t.capMask;
 	for (int probe = 0; probe < 8192; ++probe) {
+		// the pass is void once the table went over its load limit (it is grown and the pass redone): do not crawl through a
+		// nearly full table for nothing
+		if ((probe & 63) == 63 && *(volatile uint32_t*)&t.flags[0]) return false;
 		unsigned long long cur = t.tag[idx];
 		if (cur == tag) { slot = idx; return true; }
 		if (cur == EMPTY_TAG) {
@@ -926,6 +929,8 @@ static void dedup_k64_onepass(cudaStream_t s, Pool& pool, LevelTable& T, const D
 		SVB_CUDA(cudaStreamSynchronize(s));   // (also keeps `big` alive until the query has run)
 		if (h[3]) throw Error(SVB_ECUDA, "dedup: a node of the 4^3 level has no first touch (internal error)");
 	}
+	T.lastFresh = fresh;
+	T.lastN = a.N;
 	if (fresh) {
 		if (fresh <= LIST_CAP) k_assign_list<<<blocks_for(fresh, DD_THREADS), DD_THREADS, 0, s>>>((uint32_t)fresh, newSlots.p, (const unsigned long long*)T.tag.p, (const unsigned long long*)T.minO.p, T.uid.p, T.dMinO.p, T.dKey64.p);
 		else k_assign_scan<<<blocks_for(T.cap, DD_THREADS), DD_THREADS, 0, s>>>(T.cap, (uint32_t)T.count, (const unsigned long long*)T.tag.p, (const unsigned long long*)T.minO.p, T.uid.p, T.dMinO.p, T.dKey64.p);
@@ -948,7 +953,10 @@ bool k64_tstar_optional(const LevelTable& T, uint32_t seqLo) {
 	const char* f = getenv("SVB_K64_ONEPASS");
 	if ((e && e[0] == '0') || (f && atoi(f) <= 0)) return false;
 	// the single-pass insert must be usable for whatever the batch brings (see dedup_level_t): keep well inside its limits
-	return T.kind == KIND_K64 && T.seenAny && seqLo > T.maxSeq && T.count > 0 && T.cap <= (1ull << 27) && T.count < (1ull << 29);
+	if (!(T.kind == KIND_K64 && T.seenAny && seqLo > T.maxSeq && T.count > 0 && T.cap <= (1ull << 27) && T.count < (1ull << 29))) return false;
+	// every node of a NEW entry costs a direct query (a warp walking the tile's triangles): only worth it where new entries are
+	// rare -- box meshes bring a few per 10^8 nodes, a terrain brings one per 10^2 and is better off tracking first touches
+	return T.lastN > 0 && (double)T.lastFresh * 50000.0 < (double)T.lastN;
 }
 
 bool dedup_leaf_known(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, const LeafQuery& lq, uint64_t* d_voxels) {
@@ -1000,7 +1008,13 @@ static void dedup_level_t(cudaStream_t s, Pool& pool, LevelTable& T, const Dedup
 	// size the slot array for this level: at least 2x the entries it may end up holding if ~1/8 of the
 	// nodes are new; an overflow simply grows x4 and redoes the pass (failed attempts leave no trace:
 	// their slots have no uid and are dropped by the rebuild).
-	uint64_t want = next_pow2(2 * (T.count + a.N / 8 + 1024));
+	// ... where 1/8 is replaced by what the previous batch showed (its share of new entries, doubled), and by 1/2 for the first
+	// batch of a level with 9 or more voxel patterns below it: a terrain level is mostly unique nodes, and a pass that runs the
+	// table over its limit costs far more than the pass itself (long probe chains, then everything again).
+	uint64_t expectNew = a.N / 8;
+	if (T.lastN) expectNew = std::min<uint64_t>(a.N, (uint64_t)(2.0 * (double)T.lastFresh / (double)T.lastN * (double)a.N) + a.N / 64);
+	else if (T.count == 0) expectNew = a.N / 2;
+	uint64_t want = next_pow2(2 * (T.count + expectNew + 1024));
 	if (want > T.cap) grow_slots(s, pool, T, want);
 	const bool later = later_batch(T, a);
 	const char* pk = getenv("SVB_K64_PERM");   // 0: the byte-by-byte key builder (A/B, verification)
@@ -1065,6 +1079,8 @@ static void dedup_level_t(cudaStream_t s, Pool& pool, LevelTable& T, const Dedup
 		SVB_CUDA(cudaStreamSynchronize(s));
 		if (h[1]) throw Error(SVB_ECOLLISION, "64-bit node-key hash collision (exact verify failed)");
 	}
+	T.lastFresh = fresh;
+	T.lastN = a.N;
 	T.count += fresh;
 }
 

@@ -228,6 +228,7 @@ struct LevelTable {
 	bool seenAny = false;
 	uint32_t maxSeq = 0;
 	uint32_t known = 0, lastAdded = 0;   // KIND_LEAF: voxel masks with an entry, and how many of them the last batch brought
+	uint64_t lastFresh = 0, lastN = 0;   // KIND_K64 / KIND_INNER: entries the last batch created, out of how many nodes
 	// finalize
 	DevBuf<uint32_t> rank;    // uid -> final id (LEAF: mask value -> final id)
 	uint64_t unique = 0;
@@ -266,6 +267,13 @@ void scan_tiles_popc8(cudaStream_t s, Pool& pool, const uint8_t* bytes, uint64_t
 // A = popcount(hit) of every pair, B = the same restricted to pairs whose flags put their children into the flat stream
 void scan_tiles_pairs(cudaStream_t s, Pool& pool, const uint8_t* hit, const uint16_t* flags, uint64_t n,
                       DevBuf<uint64_t>& tileOffsA, DevBuf<uint64_t>& tileOffsB, uint64_t* d_totalA, uint64_t* d_totalB, DevBuf<uint32_t>* rel = nullptr);
+// The four tile-granular scans of one voxelizer level in one go (three reduce kernels + ONE launch for the four scans of the
+// tile sums): children per node, child pairs of the flat stream, child pairs / flat child pairs of the slow stream.
+// d_tot4[0..3] receive the four totals.
+void scan_level_tiles(cudaStream_t s, Pool& pool, const uint8_t* nodeMask, uint64_t nNodes, const uint8_t* hitF, uint64_t nF,
+                      const uint8_t* hitS, const uint16_t* flagsS, uint64_t nS,
+                      DevBuf<uint64_t>& nodeOffs, DevBuf<uint64_t>& offF, DevBuf<uint64_t>& offS, DevBuf<uint64_t>& offSF,
+                      DevBuf<uint32_t>* relF, DevBuf<uint32_t>* relS, uint64_t* d_tot4);
 // exclusive scan of uint32 values (in place allowed), total to *d_total
 void scan_u32(cudaStream_t s, Pool& pool, const uint32_t* in, uint64_t n, uint32_t* out, uint64_t* d_total);
 // stable LSD radix sort of (key u64, val u32) pairs on the low `bits` bits of the key.

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const uint32_t* __re
 // is a serial chain of trips (two barriers each), 4 of them per level -- 8x fewer trips (default; SVB_SCAN_WIDE=0: the
 // kernel above).
 constexpr int SW_THREADS = 1024, SW_ITEMS = 16;
-__global__ void __launch_bounds__(SW_THREADS) k_scan_sums_wide(const uint32_t* __restrict__ sums, uint64_t nb, uint64_t* __restrict__ offs, uint64_t* __restrict__ total) {
+__device__ __forceinline__ void scan_sums_wide_body(const uint32_t* __restrict__ sums, uint64_t nb, uint64_t* __restrict__ offs, uint64_t* __restrict__ total) {
 	__shared__ unsigned long long wsum[SW_THREADS / 32];
 	__shared__ unsigned long long carry;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -174,6 +174,22 @@ __global__ void __launch_bounds__(SW_THREADS) k_scan_sums_wide(const uint32_t* _
 		__syncthreads();   // wsum / carry are rewritten by the next trip
 	}
 	if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(SW_THREADS) k_scan_sums_wide(const uint32_t* __restrict__ sums, uint64_t nb, uint64_t* __restrict__ offs, uint64_t* __restrict__ total) {
+	scan_sums_wide_body(sums, nb, offs, total);
+}
+// up to four independent scans in one launch, one CTA each: the four tile-sum scans of a voxelizer level used to be four
+// launches of a single CTA in a row on the stream (~10 us each, ~800 per build, the GPU idle behind each of them)
+struct ScanJobs4 {
+	const uint32_t* sums[4];
+	uint64_t nb[4];
+	uint64_t* offs[4];
+	uint64_t* total[4];
+};
+__global__ void __launch_bounds__(SW_THREADS) k_scan_sums_wide_multi(ScanJobs4 J) {
+	const int j = blockIdx.x;
+	if (J.nb[j] == 0) { if (threadIdx.x == 0) *J.total[j] = 0; return; }
+	scan_sums_wide_body(J.sums[j], J.nb[j], J.offs[j], J.total[j]);
 }
 static void launch_scan_sums(cudaStream_t s, const uint32_t* sums, uint64_t nb, uint64_t* offs, uint64_t* total) {
 	const char* e = getenv("SVB_SCAN_WIDE");
@@ -334,6 +350,30 @@ void scan_tiles_pairs(cudaStream_t s, Pool& pool, const uint8_t* hit, const uint
 	launch_scan_sums(s, sumsA.p, nb, tileOffsA.p, d_totalA);
 	SVB_KERNEL_CHECK();
 	launch_scan_sums(s, sumsB.p, nb, tileOffsB.p, d_totalB);
+	SVB_KERNEL_CHECK();
+}
+
+void scan_level_tiles(cudaStream_t s, Pool& pool, const uint8_t* nodeMask, uint64_t nNodes, const uint8_t* hitF, uint64_t nF,
+                      const uint8_t* hitS, const uint16_t* flagsS, uint64_t nS,
+                      DevBuf<uint64_t>& nodeOffs, DevBuf<uint64_t>& offF, DevBuf<uint64_t>& offS, DevBuf<uint64_t>& offSF,
+                      DevBuf<uint32_t>* relF, DevBuf<uint32_t>* relS, uint64_t* d_tot4) {
+	const uint64_t nbN = (nNodes + SCAN_TILE - 1) / SCAN_TILE, nbF = (nF + SCAN_TILE - 1) / SCAN_TILE, nbS = (nS + SCAN_TILE - 1) / SCAN_TILE;
+	nodeOffs.reset(pool, nbN ? nbN : 1);
+	offF.reset(pool, nbF ? nbF : 1);
+	offS.reset(pool, nbS ? nbS : 1);
+	offSF.reset(pool, nbS ? nbS : 1);
+	if (relF) relF->reset(pool, nbF ? nbF * SCAN_THREADS : 1);
+	if (relS) relS->reset(pool, nbS ? nbS * SCAN_THREADS : 1);
+	DevBuf<uint32_t> sumsN(pool, nbN ? nbN : 1), sumsF(pool, nbF ? nbF : 1), sumsA(pool, nbS ? nbS : 1), sumsB(pool, nbS ? nbS : 1);
+	if (nbN) { k_scan_reduce<Popc8In><<<(unsigned)nbN, SCAN_THREADS, 0, s>>>(Popc8In{nodeMask}, nNodes, sumsN.p, nullptr); SVB_KERNEL_CHECK(); }
+	if (nbF) { k_scan_reduce<Popc8In><<<(unsigned)nbF, SCAN_THREADS, 0, s>>>(Popc8In{hitF}, nF, sumsF.p, relF ? relF->p : nullptr); SVB_KERNEL_CHECK(); }
+	if (nbS) { k_pair_reduce<<<(unsigned)nbS, SCAN_THREADS, 0, s>>>(hitS, flagsS, nS, sumsA.p, sumsB.p, relS ? relS->p : nullptr); SVB_KERNEL_CHECK(); }
+	ScanJobs4 J;
+	J.sums[0] = sumsN.p; J.nb[0] = nbN; J.offs[0] = nodeOffs.p; J.total[0] = d_tot4 + 0;
+	J.sums[1] = sumsF.p; J.nb[1] = nbF; J.offs[1] = offF.p; J.total[1] = d_tot4 + 1;
+	J.sums[2] = sumsA.p; J.nb[2] = nbS; J.offs[2] = offS.p; J.total[2] = d_tot4 + 2;
+	J.sums[3] = sumsB.p; J.nb[3] = nbS; J.offs[3] = offSF.p; J.total[3] = d_tot4 + 3;
+	k_scan_sums_wide_multi<<<4, SW_THREADS, 0, s>>>(J);
 	SVB_KERNEL_CHECK();
 }
 

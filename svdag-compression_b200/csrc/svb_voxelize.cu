@@ -321,6 +321,64 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_flat_leaves(uint64_t P, co
 	if (acc && (!precheck || (words[curWord] & acc) != acc)) atomicOr(words + curWord, acc);
 }
 
+// Two parent pairs per thread (default; SVB_LEAVES_ILP=1 selects the kernel above): the pair fields and the node fields of both
+// pairs are in flight before the first pair is decided -- the kernel is a chain of dependent gathers (pair -> node ->
+// tile / triangle), and the loads a warp has outstanding decide its rate.
+template <bool DIRECT, int MINB, bool STAR>
+__global__ void __launch_bounds__(VX_THREADS, MINB) k_flat_leaves2(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
+                                                                const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit,
+                                                                const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase, const uint32_t* __restrict__ tstar,
+                                                                int lc, double kscaleParent, const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
+                                                                const uint32_t* __restrict__ rootTri, uint8_t* __restrict__ cmask, uint32_t* __restrict__ ctstar, int onlyFlatKids, int precheck) {
+	const uint64_t p0 = (uint64_t)blockIdx.x * (2 * VX_THREADS) + threadIdx.x;
+	unsigned m[2], fl[2], nm[2];
+	uint32_t t[2], n[2], base[2], ts[2], tr[2];
+	uint64_t cd[2];
+#pragma unroll
+	for (int j = 0; j < 2; ++j) {
+		const uint64_t p = p0 + (uint64_t)j * VX_THREADS;
+		m[j] = 0; fl[j] = 0; t[j] = 0; n[j] = 0;
+		if (p < P) { m[j] = hit[p]; fl[j] = pflags[p]; t[j] = ptri[p]; n[j] = pnode[p]; }
+		if (onlyFlatKids && !pair_is_fast(fl[j])) m[j] = 0;
+	}
+#pragma unroll
+	for (int j = 0; j < 2; ++j) {
+		cd[j] = 0; nm[j] = 0; base[j] = 0; ts[j] = 0; tr[j] = 0;
+		if (m[j]) {
+			cd[j] = code[n[j]]; nm[j] = mask[n[j]]; base[j] = childBase[n[j]]; tr[j] = rootTri[t[j]];
+			if (STAR && ctstar) ts[j] = tstar[n[j]];
+		}
+	}
+	unsigned* const words = reinterpret_cast<unsigned*>(cmask);
+#pragma unroll
+	for (int j = 0; j < 2; ++j) {
+		unsigned mm = m[j];
+		if (!mm) continue;
+		const bool star = STAR && ctstar && ts[j] == t[j];
+		const double* tg = reinterpret_cast<const double*>(tiles + (uint32_t)(cd[j] >> (3 * (lc - 1))));
+		unsigned lohi[3][2];
+		flat_leaf_masks<DIRECT>(cd[j], lc - 1, tg, kscaleParent, tris + 9ull * tr[j], fl[j], lohi);
+		uint32_t curWord = 0xFFFFFFFFu;
+		unsigned acc = 0;
+		while (mm) {
+			const int c = __ffs(mm) - 1;
+			mm &= mm - 1;
+			const uint32_t child = base[j] + __popc(nm[j] & ((1u << c) - 1));
+			const unsigned mc = lohi[0][(c >> 2) & 1] & lohi[1][(c >> 1) & 1] & lohi[2][c & 1];
+			if ((child >> 2) != curWord) {
+				if (acc && (!precheck || (words[curWord] & acc) != acc)) atomicOr(words + curWord, acc);
+				curWord = child >> 2;
+				acc = 0;
+			}
+			acc |= mc << (8 * (child & 3));
+			if (!ctstar) continue;
+			if (star) ctstar[child] = t[j];
+			else if (!precheck || ctstar[child] > t[j]) atomicMin(&ctstar[child], t[j]);
+		}
+		if (acc && (!precheck || (words[curWord] & acc) != acc)) atomicOr(words + curWord, acc);
+	}
+}
+
 // ------------------------------------------------------------------ emit the child pairs
 // One CTA per tile of parent pairs.  The pair arrays are kept as two streams: [0, nFlat) flat-stream pairs,
 // [slowBase, ...) the others (stable partition: both streams stay sorted by triangle id).  SLOW = false: parents of
@@ -903,9 +961,13 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		// children of the nodes, child pairs of the pairs: tile-granular scans, one read-back
 		DevBuf<uint64_t> nodeOffs, offF, offFB, offS, offSF;
 		DevBuf<uint32_t> relF, relS;   // tile-relative offsets per 8 pairs (k_emit_warp)
-		scan_tiles_popc8(s, pool, L.mask.p, L.n, nodeOffs, tot.p + 0);
-		scan_tiles_popc8(s, pool, hit.p, F, offF, tot.p + 1, emitWarp ? &relF : nullptr);
-		scan_tiles_pairs(s, pool, hit.p + Fa, pflags.p + Fa, S, offS, offSF, tot.p + 2, tot.p + 3, emitWarp ? &relS : nullptr);
+		const bool scanMulti = [] { const char* e = getenv("SVB_SCAN_MULTI"); return !(e && e[0] == '0') && !(getenv("SVB_SCAN_WIDE") && getenv("SVB_SCAN_WIDE")[0] == '0'); }();
+		if (scanMulti) scan_level_tiles(s, pool, L.mask.p, L.n, hit.p, F, hit.p + Fa, pflags.p + Fa, S, nodeOffs, offF, offS, offSF, emitWarp ? &relF : nullptr, emitWarp ? &relS : nullptr, tot.p);
+		else {
+			scan_tiles_popc8(s, pool, L.mask.p, L.n, nodeOffs, tot.p + 0);
+			scan_tiles_popc8(s, pool, hit.p, F, offF, tot.p + 1, emitWarp ? &relF : nullptr);
+			scan_tiles_pairs(s, pool, hit.p + Fa, pflags.p + Fa, S, offS, offSF, tot.p + 2, tot.p + 3, emitWarp ? &relS : nullptr);
+		}
 		uint64_t h[4];
 		SVB_CUDA(cudaMemcpyAsync(h, tot.p, 32, cudaMemcpyDeviceToHost, s));
 		SVB_CUDA(cudaStreamSynchronize(s));
@@ -965,13 +1027,17 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 			static const int occLeaves = [] { const char* e = getenv("SVB_VX_OCC_LEAVES"); return e ? atoi(e) : 8; }();   // 8 CTAs/SM measured best
 #define SVB_LAUNCH_FL(DIR, N, OFF, ONLY) if (occLeaves >= 8) SVB_LAUNCH_FL2(DIR, 8, N, OFF, ONLY); else SVB_LAUNCH_FL2(DIR, 6, N, OFF, ONLY)
 #define SVB_LAUNCH_FL2(DIR, MB, N, OFF, ONLY) if (starStore) SVB_LAUNCH_FL3(DIR, MB, true, N, OFF, ONLY); else SVB_LAUNCH_FL3(DIR, MB, false, N, OFF, ONLY)
-#define SVB_LAUNCH_FL3(DIR, MB, ST, N, OFF, ONLY) k_flat_leaves<DIR, MB, ST><<<blocks_for(N, VX_THREADS), VX_THREADS, 0, s>>>(N, ptri.p + (OFF), pnode.p + (OFF), pflags.p + (OFF), hit.p + (OFF), \
-			L.code.p, L.mask.p, L.childBase.p, L.tstar.p, l + 1, kscale, d_tiles, d_tris, rootTri, C.mask.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), ONLY, precheckKids)
+#define SVB_FL_ARGS(N, OFF, ONLY) N, ptri.p + (OFF), pnode.p + (OFF), pflags.p + (OFF), hit.p + (OFF), \
+			L.code.p, L.mask.p, L.childBase.p, L.tstar.p, l + 1, kscale, d_tiles, d_tris, rootTri, C.mask.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), ONLY, precheckKids
+			const int leavesIlp = [] { const char* e = getenv("SVB_LEAVES_ILP"); return e ? atoi(e) : 2; }();
+#define SVB_LAUNCH_FL3(DIR, MB, ST, N, OFF, ONLY) do { if (leavesIlp >= 2) k_flat_leaves2<DIR, (MB >= 8 ? 6 : 5), ST><<<blocks_for(N, 2 * VX_THREADS), VX_THREADS, 0, s>>>(SVB_FL_ARGS(N, OFF, ONLY)); \
+			else k_flat_leaves<DIR, MB, ST><<<blocks_for(N, VX_THREADS), VX_THREADS, 0, s>>>(SVB_FL_ARGS(N, OFF, ONLY)); } while (0)
 			if (F) { if (directCentre) SVB_LAUNCH_FL(true, F, 0, 0); else SVB_LAUNCH_FL(false, F, 0, 0); SVB_KERNEL_CHECK(); }
 			if (fuseS && S && cSF) { if (directCentre) SVB_LAUNCH_FL(true, S, Fa, 1); else SVB_LAUNCH_FL(false, S, Fa, 1); SVB_KERNEL_CHECK(); }
 #undef SVB_LAUNCH_FL
 #undef SVB_LAUNCH_FL2
 #undef SVB_LAUNCH_FL3
+#undef SVB_FL_ARGS
 			pairsTotal += cF + (fuseS ? cSF : 0);   // decided here instead of as pairs of the last level
 		} else if (F) {
 #define SVB_EMIT_ARGS_F(...) F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p, __VA_ARGS__ ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), 0, precheckKids
