@@ -1013,8 +1013,10 @@ static void dedup_level_t(cudaStream_t s, Pool& pool, LevelTable& T, const Dedup
 	// table over its limit costs far more than the pass itself (long probe chains, then everything again).
 	uint64_t expectNew = a.N / 8;
 	if (T.lastN) expectNew = std::min<uint64_t>(a.N, (uint64_t)(2.0 * (double)T.lastFresh / (double)T.lastN * (double)a.N) + a.N / 64);
-	else if (T.count == 0) expectNew = a.N / 2;
+	else if (T.count == 0) expectNew = std::max<uint64_t>(a.N / 8, std::min<uint64_t>(a.N / 2, 16ull << 20));
 	uint64_t want = next_pow2(2 * (T.count + expectNew + 1024));
+	// (the single-pass 4^3 insert needs <= 2^28 slots: do not size it out of reach on a guess -- an overflow grows the table anyway)
+	if (k64 && want > (1ull << 28) && T.count < (1ull << 26)) want = 1ull << 28;
 	if (want > T.cap) grow_slots(s, pool, T, want);
 	const bool later = later_batch(T, a);
 	const char* pk = getenv("SVB_K64_PERM");   // 0: the byte-by-byte key builder (A/B, verification)

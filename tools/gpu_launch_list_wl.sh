@@ -1,6 +1,6 @@
 #!/bin/bash
 # ncu launch list of one build of a bench workload (default terrain_4k), aggregated per kernel
-W=${1:-terrain_4k}
+W=${1:-terrain_4k}; NB=${2:-2}
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 cat > /tmp/ncu_wl.py <<PY
@@ -14,7 +14,7 @@ tris = pkg.meshgen.make_mesh(wl["mesh"], **wl["kw"])
 v = tris.reshape(-1, 3)
 bbox = (v.min(axis=0).astype(np.float64), v.max(axis=0).astype(np.float64))
 t = pkg.GeomOctree(tris)
-for it in range(2):
+for it in range($NB):
     st = t.build(wl["levels"], wl["step"], bbox=bbox); sd = t.to_sdag()
 print(st["nTotalVoxels"], st["msTotal"], st["msVoxelize"], st["msDedup"], st["msFinalize"], sd["msSdag"], st["nKernelLaunches"], t.level_sizes())
 PY
@@ -25,7 +25,7 @@ import csv, collections
 with open("gpurun_out/launches_$W.csv") as f:
     lines = [l for l in f if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
-rows = rows[len(rows) // 2:]          # second build only (warm pool)
+rows = rows[len(rows) // 2:] if $NB == 2 else rows         # second build only (warm pool)
 agg = collections.OrderedDict()
 for row in rows:
     name = row["Kernel Name"].split("(")[0]
