@@ -218,6 +218,114 @@ __global__ void __launch_bounds__(VX_THREADS) k_children(uint64_t N, const uint6
 	}
 }
 
+// ------------------------------------------------------------------ k_children with TMA bulk copies (sm_100a; default, SVB_CHILDREN_TMA=0: the kernel above)
+// The level buffers this kernel moves are plain contiguous streams: node codes and masks in, child codes out.  Here the
+// copy engine moves them: the CTA's 2048-node tile is cut into 4 stages of 512 nodes; one elected thread issues
+// cp.async.bulk (global -> shared, completion counted in bytes on an mbarrier) for stage i+1 while the threads work on
+// stage i out of shared memory, and the staged child codes of a stage leave with ONE cp.async.bulk (shared -> global) instead
+// of a store loop.  Bulk copies want 16-byte aligned addresses and sizes on both sides: the staging buffer is shifted by
+// (run & 1) elements so that shared and global addresses agree mod 16, and the at most one leading / trailing 8-byte element
+// goes out with a plain store.  childBase is written as one 8-byte store per thread (two consecutive nodes).
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra DONE_%=;\n"
+	    "bra WAIT_%=;\n"
+	    "DONE_%=:\n"
+	    "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared, completion on an mbarrier (bytes: multiple of 16; both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global, tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dstGlobal, const void* srcSmem, uint32_t bytes) {
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstGlobal), "r"(smem_u32(srcSmem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+}  // namespace tma
+
+constexpr int CT_STAGE = 256;                      // nodes per pipeline stage (1 per thread)
+constexpr int CT_STAGES = VX_TILE / CT_STAGE;      // 8 stages per 2048-node tile
+__global__ void __launch_bounds__(VX_THREADS, 5) k_children_tma(uint64_t N, const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask,
+                                                                 const uint64_t* __restrict__ tileOffs, uint32_t* __restrict__ childBase, uint64_t* __restrict__ ccode) {
+	__shared__ __align__(16) uint64_t s_in[2][CT_STAGE];            // node codes of a stage, double buffered (2 KB each)
+	__shared__ __align__(16) uint8_t s_mask[2][CT_STAGE];           // node masks
+	__shared__ __align__(16) uint64_t s_out[2][CT_STAGE * 8 + 2];   // child codes of a stage (16 KB each, double buffered) + the alignment shift
+	__shared__ __align__(8) uint64_t bar[2];
+	__shared__ uint32_t wsum[9];
+	const uint64_t n0 = (uint64_t)blockIdx.x * VX_TILE;
+	const int tid = threadIdx.x;
+	auto stage_count = [&](int st) -> uint32_t {   // nodes of stage st that exist
+		const uint64_t b = n0 + (uint64_t)st * CT_STAGE;
+		return (st >= CT_STAGES || b >= N) ? 0u : (uint32_t)((N - b) < CT_STAGE ? (N - b) : CT_STAGE);
+	};
+	auto issue = [&](int st) {   // one thread: arm the stage's barrier and start its two bulk loads
+		const uint32_t cnt = stage_count(st);
+		if (!cnt) return;
+		const int buf = st & 1;
+		const uint32_t bc = (cnt * 8 + 15) & ~15u, bm = (cnt + 15) & ~15u;   // (rounded-up reads stay inside the pool block)
+		tma::mbar_expect_tx(&bar[buf], bc + bm);
+		tma::bulk_g2s(s_in[buf], code + n0 + (uint64_t)st * CT_STAGE, bc, &bar[buf]);
+		tma::bulk_g2s(s_mask[buf], mask + n0 + (uint64_t)st * CT_STAGE, bm, &bar[buf]);
+	};
+	if (tid == 0) {
+		tma::mbar_init(&bar[0], 1);
+		tma::mbar_init(&bar[1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (tid == 0) { issue(0); issue(1); }
+	uint64_t run = tileOffs[blockIdx.x];
+	for (int st = 0; st < CT_STAGES; ++st) {
+		const uint32_t cnt = stage_count(st);
+		if (!cnt) break;
+		const int buf = st & 1;
+		tma::mbar_wait(&bar[buf], (st >> 1) & 1);                     // stage st has landed
+		unsigned m = 0;
+		uint64_t cd = 0;
+		if ((uint32_t)tid < cnt) { m = s_mask[buf][tid]; cd = s_in[buf][tid] << 3; }
+		uint32_t tot;
+		uint32_t o = cta_excl_scan(__popc(m), wsum, &tot);            // (its barriers also end every thread's reads of the input buffer)
+		if (tid == 0) issue(st + 2);                                  // refill the input buffer just consumed
+		if ((uint32_t)tid < cnt) childBase[n0 + (uint64_t)st * CT_STAGE + tid] = (uint32_t)(run + o);
+		const uint32_t shift = (uint32_t)(run & 1);                   // shared and global addresses agree mod 16
+		uint64_t* const so = s_out[buf];                              // (its previous bulk store, two stages ago, has been drained below)
+		uint32_t w = shift + o;
+		while (m) { const int c = __ffs(m) - 1; m &= m - 1; so[w++] = cd | (uint64_t)c; }
+		tma::fence_proxy_async();                                      // the staged codes must be visible to the copy engine
+		__syncthreads();
+		if (tid == 0) {
+			if (tot) {
+				uint32_t head = shift ? 1u : 0u;                      // a leading element on an odd global index
+				if (head > tot) head = tot;
+				const uint32_t body = (tot - head) & ~1u;             // 16-byte granules
+				if (head) ccode[run] = so[shift];
+				if (body) tma::bulk_s2g(ccode + run + head, &so[shift + head], body * 8);
+				if (head + body < tot) ccode[run + tot - 1] = so[shift + tot - 1];
+			}
+			tma::bulk_commit();                                        // one group per stage (possibly empty)
+			asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store of stage st-1 has read its buffer: stage st+1 may overwrite it
+		}
+		run += tot;
+		__syncthreads();
+	}
+	if (tid == 0) tma::bulk_wait_read0();
+}
+
 // ------------------------------------------------------------------ classify, fast stream
 // Pairs of the flat stream (pair_is_fast(), svb_classify.cuh): exact box-axis tests only.  Few registers, full
 // occupancy: the kernel is a chain of three dependent loads (pair -> node code -> tile geometry / vertex
@@ -902,6 +1010,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 	const bool exactOnly = classify_exact_only();
 	// k_emit variant: 0 = one chunk at a time, else software-pipelined (read per batch, not cached: A/B inside one process)
 	const bool childrenPipe = [] { const char* e = getenv("SVB_CHILDREN_PIPE"); return !(e && e[0] == '0'); }();
+	const bool childrenTma = childrenPipe && [] { const char* e = getenv("SVB_CHILDREN_TMA"); return !(e && e[0] == '0'); }();   // cp.async.bulk + mbarrier pipeline (k_children_tma)
 	const int emitPipe = [] { const char* e = getenv("SVB_EMIT_PIPE"); return e ? atoi(e) : 8; }();
 	const bool emitWarp = emitPipe != 0 && [] { const char* e = getenv("SVB_EMIT_WARP"); return !(e && e[0] == '0'); }();   // warp-granular emit (k_emit_warp)
 	const bool starStore = [] { const char* e = getenv("SVB_STAR_STORE"); return !(e && e[0] == '0'); }();   // first touch of the children of a node's own first-touch pair by plain store
@@ -1015,7 +1124,8 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		L.childBase.reset(pool, L.n);
 		// algorithmic bytes: 9 B read (code, mask) + 4 B childBase written per node, 8 B code written per child node
 		const int pidC = prof ? prof->begin("children", (uint32_t)l, L.n) : -1;
-		if (childrenPipe) k_children<true><<<blocks_for(L.n, VX_TILE), VX_THREADS, 0, s>>>(L.n, L.code.p, L.mask.p, nodeOffs.p, L.childBase.p, C.code.p);
+		if (childrenTma) k_children_tma<<<blocks_for(L.n, VX_TILE), VX_THREADS, 0, s>>>(L.n, L.code.p, L.mask.p, nodeOffs.p, L.childBase.p, C.code.p);
+		else if (childrenPipe) k_children<true><<<blocks_for(L.n, VX_TILE), VX_THREADS, 0, s>>>(L.n, L.code.p, L.mask.p, nodeOffs.p, L.childBase.p, C.code.p);
 		else k_children<false><<<blocks_for(L.n, VX_TILE), VX_THREADS, 0, s>>>(L.n, L.code.p, L.mask.p, nodeOffs.p, L.childBase.p, C.code.p);
 		SVB_KERNEL_CHECK();
 		if (prof) prof->end(pidC, Nn, 13.0 * (double)L.n + 8.0 * (double)Nn);
