@@ -198,6 +198,24 @@ int64_t svb_encode_levels(uint32_t levels, const uint64_t* counts, const uint8_t
  * [start[l], start[l+1]); level 0 (the root) is not sorted.  order[start[l] + r] = index of the node at rank r. */
 int svb_ssvdag_order_from_refs(const uint32_t* refs, const uint32_t* start, uint32_t nLevels, uint32_t* order);
 
+/* ---- material-id leaves + Gray-coded attribute bit-trees (BASELINE.json configs[3]) -------------------
+ * svb_build_svo_materials = GeomOctree::buildSVO(levels, bbox, false, NULL, putMaterialIdInLeaves = true)
+ * (geom_octree.cpp:171-280): while voxelizing triangle iTri the reference stores Scene::getTriangleMaterialId(iTri) in the
+ * leaf node's child slot of every voxel the triangle touches (:210-211, :252), so a voxel keeps the material of the LAST
+ * triangle in file order that touches it.  triMaterial: host array, one id per triangle.  *nLeafNodes = nNodesLastLevSVO.
+ * svb_download_leaf_materials copies the leaf level out IN THE REFERENCE'S NODE ORDER: mask[n], material8[n * 8] with
+ * SVB_NULL_NODE in the slots of unset voxels -- exactly `_data[levels-1][i].childrenBitmask / .children[0..7]` after the
+ * call (pinned against the unmodified reference through oracle/ref_attr_driver.cpp).
+ * svb_attribute_bit_trees is SELF-SPECIFIED (the reference names the idea in readme.md:8 and ships no code): the attribute
+ * code of a voxel is its material id (gray = 0) or the reflected Gray code of it (gray = 1, svb_gray_code); bit-tree b is
+ * the sparse voxel DAG of the voxels whose code has bit b set, reduced per level like the geometry; nodes[b] / voxels[b]
+ * (either may be NULL except nodes) receive its node count (root included, 0 for an empty tree) and voxel count. */
+int svb_build_svo_materials(svb_ctx* ctx, uint32_t levels, const double bbox_min[3], const double bbox_max[3],
+                            const uint32_t* triMaterial, uint64_t* nLeafNodes);
+int svb_download_leaf_materials(svb_ctx* ctx, uint8_t* mask, uint32_t* material8);
+int svb_attribute_bit_trees(svb_ctx* ctx, uint32_t nbits, int gray, uint64_t* nodes, uint64_t* voxels);
+uint32_t svb_gray_code(uint32_t a);
+
 /* Per-kernel profile of the last svb_build/svb_to_sdag (enabled by svb_set_profiling(ctx,1)):
  * one record per dedup-family launch group, with the algorithmic byte count SURVEY.md §8(d)
  * assigns to it.  Used by bench.py for the roofline object. */

@@ -25,7 +25,7 @@ NULLNODE = 0xFFFFFFFE
 
 def build(ref: bool = True) -> None:
     """(Re)build the oracle library (and the reference binary when /root/reference exists)."""
-    targets = ["oracle"] + (["ref"] if ref else [])
+    targets = ["oracle"] + (["ref", "ref_attr"] if ref else [])
     subprocess.run(["make", "-C", str(HERE)] + targets, check=True, stdout=subprocess.DEVNULL)
 
 
@@ -43,6 +43,7 @@ def lib() -> C.CDLL:
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_build.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p]
         L.orc_build_svo_only.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]
+        L.orc_build_svo_materials.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_to_dag.argtypes = [C.c_void_p]
         L.orc_to_sdag.argtypes = [C.c_void_p]
         L.orc_cross_merge.argtypes = [C.c_void_p]
@@ -89,6 +90,17 @@ class OracleOctree:
         rc = lib().orc_build(self.h, levels, step, lo.ctypes.data, hi.ctypes.data)
         if rc != 0:
             raise RuntimeError("orc_build failed")
+
+    def build_svo_materials(self, levels: int, materials, bbox=None):
+        """buildSVO(levels, bbox, false, NULL, putMaterialIdInLeaves=true): returns (mask (n,), material (n, 8)) of the leaf
+        level in SVO node order; material slots of unset voxels hold 0xFFFFFFFE (nullNode)."""
+        lo, hi = bbox if bbox is not None else self.scene_bbox()
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        m = np.ascontiguousarray(materials, dtype=np.uint32)
+        lib().orc_build_svo_materials(self.h, levels, lo.ctypes.data, hi.ctypes.data, m.ctypes.data)
+        lv = self.level(levels - 1)
+        return lv["mask"], lv["child"]
 
     def to_sdag(self) -> None:
         lib().orc_to_sdag(self.h)
@@ -182,6 +194,32 @@ def run_reference(workdir, tris: np.ndarray, levels: int, step: int, cross: bool
         if f.exists():
             files[ext] = f.read_bytes()
     return {"files": files, "log": p.stdout, "seconds": dt}
+
+
+ATTR_BIN = HERE / "_ref" / "ref_attr_driver"
+
+
+def run_reference_materials(workdir, tris: np.ndarray, materials, levels: int, name: str = "m", timeout: float | None = None):
+    """The unmodified reference's buildSVO with putMaterialIdInLeaves = true (through oracle/ref_attr_driver.cpp):
+    returns (mask (n,), material (n, 8)) of its leaf level, in its node order."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_svb_meshgen", HERE.parent / "svdag-compression_b200" / "meshgen.py")
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    if not ATTR_BIN.exists():
+        raise FileNotFoundError(f"{ATTR_BIN} missing: run `make -C oracle ref_attr` where /root/reference exists")
+    wd = Path(workdir)
+    wd.mkdir(parents=True, exist_ok=True)
+    obj = wd / f"{name}.obj"
+    mg.write_scene(obj, tris, materials=np.asarray(materials))
+    out = wd / f"{name}_leaves.bin"
+    p = subprocess.run([str(ATTR_BIN), str(obj), str(levels), str(out)], cwd=wd, capture_output=True, text=True, timeout=timeout)
+    if p.returncode != 0:
+        raise RuntimeError(f"ref_attr_driver failed rc={p.returncode}\n{p.stdout[-2000:]}\n{p.stderr[-2000:]}")
+    raw = out.read_bytes()
+    n = int(np.frombuffer(raw[:8], dtype=np.uint64)[0])
+    rec = np.frombuffer(raw[8:8 + 33 * n], dtype=np.dtype([("mask", "u1"), ("child", "<u4", (8,))]))
+    return rec["mask"].copy(), rec["child"].copy()
 
 
 # ------------------------------------------------------------------ DDA ray caster (oracle/dda_oracle.c)

@@ -168,7 +168,9 @@ struct Oct {
 	double halfSideD(unsigned level) const { return double(rootSide) / double(1u << (level + 1)); }  // octree.hpp:115
 
 	// geom_octree.cpp:171-280
-	void buildSVO(unsigned lv, const double bmin[3], const double bmax[3], std::vector<std::array<double, 3>>* leavesCenters) {
+	// triMat (optional): putMaterialIdInLeaves = true (geom_octree.cpp:210-211, :252): the leaf node's child slot of a voxel holds
+	// the material id of the triangle being voxelized, i.e. finally that of the LAST triangle (file order) touching the voxel
+	void buildSVO(unsigned lv, const double bmin[3], const double bmax[3], std::vector<std::array<double, 3>>* leavesCenters, const uint32_t* triMat = nullptr) {
 		for (int k = 0; k < 3; ++k) { bboxF[k] = float(bmin[k]); bboxF[3 + k] = float(bmax[k]); }
 		levels = lv;
 		float sides[3];
@@ -208,7 +210,7 @@ struct Oct {
 						Item it; it.id = data[qi.level][qi.id].ch[i]; it.level = uint8_t(qi.level + 1);
 						it.c[0] = cc[i][0]; it.c[1] = cc[i][1]; it.c[2] = cc[i][2];
 						stack.push_back(it);
-					}
+					} else if (triMat) data[qi.level][qi.id].ch[i] = triMat[t];   // :252
 				}
 			}
 		}
@@ -645,6 +647,10 @@ int orc_build(void* h, unsigned levels, unsigned step, const double bmin[3], con
 }
 int orc_build_svo_only(void* h, unsigned levels, const double bmin[3], const double bmax[3]) {
 	((Oct*)h)->buildSVO(levels, bmin, bmax, nullptr);
+	return 0;
+}
+int orc_build_svo_materials(void* h, unsigned levels, const double bmin[3], const double bmax[3], const uint32_t* triMat) {
+	((Oct*)h)->buildSVO(levels, bmin, bmax, nullptr, triMat);
 	return 0;
 }
 int orc_to_dag(void* h) { Oct* o = (Oct*)h; o->toDAG(true); o->initChildLevels(); return 0; }

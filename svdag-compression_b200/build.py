@@ -18,7 +18,7 @@ SVBUILDER = HERE / "svbuilder"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = "/usr/bin/g++"   # the environment's CXX points at a compiler without libgomp; pin the system one
 
-CU_SOURCES = ["svb_prims.cu", "svb_voxelize.cu", "svb_dedup.cu", "svb_sdag.cu", "svb_cross.cu", "svb_encode.cu", "svb_api.cu", "svb_raycast.cu", "host/encoders.cpp"]
+CU_SOURCES = ["svb_prims.cu", "svb_voxelize.cu", "svb_dedup.cu", "svb_sdag.cu", "svb_cross.cu", "svb_encode.cu", "svb_attr.cu", "svb_api.cu", "svb_raycast.cu", "host/encoders.cpp"]
 # the ray caster must round every float operation separately (pixel-exact against oracle/dda_oracle.c)
 EXTRA_FLAGS = {"svb_raycast.cu": ["--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false"]}
 NVCC_FLAGS = [

@@ -88,6 +88,11 @@ def lib() -> C.CDLL:
         L.svb_shard_export_roots.argtypes = [vp, vp]
         L.svb_shard_import_roots.argtypes = [vp, vp]
         L.svb_shard_finish.argtypes = [vp, vp, C.POINTER(Stats)]
+        L.svb_build_svo_materials.argtypes = [vp, u32, vp, vp, vp, C.POINTER(u64)]
+        L.svb_download_leaf_materials.argtypes = [vp, vp, vp]
+        L.svb_attribute_bit_trees.argtypes = [vp, u32, C.c_int, vp, vp]
+        L.svb_gray_code.argtypes = [u32]
+        L.svb_gray_code.restype = u32
         L.svb_set_profiling.argtypes = [vp, C.c_int]
         L.svb_profile_count.argtypes = [vp]
         L.svb_profile_get.argtypes = [vp, C.c_int, C.POINTER(ProfRec)]
@@ -264,6 +269,28 @@ class GeomOctree:
         bb = np.ascontiguousarray(bboxF, dtype=np.float32)
         self._check(self._L.svb_upload_levels(self._h, len(levels), counts.ctypes.data, mask.ctypes.data, child.ctypes.data,
                                               bb.ctypes.data, float(root_side), int(n_voxels)))
+
+    # ---- material-id leaves + attribute bit-trees (include/svb.h)
+    def build_svo_materials(self, levels: int, materials, bbox=None):
+        """buildSVO(levels, bbox, false, NULL, putMaterialIdInLeaves=true): (mask (n,), material (n, 8)) of the leaf level in
+        the reference's node order; unset voxels hold 0xFFFFFFFE."""
+        lo, hi = bbox if bbox is not None else self.scene_bbox()
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        m = np.ascontiguousarray(materials, dtype=np.uint32)
+        n = C.c_uint64()
+        self._check(self._L.svb_build_svo_materials(self._h, levels, lo.ctypes.data, hi.ctypes.data, m.ctypes.data, C.byref(n)))
+        mask = np.zeros(int(n.value), np.uint8)
+        mat = np.zeros((int(n.value), 8), np.uint32)
+        self._check(self._L.svb_download_leaf_materials(self._h, mask.ctypes.data, mat.ctypes.data))
+        return mask, mat
+
+    def attribute_bit_trees(self, nbits: int, gray: bool):
+        """(nodes[nbits], voxels[nbits]) of the bit-trees of the last build_svo_materials (self-specified)."""
+        nodes = np.zeros(nbits, np.uint64)
+        vox = np.zeros(nbits, np.uint64)
+        self._check(self._L.svb_attribute_bit_trees(self._h, nbits, 1 if gray else 0, nodes.ctypes.data, vox.ctypes.data))
+        return nodes, vox
 
     # ---- instrumentation
     def set_profiling(self, on=True):

@@ -12,6 +12,7 @@
 #include <cstring>
 
 #include "svb_context.cuh"
+#include "svb_attr.cuh"
 #include "svb_cross.cuh"
 #include "host/octree_data.hpp"
 #include "svb_dedup.cuh"
@@ -451,6 +452,7 @@ void build_local(svb_ctx* c, uint32_t L, uint32_t step, const double bmin[3], co
 	if (world == 0 || rank >= world) throw Error(SVB_EINVAL, "bad rank/world");
 	if (world > 1 && step == 0) throw Error(SVB_EINVAL, "a sharded build needs step > 0 (sub-octrees are the unit of distribution)");
 	c->out.clear();
+	c->attr.reset();
 	c->state = SVB_S_EMPTY;
 	if (!c->profAccumulate) c->prof.clear();
 	c->lastImageKind = -1;
@@ -821,6 +823,8 @@ void svb_destroy(svb_ctx* c) {
 	if (!c) return;
 	cudaSetDevice(c->device);
 	c->out.clear();
+	c->attr.reset();
+	c->build.reset();
 	c->trisOwned.release();
 	cudaStreamSynchronize(c->stream);
 	c->image.release();
@@ -1255,6 +1259,27 @@ int svb_load_svdag(svb_ctx* c, const uint8_t* file, uint64_t size, svb_stats* ou
 	}
 	return rc;
 }
+
+// ---- material-id leaves + Gray-coded attribute bit-trees (svb_attr.cu)
+int svb_build_svo_materials(svb_ctx* c, uint32_t levels, const double bmin[3], const double bmax[3], const uint32_t* triMaterial, uint64_t* nLeafNodes) {
+	int rc = guarded(c, [&] {
+		if (!bmin || !bmax) throw Error(SVB_EINVAL, "null bbox");
+		with_hash_retries(c, [&] { attr_build(c, levels, bmin, bmax, triMaterial); });
+		if (nLeafNodes) *nLeafNodes = attr_leaf_count(c);
+	});
+	if (rc != SVB_OK && c) c->attr.reset();
+	return rc;
+}
+int svb_download_leaf_materials(svb_ctx* c, uint8_t* mask, uint32_t* material8) {
+	return guarded(c, [&] { attr_download(c, mask, material8); });
+}
+int svb_attribute_bit_trees(svb_ctx* c, uint32_t nbits, int gray, uint64_t* nodes, uint64_t* voxels) {
+	return guarded(c, [&] {
+		if (!nodes) throw Error(SVB_EINVAL, "null output");
+		with_hash_retries(c, [&] { attr_bit_trees(c, nbits, gray, nodes, voxels); });
+	});
+}
+uint32_t svb_gray_code(uint32_t a) { return a ^ (a >> 1); }
 
 int svb_set_profiling(svb_ctx* c, int enabled) {
 	if (!c) return SVB_EINVAL;

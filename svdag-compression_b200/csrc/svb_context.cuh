@@ -5,6 +5,7 @@
 #include "svb_internal.cuh"
 
 struct svb_build_state;   // svb_api.cu: tables and tile list a build keeps between its phases
+struct svb_attr_state;    // svb_attr.cu: the SVO of an attribute build (material-id leaves, bit-trees)
 
 // page-locked host buffer owned by a context: D2H / H2D copies run at full PCIe rate and without a bounce buffer
 struct PinnedBuf {
@@ -56,5 +57,6 @@ struct svb_ctx {
 	uint64_t imageSize = 0;
 	int lastImageKind = -1;
 	std::shared_ptr<svb_build_state> build;   // non-null between svb_shard_build and svb_shard_finish
+	std::shared_ptr<svb_attr_state> attr;     // non-null after svb_build_svo_materials
 	svb_ctx() { memset(&stats, 0, sizeof(stats)); }
 };

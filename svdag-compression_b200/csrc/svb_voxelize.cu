@@ -83,14 +83,15 @@ __global__ void __launch_bounds__(VX_THREADS) k_candidates(const float* __restri
 // (geom_octree.cpp:222-230), so it carries exactly the reference's roundings for any bbox.
 __global__ void __launch_bounds__(VX_THREADS) k_classify(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
                                                           const uint64_t* __restrict__ code, int l, const TileGeom* __restrict__ tiles,
-                                                          const float* __restrict__ tris, const uint32_t* __restrict__ rootTri, uint8_t* __restrict__ hit, uint8_t* __restrict__ mask, int last) {
+                                                          const float* __restrict__ tris, const uint32_t* __restrict__ rootTri, uint8_t* __restrict__ hit, uint8_t* __restrict__ mask, int last,
+                                                          uint32_t* __restrict__ lastTri = nullptr) {
 	uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	uint64_t p = gid >> 3;
 	int c = (int)(gid & 7);
 	bool ok = false;
-	uint32_t n = 0;
+	uint32_t n = 0, t = 0;
 	if (p < P) {
-		uint32_t t = rootTri[ptri[p]];
+		t = rootTri[ptri[p]];
 		n = pnode[p];
 		uint64_t cd = code[n];
 		uint32_t tile = (uint32_t)(cd >> (3 * l));
@@ -108,6 +109,8 @@ __global__ void __launch_bounds__(VX_THREADS) k_classify(uint64_t P, const uint3
 		cy = __dadd_rn(cy, (c & 2) ? k : -k);
 		cz = __dadd_rn(cz, (c & 1) ? k : -k);
 		ok = tri_box_overlap(cx, cy, cz, k, tris + 9ull * t);
+		// leaf level of an attribute build: the LAST triangle (file order) that touches voxel c of leaf node n (1-based; 0 = none)
+		if (ok && lastTri) atomicMax(&lastTri[(uint64_t)n * 8 + c], t + 1);
 	}
 	unsigned b = __ballot_sync(0xFFFFFFFFu, ok);
 	int lane = threadIdx.x & 31;
@@ -991,7 +994,8 @@ void batch_root_pairs(cudaStream_t s, Pool& pool, const RootPairsAll& R, uint32_
 
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
                     DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, const uint32_t* rootTri, const uint32_t* tileStart, uint64_t P,
-                    uint64_t budget_bytes, uint64_t nodeCap, std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre, bool allFlat, int untracked, ProfHook* prof) {
+                    uint64_t budget_bytes, uint64_t nodeCap, std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre, bool allFlat, int untracked, ProfHook* prof,
+                    DevBuf<uint32_t>* leafLastTri) {
 	if (const char* e = getenv("SVB_CENTRE")) directCentre = directCentre && e[0] != 'c';   // SVB_CENTRE=chain: always replay the chain
 	lv.clear();
 	lv.resize(Lt);
@@ -1007,7 +1011,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 	uint64_t F = 0, Fa = 0, S = P;
 	DevBuf<uint16_t> pflags(pool, P + 16);   // settled-axis flags per pair (svb_classify.cuh)
 	pflags.zero();
-	const bool exactOnly = classify_exact_only();
+	const bool exactOnly = classify_exact_only() || leafLastTri != nullptr;   // attribute builds decide every voxel with the reference-order predicate, one lane per voxel
 	// k_emit variant: 0 = one chunk at a time, else software-pipelined (read per batch, not cached: A/B inside one process)
 	const bool childrenPipe = [] { const char* e = getenv("SVB_CHILDREN_PIPE"); return !(e && e[0] == '0'); }();
 	const bool childrenTma = childrenPipe && [] { const char* e = getenv("SVB_CHILDREN_TMA"); return !(e && e[0] == '0'); }();   // cp.async.bulk + mbarrier pipeline (k_children_tma)
@@ -1045,8 +1049,11 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		}
 		if (S) {
 			const uint32_t* st = ptri.p + Fa; const uint32_t* sn = pnode.p + Fa; uint16_t* sf = pflags.p + Fa; uint8_t* sh = hit.p + (last ? 0 : Fa);
-			if (exactOnly)
-				k_classify<<<blocks_for(S * 8, VX_THREADS), VX_THREADS, 0, s>>>(S, st, sn, L.code.p, l, d_tiles, d_tris, rootTri, sh, L.mask.p, last);
+			if (exactOnly) {
+				uint32_t* lt = nullptr;
+				if (last && leafLastTri) { leafLastTri->reset(pool, L.n * 8 + 8); leafLastTri->zero(); lt = leafLastTri->p; }
+				k_classify<<<blocks_for(S * 8, VX_THREADS), VX_THREADS, 0, s>>>(S, st, sn, L.code.p, l, d_tiles, d_tris, rootTri, sh, L.mask.p, last, lt);
+			}
 			else {
 				unsigned nb = blocks_for(S, VX_THREADS);
 #define SVB_LAUNCH_CF3(OCC, DIR, FLAT, LST) k_classify_filtered<OCC, DIR, FLAT, LST><<<nb, VX_THREADS, 0, s>>>(S, st, sn, sf, L.code.p, l, kscale, last, d_tiles, d_tris, rootTri, sh, L.mask.p, (unsigned long long*)d_nExact, precheck)

@@ -55,7 +55,10 @@ uint32_t max_candidates_per_tile(cudaStream_t s, Pool& pool, const float* d_tris
 void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileGeom* d_tiles, uint32_t ntiles, int Lt,
                     DevBuf<uint32_t>& ptri, DevBuf<uint32_t>& pnode, const uint32_t* rootTri, const uint32_t* tileStart, uint64_t P,
                     uint64_t budget_bytes, uint64_t nodeCap, std::vector<BatchLevel>& lv, uint64_t& pairsTotal, uint64_t* d_nExact, bool directCentre, bool allFlat,
-                    int untracked = 0, ProfHook* prof = nullptr);
+                    int untracked = 0, ProfHook* prof = nullptr, DevBuf<uint32_t>* leafLastTri = nullptr);
+// leafLastTri (attribute builds, svb_attr.cu): receives, per leaf node and voxel, 1 + the index of the LAST triangle in file
+// order that touches the voxel (0: none) -- what GeomOctree::buildSVO(..., putMaterialIdInLeaves = true) keeps
+// (geom_octree.cpp:210-211, :252).  Implies the exact classifier (every voxel decided by its own lane).
 // prof: per-launch records "emit" (n_in = parent pairs, n_out = child pairs) and "children" (n_in = nodes, n_out = child nodes)
 // with their algorithmic bytes.
 // untracked = 1: the first touches of the deepest level are not tracked (lv[Lt-1].tstar stays empty); 2: nor those of the

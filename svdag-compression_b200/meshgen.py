@@ -255,34 +255,53 @@ def write_obj(path, tris: np.ndarray) -> None:
             f.write("f %d %d %d\n" % (3 * k + 1, 3 * k + 2, 3 * k + 3))
 
 
-def write_bincache(path, tris: np.ndarray) -> None:
+def write_bincache(path, tris: np.ndarray, materials=None) -> None:
     """`<obj>.bincache` as `Scene::saveBinObj` writes it (scene.cpp:324-348): 56-byte
-    header, float32 vertices, one 300-byte default material, 56-byte indexed triangles."""
+    header, float32 vertices, 300-byte materials (one default material unless `materials` -- a per-triangle array of
+    material indices, scene.hpp:41-45 `TIndexedTri::material` -- asks for more), 56-byte indexed triangles."""
     tris = np.asarray(tris, dtype=np.float32).reshape(-1, 3, 3)
     nt = tris.shape[0]
     verts = tris.reshape(-1, 3)
     lo = verts.min(axis=0)
     hi = verts.max(axis=0)
+    nmat = 1 if materials is None else int(np.max(materials)) + 1
     with open(path, "wb") as f:
-        f.write(struct.pack("<4Q6f", nt * 3, 0, 1, nt, *[float(x) for x in lo], *[float(x) for x in hi]))
+        f.write(struct.pack("<4Q6f", nt * 3, 0, nmat, nt, *[float(x) for x in lo], *[float(x) for x in hi]))
         f.write(verts.astype("<f4").tobytes())
-        name = b"Voxelator Default Mat"
-        mat = name + b"\0" * (256 - len(name))
-        mat += struct.pack("<9f", 0.9, 0.9, 0.9, 0.2, 0.2, 0.2, 0.1, 0.1, 0.1)
-        mat += struct.pack("<2f", 0.0, 0.0)
-        assert len(mat) == 300
-        f.write(mat)
+        for k in range(nmat):
+            name = b"Voxelator Default Mat" if nmat == 1 else b"mat%d" % k
+            mat = name + b"\0" * (256 - len(name))
+            mat += struct.pack("<9f", 0.9, 0.9, 0.9, 0.2, 0.2, 0.2, 0.1, 0.1, 0.1)
+            mat += struct.pack("<2f", 0.0, 0.0)
+            assert len(mat) == 300
+            f.write(mat)
         idx = np.zeros((nt, 7), dtype="<u8")
         idx[:, 0:3] = np.arange(nt * 3, dtype=np.uint64).reshape(nt, 3)
+        if materials is not None:
+            idx[:, 6] = np.asarray(materials, dtype=np.uint64)
         f.write(idx.tobytes())
 
 
-def write_scene(obj_path, tris: np.ndarray, ascii_obj: bool = False) -> Path:
+def materials_for(tris: np.ndarray, n_materials: int = 13, seed: int = 99) -> np.ndarray:
+    """Synthetic per-triangle material ids: runs of consecutive triangles share a material (as the faces of one object do
+    in an OBJ with `usemtl` groups), ids in [0, n_materials)."""
+    nt = int(np.asarray(tris).reshape(-1, 9).shape[0])
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = np.zeros(nt, np.uint32)
+    i = 0
+    while i < nt:
+        run = int(rng.integers(1, 40))
+        out[i:i + run] = rng.integers(0, n_materials)
+        i += run
+    return out
+
+
+def write_scene(obj_path, tris: np.ndarray, ascii_obj: bool = False, materials=None) -> Path:
     """Write `<obj_path>` (a stub unless ascii_obj) and `<obj_path>.bincache`."""
     obj_path = Path(obj_path)
     if ascii_obj:
         write_obj(obj_path, tris)
     else:
         obj_path.write_text("# geometry lives in the .bincache next to this file\n")
-    write_bincache(str(obj_path) + ".bincache", tris)
+    write_bincache(str(obj_path) + ".bincache", tris, materials)
     return obj_path
