@@ -629,3 +629,26 @@ def test_merge_collision_is_reported_to_every_rank_and_retried(pkg, meshgen, mon
     octs, _ = _simulate_ranks(pkg, tris, 9, 2, 3, merge_seed=1)
     for r, oc in enumerate(octs):
         _assert_levels_equal(oc.levels_host(), want, f"rank {r} after the merge retry")
+
+
+def test_context_on_a_caller_owned_stream(pkg, orc, meshgen):
+    """svb_create_on_stream: the context enqueues everything on a stream the host owns (here a torch stream, as bench.py does
+    for the multi-rank build); same octree, and the stream is still usable after the context is gone."""
+    import torch
+    tris = meshgen.make_mesh("city", lots=8)
+    o = orc.OracleOctree(tris)
+    o.build(9, 2)
+    ts = torch.cuda.Stream()
+    t = pkg.GeomOctree(tris, stream=ts)
+    assert t.stream_ptr() == ts.cuda_stream
+    st = t.build(9, 2)
+    assert st["nNodesDAG"] == o.stat("nNodesDAG")
+    _assert_levels_equal(t.levels_host(), _oracle_levels(o), "DAG built on a torch stream")
+    t.to_sdag()
+    o.to_sdag()
+    assert pkg.encoders.encode(t, "ssvdag") == o.encode("ssvdag")
+    t.close()
+    with torch.cuda.stream(ts):
+        x = torch.ones(1024, device="cuda").sum()
+    ts.synchronize()
+    assert float(x) == 1024.0
