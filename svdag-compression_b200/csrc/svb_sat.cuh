@@ -32,6 +32,22 @@
 #define SVB_FMA(a, b, c) __fma_rn((a), (b), (c))
 #define SVB_FFS(x) __ffs(x)
 #define SVB_POPC(x) __popc(x)
+#elif defined(SVB_HOST_STRICT_OPS)
+// host pass of the SECOND test harness, built with -ffp-contract=fast -mfma so that every plain a * b + c of the interval
+// filter is contracted into an FMA, as nvcc contracts it on the device (85-108 DFMA per k_classify_filtered instantiation):
+// the explicitly rounded operations go through out-of-line functions that hold a single operation each -- nothing to
+// contract with -- and stay separately rounded, like __dadd_rn / __dmul_rn on the device.
+namespace svb { namespace hostops {
+__attribute__((noinline)) inline double add(double a, double b) { return a + b; }
+__attribute__((noinline)) inline double sub(double a, double b) { return a - b; }
+__attribute__((noinline)) inline double mul(double a, double b) { return a * b; }
+} }
+#define SVB_DADD(a, b) ::svb::hostops::add((double)(a), (double)(b))
+#define SVB_DSUB(a, b) ::svb::hostops::sub((double)(a), (double)(b))
+#define SVB_DMUL(a, b) ::svb::hostops::mul((double)(a), (double)(b))
+#define SVB_FMA(a, b, c) std::fma((double)(a), (double)(b), (double)(c))
+#define SVB_FFS(x) __builtin_ffs((int)(x))
+#define SVB_POPC(x) __builtin_popcount((unsigned)(x))
 #else   // host pass: plain IEEE operations; the translation unit must be built with -ffp-contract=off
 #define SVB_DADD(a, b) ((double)(a) + (double)(b))
 #define SVB_DSUB(a, b) ((double)(a) - (double)(b))

@@ -15,14 +15,26 @@ SRC = ROOT / "tests" / "harness" / "classify_harness.cpp"
 OUT = ROOT / "tests" / "harness" / "build" / "libclassify_harness.so"
 
 
-@pytest.fixture(scope="module")
-def harness():
+# Two builds of the same source.  "separate": every operation rounded on its own (-ffp-contract=off).  "contracted": the
+# filter's plain a * b + c expressions fused into FMAs (-ffp-contract=fast -mfma), which is how nvcc compiles them for the
+# device, while the explicitly rounded operations of the predicate and the centre chain stay single operations
+# (SVB_HOST_STRICT_OPS, svb_sat.cuh).  The filter's 2^-40 margin must make its verdicts independent of that choice.
+@pytest.fixture(scope="module", params=["separate", "contracted"])
+def harness(request):
     OUT.parent.mkdir(exist_ok=True)
+    contracted = request.param == "contracted"
+    if contracted and " fma " not in Path("/proc/cpuinfo").read_text().replace("\n", " "):
+        pytest.skip("host CPU without FMA")
+    out = OUT.with_name("libclassify_harness_fma.so") if contracted else OUT
     deps = [SRC] + list((ROOT / "svdag-compression_b200" / "csrc").glob("svb_*.cuh"))
-    if not OUT.exists() or any(d.stat().st_mtime > OUT.stat().st_mtime for d in deps):
-        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
-                        str(SRC), "-o", str(OUT)], check=True)
-    L = C.CDLL(str(OUT))
+    if not out.exists() or any(d.stat().st_mtime > out.stat().st_mtime for d in deps):
+        flags = ["-ffp-contract=fast", "-mfma", "-DSVB_HOST_STRICT_OPS"] if contracted else ["-ffp-contract=off"]
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17"] + flags + ["-fPIC", "-shared", "-Wno-unknown-pragmas",
+                        str(SRC), "-o", str(out)], check=True)
+    if contracted:   # the build really contains fused multiply-adds (and the predicate's operations really are out of line)
+        dis = subprocess.run(["objdump", "-d", "--no-show-raw-insn", str(out)], capture_output=True, text=True).stdout
+        assert dis.count("vfmadd") + dis.count("vfmsub") + dis.count("vfnmadd") > 20, "no FMA contraction in the contracted harness"
+    L = C.CDLL(str(out))
     L.harness_run.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.harness_chain_exact.argtypes = [C.c_void_p, C.c_double, C.c_int]
     return L
