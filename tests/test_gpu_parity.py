@@ -133,7 +133,9 @@ def test_empty_scene(pkg):
     ("city", dict(lots=16), 10, 3),
     ("terrain", dict(n=128), 10, 2),
     ("sphere_menger", dict(n_lat=48, n_lon=96, sponge_level=2), 9, 0),
-], ids=["city", "terrain", "spongeball"])
+    ("terrain", dict(n=1024), 12, 3),        # BASELINE configs[1] at full size: 2.09 M general triangles at 4096^3
+    ("composite_crop", dict(n_terrain=257, lots=64, octant=0), 11, 2),   # terrain under axis-aligned boxes
+], ids=["city", "terrain", "spongeball", "terrain4k", "composite-crop"])
 def test_filtered_classifier_equals_exact_predicate(pkg, meshgen, mesh, kw, levels, step, monkeypatch):
     """The FP64 interval filter in front of the SAT predicate must never change a decision: a build
     with every child decided by the reference-order predicate (SVB_CLASSIFY=exact) gives the same
