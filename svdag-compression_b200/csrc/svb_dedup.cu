@@ -188,13 +188,19 @@ __global__ void __launch_bounds__(DD_THREADS) k_leaf_min(DedupArgs a, unsigned l
 // count): 1 B/node instead of 13 for all but the first nodes of each mask.  Loads are skipped per 4-node quad, i.e. per
 // 16 B of t* / 32 B of codes, so whole DRAM sectors stay untouched.  Skipping is only ever a filter on nodes that
 // provably lose; the 64-bit minimum itself is taken exactly as in MODE 0.
-__global__ void __launch_bounds__(DD_THREADS) k_leaf_lazy(DedupArgs a, unsigned long long* __restrict__ gmin, unsigned long long* __restrict__ voxels, int later) {
+// gminBefore: the table as it was BEFORE this launch.  "Frozen" must be decided on that snapshot, never on the live table: the
+// grid does not fit the machine at once (48 registers: 5 CTAs/SM resident out of 8 launched per SM), so late CTAs start
+// after early ones have already merged their minima -- a voxel mask that is NEW in this batch would look frozen to them, and
+// they would skip nodes that may hold its smallest order key.  (Round-1 bug, found in round 2 when warm-up batches made new
+// masks in "later" batches common on terrain-like scenes: tests/golden/size_composite_crop4k.json under low free memory.)
+__global__ void __launch_bounds__(DD_THREADS) k_leaf_lazy(DedupArgs a, unsigned long long* __restrict__ gmin, const unsigned long long* __restrict__ gminBefore,
+                                                           unsigned long long* __restrict__ voxels, int later) {
 	__shared__ unsigned long long smin[256];
 	__shared__ uint32_t sq[256];        // smallest t* seen for the mask by this CTA
 	__shared__ uint8_t sfrozen[256];
 	smin[threadIdx.x] = MAX_ORDER;
 	sq[threadIdx.x] = 0xFFFFFFFFu;
-	sfrozen[threadIdx.x] = (later && gmin[threadIdx.x] != MAX_ORDER) ? 1 : 0;
+	sfrozen[threadIdx.x] = (later && gminBefore[threadIdx.x] != MAX_ORDER) ? 1 : 0;
 	if (threadIdx.x == 0) sfrozen[0] = 1;   // empty nodes take no part
 	__syncthreads();
 	unsigned vox = 0;
@@ -846,8 +852,11 @@ void dedup_leaf(cudaStream_t s, Pool& pool, LevelTable& T, const DedupArgs& a, u
 	const bool later = later_batch(T, a);
 	if (!T.wide) {
 		const char* e = getenv("SVB_LEAF_LAZY");   // 0: stream all 13 B of every node (k_leaf_min<0>)
-		if (a.seqMonotone && !(e && e[0] == '0')) k_leaf_lazy<<<nb, DD_THREADS, 0, s>>>(a, g, (unsigned long long*)d_voxels, later ? 1 : 0);
-		else k_leaf_min<0><<<nb, DD_THREADS, 0, s>>>(a, g, (unsigned long long*)d_voxels);
+		DevBuf<uint64_t> snapshot(pool, 256);   // the table before this launch (freed after the read-back below has synchronised)
+		if (a.seqMonotone && !(e && e[0] == '0')) {
+			SVB_CUDA(cudaMemcpyAsync(snapshot.p, T.minO.p, 256 * 8, cudaMemcpyDeviceToDevice, s));
+			k_leaf_lazy<<<nb, DD_THREADS, 0, s>>>(a, g, (const unsigned long long*)snapshot.p, (unsigned long long*)d_voxels, later ? 1 : 0);
+		} else k_leaf_min<0><<<nb, DD_THREADS, 0, s>>>(a, g, (unsigned long long*)d_voxels);
 		SVB_KERNEL_CHECK();
 		// did this batch bring new voxel masks?  (leaf_tstar_needed: the next batch goes without first touches only if not)
 		DevBuf<uint32_t> cnt(pool, 1);

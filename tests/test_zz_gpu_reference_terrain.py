@@ -76,3 +76,25 @@ def test_composite_octant_sharded_build_equals_reference(pkg, meshgen):
     assert hashlib.sha256(pkg.encoders.encode(t, "svdag")).hexdigest() == g["files"]["svdag"]["sha256"]
     assert t.to_sdag()["nNodesSDAG"] == g["SDAG Nodes"]
     assert hashlib.sha256(pkg.encoders.encode(t, "ssvdag")).hexdigest() == g["files"]["ssvdag"]["sha256"]
+
+
+@pytest.mark.skipif(not CROP.exists(), reason="tests/golden/size_composite_crop4k.json not minted")
+@pytest.mark.parametrize("budget_mb", [192, 384, 768, 1536], ids=lambda b: f"{b}MB")
+def test_composite_octant_equals_reference_under_any_batch_plan(pkg, meshgen, budget_mb):
+    """The result must not depend on how the sub-octrees are cut into tile batches.  Regression test of a round-1 bug found in
+    round 2: the lazy leaf pass decided "this voxel mask is frozen" on the LIVE table, which CTAs of the same launch were
+    already updating -- with batches that bring new voxel masks after the first one (terrain under boxes, several million leaf
+    nodes per batch so that the grid does not fit the machine at once) late CTAs skipped nodes that held a mask's smallest
+    order key, and the node order of the file changed with the batch plan (i.e. with the free device memory)."""
+    g = json.loads(CROP.read_text())
+    tris = meshgen.make_mesh(g["mesh"], **g["kw"])
+    v = tris.reshape(-1, 3)
+    bbox = (v.min(axis=0).astype(np.float64), v.max(axis=0).astype(np.float64))
+    t = pkg.GeomOctree(tris)
+    t.set_batch_budget(budget_mb << 20)
+    st = t.build(g["levels"], g["step"], bbox=bbox)
+    assert st["nBatches"] >= 3
+    assert (st["nTotalVoxels"], st["nNodesSVO"], st["nNodesDAG"]) == (g["Voxels"], g["SVO Nodes"], g["DAG Nodes"])
+    assert hashlib.sha256(pkg.encoders.encode(t, "svdag")).hexdigest() == g["files"]["svdag"]["sha256"]
+    t.to_sdag()
+    assert hashlib.sha256(pkg.encoders.encode(t, "ssvdag")).hexdigest() == g["files"]["ssvdag"]["sha256"]
