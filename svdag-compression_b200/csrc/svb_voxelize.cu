@@ -1000,7 +1000,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 	lv.clear();
 	lv.resize(Lt);
 	lv[0].n = ntiles;
-	lv[0].code.reset(pool, ntiles);
+	lv[0].code.reset(pool, (uint64_t)ntiles + 2);   // (+2: k_children_tma rounds its last bulk load up to 16 bytes)
 	lv[0].tstar.reset(pool, ntiles);
 	k_init_roots<<<blocks_for(ntiles, 256), 256, 0, s>>>(ntiles, lv[0].code.p, lv[0].tstar.p, tileStart);
 	SVB_KERNEL_CHECK();
@@ -1120,7 +1120,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		}
 		BatchLevel& C = lv[l + 1];
 		C.n = Nn;
-		C.code.reset(pool, Nn);
+		C.code.reset(pool, Nn + 2);   // (+2: see lv[0].code)
 		// first touches of the leaf nodes only matter for voxel masks the dedup table does not know yet: a later batch
 		// goes without them (leafTstar == false; the caller re-runs the batch in the rare case that it does meet one)
 		const bool trackKids = (l + 1 < Lt - untracked);   // untracked = 1: the leaf level, 2: the 4^3 level above it as well
