@@ -38,6 +38,7 @@ struct Shared {
 	std::vector<std::vector<uint32_t>> recBytes;
 	std::vector<std::vector<uint64_t>> counters;   // [rank][5]
 	std::vector<std::string> error;                // per rank
+	std::vector<int> collision;                    // per rank: svb_shard_finish reported a tag collision of the level merge
 	std::vector<double> msUpload, msExchange;
 	bool failed() const { for (auto& e : error) if (!e.empty()) return true; return false; }
 };
@@ -126,13 +127,20 @@ void rank_main(int rank, Shared& S, Barrier& bar, int device, svb_ctx* c, const 
 	for (int r = 0; r < world; ++r) for (int k = 0; k < 5; ++k) totals[k] += S.counters[r][k];
 	svb_stats st;
 	memset(&st, 0, sizeof(st));
-	if (S.error[rank].empty()) SV(svb_shard_finish(c, totals, &st));   // synchronises the stream: the scratch may go
-	else CU(cudaStreamSynchronize(s));
+	if (S.error[rank].empty()) {   // synchronises the stream: the scratch may go
+		const int rc = svb_shard_finish(c, totals, &st);
+		if (rc == SVB_ECOLLISION) S.collision[rank] = 1;
+		if (rc != SVB_OK) RANK_FAIL(std::string("svb_shard_finish: ") + svb_last_error(c));
+	} else CU(cudaStreamSynchronize(s));
 	S.msExchange[rank] = std::chrono::duration<double, std::milli>(clk::now() - t1).count();
 	if (rank == 0 && out) *out = st;
 }
 
 }  // namespace
+
+static bool build_once(const std::vector<int>& devices, const std::vector<svb_ctx*>& ctx, const float* tris, uint64_t ntris,
+                       unsigned levels, unsigned step, const double bmin[3], const double bmax[3], svb_stats* out, std::string* err,
+                       double* msUpload, double* msExchange, bool* collided);
 
 bool build_dag_sharded(const std::vector<int>& devices, const std::vector<svb_ctx*>& ctx, const float* tris, uint64_t ntris,
                        unsigned levels, unsigned step, const double bmin[3], const double bmax[3], svb_stats* out, std::string* err,
@@ -140,10 +148,24 @@ bool build_dag_sharded(const std::vector<int>& devices, const std::vector<svb_ct
 	const int world = (int)devices.size();
 	if (world < 2 || ctx.size() != devices.size()) { if (err) *err = "build_dag_sharded needs >= 2 devices and one context per device"; return false; }
 	if (step == 0 || step + 1 >= levels) { if (err) *err = "a sharded build needs 0 < step and step + 1 < levels (sub-octrees are the unit of distribution)"; return false; }
+	// A 64-bit tag collision in the level merge is seen by every rank alike (identical records, identical seed): all of them
+	// repeat the build under the next merge seed (include/svb.h: svb_set_merge_seed)
+	for (uint64_t seed = 0;; ++seed) {
+		for (svb_ctx* c : ctx) svb_set_merge_seed(c, seed);
+		bool collided = false;
+		const bool ok = build_once(devices, ctx, tris, ntris, levels, step, bmin, bmax, out, err, msUpload, msExchange, &collided);
+		if (ok || !collided || seed >= 3) return ok;
+	}
+}
+
+static bool build_once(const std::vector<int>& devices, const std::vector<svb_ctx*>& ctx, const float* tris, uint64_t ntris,
+                       unsigned levels, unsigned step, const double bmin[3], const double bmax[3], svb_stats* out, std::string* err,
+                       double* msUpload, double* msExchange, bool* collided) {
+	const int world = (int)devices.size();
 	Shared S;
 	S.world = world;
 	S.comm.resize(world);
-	S.counts.resize(world); S.recBytes.resize(world); S.counters.resize(world); S.error.resize(world);
+	S.counts.resize(world); S.recBytes.resize(world); S.counters.resize(world); S.error.resize(world); S.collision.assign(world, 0);
 	S.msUpload.assign(world, 0); S.msExchange.assign(world, 0);
 	ncclResult_t nr = ncclCommInitAll(S.comm.data(), world, devices.data());
 	if (nr != ncclSuccess) { if (err) *err = std::string("ncclCommInitAll: ") + ncclGetErrorString(nr); return false; }
@@ -158,6 +180,7 @@ bool build_dag_sharded(const std::vector<int>& devices, const std::vector<svb_ct
 	for (int r = 0; r < world; ++r) if (dTris[r]) { cudaSetDevice(devices[r]); svb_set_triangles_device(ctx[r], nullptr, 0); cudaFree(dTris[r]); }
 	if (msUpload) *msUpload = *std::max_element(S.msUpload.begin(), S.msUpload.end());
 	if (msExchange) *msExchange = *std::max_element(S.msExchange.begin(), S.msExchange.end());
+	if (collided) { *collided = true; for (int r = 0; r < world; ++r) if (!S.collision[r]) *collided = false; }
 	for (int r = 0; r < world; ++r)
 		if (!S.error[r].empty()) { if (err) *err = "device " + std::to_string(devices[r]) + ": " + S.error[r]; return false; }
 	return true;

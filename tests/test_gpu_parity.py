@@ -546,6 +546,15 @@ def test_svbuilder_cli_multi_gpu_writes_reference_files(pkg, tmp_path):
         for ext, data in g["files"].items():
             name = f"m_{g['levels']}" + ("-multi.svdag" if ext == "multi_svdag" else "." + ext)
             assert (d / name).read_bytes() == data, f"{g['name']}: {name} differs from the reference's file"
+        if path.stem == "terrain_L7_s3":
+            # the same once more with the tags of every first hash seed truncated: the level merge collides on every rank alike and
+            # all of them repeat the build under the next merge seed (csrc/host/sharded_build.cpp)
+            import os
+            r2 = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=300, env=dict(os.environ, SVB_TEST_WEAK_HASH="6"))
+            assert r2.returncode == 0, r2.stdout[-2000:] + r2.stderr[-2000:]
+            for ext, data in g["files"].items():
+                name = f"m_{g['levels']}" + ("-multi.svdag" if ext == "multi_svdag" else "." + ext)
+                assert (d / name).read_bytes() == data, f"{g['name']}: {name} differs after the merge retry"
 
 
 @pytest.mark.parametrize("mesh,kw,levels,step,cross", [
