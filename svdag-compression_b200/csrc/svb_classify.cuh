@@ -310,6 +310,138 @@ SVB_HD unsigned classify_flat_slow(const uint64_t cd, const int l, const double*
 	return m;
 }
 
+// ---- slow-stream pair of a FLAT triangle at the second-to-last level: the voxels of its children, decided in place
+// (k_slow_leaves, svb_voxelize.cu) instead of emitting the child pairs and classifying them at the last level.
+// Along each axis the 4 x 4 x 4 voxels under the node sit at C + (2i - 3) * kh, i = 2 * (child bit) + (voxel bit),
+// kh = k / 2 the voxel half side, reached by the reference through two more steps of the centre chain
+// (fl(fl(C +- k) +- kh), geom_octree.cpp:222-230).  All 64 voxels are carried in one 64-bit word, bit 8 c + v =
+// voxel v of child c (both indexed X=4, Y=2, Z=1), so that a verdict on a whole slab / column of voxels is one mask.
+//   Box axes: the reference's own 1-D tests (test_triangle_box.cpp:165-174) at those centres, one per slab -- exact.
+//   Unsettled in-plane edge axes: the interval filter of edge_axis(), one level further down -- 16 in-plane voxel
+//   columns per axis instead of 4 child positions, same projections, same 2^-40 margin (the shifts are <= 3 kh < 2 k,
+//   inside the bound M the tolerance is built from).  The test "mn - s > rad" is evaluated as "s < mn - rad": another
+//   rounding of the same order, far inside the margin.
+SVB_HD constexpr uint64_t vox64_children(unsigned bit, bool hi) {   // every voxel of the children whose index has `bit` set / clear
+	uint64_t m = 0;
+	for (unsigned c = 0; c < 8; ++c)
+		if (((c & bit) != 0) == hi) m |= 0xFFull << (8 * c);
+	return m;
+}
+SVB_HD constexpr uint64_t vox64_voxels(unsigned bit, bool hi) {   // in every child, the voxels whose index has `bit` set / clear
+	uint64_t m = 0;
+	for (unsigned v = 0; v < 64; ++v)
+		if (((v & bit) != 0) == hi) m |= 1ull << v;
+	return m;
+}
+SVB_HD constexpr uint64_t vox64_slab(unsigned bit, int i) { return vox64_children(bit, (i >> 1) != 0) & vox64_voxels(bit, (i & 1) != 0); }   // position i = 0..3 along the axis
+
+// box axis a, exactly: clears the slabs of `box` the reference's 1-D test rejects
+template <int a>
+SVB_HD void box_axis_slabs(const double C, const double k, const double kh, const double dmin, const double dmax, uint64_t& box) {
+	constexpr unsigned BIT = 4u >> a;
+	const double cLo = SVB_DADD(C, -k), cHi = SVB_DADD(C, k);   // child centres, then the voxel centres: the next two steps of the chain
+	const double c0 = SVB_DADD(cLo, -kh), c1 = SVB_DADD(cLo, kh), c2 = SVB_DADD(cHi, -kh), c3 = SVB_DADD(cHi, kh);
+	if (SVB_DSUB(dmin, c0) > kh || SVB_DSUB(dmax, c0) < -kh) box &= ~vox64_slab(BIT, 0);
+	if (SVB_DSUB(dmin, c1) > kh || SVB_DSUB(dmax, c1) < -kh) box &= ~vox64_slab(BIT, 1);
+	if (SVB_DSUB(dmin, c2) > kh || SVB_DSUB(dmax, c2) < -kh) box &= ~vox64_slab(BIT, 2);
+	if (SVB_DSUB(dmin, c3) > kh || SVB_DSUB(dmax, c3) < -kh) box &= ~vox64_slab(BIT, 3);
+}
+
+// one in-plane edge axis over the 16 voxel columns: rej / uns get the columns the axis separates / cannot decide
+template <unsigned BITU, unsigned BITW>
+SVB_HD void edge_axis16(double ca, double cb, double viA, double viB, double vjA, double vjB,
+                        double kh, double tol2, uint64_t& rej, uint64_t& uns) {
+	const double pi = fma(ca, viA, cb * viB), pj = fma(ca, vjA, cb * vjB);
+	const bool swap = pj < pi;
+	const double mn = swap ? pj : pi, mx = swap ? pi : pj;
+	const double rad = (fabs(ca) + fabs(cb)) * kh;   // of one voxel
+	const double r2 = rad + rad;
+	// |shift| <= 3 rad for every voxel: all 16 columns overlap on this axis
+	if (mn < -r2 - tol2 && mx > r2 + tol2) return;
+	const double qa = kh * ca, qb = kh * cb, qa3 = 3.0 * qa, qb3 = 3.0 * qb;
+	const double R1 = rad + tol2, R0 = rad - tol2;
+	// column with shift s: separated <=> mn - s > R1 or mx - s < -R1; surely overlapping <=> mn - s < R0 and mx - s > -R0
+	const double tLoRej = mn - R1, tHiRej = mx + R1, tLoAcc = mn - R0, tHiAcc = mx + R0;
+#pragma unroll
+	for (int iu = 0; iu < 4; ++iu) {
+		const double sa = (iu == 0) ? -qa3 : (iu == 1) ? -qa : (iu == 2) ? qa : qa3;
+#pragma unroll
+		for (int iw = 0; iw < 4; ++iw) {
+			const double sb = (iw == 0) ? -qb3 : (iw == 1) ? -qb : (iw == 2) ? qb : qb3;
+			const double sh = sa + sb;
+			const uint64_t col = vox64_slab(BITU, iu) & vox64_slab(BITW, iw);
+			if (sh < tLoRej || sh > tHiRej) rej |= col;
+			else if (!(sh > tLoAcc && sh < tHiAcc)) uns |= col;
+		}
+	}
+}
+
+// Bit 8 c + v of the result = voxel v of child c, for every child c in `m` (the pair's hit mask); fl = the pair's flags
+// AFTER its own classification (edge / box axes settled for the node are settled for every voxel inside it).
+template <bool DIRECT, int A>
+SVB_HD uint64_t slow_leaf_voxels_axis(const uint64_t cd, const int l, const double* __restrict__ tg4, const double kscale, const float* __restrict__ tp,
+                                      const unsigned fl, const unsigned m, unsigned& nUnsure) {
+	constexpr int U = (A == 0) ? 1 : 0, W = (A == 2) ? 1 : 2;
+	constexpr unsigned BITU = 4u >> U, BITW = 4u >> W;
+	constexpr unsigned E0 = 1u << A, E1 = 8u << A, E2 = 64u << A, EALL = E0 | E1 | E2;
+	constexpr unsigned BU = 1u << (FL_BOX + U), BW = 1u << (FL_BOX + W);
+	const double k = tg4[3] * kscale, kh = k * 0.5;
+	const uint64_t path = cd & ((1ull << (3 * l)) - 1);
+	// the hit children
+	uint64_t vox = 0;
+#pragma unroll
+	for (int c = 0; c < 8; ++c)
+		if ((m >> c) & 1u) vox |= 0xFFull << (8 * c);
+	// ---- box axes (flat axis: one coordinate, never settles)
+	{
+		const double CA = DIRECT ? centre_axis_direct(path, l, 2 - A, tg4[A], k) : centre_axis_chain(cd, l, 2 - A, tg4[A], tg4[3]);
+		const double ta = (double)tp[A];
+		box_axis_slabs<A>(CA, k, kh, ta, ta, vox);
+	}
+	const bool needEdges = (fl & EALL) != EALL;
+	if ((fl & (BU | BW)) == (BU | BW) && !needEdges) return vox;
+	const float fu0 = tp[U], fu1 = tp[3 + U], fu2 = tp[6 + U], fw0 = tp[W], fw1 = tp[3 + W], fw2 = tp[6 + W];
+	const double CU = DIRECT ? centre_axis_direct(path, l, 2 - U, tg4[U], k) : centre_axis_chain(cd, l, 2 - U, tg4[U], tg4[3]);
+	const double CW = DIRECT ? centre_axis_direct(path, l, 2 - W, tg4[W], k) : centre_axis_chain(cd, l, 2 - W, tg4[W], tg4[3]);
+	if (!(fl & BU)) box_axis_slabs<U>(CU, k, kh, (double)fminf(fu0, fminf(fu1, fu2)), (double)fmaxf(fu0, fmaxf(fu1, fu2)), vox);
+	if (!(fl & BW)) box_axis_slabs<W>(CW, k, kh, (double)fminf(fw0, fminf(fw1, fw2)), (double)fmaxf(fw0, fmaxf(fw1, fw2)), vox);
+	if (!needEdges || !vox) return vox;
+	// ---- in-plane edge axes (same coefficient / vertex-pair pattern as classify_flat_slow)
+	const double u0 = (double)fu0 - CU, w0 = (double)fw0 - CW;
+	const double u1 = (double)fu1 - CU, w1 = (double)fw1 - CW;
+	const double u2 = (double)fu2 - CU, w2 = (double)fw2 - CW;
+	const double M = fmax(fmax(fmax(fabs(u0), fabs(w0)), fmax(fabs(u1), fabs(w1))), fmax(fabs(u2), fabs(w2))) + (k + k);
+	const double tol2 = M * (M * 9.094947017729282e-13);
+	uint64_t rej = 0, uns = 0;
+	if (!(fl & E0)) edge_axis16<BITU, BITW>(w1 - w0, -(u1 - u0), u0, w0, u2, w2, kh, tol2, rej, uns);
+	if (!(fl & E1)) edge_axis16<BITU, BITW>(w2 - w1, -(u2 - u1), u0, w0, u2, w2, kh, tol2, rej, uns);
+	if (!(fl & E2)) edge_axis16<BITU, BITW>(w0 - w2, -(u0 - u2), u0, w0, u1, w1, kh, tol2, rej, uns);
+	vox &= ~rej;
+	uint64_t ask = uns & vox;
+	if (ask) {   // within the margin: the reference-order predicate at the chain-rounded voxel centres decides
+		const double CA = DIRECT ? centre_axis_direct(path, l, 2 - A, tg4[A], k) : centre_axis_chain(cd, l, 2 - A, tg4[A], tg4[3]);
+		const double Cx = (A == 0) ? CA : CU, Cy = (A == 1) ? CA : ((A == 0) ? CU : CW), Cz = (A == 2) ? CA : CW;
+		vox &= ~ask;
+#pragma unroll 1
+		for (int c = 0; c < 8; ++c) {
+			const unsigned a8 = (unsigned)(ask >> (8 * c)) & 0xFFu;
+			if (!a8) continue;
+			const double ccx = SVB_DADD(Cx, (c & 4) ? k : -k), ccy = SVB_DADD(Cy, (c & 2) ? k : -k), ccz = SVB_DADD(Cz, (c & 1) ? k : -k);
+			vox |= (uint64_t)exact_children(a8, ccx, ccy, ccz, kh, tp) << (8 * c);
+			nUnsure += (unsigned)SVB_POPC(a8);
+		}
+	}
+	return vox;
+}
+// fl must carry a flat bit (FL_FLAT..): the triangle is flat on that axis
+template <bool DIRECT>
+SVB_HD uint64_t slow_leaf_voxels(const uint64_t cd, const int l, const double* __restrict__ tg4, const double kscale, const float* __restrict__ tp,
+                                 const unsigned fl, const unsigned m, unsigned& nUnsure) {
+	if (fl & (1u << (FL_FLAT + 0))) return slow_leaf_voxels_axis<DIRECT, 0>(cd, l, tg4, kscale, tp, fl, m, nUnsure);
+	if (fl & (1u << (FL_FLAT + 1))) return slow_leaf_voxels_axis<DIRECT, 1>(cd, l, tg4, kscale, tp, fl, m, nUnsure);
+	return slow_leaf_voxels_axis<DIRECT, 2>(cd, l, tg4, kscale, tp, fl, m, nUnsure);
+}
+
 // Decides the 8 children of the node with Morton code `cd` (tile-local level l, tile geometry tg4 = {cx,cy,cz,rootSide}) against the
 // triangle tp[0..8].  fl: the pair's settled-axis flags (in: inherited from the parent pair, out: for the child
 // pairs).  nUnsure: children that had to be re-decided by the reference-order predicate.  Returns the hit mask.

@@ -490,6 +490,56 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_flat_leaves2(uint64_t P, c
 	}
 }
 
+// ------------------------------------------------------------------ slow stream of a box mesh, last two levels fused
+// Same idea for the pairs that are still in the slow stream at the second-to-last level when every triangle of the scene
+// is flat (allFlat): the thread that owns the parent pair decides the 4 x 4 x 4 voxels under its node on the spot
+// (slow_leaf_voxels, svb_classify.cuh: box axes exactly, the unsettled in-plane edge axes through the interval filter one
+// level further down, the reference-order predicate for voxels within its margin) and ORs the voxel masks of the hit
+// children into the leaf level.  The last level then has no pair list at all: no emit at the second-to-last level, no
+// classify at the last (SVB_SLOW_LEAVES=0 restores both).
+template <bool DIRECT, int MINB, bool STAR>
+__global__ void __launch_bounds__(VX_THREADS, MINB) k_slow_leaves(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
+                                                               const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit,
+                                                               const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase, const uint32_t* __restrict__ tstar,
+                                                               int lc, double kscaleParent, const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
+                                                               const uint32_t* __restrict__ rootTri, uint8_t* __restrict__ cmask, uint32_t* __restrict__ ctstar,
+                                                               unsigned long long* __restrict__ nExact, int precheck) {
+	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= P) return;
+	unsigned m = hit[p];
+	const unsigned fl = pflags[p];
+	const uint32_t t = ptri[p], n = pnode[p];
+	if (!m) return;
+	const uint64_t cd = code[n];
+	const unsigned nm = mask[n];
+	const uint32_t base = childBase[n];
+	const bool star = STAR && ctstar && tstar[n] == t;
+	const double* tg = reinterpret_cast<const double*>(tiles + (uint32_t)(cd >> (3 * (lc - 1))));
+	const float* tp = tris + 9ull * rootTri[t];
+	unsigned nUnsure = 0;
+	const uint64_t vox = slow_leaf_voxels<DIRECT>(cd, lc - 1, tg, kscaleParent, tp, fl, m, nUnsure);
+	if (nUnsure && nExact) atomicAdd(nExact, (unsigned long long)nUnsure);
+	unsigned* const words = reinterpret_cast<unsigned*>(cmask);
+	uint32_t curWord = 0xFFFFFFFFu;
+	unsigned acc = 0;
+	while (m) {
+		const int c = __ffs(m) - 1;
+		m &= m - 1;
+		const uint32_t child = base + __popc(nm & ((1u << c) - 1));
+		const unsigned mc = (unsigned)(vox >> (8 * c)) & 0xFFu;
+		if ((child >> 2) != curWord) {
+			if (acc && (!precheck || (words[curWord] & acc) != acc)) atomicOr(words + curWord, acc);
+			curWord = child >> 2;
+			acc = 0;
+		}
+		acc |= mc << (8 * (child & 3));
+		if (!ctstar) continue;   // first touches of the leaf nodes are not tracked
+		if (star) ctstar[child] = t;
+		else if (!precheck || ctstar[child] > t) atomicMin(&ctstar[child], t);
+	}
+	if (acc && (!precheck || (words[curWord] & acc) != acc)) atomicOr(words + curWord, acc);
+}
+
 // ------------------------------------------------------------------ emit the child pairs
 // One CTA per tile of parent pairs.  The pair arrays are kept as two streams: [0, nFlat) flat-stream pairs,
 // [slowBase, ...) the others (stable partition: both streams stay sorted by triangle id).  SLOW = false: parents of
@@ -1090,10 +1140,12 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		const uint64_t Nn = h[0], cF = h[1], cS = h[2], cSF = h[3];
 		// second-to-last level: the children of the flat stream are decided in place (k_flat_leaves), not emitted
 		static const bool fuseSlowKids = [] { const char* e = getenv("SVB_FUSE_SLOW"); return e ? e[0] != '0' : false; }();   // measured slower on B200 (850 vs 823 ms): off
-		const bool fuseFlat = (l == Lt - 2) && (fuseSlowKids ? (cF + cSF) != 0 : F != 0) && !getenv("SVB_NO_FUSE");
-		const bool fuseS = fuseFlat && fuseSlowKids;   // also decide the flat children of slow-stream parents in place
+		const bool slowLeaves = [] { const char* e = getenv("SVB_SLOW_LEAVES"); return !(e && e[0] == '0'); }();   // box meshes: the slow stream's last two levels fused as well (k_slow_leaves)
+		const bool fuseAll = (l == Lt - 2) && allFlat && !exactOnly && slowLeaves && !getenv("SVB_NO_FUSE");
+		const bool fuseFlat = (l == Lt - 2) && (fuseAll ? (F + S) != 0 : fuseSlowKids ? (cF + cSF) != 0 : F != 0) && !getenv("SVB_NO_FUSE");
+		const bool fuseS = fuseFlat && fuseSlowKids && !fuseAll;   // also decide the flat children of slow-stream parents in place
 		const uint64_t cFe = fuseFlat ? 0 : cF;
-		const uint64_t Fn = cFe + (fuseS ? 0 : cSF), Fan = (Fn + 15) & ~15ull, Sn = cS - cSF, Pn = Fan + Sn;
+		const uint64_t Fn = fuseAll ? 0 : cFe + (fuseS ? 0 : cSF), Fan = (Fn + 15) & ~15ull, Sn = fuseAll ? 0 : cS - cSF, Pn = Fan + Sn;
 		const int precheckKids = forcePre >= 0 ? forcePre : (10 * (cF + cS) > preRatio10 * Nn ? 1 : 0);
 		{
 			// will this batch fit all the way down?  Surfaces grow ~4x per level; use the observed ratio.
@@ -1155,7 +1207,20 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 #undef SVB_LAUNCH_FL2
 #undef SVB_LAUNCH_FL3
 #undef SVB_FL_ARGS
-			pairsTotal += cF + (fuseS ? cSF : 0);   // decided here instead of as pairs of the last level
+			if (fuseAll && S) {
+#define SVB_SL_ARGS S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, L.code.p, L.mask.p, L.childBase.p, L.tstar.p, l + 1, kscale, d_tiles, d_tris, rootTri, \
+			C.mask.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), (unsigned long long*)d_nExact, precheckKids
+				const unsigned nb = blocks_for(S, VX_THREADS);
+				const int occSL = [] { const char* e = getenv("SVB_VX_OCC_SL"); return e ? atoi(e) : 5; }();   // CTAs/SM: 3 (80 registers), 4 (64), 5 (48), 6 (40); measured on the 16K^3 city: 526.6 / 508.5 / 504.3 ms voxelize
+#define SVB_LAUNCH_SL2(DIR, MB) do { if (starStore) k_slow_leaves<DIR, MB, true><<<nb, VX_THREADS, 0, s>>>(SVB_SL_ARGS); else k_slow_leaves<DIR, MB, false><<<nb, VX_THREADS, 0, s>>>(SVB_SL_ARGS); } while (0)
+#define SVB_LAUNCH_SL(DIR) do { if (occSL >= 6) SVB_LAUNCH_SL2(DIR, 6); else if (occSL == 5) SVB_LAUNCH_SL2(DIR, 5); else if (occSL == 4) SVB_LAUNCH_SL2(DIR, 4); else SVB_LAUNCH_SL2(DIR, 3); } while (0)
+				if (directCentre) SVB_LAUNCH_SL(true); else SVB_LAUNCH_SL(false);
+#undef SVB_LAUNCH_SL
+#undef SVB_LAUNCH_SL2
+#undef SVB_SL_ARGS
+				SVB_KERNEL_CHECK();
+			}
+			pairsTotal += cF + (fuseS ? cSF : 0) + (fuseAll ? cS : 0);   // decided here instead of as pairs of the last level
 		} else if (F) {
 #define SVB_EMIT_ARGS_F(...) F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p, __VA_ARGS__ ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), 0, precheckKids
 			const unsigned nb = blocks_for(F, VX_TILE);
@@ -1173,7 +1238,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 			SVB_KERNEL_CHECK();
 			if (prof) prof->end(pidE, cF, 20.0 * (double)F + (trackKids ? 14.0 : 10.0) * (double)cF);
 		}
-		if (S) {
+		if (S && !fuseAll) {
 #define SVB_EMIT_ARGS_S(...) S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, cFe, Fan, L.mask.p, L.childBase.p, __VA_ARGS__ ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), fuseS ? 1 : 0, precheckKids
 			const unsigned nb = blocks_for(S, VX_TILE);
 			const uint64_t kids = fuseS ? cS - cSF : cS;

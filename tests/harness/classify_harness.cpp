@@ -81,6 +81,32 @@ int harness_run(const float* tris, uint64_t T, const double centre[3], double ro
 					}
 				}
 			}
+			// second-to-last level, flat triangle that stays in the slow stream: the fused kernel k_slow_leaves decides the
+			// voxels of its children with slow_leaf_voxels() (box axes exactly, in-plane edge axes through the filter one
+			// level further down); compare with the predicate on every voxel.  (Pairs that join the flat stream run
+			// through it as well -- the kernel takes every slow-stream parent.)
+			if (l == Lt - 2 && (fl & (7u << FL_FLAT)) && want) {
+				const double tg4[4] = {tg.cx, tg.cy, tg.cz, tg.rootSide};
+				unsigned nu = 0;
+				const uint64_t vox = direct ? slow_leaf_voxels<true>(p.code, l, tg4, kscale, tp, fl, want, nu) : slow_leaf_voxels<false>(p.code, l, tg4, kscale, tp, fl, want, nu);
+				out[3] += nu;
+				for (int c = 0; c < 8; ++c) {
+					if (!((want >> c) & 1)) continue;
+					const unsigned got = (unsigned)(vox >> (8 * c)) & 0xFFu;
+					double ccx = cx + ((c & 4) ? k : -k), ccy = cy + ((c & 2) ? k : -k), ccz = cz + ((c & 1) ? k : -k);
+					const double kh = k * 0.5;
+					unsigned wantv = 0;
+					for (int q = 0; q < 8; ++q) {
+						double vx = ccx + ((q & 4) ? kh : -kh), vy = ccy + ((q & 2) ? kh : -kh), vz = ccz + ((q & 1) ? kh : -kh);
+						if (tri_box_overlap(vx, vy, vz, kh, tp)) wantv |= 1u << q;
+					}
+					out[0]++;
+					if (got != wantv) {
+						if (out[1] == 0) { out[4] = (uint64_t)l + 200; out[5] = p.tri; out[6] = (p.code << 3) | (uint64_t)c; out[7] = got; out[8] = wantv; out[9] = fl; }
+						out[1]++;
+					}
+				}
+			}
 			// descend along the REFERENCE decision so one wrong pair does not hide its subtree
 			for (int c = 0; c < 8; ++c)
 				if ((want >> c) & 1) nxt.push_back(Pair{p.tri, (p.code << 3) | (uint64_t)c, (uint16_t)fl});
