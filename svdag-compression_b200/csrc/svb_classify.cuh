@@ -380,7 +380,7 @@ SVB_HD void edge_axis16(double ca, double cb, double viA, double viB, double vjA
 // AFTER its own classification (edge / box axes settled for the node are settled for every voxel inside it).
 template <bool DIRECT, int A>
 SVB_HD uint64_t slow_leaf_voxels_axis(const uint64_t cd, const int l, const double* __restrict__ tg4, const double kscale, const float* __restrict__ tp,
-                                      const unsigned fl, const unsigned m, unsigned& nUnsure) {
+                                      const unsigned fl, const unsigned m, uint64_t& ask) {
 	constexpr int U = (A == 0) ? 1 : 0, W = (A == 2) ? 1 : 2;
 	constexpr unsigned BITU = 4u >> U, BITW = 4u >> W;
 	constexpr unsigned E0 = 1u << A, E1 = 8u << A, E2 = 64u << A, EALL = E0 | E1 | E2;
@@ -417,29 +417,41 @@ SVB_HD uint64_t slow_leaf_voxels_axis(const uint64_t cd, const int l, const doub
 	if (!(fl & E1)) edge_axis16<BITU, BITW>(w2 - w1, -(u2 - u1), u0, w0, u2, w2, kh, tol2, rej, uns);
 	if (!(fl & E2)) edge_axis16<BITU, BITW>(w0 - w2, -(u0 - u2), u0, w0, u1, w1, kh, tol2, rej, uns);
 	vox &= ~rej;
-	uint64_t ask = uns & vox;
-	if (ask) {   // within the margin: the reference-order predicate at the chain-rounded voxel centres decides
-		const double CA = DIRECT ? centre_axis_direct(path, l, 2 - A, tg4[A], k) : centre_axis_chain(cd, l, 2 - A, tg4[A], tg4[3]);
-		const double Cx = (A == 0) ? CA : CU, Cy = (A == 1) ? CA : ((A == 0) ? CU : CW), Cz = (A == 2) ? CA : CW;
-		vox &= ~ask;
-#pragma unroll 1
-		for (int c = 0; c < 8; ++c) {
-			const unsigned a8 = (unsigned)(ask >> (8 * c)) & 0xFFu;
-			if (!a8) continue;
-			const double ccx = SVB_DADD(Cx, (c & 4) ? k : -k), ccy = SVB_DADD(Cy, (c & 2) ? k : -k), ccz = SVB_DADD(Cz, (c & 1) ? k : -k);
-			vox |= (uint64_t)exact_children(a8, ccx, ccy, ccz, kh, tp) << (8 * c);
-			nUnsure += (unsigned)SVB_POPC(a8);
-		}
-	}
-	return vox;
+	ask = uns & vox;   // within the margin: slow_leaf_exact() decides (the caller calls it: rare, kept out of this function)
+	return vox & ~ask;
 }
-// fl must carry a flat bit (FL_FLAT..): the triangle is flat on that axis
+// fl must carry a flat bit (FL_FLAT..): the triangle is flat on that axis.  ask: the voxels the filter could not decide
+// (cleared in the result); the caller hands them to slow_leaf_exact().
 template <bool DIRECT>
 SVB_HD uint64_t slow_leaf_voxels(const uint64_t cd, const int l, const double* __restrict__ tg4, const double kscale, const float* __restrict__ tp,
-                                 const unsigned fl, const unsigned m, unsigned& nUnsure) {
-	if (fl & (1u << (FL_FLAT + 0))) return slow_leaf_voxels_axis<DIRECT, 0>(cd, l, tg4, kscale, tp, fl, m, nUnsure);
-	if (fl & (1u << (FL_FLAT + 1))) return slow_leaf_voxels_axis<DIRECT, 1>(cd, l, tg4, kscale, tp, fl, m, nUnsure);
-	return slow_leaf_voxels_axis<DIRECT, 2>(cd, l, tg4, kscale, tp, fl, m, nUnsure);
+                                 const unsigned fl, const unsigned m, uint64_t& ask) {
+	ask = 0;
+	if (fl & (1u << (FL_FLAT + 0))) return slow_leaf_voxels_axis<DIRECT, 0>(cd, l, tg4, kscale, tp, fl, m, ask);
+	if (fl & (1u << (FL_FLAT + 1))) return slow_leaf_voxels_axis<DIRECT, 1>(cd, l, tg4, kscale, tp, fl, m, ask);
+	return slow_leaf_voxels_axis<DIRECT, 2>(cd, l, tg4, kscale, tp, fl, m, ask);
+}
+// The reference-order predicate (tri_box_overlap) on the voxels in `ask`, at the chain-rounded voxel centres
+// fl(fl(C +- k) +- kh); returns the ones that overlap.  Out of line and self-contained (recomputes the node centre).
+template <bool DIRECT>
+SVB_HD_NOINLINE uint64_t slow_leaf_exact(const uint64_t ask, const uint64_t cd, const int l, const double* __restrict__ tg4, const double kscale, const float* __restrict__ tp) {
+	const double k = tg4[3] * kscale, kh = k * 0.5;
+	const uint64_t path = cd & ((1ull << (3 * l)) - 1);
+	const double Cx = DIRECT ? centre_axis_direct(path, l, 2, tg4[0], k) : centre_axis_chain(cd, l, 2, tg4[0], tg4[3]);
+	const double Cy = DIRECT ? centre_axis_direct(path, l, 1, tg4[1], k) : centre_axis_chain(cd, l, 1, tg4[1], tg4[3]);
+	const double Cz = DIRECT ? centre_axis_direct(path, l, 0, tg4[2], k) : centre_axis_chain(cd, l, 0, tg4[2], tg4[3]);
+	float tf[9];
+#pragma unroll
+	for (int i = 0; i < 9; ++i) tf[i] = tp[i];
+	uint64_t res = 0, rest = ask;
+	while (rest) {
+		const int b = SVB_FFSLL(rest) - 1;   // bit 8 c + v
+		rest &= rest - 1;
+		const int c = b >> 3, v = b & 7;
+		const double ccx = SVB_DADD(Cx, (c & 4) ? k : -k), ccy = SVB_DADD(Cy, (c & 2) ? k : -k), ccz = SVB_DADD(Cz, (c & 1) ? k : -k);
+		const double vx = SVB_DADD(ccx, (v & 4) ? kh : -kh), vy = SVB_DADD(ccy, (v & 2) ? kh : -kh), vz = SVB_DADD(ccz, (v & 1) ? kh : -kh);
+		if (tri_box_overlap(vx, vy, vz, kh, tf)) res |= 1ull << b;
+	}
+	return res;
 }
 
 // Decides the 8 children of the node with Morton code `cd` (tile-local level l, tile geometry tg4 = {cx,cy,cz,rootSide}) against the

@@ -31,6 +31,7 @@
 #define SVB_DMUL(a, b) __dmul_rn((a), (b))
 #define SVB_FMA(a, b, c) __fma_rn((a), (b), (c))
 #define SVB_FFS(x) __ffs(x)
+#define SVB_FFSLL(x) __ffsll((long long)(x))
 #define SVB_POPC(x) __popc(x)
 #elif defined(SVB_HOST_STRICT_OPS)
 // host pass of the SECOND test harness, built with -ffp-contract=fast -mfma so that every plain a * b + c of the interval
@@ -47,6 +48,7 @@ __attribute__((noinline)) inline double mul(double a, double b) { return a * b; 
 #define SVB_DMUL(a, b) ::svb::hostops::mul((double)(a), (double)(b))
 #define SVB_FMA(a, b, c) std::fma((double)(a), (double)(b), (double)(c))
 #define SVB_FFS(x) __builtin_ffs((int)(x))
+#define SVB_FFSLL(x) __builtin_ffsll((long long)(x))
 #define SVB_POPC(x) __builtin_popcount((unsigned)(x))
 #else   // host pass: plain IEEE operations; the translation unit must be built with -ffp-contract=off
 #define SVB_DADD(a, b) ((double)(a) + (double)(b))
@@ -54,6 +56,7 @@ __attribute__((noinline)) inline double mul(double a, double b) { return a * b; 
 #define SVB_DMUL(a, b) ((double)(a) * (double)(b))
 #define SVB_FMA(a, b, c) std::fma((double)(a), (double)(b), (double)(c))
 #define SVB_FFS(x) __builtin_ffs((int)(x))
+#define SVB_FFSLL(x) __builtin_ffsll((long long)(x))
 #define SVB_POPC(x) __builtin_popcount((unsigned)(x))
 #endif
 

@@ -516,9 +516,12 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_slow_leaves(uint64_t P, co
 	const bool star = STAR && ctstar && tstar[n] == t;
 	const double* tg = reinterpret_cast<const double*>(tiles + (uint32_t)(cd >> (3 * (lc - 1))));
 	const float* tp = tris + 9ull * rootTri[t];
-	unsigned nUnsure = 0;
-	const uint64_t vox = slow_leaf_voxels<DIRECT>(cd, lc - 1, tg, kscaleParent, tp, fl, m, nUnsure);
-	if (nUnsure && nExact) atomicAdd(nExact, (unsigned long long)nUnsure);
+	uint64_t ask;
+	uint64_t vox = slow_leaf_voxels<DIRECT>(cd, lc - 1, tg, kscaleParent, tp, fl, m, ask);
+	if (ask) {
+		vox |= slow_leaf_exact<DIRECT>(ask, cd, lc - 1, tg, kscaleParent, tp);
+		if (nExact) atomicAdd(nExact, (unsigned long long)__popcll(ask));
+	}
 	unsigned* const words = reinterpret_cast<unsigned*>(cmask);
 	uint32_t curWord = 0xFFFFFFFFu;
 	unsigned acc = 0;

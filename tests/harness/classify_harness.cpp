@@ -87,9 +87,10 @@ int harness_run(const float* tris, uint64_t T, const double centre[3], double ro
 			// through it as well -- the kernel takes every slow-stream parent.)
 			if (l == Lt - 2 && (fl & (7u << FL_FLAT)) && want) {
 				const double tg4[4] = {tg.cx, tg.cy, tg.cz, tg.rootSide};
-				unsigned nu = 0;
-				const uint64_t vox = direct ? slow_leaf_voxels<true>(p.code, l, tg4, kscale, tp, fl, want, nu) : slow_leaf_voxels<false>(p.code, l, tg4, kscale, tp, fl, want, nu);
-				out[3] += nu;
+				uint64_t ask = 0;
+				uint64_t vox = direct ? slow_leaf_voxels<true>(p.code, l, tg4, kscale, tp, fl, want, ask) : slow_leaf_voxels<false>(p.code, l, tg4, kscale, tp, fl, want, ask);
+				if (ask) vox |= direct ? slow_leaf_exact<true>(ask, p.code, l, tg4, kscale, tp) : slow_leaf_exact<false>(ask, p.code, l, tg4, kscale, tp);
+				out[3] += (uint64_t)__builtin_popcountll(ask);
 				for (int c = 0; c < 8; ++c) {
 					if (!((want >> c) & 1)) continue;
 					const unsigned got = (unsigned)(vox >> (8 * c)) & 0xFFu;

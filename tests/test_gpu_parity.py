@@ -380,7 +380,7 @@ def test_svbuilder_cli_from_svdag_input(pkg, tmp_path):
 LEGACY = {  # every environment toggle that selects the straightforward variant of a kernel / pass
     "SVB_EMIT_PIPE": "0", "SVB_CHILDREN_PIPE": "0", "SVB_STAR_STORE": "0", "SVB_K64_PERM": "0", "SVB_K64_ONEPASS": "0",
     "SVB_DEDUP_LAZY": "0", "SVB_LEAF_LAZY": "0", "SVB_INNER_MARKED": "0", "SVB_LEAF_NOTSTAR": "0", "SVB_SCAN_WIDE": "0",
-    "SVB_K64_NOTSTAR": "0", "SVB_ROOTS_ONCE": "0", "SVB_EMIT_WARP": "0", "SVB_SCAN_MULTI": "0", "SVB_FAST_ILP": "1", "SVB_LEAVES_ILP": "1", "SVB_CHILDREN_TMA": "0",
+    "SVB_K64_NOTSTAR": "0", "SVB_ROOTS_ONCE": "0", "SVB_EMIT_WARP": "0", "SVB_SCAN_MULTI": "0", "SVB_FAST_ILP": "1", "SVB_LEAVES_ILP": "1", "SVB_CHILDREN_TMA": "0", "SVB_SLOW_LEAVES": "0",
 }
 
 
@@ -429,6 +429,37 @@ def test_each_toggle_alone(pkg, meshgen, toggle, monkeypatch):
     _assert_levels_equal(b.levels_host(), want_levels, f"DAG with {toggle}={LEGACY[toggle]}")
     b.to_sdag()
     assert pkg.encoders.encode(b, "ssvdag") == want
+
+
+@pytest.mark.parametrize("centre", ["auto", "chain"])
+@pytest.mark.parametrize("occ", ["3", "4", "5", "6"])
+def test_slow_stream_fused_leaves_every_variant(pkg, orc, meshgen, occ, centre, monkeypatch, capfd):
+    """Box mesh: the slow stream's last two levels are decided in place (k_slow_leaves): every instantiation (CTAs/SM x
+    closed-form / replayed centres) equals the oracle on a scaled, shifted city whose hypotenuses produce voxels inside
+    the filter's margin (the reference-order predicate decides those: nExactTests > 0), and the last level really has
+    no pair list."""
+    tris = _affine(meshgen.make_mesh("city", lots=8), (3.7, 2.9, 5.3), (11.3, -5.1, 2.9))
+    o = orc.OracleOctree(tris)
+    o.build(9, 2)
+    monkeypatch.setenv("SVB_VX_OCC_SL", occ)
+    monkeypatch.setenv("SVB_VX_STATS", "1")
+    if centre == "chain":
+        monkeypatch.setenv("SVB_CENTRE", "chain")
+    t = pkg.GeomOctree(tris)
+    st = t.build(9, 2)
+    err = capfd.readouterr().err
+    import re
+    lv = [re.search(r"level (\d+)/(\d+) nodes \d+ flat pairs (\d+) slow pairs (\d+)", ln) for ln in err.splitlines() if ln.startswith("[vx-stats] tiles")]
+    last = [m for m in lv if m and m.group(1) == m.group(2)]
+    assert last and all(m.group(3) == "0" and m.group(4) == "0" for m in last), err[-600:]
+    for k in ("nTotalVoxels", "nNodesSVO", "nNodesDAG"):
+        assert st[k] == o.stat(k), k
+    assert st["nExactTests"] > 0
+    _assert_levels_equal(t.levels_host(), _oracle_levels(o), f"DAG (k_slow_leaves, {occ} CTAs/SM, centres {centre})")
+    monkeypatch.setenv("SVB_SLOW_LEAVES", "0")
+    u = pkg.GeomOctree(tris)
+    su = u.build(9, 2)
+    assert su["nPairsTotal"] == st["nPairsTotal"]   # the same pairs, decided elsewhere
 
 
 def test_leaf_level_without_first_touches_is_exercised(pkg, orc, meshgen, monkeypatch, capfd):
