@@ -413,9 +413,18 @@ SVB_HD uint64_t slow_leaf_voxels_axis(const uint64_t cd, const int l, const doub
 	const double M = fmax(fmax(fmax(fabs(u0), fabs(w0)), fmax(fabs(u1), fabs(w1))), fmax(fabs(u2), fabs(w2))) + (k + k);
 	const double tol2 = M * (M * 9.094947017729282e-13);
 	uint64_t rej = 0, uns = 0;
-	if (!(fl & E0)) edge_axis16<BITU, BITW>(w1 - w0, -(u1 - u0), u0, w0, u2, w2, kh, tol2, rej, uns);
-	if (!(fl & E1)) edge_axis16<BITU, BITW>(w2 - w1, -(u2 - u1), u0, w0, u2, w2, kh, tol2, rej, uns);
-	if (!(fl & E2)) edge_axis16<BITU, BITW>(w0 - w2, -(u0 - u2), u0, w0, u1, w1, kh, tol2, rej, uns);
+	// one copy of the 16-column code for the three edges (a box mesh leaves one edge axis -- the hypotenuse's -- unsettled,
+	// which of the three depends on the triangle: lanes with different edges share the instructions, and the kernel stays
+	// small enough for the instruction cache)
+#pragma unroll 1
+	for (unsigned rem = ~fl & EALL; rem; rem &= rem - 1) {
+		const unsigned e = rem & (0u - rem);
+		// edge 0: v0 -> v1, projected pair (v0, v2); edge 1: v1 -> v2, (v0, v2); edge 2: v2 -> v0, (v0, v1)
+		const double ca = (e == E0) ? w1 - w0 : (e == E1) ? w2 - w1 : w0 - w2;
+		const double cb = (e == E0) ? -(u1 - u0) : (e == E1) ? -(u2 - u1) : -(u0 - u2);
+		const double vjU = (e == E2) ? u1 : u2, vjW = (e == E2) ? w1 : w2;
+		edge_axis16<BITU, BITW>(ca, cb, u0, w0, vjU, vjW, kh, tol2, rej, uns);
+	}
 	vox &= ~rej;
 	ask = uns & vox;   // within the margin: slow_leaf_exact() decides (the caller calls it: rare, kept out of this function)
 	return vox & ~ask;
