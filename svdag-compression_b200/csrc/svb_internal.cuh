@@ -266,14 +266,14 @@ uint64_t scan_tile_items();
 void scan_tiles_popc8(cudaStream_t s, Pool& pool, const uint8_t* bytes, uint64_t n, DevBuf<uint64_t>& tileOffs, uint64_t* d_total, DevBuf<uint32_t>* rel = nullptr);
 // A = popcount(hit) of every pair, B = the same restricted to pairs whose flags put their children into the flat stream
 void scan_tiles_pairs(cudaStream_t s, Pool& pool, const uint8_t* hit, const uint16_t* flags, uint64_t n,
-                      DevBuf<uint64_t>& tileOffsA, DevBuf<uint64_t>& tileOffsB, uint64_t* d_totalA, uint64_t* d_totalB, DevBuf<uint32_t>* rel = nullptr);
+                      DevBuf<uint64_t>& tileOffsA, DevBuf<uint64_t>& tileOffsB, uint64_t* d_totalA, uint64_t* d_totalB, DevBuf<uint32_t>* rel = nullptr, int flatTri = 0);
 // The four tile-granular scans of one voxelizer level in one go (three reduce kernels + ONE launch for the four scans of the
 // tile sums): children per node, child pairs of the flat stream, child pairs / flat child pairs of the slow stream.
 // d_tot4[0..3] receive the four totals.
 void scan_level_tiles(cudaStream_t s, Pool& pool, const uint8_t* nodeMask, uint64_t nNodes, const uint8_t* hitF, uint64_t nF,
                       const uint8_t* hitS, const uint16_t* flagsS, uint64_t nS,
                       DevBuf<uint64_t>& nodeOffs, DevBuf<uint64_t>& offF, DevBuf<uint64_t>& offS, DevBuf<uint64_t>& offSF,
-                      DevBuf<uint32_t>* relF, DevBuf<uint32_t>* relS, uint64_t* d_tot4);
+                      DevBuf<uint32_t>* relF, DevBuf<uint32_t>* relS, uint64_t* d_tot4, int flatTri = 0);
 // exclusive scan of uint32 values (in place allowed), total to *d_total
 void scan_u32(cudaStream_t s, Pool& pool, const uint32_t* in, uint64_t n, uint32_t* out, uint64_t* d_total);
 // stable LSD radix sort of (key u64, val u32) pairs on the low `bits` bits of the key.

@@ -199,8 +199,9 @@ static void launch_scan_sums(cudaStream_t s, const uint32_t* sums, uint64_t nb, 
 
 // pair streams: per tile of SCAN_TILE pairs, the number of child pairs (popcount of the hit masks) and the number of
 // those whose flags put them into the flat stream (pair_is_fast, svb_classify.cuh), in one pass
+// (flatTri != 0: the second count is over the pairs of FLAT triangles instead -- the ones k_slow_leaves decides in place)
 __global__ void __launch_bounds__(SCAN_THREADS) k_pair_reduce(const uint8_t* __restrict__ hit, const uint16_t* __restrict__ fl, uint64_t n,
-                                                              uint32_t* __restrict__ sumsA, uint32_t* __restrict__ sumsB, uint32_t* __restrict__ rel) {
+                                                              uint32_t* __restrict__ sumsA, uint32_t* __restrict__ sumsB, uint32_t* __restrict__ rel, int flatTri) {
 	uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
 	uint32_t a = 0, b = 0;
 	if (base + SCAN_ITEMS <= n) {
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_pair_reduce(const uint8_t* __r
 				uint32_t c = __popc(((i < 4 ? w.x : w.y) >> (8 * (i & 3))) & 0xFF);
 				uint32_t g = (fw[i >> 1] >> (16 * (i & 1))) & 0xFFFF;
 				a += c;
-				if (pair_is_fast(g)) b += c;
+				if (flatTri ? (g & (7u << FL_FLAT)) != 0 : pair_is_fast(g)) b += c;
 			}
 		}
 	} else {
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_pair_reduce(const uint8_t* __r
 			if (base + i < n) {
 				uint32_t c = __popc((uint32_t)hit[base + i]);
 				a += c;
-				if (c && pair_is_fast(fl[base + i])) b += c;
+				if (c && (flatTri ? (fl[base + i] & (7u << FL_FLAT)) != 0 : pair_is_fast(fl[base + i]))) b += c;
 			}
 	}
 	uint32_t packed = a | (b << 16);   // a, b <= 8 * SCAN_ITEMS per thread, <= 8 * SCAN_TILE = 16384 per tile: fits 16 bits each
@@ -338,14 +339,14 @@ void scan_tiles_popc8(cudaStream_t s, Pool& pool, const uint8_t* bytes, uint64_t
 }
 
 void scan_tiles_pairs(cudaStream_t s, Pool& pool, const uint8_t* hit, const uint16_t* flags, uint64_t n,
-                      DevBuf<uint64_t>& tileOffsA, DevBuf<uint64_t>& tileOffsB, uint64_t* d_totalA, uint64_t* d_totalB, DevBuf<uint32_t>* rel) {
+                      DevBuf<uint64_t>& tileOffsA, DevBuf<uint64_t>& tileOffsB, uint64_t* d_totalA, uint64_t* d_totalB, DevBuf<uint32_t>* rel, int flatTri) {
 	uint64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
 	tileOffsA.reset(pool, nb ? nb : 1);
 	tileOffsB.reset(pool, nb ? nb : 1);
 	if (rel) rel->reset(pool, nb ? nb * SCAN_THREADS : 1);
 	if (n == 0) { SVB_CUDA(cudaMemsetAsync(d_totalA, 0, 8, s)); SVB_CUDA(cudaMemsetAsync(d_totalB, 0, 8, s)); return; }
 	DevBuf<uint32_t> sumsA(pool, nb), sumsB(pool, nb);
-	k_pair_reduce<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(hit, flags, n, sumsA.p, sumsB.p, rel ? rel->p : nullptr);
+	k_pair_reduce<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(hit, flags, n, sumsA.p, sumsB.p, rel ? rel->p : nullptr, flatTri);
 	SVB_KERNEL_CHECK();
 	launch_scan_sums(s, sumsA.p, nb, tileOffsA.p, d_totalA);
 	SVB_KERNEL_CHECK();
@@ -356,7 +357,7 @@ void scan_tiles_pairs(cudaStream_t s, Pool& pool, const uint8_t* hit, const uint
 void scan_level_tiles(cudaStream_t s, Pool& pool, const uint8_t* nodeMask, uint64_t nNodes, const uint8_t* hitF, uint64_t nF,
                       const uint8_t* hitS, const uint16_t* flagsS, uint64_t nS,
                       DevBuf<uint64_t>& nodeOffs, DevBuf<uint64_t>& offF, DevBuf<uint64_t>& offS, DevBuf<uint64_t>& offSF,
-                      DevBuf<uint32_t>* relF, DevBuf<uint32_t>* relS, uint64_t* d_tot4) {
+                      DevBuf<uint32_t>* relF, DevBuf<uint32_t>* relS, uint64_t* d_tot4, int flatTri) {
 	const uint64_t nbN = (nNodes + SCAN_TILE - 1) / SCAN_TILE, nbF = (nF + SCAN_TILE - 1) / SCAN_TILE, nbS = (nS + SCAN_TILE - 1) / SCAN_TILE;
 	nodeOffs.reset(pool, nbN ? nbN : 1);
 	offF.reset(pool, nbF ? nbF : 1);
@@ -367,7 +368,7 @@ void scan_level_tiles(cudaStream_t s, Pool& pool, const uint8_t* nodeMask, uint6
 	DevBuf<uint32_t> sumsN(pool, nbN ? nbN : 1), sumsF(pool, nbF ? nbF : 1), sumsA(pool, nbS ? nbS : 1), sumsB(pool, nbS ? nbS : 1);
 	if (nbN) { k_scan_reduce<Popc8In><<<(unsigned)nbN, SCAN_THREADS, 0, s>>>(Popc8In{nodeMask}, nNodes, sumsN.p, nullptr); SVB_KERNEL_CHECK(); }
 	if (nbF) { k_scan_reduce<Popc8In><<<(unsigned)nbF, SCAN_THREADS, 0, s>>>(Popc8In{hitF}, nF, sumsF.p, relF ? relF->p : nullptr); SVB_KERNEL_CHECK(); }
-	if (nbS) { k_pair_reduce<<<(unsigned)nbS, SCAN_THREADS, 0, s>>>(hitS, flagsS, nS, sumsA.p, sumsB.p, relS ? relS->p : nullptr); SVB_KERNEL_CHECK(); }
+	if (nbS) { k_pair_reduce<<<(unsigned)nbS, SCAN_THREADS, 0, s>>>(hitS, flagsS, nS, sumsA.p, sumsB.p, relS ? relS->p : nullptr, flatTri); SVB_KERNEL_CHECK(); }
 	ScanJobs4 J;
 	J.sums[0] = sumsN.p; J.nb[0] = nbN; J.offs[0] = nodeOffs.p; J.total[0] = d_tot4 + 0;
 	J.sums[1] = sumsF.p; J.nb[1] = nbF; J.offs[1] = offF.p; J.total[1] = d_tot4 + 1;

@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_slow_leaves(uint64_t P, co
 	unsigned m = hit[p];
 	const unsigned fl = pflags[p];
 	const uint32_t t = ptri[p], n = pnode[p];
-	if (!m) return;
+	if (!m || !(fl & (7u << FL_FLAT))) return;   // (mixed scenes: the pairs of general triangles are emitted and classified at the last level)
 	const uint64_t cd = code[n];
 	const unsigned nm = mask[n];
 	const uint32_t base = childBase[n];
@@ -757,7 +757,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_emit_warp(uint64_t P, cons
 	};
 	auto load_node = [&](PairIn& f) {
 		NodeIn q = {0u, 0u, 0u};
-		if (SLOW && skipFlat && pair_is_fast(f.fl)) f.m = 0;   // decided in place by k_flat_leaves
+		if (SLOW && skipFlat && (skipFlat == 2 ? (f.fl & (7u << FL_FLAT)) != 0 : pair_is_fast(f.fl))) f.m = 0;   // decided in place by k_flat_leaves / (2: every flat triangle) k_slow_leaves
 		if (f.m) { q.nm = mask[f.n]; q.base = childBase[f.n]; if (STAR && ctstar) q.ts = tstar[f.n]; }
 		return q;
 	};
@@ -1131,11 +1131,17 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		DevBuf<uint64_t> nodeOffs, offF, offFB, offS, offSF;
 		DevBuf<uint32_t> relF, relS;   // tile-relative offsets per 8 pairs (k_emit_warp)
 		const bool scanMulti = [] { const char* e = getenv("SVB_SCAN_MULTI"); return !(e && e[0] == '0') && !(getenv("SVB_SCAN_WIDE") && getenv("SVB_SCAN_WIDE")[0] == '0'); }();
-		if (scanMulti) scan_level_tiles(s, pool, L.mask.p, L.n, hit.p, F, hit.p + Fa, pflags.p + Fa, S, nodeOffs, offF, offS, offSF, emitWarp ? &relF : nullptr, emitWarp ? &relS : nullptr, tot.p);
+		// second-to-last level: the children of the flat stream are decided in place (k_flat_leaves), and so are the children of
+		// the slow-stream pairs of flat triangles (k_slow_leaves; all of them in a box mesh, the flat ones in a mixed scene --
+		// there the scans count them apart and the emit drops them)
+		const bool slowLeaves = [] { const char* e = getenv("SVB_SLOW_LEAVES"); return !(e && e[0] == '0'); }() && (l == Lt - 2) && !exactOnly && !getenv("SVB_NO_FUSE");
+		const bool fuseAll = slowLeaves && allFlat;
+		const bool fuseMixed = slowLeaves && !allFlat && emitWarp && S != 0 && [] { const char* e = getenv("SVB_SLOW_LEAVES_MIXED"); return !(e && e[0] == '0'); }();
+		if (scanMulti) scan_level_tiles(s, pool, L.mask.p, L.n, hit.p, F, hit.p + Fa, pflags.p + Fa, S, nodeOffs, offF, offS, offSF, emitWarp ? &relF : nullptr, emitWarp ? &relS : nullptr, tot.p, fuseMixed ? 1 : 0);
 		else {
 			scan_tiles_popc8(s, pool, L.mask.p, L.n, nodeOffs, tot.p + 0);
 			scan_tiles_popc8(s, pool, hit.p, F, offF, tot.p + 1, emitWarp ? &relF : nullptr);
-			scan_tiles_pairs(s, pool, hit.p + Fa, pflags.p + Fa, S, offS, offSF, tot.p + 2, tot.p + 3, emitWarp ? &relS : nullptr);
+			scan_tiles_pairs(s, pool, hit.p + Fa, pflags.p + Fa, S, offS, offSF, tot.p + 2, tot.p + 3, emitWarp ? &relS : nullptr, fuseMixed ? 1 : 0);
 		}
 		uint64_t h[4];
 		SVB_CUDA(cudaMemcpyAsync(h, tot.p, 32, cudaMemcpyDeviceToHost, s));
@@ -1143,12 +1149,11 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		const uint64_t Nn = h[0], cF = h[1], cS = h[2], cSF = h[3];
 		// second-to-last level: the children of the flat stream are decided in place (k_flat_leaves), not emitted
 		static const bool fuseSlowKids = [] { const char* e = getenv("SVB_FUSE_SLOW"); return e ? e[0] != '0' : false; }();   // measured slower on B200 (850 vs 823 ms): off
-		const bool slowLeaves = [] { const char* e = getenv("SVB_SLOW_LEAVES"); return !(e && e[0] == '0'); }();   // box meshes: the slow stream's last two levels fused as well (k_slow_leaves)
-		const bool fuseAll = (l == Lt - 2) && allFlat && !exactOnly && slowLeaves && !getenv("SVB_NO_FUSE");
-		const bool fuseFlat = (l == Lt - 2) && (fuseAll ? (F + S) != 0 : fuseSlowKids ? (cF + cSF) != 0 : F != 0) && !getenv("SVB_NO_FUSE");
-		const bool fuseS = fuseFlat && fuseSlowKids && !fuseAll;   // also decide the flat children of slow-stream parents in place
+		// (fuseMixed: cSF counts the children of flat-triangle pairs -- decided in place -- instead of the flat-stream children)
+		const bool fuseFlat = (l == Lt - 2) && ((fuseAll || fuseMixed) ? (F + S) != 0 : fuseSlowKids ? (cF + cSF) != 0 : F != 0) && !getenv("SVB_NO_FUSE");
+		const bool fuseS = fuseFlat && fuseSlowKids && !fuseAll && !fuseMixed;   // also decide the flat children of slow-stream parents in place
 		const uint64_t cFe = fuseFlat ? 0 : cF;
-		const uint64_t Fn = fuseAll ? 0 : cFe + (fuseS ? 0 : cSF), Fan = (Fn + 15) & ~15ull, Sn = fuseAll ? 0 : cS - cSF, Pn = Fan + Sn;
+		const uint64_t Fn = (fuseAll || fuseMixed) ? 0 : cFe + (fuseS ? 0 : cSF), Fan = (Fn + 15) & ~15ull, Sn = fuseAll ? 0 : cS - cSF, Pn = Fan + Sn;
 		const int precheckKids = forcePre >= 0 ? forcePre : (10 * (cF + cS) > preRatio10 * Nn ? 1 : 0);
 		{
 			// will this batch fit all the way down?  Surfaces grow ~4x per level; use the observed ratio.
@@ -1210,7 +1215,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 #undef SVB_LAUNCH_FL2
 #undef SVB_LAUNCH_FL3
 #undef SVB_FL_ARGS
-			if (fuseAll && S) {
+			if ((fuseAll || fuseMixed) && S) {
 #define SVB_SL_ARGS S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, L.code.p, L.mask.p, L.childBase.p, L.tstar.p, l + 1, kscale, d_tiles, d_tris, rootTri, \
 			C.mask.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), (unsigned long long*)d_nExact, precheckKids
 				const unsigned nb = blocks_for(S, VX_THREADS);
@@ -1223,7 +1228,7 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 #undef SVB_SL_ARGS
 				SVB_KERNEL_CHECK();
 			}
-			pairsTotal += cF + (fuseS ? cSF : 0) + (fuseAll ? cS : 0);   // decided here instead of as pairs of the last level
+			pairsTotal += cF + ((fuseS || fuseMixed) ? cSF : 0) + (fuseAll ? cS : 0);   // decided here instead of as pairs of the last level
 		} else if (F) {
 #define SVB_EMIT_ARGS_F(...) F, ptri.p, pnode.p, pflags.p, hit.p, offF.p, nullptr, 0, 0, L.mask.p, L.childBase.p, __VA_ARGS__ ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), 0, precheckKids
 			const unsigned nb = blocks_for(F, VX_TILE);
@@ -1244,11 +1249,11 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 		if (S && !fuseAll) {
 #define SVB_EMIT_ARGS_S(...) S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, cFe, Fan, L.mask.p, L.childBase.p, __VA_ARGS__ ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), fuseS ? 1 : 0, precheckKids
 			const unsigned nb = blocks_for(S, VX_TILE);
-			const uint64_t kids = fuseS ? cS - cSF : cS;
+			const uint64_t kids = (fuseS || fuseMixed) ? cS - cSF : cS;
 			const int pidE = prof ? prof->begin("emit", (uint32_t)l, S) : -1;
 			if (emitPipe == 0) k_emit<true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S());
-			else if (emitWarp && starStore) k_emit_warp<true, 8, true><<<nb, VX_THREADS, 0, s>>>(S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, relS.p, cFe, Fan, L.mask.p, L.childBase.p, L.tstar.p, ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), fuseS ? 1 : 0, precheckKids);
-			else if (emitWarp) k_emit_warp<true, 8, false><<<nb, VX_THREADS, 0, s>>>(S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, relS.p, cFe, Fan, L.mask.p, L.childBase.p, L.tstar.p, ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), fuseS ? 1 : 0, precheckKids);
+			else if (emitWarp && starStore) k_emit_warp<true, 8, true><<<nb, VX_THREADS, 0, s>>>(S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, relS.p, cFe, Fan, L.mask.p, L.childBase.p, L.tstar.p, ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), fuseMixed ? 2 : fuseS ? 1 : 0, precheckKids);
+			else if (emitWarp) k_emit_warp<true, 8, false><<<nb, VX_THREADS, 0, s>>>(S, ptri.p + Fa, pnode.p + Fa, pflags.p + Fa, hit.p + Fa, offS.p, offSF.p, relS.p, cFe, Fan, L.mask.p, L.childBase.p, L.tstar.p, ntri.p, nnode.p, nflags.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), fuseMixed ? 2 : fuseS ? 1 : 0, precheckKids);
 			else if (!emitRedOut && !starStore) k_emit_pipe<true, 8, false, false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S(L.tstar.p,));
 			else if (!emitRedOut) k_emit_pipe<true, 8, false, true><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S(L.tstar.p,));
 			else if (!starStore) k_emit_pipe<true, 8, true, false><<<nb, VX_THREADS, 0, s>>>(SVB_EMIT_ARGS_S(L.tstar.p,));

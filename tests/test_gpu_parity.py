@@ -380,7 +380,7 @@ def test_svbuilder_cli_from_svdag_input(pkg, tmp_path):
 LEGACY = {  # every environment toggle that selects the straightforward variant of a kernel / pass
     "SVB_EMIT_PIPE": "0", "SVB_CHILDREN_PIPE": "0", "SVB_STAR_STORE": "0", "SVB_K64_PERM": "0", "SVB_K64_ONEPASS": "0",
     "SVB_DEDUP_LAZY": "0", "SVB_LEAF_LAZY": "0", "SVB_INNER_MARKED": "0", "SVB_LEAF_NOTSTAR": "0", "SVB_SCAN_WIDE": "0",
-    "SVB_K64_NOTSTAR": "0", "SVB_ROOTS_ONCE": "0", "SVB_EMIT_WARP": "0", "SVB_SCAN_MULTI": "0", "SVB_FAST_ILP": "1", "SVB_LEAVES_ILP": "1", "SVB_CHILDREN_TMA": "0", "SVB_SLOW_LEAVES": "0",
+    "SVB_K64_NOTSTAR": "0", "SVB_ROOTS_ONCE": "0", "SVB_EMIT_WARP": "0", "SVB_SCAN_MULTI": "0", "SVB_FAST_ILP": "1", "SVB_LEAVES_ILP": "1", "SVB_CHILDREN_TMA": "0", "SVB_SLOW_LEAVES": "0", "SVB_SLOW_LEAVES_MIXED": "0",
 }
 
 
