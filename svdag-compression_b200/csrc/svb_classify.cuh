@@ -347,6 +347,33 @@ SVB_HD void box_axis_slabs(const double C, const double k, const double kh, cons
 	if (SVB_DSUB(dmin, c3) > kh || SVB_DSUB(dmax, c3) < -kh) box &= ~vox64_slab(BIT, 3);
 }
 
+// Flat-stream pair at the second-to-last level in the same 64-bit form (k_flat_leaves): only box axes are left of the
+// predicate.  Byte c of the result is the voxel mask of child c; bytes of children the pair does not hit are meaningless.
+template <bool DIRECT>
+SVB_HD uint64_t flat_leaf_voxels(const uint64_t cd, const int l, const double* __restrict__ tg4, const double kscale, const float* __restrict__ tp, const unsigned fl) {
+	const double rootSide = tg4[3];
+	const double k = rootSide * kscale, kh = k * 0.5;
+	const uint64_t path = cd & ((1ull << (3 * l)) - 1);
+	const unsigned ub = (~fl >> FL_BOX) & 7u;
+	uint64_t vox = ~0ull;
+	if (ub & 1u) {
+		double dmin, dmax;
+		axis_extent(tp, 0, ((fl >> (FL_FLAT + 0)) & 1u) != 0, dmin, dmax);
+		box_axis_slabs<0>(DIRECT ? centre_axis_direct(path, l, 2, tg4[0], k) : centre_axis_chain(cd, l, 2, tg4[0], rootSide), k, kh, dmin, dmax, vox);
+	}
+	if (ub & 2u) {
+		double dmin, dmax;
+		axis_extent(tp, 1, ((fl >> (FL_FLAT + 1)) & 1u) != 0, dmin, dmax);
+		box_axis_slabs<1>(DIRECT ? centre_axis_direct(path, l, 1, tg4[1], k) : centre_axis_chain(cd, l, 1, tg4[1], rootSide), k, kh, dmin, dmax, vox);
+	}
+	if (ub & 4u) {
+		double dmin, dmax;
+		axis_extent(tp, 2, ((fl >> (FL_FLAT + 2)) & 1u) != 0, dmin, dmax);
+		box_axis_slabs<2>(DIRECT ? centre_axis_direct(path, l, 0, tg4[2], k) : centre_axis_chain(cd, l, 0, tg4[2], rootSide), k, kh, dmin, dmax, vox);
+	}
+	return vox;
+}
+
 // one in-plane edge axis over the 16 voxel columns: rej / uns get the columns the axis separates / cannot decide
 template <unsigned BITU, unsigned BITW>
 SVB_HD void edge_axis16(double ca, double cb, double viA, double viB, double vjA, double vjB,

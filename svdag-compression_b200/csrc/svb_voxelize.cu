@@ -490,6 +490,70 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_flat_leaves2(uint64_t P, c
 	}
 }
 
+// ------------------------------------------------------------------ leaf-level output of the fused kernels
+// vox: byte c = voxel mask of child c.  The children of a node are consecutive (rank = the number of lower children in the
+// node's mask nm), so the bytes of the hit children are compacted into one 64-bit value and ORed into the leaf level's mask
+// array as up to three aligned words; first touches of the children where they are tracked (star: this pair carries the
+// node's own first touch, so it is every child's as well: plain store).
+__device__ __forceinline__ void leaf_or_out(const uint64_t vox, unsigned m, const unsigned nm, const uint32_t base, const uint32_t t, const bool star,
+                                            unsigned* __restrict__ words, uint32_t* __restrict__ ctstar, const int precheck) {
+	uint64_t V = 0;
+	while (m) {
+		const int c = __ffs(m) - 1;
+		m &= m - 1;
+		const unsigned r = __popc(nm & ((1u << c) - 1));
+		V |= ((vox >> (8 * c)) & 0xFFull) << (8 * r);
+		if (!ctstar) continue;   // first touches of the leaf nodes are not tracked
+		if (star) ctstar[base + r] = t;
+		else if (!precheck || ctstar[base + r] > t) atomicMin(&ctstar[base + r], t);
+	}
+	const unsigned sh = 8 * (base & 3), lo = (unsigned)V, hi = (unsigned)(V >> 32);
+	const unsigned a0 = lo << sh, a1 = __funnelshift_l(lo, hi, sh), a2 = __funnelshift_l(hi, 0u, sh);
+	unsigned* const w = words + (base >> 2);
+	// (read before the atomic only where many pairs share a node; at the leaf levels -- ~1.4 pairs per node -- the
+	// reduction goes out fire-and-forget)
+	if (a0 && (!precheck || (w[0] & a0) != a0)) atomicOr(w, a0);
+	if (a1 && (!precheck || (w[1] & a1) != a1)) atomicOr(w + 1, a1);
+	if (a2 && (!precheck || (w[2] & a2) != a2)) atomicOr(w + 2, a2);
+}
+
+// k_flat_leaves2 with the voxels of all children in one 64-bit word (flat_leaf_voxels) and the output above (default,
+// SVB_LEAVES_ILP=3): ncu had k_flat_leaves2 issue bound (89 % issue-active), 55 % of its instructions in the per-child loop
+// (the per-axis tables indexed by the child's bits compile to compare / select chains).
+template <bool DIRECT, int MINB, bool STAR>
+__global__ void __launch_bounds__(VX_THREADS, MINB) k_flat_leaves3(uint64_t P, const uint32_t* __restrict__ ptri, const uint32_t* __restrict__ pnode,
+                                                                const uint16_t* __restrict__ pflags, const uint8_t* __restrict__ hit,
+                                                                const uint64_t* __restrict__ code, const uint8_t* __restrict__ mask, const uint32_t* __restrict__ childBase, const uint32_t* __restrict__ tstar,
+                                                                int lc, double kscaleParent, const TileGeom* __restrict__ tiles, const float* __restrict__ tris,
+                                                                const uint32_t* __restrict__ rootTri, uint8_t* __restrict__ cmask, uint32_t* __restrict__ ctstar, int onlyFlatKids, int precheck) {
+	const uint64_t p0 = (uint64_t)blockIdx.x * (2 * VX_THREADS) + threadIdx.x;
+	unsigned m[2], fl[2], nm[2];
+	uint32_t t[2], n[2], base[2], ts[2], tr[2];
+	uint64_t cd[2];
+#pragma unroll
+	for (int j = 0; j < 2; ++j) {
+		const uint64_t p = p0 + (uint64_t)j * VX_THREADS;
+		m[j] = 0; fl[j] = 0; t[j] = 0; n[j] = 0;
+		if (p < P) { m[j] = hit[p]; fl[j] = pflags[p]; t[j] = ptri[p]; n[j] = pnode[p]; }
+		if (onlyFlatKids && !pair_is_fast(fl[j])) m[j] = 0;
+	}
+#pragma unroll
+	for (int j = 0; j < 2; ++j) {
+		cd[j] = 0; nm[j] = 0; base[j] = 0; ts[j] = 0; tr[j] = 0;
+		if (m[j]) {
+			cd[j] = code[n[j]]; nm[j] = mask[n[j]]; base[j] = childBase[n[j]]; tr[j] = rootTri[t[j]];
+			if (STAR && ctstar) ts[j] = tstar[n[j]];
+		}
+	}
+#pragma unroll
+	for (int j = 0; j < 2; ++j) {
+		if (!m[j]) continue;
+		const double* tg = reinterpret_cast<const double*>(tiles + (uint32_t)(cd[j] >> (3 * (lc - 1))));
+		const uint64_t vox = flat_leaf_voxels<DIRECT>(cd[j], lc - 1, tg, kscaleParent, tris + 9ull * tr[j], fl[j]);
+		leaf_or_out(vox, m[j], nm[j], base[j], t[j], STAR && ctstar && ts[j] == t[j], reinterpret_cast<unsigned*>(cmask), ctstar, precheck);
+	}
+}
+
 // ------------------------------------------------------------------ slow stream of a box mesh, last two levels fused
 // Same idea for the pairs that are still in the slow stream at the second-to-last level when every triangle of the scene
 // is flat (allFlat): the thread that owns the parent pair decides the 4 x 4 x 4 voxels under its node on the spot
@@ -522,25 +586,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_slow_leaves(uint64_t P, co
 		vox |= slow_leaf_exact<DIRECT>(ask, cd, lc - 1, tg, kscaleParent, tp);
 		if (nExact) atomicAdd(nExact, (unsigned long long)__popcll(ask));
 	}
-	unsigned* const words = reinterpret_cast<unsigned*>(cmask);
-	uint32_t curWord = 0xFFFFFFFFu;
-	unsigned acc = 0;
-	while (m) {
-		const int c = __ffs(m) - 1;
-		m &= m - 1;
-		const uint32_t child = base + __popc(nm & ((1u << c) - 1));
-		const unsigned mc = (unsigned)(vox >> (8 * c)) & 0xFFu;
-		if ((child >> 2) != curWord) {
-			if (acc && (!precheck || (words[curWord] & acc) != acc)) atomicOr(words + curWord, acc);
-			curWord = child >> 2;
-			acc = 0;
-		}
-		acc |= mc << (8 * (child & 3));
-		if (!ctstar) continue;   // first touches of the leaf nodes are not tracked
-		if (star) ctstar[child] = t;
-		else if (!precheck || ctstar[child] > t) atomicMin(&ctstar[child], t);
-	}
-	if (acc && (!precheck || (words[curWord] & acc) != acc)) atomicOr(words + curWord, acc);
+	leaf_or_out(vox, m, nm, base, t, star, reinterpret_cast<unsigned*>(cmask), ctstar, precheck);
 }
 
 // ------------------------------------------------------------------ emit the child pairs
@@ -1206,8 +1252,9 @@ void voxelize_batch(cudaStream_t s, Pool& pool, const float* d_tris, const TileG
 #define SVB_LAUNCH_FL2(DIR, MB, N, OFF, ONLY) if (starStore) SVB_LAUNCH_FL3(DIR, MB, true, N, OFF, ONLY); else SVB_LAUNCH_FL3(DIR, MB, false, N, OFF, ONLY)
 #define SVB_FL_ARGS(N, OFF, ONLY) N, ptri.p + (OFF), pnode.p + (OFF), pflags.p + (OFF), hit.p + (OFF), \
 			L.code.p, L.mask.p, L.childBase.p, L.tstar.p, l + 1, kscale, d_tiles, d_tris, rootTri, C.mask.p, (trackKids ? C.tstar.p : (uint32_t*)nullptr), ONLY, precheckKids
-			const int leavesIlp = [] { const char* e = getenv("SVB_LEAVES_ILP"); return e ? atoi(e) : 2; }();
-#define SVB_LAUNCH_FL3(DIR, MB, ST, N, OFF, ONLY) do { if (leavesIlp >= 2) k_flat_leaves2<DIR, (MB >= 8 ? 6 : 5), ST><<<blocks_for(N, 2 * VX_THREADS), VX_THREADS, 0, s>>>(SVB_FL_ARGS(N, OFF, ONLY)); \
+			const int leavesIlp = [] { const char* e = getenv("SVB_LEAVES_ILP"); return e ? atoi(e) : 3; }();   // 3: k_flat_leaves3, 2: k_flat_leaves2, 1: k_flat_leaves
+#define SVB_LAUNCH_FL3(DIR, MB, ST, N, OFF, ONLY) do { if (leavesIlp >= 3) k_flat_leaves3<DIR, (MB >= 8 ? 6 : 5), ST><<<blocks_for(N, 2 * VX_THREADS), VX_THREADS, 0, s>>>(SVB_FL_ARGS(N, OFF, ONLY)); \
+			else if (leavesIlp >= 2) k_flat_leaves2<DIR, (MB >= 8 ? 6 : 5), ST><<<blocks_for(N, 2 * VX_THREADS), VX_THREADS, 0, s>>>(SVB_FL_ARGS(N, OFF, ONLY)); \
 			else k_flat_leaves<DIR, MB, ST><<<blocks_for(N, VX_THREADS), VX_THREADS, 0, s>>>(SVB_FL_ARGS(N, OFF, ONLY)); } while (0)
 			if (F) { if (directCentre) SVB_LAUNCH_FL(true, F, 0, 0); else SVB_LAUNCH_FL(false, F, 0, 0); SVB_KERNEL_CHECK(); }
 			if (fuseS && S && cSF) { if (directCentre) SVB_LAUNCH_FL(true, S, Fa, 1); else SVB_LAUNCH_FL(false, S, Fa, 1); SVB_KERNEL_CHECK(); }

@@ -64,9 +64,11 @@ int harness_run(const float* tris, uint64_t T, const double centre[3], double ro
 				const double tg4[4] = {tg.cx, tg.cy, tg.cz, tg.rootSide};
 				unsigned lohi[3][2];
 				if (direct) flat_leaf_masks<true>(p.code, l, tg4, kscale, tp, fl, lohi); else flat_leaf_masks<false>(p.code, l, tg4, kscale, tp, fl, lohi);
+				const uint64_t vox64 = direct ? flat_leaf_voxels<true>(p.code, l, tg4, kscale, tp, fl) : flat_leaf_voxels<false>(p.code, l, tg4, kscale, tp, fl);   // (the kernels' default form)
 				for (int c = 0; c < 8; ++c) {
 					if (!((want >> c) & 1)) continue;
-					const unsigned got = lohi[0][(c >> 2) & 1] & lohi[1][(c >> 1) & 1] & lohi[2][c & 1];
+					unsigned got = lohi[0][(c >> 2) & 1] & lohi[1][(c >> 1) & 1] & lohi[2][c & 1];
+					if (((unsigned)(vox64 >> (8 * c)) & 0xFFu) != got) got = 0x100u | ((unsigned)(vox64 >> (8 * c)) & 0xFFu);   // the two forms disagree: report the 64-bit one, marked
 					double ccx = cx + ((c & 4) ? k : -k), ccy = cy + ((c & 2) ? k : -k), ccz = cz + ((c & 1) ? k : -k);
 					const double kh = k * 0.5;
 					unsigned wantv = 0;
