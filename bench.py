@@ -78,14 +78,19 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, device_index=0):
-        self.dev = device_index
+    def __init__(self, devices=(0,)):
+        self.dev = ",".join(str(d) for d in devices)
         self.rows = []
         self.proc = None
+        self.first = 0
+
+    def mark(self):
+        """The timed region starts here: rows read so far (warm-up) are not counted."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.dev)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", self.dev],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -104,6 +109,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        self.rows = self.rows[self.first:] or self.rows[-1:]     # (a timed region shorter than one polling interval: the last row before it)
         sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
         mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -285,13 +291,22 @@ def main():
 
     # ---- resident-input timing (value)
     oct_.set_triangles_ptr(pinned.data_ptr(), T)
+    # one nvidia-smi poller for the whole job (rank 0, all N GPUs), started BEFORE the warm-up steps: its start-up (NVML
+    # initialisation, hundreds of ms of driver traffic) and N pollers side by side used to land in the first timed steps --
+    # at N = 8 the resident figure came out 7 ms per step above the end-to-end one that ran right after it
+    sampler = ClockSampler(range(world) if world > 1 else (local_rank,))
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step_resident()
-    oct_.set_profiling(2)      # per-launch CUDA-event records accumulate inside the library; they are fetched after the timed region
-    sampler = ClockSampler(local_rank)
+    # CUDA events around every launch of the roofline kernel (the "emit" family) accumulate inside the library and are fetched
+    # after the timed region; the other families are bracketed in ONE extra step after the timed regions (`kernels`,
+    # `roofline_dedup`): ~1400 event records per build between the launches cost the timed figure 4 % (resident 623 ms next to an
+    # end-to-end step of 598 ms on the same box)
+    oct_.set_profiling(3)
     prof, launches = [], 0
     barrier()
-    sampler.start()
+    sampler.mark()
     t0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(args.steps):
@@ -315,6 +330,14 @@ def main():
         barrier()
         elapsed_e2e = time.perf_counter() - t1
         d2h = len(img) + 4 * sum(oct_.level_sizes()[:-1])       # the image + the per-level reference counts of the SSVDAG node order
+
+    # ---- one more resident step with every kernel family bracketed (not timed: the breakdown below)
+    oct_.set_profiling(2)
+    barrier()
+    step_resident()
+    barrier()
+    prof_all = oct_.profile()
+    oct_.set_profiling(False)
 
     per_rank = None
     if world > 1:
@@ -359,10 +382,19 @@ def main():
     #      (profiles/ncu_traffic.json).  The dedup family BASELINE.json's metric names gets its own block, `roofline_dedup`, with
     #      REAL DRAM bytes per node from ncu (not the "effective" figures of round 1).
     peak, peak_src = measured_peak_gbs()
-    fam = {}
-    for r in prof:
-        f = fam.setdefault(r["name"], {"launches": 0, "ms": 0.0, "units": 0, "out": 0, "bytes_survey": 0.0})
-        f["launches"] += 1; f["ms"] += r["ms"]; f["units"] += r["n_in"]; f["out"] += r["n_out"]; f["bytes_survey"] += r["bytes"]
+    def families(records, nsteps, skip=()):   # per-step totals of every kernel family
+        out = {}
+        for r in records:
+            if r["name"] in skip:
+                continue
+            f = out.setdefault(r["name"], {"launches": 0, "ms": 0.0, "units": 0, "out": 0, "bytes_survey": 0.0})
+            f["launches"] += 1; f["ms"] += r["ms"]; f["units"] += r["n_in"]; f["out"] += r["n_out"]; f["bytes_survey"] += r["bytes"]
+        for f in out.values():
+            for k in f:
+                f[k] = f[k] / nsteps
+        return out
+    fam = families(prof, args.steps)                         # the timed region: the roofline kernel
+    fam.update(families(prof_all, 1, skip=tuple(fam)))       # the extra instrumented step: everything else
     emit = fam.get("emit")
     roof = None
     tj_all = {}
@@ -385,7 +417,7 @@ def main():
                 "algorithmic_bytes_per_launch": alg / emit["launches"], "peak_source": peak_src,
                 "bytes_per_unit": "20 B per parent pair (11 B pair + 9 B node fields) + 10 B per child pair (+ 4 B first touch where tracked)",
                 "units_per_launch": {"parent_pairs": emit["units"] / emit["launches"], "child_pairs": emit["out"] / emit["launches"]},
-                "avg_launch_ms": emit["ms"] / emit["launches"], "share_of_step": emit["ms"] / (dev_ms if dev_ms else 1.0),
+                "avg_launch_ms": emit["ms"] / emit["launches"], "share_of_step": emit["ms"] / (dev_ms / args.steps if dev_ms else 1.0),
                 "note": "all launches of the step, the many small upper-level ones included (the deepest launches alone run at 0.65 of the peak, issue bound: profiles/r2h_ncu_emit_dedup_city16k.md)"}
         ch = fam.get("children")
         if ch and ch["ms"] > 0:
@@ -403,11 +435,12 @@ def main():
             continue
         bpn = float(dd.get(key, {}).get("dram_bytes_per_node", 0.0))
         achd = bpn * f["units"] / (f["ms"] * 1e-3) / 1e9
-        roofline_dedup[famname] = {"kernels": label, "nodes_per_step": f["units"] // args.steps, "ms_per_step": f["ms"] / args.steps,
+        roofline_dedup[famname] = {"kernels": label, "nodes_per_step": int(f["units"]), "ms_per_step": f["ms"],
                                    "dram_bytes_per_node": bpn, "achieved": achd, "peak": peak, "unit": "GB/s", "frac": achd / peak,
                                    "source": dd.get(key, {}).get("source")}
     dedup_eff = roofline_dedup or None
-    kernels = {k: {"launches": f["launches"] // args.steps, "ms_per_step": f["ms"] / args.steps, "units_per_step": f["units"] // args.steps}
+    kernels = {k: {"launches": int(f["launches"]), "ms_per_step": f["ms"], "units_per_step": int(f["units"]),
+                   "measured": "timed region" if k == "emit" else "one extra instrumented step"}
                for k, f in sorted(fam.items())}
 
     line = {"metric": METRIC, "value": vox / sec / 1e9, "unit": "Gvoxel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -227,7 +227,8 @@ typedef struct svb_prof_rec {
 	double   ms;           /* CUDA-event duration on the context's stream */
 	double   bytes;        /* algorithmic bytes of this launch group */
 } svb_prof_rec;
-int svb_set_profiling(svb_ctx* ctx, int enabled);   /* 0 off, 1 records of the last build, 2 records accumulate over builds until svb_profile_clear */
+int svb_set_profiling(svb_ctx* ctx, int enabled);   /* 0 off, 1 records of the last build, 2 records accumulate over builds until svb_profile_clear,
+                                                        3 as 2 but only the launches of the "emit" family are bracketed (a timed region that wants one kernel's rate) */
 int svb_profile_clear(svb_ctx* ctx);
 int svb_profile_count(const svb_ctx* ctx);
 int svb_profile_get(const svb_ctx* ctx, int i, svb_prof_rec* out);

@@ -294,7 +294,8 @@ class GeomOctree:
 
     # ---- instrumentation
     def set_profiling(self, on=True):
-        """True / 1: records of the last build; 2: records accumulate over builds (read them once with profile()); False: off."""
+        """True / 1: records of the last build; 2: records accumulate over builds (read them once with profile()); 3: as 2, but only
+        the launches of the "emit" family are bracketed by events; False: off."""
         self._L.svb_set_profiling(self._h, int(on))
 
     def profile(self):

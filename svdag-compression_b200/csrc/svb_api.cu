@@ -55,18 +55,26 @@ __global__ void k_min_u32_rows(uint64_t n, uint32_t rows, const uint32_t* __rest
 	out[i] = m;
 }
 
+static cudaEvent_t prof_event(svb_ctx* c) {
+	if (!c->evPool.empty()) { cudaEvent_t e = c->evPool.back(); c->evPool.pop_back(); return e; }
+	cudaEvent_t e;
+	cudaEventCreate(&e);
+	return e;
+}
+static bool prof_wanted(const svb_ctx* c, const char* name) { return c->profiling && (!c->profEmitOnly || strcmp(name, "emit") == 0); }
+
 struct ProfScope {
 	svb_ctx* c;
 	int idx = -1;
 	ProfScope(svb_ctx* ctx, const char* name, uint32_t level, uint64_t n_in) : c(ctx) {
-		if (!c->profiling) return;
+		if (!prof_wanted(c, name)) return;
 		svb_ctx::PendingProf p;
 		memset(&p.rec, 0, sizeof(p.rec));
 		snprintf(p.rec.name, sizeof(p.rec.name), "%s", name);
 		p.rec.level = level;
 		p.rec.n_in = n_in;
-		cudaEventCreate(&p.e0);
-		cudaEventCreate(&p.e1);
+		p.e0 = prof_event(c);
+		p.e1 = prof_event(c);
 		cudaEventRecord(p.e0, c->stream);
 		c->pending.push_back(p);
 		idx = (int)c->pending.size() - 1;
@@ -84,18 +92,20 @@ struct CtxProfHook : ProfHook {
 	svb_ctx* c;
 	explicit CtxProfHook(svb_ctx* ctx) : c(ctx) {}
 	int begin(const char* name, uint32_t level, uint64_t n_in) override {
+		if (!prof_wanted(c, name)) return -1;
 		svb_ctx::PendingProf p;
 		memset(&p.rec, 0, sizeof(p.rec));
 		snprintf(p.rec.name, sizeof(p.rec.name), "%s", name);
 		p.rec.level = level;
 		p.rec.n_in = n_in;
-		cudaEventCreate(&p.e0);
-		cudaEventCreate(&p.e1);
+		p.e0 = prof_event(c);
+		p.e1 = prof_event(c);
 		cudaEventRecord(p.e0, c->stream);
 		c->pending.push_back(p);
 		return (int)c->pending.size() - 1;
 	}
 	void end(int id, uint64_t n_out, double bytes) override {
+		if (id < 0) return;
 		cudaEventRecord(c->pending[id].e1, c->stream);
 		c->pending[id].closed = true;
 		c->pending[id].rec.n_out = n_out;
@@ -112,8 +122,8 @@ void resolve_profile(svb_ctx* c) {
 			p.rec.ms = ms;
 			c->prof.push_back(p.rec);
 		}
-		cudaEventDestroy(p.e0);
-		cudaEventDestroy(p.e1);
+		c->evPool.push_back(p.e0);
+		c->evPool.push_back(p.e1);
 	}
 	c->pending.clear();
 }
@@ -830,6 +840,8 @@ void svb_destroy(svb_ctx* c) {
 	c->image.release();
 	c->staging.release();
 	c->pool.release_all();
+	for (auto& p : c->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+	for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
 	if (c->ownsStream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -1284,8 +1296,13 @@ uint32_t svb_gray_code(uint32_t a) { return a ^ (a >> 1); }
 int svb_set_profiling(svb_ctx* c, int enabled) {
 	if (!c) return SVB_EINVAL;
 	c->profiling = enabled != 0;
-	c->profAccumulate = enabled == 2;   // 2: keep the records of successive builds (read and cleared by the caller: svb_profile_clear)
+	c->profAccumulate = enabled >= 2;   // 2 / 3: keep the records of successive builds (read and cleared by the caller: svb_profile_clear)
+	c->profEmitOnly = enabled == 3;     // 3: only the "emit" launches are bracketed (bench.py: the roofline kernel inside the timed region)
 	if (!enabled) c->prof.clear();
+	if (enabled >= 2) {                 // the events of a timed region are created here, not between its launches
+		cudaSetDevice(c->device);
+		while (c->evPool.size() < 8192) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) break; c->evPool.push_back(e); }
+	}
 	return SVB_OK;
 }
 int svb_profile_clear(svb_ctx* c) {

@@ -43,6 +43,8 @@ struct svb_ctx {
 	std::vector<uint64_t> svoCounts;
 	// instrumentation
 	bool profiling = false, profAccumulate = false;
+	bool profEmitOnly = false;              // svb_set_profiling(ctx, 3): only the launches of the "emit" family are bracketed
+	std::vector<cudaEvent_t> evPool;        // events of resolved records, reused (cudaEventCreate costs more than the record itself)
 	struct PendingProf { svb_prof_rec rec; cudaEvent_t e0, e1; bool closed = false; };
 	std::vector<PendingProf> pending;
 	std::vector<svb_prof_rec> prof;
