@@ -420,13 +420,21 @@ void run_tiles_split(svb_ctx* c, BuildState& B, const std::vector<uint32_t>& sel
 		const uint32_t div = e ? (uint32_t)atoi(e) : 48u;
 		if (div >= 2 && b >= 4 * div) { plan.insert(plan.begin(), b / div + b / (2 * div)); plan.insert(plan.begin(), b / (2 * div)); }
 	}
+	// A piece that comes out of a weight-based cut is not second-guessed by the voxelizer's own early prediction (nodeCap = 0
+	// switches it off; the hard memory check stays): that prediction clamps the growth per level at 5, so one level further
+	// down it over-estimates the leaf level by ~1.6x and used to cut EVERY piece of the 16K^3 city in two again -- nine aborted
+	// attempts of five levels each (~30 ms of 570) and twice the batches (SVB_TRUST_CUTS=0: as before).
+	const bool trustCuts = [] { const char* e = getenv("SVB_TRUST_CUTS"); return !(e && e[0] == '0'); }();
+	std::vector<char> trusted(plan.size(), 0);
 	while (a < b) {
 		uint32_t e = plan.front();
 		try {
-			run_tile_batch(c, B, B.tiles, sel, a, e, B.grid, B.dGrid.p, B.dSelPos.p, Lt, gbase, budget, nodeCap, nullptr);
+			run_tile_batch(c, B, B.tiles, sel, a, e, B.grid, B.dGrid.p, B.dSelPos.p, Lt, gbase, budget, (trustCuts && trusted.front()) ? 0 : nodeCap, nullptr);
 			a = e;
 			plan.erase(plan.begin());
+			trusted.erase(trusted.begin());
 		} catch (const BatchTooBig& x) {
+			if (getenv("SVB_VX_STATS")) fprintf(stderr, "[vx-stats] batch [%u,%u) cut at level %d (%d levels to go, growth %.2f)\n", a, e, x.level, x.remaining, x.growth);
 			if (e - a <= 1) throw Error(SVB_ENOMEM, "a single sub-octree does not fit the batch budget; use a larger step");
 			std::vector<uint32_t> cuts;
 			if (x.weight.size() == e - a) {
@@ -442,8 +450,11 @@ void run_tiles_split(svb_ctx* c, BuildState& B, const std::vector<uint32_t>& sel
 					if (acc >= per) { cuts.push_back(a + i + 1); acc = 0; }
 				}
 			}
+			const bool byWeight = !cuts.empty();
 			if (cuts.empty()) cuts.push_back(a + (e - a) / 2);
 			plan.insert(plan.begin(), cuts.begin(), cuts.end());
+			trusted.front() = byWeight ? 1 : 0;   // (the piece that ends at e)
+			trusted.insert(trusted.begin(), cuts.size(), byWeight ? 1 : 0);
 		}
 	}
 }
