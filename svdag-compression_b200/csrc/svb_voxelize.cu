@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) k_flat_leaves(uint64_t P, co
 	if (acc && (!precheck || (words[curWord] & acc) != acc)) atomicOr(words + curWord, acc);
 }
 
-// Two parent pairs per thread (default; SVB_LEAVES_ILP=1 selects the kernel above): the pair fields and the node fields of both
+// Two parent pairs per thread (SVB_LEAVES_ILP=2; 1 selects the kernel above, the default is k_flat_leaves3 below): the pair fields and the node fields of both
 // pairs are in flight before the first pair is decided -- the kernel is a chain of dependent gathers (pair -> node ->
 // tile / triangle), and the loads a warp has outstanding decide its rate.
 template <bool DIRECT, int MINB, bool STAR>
@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(VX_THREADS) k_emit(uint64_t P, const uint32_t*
 	}
 }
 
-// Software-pipelined k_emit (default; SVB_EMIT_PIPE=0 selects the kernel above).  k_emit walks its tile in 8 chunks, and
+// Software-pipelined k_emit (round 1's default, now SVB_EMIT_WARP=0; SVB_EMIT_PIPE=0 selects the kernel above).  k_emit walks its tile in 8 chunks, and
 // every chunk used to pay two dependent global round trips in series behind CTA-wide barriers (pair fields, then the
 // node's mask / childBase gathered after the scan), which no other warp of the CTA can hide because all of them wait on
 // the same barriers.  Here the pair fields are fetched two chunks ahead and the node fields one chunk ahead, so that by
