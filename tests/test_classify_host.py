@@ -100,6 +100,45 @@ def test_filter_equals_predicate_full_double_bbox(harness, meshgen):
     assert r["bad"] == 0, r
 
 
+def _oblique_flat_triangles(n, seed, lattice):
+    """Flat triangles whose three in-plane edges are all oblique (a box mesh only ever leaves ONE edge axis unsettled: the
+    hypotenuse's), on every flat axis; vertices on a 1/lattice grid so that edges pass exactly through voxel corners
+    (ties: the reference-order predicate has to decide them) or, lattice = 0, anywhere."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n, 3, 3), np.float32)
+    for i in range(n):
+        a = i % 3
+        u, w = [k for k in range(3) if k != a]
+        while True:
+            if lattice:
+                p = rng.integers(0, lattice + 1, size=(3, 2)).astype(np.float64) / lattice
+            else:
+                p = rng.random((3, 2))
+            e = np.array([p[1] - p[0], p[2] - p[1], p[0] - p[2]])
+            area = abs(e[0][0] * e[1][1] - e[0][1] * e[1][0])
+            if area > 1e-3 and np.all(np.abs(e) > 1e-6):      # not degenerate, no axis-aligned edge
+                break
+        out[i, :, a] = (rng.integers(0, 65) / 64.0) if lattice else rng.random()
+        out[i, :, u] = p[:, 0]
+        out[i, :, w] = p[:, 1]
+    return np.ascontiguousarray(out.reshape(n, 9))
+
+
+@pytest.mark.parametrize("direct", [True, False], ids=["direct", "chain"])
+@pytest.mark.parametrize("lattice", [64, 0], ids=["lattice", "random"])
+def test_flat_triangles_with_three_oblique_edges(harness, lattice, direct):
+    """All three edge axes of a flat triangle unsettled at once: the three-edge loop of slow_leaf_voxels / the three edge
+    blocks of classify_flat_slow, voxel by voxel against the predicate; the lattice variant is full of exact ties."""
+    tris = _oblique_flat_triangles(90, 5 if lattice else 6, lattice)
+    lo, hi = np.zeros(3), np.ones(3)
+    for flat_only in (1, 0):
+        r = _run(harness, tris, lo, hi, 7, direct, flat_only=flat_only)
+        assert r["bad"] == 0, r
+        assert r["pairs"] > 100000
+        if lattice:
+            assert r["exact"] > 0, r
+
+
 def _chain_partial_sums_exact(centre, root_side, levels):
     """Brute force with exact rational arithmetic: is every partial sum c0 + sum(+-k_j) a representable double?"""
     from fractions import Fraction

@@ -462,6 +462,23 @@ def test_slow_stream_fused_leaves_every_variant(pkg, orc, meshgen, occ, centre, 
     assert su["nPairsTotal"] == st["nPairsTotal"]   # the same pairs, decided elsewhere
 
 
+@pytest.mark.parametrize("lattice", [64, 0], ids=["lattice", "random"])
+def test_flat_triangles_with_three_oblique_edges(pkg, orc, lattice):
+    """A box-mesh-like scene (every triangle flat: the FLATONLY kernels, k_slow_leaves) whose triangles have three oblique
+    in-plane edges -- all three edge axes unsettled at once, vertices on a lattice so that edges run through voxel corners."""
+    from test_classify_host import _oblique_flat_triangles
+    tris = _oblique_flat_triangles(90, 5 if lattice else 6, lattice)
+    bbox = (np.zeros(3), np.ones(3))
+    o = orc.OracleOctree(tris)
+    o.build(8, 2, bbox=bbox)
+    t = pkg.GeomOctree(tris)
+    st = t.build(8, 2, bbox=bbox)
+    for k in ("nTotalVoxels", "nNodesSVO", "nNodesDAG"):
+        assert st[k] == o.stat(k), k
+    _assert_levels_equal(t.levels_host(), _oracle_levels(o), "DAG (oblique flat triangles)")
+    assert pkg.encoders.encode(t, "svdag") == o.encode("svdag")
+
+
 def test_leaf_level_without_first_touches_is_exercised(pkg, orc, meshgen, monkeypatch, capfd):
     """A scene whose last batches still bring new voxel masks goes through all three leaf-level routes (tracked first
     touches, none needed, direct query for the nodes with a new mask); SVB_VX_STATS reports the query on stderr
