@@ -164,7 +164,8 @@ def _affine(tris, scale, offset):
     ("sphere", dict(n_lat=32, n_lon=64), 9, 3, "scene"),
     ("city", dict(lots=8), 9, 2, "double"),
     ("terrain", dict(n=48), 9, 1, "double"),
-], ids=["terrain-s0", "city-s2", "sphere-s3", "city-doublebox", "terrain-doublebox"])
+    ("soup", dict(n=400, seed=7), 8, 2, "double"),       # flat and general triangles in one scene, replayed centres (k_slow_leaves<false> next to the pair path)
+], ids=["terrain-s0", "city-s2", "sphere-s3", "city-doublebox", "terrain-doublebox", "soup-doublebox"])
 def test_arbitrary_bbox_matches_oracle(pkg, orc, meshgen, mesh, kw, levels, step, bbox_mode, centre, monkeypatch):
     """Scenes whose bbox is NOT the unit cube: node centres are no longer short dyadic numbers, so the
     reference's centre chain (geom_octree.cpp:222-230) and the float narrowing of sub-octree boxes (:177-184,
