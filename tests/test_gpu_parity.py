@@ -480,6 +480,21 @@ def test_flat_triangles_with_three_oblique_edges(pkg, orc, lattice):
     assert pkg.encoders.encode(t, "svdag") == o.encode("svdag")
 
 
+@pytest.mark.parametrize("levels,step", [(7, 4), (6, 4), (5, 2), (4, 1)], ids=["L7s4", "L6s4", "L5s2", "L4s1"])
+@pytest.mark.parametrize("mesh,kw", [("city", dict(lots=8)), ("soup", dict(n=300, seed=3))], ids=["city", "soup"])
+def test_shallow_sub_octrees(pkg, orc, meshgen, mesh, kw, levels, step):
+    """Sub-octrees of one or two levels: the fused leaf kernels then run on the sub-octree's ROOT pairs (flags still unset when
+    the level starts) or not at all."""
+    tris = meshgen.make_mesh(mesh, **kw)
+    o = orc.OracleOctree(tris)
+    o.build(levels, step)
+    t = pkg.GeomOctree(tris)
+    st = t.build(levels, step)
+    for k in ("nTotalVoxels", "nNodesSVO", "nNodesDAG"):
+        assert st[k] == o.stat(k), k
+    _assert_levels_equal(t.levels_host(), _oracle_levels(o), f"DAG ({mesh}, levels {levels}, step {step})")
+
+
 def test_leaf_level_without_first_touches_is_exercised(pkg, orc, meshgen, monkeypatch, capfd):
     """A scene whose last batches still bring new voxel masks goes through all three leaf-level routes (tracked first
     touches, none needed, direct query for the nodes with a new mask); SVB_VX_STATS reports the query on stderr
